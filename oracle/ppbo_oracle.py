@@ -1,0 +1,324 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (numpy/scipy, FP64) restatement of the PPBO hot path.
+
+This file is the *checker* for the CUDA path in ``ppbo_b200/``.  It is never imported by
+the product (``ppbo_b200/``, ``src/``); only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may use it.
+
+It restates, function by function, what the reference (AaltoPML/PPBO, /root/reference)
+computes on the path  GPModel.update_model -> next_query -> Hsampler.  Python-level loops
+of the reference are vectorised (which makes this port *faster* than the real reference,
+so speed-ups quoted against it are conservative), but the numerical recipe is kept:
+expansion-form distances, SVD round trip + shrinkage, explicit SPD inverses, 200-point
+Gauss-Hermite quadrature for the likelihood, scipy's ``trust-exact`` driver, numpy's
+SVD-factor ``multivariate_normal`` fed from the legacy global RNG in reference call order.
+
+PARITY PIN: the reference ships no tests or golden vectors, so this oracle is
+pinned against the *executed* reference: ``oracle/make_golden.py`` runs the unmodified
+reference (through ``oracle/ref_shim.py``) in the build container and stores its inputs and
+outputs in ``tests/golden/*.npz``; ``tests/test_oracle_vs_golden.py`` checks every function
+here against those files.
+"""
+import numpy as np
+import scipy.linalg
+import scipy.optimize
+from scipy.special import ndtr
+
+SQRT2 = np.sqrt(2.0)
+SHRINKAGE = 1e-6            # GPModel.COVARIANCE_SHRINKAGE, src/gp_model.py:26
+GH_POINTS = 200             # PPBO_settings.n_gausshermite_sample_points, src/ppbo_settings.py:52
+EI_GRID_POINTS = 70         # hard-coded in src/acquisition.py:73,171
+
+
+# --------------------------------------------------------------------------- kernels
+def sqdist(X1, X2):
+    """src/kernels.py:3-11 -- |x|^2 + |y|^2 - 2 x.y, clipped at 0."""
+    n1 = np.einsum("ij,ij->i", X1, X1)
+    n2 = np.einsum("ij,ij->i", X2, X2)
+    return np.maximum(n1[:, None] + n2[None, :] - 2.0 * (X1 @ X2.T), 0.0)
+
+
+def se_kernel(X1, X2, theta):
+    """src/kernels.py:19-25 -- isotropic squared exponential, theta=(sigma, l, sigma_f)."""
+    return theta[2] ** 2 * np.exp(-0.5 * sqdist(X1, X2) / theta[1] ** 2)
+
+
+def rq_kernel(X1, X2, theta, alpha=2):
+    """src/kernels.py:27-34 -- rational quadratic with alpha=2."""
+    return theta[2] ** 2 * (1.0 + sqdist(X1, X2) / (2 * alpha * theta[1] ** 2)) ** (-alpha)
+
+
+def camphor_copper_kernel(X1, X2, theta):
+    """src/kernels.py:36-53 -- periodic (period 1) on dims 0,1,3,4,5; SE with l+0.05 on dim 2."""
+    l, sf = theta[1], theta[2]
+    K = np.full((X1.shape[0], X2.shape[0]), sf ** 2)
+    for d in range(6):
+        r = np.abs(X1[:, d][:, None] - X2[:, d][None, :])
+        if d == 2:
+            K = K * np.exp(-0.5 * r ** 2 / (l + 0.05) ** 2)
+        else:
+            K = K * np.exp(-2.0 * np.sin(np.pi * r) ** 2 / l ** 2)
+    return K
+
+
+KERNELS = {"SE_kernel": se_kernel, "RQ_kernel": rq_kernel, "camphor_copper_kernel": camphor_copper_kernel}
+
+
+# --------------------------------------------------------------------------- linear algebra helpers
+def regularize_covariance(K, shrinkage=SHRINKAGE, jitter=1e-7, svd_roundtrip=True):
+    """src/misc.py:71-88 -- negative diagonal -> jitter; SVD round trip; sklearn shrunk_covariance
+    == (1-s) K + s tr(K)/n I.  ``svd_roundtrip=False`` gives the closed form the CUDA path fuses."""
+    K = np.array(K, dtype=float, copy=True)
+    dg = np.diag(K).copy()
+    dg[dg < 0] = jitter
+    np.fill_diagonal(K, dg)
+    if svd_roundtrip:
+        u, s, vh = np.linalg.svd(K, full_matrices=False)
+        K = np.matmul(np.matmul(u, np.diag(s)), vh)
+    n = K.shape[0]
+    mu = np.trace(K) / n
+    K = (1.0 - shrinkage) * K
+    K.flat[:: n + 1] += shrinkage * mu
+    return K
+
+
+def pd_inverse(M):
+    """src/misc.py:96-100 -- solve(M, I) with the SPD (dposv) driver."""
+    return scipy.linalg.solve(M, np.eye(M.shape[0]), assume_a="pos", overwrite_b=True)
+
+
+def var2_normal_pdf(x):
+    """src/misc.py:134-135 -- density of N(0, 2)."""
+    return np.exp(-0.25 * np.square(x)) / np.sqrt(4.0 * np.pi)
+
+
+_GH_CACHE = {}
+
+
+def _gauss_hermite(n):
+    if n not in _GH_CACHE:
+        _GH_CACHE[n] = np.polynomial.hermite.hermgauss(n)
+    return _GH_CACHE[n]
+
+
+# --------------------------------------------------------------------------- likelihood terms
+def deltas(f, Q, m, sigma):
+    """Delta_qj = (f[pseudo j of set q] - f[winner of set q]) / sigma, shape (Q, m).
+    Row layout: set q occupies rows q(m+1) .. q(m+1)+m, winner first (src/feedback_processing.py:121-123)."""
+    F = np.asarray(f, dtype=float).reshape(Q, m + 1)
+    return (F[:, 1:] - F[:, :1]) / sigma
+
+
+def sum_phi(f, Q, m, sigma, order, quadrature=True):
+    """src/gp_model.py:176-218 -- per comparison set: order 0: sum_j Phi~(Delta_j) (Gauss-Hermite 200,
+    == Phi(Delta/sqrt2)); order 1: sum_j phi~(Delta_j); order 2: sum_j -Delta_j phi~(Delta_j)/2."""
+    Dl = deltas(f, Q, m, sigma)
+    if order == 0:
+        if quadrature:
+            t, w = _gauss_hermite(GH_POINTS)
+            vals = ndtr(Dl[..., None] - SQRT2 * t) @ w / np.sqrt(np.pi)
+        else:
+            vals = ndtr(Dl / SQRT2)
+        return vals.sum(axis=1)
+    if order == 1:
+        return var2_normal_pdf(Dl).sum(axis=1)
+    if order == 2:
+        return (-0.5 * Dl * var2_normal_pdf(Dl)).sum(axis=1)
+    raise ValueError(order)
+
+
+def T_value(f, Sigma_inv, Q, m, sigma, quadrature=True):
+    """src/gp_model.py:221-226."""
+    f = np.asarray(f, dtype=float).ravel()
+    return -0.5 * f @ Sigma_inv @ f - sum_phi(f, Q, m, sigma, 0, quadrature).sum() / m
+
+
+def lik_beta(f, Q, m, sigma):
+    """Likelihood part of the gradient, src/gp_model.py:234-238."""
+    ph = var2_normal_pdf(deltas(f, Q, m, sigma)) / (sigma * m)
+    beta = np.empty((Q, m + 1))
+    beta[:, 0] = ph.sum(axis=1)
+    beta[:, 1:] = -ph
+    return beta.ravel()
+
+
+def T_grad(f, Sigma_inv, Q, m, sigma):
+    """src/gp_model.py:228-240."""
+    f = np.asarray(f, dtype=float).ravel()
+    return -Sigma_inv @ f + lik_beta(f, Q, m, sigma)
+
+
+def arrow_coeffs(f, Q, m, sigma):
+    """a_qj = -Delta phi~(Delta) / (2 m sigma^2): W = -Lambda = B diag(a) B^T."""
+    Dl = deltas(f, Q, m, sigma)
+    return -0.5 * Dl * var2_normal_pdf(Dl) / (m * sigma ** 2)
+
+
+def create_Lambda(f, Q, m, sigma):
+    """src/gp_model.py:249-274 -- dense N x N star/arrow blocks."""
+    a = arrow_coeffs(f, Q, m, sigma)
+    N = Q * (m + 1)
+    Lam = np.zeros((N, N))
+    for q in range(Q):
+        i = q * (m + 1)
+        js = np.arange(i + 1, i + m + 1)
+        Lam[js, js] = -a[q]
+        Lam[i, i] = -a[q].sum()
+        Lam[i, js] = a[q]
+        Lam[js, i] = a[q]
+    return Lam
+
+
+def T_hessian(f, Sigma_inv, Q, m, sigma):
+    """src/gp_model.py:242-247."""
+    return -Sigma_inv + create_Lambda(f, Q, m, sigma)
+
+
+# --------------------------------------------------------------------------- Laplace / MAP
+def fmap_trust_exact(Sigma_inv, Q, m, sigma, f_initial, gtol=None):
+    """src/gp_model.py:382-384 -- scipy trust-exact on -T with the dense Hessian (reference default gtol 1e-4)."""
+    opts = {} if gtol is None else {"gtol": gtol}
+    res = scipy.optimize.minimize(lambda f: -T_value(f, Sigma_inv, Q, m, sigma),
+                                  np.asarray(f_initial, dtype=float).ravel(), method="trust-exact",
+                                  jac=lambda f: -T_grad(f, Sigma_inv, Q, m, sigma),
+                                  hess=lambda f: -T_hessian(f, Sigma_inv, Q, m, sigma), options=opts)
+    return res.x, res
+
+
+def fmap_tight(Sigma, Q, m, sigma, f_start, iters=60, tol=1e-13):
+    """Tight stationary point of T near ``f_start``: Newton on the fixed point f = Sigma beta(f),
+    never forming Sigma^{-1} (cond(Sigma) ~ 1e7+ makes the reference's own stopping point only
+    ~1e-6 accurate).  Used as the 1e-6 yard-stick for the Laplace mode."""
+    f = np.asarray(f_start, dtype=float).ravel().copy()
+    N = f.size
+    I = np.eye(N)
+    for _ in range(iters):
+        W = -create_Lambda(f, Q, m, sigma)
+        b = W @ f + lik_beta(f, Q, m, sigma)
+        f_new = Sigma @ np.linalg.solve(I + W @ Sigma, b)
+        step = np.abs(f_new - f).max()
+        f = f_new
+        if step <= tol * max(1.0, np.abs(f).max()):
+            break
+    return f
+
+
+def posterior_covariance(Sigma_inv, fMAP, Q, m, sigma):
+    """src/gp_model.py:111-117."""
+    Lam = create_Lambda(fMAP, Q, m, sigma)
+    Pinv = Sigma_inv - Lam
+    return Lam, Pinv, pd_inverse(Pinv)
+
+
+# --------------------------------------------------------------------------- prediction
+def mu_Sigma_pred(X, Xp, theta, kernel, Sigma_inv, fMAP, post_cov, svd_roundtrip=True):
+    """src/gp_model.py:441-452 (same operation order as the reference)."""
+    k = kernel(X, Xp, theta)
+    mu = k.T.dot(Sigma_inv).dot(fMAP)
+    Kss = regularize_covariance(kernel(Xp, Xp, theta), SHRINKAGE, svd_roundtrip=svd_roundtrip)
+    A = Sigma_inv - Sigma_inv.dot(post_cov).dot(Sigma_inv)
+    return mu, Kss - k.T.dot(A).dot(k)
+
+
+def mu_pred(X, x, theta, kernel, Sigma_inv, fMAP):
+    """src/gp_model.py:454-458."""
+    k = kernel(X, np.asarray(x, dtype=float).reshape(1, -1), theta)
+    return float((k.T @ Sigma_inv @ fMAP)[0])
+
+
+# --------------------------------------------------------------------------- acquisition
+def equispaced_alpha(alpha_min, alpha_max, P, noise=0.01):
+    """src/feedback_processing.py:66-74 -- jittered linspace (consumes the global legacy RNG)."""
+    eps_b = (alpha_max - alpha_min) * (noise / 2)
+    eps_n = abs(alpha_max - alpha_min) * noise
+    while True:
+        a = np.linspace(alpha_min + eps_b, alpha_max - eps_b, num=P) + np.random.normal(0, eps_n, P)
+        a = np.unique(np.clip(a, alpha_min, alpha_max))
+        if len(a) == P:
+            return a
+
+
+def xi_grid_scaled(xi, x, P):
+    """src/feedback_processing.py:47-108 with is_scaled=True, 'equispaced'."""
+    a = equispaced_alpha(0.0, 1.0, P)
+    return a[:, None] * np.asarray(xi, dtype=float)[None, :] + np.asarray(x, dtype=float)[None, :]
+
+
+def mvn_svd_factor(cov):
+    """numpy legacy multivariate_normal factor: x = mean + z @ (sqrt(s)[:,None] * vh)."""
+    _, s, vh = np.linalg.svd(cov)
+    return np.sqrt(s)[:, None] * vh
+
+
+def sample_max(mu, cov, S):
+    """f_max for S draws exactly as src/acquisition.py:78-80 / :175-177 (one draw per call)."""
+    out = np.empty(S)
+    for s in range(S):
+        out[s] = np.max(np.random.multivariate_normal(mu, cov))
+    return out
+
+
+def EI_from_fmax(fmax, mustar):
+    """src/acquisition.py:80-81."""
+    return float(np.mean(np.maximum(fmax - mustar, 0.0)))
+
+
+def varmax_from_fmax(fmax):
+    """src/acquisition.py:178."""
+    return float(np.mean(np.power(fmax - np.mean(fmax), 2)))
+
+
+# --------------------------------------------------------------------------- random Fourier features
+def rff_features(W, b, X, sigma_f):
+    """src/random_fourier_sampler.py:45-47 -- phi(X) = sqrt(2 sf^2/F) cos(W X^T + b), shape F x n."""
+    F = W.shape[0]
+    return np.sqrt(2.0 * sigma_f ** 2 / F) * np.cos(W @ np.atleast_2d(X).T + np.asarray(b).reshape(F, 1))
+
+
+def rff_jacobian(W, b, x, sigma_f):
+    """src/random_fourier_sampler.py:51-53 -- d phi / d x, shape F x D."""
+    F = W.shape[0]
+    return -np.sqrt(2.0 * sigma_f ** 2 / F) * np.sin(W @ np.asarray(x, dtype=float) + np.asarray(b).reshape(F))[:, None] * W
+
+
+def rff_S(omega, PhiX, Q, m, sigma, quadrature=True):
+    """src/random_fourier_sampler.py:106-110."""
+    f = PhiX.T @ omega
+    return -0.5 * omega @ omega - sum_phi(f, Q, m, sigma, 0, quadrature).sum() / m
+
+
+def _rff_diffs(PhiX, Q, m):
+    F = PhiX.shape[0]
+    P3 = PhiX.reshape(F, Q, m + 1)
+    return P3[:, :, 1:] - P3[:, :, :1]          # F x Q x m : phi_j - phi_i
+
+
+def rff_S_grad(omega, PhiX, Q, m, sigma):
+    """src/random_fourier_sampler.py:112-116."""
+    f = PhiX.T @ omega
+    ph = var2_normal_pdf(deltas(f, Q, m, sigma)) / (sigma * m)
+    return -omega - np.einsum("fqj,qj->f", _rff_diffs(PhiX, Q, m), ph)
+
+
+def rff_S_hess_diag(omega, PhiX, Q, m, sigma):
+    """Diagonal of src/random_fourier_sampler.py:118-122 (the reference Hessian *is* diagonal)."""
+    f = PhiX.T @ omega
+    Dl = deltas(f, Q, m, sigma)
+    c = -0.5 * Dl * var2_normal_pdf(Dl) / (m * sigma ** 2)
+    return -1.0 - np.einsum("fqj,qj->f", _rff_diffs(PhiX, Q, m) ** 2, c)
+
+
+def rff_omega_map(PhiX, Q, m, sigma, omega0, gtol=None):
+    """src/random_fourier_sampler.py:124-132."""
+    opts = {} if gtol is None else {"gtol": gtol}
+    res = scipy.optimize.minimize(lambda w: -rff_S(w, PhiX, Q, m, sigma), np.asarray(omega0, dtype=float),
+                                  method="trust-exact", jac=lambda w: -rff_S_grad(w, PhiX, Q, m, sigma),
+                                  hess=lambda w: -np.diag(rff_S_hess_diag(w, PhiX, Q, m, sigma)), options=opts)
+    return res.x, res
+
+
+def rff_eval_argmax(Omega, Phi_grid):
+    """Batched form of the objective of src/random_fourier_sampler.py:166,170:
+    Fs[S x P] = Omega[S x F] . Phi_grid[F x P]; per-sample max and first arg-max over P."""
+    Fs = Omega @ Phi_grid
+    idx = np.argmax(Fs, axis=1)
+    return Fs[np.arange(Fs.shape[0]), idx], idx.astype(np.int32)
