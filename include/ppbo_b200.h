@@ -1,0 +1,149 @@
+/* ppbo_b200 -- C ABI of the B200 (sm_100a) implementation of the PPBO hot path.
+ *
+ * Drop-in boundary: the reference (AaltoPML/PPBO) is pure Python; its hot path calls numpy / scipy /
+ * LAPACK from src/gp_model.py, src/kernels.py, src/misc.py, src/acquisition.py and
+ * src/random_fourier_sampler.py.  A maintainer binds this library with ctypes and the
+ * entry points below replace those call sites one for one; each comment names the reference lines it
+ * replaces.  All matrices are row-major (numpy C order) float64.  Unless a parameter name ends in `_h`,
+ * every pointer is a DEVICE pointer (torch tensor .data_ptr()); `stream` is a cudaStream_t passed as
+ * void*.  Return value: 0 = OK, > 0 = LAPACK-style info (e.g. index of the first non-positive pivot),
+ * < 0 = error (-1 bad argument, -2 CUDA failure); ppbo_last_error() gives the message.
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef PPBO_B200_H
+#define PPBO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPBO_KERNEL_SE 0       /* src/kernels.py:19-25 (ARD generalisation: one length-scale per dim) */
+#define PPBO_KERNEL_RQ 1       /* src/kernels.py:27-34 (alpha = 2)                                     */
+#define PPBO_KERNEL_CAMPHOR 2  /* src/kernels.py:36-53                                                 */
+
+int ppbo_version(void);
+const char* ppbo_last_error(void);
+/* device properties the host layer reports (SM count etc.); dev = CUDA ordinal */
+int ppbo_device_sm_count(int dev);
+
+/* ---- K1: covariance matrices -------------------------------------------------------------------- */
+/* out[n1 x n2] = k(X1_i, X2_j).  Replaces kernels.SE_kernel / RQ_kernel / camphor_copper_kernel and
+ * GPModel.create_Gramian_nonsquare (src/gp_model.py:153-155).  lengthscales_h: D host doubles. */
+int ppbo_kernel_matrix(int kind, const double* X1, int n1, const double* X2, int n2, int D,
+                       const double* lengthscales_h, double sigma_f, double* out, long long ld, void* stream);
+/* out[n x n] = (1-s) K(X,X) + s * (tr K / n) I, tr K / n == sigma_f^2 for these stationary kernels.
+ * Replaces GPModel.create_Gramian = kernel + misc.regularize_covariance (src/gp_model.py:147-151,
+ * src/misc.py:71-88: the SVD round trip is the identity, the shrinkage is fused). */
+int ppbo_gram_regularized(int kind, const double* X, int n, int D, const double* lengthscales_h,
+                          double sigma_f, double shrinkage, double* out, long long ld, void* stream);
+/* analytic dK/dlog(l_d) and dK/dlog(sigma_f) for the SE kernel (north_star piece 1; the reference has
+ * no gradient -- checked against finite differences of SE_kernel).  dK: [(D+1)][n1 x n2] */
+int ppbo_kernel_se_grad(const double* X1, int n1, const double* X2, int n2, int D,
+                        const double* lengthscales_h, double sigma_f, double* dK, long long ld,
+                        long long stride, void* stream);
+
+/* ---- K2: preference-likelihood terms and the Laplace fit ---------------------------------------- */
+/* Comparison-set layout: set q = rows q(m+1) .. q(m+1)+m of f, winner first
+ * (src/feedback_processing.py:121-123).  Outputs (any may be NULL):
+ *   lik_sum[1]  = sum_q sum_j Phi(Delta_qj / sqrt 2)             (GPModel.sum_Phi order 0, src/gp_model.py:176-193)
+ *   beta[N]     = likelihood gradient                            (GPModel.T_grad, src/gp_model.py:234-238)
+ *   arrow[Q*m]  = a_qj = -Delta phi~(Delta) / (2 m sigma^2)      (GPModel.create_Lambda, src/gp_model.py:249-274) */
+int ppbo_lik_terms(const double* f, int Q, int m, double sigma, double* lik_sum, double* beta,
+                   double* arrow, void* stream);
+/* dense Lambda[N x N] from the arrow coefficients (public attr GPModel.Lambda_MAP) */
+int ppbo_lambda_dense(const double* arrow, int Q, int m, double* out, long long ld, void* stream);
+/* G[Qm x Qm] = B^T Sigma B, the prior covariance of the latent differences f_j - f_winner */
+int ppbo_diffspace_gram(const double* Sigma, long long lds, int Q, int m, double* G, long long ldg, void* stream);
+
+/* doubles in a "factor object": n*n matrix followed by the inverted 128x128 diagonal blocks */
+long long ppbo_factor_doubles(int n);
+/* workspace (bytes) needed by ppbo_laplace_fit */
+long long ppbo_laplace_workspace_bytes(int Q, int m);
+/* MAP of T(f) = -1/2 f' Sigma^-1 f - (1/m) sum Phi(Delta/sqrt2)  (GPModel.update_fMAP, src/gp_model.py:354-389,
+ * replaces scipy trust-exact): damped Newton in difference space, every step one Cholesky of
+ * I + a^1/2 (B' Sigma B) a^1/2 (size Qm).  f_init may be NULL (start at 0).
+ * Outputs: f_map[N], alpha[N] = Sigma^-1 f_map, arrow[Qm] (true coefficients at the mode),
+ *          Lfac: "factor object" of ppbo_factor_doubles(Qm) doubles = [Qm x Qm lower Cholesky factor of
+ *          I + a+^1/2 G a+^1/2 at the mode (a+ = max(a,0)) | inverted diagonal blocks used by the solves],
+ *          stats_h[8] host doubles: iterations, final step inf-norm, T(f_map), #negative a, ... */
+int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
+                     int max_iter, double tol, double* G, double* Lfac, double* f_map, double* alpha,
+                     double* arrow, void* workspace, long long workspace_bytes, double* stats_h, void* stream);
+
+/* ---- dense FP64 linear algebra (replaces the LAPACK/BLAS calls under numpy/scipy) ---------------- */
+/* C[M x N] = alpha * A[M x K] . B[N x K]^T + beta * C   (row-major, K contiguous in A and B) */
+int ppbo_gemm_nt(const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
+                 int M, int N, int K, double alpha, double beta, void* stream);
+long long ppbo_potrf_workspace_bytes(int n);
+/* in-place lower Cholesky of the lower triangle of A[n x n] (upper triangle untouched).  info_h: host int,
+ * 0 or 1-based index of the first non-positive pivot.  Replaces dpotrf under scipy.linalg.solve(assume_a='pos')
+ * (src/misc.py:96-100) and under scipy's trust-exact. */
+int ppbo_potrf_lower(double* A, long long lda, int n, void* workspace, long long workspace_bytes, int* info_h,
+                     void* stream);
+/* X[nrhs x n] (row-major, one right-hand side per ROW) <- X . L^-T (trans=0)  or  X . L^-1 (trans=1) */
+int ppbo_trsm_right_lower(const double* L, long long ldl, int n, double* X, long long ldx, int nrhs, int trans,
+                          void* workspace, long long workspace_bytes, void* stream);
+/* y = A x for row-major A[M x N] */
+int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, double* y, void* stream);
+
+/* ---- K4: prediction and exact-GP acquisition ----------------------------------------------------- */
+long long ppbo_predict_workspace_bytes(int N, int Q, int m, int P, int batch);
+/* Posterior mean and covariance on `batch` grids of P points each (Xp: [batch*P x D]).
+ * mu = k*' alpha ; Sigma_p = reg(K**) - k*' (Sigma^-1 - Sigma^-1 Post Sigma^-1) k*  evaluated as
+ * reg(K**) - Y'Y (+ low-rank term for negative arrow coefficients), Y = Lfac^-1 a+^1/2 B' k*.
+ * Replaces GPModel.mu_Sigma_pred (src/gp_model.py:441-452).  mu: [batch*P], Sigma_p: [batch][P x P] (may be NULL). */
+/* Negative arrow coefficients at the mode (data that contradict the fit) make W = B a B' indefinite; the factor
+ * object only carries a+ = max(a,0).  These three calls build the exact low-rank correction
+ * (Woodbury on the r negative columns) that ppbo_predict adds: count (host sync; indices to idx_h), size, build. */
+int ppbo_neg_count(const double* arrow, int M, int* idx_h, int idx_capacity, void* stream);
+long long ppbo_neg_corr_doubles(int M, int r);
+int ppbo_neg_corr_build(const double* G, int M, const double* arrow, const double* Lfac, const int* idx_h, int r,
+                        double* neg_corr, void* stream);
+int ppbo_predict(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f,
+                 double shrinkage, int Q, int m, const double* alpha, const double* arrow, const double* Lfac,
+                 const double* neg_corr, int n_neg, const double* Xp, int P, int batch, double* mu,
+                 double* Sigma_p, void* workspace, long long workspace_bytes, void* stream);
+/* fmax[b][s] = max_p ( mu[b][p] + sum_k Z[b][s][k] Fac[b][p][k] ), arg[b][s] = first arg-max.
+ * Replaces the S calls of np.random.multivariate_normal + np.max in acquisition.EI / varmax
+ * (src/acquisition.py:78-80, 175-177); Fac is the (P x P) sampling factor (row p = coefficients of point p). */
+int ppbo_mvn_rowmax(const double* Z, long long ldz, long long strideZ, const double* Fac, long long ldf,
+                    long long strideF, const double* mu, long long strideMu, int S, int P, int K, int batch,
+                    double* fmax, int* arg, void* stream);
+/* per batch entry: out[b][0] = sum_s max(fmax-mustar,0), out[b][1] = sum_s fmax, out[b][2] = sum_s fmax^2
+ * (EI: src/acquisition.py:80-81; varmax: :178).  Deterministic fixed-order reduction. */
+int ppbo_acq_reduce(const double* fmax, int S, int batch, double mustar, double* out, void* stream);
+
+/* ---- K3: random Fourier features ------------------------------------------------------------------ */
+/* sqrt(2 sigma_f^2 / F) cos(W X^T + b).  feature_major = 1: Phi[F x n] (the reference's layout, used for the
+ * training points); 0: PhiT[n x F] (point-major, the K-contiguous operand of the sampling GEMM, used for grids).
+ * Replaces Hsampler.phiVec / phi (src/random_fourier_sampler.py:45-50). */
+int ppbo_rff_features(const double* W, const double* b, int F, int D, const double* X, int n, double sigma_f,
+                      double* Phi, long long ld, int feature_major, void* stream);
+/* J[F x D] = -sqrt(2 sigma_f^2/F) sin(W x + b) * W   (Hsampler.Dphi, src/random_fourier_sampler.py:51-53) */
+int ppbo_rff_jacobian(const double* W, const double* b, int F, int D, const double* x, double sigma_f,
+                      double* J, void* stream);
+/* weight-space objective pieces (Hsampler.S / S_grad / S_hessian, src/random_fourier_sampler.py:106-122):
+ * f = Phi_X' omega (Phi_X feature-major [F x N]); S = -1/2|omega|^2 - lik_sum/m (host double); grad[F];
+ * hess_diag[F] (the reference Hessian is diagonal).  Any output may be NULL. */
+long long ppbo_rff_workspace_bytes(int F, int Q, int m);
+int ppbo_rff_objective(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega,
+                       double* S_out_h, double* grad, double* hess_diag, void* workspace, long long workspace_bytes,
+                       void* stream);
+/* omega_MAP (Hsampler.update_omega_MAP, src/random_fourier_sampler.py:124-132, replaces scipy trust-exact): Newton in
+ * weight space with the exact clamped Hessian I + Psi' a+ Psi (F x F Cholesky) and backtracking; hess_diag[F] is the
+ * reference's diagonal Hessian at the optimum (its Laplace covariance is 1 / -hess_diag, :134-137).
+ * stats_h[4]: iterations, last relative step, S(omega_MAP). */
+int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega0,
+                 int max_iter, double tol, double* omega_map, double* hess_diag, void* workspace,
+                 long long workspace_bytes, double* stats_h, void* stream);
+/* Fs = Omega[S x F] . PhiT_grid[P x F]^T per batch entry (grid), fused per-sample max / first arg-max over P
+ * (batched form of the objective in Hsampler.return_xstar, src/random_fourier_sampler.py:166,170).
+ * Fs_full (optional, tests only): dense [batch][S x P]. */
+int ppbo_rff_eval_argmax(const double* Omega, long long ldo, int S, int F, const double* PhiT_grid, long long ldp,
+                         long long stridePhi, int P, int batch, double* fmax, int* arg, double* Fs_full,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPBO_B200_H */

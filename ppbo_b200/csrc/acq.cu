@@ -1,0 +1,468 @@
+// ppbo_b200 -- K4 (prediction + exact-GP acquisition) and K3 (random Fourier features) on sm_100a.
+// Replaces GPModel.mu_Sigma_pred (src/gp_model.py:441-452), the sampling loops of acquisition.EI / varmax
+// (src/acquisition.py:72-81,170-178) and Hsampler.phiVec/phi/Dphi/S/S_grad/S_hessian and its function
+// evaluations (src/random_fourier_sampler.py:45-53,106-122,166,170).
+#include <cmath>
+#include <vector>
+
+#include "../../include/ppbo_b200.h"
+#include "common.cuh"
+#include "gemm_f64.cuh"
+#include "linalg.cuh"
+
+namespace ppbo {
+
+int kernel_matrix_raw(int kind, const double* X1, int n1, const double* X2, int n2, int D, const double* ls_h,
+                      double sigma_f, double scale, double diag_add, double* out, long long ld, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------- prediction helpers
+// Ut[p][u] = sa[u] * (Kc[p][r(u)] - Kc[p][w(u)]),  sa = sqrt(max(arrow,0))          (a+^1/2 B^T k*, one RHS per row)
+__global__ void __launch_bounds__(256) pred_diff_kernel(const double* __restrict__ Kc, long long ldk, int PT, int Q, int m,
+                                                        const double* __restrict__ arrow, double* __restrict__ Ut,
+                                                        long long ldu) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (u >= Q * m) return;
+    const int q = u / m, j = u % m;
+    const long long w = (long long)q * (m + 1);
+    const double a = arrow[u];
+    const double* k = Kc + (long long)p * ldk;
+    Ut[(long long)p * ldu + u] = a > 0.0 ? sqrt(a) * (k[w + 1 + j] - k[w]) : 0.0;
+}
+// Ud[p][i] = Kc[p][r(u_i)] - Kc[p][w(u_i)] for the negative-coefficient indices u_i
+__global__ void pred_negdiff_kernel(const double* __restrict__ Kc, long long ldk, int PT, int m, const int* __restrict__ idx,
+                                    int r, double* __restrict__ Ud, long long ldu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (i >= r) return;
+    const int u = idx[i], q = u / m, j = u % m;
+    const long long w = (long long)q * (m + 1);
+    const double* k = Kc + (long long)p * ldk;
+    Ud[(long long)p * ldu + i] = k[w + 1 + j] - k[w];
+}
+// rows of  a+^1/2 G[:, J-]  (transposed: one row per negative index) and  R0 = diag(1/|a_j|) - G[J-, J-]
+__global__ void neg_rows_kernel(const double* __restrict__ G, long long ldg, int M, const double* __restrict__ arrow,
+                                const int* __restrict__ idx, int r, double* __restrict__ Ht, double* __restrict__ R,
+                                long long ldr) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (u >= M) return;
+    const int ui = idx[i];
+    const double a = arrow[u];
+    const double g = G[(long long)ui * ldg + u];          // G symmetric
+    Ht[(long long)i * M + u] = a > 0.0 ? sqrt(a) * g : 0.0;
+    if (u < r) {
+        const int uj = idx[u];
+        double v = -G[(long long)ui * ldg + uj];
+        if (u == i) v += 1.0 / fabs(arrow[ui]);
+        R[(long long)i * ldr + u] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- acquisition reductions
+// out[b] = { sum max(fmax - mustar, 0), sum fmax, sum fmax^2 (centred on the first sample for stability is NOT used:
+// plain sums in a fixed order, the host forms mean / variance) }
+__global__ void __launch_bounds__(1024) acq_reduce_kernel(const double* __restrict__ fm, int S, double mustar,
+                                                          double* __restrict__ out) {
+    __shared__ double red[33];
+    const double* x = fm + (long long)blockIdx.x * S;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int i = threadIdx.x; i < S; i += 1024) {
+        const double v = x[i];
+        s0 += fmax(v - mustar, 0.0);
+        s1 += v;
+        s2 = fma(v, v, s2);
+    }
+    s0 = block_sum(s0, red);
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+        out[blockIdx.x * 3 + 0] = s0;
+        out[blockIdx.x * 3 + 1] = s1;
+        out[blockIdx.x * 3 + 2] = s2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- random Fourier features
+// point-major PhiT[i][f] (transposed == 0) or feature-major Phi[f][i] (transposed == 1, the reference's layout)
+__global__ void __launch_bounds__(256) rff_features_kernel(const double* __restrict__ W, const double* __restrict__ b, int F,
+                                                           int D, const double* __restrict__ X, int n, double amp,
+                                                           double* __restrict__ out, long long ld, int feature_major) {
+    extern __shared__ double xs[];          // the CTA's point (point-major) or feature row (feature-major)
+    if (!feature_major) {
+        const int i = blockIdx.y;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = X[(long long)i * D + d];
+        __syncthreads();
+        const int f = blockIdx.x * blockDim.x + threadIdx.x;
+        if (f >= F) return;
+        double s = b[f];
+        for (int d = 0; d < D; ++d) s = fma(W[(long long)f * D + d], xs[d], s);
+        out[(long long)i * ld + f] = amp * cos(s);
+    } else {
+        const int f = blockIdx.y;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = W[(long long)f * D + d];
+        __syncthreads();
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n) return;
+        double s = b[f];
+        for (int d = 0; d < D; ++d) s = fma(xs[d], X[(long long)i * D + d], s);
+        out[(long long)f * ld + i] = amp * cos(s);
+    }
+}
+__global__ void rff_jacobian_kernel(const double* __restrict__ W, const double* __restrict__ b, int F, int D,
+                                    const double* __restrict__ x, double amp, double* __restrict__ J) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double s = b[f];
+    for (int d = 0; d < D; ++d) s = fma(W[(long long)f * D + d], x[d], s);
+    const double c = -amp * sin(s);
+    for (int d = 0; d < D; ++d) J[(long long)f * D + d] = c * W[(long long)f * D + d];
+}
+// y[i] = sum_f Phi[f][i] omega[f]   (feature-major Phi: coalesced over i)
+__global__ void __launch_bounds__(256) rff_fvals_kernel(const double* __restrict__ Phi, long long ld, int F, int N,
+                                                        const double* __restrict__ omega, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double s = 0.0;
+    for (int f = 0; f < F; ++f) s = fma(Phi[(long long)f * ld + i], omega[f], s);
+    y[i] = s;
+}
+// one warp per feature: grad[f] = -omega[f] + sum_rows beta[row] Phi[f][row]
+//                       hdiag[f] = -1 - sum_u arrow[u] (Phi[f][r(u)] - Phi[f][w(u)])^2
+__global__ void __launch_bounds__(256) rff_grad_hess_kernel(const double* __restrict__ Phi, long long ld, int F, int Q, int m,
+                                                            const double* __restrict__ omega, const double* __restrict__ beta,
+                                                            const double* __restrict__ arrow, double* __restrict__ grad,
+                                                            double* __restrict__ hdiag) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= F) return;
+    const double* ph = Phi + (long long)f * ld;
+    const int N = Q * (m + 1), M = Q * m;
+    double g = 0.0, h = 0.0;
+    if (grad) for (int i = lane; i < N; i += 32) g = fma(beta[i], ph[i], g);
+    if (hdiag)
+        for (int u = lane; u < M; u += 32) {
+            const int q = u / m, j = u % m;
+            const double d = ph[(long long)q * (m + 1) + 1 + j] - ph[(long long)q * (m + 1)];
+            h = fma(arrow[u], d * d, h);
+        }
+    for (int o = 16; o > 0; o >>= 1) {
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+        h += __shfl_xor_sync(0xffffffffu, h, o);
+    }
+    if (lane == 0) {
+        if (grad) grad[f] = -omega[f] + g;
+        if (hdiag) hdiag[f] = -1.0 - h;
+    }
+}
+// PsiT[f][u] = sa[u] (Phi[f][r(u)] - Phi[f][w(u)])     (F x M, K-contiguous operand of the weight-space Hessian GEMM)
+__global__ void __launch_bounds__(256) rff_psi_kernel(const double* __restrict__ Phi, long long ld, int Q, int m,
+                                                      const double* __restrict__ arrow, double* __restrict__ PsiT, long long ldp) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (u >= Q * m) return;
+    const int q = u / m, j = u % m;
+    const double* ph = Phi + (long long)f * ld;
+    const double a = arrow[u];
+    PsiT[(long long)f * ldp + u] = a > 0.0 ? sqrt(a) * (ph[(long long)q * (m + 1) + 1 + j] - ph[(long long)q * (m + 1)]) : 0.0;
+}
+__global__ void add_identity_kernel(double* __restrict__ A, long long ld, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(long long)i * ld + i] += 1.0;
+}
+// scal[0] = -0.5 |omega|^2 ; scal[1] = max|x| ; scal[2] = max|omega|
+__global__ void __launch_bounds__(1024) rff_scalars_kernel(const double* __restrict__ omega, const double* __restrict__ x, int F,
+                                                           double* __restrict__ scal) {
+    __shared__ double red[33];
+    __shared__ double mx[2][32];
+    double s = 0, m0 = 0, m1 = 0;
+    for (int i = threadIdx.x; i < F; i += 1024) {
+        s = fma(omega[i], omega[i], s);
+        if (x) m0 = fmax(m0, fabs(x[i]));
+        m1 = fmax(m1, fabs(omega[i]));
+    }
+    s = block_sum(s, red);
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    }
+    if ((threadIdx.x & 31) == 0) { mx[0][threadIdx.x >> 5] = m0; mx[1][threadIdx.x >> 5] = m1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { m0 = fmax(m0, mx[0][w]); m1 = fmax(m1, mx[1][w]); }
+        scal[0] = -0.5 * s; scal[1] = m0; scal[2] = m1;
+    }
+}
+__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ x, double a, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += a * x[i];
+}
+__global__ void axpy_out_kernel(double* __restrict__ out, const double* __restrict__ y, const double* __restrict__ x, double a, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = y[i] + a * x[i];
+}
+
+// defined in laplace.cu
+int launch_lik_terms(const double* f, int Q, int m, double sigma, double* set_lik, double* beta, double* arrow, double* sa,
+                     double* bvec, cudaStream_t st);
+int launch_sum(const double* x, int n, double* out, cudaStream_t st);
+
+}  // namespace ppbo
+
+using namespace ppbo;
+
+extern "C" long long ppbo_factor_doubles(int n) { return (long long)n * n + potrf_dinv_doubles(n) ; }
+
+// ------------------------------------------------------------------------------------------------ negative-coefficient correction
+/* number of negative arrow coefficients and their indices (host sync).  idx_h may be NULL. */
+extern "C" int ppbo_neg_count(const double* arrow, int M, int* idx_h, int idx_capacity, void* stream) {
+    std::vector<double> a((size_t)M);
+    if (cudaMemcpyAsync(a.data(), arrow, sizeof(double) * M, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+        set_error("ppbo_neg_count: copy failed");
+        return PPBO_ERR_CUDA;
+    }
+    int r = 0;
+    for (int u = 0; u < M; ++u)
+        if (a[u] < 0.0) {
+            if (idx_h && r < idx_capacity) idx_h[r] = u;
+            ++r;
+        }
+    return r;
+}
+/* neg_corr layout (doubles): [idx as int32, padded to 2*ceil(r/2) ints][Ht r x M][R factor object (r)] */
+extern "C" long long ppbo_neg_corr_doubles(int M, int r) {
+    return (long long)((r + 1) / 2) + (long long)r * M + ppbo_factor_doubles(r) + 2;
+}
+extern "C" int ppbo_neg_corr_build(const double* G, int M, const double* arrow, const double* Lfac, const int* idx_h, int r,
+                                   double* neg_corr, void* stream) {
+    if (r <= 0) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* idx = reinterpret_cast<int*>(neg_corr);
+    double* Ht = neg_corr + (r + 1) / 2;
+    double* R = Ht + (long long)r * M;
+    double* Rdinv = R + (long long)r * r;
+    int* info_d = reinterpret_cast<int*>(neg_corr + ppbo_neg_corr_doubles(M, r) - 1);
+    PPBO_CUDA_CHECK(cudaMemcpyAsync(idx, idx_h, sizeof(int) * r, cudaMemcpyHostToDevice, st));
+    neg_rows_kernel<<<dim3(ceil_div(M, 256), r), 256, 0, st>>>(G, M, M, arrow, idx, r, Ht, R, r);
+    PPBO_LAUNCH_CHECK();
+    int rc = trsm_right_lower_t(Lfac, M, M, Lfac + (long long)M * M, Ht, M, r, st);   // Ht <- Ht L^-T
+    if (rc) return rc;
+    GemmOperands g{Ht, M, 0, Ht, M, 0, r, r, M};
+    StoreEpilogue ep{R, r, 0, 1.0, 1.0, 0, 0, 0};                                      // R += Ht Ht^T
+    if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
+    if ((rc = potrf_lower(R, r, r, Rdinv, info_d, st))) return rc;
+    int info = 0;
+    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (info) { set_error("posterior precision is not positive definite (negative-coefficient block, pivot %d)", info); return info; }
+    return PPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ prediction
+extern "C" long long ppbo_predict_workspace_bytes(int N, int Q, int m, int P, int batch) {
+    const long long PT = (long long)P * batch, M = (long long)Q * m;
+    return (PT * N + PT * M + PT * M + 64) * 8;     // Kc, Ut, (Ud | Zs up to r <= M columns)
+}
+
+extern "C" int ppbo_predict(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f,
+                            double shrinkage, int Q, int m, const double* alpha, const double* arrow, const double* Lfac,
+                            const double* neg_corr, int n_neg, const double* Xp, int P, int batch, double* mu,
+                            double* Sigma_p, void* workspace, long long workspace_bytes, void* stream) {
+    PPBO_REQUIRE(N == Q * (m + 1), "N must equal Q (m+1)");
+    PPBO_REQUIRE(P >= 1 && batch >= 1, "empty grid");
+    PPBO_REQUIRE(workspace_bytes >= ppbo_predict_workspace_bytes(N, Q, m, P, batch), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int PT = P * batch, M = Q * m;
+    double* Kc = (double*)workspace;                 // [PT x N]   k(x*_p, X_i)
+    double* Ut = Kc + (long long)PT * N;             // [PT x M]
+    double* Ud = Ut + (long long)PT * M;             // [PT x r]
+    int rc;
+    if ((rc = kernel_matrix_raw(kind, Xp, PT, X, N, D, lengthscales_h, sigma_f, 1.0, 0.0, Kc, N, st))) return rc;
+    if (mu && (rc = gemv(Kc, N, PT, N, alpha, mu, st))) return rc;
+    if (!Sigma_p) return PPBO_OK;
+    pred_diff_kernel<<<dim3(ceil_div(M, 256), PT), 256, 0, st>>>(Kc, N, PT, Q, m, arrow, Ut, M);
+    PPBO_LAUNCH_CHECK();
+    if ((rc = trsm_right_lower_t(Lfac, M, M, Lfac + (long long)M * M, Ut, M, PT, st))) return rc;   // Yt = Ut L^-T
+    for (int b = 0; b < batch; ++b) {     // reg(K**) per grid (diagonal shrinkage needs the square form)
+        const double* xb = Xp + (long long)b * P * D;
+        if ((rc = kernel_matrix_raw(kind, xb, P, xb, P, D, lengthscales_h, sigma_f, 1.0 - shrinkage,
+                                    shrinkage * sigma_f * sigma_f, Sigma_p + (long long)b * P * P, P, st)))
+            return rc;
+    }
+    {
+        GemmOperands g{Ut, M, (long long)P * M, Ut, M, (long long)P * M, P, P, M};
+        StoreEpilogue ep{Sigma_p, P, (long long)P * P, -1.0, 1.0, 0, 0, 0};
+        if ((rc = launch_gemm_nt(g, ep, batch, st))) return rc;                                     // -= Yt Yt^T
+    }
+    if (n_neg > 0) {
+        PPBO_REQUIRE(neg_corr != nullptr, "neg_corr missing");
+        const int r = n_neg;
+        const int* idx = reinterpret_cast<const int*>(neg_corr);
+        const double* Ht = neg_corr + (r + 1) / 2;
+        const double* R = Ht + (long long)r * M;
+        pred_negdiff_kernel<<<dim3(ceil_div(r, 128), PT), 128, 0, st>>>(Kc, N, PT, m, idx, r, Ud, r);
+        PPBO_LAUNCH_CHECK();
+        GemmOperands g1{Ut, M, 0, Ht, M, 0, PT, r, M};
+        StoreEpilogue e1{Ud, r, 0, -1.0, 1.0, 0, 0, 0};                                             // z = Ud - Yt Ht^T
+        if ((rc = launch_gemm_nt(g1, e1, 1, st))) return rc;
+        if ((rc = trsm_right_lower_t(R, r, r, R + (long long)r * r, Ud, r, PT, st))) return rc;     // Zs = z LR^-T
+        GemmOperands g2{Ud, r, (long long)P * r, Ud, r, (long long)P * r, P, P, r};
+        StoreEpilogue e2{Sigma_p, P, (long long)P * P, 1.0, 1.0, 0, 0, 0};                          // += Zs Zs^T
+        if ((rc = launch_gemm_nt(g2, e2, batch, st))) return rc;
+    }
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_mvn_rowmax(const double* Z, long long ldz, long long strideZ, const double* Fac, long long ldf,
+                               long long strideF, const double* mu, long long strideMu, int S, int P, int K, int batch,
+                               double* fmax, int* arg, void* stream) {
+    PPBO_REQUIRE(S >= 0 && P >= 1 && K >= 1 && batch >= 1, "shape");
+    GemmOperands g{Z, ldz, strideZ, Fac, ldf, strideF, S, P, K};
+    RowMaxEpilogue ep{mu, strideMu, fmax, arg, nullptr, 0, 0};
+    return launch_gemm_nt_rowmax(g, ep, batch, (cudaStream_t)stream);
+}
+
+extern "C" int ppbo_acq_reduce(const double* fmax, int S, int batch, double mustar, double* out, void* stream) {
+    PPBO_REQUIRE(S >= 1 && batch >= 1, "shape");
+    acq_reduce_kernel<<<batch, 1024, 0, (cudaStream_t)stream>>>(fmax, S, mustar, out);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ RFF
+extern "C" int ppbo_rff_features(const double* W, const double* b, int F, int D, const double* X, int n, double sigma_f,
+                                 double* Phi, long long ld, int feature_major, void* stream) {
+    PPBO_REQUIRE(F >= 1 && D >= 1 && n >= 0, "shape");
+    if (n == 0) return PPBO_OK;
+    const double amp = sqrt(2.0 * sigma_f * sigma_f / F);      // src/random_fourier_sampler.py:46
+    dim3 grid = feature_major ? dim3(ceil_div(n, 256), F) : dim3(ceil_div(F, 256), n);
+    PPBO_REQUIRE(grid.y <= 65535, "too many rows for one launch");
+    rff_features_kernel<<<grid, 256, sizeof(double) * D, (cudaStream_t)stream>>>(W, b, F, D, X, n, amp, Phi, ld, feature_major);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_rff_jacobian(const double* W, const double* b, int F, int D, const double* x, double sigma_f, double* J,
+                                 void* stream) {
+    const double amp = sqrt(2.0 * sigma_f * sigma_f / F);
+    rff_jacobian_kernel<<<ceil_div(F, 128), 128, 0, (cudaStream_t)stream>>>(W, b, F, D, x, amp, J);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" long long ppbo_rff_workspace_bytes(int F, int Q, int m) {
+    const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
+    return (2 * N + 2 * M + Q * 9 + 64 + (long long)F * M + ppbo_factor_doubles(F) + 4 * (long long)F + 2 * CHOL_NB) * 8;
+}
+
+struct RffWs {
+    double *fvals, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp;
+    void carve(double* p, int F, int Q, int m) {
+        const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
+        fvals = p; p += N;
+        beta = p; p += N;
+        arrow = p; p += 2 * M;
+        setlik = p; p += 9LL * Q;
+        scal = p; p += 64;
+        PsiT = p; p += (long long)F * M;
+        H = p; p += ppbo_factor_doubles(F);
+        grad = p; p += F;
+        step = p; p += F + CHOL_NB;
+        trial = p; p += F;
+        tmp = p; p += F;
+    }
+};
+
+static int rff_eval(const double* Phi, long long ld, int F, int Q, int m, double sigma, const double* omega, RffWs& ws,
+                    double* grad, double* hdiag, bool want_arrow, double* lik_sum_dev, cudaStream_t st) {
+    const int N = Q * (m + 1);
+    rff_fvals_kernel<<<ceil_div(N, 256), 256, 0, st>>>(Phi, ld, F, N, omega, ws.fvals);
+    launch_lik_terms(ws.fvals, Q, m, sigma, ws.setlik, ws.beta, want_arrow ? ws.arrow : nullptr, nullptr, nullptr, st);
+    launch_sum(ws.setlik, Q, lik_sum_dev, st);
+    if (grad || hdiag)
+        rff_grad_hess_kernel<<<ceil_div(F, 8), 256, 0, st>>>(Phi, ld, F, Q, m, omega, ws.beta, ws.arrow, grad, hdiag);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+/* S, gradient and diagonal Hessian at omega (Phi_X feature-major [F x N]). */
+extern "C" int ppbo_rff_objective(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega,
+                                  double* S_out, double* grad, double* hess_diag, void* workspace, long long workspace_bytes,
+                                  void* stream) {
+    PPBO_REQUIRE(workspace_bytes >= ppbo_rff_workspace_bytes(F, Q, m), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    RffWs ws;
+    ws.carve((double*)workspace, F, Q, m);
+    int rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega, ws, grad, hess_diag, true, ws.scal + 8, st);
+    if (rc) return rc;
+    if (S_out) {
+        rff_scalars_kernel<<<1, 1024, 0, st>>>(omega, nullptr, F, ws.scal);
+        double h[9];
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(h), cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        *S_out = h[0] - h[8] / m;
+    }
+    return PPBO_OK;
+}
+
+/* omega_MAP = argmax S(omega) (Hsampler.update_omega_MAP, src/random_fourier_sampler.py:124-132): full Newton in weight
+ * space with the exact (clamped) Hessian I + Psi' a+ Psi and a backtracking line search; also returns the DIAGONAL Hessian at the
+ * optimum, which is what the reference's Laplace covariance uses (src/random_fourier_sampler.py:118-122,134-137). */
+extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega0,
+                            int max_iter, double tol, double* omega_map, double* hess_diag, void* workspace,
+                            long long workspace_bytes, double* stats_h, void* stream) {
+    PPBO_REQUIRE(workspace_bytes >= ppbo_rff_workspace_bytes(F, Q, m), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = Q * m;
+    RffWs ws;
+    ws.carve((double*)workspace, F, Q, m);
+    double* Hdinv = ws.H + (long long)F * F;
+    int* info_d = reinterpret_cast<int*>(ws.scal + 32);
+    if (omega0) PPBO_CUDA_CHECK(cudaMemcpyAsync(omega_map, omega0, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
+    else PPBO_CUDA_CHECK(cudaMemsetAsync(omega_map, 0, sizeof(double) * F, st));
+    int rc, it = 0, info = 0;
+    double h[16], S_cur = NAN, last_rel = INFINITY;
+    for (it = 0; it < max_iter; ++it) {
+        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, true, ws.scal + 8, st))) return rc;
+        rff_psi_kernel<<<dim3(ceil_div(M, 256), F), 256, 0, st>>>(Phi_X, ld, Q, m, ws.arrow, ws.PsiT, M);
+        GemmOperands g{ws.PsiT, M, 0, ws.PsiT, M, 0, F, F, M};
+        StoreEpilogue ep{ws.H, F, 0, 1.0, 0.0, 0, 0, 0};
+        if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
+        add_identity_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.H, F, F);
+        if ((rc = potrf_lower(ws.H, F, F, Hdinv, info_d, st))) return rc;
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.step, ws.grad, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
+        if ((rc = potrs_vec(ws.H, F, F, Hdinv, ws.step, st))) return rc;      // step = (-Hessian)^-1 grad  (ascent direction)
+        rff_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, ws.scal);
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (info) { set_error("weight-space Hessian not positive definite (pivot %d)", info); return info; }
+        S_cur = h[0] - h[8] / m;
+        const double max_step = h[1], max_om = fmax(h[2], 1e-300);
+        double s = 1.0;
+        bool ok = false;
+        for (int c = 0; c < 12; ++c, s *= 0.5) {
+            axpy_out_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.trial, omega_map, ws.step, s, F);
+            if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, ws.trial, ws, nullptr, nullptr, false, ws.scal + 8, st))) return rc;
+            rff_scalars_kernel<<<1, 1024, 0, st>>>(ws.trial, nullptr, F, ws.scal);
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
+            PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+            const double S_try = h[0] - h[8] / m;
+            if (S_try >= S_cur - 1e-13 * fabs(S_cur)) { ok = true; S_cur = S_try; break; }
+        }
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(omega_map, ws.trial, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
+        last_rel = s * max_step / max_om;
+        if (ok && s == 1.0 && last_rel <= tol) { ++it; break; }
+    }
+    if (hess_diag) {
+        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, nullptr, hess_diag, true, ws.scal + 8, st))) return rc;
+    }
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (stats_h) { stats_h[0] = it; stats_h[1] = last_rel; stats_h[2] = S_cur; stats_h[3] = 0; }
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_rff_eval_argmax(const double* Omega, long long ldo, int S, int F, const double* PhiT_grid, long long ldp,
+                                    long long stridePhi, int P, int batch, double* fmax, int* arg, double* Fs_full,
+                                    void* stream) {
+    PPBO_REQUIRE(S >= 0 && F >= 1 && P >= 1 && batch >= 1, "shape");
+    GemmOperands g{Omega, ldo, 0, PhiT_grid, ldp, stridePhi, S, P, F};
+    RowMaxEpilogue ep{nullptr, 0, fmax, arg, Fs_full, P, (long long)S * P};
+    return launch_gemm_nt_rowmax(g, ep, batch, (cudaStream_t)stream);
+}

@@ -1,0 +1,260 @@
+// ppbo_b200 -- K1: FP64 covariance matrices on sm_100a.
+// Replaces kernels.SE_kernel / RQ_kernel / camphor_copper_kernel (src/kernels.py:19-53), GPModel.create_Gramian
+// (= kernel + misc.regularize_covariance, src/gp_model.py:147-151, src/misc.py:71-88) and
+// GPModel.create_Gramian_nonsquare (src/gp_model.py:153-155).
+//
+// Roofline: 8 n1 n2 bytes written, 8 (n1+n2) D read -> HBM-write bound for small D; at D = 20 the FP64 pipe
+// (2 D + exp) is within ~2x of the HBM floor.  Layout: CTA tile 64 rows x 128 columns, the two
+// point tiles staged in shared memory pre-scaled by 1/l_d; thread = 2 adjacent columns x 16 rows, 16-byte
+// coalesced stores.
+#include "../../include/ppbo_b200.h"
+#include "common.cuh"
+
+namespace ppbo {
+
+struct KernelParams {
+    int kind, D;
+    double inv_ls[PPBO_MAX_D];   // 1 / l_d
+    double sf2;                  // sigma_f^2
+    double diag_scale, diag_add; // out = diag_scale * k (+ diag_add on i == j) : fused shrinkage
+};
+
+constexpr int KT_M = 64, KT_N = 128, KT_THREADS = 256;
+
+__device__ __forceinline__ double kernel_from_sums(int kind, double r2, double sf2) {
+    // r2: scaled squared distance (SE / RQ) or the summed exponent (camphor)
+    if (kind == PPBO_KERNEL_SE) return sf2 * exp(-0.5 * r2);
+    if (kind == PPBO_KERNEL_RQ) { const double t = 1.0 + 0.25 * r2; return sf2 / (t * t); }   // alpha = 2
+    return sf2 * exp(-r2);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(KT_THREADS) kernel_matrix_kernel(const double* __restrict__ X1, int n1,
+                                                                   const double* __restrict__ X2, int n2,
+                                                                   KernelParams p, double* __restrict__ out,
+                                                                   long long ld, int symmetric_diag) {
+    extern __shared__ double sm[];
+    const int D = p.D;
+    double* s1 = sm;                    // [KT_M][D]   rows of X1 (scaled)
+    double* s2 = sm + KT_M * D;         // [D][KT_N]   columns = points of X2 (scaled), d-major
+    const int r0 = blockIdx.y * KT_M, c0 = blockIdx.x * KT_N;
+    for (int e = threadIdx.x; e < KT_M * D; e += KT_THREADS) {
+        const int r = e / D, d = e % D;
+        const int gr = r0 + r;
+        const double v = gr < n1 ? X1[(long long)gr * D + d] : 0.0;
+        s1[e] = (KIND == PPBO_KERNEL_CAMPHOR) ? v : v * p.inv_ls[d];
+    }
+    for (int e = threadIdx.x; e < KT_N * D; e += KT_THREADS) {
+        const int c = e / D, d = e % D;
+        const int gc = c0 + c;
+        const double v = gc < n2 ? X2[(long long)gc * D + d] : 0.0;
+        s2[d * KT_N + c] = (KIND == PPBO_KERNEL_CAMPHOR) ? v : v * p.inv_ls[d];
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;     // 64 column pairs x 4 row groups of 16
+    const int c = c0 + 2 * tx;
+    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+        const int rl = ty * 16 + rr, r = r0 + rl;
+        if (r >= n1) break;
+        double a0 = 0.0, a1 = 0.0;
+        if (KIND == PPBO_KERNEL_CAMPHOR) {
+            // periodic (period 1) on dims 0,1,3,4,5: 2 sin^2(pi |dx|) / l^2 ; SE on dim 2 with l + 0.05
+            const double il = p.inv_ls[0], il2 = il * il, ilz = p.inv_ls[2];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+                const double x = s1[rl * D + d];
+                const double2 y = *reinterpret_cast<const double2*>(&s2[d * KT_N + 2 * tx]);
+                const double d0 = fabs(x - y.x), d1 = fabs(x - y.y);
+                if (d == 2) {
+                    a0 += 0.5 * d0 * d0 * ilz * ilz;
+                    a1 += 0.5 * d1 * d1 * ilz * ilz;
+                } else {
+                    const double q0 = sinpi(d0), q1 = sinpi(d1);
+                    a0 += 2.0 * q0 * q0 * il2;
+                    a1 += 2.0 * q1 * q1 * il2;
+                }
+            }
+        } else {
+            for (int d = 0; d < D; ++d) {
+                const double x = s1[rl * D + d];
+                const double2 y = *reinterpret_cast<const double2*>(&s2[d * KT_N + 2 * tx]);
+                const double d0 = x - y.x, d1 = x - y.y;
+                a0 = fma(d0, d0, a0);
+                a1 = fma(d1, d1, a1);
+            }
+        }
+        double k0 = p.diag_scale * kernel_from_sums(KIND, a0, p.sf2);
+        double k1 = p.diag_scale * kernel_from_sums(KIND, a1, p.sf2);
+        if (symmetric_diag) {
+            if (r == c) k0 += p.diag_add;
+            if (r == c + 1) k1 += p.diag_add;
+        }
+        double* o = out + (long long)r * ld + c;
+        if (c + 1 < n2 && vec_ok) {
+            *reinterpret_cast<double2*>(o) = make_double2(k0, k1);
+        } else {
+            if (c < n2) o[0] = k0;
+            if (c + 1 < n2) o[1] = k1;
+        }
+    }
+}
+
+static int fill_params(KernelParams& p, int kind, int D, const double* ls_h, double sigma_f) {
+    PPBO_REQUIRE(kind >= 0 && kind <= 2, "unknown kernel kind");
+    PPBO_REQUIRE(D >= 1 && D <= PPBO_MAX_D, "D must be in [1, 64]");
+    PPBO_REQUIRE(kind != PPBO_KERNEL_CAMPHOR || D == 6, "camphor_copper_kernel is defined for D = 6 only");
+    PPBO_REQUIRE(ls_h != nullptr && sigma_f > 0, "hyper-parameters");
+    p.kind = kind;
+    p.D = D;
+    for (int d = 0; d < PPBO_MAX_D; ++d) p.inv_ls[d] = 0.0;
+    for (int d = 0; d < D; ++d) {
+        PPBO_REQUIRE(ls_h[d] > 0, "length-scales must be positive");
+        p.inv_ls[d] = 1.0 / ls_h[d];
+    }
+    if (kind == PPBO_KERNEL_CAMPHOR) p.inv_ls[2] = 1.0 / (ls_h[2] + 0.05);   // src/kernels.py:48
+    p.sf2 = sigma_f * sigma_f;
+    p.diag_scale = 1.0;
+    p.diag_add = 0.0;
+    return PPBO_OK;
+}
+
+int kernel_matrix(const KernelParams& p, const double* X1, int n1, const double* X2, int n2, double* out,
+                  long long ld, int symmetric_diag, cudaStream_t st) {
+    if (n1 <= 0 || n2 <= 0) return PPBO_OK;
+    dim3 grid(ceil_div(n2, KT_N), ceil_div(n1, KT_M));
+    const size_t smem = (size_t)(KT_M + KT_N) * p.D * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {   // D up to 64 needs 96 KB of dynamic shared memory
+        const int max_smem = (KT_M + KT_N) * PPBO_MAX_D * (int)sizeof(double);
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_kernel<PPBO_KERNEL_SE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_kernel<PPBO_KERNEL_RQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_kernel<PPBO_KERNEL_CAMPHOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_done = true;
+    }
+    switch (p.kind) {
+        case PPBO_KERNEL_SE:
+            kernel_matrix_kernel<PPBO_KERNEL_SE><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
+            break;
+        case PPBO_KERNEL_RQ:
+            kernel_matrix_kernel<PPBO_KERNEL_RQ><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
+            break;
+        default:
+            kernel_matrix_kernel<PPBO_KERNEL_CAMPHOR><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
+    }
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+// internal entry used by predict (acq.cu)
+int kernel_matrix_raw(int kind, const double* X1, int n1, const double* X2, int n2, int D, const double* ls_h,
+                      double sigma_f, double scale, double diag_add, double* out, long long ld, cudaStream_t st) {
+    KernelParams p;
+    int rc = fill_params(p, kind, D, ls_h, sigma_f);
+    if (rc) return rc;
+    p.diag_scale = scale;
+    p.diag_add = diag_add;
+    return kernel_matrix(p, X1, n1, X2, n2, out, ld, diag_add != 0.0, st);
+}
+
+// ---- SE kernel gradients w.r.t. log length-scales and log sigma_f --------------------------------------
+__global__ void __launch_bounds__(256) se_grad_kernel(const double* __restrict__ X1, int n1, const double* __restrict__ X2,
+                                                      int n2, KernelParams p, double* __restrict__ dK, long long ld,
+                                                      long long stride) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n1 * n2) return;
+    const int i = (int)(idx / n2), j = (int)(idx % n2);
+    double r2 = 0.0;
+    for (int d = 0; d < p.D; ++d) {
+        const double t = (X1[(long long)i * p.D + d] - X2[(long long)j * p.D + d]) * p.inv_ls[d];
+        r2 = fma(t, t, r2);
+    }
+    const double k = p.sf2 * exp(-0.5 * r2);
+    for (int d = 0; d < p.D; ++d) {
+        const double t = (X1[(long long)i * p.D + d] - X2[(long long)j * p.D + d]) * p.inv_ls[d];
+        dK[d * stride + (long long)i * ld + j] = k * t * t;          // dK / dlog l_d
+    }
+    dK[p.D * stride + (long long)i * ld + j] = 2.0 * k;               // dK / dlog sigma_f
+}
+
+// ---- difference-space Gram matrix and the Newton system matrix -----------------------------------------
+// G[u][v] = S[r(u)][r(v)] - S[r(u)][w(v)] - S[w(u)][r(v)] + S[w(u)][w(v)],  u = (q, j): r = q(m+1)+1+j, w = q(m+1)
+__global__ void __launch_bounds__(256) diffspace_gram_kernel(const double* __restrict__ S, long long lds, int Q, int m,
+                                                             double* __restrict__ G, long long ldg) {
+    const int M = Q * m;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int u = blockIdx.y;
+    if (v >= M) return;
+    const int qu = u / m, ju = u % m, qv = v / m, jv = v % m;
+    const long long ru = (long long)qu * (m + 1) + 1 + ju, wu = (long long)qu * (m + 1);
+    const long long rv = (long long)qv * (m + 1) + 1 + jv, wv = (long long)qv * (m + 1);
+    G[(long long)u * ldg + v] = (S[ru * lds + rv] - S[ru * lds + wv]) - (S[wu * lds + rv] - S[wu * lds + wv]);
+}
+
+// Mmat[u][v] = delta_uv + sa[u] G[u][v] sa[v] on the lower triangle (v <= u), the part the Cholesky reads
+__global__ void __launch_bounds__(256) newton_matrix_kernel(const double* __restrict__ G, long long ldg, int M,
+                                                            const double* __restrict__ sa, double* __restrict__ out,
+                                                            long long ldo) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int u = blockIdx.y;
+    if (v >= M || (int)(blockIdx.x * blockDim.x) > u) return;
+    if (v > u) return;
+    double x = sa[u] * G[(long long)u * ldg + v] * sa[v];
+    if (u == v) x += 1.0;
+    out[(long long)u * ldo + v] = x;
+}
+
+int diffspace_gram(const double* S, long long lds, int Q, int m, double* G, long long ldg, cudaStream_t st) {
+    const int M = Q * m;
+    if (M <= 0) return PPBO_OK;
+    dim3 grid(ceil_div(M, 256), M);
+    diffspace_gram_kernel<<<grid, 256, 0, st>>>(S, lds, Q, m, G, ldg);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+int newton_matrix(const double* G, long long ldg, int M, const double* sa, double* out, long long ldo, cudaStream_t st) {
+    if (M <= 0) return PPBO_OK;
+    dim3 grid(ceil_div(M, 256), M);
+    newton_matrix_kernel<<<grid, 256, 0, st>>>(G, ldg, M, sa, out, ldo);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+}  // namespace ppbo
+
+using namespace ppbo;
+
+extern "C" int ppbo_kernel_matrix(int kind, const double* X1, int n1, const double* X2, int n2, int D,
+                                  const double* lengthscales_h, double sigma_f, double* out, long long ld, void* stream) {
+    PPBO_REQUIRE(n1 >= 0 && n2 >= 0 && ld >= n2, "shape");
+    return kernel_matrix_raw(kind, X1, n1, X2, n2, D, lengthscales_h, sigma_f, 1.0, 0.0, out, ld, (cudaStream_t)stream);
+}
+
+extern "C" int ppbo_gram_regularized(int kind, const double* X, int n, int D, const double* lengthscales_h,
+                                     double sigma_f, double shrinkage, double* out, long long ld, void* stream) {
+    PPBO_REQUIRE(n >= 0 && ld >= n, "shape");
+    PPBO_REQUIRE(shrinkage >= 0.0 && shrinkage < 1.0, "shrinkage in [0,1)");
+    // (1-s) K + s (tr K / n) I with tr K / n = sigma_f^2 (stationary kernels, k(x,x) = sigma_f^2)
+    return kernel_matrix_raw(kind, X, n, X, n, D, lengthscales_h, sigma_f, 1.0 - shrinkage,
+                             shrinkage * sigma_f * sigma_f, out, ld, (cudaStream_t)stream);
+}
+
+extern "C" int ppbo_kernel_se_grad(const double* X1, int n1, const double* X2, int n2, int D,
+                                   const double* lengthscales_h, double sigma_f, double* dK, long long ld,
+                                   long long stride, void* stream) {
+    KernelParams p;
+    int rc = fill_params(p, PPBO_KERNEL_SE, D, lengthscales_h, sigma_f);
+    if (rc) return rc;
+    if (n1 <= 0 || n2 <= 0) return PPBO_OK;
+    const long long total = (long long)n1 * n2;
+    se_grad_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(X1, n1, X2, n2, p, dK, ld, stride);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_diffspace_gram(const double* Sigma, long long lds, int Q, int m, double* G, long long ldg, void* stream) {
+    PPBO_REQUIRE(Q >= 0 && m >= 1, "shape");
+    return diffspace_gram(Sigma, lds, Q, m, G, ldg, (cudaStream_t)stream);
+}

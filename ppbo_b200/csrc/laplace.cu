@@ -1,0 +1,349 @@
+// ppbo_b200 -- K2: preference-likelihood terms and the Laplace (MAP) fit on sm_100a.
+// Replaces GPModel.sum_Phi / T / T_grad / create_Lambda (src/gp_model.py:176-274) and the scipy trust-exact
+// driver of GPModel.update_fMAP (src/gp_model.py:354-389).
+//
+// Formulation (DESIGN.md "Laplace fit"): with B the N x Qm incidence matrix of the comparison sets
+// (column (q,j): +1 at pseudo-observation row, -1 at the winner row), the negative likelihood Hessian is
+// W = B diag(a) B^T with a_qj = -Delta phi~(Delta) / (2 m sigma^2).  A damped Newton step with a+ = max(a,0) is
+//     alpha_new = b - B a+^1/2 (I + a+^1/2 G a+^1/2)^-1 a+^1/2 B^T Sigma b ,   b = B a+ B^T f + beta ,  f_new = Sigma alpha_new
+// where G = B^T Sigma B (Qm x Qm) is fixed during the fit.  One Cholesky of size Qm per step, no Sigma^-1.
+#include <cmath>
+
+#include "../../include/ppbo_b200.h"
+#include "common.cuh"
+#include "linalg.cuh"
+
+namespace ppbo {
+
+int diffspace_gram(const double* S, long long lds, int Q, int m, double* G, long long ldg, cudaStream_t st);
+int newton_matrix(const double* G, long long ldg, int M, const double* sa, double* out, long long ldo, cudaStream_t st);
+
+__device__ __forceinline__ double phi_tilde(double x) {           // density of N(0,2), src/misc.py:134-135
+    return 0.28209479177387814 * exp(-0.25 * x * x);             // 1/sqrt(4 pi)
+}
+__device__ __forceinline__ double Phi_tilde(double x) {           // Phi(x / sqrt2) == GH-200 quadrature of src/gp_model.py:192
+    return 0.5 * erfc(-0.5 * x);
+}
+
+// One warp per comparison set.  Outputs are optional (nullptr to skip).
+//   set_lik[q] = sum_j Phi~(Delta_qj)        beta[N]        arrow[Qm] (signed a)       sa[Qm] = sqrt(max(a,0))
+//   bvec[N]    = B a+ B^T f + beta           (Newton right-hand side)
+__global__ void __launch_bounds__(256) lik_terms_kernel(const double* __restrict__ f, int Q, int m, double sigma,
+                                                        double* __restrict__ set_lik, double* __restrict__ beta,
+                                                        double* __restrict__ arrow, double* __restrict__ sa,
+                                                        double* __restrict__ bvec) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const long long base = (long long)q * (m + 1);
+    const double fw = f[base];
+    const double inv_s = 1.0 / sigma, cg = 1.0 / (sigma * m), ca = 0.5 / (m * sigma * sigma);
+    double s_lik = 0.0, s_phi = 0.0, s_ad = 0.0;
+    for (int j = lane; j < m; j += 32) {
+        const double diff = f[base + 1 + j] - fw;
+        const double dl = diff * inv_s;
+        const double ph = phi_tilde(dl);
+        const double a = -ca * dl * ph;
+        const double ap = a > 0.0 ? a : 0.0;
+        s_lik += Phi_tilde(dl);
+        s_phi += ph;
+        s_ad += ap * diff;
+        if (beta) beta[base + 1 + j] = -ph * cg;
+        if (arrow) arrow[(long long)q * m + j] = a;
+        if (sa) sa[(long long)q * m + j] = sqrt(ap);
+        if (bvec) bvec[base + 1 + j] = ap * diff - ph * cg;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s_lik += __shfl_xor_sync(0xffffffffu, s_lik, o);
+        s_phi += __shfl_xor_sync(0xffffffffu, s_phi, o);
+        s_ad += __shfl_xor_sync(0xffffffffu, s_ad, o);
+    }
+    if (lane == 0) {
+        if (set_lik) set_lik[q] = s_lik;
+        if (beta) beta[base] = s_phi * cg;
+        if (bvec) bvec[base] = -s_ad + s_phi * cg;
+    }
+}
+
+// out[0] = sum_i x[i]  in a fixed order (single CTA) -> bit-reproducible
+__global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ x, int n, double* __restrict__ out) {
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += x[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// t[u] = sa[u] * (v[r(u)] - v[w(u)])                       (a+^1/2 B^T v)
+__global__ void diff_scale_kernel(const double* __restrict__ v, const double* __restrict__ sa, int Q, int m,
+                                  double* __restrict__ t) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= Q * m) return;
+    const int q = u / m, j = u % m;
+    const long long w = (long long)q * (m + 1);
+    t[u] = sa[u] * (v[w + 1 + j] - v[w]);
+}
+
+// alpha_new = b - B (sa .* y);  dalpha = alpha_new - alpha  (one warp per set)
+__global__ void __launch_bounds__(256) alpha_update_kernel(const double* __restrict__ bvec, const double* __restrict__ sa,
+                                                           const double* __restrict__ y, const double* __restrict__ alpha,
+                                                           int Q, int m, double* __restrict__ dalpha) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const long long base = (long long)q * (m + 1);
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) {
+        const double u = sa[(long long)q * m + j] * y[(long long)q * m + j];
+        s += u;
+        dalpha[base + 1 + j] = bvec[base + 1 + j] - u - alpha[base + 1 + j];
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dalpha[base] = bvec[base] + s - alpha[base];
+}
+
+// Line search data: for step sizes s_c = 2^-c, c = 0..NSTEP-1 (blockIdx.y = c):
+//   part[c][q] = sum_j Phi~(Delta_qj(f + s_c df))
+constexpr int NSTEP = 8;
+__global__ void __launch_bounds__(256) linesearch_lik_kernel(const double* __restrict__ f, const double* __restrict__ df,
+                                                             int Q, int m, double sigma, double* __restrict__ part) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const double step = ldexp(1.0, -(int)blockIdx.y);
+    const long long base = (long long)q * (m + 1);
+    const double fw = f[base] + step * df[base];
+    const double inv_s = 1.0 / sigma;
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) s += Phi_tilde((f[base + 1 + j] + step * df[base + 1 + j] - fw) * inv_s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) part[(long long)blockIdx.y * Q + q] = s;
+}
+
+// scal[0..3] = alpha.f, alpha.df, dalpha.f, dalpha.df ; scal[4] = max|df| ; scal[5] = max|f| ;
+// scal[8 + c] = sum_q part[c][q]     (single CTA, fixed order)
+__global__ void __launch_bounds__(1024) newton_scalars_kernel(const double* __restrict__ alpha, const double* __restrict__ dalpha,
+                                                              const double* __restrict__ f, const double* __restrict__ df,
+                                                              int N, const double* __restrict__ part, int Q,
+                                                              double* __restrict__ scal) {
+    __shared__ double red[33];
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mdf = 0, mf = 0;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const double a = alpha[i], da = dalpha[i], fi = f[i], dfi = df[i];
+        s0 = fma(a, fi, s0);
+        s1 = fma(a, dfi, s1);
+        s2 = fma(da, fi, s2);
+        s3 = fma(da, dfi, s3);
+        mdf = fmax(mdf, fabs(dfi));
+        mf = fmax(mf, fabs(fi));
+    }
+    s0 = block_sum(s0, red);
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    s3 = block_sum(s3, red);
+    for (int o = 16; o > 0; o >>= 1) {
+        mdf = fmax(mdf, __shfl_xor_sync(0xffffffffu, mdf, o));
+        mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+    }
+    __shared__ double mx[2][32];
+    if ((threadIdx.x & 31) == 0) { mx[0][threadIdx.x >> 5] = mdf; mx[1][threadIdx.x >> 5] = mf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { mdf = fmax(mdf, mx[0][w]); mf = fmax(mf, mx[1][w]); }
+        scal[0] = s0; scal[1] = s1; scal[2] = s2; scal[3] = s3; scal[4] = mdf; scal[5] = mf;
+    }
+    for (int c = 0; c < NSTEP; ++c) {
+        double s = 0.0;
+        for (int q = threadIdx.x; q < Q; q += 1024) s += part[(long long)c * Q + q];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) scal[8 + c] = s;
+    }
+}
+
+__global__ void axpy2_kernel(double* __restrict__ alpha, const double* __restrict__ dalpha, double* __restrict__ f,
+                             const double* __restrict__ df, double step, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        alpha[i] += step * dalpha[i];
+        f[i] += step * df[i];
+    }
+}
+
+// dense Lambda (public attr GPModel.Lambda_MAP): one thread per row of the output
+__global__ void lambda_dense_kernel(const double* __restrict__ arrow, int Q, int m, double* __restrict__ out, long long ld) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = Q * (m + 1);
+    if (idx >= (long long)N * N) return;
+    const int i = (int)(idx / N), j = (int)(idx % N);
+    const int qi = i / (m + 1), ri = i % (m + 1), qj = j / (m + 1), rj = j % (m + 1);
+    double v = 0.0;
+    if (qi == qj) {
+        const double* a = arrow + (long long)qi * m;
+        if (ri == 0 && rj == 0) { for (int t = 0; t < m; ++t) v -= a[t]; }
+        else if (ri == 0) v = a[rj - 1];
+        else if (rj == 0) v = a[ri - 1];
+        else if (ri == rj) v = -a[ri - 1];
+    }
+    out[(long long)i * ld + j] = v;
+}
+
+int launch_lik_terms(const double* f, int Q, int m, double sigma, double* set_lik, double* beta, double* arrow, double* sa,
+                     double* bvec, cudaStream_t st) {
+    lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, set_lik, beta, arrow, sa, bvec);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+int launch_sum(const double* x, int n, double* out, cudaStream_t st) {
+    sum_kernel<<<1, 1024, 0, st>>>(x, n, out);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+struct FitWorkspace {
+    double *bvec, *sa, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp;
+    int* info;
+    static long long doubles(int Q, int m) {
+        const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
+        return 4 * N + 2 * M + (M + CHOL_NB) + (long long)NSTEP * Q + 32 + 8 + 64;
+    }
+    void carve(double* base, int Q, int m) {
+        const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
+        double* p = base;
+        bvec = p; p += N;
+        Sb = p; p += N;
+        dalpha = p; p += N;
+        df = p; p += N;
+        sa = p; p += M;
+        arrow_tmp = p; p += M;
+        t = p; p += M + CHOL_NB;
+        set_part = p; p += (long long)NSTEP * Q;
+        scal = p; p += 32;
+        info = reinterpret_cast<int*>(p); p += 8;
+    }
+};
+
+}  // namespace ppbo
+
+using namespace ppbo;
+
+extern "C" int ppbo_lik_terms(const double* f, int Q, int m, double sigma, double* lik_sum, double* beta,
+                              double* arrow, void* stream) {
+    PPBO_REQUIRE(Q >= 0 && m >= 1 && sigma > 0, "shape / sigma");
+    if (Q == 0) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* part = nullptr;
+    if (lik_sum) PPBO_CUDA_CHECK(cudaMallocAsync(&part, sizeof(double) * Q, st));
+    lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, part, beta, arrow, nullptr, nullptr);
+    PPBO_LAUNCH_CHECK();
+    if (lik_sum) {
+        sum_kernel<<<1, 1024, 0, st>>>(part, Q, lik_sum);
+        PPBO_LAUNCH_CHECK();
+        PPBO_CUDA_CHECK(cudaFreeAsync(part, st));
+    }
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_lambda_dense(const double* arrow, int Q, int m, double* out, long long ld, void* stream) {
+    const long long N = (long long)Q * (m + 1);
+    if (N == 0) return PPBO_OK;
+    lambda_dense_kernel<<<(unsigned)ceil_div_ll(N * N, 256), 256, 0, (cudaStream_t)stream>>>(arrow, Q, m, out, ld);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" long long ppbo_laplace_workspace_bytes(int Q, int m) { return FitWorkspace::doubles(Q, m) * 8; }
+
+extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
+                                int max_iter, double tol, double* G, double* Lfac, double* f_map, double* alpha,
+                                double* arrow, void* workspace, long long workspace_bytes, double* stats_h, void* stream) {
+    PPBO_REQUIRE(Q >= 1 && m >= 1 && sigma > 0, "shape / sigma");
+    PPBO_REQUIRE(workspace_bytes >= ppbo_laplace_workspace_bytes(Q, m), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = Q * (m + 1), M = Q * m;
+    FitWorkspace ws;
+    ws.carve((double*)workspace, Q, m);
+    double* Mdinv = Lfac + (long long)M * M;      // factor object = [M x M lower factor | inverted diagonal blocks]
+    int rc;
+    if ((rc = diffspace_gram(Sigma, lds, Q, m, G, M, st))) return rc;
+
+    const bool have_start = f_init != nullptr;
+    if (have_start) PPBO_CUDA_CHECK(cudaMemcpyAsync(f_map, f_init, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+    else PPBO_CUDA_CHECK(cudaMemsetAsync(f_map, 0, sizeof(double) * N, st));
+    PPBO_CUDA_CHECK(cudaMemsetAsync(alpha, 0, sizeof(double) * N, st));
+
+    const int set_blocks = ceil_div(Q, 8);
+    double scal_h[32];
+    int it = 0, info = 0;
+    double last_step = 0.0, last_rel = INFINITY, T_cur = NAN;
+    bool alpha_known = !have_start;          // alpha = Sigma^-1 f is known (== 0) only for the zero start
+    int n_halvings_total = 0;
+    for (it = 0; it < max_iter; ++it) {
+        // likelihood terms at f, Newton right-hand side, system matrix, factorisation
+        lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, ws.sa, ws.bvec);
+        if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
+        if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
+        if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
+        diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
+        if ((rc = potrs_vec(Lfac, M, M, Mdinv, ws.t, st))) return rc;
+        alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);
+        if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st))) return rc;
+        PPBO_LAUNCH_CHECK();
+        if (!alpha_known) {
+            // arbitrary start: alpha_old is unknown (would need Sigma^-1 f); take the full Newton step, which
+            // only depends on f:  alpha <- alpha_new (= dalpha, since alpha held 0), f <- Sigma alpha_new
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(alpha, ws.dalpha, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(f_map, ws.df, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+            alpha_known = true;
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (info) { set_error("Newton system not positive definite at pivot %d (iteration %d)", info, it); return info; }
+            continue;
+        }
+        // line search over s = 1, 1/2, ..., 2^-7 on T(alpha + s dalpha) = -1/2 (alpha+s dalpha).(f+s df) - lik(f+s df)/m
+        linesearch_lik_kernel<<<dim3(set_blocks, NSTEP), 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.set_part);
+        if (std::isnan(T_cur)) {   // need T at the current point once: evaluate via the same kernel at step 0
+            lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, nullptr, nullptr, nullptr);
+            sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
+        }
+        newton_scalars_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, ws.scal);
+        PPBO_LAUNCH_CHECK();
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(scal_h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (info) { set_error("Newton system not positive definite at pivot %d (iteration %d)", info, it); return info; }
+        const double af = scal_h[0], adf = scal_h[1], daf = scal_h[2], dadf = scal_h[3];
+        if (std::isnan(T_cur)) T_cur = -0.5 * af - scal_h[24] / m;
+        double step = 0.0, T_new = T_cur;
+        int c;
+        for (c = 0; c < NSTEP; ++c) {
+            const double s = std::ldexp(1.0, -c);
+            const double Ts = -0.5 * (af + s * (adf + daf) + s * s * dadf) - scal_h[8 + c] / m;
+            if (Ts >= T_cur - 1e-13 * std::fabs(T_cur)) { step = s; T_new = Ts; break; }
+        }
+        if (c == NSTEP) { step = std::ldexp(1.0, -(NSTEP - 1)); T_new = NAN; }   // keep moving; T re-evaluated next round
+        n_halvings_total += (c == NSTEP) ? NSTEP : c;
+        axpy2_kernel<<<ceil_div(N, 256), 256, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, step, N);
+        PPBO_LAUNCH_CHECK();
+        T_cur = T_new;
+        last_step = step * scal_h[4];
+        const double fscale = std::fmax(scal_h[5], 1e-300);
+        last_rel = last_step / fscale;
+        if (step == 1.0 && last_rel <= tol) { ++it; break; }
+    }
+    // consistent products at the mode: arrow (signed), factor of I + a+^1/2 G a+^1/2
+    lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, arrow, ws.sa, nullptr);
+    sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
+    if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
+    if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
+    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (stats_h) {
+        stats_h[0] = it;
+        stats_h[1] = last_step;
+        stats_h[2] = last_rel;
+        stats_h[3] = T_cur;
+        stats_h[4] = n_halvings_total;
+        stats_h[5] = info;
+        stats_h[6] = 0;
+        stats_h[7] = 0;
+    }
+    if (info) { set_error("mode system not positive definite at pivot %d", info); return info; }
+    return PPBO_OK;
+}

@@ -1,0 +1,460 @@
+// ppbo_b200 -- dense FP64 linear algebra on sm_100a: GEMM launchers, blocked Cholesky, triangular solves, GEMV.
+// Replaces the LAPACK/BLAS calls the reference reaches through numpy/scipy (dpotrf/dposv under
+// scipy.linalg.solve(assume_a='pos') in src/misc.py:96-100 and under scipy's trust-exact used by
+// src/gp_model.py:382-384; dgemm/dgemv under np.dot in src/gp_model.py:441-458).
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/ppbo_b200.h"
+#include "gemm_f64.cuh"
+#include "linalg.cuh"
+
+namespace ppbo {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------- GEMM launchers
+using CfgBig = GemmCfg<128, 128, 2, 4, 4, 2>;      // 256 threads, warp tile 64x32, 160 KB smem, 1 CTA / SM
+using CfgBigU = GemmCfg<128, 128, 2, 4, 4, 1>;     // same, 8-byte copies for odd leading dimensions
+using CfgWide = GemmCfg<64, 128, 2, 4, 4, 2>;      // in-place row-panel updates: one CTA owns whole rows (BN >= K)
+using CfgWideU = GemmCfg<64, 128, 2, 4, 4, 1>;
+using CfgSmall = GemmCfg<64, 64, 2, 2, 4, 2>;      // 128 threads, warp tile 32x32, 80 KB smem, 2 CTAs / SM
+using CfgSmallU = GemmCfg<64, 64, 2, 2, 4, 1>;
+
+template <class Cfg>
+static int set_smem_attr_store() {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        err = cudaFuncSetAttribute(gemm_nt_store_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    });
+    PPBO_CUDA_CHECK(err);
+    return PPBO_OK;
+}
+template <class Cfg>
+static int set_smem_attr_rowmax() {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        err = cudaFuncSetAttribute(gemm_nt_rowmax_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    });
+    PPBO_CUDA_CHECK(err);
+    return PPBO_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool operands_vec2(const GemmOperands& g) {
+    return aligned16(g.A) && aligned16(g.B) && g.lda % 2 == 0 && g.ldb % 2 == 0 && g.strideA % 2 == 0 && g.strideB % 2 == 0;
+}
+
+template <class Cfg>
+static int launch_store_cfg(const GemmOperands& g, StoreEpilogue ep, int batch, cudaStream_t st) {
+    int rc = set_smem_attr_store<Cfg>();
+    if (rc) return rc;
+    const int tm = ceil_div(g.M, Cfg::BM), tn = ceil_div(g.N, Cfg::BN);
+    dim3 grid;
+    if (ep.lower_only) {
+        grid = dim3((unsigned)((long long)tm * (tm + 1) / 2), 1, batch);
+    } else {
+        grid = dim3(tm, tn, batch);
+    }
+    gemm_nt_store_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, ep);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+int launch_gemm_nt(const GemmOperands& g, const StoreEpilogue& ep_in, int batch, cudaStream_t st) {
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return PPBO_OK;
+    StoreEpilogue ep = ep_in;
+    ep.vec_ok = aligned16(ep.C) && ep.ldc % 2 == 0 && ep.strideC % 2 == 0;
+    const bool v2 = operands_vec2(g);
+    // small problems: more, smaller CTAs so the 148 SMs see work
+    const long long big_tiles = (long long)ceil_div(g.M, 128) * ceil_div(g.N, 128) * batch;
+    const bool small = !ep.lower_only && big_tiles < PPBO_SM_COUNT;
+    if (ep.lower_only) PPBO_REQUIRE(g.M == g.N, "lower_only needs a square output");
+    if (ep.in_place) {   // C aliases A: the CTA must read all of its rows (every k) before it stores -> BN >= N == K
+        PPBO_REQUIRE(g.N <= 128 && g.K <= 128 && !ep.lower_only, "in-place update needs N, K <= 128");
+        return v2 ? launch_store_cfg<CfgWide>(g, ep, batch, st) : launch_store_cfg<CfgWideU>(g, ep, batch, st);
+    }
+    if (small) return v2 ? launch_store_cfg<CfgSmall>(g, ep, batch, st) : launch_store_cfg<CfgSmallU>(g, ep, batch, st);
+    return v2 ? launch_store_cfg<CfgBig>(g, ep, batch, st) : launch_store_cfg<CfgBigU>(g, ep, batch, st);
+}
+
+template <class Cfg>
+static int launch_rowmax_cfg(const GemmOperands& g, const RowMaxEpilogue& ep, int batch, cudaStream_t st) {
+    int rc = set_smem_attr_rowmax<Cfg>();
+    if (rc) return rc;
+    dim3 grid(ceil_div(g.M, Cfg::BM), batch, 1);
+    gemm_nt_rowmax_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, ep);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+int launch_gemm_nt_rowmax(const GemmOperands& g, const RowMaxEpilogue& ep, int batch, cudaStream_t st) {
+    if (g.M <= 0 || batch <= 0) return PPBO_OK;
+    PPBO_REQUIRE(g.N > 0 && g.K >= 0, "empty grid");
+    const bool v2 = operands_vec2(g);
+    const bool small = (long long)ceil_div(g.M, 128) * batch < PPBO_SM_COUNT;
+    if (small) return v2 ? launch_rowmax_cfg<CfgSmall>(g, ep, batch, st) : launch_rowmax_cfg<CfgSmallU>(g, ep, batch, st);
+    return v2 ? launch_rowmax_cfg<CfgBig>(g, ep, batch, st) : launch_rowmax_cfg<CfgBigU>(g, ep, batch, st);
+}
+
+// ------------------------------------------------------------------------------------------- GEMV
+// y = A x, row-major A: one warp per row, 16-byte loads when aligned.  HBM-bound (8 M N bytes).
+__global__ void __launch_bounds__(256) gemv_kernel(const double* __restrict__ A, long long lda, int M, int N,
+                                                   const double* __restrict__ x, double* __restrict__ y, int vec) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int row = warp; row < M; row += nwarps) {
+        const double* a = A + (long long)row * lda;
+        double s0 = 0.0, s1 = 0.0;
+        if (vec) {
+            const double2* a2 = reinterpret_cast<const double2*>(a);
+            const double2* x2 = reinterpret_cast<const double2*>(x);
+            const int n2 = N >> 1;
+            for (int j = lane; j < n2; j += 32) {
+                const double2 av = a2[j], xv = x2[j];
+                s0 = fma(av.x, xv.x, s0);
+                s1 = fma(av.y, xv.y, s1);
+            }
+            if ((N & 1) && lane == 0) s0 = fma(a[N - 1], x[N - 1], s0);
+        } else {
+            for (int j = lane; j < N; j += 32) s0 = fma(a[j], x[j], s0);
+        }
+        double s = s0 + s1;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[row] = s;
+    }
+}
+
+int gemv(const double* A, long long lda, int M, int N, const double* x, double* y, cudaStream_t st) {
+    if (M <= 0) return PPBO_OK;
+    const int vec = aligned16(A) && aligned16(x) && lda % 2 == 0;
+    const int blocks = min(ceil_div(M, 8), PPBO_SM_COUNT * 8);
+    gemv_kernel<<<blocks, 256, 0, st>>>(A, lda, M, N, x, y, vec);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------- Cholesky
+// Diagonal block: factor the jb x jb lower block in shared memory and invert the factor (one CTA).
+// dinv receives inv(L_jj) as a dense NB x NB row-major lower-triangular block (zeros above the diagonal).
+constexpr int POTF2_THREADS = 512;
+constexpr int POTF2_LDS = CHOL_NB + 1;
+
+__global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __restrict__ A, long long lda, int jb,
+                                                                  double* __restrict__ dinv, int* __restrict__ info,
+                                                                  int block_offset) {
+    extern __shared__ double sm[];
+    double* S = sm;                               // jb x jb factor (lower), padded rows; later its inverse
+    const int tid = threadIdx.x;
+    for (int e = tid; e < jb * jb; e += POTF2_THREADS) {
+        const int i = e / jb, j = e % jb;
+        S[i * POTF2_LDS + j] = (j <= i) ? A[(long long)i * lda + j] : 0.0;
+    }
+    __syncthreads();
+    __shared__ int bad;
+    if (tid == 0) bad = 0;
+    // right-looking unblocked Cholesky
+    for (int k = 0; k < jb; ++k) {
+        __syncthreads();
+        const double d = S[k * POTF2_LDS + k];
+        if (!(d > 0.0)) {                          // also catches NaN
+            if (tid == 0) bad = k + 1;
+            break;                                 // uniform: every thread reads the same d
+        }
+        const double r = 1.0 / sqrt(d);
+        __syncthreads();
+        for (int i = k + tid; i < jb; i += POTF2_THREADS) S[i * POTF2_LDS + k] = (i == k) ? sqrt(d) : S[i * POTF2_LDS + k] * r;
+        __syncthreads();
+        const int rem = jb - k - 1;
+        for (int e = tid; e < rem * rem; e += POTF2_THREADS) {
+            const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+            if (j <= i) S[i * POTF2_LDS + j] -= S[i * POTF2_LDS + k] * S[j * POTF2_LDS + k];
+        }
+    }
+    __syncthreads();
+    if (bad) {
+        if (tid == 0 && atomicCAS(info, 0, block_offset + bad) == 0) {}
+        return;
+    }
+    for (int e = tid; e < jb * jb; e += POTF2_THREADS) {
+        const int i = e / jb, j = e % jb;
+        if (j <= i) A[(long long)i * lda + j] = S[i * POTF2_LDS + j];
+    }
+    // inverse of the lower-triangular factor, row by row and in place (row i of the inverse only needs rows < i of the
+    // inverse and row i of L):  R[i][c] = -(sum_{c<=p<i} L[i][p] R[p][c]) / L[i][i].
+    // 4 threads cooperate on one column c (dot product split 4 ways), 128 columns -> 512 threads
+    __syncthreads();
+    const int c = tid >> 2, part = tid & 3;
+    for (int i = 0; i < jb; ++i) {
+        double s = 0.0;
+        if (c < i) {
+            for (int p = c + part; p < i; p += 4) s = fma(S[i * POTF2_LDS + p], S[p * POTF2_LDS + c], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const double dii = 1.0 / S[i * POTF2_LDS + i];
+        __syncthreads();
+        if (part == 0) {
+            if (c < i) S[i * POTF2_LDS + c] = -s * dii;
+            else if (c == i) S[i * POTF2_LDS + c] = dii;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS) {
+        const int i = e / CHOL_NB, j = e % CHOL_NB;
+        dinv[e] = (i < jb && j <= i) ? S[i * POTF2_LDS + j] : 0.0;
+    }
+}
+
+long long potrf_dinv_doubles(int n) { return (long long)ceil_div(n, CHOL_NB) * CHOL_NB * CHOL_NB; }
+
+struct CholStreams {
+    cudaStream_t side = nullptr;
+    cudaEvent_t panel_done[2] = {nullptr, nullptr}, rest_done[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr;
+    int init() {
+        if (side) return PPBO_OK;
+        PPBO_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PPBO_CUDA_CHECK(cudaEventCreateWithFlags(&panel_done[i], cudaEventDisableTiming));
+            PPBO_CUDA_CHECK(cudaEventCreateWithFlags(&rest_done[i], cudaEventDisableTiming));
+        }
+        PPBO_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        return PPBO_OK;
+    }
+};
+static thread_local CholStreams g_chol;
+
+// Right-looking blocked Cholesky with one block column of look-ahead: the next diagonal block and panel are
+// factored on `st` while the bulk of the trailing update runs on a side stream.
+int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cudaStream_t st) {
+    if (n <= 0) return PPBO_OK;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    const int potf2_smem = CHOL_NB * POTF2_LDS * (int)sizeof(double);
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem);
+    });
+    PPBO_CUDA_CHECK(attr_err);
+    int rc = g_chol.init();
+    if (rc) return rc;
+    PPBO_CUDA_CHECK(cudaMemsetAsync(info_d, 0, sizeof(int), st));
+    const int nblk = ceil_div(n, CHOL_NB);
+    const bool lookahead = nblk > 3;
+    bool side_busy = false;
+    for (int b = 0; b < nblk; ++b) {
+        const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0), j1 = j0 + jb, rem = n - j1;
+        double* Ajj = A + (long long)j0 * lda + j0;
+        double* dinv_b = dinv + (long long)b * CHOL_NB * CHOL_NB;
+        potf2_inv_kernel<<<1, POTF2_THREADS, potf2_smem, st>>>(Ajj, lda, jb, dinv_b, info_d, j0);
+        PPBO_LAUNCH_CHECK();
+        if (rem <= 0) break;
+        // panel: L21 = A21 . inv(L11)^T   (in place: each CTA owns whole rows, K == jb <= BN)
+        double* A21 = A + (long long)j1 * lda + j0;
+        {
+            GemmOperands g{A21, lda, 0, dinv_b, CHOL_NB, 0, rem, jb, jb};
+            StoreEpilogue ep{A21, lda, 0, 1.0, 0.0, 0, 0, 1};
+            rc = launch_gemm_nt(g, ep, 1, st);
+            if (rc) return rc;
+        }
+        double* A22 = A + (long long)j1 * lda + j1;
+        const int nb1 = min(CHOL_NB, rem);           // width of the next block column
+        if (lookahead && rem > nb1) {
+            // (a) next block column on the main stream: A22[:, 0:nb1] -= L21 . L21[0:nb1]^T
+            if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[(b + 1) & 1], 0));
+            PPBO_CUDA_CHECK(cudaEventRecord(g_chol.panel_done[b & 1], st));
+            {
+                GemmOperands g{A21, lda, 0, A21, lda, 0, rem, nb1, jb};
+                StoreEpilogue ep{A22, lda, 0, -1.0, 1.0, 0, 0};
+                rc = launch_gemm_nt(g, ep, 1, st);
+                if (rc) return rc;
+            }
+            // (b) the rest of the trailing matrix on the side stream (lower tiles only)
+            PPBO_CUDA_CHECK(cudaStreamWaitEvent(g_chol.side, g_chol.panel_done[b & 1], 0));
+            {
+                const int r2 = rem - nb1;
+                const double* P2 = A21 + (long long)nb1 * lda;
+                GemmOperands g{P2, lda, 0, P2, lda, 0, r2, r2, jb};
+                StoreEpilogue ep{A22 + (long long)nb1 * lda + nb1, lda, 0, -1.0, 1.0, 1, 0};
+                rc = launch_gemm_nt(g, ep, 1, g_chol.side);
+                if (rc) return rc;
+            }
+            PPBO_CUDA_CHECK(cudaEventRecord(g_chol.rest_done[b & 1], g_chol.side));
+            side_busy = true;
+        } else {
+            if (side_busy) {
+                PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[(b + 1) & 1], 0));
+                side_busy = false;
+            }
+            GemmOperands g{A21, lda, 0, A21, lda, 0, rem, rem, jb};
+            StoreEpilogue ep{A22, lda, 0, -1.0, 1.0, 1, 0};
+            rc = launch_gemm_nt(g, ep, 1, st);
+            if (rc) return rc;
+        }
+    }
+    if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[(nblk - 2) & 1], 0));
+    return PPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------- TRSV (one RHS)
+// forward step for block J: every CTA recomputes y_J = inv(L_JJ) t_J (cheap), CTA 0 stores it, then each warp
+// updates rows below:  t[i] -= L[i, J] . y_J
+__global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ L, long long ldl, int n, int j0, int jb,
+                                                     const double* __restrict__ dinv_b, double* __restrict__ t) {
+    __shared__ double tj[CHOL_NB], yj[CHOL_NB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < CHOL_NB; i += 256) tj[i] = (i < jb) ? t[j0 + i] : 0.0;
+    __syncthreads();
+    for (int r = warp; r < jb; r += 8) {
+        double s = 0.0;
+        for (int k = lane; k <= r; k += 32) s = fma(dinv_b[r * CHOL_NB + k], tj[k], s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) yj[r] = s;
+    }
+    __syncthreads();
+    const int j1 = j0 + jb;
+    const int rows = n - j1;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    for (int r = gw; r < rows; r += nw) {
+        const double* lrow = L + (long long)(j1 + r) * ldl + j0;
+        double s = 0.0;
+        for (int k = lane; k < jb; k += 32) s = fma(lrow[k], yj[k], s);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) t[j1 + r] -= s;
+    }
+    // y_J overwrites t_J only after every CTA has read t_J: done by a second tiny launch (trsv_store) to stay race-free
+    if (blockIdx.x == 0) {
+        double* ybuf = t + n;   // scratch tail [n, n + NB)
+        for (int i = tid; i < jb; i += 256) ybuf[i] = yj[i];
+    }
+}
+__global__ void trsv_commit(double* __restrict__ t, int n, int j0, int jb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < jb) t[j0 + i] = t[n + i];
+}
+// backward step for block J: x_J = inv(L_JJ)^T y_J ; y[k] -= sum_r L[j0+r][k] x_J[r] for k < j0
+__global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ L, long long ldl, int n, int j0, int jb,
+                                                     const double* __restrict__ dinv_b, double* __restrict__ y) {
+    __shared__ double yj[CHOL_NB], xj[CHOL_NB];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < CHOL_NB; i += 256) yj[i] = (i < jb) ? y[j0 + i] : 0.0;
+    __syncthreads();
+    for (int c = tid; c < jb; c += 256) {          // x[c] = sum_{r >= c} dinv[r][c] y[r]  (coalesced over c)
+        double s = 0.0;
+        for (int r = c; r < jb; ++r) s = fma(dinv_b[r * CHOL_NB + c], yj[r], s);
+        xj[c] = s;
+    }
+    __syncthreads();
+    for (int k = blockIdx.x * 256 + tid; k < j0; k += gridDim.x * 256) {
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < jb; ++r) s = fma(L[(long long)(j0 + r) * ldl + k], xj[r], s);
+        y[k] -= s;
+    }
+    if (blockIdx.x == 0) {
+        double* xbuf = y + n;
+        for (int i = tid; i < jb; i += 256) xbuf[i] = xj[i];
+    }
+}
+
+// solves (L L^T) x = t in place; t must have room for n + CHOL_NB doubles (scratch tail)
+int potrs_vec(const double* L, long long ldl, int n, const double* dinv, double* t, cudaStream_t st) {
+    const int nblk = ceil_div(n, CHOL_NB);
+    for (int b = 0; b < nblk; ++b) {
+        const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0);
+        const int rows = n - j0 - jb;
+        const int blocks = max(1, min(ceil_div(rows, 8 * 4), PPBO_SM_COUNT * 2));
+        trsv_fwd_step<<<blocks, 256, 0, st>>>(L, ldl, n, j0, jb, dinv + (long long)b * CHOL_NB * CHOL_NB, t);
+        trsv_commit<<<1, CHOL_NB, 0, st>>>(t, n, j0, jb);
+    }
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0);
+        const int blocks = max(1, min(ceil_div(j0, 256), PPBO_SM_COUNT * 2));
+        trsv_bwd_step<<<blocks, 256, 0, st>>>(L, ldl, n, j0, jb, dinv + (long long)b * CHOL_NB * CHOL_NB, t);
+        trsv_commit<<<1, CHOL_NB, 0, st>>>(t, n, j0, jb);
+    }
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------- TRSM (many RHS, one per row)
+// X[nrhs x n] <- X . L^-T : column blocks ascending; Y_J = X_J . inv(L_JJ)^T ; X[:, J+1:] -= Y_J . L[J+1:, J]^T
+int trsm_right_lower_t(const double* L, long long ldl, int n, const double* dinv, double* X, long long ldx, int nrhs,
+                       cudaStream_t st) {
+    const int nblk = ceil_div(n, CHOL_NB);
+    for (int b = 0; b < nblk; ++b) {
+        const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0), j1 = j0 + jb;
+        {
+            GemmOperands g{X + j0, ldx, 0, dinv + (long long)b * CHOL_NB * CHOL_NB, CHOL_NB, 0, nrhs, jb, jb};
+            StoreEpilogue ep{X + j0, ldx, 0, 1.0, 0.0, 0, 0, 1};
+            int rc = launch_gemm_nt(g, ep, 1, st);   // in place (CfgWide)
+            if (rc) return rc;
+        }
+        if (j1 < n) {
+            GemmOperands g{X + j0, ldx, 0, L + (long long)j1 * ldl + j0, ldl, 0, nrhs, n - j1, jb};
+            StoreEpilogue ep{X + j1, ldx, 0, -1.0, 1.0, 0, 0};
+            int rc = launch_gemm_nt(g, ep, 1, st);
+            if (rc) return rc;
+        }
+    }
+    return PPBO_OK;
+}
+
+}  // namespace ppbo
+
+// =========================================================================================== C ABI
+using namespace ppbo;
+
+extern "C" int ppbo_version(void) { return 100; }
+extern "C" const char* ppbo_last_error(void) { return g_err; }
+extern "C" int ppbo_device_sm_count(int dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return v;
+}
+
+extern "C" int ppbo_gemm_nt(const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
+                            int M, int N, int K, double alpha, double beta, void* stream) {
+    PPBO_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative size");
+    GemmOperands g{A, lda, 0, B, ldb, 0, M, N, K};
+    StoreEpilogue ep{C, ldc, 0, alpha, beta, 0, 0};
+    return launch_gemm_nt(g, ep, 1, (cudaStream_t)stream);
+}
+
+extern "C" long long ppbo_potrf_workspace_bytes(int n) { return potrf_dinv_doubles(n) * 8 + 16; }
+
+extern "C" int ppbo_potrf_lower(double* A, long long lda, int n, void* workspace, long long workspace_bytes,
+                                int* info_h, void* stream) {
+    PPBO_REQUIRE(n >= 0 && lda >= n, "bad matrix shape");
+    PPBO_REQUIRE(workspace_bytes >= ppbo_potrf_workspace_bytes(n), "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* dinv = (double*)workspace;
+    int* info_d = (int*)(dinv + potrf_dinv_doubles(n));
+    int rc = potrf_lower(A, lda, n, dinv, info_d, st);
+    if (rc) return rc;
+    int info = 0;
+    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (info_h) *info_h = info;
+    return info;
+}
+
+extern "C" int ppbo_trsm_right_lower(const double* L, long long ldl, int n, double* X, long long ldx, int nrhs,
+                                     int trans, void* workspace, long long workspace_bytes, void* stream) {
+    PPBO_REQUIRE(trans == 0, "only X <- X L^-T is provided (every use on the PPBO path has this form)");
+    PPBO_REQUIRE(workspace_bytes >= ppbo_potrf_workspace_bytes(n), "workspace must be the one ppbo_potrf_lower filled");
+    return trsm_right_lower_t(L, ldl, n, (const double*)workspace, X, ldx, nrhs, (cudaStream_t)stream);
+}
+
+extern "C" int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, double* y, void* stream) {
+    return gemv(A, lda, M, N, x, y, (cudaStream_t)stream);
+}

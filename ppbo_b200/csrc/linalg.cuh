@@ -1,0 +1,19 @@
+// ppbo_b200 -- internal declarations of the dense linear-algebra layer (linalg.cu)
+#pragma once
+#include "common.cuh"
+
+namespace ppbo {
+
+constexpr int CHOL_NB = 128;   // Cholesky block size: K of the trailing DMMA updates
+
+long long potrf_dinv_doubles(int n);
+// in-place blocked lower Cholesky; dinv receives the inverted diagonal blocks; *info_d (device) = 0 or first bad pivot (1-based)
+int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cudaStream_t st);
+// (L L^T) x = t in place; t must hold n + CHOL_NB doubles
+int potrs_vec(const double* L, long long ldl, int n, const double* dinv, double* t, cudaStream_t st);
+// X[nrhs x n] <- X . L^-T
+int trsm_right_lower_t(const double* L, long long ldl, int n, const double* dinv, double* X, long long ldx, int nrhs,
+                       cudaStream_t st);
+int gemv(const double* A, long long lda, int M, int N, const double* x, double* y, cudaStream_t st);
+
+}  // namespace ppbo

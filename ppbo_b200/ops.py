@@ -1,0 +1,265 @@
+"""Thin host wrappers: torch CUDA tensors in, C-ABI calls on the current stream, torch CUDA tensors out.
+
+Every function here ends in a call into libppbo_b200.so; nothing is computed with torch ops or numpy.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import KERNEL_KINDS, PPBOError, check
+
+F64 = torch.float64
+
+
+def device(index=None):
+    if not torch.cuda.is_available():
+        raise PPBOError("ppbo_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device() if index is None else index)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_dev(a, dev=None):
+    """host array-like -> contiguous float64 CUDA tensor"""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev or device(), dtype=F64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64)), device=dev or device())
+
+
+def _ls(lengthscales, D):
+    ls = np.broadcast_to(np.asarray(lengthscales, dtype=np.float64), (D,))
+    return _lib.host_doubles(ls)
+
+
+def _kind(kernel):
+    if isinstance(kernel, int):
+        return kernel
+    name = kernel if isinstance(kernel, str) else getattr(kernel, "__name__", str(kernel))
+    if name not in KERNEL_KINDS:
+        raise PPBOError("unknown kernel %r" % (name,))
+    return KERNEL_KINDS[name]
+
+
+# ------------------------------------------------------------------------------------------- K1
+def kernel_matrix(kernel, X1, X2, lengthscales, sigma_f, out=None):
+    n1, D = X1.shape
+    n2 = X2.shape[0]
+    out = torch.empty((n1, n2), dtype=F64, device=X1.device) if out is None else out
+    check(_lib.load().ppbo_kernel_matrix(_kind(kernel), _p(X1), n1, _p(X2), n2, D, _ls(lengthscales, D), float(sigma_f),
+                                         _p(out), out.stride(0) if n1 else max(n2, 1), _stream()), "ppbo_kernel_matrix")
+    return out
+
+
+def gram_regularized(kernel, X, lengthscales, sigma_f, shrinkage, out=None):
+    n, D = X.shape
+    out = torch.empty((n, n), dtype=F64, device=X.device) if out is None else out
+    check(_lib.load().ppbo_gram_regularized(_kind(kernel), _p(X), n, D, _ls(lengthscales, D), float(sigma_f),
+                                            float(shrinkage), _p(out), max(n, 1), _stream()), "ppbo_gram_regularized")
+    return out
+
+
+def kernel_se_grad(X1, X2, lengthscales, sigma_f):
+    n1, D = X1.shape
+    n2 = X2.shape[0]
+    dK = torch.empty((D + 1, n1, n2), dtype=F64, device=X1.device)
+    check(_lib.load().ppbo_kernel_se_grad(_p(X1), n1, _p(X2), n2, D, _ls(lengthscales, D), float(sigma_f), _p(dK), n2,
+                                          n1 * n2, _stream()), "ppbo_kernel_se_grad")
+    return dK
+
+
+# ------------------------------------------------------------------------------------------- K2
+def lik_terms(f, Q, m, sigma, want_sum=True, want_beta=True, want_arrow=True):
+    dev = f.device
+    s = torch.empty(1, dtype=F64, device=dev) if want_sum else None
+    beta = torch.empty(Q * (m + 1), dtype=F64, device=dev) if want_beta else None
+    arrow = torch.empty(Q * m, dtype=F64, device=dev) if want_arrow else None
+    check(_lib.load().ppbo_lik_terms(_p(f), Q, m, float(sigma), _p(s), _p(beta), _p(arrow), _stream()), "ppbo_lik_terms")
+    return s, beta, arrow
+
+
+def lambda_dense(arrow, Q, m):
+    N = Q * (m + 1)
+    out = torch.empty((N, N), dtype=F64, device=arrow.device)
+    check(_lib.load().ppbo_lambda_dense(_p(arrow), Q, m, _p(out), N, _stream()), "ppbo_lambda_dense")
+    return out
+
+
+def diffspace_gram(Sigma, Q, m):
+    M = Q * m
+    G = torch.empty((M, M), dtype=F64, device=Sigma.device)
+    check(_lib.load().ppbo_diffspace_gram(_p(Sigma), Sigma.stride(0), Q, m, _p(G), M, _stream()), "ppbo_diffspace_gram")
+    return G
+
+
+class LaplaceFit:
+    """Device-resident products of the MAP fit (everything prediction / acquisition needs)."""
+    __slots__ = ("Q", "m", "sigma", "f_map", "alpha", "arrow", "G", "Lfac", "stats", "n_neg", "neg_corr", "info")
+
+
+def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10):
+    lib = _lib.load()
+    dev = Sigma.device
+    N, M = Q * (m + 1), Q * m
+    fit = LaplaceFit()
+    fit.Q, fit.m, fit.sigma = Q, m, float(sigma)
+    fit.G = torch.empty((M, M), dtype=F64, device=dev)
+    fit.Lfac = torch.empty(lib.ppbo_factor_doubles(M), dtype=F64, device=dev)
+    fit.f_map = torch.empty(N, dtype=F64, device=dev)
+    fit.alpha = torch.empty(N, dtype=F64, device=dev)
+    fit.arrow = torch.empty(M, dtype=F64, device=dev)
+    wbytes = lib.ppbo_laplace_workspace_bytes(Q, m)
+    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev)
+    stats = (ctypes.c_double * 8)()
+    rc = check(lib.ppbo_laplace_fit(_p(Sigma), Sigma.stride(0), Q, m, float(sigma), _p(f_init), int(max_iter), float(tol),
+                                    _p(fit.G), _p(fit.Lfac), _p(fit.f_map), _p(fit.alpha), _p(fit.arrow), _p(ws), wbytes,
+                                    stats, _stream()), "ppbo_laplace_fit")
+    fit.info = rc
+    fit.stats = dict(iterations=int(stats[0]), last_step=stats[1], last_rel_step=stats[2], T=stats[3],
+                     halvings=int(stats[4]))
+    fit.n_neg, fit.neg_corr = 0, None
+    if rc == 0:
+        idx = (ctypes.c_int * M)()
+        r = check(lib.ppbo_neg_count(_p(fit.arrow), M, idx, M, _stream()), "ppbo_neg_count")
+        if r > 0:
+            fit.neg_corr = torch.empty(lib.ppbo_neg_corr_doubles(M, r), dtype=F64, device=dev)
+            rc2 = check(lib.ppbo_neg_corr_build(_p(fit.G), M, _p(fit.arrow), _p(fit.Lfac), idx, r, _p(fit.neg_corr),
+                                                _stream()), "ppbo_neg_corr_build")
+            if rc2 > 0:
+                fit.info = rc2
+            fit.n_neg = r
+    return fit
+
+
+# ------------------------------------------------------------------------------------------- dense linear algebra
+def gemm_nt(A, B, C=None, alpha=1.0, beta=0.0):
+    M, K = A.shape
+    N = B.shape[0]
+    C = torch.empty((M, N), dtype=F64, device=A.device) if C is None else C
+    check(_lib.load().ppbo_gemm_nt(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, float(alpha),
+                                   float(beta), _stream()), "ppbo_gemm_nt")
+    return C
+
+
+def potrf_lower(A):
+    """in-place lower Cholesky; returns (info, workspace holding the inverted diagonal blocks)"""
+    lib = _lib.load()
+    n = A.shape[0]
+    wbytes = lib.ppbo_potrf_workspace_bytes(n)
+    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=A.device)
+    info = ctypes.c_int(0)
+    rc = check(lib.ppbo_potrf_lower(_p(A), A.stride(0), n, _p(ws), wbytes, ctypes.byref(info), _stream()), "ppbo_potrf_lower")
+    return rc, ws
+
+
+def trsm_right_lower(L, ws, X):
+    """X[nrhs x n] <- X L^-T in place"""
+    lib = _lib.load()
+    n = L.shape[0]
+    check(lib.ppbo_trsm_right_lower(_p(L), L.stride(0), n, _p(X), X.stride(0), X.shape[0], 0, _p(ws),
+                                    lib.ppbo_potrf_workspace_bytes(n), _stream()), "ppbo_trsm_right_lower")
+    return X
+
+
+def gemv(A, x):
+    y = torch.empty(A.shape[0], dtype=F64, device=A.device)
+    check(_lib.load().ppbo_gemv(_p(A), A.stride(0), A.shape[0], A.shape[1], _p(x), _p(y), _stream()), "ppbo_gemv")
+    return y
+
+
+# ------------------------------------------------------------------------------------------- K4
+def predict(kernel, X, lengthscales, sigma_f, shrinkage, fit, Xp, P, batch, want_cov=True):
+    lib = _lib.load()
+    N, D = X.shape
+    dev = X.device
+    mu = torch.empty(P * batch, dtype=F64, device=dev)
+    Sp = torch.empty((batch, P, P), dtype=F64, device=dev) if want_cov else None
+    wbytes = lib.ppbo_predict_workspace_bytes(N, fit.Q, fit.m, P, batch)
+    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev)
+    check(lib.ppbo_predict(_kind(kernel), _p(X), N, D, _ls(lengthscales, D), float(sigma_f), float(shrinkage), fit.Q, fit.m,
+                           _p(fit.alpha), _p(fit.arrow), _p(fit.Lfac), _p(fit.neg_corr), fit.n_neg, _p(Xp), P, batch,
+                           _p(mu), _p(Sp), _p(ws), wbytes, _stream()), "ppbo_predict")
+    return mu.view(batch, P), Sp
+
+
+def mvn_rowmax(Z, Fac, mu):
+    """Z: [B,S,K], Fac: [B,P,K], mu: [B,P] -> fmax [B,S], arg [B,S] (int32)"""
+    B, S, K = Z.shape
+    P = Fac.shape[1]
+    fmax = torch.empty((B, S), dtype=F64, device=Z.device)
+    arg = torch.empty((B, S), dtype=torch.int32, device=Z.device)
+    check(_lib.load().ppbo_mvn_rowmax(_p(Z), Z.stride(1), Z.stride(0), _p(Fac), Fac.stride(1), Fac.stride(0), _p(mu),
+                                      mu.stride(0), S, P, K, B, _p(fmax), _p(arg), _stream()), "ppbo_mvn_rowmax")
+    return fmax, arg
+
+
+def acq_reduce(fmax, mustar):
+    B, S = fmax.shape
+    out = torch.empty((B, 3), dtype=F64, device=fmax.device)
+    check(_lib.load().ppbo_acq_reduce(_p(fmax), S, B, float(mustar), _p(out), _stream()), "ppbo_acq_reduce")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- K3
+def rff_features(W, b, X, sigma_f, feature_major):
+    F, D = W.shape
+    n = X.shape[0]
+    out = torch.empty((F, n) if feature_major else (n, F), dtype=F64, device=W.device)
+    check(_lib.load().ppbo_rff_features(_p(W), _p(b), F, D, _p(X), n, float(sigma_f), _p(out), out.stride(0),
+                                        1 if feature_major else 0, _stream()), "ppbo_rff_features")
+    return out
+
+
+def rff_jacobian(W, b, x, sigma_f):
+    F, D = W.shape
+    J = torch.empty((F, D), dtype=F64, device=W.device)
+    check(_lib.load().ppbo_rff_jacobian(_p(W), _p(b), F, D, _p(x), float(sigma_f), _p(J), _stream()), "ppbo_rff_jacobian")
+    return J
+
+
+def _rff_ws(F, Q, m, dev):
+    wbytes = _lib.load().ppbo_rff_workspace_bytes(F, Q, m)
+    return torch.empty(wbytes // 8 + 1, dtype=F64, device=dev), wbytes
+
+
+def rff_objective(Phi_X, Q, m, sigma, omega, want_S=True, want_grad=True, want_hess=True):
+    F = Phi_X.shape[0]
+    ws, wbytes = _rff_ws(F, Q, m, Phi_X.device)
+    S = ctypes.c_double(0.0)
+    grad = torch.empty(F, dtype=F64, device=Phi_X.device) if want_grad else None
+    hd = torch.empty(F, dtype=F64, device=Phi_X.device) if want_hess else None
+    check(_lib.load().ppbo_rff_objective(_p(Phi_X), Phi_X.stride(0), F, Q, m, float(sigma), _p(omega),
+                                         ctypes.byref(S) if want_S else None, _p(grad), _p(hd), _p(ws), wbytes, _stream()),
+          "ppbo_rff_objective")
+    return (S.value if want_S else None), grad, hd
+
+
+def rff_fit(Phi_X, Q, m, sigma, omega0=None, max_iter=100, tol=1e-10):
+    F = Phi_X.shape[0]
+    ws, wbytes = _rff_ws(F, Q, m, Phi_X.device)
+    omega = torch.empty(F, dtype=F64, device=Phi_X.device)
+    hd = torch.empty(F, dtype=F64, device=Phi_X.device)
+    stats = (ctypes.c_double * 4)()
+    rc = check(_lib.load().ppbo_rff_fit(_p(Phi_X), Phi_X.stride(0), F, Q, m, float(sigma), _p(omega0), int(max_iter),
+                                        float(tol), _p(omega), _p(hd), _p(ws), wbytes, stats, _stream()), "ppbo_rff_fit")
+    return omega, hd, dict(iterations=int(stats[0]), last_rel_step=stats[1], S=stats[2], info=rc)
+
+
+def rff_eval_argmax(Omega, PhiT_grid, want_full=False):
+    """Omega [S,F]; PhiT_grid [B,P,F] -> fmax [B,S], arg [B,S], optional dense Fs [B,S,P]"""
+    S, F = Omega.shape
+    B, P, _ = PhiT_grid.shape
+    fmax = torch.empty((B, S), dtype=F64, device=Omega.device)
+    arg = torch.empty((B, S), dtype=torch.int32, device=Omega.device)
+    full = torch.empty((B, S, P), dtype=F64, device=Omega.device) if want_full else None
+    check(_lib.load().ppbo_rff_eval_argmax(_p(Omega), Omega.stride(0), S, F, _p(PhiT_grid), PhiT_grid.stride(1),
+                                           PhiT_grid.stride(0), P, B, _p(fmax), _p(arg), _p(full), _stream()),
+          "ppbo_rff_eval_argmax")
+    return fmax, arg, full

@@ -1,0 +1,262 @@
+"""GPU parity tests (run with -m gpu on the B200): every C-ABI entry point against the CPU oracle and against the
+golden vectors recorded from the executed reference.  Tolerances follow BASELINE.json's north_star:
+kernel matrix 1e-10 relative, Laplace mode / posterior mean / variance 1e-6 relative, arg-max indices identical."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from ppbo_b200 import ops as _ops
+    return _ops
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _ls(g):
+    return g["theta"][1]
+
+
+# ----------------------------------------------------------------------------------------------- K1
+def test_kernel_matrix_vs_reference(ops, golden):
+    g = golden
+    X = ops.to_dev(g["X"])
+    K = _np(ops.kernel_matrix(g["kernel"], X, X, _ls(g), g["theta"][2]))
+    assert np.max(np.abs(K - g["K_raw"]) / np.abs(g["K_raw"]).clip(1e-300)) < 1e-10      # element-wise relative
+    Kc = _np(ops.kernel_matrix(g["kernel"], X, ops.to_dev(g["pred_grid"]), _ls(g), g["theta"][2]))
+    assert np.max(np.abs(Kc - g["K_cross"]) / np.abs(g["K_cross"]).clip(1e-300)) < 1e-10
+    S = _np(ops.gram_regularized(g["kernel"], X, _ls(g), g["theta"][2], 1e-6))
+    assert relerr(S, g["Sigma"]) < 1e-10                                                  # max-norm (SVD round trip)
+
+
+def test_kernel_matrix_ragged_and_empty(ops):
+    from oracle import ppbo_oracle as O
+    rng = np.random.RandomState(0)
+    for n1, n2, D in ((1, 1, 1), (3, 257, 5), (130, 1, 20), (67, 129, 64), (0, 5, 3)):
+        X1, X2 = rng.rand(n1, D), rng.rand(n2, D)
+        K = _np(ops.kernel_matrix("SE_kernel", ops.to_dev(X1), ops.to_dev(X2), 0.3, 0.7))
+        assert K.shape == (n1, n2)
+        if n1:
+            assert relerr(K, O.se_kernel(X1, X2, [0, 0.3, 0.7])) < 1e-12
+
+
+def test_se_kernel_ard_and_gradients(ops):
+    """ARD generalises the reference's isotropic kernel; gradients are checked by finite differences of the oracle."""
+    from oracle import ppbo_oracle as O
+    rng = np.random.RandomState(1)
+    X1, X2 = rng.rand(40, 4), rng.rand(33, 4)
+    ls = np.array([0.2, 0.35, 0.5, 0.8])
+    sf = 0.6
+    K = _np(ops.kernel_matrix("SE_kernel", ops.to_dev(X1), ops.to_dev(X2), ls, sf))
+    Kref = O.se_kernel(X1 / ls, X2 / ls, [0, 1.0, sf])
+    assert relerr(K, Kref) < 1e-12
+    dK = _np(ops.kernel_se_grad(ops.to_dev(X1), ops.to_dev(X2), ls, sf))
+    eps = 1e-6
+    for d in range(4):
+        lp, lm = ls.copy(), ls.copy()
+        lp[d] *= np.exp(eps)
+        lm[d] *= np.exp(-eps)
+        fd = (O.se_kernel(X1 / lp, X2 / lp, [0, 1.0, sf]) - O.se_kernel(X1 / lm, X2 / lm, [0, 1.0, sf])) / (2 * eps)
+        assert np.abs(dK[d] - fd).max() < 1e-8 * sf ** 2
+    assert relerr(dK[4], 2 * Kref) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------- linear algebra
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (70, 70, 70), (129, 65, 33), (300, 257, 1000), (1400, 70, 175), (64, 513, 17)])
+def test_gemm_nt(ops, M, N, K):
+    rng = np.random.RandomState(M + N + K)
+    A, B, C = rng.randn(M, K), rng.randn(N, K), rng.randn(M, N)
+    out = _np(ops.gemm_nt(ops.to_dev(A), ops.to_dev(B), ops.to_dev(C), alpha=-0.5, beta=2.0))
+    ref = -0.5 * A @ B.T + 2.0 * C
+    assert np.abs(out - ref).max() <= 1e-13 * K * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n", [1, 5, 128, 129, 300, 777])
+def test_potrf_and_trsm(ops, n):
+    rng = np.random.RandomState(n)
+    A0 = rng.randn(n, n)
+    A = A0 @ A0.T + n * np.eye(n)
+    Ad = ops.to_dev(A)
+    info, ws = ops.potrf_lower(Ad)
+    assert info == 0
+    L = np.tril(_np(Ad))
+    assert relerr(L @ L.T, A) < 1e-13
+    X = rng.randn(37, n)
+    Y = _np(ops.trsm_right_lower(Ad, ws, ops.to_dev(X)))
+    assert relerr(Y @ L.T, X) < 1e-11
+
+
+def test_potrf_reports_bad_pivot(ops):
+    A = np.eye(200)
+    A[150, 150] = -1.0
+    info, _ = ops.potrf_lower(ops.to_dev(A))
+    assert info == 151
+
+
+def test_gemv(ops):
+    rng = np.random.RandomState(3)
+    for M, N in ((1, 1), (77, 131), (500, 64)):
+        A, x = rng.randn(M, N), rng.randn(N)
+        assert relerr(_np(ops.gemv(ops.to_dev(A), ops.to_dev(x))), A @ x) < 1e-13
+
+
+# ----------------------------------------------------------------------------------------------- K2
+def test_likelihood_terms(ops, golden):
+    from oracle import ppbo_oracle as O
+    g = golden
+    Q, m, sigma = g["Q"], g["m"], g["theta"][0]
+    for f in (g["f_initial"], g["fMAP"]):
+        s, beta, arrow = ops.lik_terms(ops.to_dev(f), Q, m, sigma)
+        assert abs(float(s) - O.sum_phi(f, Q, m, sigma, 0).sum()) <= 1e-12 * Q * m
+        assert relerr(_np(beta), O.lik_beta(f, Q, m, sigma)) < 1e-12
+        a_ref = O.arrow_coeffs(f, Q, m, sigma).ravel()
+        assert np.abs(_np(arrow) - a_ref).max() <= 1e-12 * max(np.abs(a_ref).max(), 1e-300)
+        Lam = _np(ops.lambda_dense(arrow, Q, m))
+        assert np.abs(Lam - O.create_Lambda(f, Q, m, sigma)).max() <= 1e-12 * max(np.abs(a_ref).max(), 1e-300)
+    # golden: the reference's own Lambda rows at the mode
+    _, _, arrow = ops.lik_terms(ops.to_dev(g["fMAP"]), Q, m, sigma)
+    Lam = _np(ops.lambda_dense(arrow, Q, m))
+    rows = np.array([Lam[i, i:i + m + 1] for i in g["obs_indices"]])
+    assert relerr(rows, g["Lambda_MAP_rows"]) < 1e-10
+
+
+@pytest.mark.parametrize("start", ["zero", "reference_start"])
+def test_laplace_mode(ops, golden, start):
+    """1e-6 yard-stick: the tight stationary point of the reference's own T (oracle.fmap_tight).  The reference's
+    recorded fMAP stops at |grad| < 1e-4 and is only ~1e-6..1e-5 accurate itself, so against it we
+    require (a) agreement within that slack and (b) that our mode has a smaller gradient under the reference's formula."""
+    from oracle import ppbo_oracle as O
+    g = golden
+    Q, m, sigma = g["Q"], g["m"], g["theta"][0]
+    Sigma = ops.to_dev(g["Sigma"])
+    f0 = None if start == "zero" else ops.to_dev(g["f_initial"])
+    fit = ops.laplace_fit(Sigma, Q, m, sigma, f_init=f0)
+    assert fit.info == 0
+    f = _np(fit.f_map)
+    f_tight = O.fmap_tight(g["Sigma"], Q, m, sigma, g["fMAP"])
+    scale = np.abs(f_tight).max()
+    assert np.abs(f - f_tight).max() <= 1e-6 * scale
+    assert np.abs(f - g["fMAP"]).max() <= 1e-4 * scale
+    gn = np.linalg.norm(O.T_grad(f, g["Sigma_inv"], Q, m, sigma))
+    assert gn <= max(np.linalg.norm(g["T_grad_map"]), 1e-6)
+    # alpha = Sigma^-1 f_map without ever forming Sigma^-1
+    assert relerr(g["Sigma"] @ _np(fit.alpha), f) < 1e-9
+    assert fit.stats["iterations"] <= 40
+
+
+# ----------------------------------------------------------------------------------------------- K4
+def test_prediction_vs_reference(ops, golden):
+    g = golden
+    Q, m, sigma = g["Q"], g["m"], g["theta"][0]
+    X = ops.to_dev(g["X"])
+    Sigma = ops.gram_regularized(g["kernel"], X, _ls(g), g["theta"][2], 1e-6)
+    fit = ops.laplace_fit(Sigma, Q, m, sigma)
+    P = g["pred_grid"].shape[0]
+    mu, Sp = ops.predict(g["kernel"], X, _ls(g), g["theta"][2], 1e-6, fit, ops.to_dev(g["pred_grid"]), P, 1)
+    sf2 = g["theta"][2] ** 2
+    # posterior mean: 1e-6 relative (max-norm); the reference's own value carries its 1e-4 gradient slack
+    assert relerr(_np(mu)[0], g["pred_mu"]) < 2e-5
+    # posterior (co)variance: relative to the prior variance sigma_f^2 (a cancellation)
+    assert np.abs(_np(Sp)[0] - g["pred_Sigma"]).max() <= 2e-5 * sf2
+
+
+def test_prediction_vs_tight_oracle(ops, golden):
+    """Same comparison with the reference's slack removed: oracle posterior at the tight mode, 1e-6."""
+    from oracle import ppbo_oracle as O
+    g = golden
+    Q, m, sigma = g["Q"], g["m"], g["theta"][0]
+    kern = O.KERNELS[g["kernel"]]
+    f_tight = O.fmap_tight(g["Sigma"], Q, m, sigma, g["fMAP"])
+    _, _, post = O.posterior_covariance(g["Sigma_inv"], f_tight, Q, m, sigma)
+    mu_o, Sp_o = O.mu_Sigma_pred(g["X"], g["pred_grid"], g["theta"], kern, g["Sigma_inv"], f_tight, post)
+    X = ops.to_dev(g["X"])
+    fit = ops.laplace_fit(ops.to_dev(g["Sigma"]), Q, m, sigma)
+    P = g["pred_grid"].shape[0]
+    mu, Sp = ops.predict(g["kernel"], X, _ls(g), g["theta"][2], 1e-6, fit, ops.to_dev(g["pred_grid"]), P, 1)
+    assert relerr(_np(mu)[0], mu_o) < 1e-6
+    assert np.abs(_np(Sp)[0] - Sp_o).max() <= 1e-6 * g["theta"][2] ** 2
+
+
+def test_prediction_batched_grids(ops, golden):
+    g = golden
+    Q, m, sigma = g["Q"], g["m"], g["theta"][0]
+    X = ops.to_dev(g["X"])
+    fit = ops.laplace_fit(ops.to_dev(g["Sigma"]), Q, m, sigma)
+    rng = np.random.RandomState(5)
+    B, P = 3, 33
+    grids = rng.rand(B * P, g["D"])
+    mu_b, Sp_b = ops.predict(g["kernel"], X, _ls(g), g["theta"][2], 1e-6, fit, ops.to_dev(grids), P, B)
+    for b in range(B):
+        mu1, Sp1 = ops.predict(g["kernel"], X, _ls(g), g["theta"][2], 1e-6, fit, ops.to_dev(grids[b * P:(b + 1) * P]), P, 1)
+        assert np.array_equal(_np(mu_b)[b], _np(mu1)[0])
+        assert np.abs(_np(Sp_b)[b] - _np(Sp1)[0]).max() <= 1e-13 * g["theta"][2] ** 2
+
+
+@pytest.mark.parametrize("B,S,P,K", [(1, 150, 70, 70), (3, 257, 70, 70), (2, 1000, 130, 64), (1, 1, 1, 1)])
+def test_mvn_rowmax(ops, B, S, P, K):
+    rng = np.random.RandomState(S + P)
+    Z, Fac, mu = rng.randn(B, S, K), rng.randn(B, P, K), rng.randn(B, P)
+    fmax, arg = ops.mvn_rowmax(ops.to_dev(Z), ops.to_dev(Fac), ops.to_dev(mu))
+    ref = np.einsum("bsk,bpk->bsp", Z, Fac) + mu[:, None, :]
+    assert np.array_equal(_np(arg), ref.argmax(axis=2))
+    assert np.abs(_np(fmax) - ref.max(axis=2)).max() <= 1e-13 * K * np.abs(ref).max()
+    red = _np(ops.acq_reduce(fmax, 0.1))
+    fm = ref.max(axis=2)
+    assert relerr(red[:, 0], np.maximum(fm - 0.1, 0).sum(axis=1)) < 1e-12
+    assert relerr(red[:, 1], fm.sum(axis=1)) < 1e-12
+    assert relerr(red[:, 2], (fm ** 2).sum(axis=1)) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------- K3
+def test_rff_vs_reference(ops, golden):
+    g = golden
+    if "rff_W" not in g:
+        pytest.skip("RFF basis exists for the SE kernel only")
+    Q, m, sigma, sf = g["Q"], g["m"], g["theta"][0], g["theta"][2]
+    W, b, X = ops.to_dev(g["rff_W"]), ops.to_dev(g["rff_b"]), ops.to_dev(g["X"])
+    Phi = ops.rff_features(W, b, X, sf, feature_major=True)
+    assert relerr(_np(Phi), g["rff_phi_X"]) < 1e-12
+    PhiT = ops.rff_features(W, b, X, sf, feature_major=False)
+    assert np.array_equal(_np(PhiT), _np(Phi).T)
+    assert relerr(_np(ops.rff_jacobian(W, b, ops.to_dev(g["xstar"]), sf)), g["rff_Dphi_xstar"]) < 1e-12
+    S, grad, hd = ops.rff_objective(Phi, Q, m, sigma, ops.to_dev(g["rff_omega_probe"]))
+    assert abs(S - float(g["rff_S_probe"])) <= 1e-12 * abs(float(g["rff_S_probe"]))
+    assert relerr(_np(grad), g["rff_S_grad_probe"]) < 1e-11
+    assert relerr(_np(hd), g["rff_S_hess_diag_probe"]) < 1e-11
+    # batched function evaluation + per-sample arg-max: identical indices, values to 1e-12
+    grid = ops.rff_features(W, b, ops.to_dev(g["rff_grid"]), sf, feature_major=False)[None]
+    fmax, arg, full = ops.rff_eval_argmax(ops.to_dev(g["rff_Omega"]), grid, want_full=True)
+    assert np.array_equal(_np(arg)[0], g["rff_argmax"])
+    assert relerr(_np(fmax)[0], g["rff_max"]) < 1e-12
+    assert relerr(_np(full)[0], g["rff_Fs"]) < 1e-12
+
+
+def test_rff_map(ops, golden):
+    from oracle import ppbo_oracle as O
+    g = golden
+    if "rff_W" not in g:
+        pytest.skip("RFF basis exists for the SE kernel only")
+    Q, m, sigma, sf = g["Q"], g["m"], g["theta"][0], g["theta"][2]
+    Phi = ops.rff_features(ops.to_dev(g["rff_W"]), ops.to_dev(g["rff_b"]), ops.to_dev(g["X"]), sf, feature_major=True)
+    omega, hd, stats = ops.rff_fit(Phi, Q, m, sigma, omega0=ops.to_dev(g["rff_omega0"]))
+    w = _np(omega)
+    # the optimum is defined by grad S = 0: compare with the oracle driven tight from the reference's own optimum
+    w_tight, _ = O.rff_omega_map(g["rff_phi_X"], Q, m, sigma, g["rff_omega_MAP"], gtol=1e-11)
+    scale = np.abs(w_tight).max()
+    assert np.abs(w - w_tight).max() <= 1e-6 * scale
+    assert np.abs(w - g["rff_omega_MAP"]).max() <= 1e-3 * scale     # reference stops at |grad| < 1e-4
+    gn = np.linalg.norm(O.rff_S_grad(w, g["rff_phi_X"], Q, m, sigma))
+    assert gn <= max(np.linalg.norm(O.rff_S_grad(g["rff_omega_MAP"], g["rff_phi_X"], Q, m, sigma)), 1e-8)
+    cov = 1.0 / (-_np(hd))
+    assert relerr(cov, 1.0 / (-O.rff_S_hess_diag(w, g["rff_phi_X"], Q, m, sigma))) < 1e-10
+    assert relerr(cov, g["rff_cov_diag"]) < 1e-3
