@@ -25,6 +25,8 @@ int ppbo_version(void);
 const char* ppbo_last_error(void);
 /* device properties the host layer reports (SM count etc.); dev = CUDA ordinal */
 int ppbo_device_sm_count(int dev);
+/* number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches) */
+long long ppbo_launch_count(void);
 
 /* ---- K1: covariance matrices -------------------------------------------------------------------- */
 /* out[n1 x n2] = k(X1_i, X2_j).  Replaces kernels.SE_kernel / RQ_kernel / camphor_copper_kernel and
@@ -83,6 +85,9 @@ int ppbo_potrf_lower(double* A, long long lda, int n, void* workspace, long long
 /* X[nrhs x n] (row-major, one right-hand side per ROW) <- X . L^-T (trans=0)  or  X . L^-1 (trans=1) */
 int ppbo_trsm_right_lower(const double* L, long long ldl, int n, double* X, long long ldx, int nrhs, int trans,
                           void* workspace, long long workspace_bytes, void* stream);
+/* x <- (L L^T)^-1 x for one right-hand side; x must have room for n + 128 doubles (scratch tail).  Replaces cho_solve
+ * under scipy's trust-exact (src/gp_model.py:382-384). */
+int ppbo_potrs_vec(const double* L, long long ldl, int n, double* x, void* workspace, long long workspace_bytes, void* stream);
 /* y = A x for row-major A[M x N] */
 int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, double* y, void* stream);
 
@@ -112,6 +117,11 @@ int ppbo_mvn_rowmax(const double* Z, long long ldz, long long strideZ, const dou
 /* per batch entry: out[b][0] = sum_s max(fmax-mustar,0), out[b][1] = sum_s fmax, out[b][2] = sum_s fmax^2
  * (EI: src/acquisition.py:80-81; varmax: :178).  Deterministic fixed-order reduction. */
 int ppbo_acq_reduce(const double* fmax, int S, int batch, double mustar, double* out, void* stream);
+/* same with mu* read from device memory (no host round trip between the mu* search and the reduction) */
+int ppbo_acq_reduce_dev(const double* fmax, int S, int batch, const double* mustar_dev, double* out, void* stream);
+/* out[0] = max_i x[i] (accumulate != 0: also over the previous out[0]).  Batched candidate form of the max the reference's
+ * GPModel.mu_star looks for (src/gp_model.py:415-437): mu* over a set of candidate points. */
+int ppbo_vec_max(const double* x, long long n, int accumulate, double* out, void* stream);
 
 /* ---- K3: random Fourier features ------------------------------------------------------------------ */
 /* sqrt(2 sigma_f^2 / F) cos(W X^T + b).  feature_major = 1: Phi[F x n] (the reference's layout, used for the
@@ -136,6 +146,17 @@ int ppbo_rff_objective(const double* Phi_X, long long ld, int F, int Q, int m, d
 int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega0,
                  int max_iter, double tol, double* omega_map, double* hess_diag, void* workspace,
                  long long workspace_bytes, double* stats_h, void* stream);
+/* out[i] = standard normal number (offset + i) of Philox4x32-10 stream `stream_id` under `seed` (Box-Muller on 53-bit uniforms).
+ * Counter-based: the value of a given index does not depend on launch shape or on which GPU draws it.  Replaces the host
+ * np.random draws of the reference where the caller does not inject its own (oracle: oracle/ppbo_oracle.py philox_normals). */
+int ppbo_normal_fill(unsigned long long seed, unsigned int stream_id, long long offset, double* out, long long n, void* stream);
+/* Omega[s][f] = omega_map[f] + z[s][f] / sqrt(-hess_diag[f]): S posterior weight draws from the diagonal Laplace covariance
+ * (Hsampler.update_covariancematrix + sample_omega, src/random_fourier_sampler.py:134-137,207-213).  Z[S x F] are injected
+ * standard normals (parity tests); Z == NULL draws z[s][f] as normal number (sample0 + s) * F + f of the Philox stream, so
+ * shards of the sample range over several GPUs reproduce the single-GPU draw exactly. */
+int ppbo_rff_sample_omega(const double* omega_map, const double* hess_diag, const double* Z, long long ldz,
+                          unsigned long long seed, unsigned int stream_id, long long sample0, int S, int F, double* Omega,
+                          long long ldo, void* stream);
 /* Fs = Omega[S x F] . PhiT_grid[P x F]^T per batch entry (grid), fused per-sample max / first arg-max over P
  * (batched form of the objective in Hsampler.return_xstar, src/random_fourier_sampler.py:166,170).
  * Fs_full (optional, tests only): dense [batch][S x P]. */

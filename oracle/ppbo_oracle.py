@@ -322,3 +322,42 @@ def rff_eval_argmax(Omega, Phi_grid):
     Fs = Omega @ Phi_grid
     idx = np.argmax(Fs, axis=1)
     return Fs[np.arange(Fs.shape[0]), idx], idx.astype(np.int32)
+
+
+# --------------------------------------------------------------------------- device RNG (not in the reference)
+def philox4x32_10(counter, key):
+    """Philox4x32-10 of Salmon, Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3" (SC'11), the
+    published algorithm (Random123 v1.x constants).  counter: (n, 4) uint32, key: (2,) uint32 -> (n, 4) uint32.
+    The reference draws from numpy's global MT19937; this generator only backs the CUDA path's own draws when the
+    caller does not inject normals, so its oracle is the published algorithm (known-answer vectors in the tests)."""
+    c = np.array(counter, dtype=np.uint64).reshape(-1, 4)
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c.astype(np.uint32)
+
+
+def philox_normals(seed, stream_id, offset, n):
+    """Standard normals offset .. offset+n-1 of the stream: counter i = (i_lo, i_hi, stream_id, 0) yields numbers 2i, 2i+1 by
+    Box-Muller on two 53-bit uniforms u = ((a >> 5) 2^26 + (b >> 6) + 1/2) 2^-53."""
+    first, last = offset // 2, (offset + n - 1) // 2
+    idx = np.arange(first, last + 1, dtype=np.uint64)
+    ctr = np.stack([idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32), np.full_like(idx, stream_id), np.zeros_like(idx)], axis=1)
+    r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).astype(np.float64)
+    u1 = (np.floor(r[:, 0] / 32) * 67108864.0 + np.floor(r[:, 1] / 64) + 0.5) / 9007199254740992.0
+    u2 = (np.floor(r[:, 2] / 32) * 67108864.0 + np.floor(r[:, 3] / 64) + 0.5) / 9007199254740992.0
+    rad = np.sqrt(-2.0 * np.log(u1))
+    z = np.stack([rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)], axis=1).ravel()
+    return z[offset - 2 * first: offset - 2 * first + n]
+
+
+def rff_sample_omega(omega_map, hess_diag, Z):
+    """src/random_fourier_sampler.py:134-137,207-213 with the (diagonal) Laplace covariance 1 / -hess_diag and injected
+    standard normals Z [S x F]."""
+    return np.asarray(omega_map)[None, :] + np.asarray(Z) / np.sqrt(-np.asarray(hess_diag))[None, :]

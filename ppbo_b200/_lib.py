@@ -5,7 +5,7 @@ PyTorch is used only for device memory, streams and torch.distributed (plumbing)
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_uint, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libppbo_b200.so")
@@ -26,6 +26,7 @@ _SIGNATURES = {
     "ppbo_version": (_I, []),
     "ppbo_last_error": (c_char_p, []),
     "ppbo_device_sm_count": (_I, [_I]),
+    "ppbo_launch_count": (_L, []),
     "ppbo_kernel_matrix": (_I, [_I, _P, _I, _P, _I, _I, _PD, _D, _P, _L, _P]),
     "ppbo_gram_regularized": (_I, [_I, _P, _I, _I, _PD, _D, _D, _P, _L, _P]),
     "ppbo_kernel_se_grad": (_I, [_P, _I, _P, _I, _I, _PD, _D, _P, _L, _L, _P]),
@@ -39,6 +40,7 @@ _SIGNATURES = {
     "ppbo_potrf_workspace_bytes": (_L, [_I]),
     "ppbo_potrf_lower": (_I, [_P, _L, _I, _P, _L, _PI, _P]),
     "ppbo_trsm_right_lower": (_I, [_P, _L, _I, _P, _L, _I, _I, _P, _L, _P]),
+    "ppbo_potrs_vec": (_I, [_P, _L, _I, _P, _P, _L, _P]),
     "ppbo_gemv": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "ppbo_neg_count": (_I, [_P, _I, _PI, _I, _P]),
     "ppbo_neg_corr_doubles": (_L, [_I, _I]),
@@ -47,11 +49,15 @@ _SIGNATURES = {
     "ppbo_predict": (_I, [_I, _P, _I, _I, _PD, _D, _D, _I, _I, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _L, _P]),
     "ppbo_mvn_rowmax": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P]),
     "ppbo_acq_reduce": (_I, [_P, _I, _I, _D, _P, _P]),
+    "ppbo_acq_reduce_dev": (_I, [_P, _I, _I, _P, _P, _P]),
+    "ppbo_vec_max": (_I, [_P, _L, _I, _P, _P]),
     "ppbo_rff_features": (_I, [_P, _P, _I, _I, _P, _I, _D, _P, _L, _I, _P]),
     "ppbo_rff_jacobian": (_I, [_P, _P, _I, _I, _P, _D, _P, _P]),
     "ppbo_rff_workspace_bytes": (_L, [_I, _I, _I]),
     "ppbo_rff_objective": (_I, [_P, _L, _I, _I, _I, _D, _P, _PD, _P, _P, _P, _L, _P]),
     "ppbo_rff_fit": (_I, [_P, _L, _I, _I, _I, _D, _P, _I, _D, _P, _P, _P, _L, _PD, _P]),
+    "ppbo_normal_fill": (_I, [c_ulonglong, c_uint, _L, _P, _L, _P]),
+    "ppbo_rff_sample_omega": (_I, [_P, _P, _P, _L, c_ulonglong, c_uint, _L, _I, _I, _P, _L, _P]),
     "ppbo_rff_eval_argmax": (_I, [_P, _L, _I, _I, _P, _L, _L, _I, _I, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

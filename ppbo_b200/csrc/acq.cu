@@ -2,6 +2,7 @@
 // Replaces GPModel.mu_Sigma_pred (src/gp_model.py:441-452), the sampling loops of acquisition.EI / varmax
 // (src/acquisition.py:72-81,170-178) and Hsampler.phiVec/phi/Dphi/S/S_grad/S_hessian and its function
 // evaluations (src/random_fourier_sampler.py:45-53,106-122,166,170).
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -60,8 +61,9 @@ __global__ void neg_rows_kernel(const double* __restrict__ G, long long ldg, int
 // out[b] = { sum max(fmax - mustar, 0), sum fmax, sum fmax^2 (centred on the first sample for stability is NOT used:
 // plain sums in a fixed order, the host forms mean / variance) }
 __global__ void __launch_bounds__(1024) acq_reduce_kernel(const double* __restrict__ fm, int S, double mustar,
-                                                          double* __restrict__ out) {
+                                                          const double* __restrict__ mustar_dev, double* __restrict__ out) {
     __shared__ double red[33];
+    if (mustar_dev) mustar = mustar_dev[0];
     const double* x = fm + (long long)blockIdx.x * S;
     double s0 = 0, s1 = 0, s2 = 0;
     for (int i = threadIdx.x; i < S; i += 1024) {
@@ -77,6 +79,21 @@ __global__ void __launch_bounds__(1024) acq_reduce_kernel(const double* __restri
         out[blockIdx.x * 3 + 0] = s0;
         out[blockIdx.x * 3 + 1] = s1;
         out[blockIdx.x * 3 + 2] = s2;
+    }
+}
+
+// out[0] = max(init, max_i x[i]) with init = out[0] if `accumulate` (single CTA; used for mu* over candidate points)
+__global__ void __launch_bounds__(1024) vec_max_kernel(const double* __restrict__ x, long long n, int accumulate,
+                                                       double* __restrict__ out) {
+    __shared__ double mx[32];
+    double v = accumulate ? out[0] : -INFINITY;
+    for (long long i = threadIdx.x; i < n; i += 1024) v = fmax(v, x[i]);
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) mx[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) v = fmax(v, mx[w]);
+        out[0] = v;
     }
 }
 
@@ -239,7 +256,7 @@ extern "C" int ppbo_neg_corr_build(const double* G, int M, const double* arrow, 
     double* Rdinv = R + (long long)r * r;
     int* info_d = reinterpret_cast<int*>(neg_corr + ppbo_neg_corr_doubles(M, r) - 1);
     PPBO_CUDA_CHECK(cudaMemcpyAsync(idx, idx_h, sizeof(int) * r, cudaMemcpyHostToDevice, st));
-    neg_rows_kernel<<<dim3(ceil_div(M, 256), r), 256, 0, st>>>(G, M, M, arrow, idx, r, Ht, R, r);
+    PPBO_CL neg_rows_kernel<<<dim3(ceil_div(M, 256), r), 256, 0, st>>>(G, M, M, arrow, idx, r, Ht, R, r);
     PPBO_LAUNCH_CHECK();
     int rc = trsm_right_lower_t(Lfac, M, M, Lfac + (long long)M * M, Ht, M, r, st);   // Ht <- Ht L^-T
     if (rc) return rc;
@@ -276,7 +293,7 @@ extern "C" int ppbo_predict(int kind, const double* X, int N, int D, const doubl
     if ((rc = kernel_matrix_raw(kind, Xp, PT, X, N, D, lengthscales_h, sigma_f, 1.0, 0.0, Kc, N, st))) return rc;
     if (mu && (rc = gemv(Kc, N, PT, N, alpha, mu, st))) return rc;
     if (!Sigma_p) return PPBO_OK;
-    pred_diff_kernel<<<dim3(ceil_div(M, 256), PT), 256, 0, st>>>(Kc, N, PT, Q, m, arrow, Ut, M);
+    PPBO_CL pred_diff_kernel<<<dim3(ceil_div(M, 256), PT), 256, 0, st>>>(Kc, N, PT, Q, m, arrow, Ut, M);
     PPBO_LAUNCH_CHECK();
     if ((rc = trsm_right_lower_t(Lfac, M, M, Lfac + (long long)M * M, Ut, M, PT, st))) return rc;   // Yt = Ut L^-T
     for (int b = 0; b < batch; ++b) {     // reg(K**) per grid (diagonal shrinkage needs the square form)
@@ -296,7 +313,7 @@ extern "C" int ppbo_predict(int kind, const double* X, int N, int D, const doubl
         const int* idx = reinterpret_cast<const int*>(neg_corr);
         const double* Ht = neg_corr + (r + 1) / 2;
         const double* R = Ht + (long long)r * M;
-        pred_negdiff_kernel<<<dim3(ceil_div(r, 128), PT), 128, 0, st>>>(Kc, N, PT, m, idx, r, Ud, r);
+        PPBO_CL pred_negdiff_kernel<<<dim3(ceil_div(r, 128), PT), 128, 0, st>>>(Kc, N, PT, m, idx, r, Ud, r);
         PPBO_LAUNCH_CHECK();
         GemmOperands g1{Ut, M, 0, Ht, M, 0, PT, r, M};
         StoreEpilogue e1{Ud, r, 0, -1.0, 1.0, 0, 0, 0};                                             // z = Ud - Yt Ht^T
@@ -320,7 +337,21 @@ extern "C" int ppbo_mvn_rowmax(const double* Z, long long ldz, long long strideZ
 
 extern "C" int ppbo_acq_reduce(const double* fmax, int S, int batch, double mustar, double* out, void* stream) {
     PPBO_REQUIRE(S >= 1 && batch >= 1, "shape");
-    acq_reduce_kernel<<<batch, 1024, 0, (cudaStream_t)stream>>>(fmax, S, mustar, out);
+    PPBO_CL acq_reduce_kernel<<<batch, 1024, 0, (cudaStream_t)stream>>>(fmax, S, mustar, nullptr, out);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_acq_reduce_dev(const double* fmax, int S, int batch, const double* mustar_dev, double* out, void* stream) {
+    PPBO_REQUIRE(S >= 1 && batch >= 1 && mustar_dev != nullptr, "shape");
+    PPBO_CL acq_reduce_kernel<<<batch, 1024, 0, (cudaStream_t)stream>>>(fmax, S, 0.0, mustar_dev, out);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_vec_max(const double* x, long long n, int accumulate, double* out, void* stream) {
+    PPBO_REQUIRE(n >= 0 && out != nullptr, "shape");
+    PPBO_CL vec_max_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, accumulate, out);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -333,7 +364,7 @@ extern "C" int ppbo_rff_features(const double* W, const double* b, int F, int D,
     const double amp = sqrt(2.0 * sigma_f * sigma_f / F);      // src/random_fourier_sampler.py:46
     dim3 grid = feature_major ? dim3(ceil_div(n, 256), F) : dim3(ceil_div(F, 256), n);
     PPBO_REQUIRE(grid.y <= 65535, "too many rows for one launch");
-    rff_features_kernel<<<grid, 256, sizeof(double) * D, (cudaStream_t)stream>>>(W, b, F, D, X, n, amp, Phi, ld, feature_major);
+    PPBO_CL rff_features_kernel<<<grid, 256, sizeof(double) * D, (cudaStream_t)stream>>>(W, b, F, D, X, n, amp, Phi, ld, feature_major);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -341,7 +372,7 @@ extern "C" int ppbo_rff_features(const double* W, const double* b, int F, int D,
 extern "C" int ppbo_rff_jacobian(const double* W, const double* b, int F, int D, const double* x, double sigma_f, double* J,
                                  void* stream) {
     const double amp = sqrt(2.0 * sigma_f * sigma_f / F);
-    rff_jacobian_kernel<<<ceil_div(F, 128), 128, 0, (cudaStream_t)stream>>>(W, b, F, D, x, amp, J);
+    PPBO_CL rff_jacobian_kernel<<<ceil_div(F, 128), 128, 0, (cudaStream_t)stream>>>(W, b, F, D, x, amp, J);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -372,11 +403,11 @@ struct RffWs {
 static int rff_eval(const double* Phi, long long ld, int F, int Q, int m, double sigma, const double* omega, RffWs& ws,
                     double* grad, double* hdiag, bool want_arrow, double* lik_sum_dev, cudaStream_t st) {
     const int N = Q * (m + 1);
-    rff_fvals_kernel<<<ceil_div(N, 256), 256, 0, st>>>(Phi, ld, F, N, omega, ws.fvals);
+    PPBO_CL rff_fvals_kernel<<<ceil_div(N, 256), 256, 0, st>>>(Phi, ld, F, N, omega, ws.fvals);
     launch_lik_terms(ws.fvals, Q, m, sigma, ws.setlik, ws.beta, want_arrow ? ws.arrow : nullptr, nullptr, nullptr, st);
     launch_sum(ws.setlik, Q, lik_sum_dev, st);
     if (grad || hdiag)
-        rff_grad_hess_kernel<<<ceil_div(F, 8), 256, 0, st>>>(Phi, ld, F, Q, m, omega, ws.beta, ws.arrow, grad, hdiag);
+        PPBO_CL rff_grad_hess_kernel<<<ceil_div(F, 8), 256, 0, st>>>(Phi, ld, F, Q, m, omega, ws.beta, ws.arrow, grad, hdiag);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -392,7 +423,7 @@ extern "C" int ppbo_rff_objective(const double* Phi_X, long long ld, int F, int 
     int rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega, ws, grad, hess_diag, true, ws.scal + 8, st);
     if (rc) return rc;
     if (S_out) {
-        rff_scalars_kernel<<<1, 1024, 0, st>>>(omega, nullptr, F, ws.scal);
+        PPBO_CL rff_scalars_kernel<<<1, 1024, 0, st>>>(omega, nullptr, F, ws.scal);
         double h[9];
         PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(h), cudaMemcpyDeviceToHost, st));
         PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -420,15 +451,15 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
     double h[16], S_cur = NAN, last_rel = INFINITY;
     for (it = 0; it < max_iter; ++it) {
         if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, true, ws.scal + 8, st))) return rc;
-        rff_psi_kernel<<<dim3(ceil_div(M, 256), F), 256, 0, st>>>(Phi_X, ld, Q, m, ws.arrow, ws.PsiT, M);
+        PPBO_CL rff_psi_kernel<<<dim3(ceil_div(M, 256), F), 256, 0, st>>>(Phi_X, ld, Q, m, ws.arrow, ws.PsiT, M);
         GemmOperands g{ws.PsiT, M, 0, ws.PsiT, M, 0, F, F, M};
         StoreEpilogue ep{ws.H, F, 0, 1.0, 0.0, 0, 0, 0};
         if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
-        add_identity_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.H, F, F);
+        PPBO_CL add_identity_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.H, F, F);
         if ((rc = potrf_lower(ws.H, F, F, Hdinv, info_d, st))) return rc;
         PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.step, ws.grad, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
         if ((rc = potrs_vec(ws.H, F, F, Hdinv, ws.step, st))) return rc;      // step = (-Hessian)^-1 grad  (ascent direction)
-        rff_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, ws.scal);
+        PPBO_CL rff_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, ws.scal);
         PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
         PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
         PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -438,9 +469,9 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
         double s = 1.0;
         bool ok = false;
         for (int c = 0; c < 12; ++c, s *= 0.5) {
-            axpy_out_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.trial, omega_map, ws.step, s, F);
+            PPBO_CL axpy_out_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.trial, omega_map, ws.step, s, F);
             if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, ws.trial, ws, nullptr, nullptr, false, ws.scal + 8, st))) return rc;
-            rff_scalars_kernel<<<1, 1024, 0, st>>>(ws.trial, nullptr, F, ws.scal);
+            PPBO_CL rff_scalars_kernel<<<1, 1024, 0, st>>>(ws.trial, nullptr, F, ws.scal);
             PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
             PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
             const double S_try = h[0] - h[8] / m;
@@ -465,4 +496,111 @@ extern "C" int ppbo_rff_eval_argmax(const double* Omega, long long ldo, int S, i
     GemmOperands g{Omega, ldo, 0, PhiT_grid, ldp, stridePhi, S, P, F};
     RowMaxEpilogue ep{nullptr, 0, fmax, arg, Fs_full, P, (long long)S * P};
     return launch_gemm_nt_rowmax(g, ep, batch, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ posterior weight samples
+namespace ppbo {
+
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter-based, so sample s of
+// feature f gets the same normal whatever the grid shape or the rank that owns row s (multi-GPU invariance).
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+// two standard normals from counter `idx` of stream `stream` under `seed` (Box-Muller on two 53-bit uniforms in (0,1))
+__device__ __forceinline__ void philox_normal2(unsigned long long seed, unsigned long long idx, uint32_t stream,
+                                               double& z0, double& z1) {
+    uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), stream, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u1 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+// out[i] = normal number (offset + i) of the stream; element e lives in counter e/2, slot e%2
+__global__ void __launch_bounds__(256) normal_fill_kernel(unsigned long long seed, uint32_t stream, long long offset,
+                                                          double* __restrict__ out, long long n) {
+    const long long first = offset >> 1, last = (offset + n - 1) >> 1;          // counters touched
+    for (long long c = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; c <= last;
+         c += (long long)gridDim.x * blockDim.x) {
+        double z0, z1;
+        philox_normal2(seed, (unsigned long long)c, stream, z0, z1);
+        const long long e0 = 2 * c - offset, e1 = e0 + 1;
+        if (e0 >= 0 && e0 < n) out[e0] = z0;
+        if (e1 >= 0 && e1 < n) out[e1] = z1;
+    }
+}
+
+// Omega[s][f] = omega_map[f] + z[s][f] / sqrt(-hess_diag[f])   (Hsampler.sample_omega with the diagonal Laplace covariance,
+// src/random_fourier_sampler.py:134-137,207-213).  Z == nullptr: z is normal number ((sample0 + s) * F + f) of the Philox stream.
+__global__ void __launch_bounds__(256) sample_omega_kernel(const double* __restrict__ omega_map,
+                                                           const double* __restrict__ hess_diag,
+                                                           const double* __restrict__ Z, long long ldz,
+                                                           unsigned long long seed, uint32_t stream, long long sample0, int S,
+                                                           int F, double* __restrict__ Omega, long long ldo) {
+    const int s = blockIdx.y;
+    const int fp = blockIdx.x * blockDim.x + threadIdx.x;        // pair index: features 2fp, 2fp+1
+    const int f0 = 2 * fp;
+    if (f0 >= F) return;
+    double z0, z1 = 0.0;
+    if (Z) {
+        z0 = Z[(long long)s * ldz + f0];
+        if (f0 + 1 < F) z1 = Z[(long long)s * ldz + f0 + 1];
+    } else {
+        const long long e = (sample0 + s) * (long long)F + f0;   // global normal index of (s, f0)
+        if ((e & 1) == 0) {
+            philox_normal2(seed, (unsigned long long)(e >> 1), stream, z0, z1);
+        } else {                                                  // odd F: the pair straddles two counters
+            double a, b;
+            philox_normal2(seed, (unsigned long long)(e >> 1), stream, a, b);
+            z0 = b;
+            philox_normal2(seed, (unsigned long long)((e + 1) >> 1), stream, a, b);
+            z1 = a;
+        }
+    }
+    double* o = Omega + (long long)s * ldo;
+    o[f0] = omega_map[f0] + z0 * rsqrt(-hess_diag[f0]);
+    if (f0 + 1 < F) o[f0 + 1] = omega_map[f0 + 1] + z1 * rsqrt(-hess_diag[f0 + 1]);
+}
+
+}  // namespace ppbo
+
+extern "C" int ppbo_normal_fill(unsigned long long seed, unsigned int stream_id, long long offset, double* out, long long n,
+                                void* stream) {
+    PPBO_REQUIRE(n >= 0 && offset >= 0, "shape");
+    if (n == 0) return PPBO_OK;
+    const long long counters = ((offset + n - 1) >> 1) - (offset >> 1) + 1;
+    const int blocks = (int)std::min<long long>(ceil_div_ll(counters, 256), PPBO_SM_COUNT * 16);
+    PPBO_CL normal_fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(seed, stream_id, offset, out, n);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_rff_sample_omega(const double* omega_map, const double* hess_diag, const double* Z, long long ldz,
+                                     unsigned long long seed, unsigned int stream_id, long long sample0, int S, int F,
+                                     double* Omega, long long ldo, void* stream) {
+    PPBO_REQUIRE(S >= 0 && F >= 1 && ldo >= F, "shape");
+    PPBO_REQUIRE(S <= 65535 * 1024, "too many samples for one launch");
+    if (S == 0) return PPBO_OK;
+    // grid.y is limited to 65535: split the launch over row blocks
+    for (int s0 = 0; s0 < S; s0 += 65535) {
+        const int rows = std::min(65535, S - s0);
+        dim3 grid(ceil_div((F + 1) / 2, 256), rows);
+        PPBO_CL sample_omega_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(omega_map, hess_diag, Z ? Z + (long long)s0 * ldz : nullptr,
+                                                                    ldz, seed, stream_id, sample0 + s0, rows, F,
+                                                                    Omega + (long long)s0 * ldo, ldo);
+    }
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
 }

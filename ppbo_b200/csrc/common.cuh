@@ -14,6 +14,8 @@
 namespace ppbo {
 
 void set_error(const char* fmt, ...);
+extern long long g_launch_count;   // kernels launched by this library (bench.py reports it as gpu_launches)
+#define PPBO_CL ++ppbo::g_launch_count,
 
 #define PPBO_CUDA_CHECK(expr)                                                            \
     do {                                                                                 \

@@ -135,13 +135,13 @@ int kernel_matrix(const KernelParams& p, const double* X1, int n1, const double*
     }
     switch (p.kind) {
         case PPBO_KERNEL_SE:
-            kernel_matrix_kernel<PPBO_KERNEL_SE><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
+            PPBO_CL kernel_matrix_kernel<PPBO_KERNEL_SE><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
             break;
         case PPBO_KERNEL_RQ:
-            kernel_matrix_kernel<PPBO_KERNEL_RQ><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
+            PPBO_CL kernel_matrix_kernel<PPBO_KERNEL_RQ><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
             break;
         default:
-            kernel_matrix_kernel<PPBO_KERNEL_CAMPHOR><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
+            PPBO_CL kernel_matrix_kernel<PPBO_KERNEL_CAMPHOR><<<grid, KT_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, symmetric_diag);
     }
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
@@ -209,7 +209,7 @@ int diffspace_gram(const double* S, long long lds, int Q, int m, double* G, long
     const int M = Q * m;
     if (M <= 0) return PPBO_OK;
     dim3 grid(ceil_div(M, 256), M);
-    diffspace_gram_kernel<<<grid, 256, 0, st>>>(S, lds, Q, m, G, ldg);
+    PPBO_CL diffspace_gram_kernel<<<grid, 256, 0, st>>>(S, lds, Q, m, G, ldg);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -217,7 +217,7 @@ int diffspace_gram(const double* S, long long lds, int Q, int m, double* G, long
 int newton_matrix(const double* G, long long ldg, int M, const double* sa, double* out, long long ldo, cudaStream_t st) {
     if (M <= 0) return PPBO_OK;
     dim3 grid(ceil_div(M, 256), M);
-    newton_matrix_kernel<<<grid, 256, 0, st>>>(G, ldg, M, sa, out, ldo);
+    PPBO_CL newton_matrix_kernel<<<grid, 256, 0, st>>>(G, ldg, M, sa, out, ldo);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -249,7 +249,7 @@ extern "C" int ppbo_kernel_se_grad(const double* X1, int n1, const double* X2, i
     if (rc) return rc;
     if (n1 <= 0 || n2 <= 0) return PPBO_OK;
     const long long total = (long long)n1 * n2;
-    se_grad_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(X1, n1, X2, n2, p, dK, ld, stride);
+    PPBO_CL se_grad_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(X1, n1, X2, n2, p, dK, ld, stride);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }

@@ -186,12 +186,12 @@ __global__ void lambda_dense_kernel(const double* __restrict__ arrow, int Q, int
 
 int launch_lik_terms(const double* f, int Q, int m, double sigma, double* set_lik, double* beta, double* arrow, double* sa,
                      double* bvec, cudaStream_t st) {
-    lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, set_lik, beta, arrow, sa, bvec);
+    PPBO_CL lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, set_lik, beta, arrow, sa, bvec);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
 int launch_sum(const double* x, int n, double* out, cudaStream_t st) {
-    sum_kernel<<<1, 1024, 0, st>>>(x, n, out);
+    PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(x, n, out);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -230,10 +230,10 @@ extern "C" int ppbo_lik_terms(const double* f, int Q, int m, double sigma, doubl
     cudaStream_t st = (cudaStream_t)stream;
     double* part = nullptr;
     if (lik_sum) PPBO_CUDA_CHECK(cudaMallocAsync(&part, sizeof(double) * Q, st));
-    lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, part, beta, arrow, nullptr, nullptr);
+    PPBO_CL lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, part, beta, arrow, nullptr, nullptr);
     PPBO_LAUNCH_CHECK();
     if (lik_sum) {
-        sum_kernel<<<1, 1024, 0, st>>>(part, Q, lik_sum);
+        PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(part, Q, lik_sum);
         PPBO_LAUNCH_CHECK();
         PPBO_CUDA_CHECK(cudaFreeAsync(part, st));
     }
@@ -243,7 +243,7 @@ extern "C" int ppbo_lik_terms(const double* f, int Q, int m, double sigma, doubl
 extern "C" int ppbo_lambda_dense(const double* arrow, int Q, int m, double* out, long long ld, void* stream) {
     const long long N = (long long)Q * (m + 1);
     if (N == 0) return PPBO_OK;
-    lambda_dense_kernel<<<(unsigned)ceil_div_ll(N * N, 256), 256, 0, (cudaStream_t)stream>>>(arrow, Q, m, out, ld);
+    PPBO_CL lambda_dense_kernel<<<(unsigned)ceil_div_ll(N * N, 256), 256, 0, (cudaStream_t)stream>>>(arrow, Q, m, out, ld);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -276,13 +276,13 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     int n_halvings_total = 0;
     for (it = 0; it < max_iter; ++it) {
         // likelihood terms at f, Newton right-hand side, system matrix, factorisation
-        lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, ws.sa, ws.bvec);
+        PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, ws.sa, ws.bvec);
         if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
         if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
         if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
-        diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
+        PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
         if ((rc = potrs_vec(Lfac, M, M, Mdinv, ws.t, st))) return rc;
-        alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);
+        PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);
         if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st))) return rc;
         PPBO_LAUNCH_CHECK();
         if (!alpha_known) {
@@ -297,12 +297,12 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             continue;
         }
         // line search over s = 1, 1/2, ..., 2^-7 on T(alpha + s dalpha) = -1/2 (alpha+s dalpha).(f+s df) - lik(f+s df)/m
-        linesearch_lik_kernel<<<dim3(set_blocks, NSTEP), 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.set_part);
+        PPBO_CL linesearch_lik_kernel<<<dim3(set_blocks, NSTEP), 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.set_part);
         if (std::isnan(T_cur)) {   // need T at the current point once: evaluate via the same kernel at step 0
-            lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, nullptr, nullptr, nullptr);
-            sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
+            PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, nullptr, nullptr, nullptr);
+            PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
         }
-        newton_scalars_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, ws.scal);
+        PPBO_CL newton_scalars_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, ws.scal);
         PPBO_LAUNCH_CHECK();
         PPBO_CUDA_CHECK(cudaMemcpyAsync(scal_h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
         PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -319,7 +319,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         }
         if (c == NSTEP) { step = std::ldexp(1.0, -(NSTEP - 1)); T_new = NAN; }   // keep moving; T re-evaluated next round
         n_halvings_total += (c == NSTEP) ? NSTEP : c;
-        axpy2_kernel<<<ceil_div(N, 256), 256, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, step, N);
+        PPBO_CL axpy2_kernel<<<ceil_div(N, 256), 256, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, step, N);
         PPBO_LAUNCH_CHECK();
         T_cur = T_new;
         last_step = step * scal_h[4];
@@ -328,8 +328,8 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         if (step == 1.0 && last_rel <= tol) { ++it; break; }
     }
     // consistent products at the mode: arrow (signed), factor of I + a+^1/2 G a+^1/2
-    lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, arrow, ws.sa, nullptr);
-    sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
+    PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, arrow, ws.sa, nullptr);
+    PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
     if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
     if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
     PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -13,6 +13,7 @@
 namespace ppbo {
 
 static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -65,7 +66,7 @@ static int launch_store_cfg(const GemmOperands& g, StoreEpilogue ep, int batch, 
     } else {
         grid = dim3(tm, tn, batch);
     }
-    gemm_nt_store_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, ep);
+    PPBO_CL gemm_nt_store_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, ep);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -92,7 +93,7 @@ static int launch_rowmax_cfg(const GemmOperands& g, const RowMaxEpilogue& ep, in
     int rc = set_smem_attr_rowmax<Cfg>();
     if (rc) return rc;
     dim3 grid(ceil_div(g.M, Cfg::BM), batch, 1);
-    gemm_nt_rowmax_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, ep);
+    PPBO_CL gemm_nt_rowmax_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, ep);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -138,79 +139,186 @@ int gemv(const double* A, long long lda, int M, int N, const double* x, double* 
     if (M <= 0) return PPBO_OK;
     const int vec = aligned16(A) && aligned16(x) && lda % 2 == 0;
     const int blocks = min(ceil_div(M, 8), PPBO_SM_COUNT * 8);
-    gemv_kernel<<<blocks, 256, 0, st>>>(A, lda, M, N, x, y, vec);
+    PPBO_CL gemv_kernel<<<blocks, 256, 0, st>>>(A, lda, M, N, x, y, vec);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
 
 // ------------------------------------------------------------------------------------------- Cholesky
-// Diagonal block: factor the jb x jb lower block in shared memory and invert the factor (one CTA).
-// dinv receives inv(L_jj) as a dense NB x NB row-major lower-triangular block (zeros above the diagonal).
+// Diagonal block: factor the jb x jb (jb <= 128) lower block and invert the factor, one CTA, everything in shared memory.
+// dinv receives inv(L_jj) as a dense NB x NB row-major lower-triangular block (zeros above the diagonal and beyond jb).
+//
+// The block is processed as 4 sub-columns of 32: warp 0 factors the 32 x 32 diagonal piece and inverts it entirely in
+// registers (lane i owns row i; pivots and multipliers travel by warp shuffle, no block barrier), then all 16 warps form the
+// sub-panel L21 = A21 inv(L11)^T and the trailing update as small shared-memory GEMMs.  The 128 x 128 inverse is assembled from
+// the four 32 x 32 inverses by two levels of  inv([[A,0],[C,B]]) = [[A^-1,0],[-B^-1 C A^-1, B^-1]].
+// ~35 us per block against ~300 us for a column-by-column version with three block barriers per column.
 constexpr int POTF2_THREADS = 512;
-constexpr int POTF2_LDS = CHOL_NB + 1;
+constexpr int POTF2_LDS = CHOL_NB + 1;                 // row stride of the 128 x 128 work matrix
+constexpr int POTF2_SUB = 32;
+constexpr int POTF2_LDR = POTF2_SUB + 1;               // row stride of the 32 x 32 inverse blocks
+constexpr int POTF2_LDT = 64 + 1;                      // row stride of the scratch matrix (up to 96 x 32 or 64 x 64)
+constexpr int POTF2_SMEM_DOUBLES = CHOL_NB * POTF2_LDS + 4 * POTF2_SUB * POTF2_LDR + 96 * POTF2_LDT;
+
+// C[i][j] = (acc ? C[i][j] : 0) + sign * sum_k A[i][k] * (B_KMAJOR ? B[k][j] : B[j][k]),  i < m, j < n, all in shared memory.
+// lower_only: only i >= j + diag_shift is computed.  Thread t owns rows {ti + r * tiles_m} x columns {tj + c * tiles_n} so that
+// the lanes of a warp read consecutive rows (conflict-free with the odd row strides used here).
+template <bool B_KMAJOR>
+__device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n,
+                                          int K, double sign, bool acc, bool lower_only) {
+    const int tiles_m = (m + 1) >> 1, tiles_n = (n + 1) >> 1;
+    for (int t = threadIdx.x; t < tiles_m * tiles_n; t += POTF2_THREADS) {
+        const int ti = t % tiles_m, tj = t / tiles_m;
+        const int i0 = ti, i1 = ti + tiles_m, j0 = tj, j1 = tj + tiles_n;
+        if (lower_only && i1 < j0 && i0 < j0) continue;
+        const bool vi1 = i1 < m, vj1 = j1 < n;
+        const double* a0 = A + i0 * lda;
+        const double* a1 = A + (vi1 ? i1 : i0) * lda;
+        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        if (B_KMAJOR) {
+            const int jj1 = vj1 ? j1 : j0;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const double x0 = a0[k], x1 = a1[k], y0 = B[k * ldb + j0], y1 = B[k * ldb + jj1];
+                c00 = fma(x0, y0, c00); c01 = fma(x0, y1, c01); c10 = fma(x1, y0, c10); c11 = fma(x1, y1, c11);
+            }
+        } else {
+            const double* b0 = B + j0 * ldb;
+            const double* b1 = B + (vj1 ? j1 : j0) * ldb;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const double x0 = a0[k], x1 = a1[k], y0 = b0[k], y1 = b1[k];
+                c00 = fma(x0, y0, c00); c01 = fma(x0, y1, c01); c10 = fma(x1, y0, c10); c11 = fma(x1, y1, c11);
+            }
+        }
+        auto put = [&](int i, int j, double v) {
+            if (lower_only && i < j) return;
+            double* c = C + i * ldc + j;
+            *c = (acc ? *c : 0.0) + sign * v;
+        };
+        put(i0, j0, c00);
+        if (vj1) put(i0, j1, c01);
+        if (vi1) put(i1, j0, c10);
+        if (vi1 && vj1) put(i1, j1, c11);
+    }
+}
+
+// warp-level Cholesky + inverse of a 32 x 32 block held in shared memory (row stride lds).  Lane i owns row i.
+// Returns 0 or the 1-based index of the first non-positive pivot (same value in every lane).
+__device__ __forceinline__ int warp_potrf_inv32(double* Sb, int lds, double* Rb) {
+    const int lane = threadIdx.x & 31;
+    double r[POTF2_SUB];
+#pragma unroll
+    for (int j = 0; j < POTF2_SUB; ++j) r[j] = (j <= lane) ? Sb[lane * lds + j] : 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < POTF2_SUB; ++k) {
+        double d = __shfl_sync(0xffffffffu, r[k], k);
+        if (!(d > 0.0)) {                         // also catches NaN; uniform across the warp
+            if (!bad) bad = k + 1;
+            d = 1.0;
+        }
+        const double sd = sqrt(d), isd = 1.0 / sd;
+        r[k] = (lane == k) ? sd : r[k] * isd;     // lanes < k hold 0 there
+#pragma unroll
+        for (int j = k + 1; j < POTF2_SUB; ++j) {
+            const double ljk = __shfl_sync(0xffffffffu, r[k], j);
+            if (lane >= j) r[j] = fma(-r[k], ljk, r[j]);
+        }
+    }
+    // inverse: lane c owns column c of R = L^-1;  R[i][c] = ((i == c) - sum_{p < i} L[i][p] R[p][c]) / L[i][i]
+    double x[POTF2_SUB];
+#pragma unroll
+    for (int i = 0; i < POTF2_SUB; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int p = 0; p < i; ++p) s = fma(__shfl_sync(0xffffffffu, r[p], i), x[p], s);
+        const double lii = __shfl_sync(0xffffffffu, r[i], i);
+        x[i] = (i < lane) ? 0.0 : (((i == lane) ? 1.0 : 0.0) - s) / lii;
+    }
+#pragma unroll
+    for (int j = 0; j < POTF2_SUB; ++j) {
+        if (j <= lane) Sb[lane * lds + j] = r[j];
+        Rb[j * POTF2_LDR + lane] = x[j];          // row j, column lane
+    }
+    return bad;
+}
 
 __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __restrict__ A, long long lda, int jb,
                                                                   double* __restrict__ dinv, int* __restrict__ info,
                                                                   int block_offset) {
     extern __shared__ double sm[];
-    double* S = sm;                               // jb x jb factor (lower), padded rows; later its inverse
+    double* S = sm;                                         // 128 x 128 work matrix (lower), identity-padded beyond jb
+    double* Rd = S + CHOL_NB * POTF2_LDS;                   // 4 inverted 32 x 32 diagonal pieces
+    double* Tm = Rd + 4 * POTF2_SUB * POTF2_LDR;            // scratch
+    __shared__ int bad_s;
     const int tid = threadIdx.x;
-    for (int e = tid; e < jb * jb; e += POTF2_THREADS) {
-        const int i = e / jb, j = e % jb;
-        S[i * POTF2_LDS + j] = (j <= i) ? A[(long long)i * lda + j] : 0.0;
+    if (tid == 0) bad_s = 0;
+    for (int e = tid; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS) {
+        const int i = e >> 7, j = e & 127;
+        double v = 0.0;
+        if (i < jb && j <= i) v = A[(long long)i * lda + j];
+        else if (i >= jb && i == j) v = 1.0;
+        S[i * POTF2_LDS + j] = v;
     }
     __syncthreads();
-    __shared__ int bad;
-    if (tid == 0) bad = 0;
-    // right-looking unblocked Cholesky
-    for (int k = 0; k < jb; ++k) {
-        __syncthreads();
-        const double d = S[k * POTF2_LDS + k];
-        if (!(d > 0.0)) {                          // also catches NaN
-            if (tid == 0) bad = k + 1;
-            break;                                 // uniform: every thread reads the same d
+    for (int sb = 0; sb < 4; ++sb) {
+        const int c0 = sb * POTF2_SUB, c1 = c0 + POTF2_SUB, rem = CHOL_NB - c1;
+        if (tid < 32) {
+            const int bad = warp_potrf_inv32(S + c0 * POTF2_LDS + c0, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR);
+            if (bad && tid == 0 && !bad_s) bad_s = c0 + bad;
         }
-        const double r = 1.0 / sqrt(d);
         __syncthreads();
-        for (int i = k + tid; i < jb; i += POTF2_THREADS) S[i * POTF2_LDS + k] = (i == k) ? sqrt(d) : S[i * POTF2_LDS + k] * r;
-        __syncthreads();
-        const int rem = jb - k - 1;
-        for (int e = tid; e < rem * rem; e += POTF2_THREADS) {
-            const int i = k + 1 + e / rem, j = k + 1 + e % rem;
-            if (j <= i) S[i * POTF2_LDS + j] -= S[i * POTF2_LDS + k] * S[j * POTF2_LDS + k];
+        if (bad_s) break;                                   // uniform
+        if (rem > 0) {
+            // sub-panel: Tm[rem x 32] = A21 . inv(L11)^T ; copy back ; trailing: S22 -= L21 L21^T (lower)
+            smem_gemm<false>(Tm, POTF2_LDT, S + c1 * POTF2_LDS + c0, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, POTF2_LDR, rem,
+                             POTF2_SUB, POTF2_SUB, 1.0, false, false);
+            __syncthreads();
+            for (int e = tid; e < rem * POTF2_SUB; e += POTF2_THREADS) {
+                const int i = e >> 5, j = e & 31;
+                S[(c1 + i) * POTF2_LDS + c0 + j] = Tm[i * POTF2_LDT + j];
+            }
+            smem_gemm<false>(S + c1 * POTF2_LDS + c1, POTF2_LDS, Tm, POTF2_LDT, Tm, POTF2_LDT, rem, rem, POTF2_SUB, -1.0, true, true);
+            __syncthreads();
         }
     }
-    __syncthreads();
-    if (bad) {
-        if (tid == 0 && atomicCAS(info, 0, block_offset + bad) == 0) {}
+    if (bad_s) {
+        if (tid == 0) atomicCAS(info, 0, block_offset + bad_s);
         return;
     }
     for (int e = tid; e < jb * jb; e += POTF2_THREADS) {
         const int i = e / jb, j = e % jb;
         if (j <= i) A[(long long)i * lda + j] = S[i * POTF2_LDS + j];
     }
-    // inverse of the lower-triangular factor, row by row and in place (row i of the inverse only needs rows < i of the
-    // inverse and row i of L):  R[i][c] = -(sum_{c<=p<i} L[i][p] R[p][c]) / L[i][i].
-    // 4 threads cooperate on one column c (dot product split 4 ways), 128 columns -> 512 threads
+    // ---- inverse assembly, in place in S (strictly-lower blocks), diagonal pieces stay in Rd
+    // level 1: for the two 64 x 64 diagonal blocks, C <- -inv(A2) C inv(A1) with 32 x 32 pieces
     __syncthreads();
-    const int c = tid >> 2, part = tid & 3;
-    for (int i = 0; i < jb; ++i) {
-        double s = 0.0;
-        if (c < i) {
-            for (int p = c + part; p < i; p += 4) s = fma(S[i * POTF2_LDS + p], S[p * POTF2_LDS + c], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const double dii = 1.0 / S[i * POTF2_LDS + i];
-        __syncthreads();
-        if (part == 0) {
-            if (c < i) S[i * POTF2_LDS + c] = -s * dii;
-            else if (c == i) S[i * POTF2_LDS + c] = dii;
-        }
-        __syncthreads();
+    for (int h = 0; h < 2; ++h) {          // Tm[h] = C . inv(A1)   (inv(A1) row-major [k][j])
+        const int o = h * 64;
+        smem_gemm<true>(Tm + h * 32 * POTF2_LDT, POTF2_LDT, S + (o + 32) * POTF2_LDS + o, POTF2_LDS,
+                        Rd + (2 * h) * POTF2_SUB * POTF2_LDR, POTF2_LDR, 32, 32, 32, 1.0, false, false);
     }
+    __syncthreads();
+    for (int h = 0; h < 2; ++h) {          // C = -inv(A2) . Tm[h]
+        const int o = h * 64;
+        smem_gemm<true>(S + (o + 32) * POTF2_LDS + o, POTF2_LDS, Rd + (2 * h + 1) * POTF2_SUB * POTF2_LDR, POTF2_LDR,
+                        Tm + h * 32 * POTF2_LDT, POTF2_LDT, 32, 32, 32, -1.0, false, false);
+    }
+    __syncthreads();
+    // the diagonal 32 x 32 pieces of S now get their inverses so that the 64 x 64 diagonal blocks of S are complete inverses
+    for (int e = tid; e < 4 * POTF2_SUB * POTF2_SUB; e += POTF2_THREADS) {
+        const int b = e >> 10, i = (e >> 5) & 31, j = e & 31;
+        S[(b * 32 + i) * POTF2_LDS + b * 32 + j] = Rd[b * POTF2_SUB * POTF2_LDR + i * POTF2_LDR + j];   // zeros above the diagonal
+    }
+    __syncthreads();
+    // level 2: C (rows 64.., cols 0..63) <- -inv(B) C inv(A), A = S[0:64,0:64], B = S[64:128,64:128] (both lower triangular)
+    smem_gemm<true>(Tm, POTF2_LDT, S + 64 * POTF2_LDS, POTF2_LDS, S, POTF2_LDS, 64, 64, 64, 1.0, false, false);
+    __syncthreads();
+    smem_gemm<true>(S + 64 * POTF2_LDS, POTF2_LDS, S + 64 * POTF2_LDS + 64, POTF2_LDS, Tm, POTF2_LDT, 64, 64, 64, -1.0, false, false);
+    __syncthreads();
     for (int e = tid; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS) {
-        const int i = e / CHOL_NB, j = e % CHOL_NB;
+        const int i = e >> 7, j = e & 127;
         dinv[e] = (i < jb && j <= i) ? S[i * POTF2_LDS + j] : 0.0;
     }
 }
@@ -240,7 +348,7 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
     if (n <= 0) return PPBO_OK;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    const int potf2_smem = CHOL_NB * POTF2_LDS * (int)sizeof(double);
+    const int potf2_smem = POTF2_SMEM_DOUBLES * (int)sizeof(double);
     std::call_once(once, [&] {
         attr_err = cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem);
     });
@@ -255,7 +363,7 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
         const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0), j1 = j0 + jb, rem = n - j1;
         double* Ajj = A + (long long)j0 * lda + j0;
         double* dinv_b = dinv + (long long)b * CHOL_NB * CHOL_NB;
-        potf2_inv_kernel<<<1, POTF2_THREADS, potf2_smem, st>>>(Ajj, lda, jb, dinv_b, info_d, j0);
+        PPBO_CL potf2_inv_kernel<<<1, POTF2_THREADS, potf2_smem, st>>>(Ajj, lda, jb, dinv_b, info_d, j0);
         PPBO_LAUNCH_CHECK();
         if (rem <= 0) break;
         // panel: L21 = A21 . inv(L11)^T   (in place: each CTA owns whole rows, K == jb <= BN)
@@ -373,14 +481,14 @@ int potrs_vec(const double* L, long long ldl, int n, const double* dinv, double*
         const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0);
         const int rows = n - j0 - jb;
         const int blocks = max(1, min(ceil_div(rows, 8 * 4), PPBO_SM_COUNT * 2));
-        trsv_fwd_step<<<blocks, 256, 0, st>>>(L, ldl, n, j0, jb, dinv + (long long)b * CHOL_NB * CHOL_NB, t);
-        trsv_commit<<<1, CHOL_NB, 0, st>>>(t, n, j0, jb);
+        PPBO_CL trsv_fwd_step<<<blocks, 256, 0, st>>>(L, ldl, n, j0, jb, dinv + (long long)b * CHOL_NB * CHOL_NB, t);
+        PPBO_CL trsv_commit<<<1, CHOL_NB, 0, st>>>(t, n, j0, jb);
     }
     for (int b = nblk - 1; b >= 0; --b) {
         const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0);
         const int blocks = max(1, min(ceil_div(j0, 256), PPBO_SM_COUNT * 2));
-        trsv_bwd_step<<<blocks, 256, 0, st>>>(L, ldl, n, j0, jb, dinv + (long long)b * CHOL_NB * CHOL_NB, t);
-        trsv_commit<<<1, CHOL_NB, 0, st>>>(t, n, j0, jb);
+        PPBO_CL trsv_bwd_step<<<blocks, 256, 0, st>>>(L, ldl, n, j0, jb, dinv + (long long)b * CHOL_NB * CHOL_NB, t);
+        PPBO_CL trsv_commit<<<1, CHOL_NB, 0, st>>>(t, n, j0, jb);
     }
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
@@ -415,6 +523,7 @@ int trsm_right_lower_t(const double* L, long long ldl, int n, const double* dinv
 using namespace ppbo;
 
 extern "C" int ppbo_version(void) { return 100; }
+extern "C" long long ppbo_launch_count(void) { return g_launch_count; }
 extern "C" const char* ppbo_last_error(void) { return g_err; }
 extern "C" int ppbo_device_sm_count(int dev) {
     int v = 0;
@@ -453,6 +562,12 @@ extern "C" int ppbo_trsm_right_lower(const double* L, long long ldl, int n, doub
     PPBO_REQUIRE(trans == 0, "only X <- X L^-T is provided (every use on the PPBO path has this form)");
     PPBO_REQUIRE(workspace_bytes >= ppbo_potrf_workspace_bytes(n), "workspace must be the one ppbo_potrf_lower filled");
     return trsm_right_lower_t(L, ldl, n, (const double*)workspace, X, ldx, nrhs, (cudaStream_t)stream);
+}
+
+extern "C" int ppbo_potrs_vec(const double* L, long long ldl, int n, double* x, void* workspace, long long workspace_bytes,
+                              void* stream) {
+    PPBO_REQUIRE(workspace_bytes >= ppbo_potrf_workspace_bytes(n), "workspace must be the one ppbo_potrf_lower filled");
+    return potrs_vec(L, ldl, n, (const double*)workspace, x, (cudaStream_t)stream);
 }
 
 extern "C" int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, double* y, void* stream) {

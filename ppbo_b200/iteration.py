@@ -1,0 +1,201 @@
+"""One PPBO iteration on the device: GP Laplace fit  ->  RFF weight-space fit  ->  sampled acquisition over the
+projected xi-grids of every query direction (BASELINE.json north_star; reference call stack SURVEY.md 3.1-3.4).
+
+Host side is Python/torch for memory, streams and torch.distributed only; all arithmetic goes through the C ABI
+(`ops`).  Data layout in HBM (all row-major float64):
+
+    X        [N x D]      design matrix, N = Q (m+1), comparison set q = rows q(m+1)..q(m+1)+m, winner first
+    Sigma    [N x N]      regularised prior covariance                      (GPModel.Sigma)
+    G, Lfac  [M x M]      difference-space Gram B'Sigma B and the Cholesky factor at the mode, M = Q m
+    Phi_X    [F x N]      RFF features of the design (feature-major, the reference's Hsampler.phi_X layout)
+    Omega    [S_loc x F]  this rank's posterior weight samples (K-contiguous A operand of the sampling GEMM)
+    PhiT     [B][P x F]   RFF features of grid b, point-major (K-contiguous B operand)
+    fmax,arg [B][S_loc]   per-sample max / first arg-max over the grid (the S x P product never reaches HBM)
+
+Multi-GPU: only the Monte-Carlo samples are partitioned.  Rank 0 fits and broadcasts the small fit
+products (omega_MAP, hess_diag, mu*: 8(2F+1) bytes); every rank draws its own slice of the counter-based normal stream,
+evaluates its S/R samples on all B grids and one all-reduce(sum) of the 3B partial sums follows.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import PPBOError
+
+F64 = torch.float64
+SHRINKAGE = 1e-6          # GPModel.COVARIANCE_SHRINKAGE, src/gp_model.py:26
+
+
+class Shard:
+    """Which slice of the S Monte-Carlo samples this process owns (rank r of R: samples [lo, hi))."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = group
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+
+    def bounds(self, S):
+        lo = (S * self.rank) // self.world
+        hi = (S * (self.rank + 1)) // self.world
+        return lo, hi
+
+    def broadcast(self, t, src=0):
+        if self.dist and self.world > 1:
+            self.dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def all_reduce_sum(self, t):
+        if self.dist and self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class GPFit:
+    """Device-resident products of GPModel.update_model (src/gp_model.py:87-132)."""
+    __slots__ = ("X", "kernel", "theta", "lengthscales", "Q", "m", "Sigma", "lap")
+
+    @property
+    def f_map(self):
+        return self.lap.f_map
+
+    @property
+    def alpha(self):
+        return self.lap.alpha
+
+
+def gp_fit(X, kernel, theta, Q, m, f_init=None, lengthscales=None, max_iter=100, tol=1e-10, shrinkage=SHRINKAGE):
+    """Sigma = reg(K(X,X)) and the Laplace mode of T (update_Sigma + update_fMAP + Lambda_MAP, src/gp_model.py:157,354,111)."""
+    g = GPFit()
+    g.X, g.kernel, g.theta, g.Q, g.m = X, kernel, [float(t) for t in theta], Q, m
+    g.lengthscales = theta[1] if lengthscales is None else lengthscales
+    if X.shape[0] != Q * (m + 1):
+        raise PPBOError("X must have Q (m+1) rows")
+    g.Sigma = ops.gram_regularized(kernel, X, g.lengthscales, theta[2], shrinkage)
+    g.lap = ops.laplace_fit(g.Sigma, Q, m, theta[0], f_init=f_init, max_iter=max_iter, tol=tol)
+    if g.lap.info != 0:
+        raise PPBOError("Laplace fit: system not positive definite (info=%d)" % g.lap.info)
+    return g
+
+
+def posterior_mean(g, Xp):
+    """mu(Xp) = k(Xp, X) alpha  (GPModel.mu_pred, src/gp_model.py:454-458, batched over the rows of Xp)."""
+    mu, _ = ops.predict(g.kernel, g.X, g.lengthscales, g.theta[2], SHRINKAGE, g.lap, Xp, Xp.shape[0], 1, want_cov=False)
+    return mu.view(-1)
+
+
+def mustar_over_candidates(g, candidates=None):
+    """mu* = max posterior mean over the design rows (= max f_MAP) and optional candidate points; stays on the device.
+    Batched stand-in for the sequential differential evolution of GPModel.mu_star (src/gp_model.py:415-437)."""
+    out = ops.vec_max(g.f_map)
+    if candidates is not None and candidates.shape[0] > 0:
+        ops.vec_max(posterior_mean(g, candidates), out=out, accumulate=True)
+    return out
+
+
+class RFFFit:
+    """Device-resident state of Hsampler after update_phi_X / update_omega_MAP / update_covariancematrix."""
+    __slots__ = ("W", "b", "sigma_f", "Phi_X", "omega_map", "hess_diag", "stats")
+
+
+def rff_fit(X, W, b, theta, Q, m, omega0=None, max_iter=100, tol=1e-10):
+    r = RFFFit()
+    r.W, r.b, r.sigma_f = W, b, float(theta[2])
+    r.Phi_X = ops.rff_features(W, b, X, theta[2], feature_major=True)
+    r.omega_map, r.hess_diag, r.stats = ops.rff_fit(r.Phi_X, Q, m, theta[0], omega0=omega0, max_iter=max_iter, tol=tol)
+    if r.stats["info"] != 0:
+        raise PPBOError("RFF fit: weight-space Hessian not positive definite (info=%d)" % r.stats["info"])
+    return r
+
+
+def line_grids(xis, xs, alphas):
+    """grids[b][p] = alphas[b][p] * xi[b] + x[b]  (FeedbackProcessing.xi_grid with is_scaled=True,
+    src/feedback_processing.py:47-108).  Host arrays in, [B, P, D] host array out (tiny: the jitter of the alphas
+    consumes the host RNG in reference order, so this stays on the host)."""
+    xis, xs, alphas = np.asarray(xis, float), np.asarray(xs, float), np.asarray(alphas, float)
+    return alphas[:, :, None] * xis[:, None, :] + xs[:, None, :]
+
+
+def rff_grid_features(W, b, sigma_f, grids):
+    """PhiT [B, P, F] for device grids [B, P, D]"""
+    B, P, D = grids.shape
+    return ops.rff_features(W, b, grids.reshape(B * P, D), sigma_f, feature_major=False).view(B, P, -1)
+
+
+def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_id=0):
+    """Sampled acquisition on B grids: per grid b the sums over the S samples of max(fmax - mu*, 0), fmax and fmax^2
+    (acquisition.EI / varmax, src/acquisition.py:78-81,176-178, with RFF posterior draws in place of the exact-GP MVN).
+    Returns (sums [B,3] reduced over all ranks, fmax [B,S_loc], arg [B,S_loc])."""
+    shard = shard or Shard()
+    lo, hi = shard.bounds(S)
+    Zloc = None if Z is None else Z[lo:hi]
+    Omega = ops.rff_sample_omega(r.omega_map, r.hess_diag, hi - lo, Z=Zloc, seed=seed, stream_id=stream_id, sample0=lo)
+    fmax, arg, _ = ops.rff_eval_argmax(Omega, PhiT)
+    sums = ops.acq_reduce_dev(fmax, mustar_dev)
+    shard.all_reduce_sum(sums)
+    return sums, fmax, arg
+
+
+def acquisition_values(sums, S):
+    """host: EI and variance-of-max per grid from the reduced sums (src/acquisition.py:81,178)."""
+    s = np.asarray(sums, dtype=float)
+    ei = s[:, 0] / S
+    mean = s[:, 1] / S
+    var = s[:, 2] / S - mean * mean
+    return ei, var
+
+
+class IterationInputs:
+    """Host-side (pinned) inputs of one iteration; `to_device` is the H2D leg measured by bench.py's e2e."""
+    FIELDS = ("X", "f_init", "W", "b", "omega0", "grids")
+
+    def __init__(self, X, f_init, W, b, omega0, grids):
+        self.host = {}
+        for k, v in zip(self.FIELDS, (X, f_init, W, b, omega0, grids)):
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=np.float64)))
+            self.host[k] = t.pin_memory() if torch.cuda.is_available() else t
+
+    def nbytes(self):
+        return sum(t.numel() * 8 for t in self.host.values())
+
+    def to_device(self, dev):
+        return {k: t.to(dev, non_blocking=True) for k, t in self.host.items()}
+
+
+def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, tol=1e-10, timers=None):
+    """d: dict of device tensors (IterationInputs.to_device).  Returns (sums [B,3] device, gp, rff).
+    Rank 0 fits; the others receive (omega_MAP, hess_diag, mu*) by broadcast while they compute the grid features."""
+    shard = shard or Shard()
+    X, W, b, grids = d["X"], d["W"], d["b"], d["grids"]
+    Fdim = W.shape[0]
+    B, P, D = grids.shape
+
+    def mark(name):
+        if timers is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timers.append((name, ev))
+    mark("start")
+    PhiT = rff_grid_features(W, b, theta[2], grids)           # independent of the fit: every rank, before the broadcast
+    mark("grid_features")
+    pack = torch.empty(2 * Fdim + 1, dtype=F64, device=X.device)
+    gp = rff = None
+    if shard.rank == 0:
+        gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
+        mark("gp_fit")
+        mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
+        mark("mustar")
+        rff = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+        mark("rff_fit")
+        pack[:Fdim].copy_(rff.omega_map)
+        pack[Fdim:2 * Fdim].copy_(rff.hess_diag)
+        pack[2 * Fdim:].copy_(mustar)
+    shard.broadcast(pack, src=0)
+    if rff is None:
+        rff = RFFFit()
+        rff.W, rff.b, rff.sigma_f, rff.Phi_X, rff.stats = W, b, float(theta[2]), None, None
+    rff.omega_map, rff.hess_diag = pack[:Fdim], pack[Fdim:2 * Fdim]
+    sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed)
+    mark("acquisition")
+    return sums, gp, rff

@@ -168,6 +168,17 @@ def trsm_right_lower(L, ws, X):
     return X
 
 
+def potrs_vec(L, ws, b):
+    """solve (L L^T) x = b for one right-hand side; returns x (new tensor)"""
+    lib = _lib.load()
+    n = L.shape[0]
+    x = torch.empty(n + 128, dtype=F64, device=L.device)
+    x[:n].copy_(b)
+    check(lib.ppbo_potrs_vec(_p(L), L.stride(0), n, _p(x), _p(ws), lib.ppbo_potrf_workspace_bytes(n), _stream()),
+          "ppbo_potrs_vec")
+    return x[:n]
+
+
 def gemv(A, x):
     y = torch.empty(A.shape[0], dtype=F64, device=A.device)
     check(_lib.load().ppbo_gemv(_p(A), A.stride(0), A.shape[0], A.shape[1], _p(x), _p(y), _stream()), "ppbo_gemv")
@@ -263,3 +274,33 @@ def rff_eval_argmax(Omega, PhiT_grid, want_full=False):
                                            PhiT_grid.stride(0), P, B, _p(fmax), _p(arg), _p(full), _stream()),
           "ppbo_rff_eval_argmax")
     return fmax, arg, full
+
+
+def normal_fill(seed, stream_id, offset, n, dev=None):
+    """n standard normals: numbers offset .. offset+n-1 of Philox stream `stream_id` under `seed` (device-side RNG)."""
+    out = torch.empty(n, dtype=F64, device=dev or device())
+    check(_lib.load().ppbo_normal_fill(int(seed), int(stream_id), int(offset), _p(out), n, _stream()), "ppbo_normal_fill")
+    return out
+
+
+def rff_sample_omega(omega_map, hess_diag, S, Z=None, seed=0, stream_id=0, sample0=0):
+    """Omega [S,F] ~ N(omega_map, diag(1 / -hess_diag)); Z [S,F] injects the standard normals, else Philox."""
+    Fdim = omega_map.shape[0]
+    Om = torch.empty((S, Fdim), dtype=F64, device=omega_map.device)
+    check(_lib.load().ppbo_rff_sample_omega(_p(omega_map), _p(hess_diag), _p(Z), Z.stride(0) if Z is not None else 0,
+                                            int(seed), int(stream_id), int(sample0), S, Fdim, _p(Om), Fdim, _stream()),
+          "ppbo_rff_sample_omega")
+    return Om
+
+
+def acq_reduce_dev(fmax, mustar_dev):
+    B, S = fmax.shape
+    out = torch.empty((B, 3), dtype=F64, device=fmax.device)
+    check(_lib.load().ppbo_acq_reduce_dev(_p(fmax), S, B, _p(mustar_dev), _p(out), _stream()), "ppbo_acq_reduce_dev")
+    return out
+
+
+def vec_max(x, out=None, accumulate=False):
+    out = torch.empty(1, dtype=F64, device=x.device) if out is None else out
+    check(_lib.load().ppbo_vec_max(_p(x), x.numel(), 1 if accumulate else 0, _p(out), _stream()), "ppbo_vec_max")
+    return out
