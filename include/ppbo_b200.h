@@ -27,6 +27,8 @@ const char* ppbo_last_error(void);
 int ppbo_device_sm_count(int dev);
 /* number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches) */
 long long ppbo_launch_count(void);
+/* tuning switches for benchmarking (key 0: tile configuration of the row-max GEMM; 0 = default) */
+int ppbo_set_tuning(int key, int value);
 
 /* ---- K1: covariance matrices -------------------------------------------------------------------- */
 /* out[n1 x n2] = k(X1_i, X2_j).  Replaces kernels.SE_kernel / RQ_kernel / camphor_copper_kernel and
@@ -38,6 +40,9 @@ int ppbo_kernel_matrix(int kind, const double* X1, int n1, const double* X2, int
  * src/misc.py:71-88: the SVD round trip is the identity, the shrinkage is fused). */
 int ppbo_gram_regularized(int kind, const double* X, int n, int D, const double* lengthscales_h,
                           double sigma_f, double shrinkage, double* out, long long ld, void* stream);
+/* K <- (1-s) K + s (tr K / n) I in place for an arbitrary square matrix (misc.regularize_covariance on a caller-supplied
+ * matrix, src/misc.py:71-88).  scratch1: one device double. */
+int ppbo_shrink_inplace(double* K, long long ld, int n, double shrinkage, double* scratch1, void* stream);
 /* analytic dK/dlog(l_d) and dK/dlog(sigma_f) for the SE kernel (north_star piece 1; the reference has
  * no gradient -- checked against finite differences of SE_kernel).  dK: [(D+1)][n1 x n2] */
 int ppbo_kernel_se_grad(const double* X1, int n1, const double* X2, int n2, int D,
@@ -67,7 +72,8 @@ long long ppbo_laplace_workspace_bytes(int Q, int m);
  * Outputs: f_map[N], alpha[N] = Sigma^-1 f_map, arrow[Qm] (true coefficients at the mode),
  *          Lfac: "factor object" of ppbo_factor_doubles(Qm) doubles = [Qm x Qm lower Cholesky factor of
  *          I + a+^1/2 G a+^1/2 at the mode (a+ = max(a,0)) | inverted diagonal blocks used by the solves],
- *          stats_h[8] host doubles: iterations, final step inf-norm, T(f_map), #negative a, ... */
+ *          stats_h[8] host doubles: iterations, last step inf-norm, last relative step, T(f_map), line-search halvings,
+ *          info, Cholesky factorisations, chord (factor-reusing) steps */
 int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
                      int max_iter, double tol, double* G, double* Lfac, double* f_map, double* alpha,
                      double* arrow, void* workspace, long long workspace_bytes, double* stats_h, void* stream);
@@ -76,6 +82,9 @@ int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double si
 /* C[M x N] = alpha * A[M x K] . B[N x K]^T + beta * C   (row-major, K contiguous in A and B) */
 int ppbo_gemm_nt(const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
                  int M, int N, int K, double alpha, double beta, void* stream);
+/* tuning entry: ppbo_gemm_nt with an explicit tile configuration index (scripts/ubench_ops.py) */
+int ppbo_gemm_nt_cfg(int cfg, const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
+                     int M, int N, int K, double alpha, double beta, void* stream);
 long long ppbo_potrf_workspace_bytes(int n);
 /* in-place lower Cholesky of the lower triangle of A[n x n] (upper triangle untouched).  info_h: host int,
  * 0 or 1-based index of the first non-positive pivot.  Replaces dpotrf under scipy.linalg.solve(assume_a='pos')
@@ -88,6 +97,11 @@ int ppbo_trsm_right_lower(const double* L, long long ldl, int n, double* X, long
 /* x <- (L L^T)^-1 x for one right-hand side; x must have room for n + 128 doubles (scratch tail).  Replaces cho_solve
  * under scipy's trust-exact (src/gp_model.py:382-384). */
 int ppbo_potrs_vec(const double* L, long long ldl, int n, double* x, void* workspace, long long workspace_bytes, void* stream);
+/* out = (L L^T)^-1 (dense, symmetric) from the factor and workspace of ppbo_potrf_lower; work: n*n doubles.
+ * Replaces misc.pd_inverse (src/misc.py:96-100; LAPACK dposv with an identity right-hand side) where a caller reads an
+ * explicit inverse (GPModel.Sigma_inv, posterior_covariance). */
+int ppbo_potri_lower(const double* L, long long ldl, int n, void* workspace, long long workspace_bytes, double* work,
+                     double* out, long long ldo, void* stream);
 /* y = A x for row-major A[M x N] */
 int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, double* y, void* stream);
 
@@ -132,6 +146,10 @@ int ppbo_rff_features(const double* W, const double* b, int F, int D, const doub
 /* J[F x D] = -sqrt(2 sigma_f^2/F) sin(W x + b) * W   (Hsampler.Dphi, src/random_fourier_sampler.py:51-53) */
 int ppbo_rff_jacobian(const double* W, const double* b, int F, int D, const double* x, double sigma_f,
                       double* J, void* stream);
+/* out[0] = phi(x)' omega and out[1..D] = its gradient in x, one launch (the objective / jac pair of Hsampler.return_xstar,
+ * src/random_fourier_sampler.py:166-167). */
+int ppbo_rff_value_grad(const double* W, const double* b, int F, int D, const double* omega, const double* x, double sigma_f,
+                        double* out, void* stream);
 /* weight-space objective pieces (Hsampler.S / S_grad / S_hessian, src/random_fourier_sampler.py:106-122):
  * f = Phi_X' omega (Phi_X feature-major [F x N]); S = -1/2|omega|^2 - lik_sum/m (host double); grad[F];
  * hess_diag[F] (the reference Hessian is diagonal).  Any output may be NULL. */

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "ppbo_last_error": (c_char_p, []),
     "ppbo_device_sm_count": (_I, [_I]),
     "ppbo_launch_count": (_L, []),
+    "ppbo_set_tuning": (_I, [_I, _I]),
     "ppbo_kernel_matrix": (_I, [_I, _P, _I, _P, _I, _I, _PD, _D, _P, _L, _P]),
     "ppbo_gram_regularized": (_I, [_I, _P, _I, _I, _PD, _D, _D, _P, _L, _P]),
     "ppbo_kernel_se_grad": (_I, [_P, _I, _P, _I, _I, _PD, _D, _P, _L, _L, _P]),
@@ -37,10 +38,13 @@ _SIGNATURES = {
     "ppbo_laplace_workspace_bytes": (_L, [_I, _I]),
     "ppbo_laplace_fit": (_I, [_P, _L, _I, _I, _D, _P, _I, _D, _P, _P, _P, _P, _P, _P, _L, _PD, _P]),
     "ppbo_gemm_nt": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _D, _D, _P]),
+    "ppbo_gemm_nt_cfg": (_I, [_I, _P, _L, _P, _L, _P, _L, _I, _I, _I, _D, _D, _P]),
     "ppbo_potrf_workspace_bytes": (_L, [_I]),
     "ppbo_potrf_lower": (_I, [_P, _L, _I, _P, _L, _PI, _P]),
     "ppbo_trsm_right_lower": (_I, [_P, _L, _I, _P, _L, _I, _I, _P, _L, _P]),
     "ppbo_potrs_vec": (_I, [_P, _L, _I, _P, _P, _L, _P]),
+    "ppbo_potri_lower": (_I, [_P, _L, _I, _P, _L, _P, _P, _L, _P]),
+    "ppbo_shrink_inplace": (_I, [_P, _L, _I, _D, _P, _P]),
     "ppbo_gemv": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "ppbo_neg_count": (_I, [_P, _I, _PI, _I, _P]),
     "ppbo_neg_corr_doubles": (_L, [_I, _I]),
@@ -53,6 +57,7 @@ _SIGNATURES = {
     "ppbo_vec_max": (_I, [_P, _L, _I, _P, _P]),
     "ppbo_rff_features": (_I, [_P, _P, _I, _I, _P, _I, _D, _P, _L, _I, _P]),
     "ppbo_rff_jacobian": (_I, [_P, _P, _I, _I, _P, _D, _P, _P]),
+    "ppbo_rff_value_grad": (_I, [_P, _P, _I, _I, _P, _P, _D, _P, _P]),
     "ppbo_rff_workspace_bytes": (_L, [_I, _I, _I]),
     "ppbo_rff_objective": (_I, [_P, _L, _I, _I, _I, _D, _P, _PD, _P, _P, _P, _L, _P]),
     "ppbo_rff_fit": (_I, [_P, _L, _I, _I, _I, _D, _P, _I, _D, _P, _P, _P, _L, _PD, _P]),

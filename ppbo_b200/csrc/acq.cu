@@ -132,6 +132,36 @@ __global__ void rff_jacobian_kernel(const double* __restrict__ W, const double* 
     const double c = -amp * sin(s);
     for (int d = 0; d < D; ++d) J[(long long)f * D + d] = c * W[(long long)f * D + d];
 }
+// out[0] = phi(x)' omega, out[1 + d] = d/dx_d (phi(x)' omega): the objective and gradient Hsampler.return_xstar hands to L-BFGS-B
+// (src/random_fourier_sampler.py:166-167), fused so a host optimiser pays one launch per evaluation.  Single CTA, D <= 64.
+__global__ void __launch_bounds__(256) rff_value_grad_kernel(const double* __restrict__ W, const double* __restrict__ b, int F,
+                                                             int D, const double* __restrict__ omega, const double* __restrict__ x,
+                                                             double amp, double* __restrict__ out) {
+    __shared__ double xs[PPBO_MAX_D];
+    __shared__ double red[33];
+    for (int d = threadIdx.x; d < D; d += 256) xs[d] = x[d];
+    __syncthreads();
+    double val = 0.0, g[PPBO_MAX_D];
+#pragma unroll 4
+    for (int d = 0; d < PPBO_MAX_D; ++d) g[d] = 0.0;
+    for (int f = threadIdx.x; f < F; f += 256) {
+        const double* w = W + (long long)f * D;
+        double s = b[f];
+        for (int d = 0; d < D; ++d) s = fma(w[d], xs[d], s);
+        double sn, cs;
+        sincos(s, &sn, &cs);
+        const double om = omega[f];
+        val = fma(om, cs, val);
+        const double c = -om * sn;
+        for (int d = 0; d < D; ++d) g[d] = fma(c, w[d], g[d]);
+    }
+    val = block_sum(val, red);
+    if (threadIdx.x == 0) out[0] = amp * val;
+    for (int d = 0; d < D; ++d) {
+        const double t = block_sum(g[d], red);
+        if (threadIdx.x == 0) out[1 + d] = amp * t;
+    }
+}
 // y[i] = sum_f Phi[f][i] omega[f]   (feature-major Phi: coalesced over i)
 __global__ void __launch_bounds__(256) rff_fvals_kernel(const double* __restrict__ Phi, long long ld, int F, int N,
                                                         const double* __restrict__ omega, double* __restrict__ y) {
@@ -373,6 +403,15 @@ extern "C" int ppbo_rff_jacobian(const double* W, const double* b, int F, int D,
                                  void* stream) {
     const double amp = sqrt(2.0 * sigma_f * sigma_f / F);
     PPBO_CL rff_jacobian_kernel<<<ceil_div(F, 128), 128, 0, (cudaStream_t)stream>>>(W, b, F, D, x, amp, J);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_rff_value_grad(const double* W, const double* b, int F, int D, const double* omega, const double* x,
+                                   double sigma_f, double* out, void* stream) {
+    PPBO_REQUIRE(F >= 1 && D >= 1 && D <= PPBO_MAX_D, "shape");
+    const double amp = sqrt(2.0 * sigma_f * sigma_f / F);
+    PPBO_CL rff_value_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(W, b, F, D, omega, x, amp, out);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }

@@ -38,8 +38,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int BM_, int BN_, int WARPS_M_, int WARPS_N_, int STAGES_, int VEC_>
+template <int BM_, int BN_, int WARPS_M_, int WARPS_N_, int STAGES_, int VEC_, int MINB_ = 1>
 struct GemmCfg {
+    static constexpr int MINB = MINB_;        // CTAs per SM the register allocation must allow
     static constexpr int BM = BM_, BN = BN_, BK = 16, LDS = BK + 4;
     static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_, STAGES = STAGES_, VEC = VEC_;
     static constexpr int THREADS = 32 * WARPS_M * WARPS_N;
@@ -127,16 +128,18 @@ struct StoreEpilogue {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS) gemm_nt_store_kernel(GemmOperands g, StoreEpilogue ep) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_store_kernel(GemmOperands g, StoreEpilogue ep) {
     extern __shared__ __align__(16) double smem[];
     int tm, tn;
     if (ep.lower_only) {
-        const int L = blockIdx.x;
-        int ti = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
-        while ((long long)(ti + 1) * (ti + 2) / 2 <= L) ++ti;
-        while ((long long)ti * (ti + 1) / 2 > L) --ti;
+        // tiles that touch the lower triangle, row-tile major: row tile ti owns column tiles 0 .. R (ti + 1) - 1, R = BM / BN
+        constexpr int R = (Cfg::BM >= Cfg::BN) ? Cfg::BM / Cfg::BN : 1;     // launchers only use lower_only with BM >= BN
+        const long long L = blockIdx.x;
+        int ti = (int)((sqrt(1.0 + 8.0 * (double)L / R) - 1.0) * 0.5);
+        while ((long long)R * (ti + 1) * (ti + 2) / 2 <= L) ++ti;
+        while ((long long)R * ti * (ti + 1) / 2 > L) --ti;
         tm = ti;
-        tn = L - ti * (ti + 1) / 2;
+        tn = (int)(L - (long long)R * ti * (ti + 1) / 2);
     } else {
         tm = blockIdx.x;
         tn = blockIdx.y;
@@ -196,7 +199,7 @@ struct RowMaxEpilogue {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS) gemm_nt_rowmax_kernel(GemmOperands g, RowMaxEpilogue ep) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_rowmax_kernel(GemmOperands g, RowMaxEpilogue ep) {
     extern __shared__ __align__(16) double smem[];
     const int m0 = blockIdx.x * Cfg::BM;
     const int bz = blockIdx.y;

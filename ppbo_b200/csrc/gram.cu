@@ -205,6 +205,34 @@ __global__ void __launch_bounds__(256) newton_matrix_kernel(const double* __rest
     out[(long long)u * ldo + v] = x;
 }
 
+// K <- (1 - s) K + s (tr K / n) I in place: the closed form of sklearn's shrunk_covariance used by misc.regularize_covariance
+// (src/misc.py:85).  Single CTA computes the trace in a fixed order, then the grid scales.
+__global__ void __launch_bounds__(1024) trace_kernel(const double* __restrict__ K, long long ld, int n, double* __restrict__ out) {
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += K[(long long)i * ld + i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s / n;
+}
+__global__ void __launch_bounds__(256) shrink_kernel(double* __restrict__ K, long long ld, int n, double s,
+                                                     const double* __restrict__ mu) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= n) return;
+    double v = (1.0 - s) * K[(long long)i * ld + j];
+    if (i == j) v += s * mu[0];
+    K[(long long)i * ld + j] = v;
+}
+__global__ void __launch_bounds__(256) set_identity_kernel(double* __restrict__ A, long long ld, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j < n) A[(long long)i * ld + j] = (i == j) ? 1.0 : 0.0;
+}
+int set_identity(double* A, long long ld, int n, cudaStream_t st) {
+    if (n <= 0) return PPBO_OK;
+    PPBO_CL set_identity_kernel<<<dim3(ceil_div(n, 256), n), 256, 0, st>>>(A, ld, n);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
 int diffspace_gram(const double* S, long long lds, int Q, int m, double* G, long long ldg, cudaStream_t st) {
     const int M = Q * m;
     if (M <= 0) return PPBO_OK;
@@ -250,6 +278,16 @@ extern "C" int ppbo_kernel_se_grad(const double* X1, int n1, const double* X2, i
     if (n1 <= 0 || n2 <= 0) return PPBO_OK;
     const long long total = (long long)n1 * n2;
     PPBO_CL se_grad_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(X1, n1, X2, n2, p, dK, ld, stride);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_shrink_inplace(double* K, long long ld, int n, double shrinkage, double* scratch1, void* stream) {
+    PPBO_REQUIRE(n >= 0 && ld >= n && scratch1 != nullptr, "shape");
+    if (n == 0) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    PPBO_CL trace_kernel<<<1, 1024, 0, st>>>(K, ld, n, scratch1);
+    PPBO_CL shrink_kernel<<<dim3(ceil_div(n, 256), n), 256, 0, st>>>(K, ld, n, shrinkage, scratch1);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }

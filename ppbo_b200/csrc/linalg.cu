@@ -28,6 +28,11 @@ using CfgWide = GemmCfg<64, 128, 2, 4, 4, 2>;      // in-place row-panel updates
 using CfgWideU = GemmCfg<64, 128, 2, 4, 4, 1>;
 using CfgSmall = GemmCfg<64, 64, 2, 2, 4, 2>;      // 128 threads, warp tile 32x32, 80 KB smem, 2 CTAs / SM
 using CfgSmallU = GemmCfg<64, 64, 2, 2, 4, 1>;
+// experimental configurations reachable through ppbo_gemm_nt_cfg (scripts/ubench_ops.py)
+using CfgTall3 = GemmCfg<128, 64, 4, 2, 3, 2, 2>;  // 256 threads, warp tile 32x32, 92 KB smem, 2 CTAs / SM
+using CfgSq16 = GemmCfg<128, 128, 4, 4, 4, 2>;     // 512 threads, warp tile 32x32, 160 KB smem, 1 CTA / SM
+using CfgSq3 = GemmCfg<128, 128, 2, 4, 3, 2>;      // CfgBig with 3 stages (120 KB)
+using CfgTall4 = GemmCfg<128, 64, 2, 2, 4, 2>;     // 128 threads, warp tile 64x32, 123 KB, 1 CTA / SM
 
 template <class Cfg>
 static int set_smem_attr_store() {
@@ -62,7 +67,8 @@ static int launch_store_cfg(const GemmOperands& g, StoreEpilogue ep, int batch, 
     const int tm = ceil_div(g.M, Cfg::BM), tn = ceil_div(g.N, Cfg::BN);
     dim3 grid;
     if (ep.lower_only) {
-        grid = dim3((unsigned)((long long)tm * (tm + 1) / 2), 1, batch);
+        constexpr int R = (Cfg::BM >= Cfg::BN) ? Cfg::BM / Cfg::BN : 1;
+        grid = dim3((unsigned)((long long)R * tm * (tm + 1) / 2), 1, batch);
     } else {
         grid = dim3(tm, tn, batch);
     }
@@ -85,6 +91,7 @@ int launch_gemm_nt(const GemmOperands& g, const StoreEpilogue& ep_in, int batch,
         return v2 ? launch_store_cfg<CfgWide>(g, ep, batch, st) : launch_store_cfg<CfgWideU>(g, ep, batch, st);
     }
     if (small) return v2 ? launch_store_cfg<CfgSmall>(g, ep, batch, st) : launch_store_cfg<CfgSmallU>(g, ep, batch, st);
+    if (v2) return launch_store_cfg<CfgTall3>(g, ep, batch, st);   // 2 CTAs / SM: prologue/epilogue overlap
     return v2 ? launch_store_cfg<CfgBig>(g, ep, batch, st) : launch_store_cfg<CfgBigU>(g, ep, batch, st);
 }
 
@@ -98,11 +105,15 @@ static int launch_rowmax_cfg(const GemmOperands& g, const RowMaxEpilogue& ep, in
     return PPBO_OK;
 }
 
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // [0]: row-max GEMM tile configuration (0 = default)
+
 int launch_gemm_nt_rowmax(const GemmOperands& g, const RowMaxEpilogue& ep, int batch, cudaStream_t st) {
     if (g.M <= 0 || batch <= 0) return PPBO_OK;
     PPBO_REQUIRE(g.N > 0 && g.K >= 0, "empty grid");
     const bool v2 = operands_vec2(g);
     const bool small = (long long)ceil_div(g.M, 128) * batch < PPBO_SM_COUNT;
+    if (v2 && !small && g_tuning[0] == 2) return launch_rowmax_cfg<CfgTall3>(g, ep, batch, st);
+    if (v2 && !small && g_tuning[0] == 3) return launch_rowmax_cfg<CfgSq16>(g, ep, batch, st);
     if (small) return v2 ? launch_rowmax_cfg<CfgSmall>(g, ep, batch, st) : launch_rowmax_cfg<CfgSmallU>(g, ep, batch, st);
     return v2 ? launch_rowmax_cfg<CfgBig>(g, ep, batch, st) : launch_rowmax_cfg<CfgBigU>(g, ep, batch, st);
 }
@@ -203,44 +214,54 @@ __device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, i
     }
 }
 
-// warp-level Cholesky + inverse of a 32 x 32 block held in shared memory (row stride lds).  Lane i owns row i.
-// Returns 0 or the 1-based index of the first non-positive pivot (same value in every lane).
-__device__ __forceinline__ int warp_potrf_inv32(double* Sb, int lds, double* Rb) {
+// warp-level Cholesky + inverse of a 32 x 32 block held in shared memory (row stride lds).  Lane i owns row i in registers;
+// column k of the running Schur complement is exchanged through a double-buffered shared-memory line read back as broadcast
+// loads (one __syncwarp per column, no shuffles).  wsm: 96 doubles of scratch.  Returns 0 or the 1-based index of the first
+// non-positive pivot (same value in every lane).
+__device__ __forceinline__ int warp_potrf_inv32(double* Sb, int lds, double* Rb, double* wsm) {
     const int lane = threadIdx.x & 31;
+    double* col = wsm;            // [2][32]
+    double* idiag = wsm + 64;     // [32]  1 / L[k][k]
     double r[POTF2_SUB];
 #pragma unroll
     for (int j = 0; j < POTF2_SUB; ++j) r[j] = (j <= lane) ? Sb[lane * lds + j] : 0.0;
     int bad = 0;
 #pragma unroll
     for (int k = 0; k < POTF2_SUB; ++k) {
-        double d = __shfl_sync(0xffffffffu, r[k], k);
+        double* c = col + (k & 1) * 32;
+        c[lane] = r[k];                           // lanes < k hold 0 there
+        __syncwarp();
+        double d = c[k];
         if (!(d > 0.0)) {                         // also catches NaN; uniform across the warp
             if (!bad) bad = k + 1;
             d = 1.0;
         }
-        const double sd = sqrt(d), isd = 1.0 / sd;
-        r[k] = (lane == k) ? sd : r[k] * isd;     // lanes < k hold 0 there
+        const double isd = rsqrt(d);
+        const double mine = r[k] * (isd * isd);
 #pragma unroll
-        for (int j = k + 1; j < POTF2_SUB; ++j) {
-            const double ljk = __shfl_sync(0xffffffffu, r[k], j);
-            if (lane >= j) r[j] = fma(-r[k], ljk, r[j]);
-        }
+        for (int j = k + 1; j < POTF2_SUB; ++j) r[j] = fma(-mine, c[j], r[j]);   // rows < j only touch their (unused) upper part
+        r[k] = (lane == k) ? d * isd : r[k] * isd;
+        if (lane == 0) idiag[k] = isd;
     }
-    // inverse: lane c owns column c of R = L^-1;  R[i][c] = ((i == c) - sum_{p < i} L[i][p] R[p][c]) / L[i][i]
+#pragma unroll
+    for (int j = 0; j < POTF2_SUB; ++j)
+        if (j <= lane) Sb[lane * lds + j] = r[j];
+    __syncwarp();
+    // inverse: lane c owns column c of R = L^-1;  R[i][c] = ((i == c) - sum_{c <= p < i} L[i][p] R[p][c]) / L[i][i]
     double x[POTF2_SUB];
 #pragma unroll
     for (int i = 0; i < POTF2_SUB; ++i) {
-        double s = 0.0;
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int p = 0; p < i; ++p) s = fma(__shfl_sync(0xffffffffu, r[p], i), x[p], s);
-        const double lii = __shfl_sync(0xffffffffu, r[i], i);
-        x[i] = (i < lane) ? 0.0 : (((i == lane) ? 1.0 : 0.0) - s) / lii;
+        for (int p = 0; p + 1 < i; p += 2) {
+            s0 = fma(Sb[i * lds + p], x[p], s0);
+            s1 = fma(Sb[i * lds + p + 1], x[p + 1], s1);
+        }
+        if (i & 1) s0 = fma(Sb[i * lds + i - 1], x[i - 1], s0);
+        x[i] = (i < lane) ? 0.0 : (((i == lane) ? 1.0 : 0.0) - (s0 + s1)) * idiag[i];
     }
 #pragma unroll
-    for (int j = 0; j < POTF2_SUB; ++j) {
-        if (j <= lane) Sb[lane * lds + j] = r[j];
-        Rb[j * POTF2_LDR + lane] = x[j];          // row j, column lane
-    }
+    for (int j = 0; j < POTF2_SUB; ++j) Rb[j * POTF2_LDR + lane] = x[j];          // row j, column lane
     return bad;
 }
 
@@ -252,6 +273,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     double* Rd = S + CHOL_NB * POTF2_LDS;                   // 4 inverted 32 x 32 diagonal pieces
     double* Tm = Rd + 4 * POTF2_SUB * POTF2_LDR;            // scratch
     __shared__ int bad_s;
+    __shared__ double wsm[96];
     const int tid = threadIdx.x;
     if (tid == 0) bad_s = 0;
     for (int e = tid; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS) {
@@ -265,7 +287,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     for (int sb = 0; sb < 4; ++sb) {
         const int c0 = sb * POTF2_SUB, c1 = c0 + POTF2_SUB, rem = CHOL_NB - c1;
         if (tid < 32) {
-            const int bad = warp_potrf_inv32(S + c0 * POTF2_LDS + c0, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR);
+            const int bad = warp_potrf_inv32(S + c0 * POTF2_LDS + c0, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, wsm);
             if (bad && tid == 0 && !bad_s) bad_s = c0 + bad;
         }
         __syncthreads();
@@ -474,9 +496,139 @@ __global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ 
     }
 }
 
-// solves (L L^T) x = t in place; t must have room for n + CHOL_NB doubles (scratch tail)
+// ---- chained single-launch solves ------------------------------------------------------------------------------------
+// One CTA per 128-row block; CTA c accumulates its dependencies on earlier blocks as they are published through global
+// flags (producer: write, __threadfence, flag; consumer: spin on the flag, then __ldcg), so the critical path of the whole
+// solve is nblk x (one 128 x 128 GEMV + publish) instead of nblk kernel launches of latency-bound work.  All CTAs are
+// co-resident (nblk <= 128 <= SM count), and every CTA only waits on CTAs with a smaller blockIdx.
+constexpr int TRSV_THREADS = 512;
+
+__device__ __forceinline__ void trsv_wait(volatile int* flag) {
+    if (threadIdx.x == 0) {
+        while (*flag == 0) { __nanosleep(40); }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void trsv_publish(volatile int* flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = 1;
+}
+
+// forward: L y = t (in place).  CTA c: v = t_c - sum_{J<c} L[c,J] y_J ; y_c = inv(L_cc) v
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_chain(const double* __restrict__ L, long long ldl, int n,
+                                                               const double* __restrict__ dinv, double* t, int* flags) {
+    extern __shared__ double sm[];
+    double* dtile = sm;                       // inv(L_cc), 128 x 128 row-major
+    double* yJ = sm + CHOL_NB * CHOL_NB;      // [128]
+    double* v = yJ + CHOL_NB;                 // [128]
+    const int c = blockIdx.x, j0 = c * CHOL_NB, jb = min(CHOL_NB, n - j0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double* dsrc = dinv + (long long)c * CHOL_NB * CHOL_NB;
+    for (int e = tid; e < CHOL_NB * CHOL_NB; e += TRSV_THREADS) dtile[e] = dsrc[e];
+    double s[8];                              // warp w owns rows w, w+16, ... (8 rows); lanes stride over the 128 columns
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) s[rr] = 0.0;
+    for (int J = 0; J < c; ++J) {
+        trsv_wait(flags + J);
+        if (tid < CHOL_NB) yJ[tid] = __ldcg(t + (long long)J * CHOL_NB + tid);
+        __syncthreads();
+        const double y0 = yJ[lane], y1 = yJ[lane + 32], y2 = yJ[lane + 64], y3 = yJ[lane + 96];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const int row = warp + 16 * rr;
+            if (row < jb) {
+                const double* lr = L + (long long)(j0 + row) * ldl + (long long)J * CHOL_NB;
+                s[rr] = fma(lr[lane], y0, fma(lr[lane + 32], y1, fma(lr[lane + 64], y2, fma(lr[lane + 96], y3, s[rr]))));
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+        double a = s[rr];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        const int row = warp + 16 * rr;
+        if (lane == 0) v[row] = (row < jb) ? t[j0 + row] - a : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {          // y_c[row] = sum_{k <= row} dinv[row][k] v[k]
+        const int row = warp + 16 * rr;
+        double a = 0.0;
+        for (int k = lane; k <= row; k += 32) a = fma(dtile[row * CHOL_NB + k], v[k], a);
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && row < jb) t[j0 + row] = a;
+    }
+    trsv_publish(flags + c);
+}
+
+// backward: L^T x = y (in place).  blockIdx b handles block c = nblk-1-b: v = y_c - sum_{K>c} L[K,c]^T x_K ; x_c = inv(L_cc)^T v
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_chain(const double* __restrict__ L, long long ldl, int n, int nblk,
+                                                               const double* __restrict__ dinv, double* t, int* flags) {
+    extern __shared__ double sm[];
+    double* dtile = sm;
+    double* xK = sm + CHOL_NB * CHOL_NB;      // [128]
+    double* part = xK + CHOL_NB;              // [4][128]
+    const int c = nblk - 1 - (int)blockIdx.x, j0 = c * CHOL_NB;
+    const int tid = threadIdx.x, g = tid >> 7, k = tid & 127;     // 4 row groups x 128 columns
+    const double* dsrc = dinv + (long long)c * CHOL_NB * CHOL_NB;
+    for (int e = tid; e < CHOL_NB * CHOL_NB; e += TRSV_THREADS) dtile[e] = dsrc[e];
+    double acc = 0.0;
+    const bool col_ok = j0 + k < n;
+    for (int K = nblk - 1; K > c; --K) {
+        trsv_wait(flags + K);
+        if (tid < CHOL_NB) xK[tid] = (K * CHOL_NB + tid < n) ? __ldcg(t + (long long)K * CHOL_NB + tid) : 0.0;
+        __syncthreads();
+        const int kb = min(CHOL_NB, n - K * CHOL_NB);
+        if (col_ok) {
+            const double* lk = L + (long long)(K * CHOL_NB + g * 32) * ldl + j0 + k;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+                if (g * 32 + r < kb) acc = fma(lk[(long long)r * ldl], xK[g * 32 + r], acc);
+        }
+        __syncthreads();
+    }
+    part[g * CHOL_NB + k] = acc;
+    __syncthreads();
+    if (tid < CHOL_NB) {
+        const double a = part[tid] + part[CHOL_NB + tid] + part[2 * CHOL_NB + tid] + part[3 * CHOL_NB + tid];
+        xK[tid] = (j0 + tid < n) ? t[j0 + tid] - a : 0.0;          // v
+    }
+    __syncthreads();
+    {   // x_c[k] = sum_{r >= k} dinv[r][k] v[r]; thread (g, k) takes rows r = g, g+4, ...
+        double a = 0.0;
+        for (int r = g; r < CHOL_NB; r += 4)
+            if (r >= k) a = fma(dtile[r * CHOL_NB + k], xK[r], a);
+        part[g * CHOL_NB + k] = a;
+    }
+    __syncthreads();
+    if (tid < CHOL_NB && j0 + tid < n)
+        t[j0 + tid] = part[tid] + part[CHOL_NB + tid] + part[2 * CHOL_NB + tid] + part[3 * CHOL_NB + tid];
+    trsv_publish(flags + c);
+}
+
+constexpr int TRSV_CHAIN_SMEM = (CHOL_NB * CHOL_NB + 6 * CHOL_NB) * (int)sizeof(double);
+
+// solves (L L^T) x = t in place; t must have room for n + CHOL_NB doubles (scratch tail: flags of the chained kernels)
 int potrs_vec(const double* L, long long ldl, int n, const double* dinv, double* t, cudaStream_t st) {
     const int nblk = ceil_div(n, CHOL_NB);
+    if (nblk <= 128) {
+        static std::once_flag once;
+        static cudaError_t err = cudaSuccess;
+        std::call_once(once, [] {
+            err = cudaFuncSetAttribute(trsv_fwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_CHAIN_SMEM);
+            if (err == cudaSuccess)
+                err = cudaFuncSetAttribute(trsv_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_CHAIN_SMEM);
+        });
+        PPBO_CUDA_CHECK(err);
+        int* flags = reinterpret_cast<int*>(t + n);          // 2 * nblk ints <= 1 KB
+        PPBO_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * 2 * nblk, st));
+        PPBO_CL trsv_fwd_chain<<<nblk, TRSV_THREADS, TRSV_CHAIN_SMEM, st>>>(L, ldl, n, dinv, t, flags);
+        PPBO_CL trsv_bwd_chain<<<nblk, TRSV_THREADS, TRSV_CHAIN_SMEM, st>>>(L, ldl, n, nblk, dinv, t, flags + nblk);
+        PPBO_LAUNCH_CHECK();
+        return PPBO_OK;
+    }
     for (int b = 0; b < nblk; ++b) {
         const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0);
         const int rows = n - j0 - jb;
@@ -524,6 +676,11 @@ using namespace ppbo;
 
 extern "C" int ppbo_version(void) { return 100; }
 extern "C" long long ppbo_launch_count(void) { return g_launch_count; }
+extern "C" int ppbo_set_tuning(int key, int value) {
+    PPBO_REQUIRE(key >= 0 && key < 8, "tuning key");
+    g_tuning[key] = value;
+    return PPBO_OK;
+}
 extern "C" const char* ppbo_last_error(void) { return g_err; }
 extern "C" int ppbo_device_sm_count(int dev) {
     int v = 0;
@@ -537,6 +694,25 @@ extern "C" int ppbo_gemm_nt(const double* A, long long lda, const double* B, lon
     GemmOperands g{A, lda, 0, B, ldb, 0, M, N, K};
     StoreEpilogue ep{C, ldc, 0, alpha, beta, 0, 0};
     return launch_gemm_nt(g, ep, 1, (cudaStream_t)stream);
+}
+
+/* debug / tuning: same as ppbo_gemm_nt with an explicit tile configuration (0 big, 1 small, 2 tall3, 3 sq16, 4 sq3, 5 tall4) */
+extern "C" int ppbo_gemm_nt_cfg(int cfg, const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
+                                int M, int N, int K, double alpha, double beta, void* stream) {
+    GemmOperands g{A, lda, 0, B, ldb, 0, M, N, K};
+    StoreEpilogue ep{C, ldc, 0, alpha, beta, 0, 0, 0};
+    ep.vec_ok = aligned16(C) && ldc % 2 == 0;
+    PPBO_REQUIRE(operands_vec2(g), "tuning entry needs 16-byte aligned operands");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cfg) {
+        case 0: return launch_store_cfg<CfgBig>(g, ep, 1, st);
+        case 1: return launch_store_cfg<CfgSmall>(g, ep, 1, st);
+        case 2: return launch_store_cfg<CfgTall3>(g, ep, 1, st);
+        case 3: return launch_store_cfg<CfgSq16>(g, ep, 1, st);
+        case 4: return launch_store_cfg<CfgSq3>(g, ep, 1, st);
+        case 5: return launch_store_cfg<CfgTall4>(g, ep, 1, st);
+    }
+    PPBO_REQUIRE(false, "unknown configuration");
 }
 
 extern "C" long long ppbo_potrf_workspace_bytes(int n) { return potrf_dinv_doubles(n) * 8 + 16; }
@@ -568,6 +744,24 @@ extern "C" int ppbo_potrs_vec(const double* L, long long ldl, int n, double* x, 
                               void* stream) {
     PPBO_REQUIRE(workspace_bytes >= ppbo_potrf_workspace_bytes(n), "workspace must be the one ppbo_potrf_lower filled");
     return potrs_vec(L, ldl, n, (const double*)workspace, x, (cudaStream_t)stream);
+}
+
+namespace ppbo { int set_identity(double* A, long long ld, int n, cudaStream_t st); }
+
+/* out = (L L^T)^-1 from the factor ppbo_potrf_lower left in A (lower) and its workspace: Y = I L^-T, out = Y Y^T.
+ * work: n*n doubles.  Replaces misc.pd_inverse (src/misc.py:96-100) for the public attributes that are explicit inverses. */
+extern "C" int ppbo_potri_lower(const double* L, long long ldl, int n, void* workspace, long long workspace_bytes, double* work,
+                                double* out, long long ldo, void* stream) {
+    PPBO_REQUIRE(n >= 0 && ldl >= n && ldo >= n, "shape");
+    PPBO_REQUIRE(workspace_bytes >= ppbo_potrf_workspace_bytes(n), "workspace must be the one ppbo_potrf_lower filled");
+    if (n == 0) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = set_identity(work, n, n, st))) return rc;
+    if ((rc = trsm_right_lower_t(L, ldl, n, (const double*)workspace, work, n, n, st))) return rc;     // Y = L^-T (upper)
+    GemmOperands g{work, n, 0, work, n, 0, n, n, n};
+    StoreEpilogue ep{out, ldo, 0, 1.0, 0.0, 0, 0, 0};
+    return launch_gemm_nt(g, ep, 1, st);
 }
 
 extern "C" int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, double* y, void* stream) {

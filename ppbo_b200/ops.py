@@ -123,7 +123,7 @@ def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10):
                                     stats, _stream()), "ppbo_laplace_fit")
     fit.info = rc
     fit.stats = dict(iterations=int(stats[0]), last_step=stats[1], last_rel_step=stats[2], T=stats[3],
-                     halvings=int(stats[4]))
+                     halvings=int(stats[4]), factorizations=int(stats[6]), chord_steps=int(stats[7]))
     fit.n_neg, fit.neg_corr = 0, None
     if rc == 0:
         idx = (ctypes.c_int * M)()
@@ -145,6 +145,14 @@ def gemm_nt(A, B, C=None, alpha=1.0, beta=0.0):
     C = torch.empty((M, N), dtype=F64, device=A.device) if C is None else C
     check(_lib.load().ppbo_gemm_nt(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, float(alpha),
                                    float(beta), _stream()), "ppbo_gemm_nt")
+    return C
+
+
+def gemm_nt_cfg(cfg, A, B, C, alpha=1.0, beta=0.0):
+    M, K = A.shape
+    N = B.shape[0]
+    check(_lib.load().ppbo_gemm_nt_cfg(int(cfg), _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K,
+                                       float(alpha), float(beta), _stream()), "ppbo_gemm_nt_cfg")
     return C
 
 
@@ -177,6 +185,25 @@ def potrs_vec(L, ws, b):
     check(lib.ppbo_potrs_vec(_p(L), L.stride(0), n, _p(x), _p(ws), lib.ppbo_potrf_workspace_bytes(n), _stream()),
           "ppbo_potrs_vec")
     return x[:n]
+
+
+def potri_lower(L, ws):
+    """dense (L L^T)^-1 from a factor produced by potrf_lower"""
+    lib = _lib.load()
+    n = L.shape[0]
+    work = torch.empty((n, n), dtype=F64, device=L.device)
+    out = torch.empty((n, n), dtype=F64, device=L.device)
+    check(lib.ppbo_potri_lower(_p(L), L.stride(0), n, _p(ws), lib.ppbo_potrf_workspace_bytes(n), _p(work), _p(out), n,
+                               _stream()), "ppbo_potri_lower")
+    return out
+
+
+def shrink_inplace(K, shrinkage):
+    n = K.shape[0]
+    scratch = torch.empty(1, dtype=F64, device=K.device)
+    check(_lib.load().ppbo_shrink_inplace(_p(K), K.stride(0), n, float(shrinkage), _p(scratch), _stream()),
+          "ppbo_shrink_inplace")
+    return K
 
 
 def gemv(A, x):
@@ -303,4 +330,13 @@ def acq_reduce_dev(fmax, mustar_dev):
 def vec_max(x, out=None, accumulate=False):
     out = torch.empty(1, dtype=F64, device=x.device) if out is None else out
     check(_lib.load().ppbo_vec_max(_p(x), x.numel(), 1 if accumulate else 0, _p(out), _stream()), "ppbo_vec_max")
+    return out
+
+
+def rff_value_grad(W, b, omega, x, sigma_f):
+    """(phi(x)' omega, gradient in x) as one [1 + D] device tensor"""
+    Fdim, D = W.shape
+    out = torch.empty(1 + D, dtype=F64, device=W.device)
+    check(_lib.load().ppbo_rff_value_grad(_p(W), _p(b), Fdim, D, _p(omega), _p(x), float(sigma_f), _p(out), _stream()),
+          "ppbo_rff_value_grad")
     return out

@@ -29,6 +29,7 @@ def main():
         A = A0 @ A0.T + n * torch.eye(n, dtype=torch.float64, device=dev)
         W = A.clone()
         t = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
+        W.copy_(A)
         info, ws = ops.potrf_lower(W)
         L = torch.tril(W)
         err = float((L @ L.T - A).abs().max() / A.abs().max())
@@ -47,6 +48,26 @@ def main():
         C = torch.zeros(M, N, dtype=torch.float64, device=dev)
         t = timeit(lambda: ops.gemm_nt(A, B, C, 1.0, 1.0))
         print("gemm_nt %dx%dx%d: %.3f ms (%.2f TFLOP/s)" % (M, N, K, t, 2.0 * M * N * K / t / 1e9))
+    for (M, N, K) in ((5000, 5000, 128), (2500, 2500, 128), (5000, 128, 5000), (4096, 4096, 4096), (1000, 1000, 5000)):
+        A = torch.randn(M, K, dtype=torch.float64, device=dev); B = torch.randn(N, K, dtype=torch.float64, device=dev)
+        C = torch.zeros(M, N, dtype=torch.float64, device=dev)
+        ref = A @ B.T
+        for cfg in range(6):
+            C.zero_()
+            ops.gemm_nt_cfg(cfg, A, B, C, 1.0, 0.0)
+            err = float((C - ref).abs().max() / ref.abs().max())
+            t = timeit(lambda: ops.gemm_nt_cfg(cfg, A, B, C, 1.0, 1.0))
+            print("  cfg %d %dx%dx%d: %.3f ms (%.2f TFLOP/s) err=%.1e" % (cfg, M, N, K, t, 2.0 * M * N * K / t / 1e9, err))
+    from ppbo_b200 import _lib
+    Om = torch.randn(32768, 1000, dtype=torch.float64, device=dev)
+    PhiT = torch.randn(20, 1024, 1000, dtype=torch.float64, device=dev)
+    for cfg in (0, 2, 3):
+        _lib.load().ppbo_set_tuning(0, cfg)
+        t = timeit(lambda: ops.rff_eval_argmax(Om, PhiT), reps=3, warm=1)
+        print("rowmax cfg %d S=32768 F=1000 P=1024 B=20: %.2f ms (%.2f TFLOP/s)" % (cfg, t, 2.0 * 32768 * 1000 * 1024 * 20 / t / 1e9))
+    _lib.load().ppbo_set_tuning(0, 0)
+    if "--gemm-only" in sys.argv:
+        return
     prob = synthetic.make_problem("ackley20d")
     X = ops.to_dev(prob["X"]); th = prob["theta"]; Q, m = prob["Q"], prob["m"]
     t = timeit(lambda: ops.gram_regularized("SE_kernel", X, th[1], th[2], 1e-6))

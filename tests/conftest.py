@@ -8,6 +8,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+SRC = os.path.join(ROOT, "src")          # the drop-in package: flat modules with the reference's names
+if SRC not in sys.path:
+    sys.path.insert(1, SRC)
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 
