@@ -190,7 +190,7 @@ def workload_config(prob, n_gpus):
                             prob["theta"], prob["F"], prob["grids"].shape[0], prob["P"], prob["S"]),
             "parallelism": "fit on rank 0 + broadcast; S sharded over %d rank(s); one all-reduce of 3 x directions doubles" % n_gpus,
             "l2_policy": "working set per step (Sigma, G, factor, Omega, PhiT: > 1 GB) exceeds the 126 MB L2; no explicit flush",
-            "fit_start": "cold (f = 0, omega = 0)"}
+            "fit_start": "cold: GP Newton from f = 0; weight-space Newton from the ridge projection of the GP mode"}
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -218,7 +218,8 @@ def main():
     kernel, theta, Q, m, S = prob["kernel"], prob["theta"], prob["Q"], prob["m"], prob["S"]
     B, P, D = prob["grids"].shape
     Fdim = prob["F"]
-    inputs = iteration.IterationInputs(prob["X"], prob["f_init"], prob["W"], prob["b"], prob["omega0"], prob["grids"])
+    # f_init = None: cold start of the GP Newton iteration at f = 0; omega0 = None: weight-space start projected from the GP mode
+    inputs = iteration.IterationInputs(prob["X"], None, prob["W"], prob["b"], None, prob["grids"])
     sums_host = torch.empty((B, 3), dtype=torch.float64).pin_memory()
 
     def barrier():

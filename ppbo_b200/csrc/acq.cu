@@ -4,6 +4,7 @@
 // evaluations (src/random_fourier_sampler.py:45-53,106-122,166,170).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/ppbo_b200.h"
@@ -248,6 +249,44 @@ __global__ void axpy_out_kernel(double* __restrict__ out, const double* __restri
 int launch_lik_terms(const double* f, int Q, int m, double sigma, double* set_lik, double* beta, double* arrow, double* sa,
                      double* bvec, cudaStream_t st);
 int launch_sum(const double* x, int n, double* out, cudaStream_t st);
+int launch_linesearch_lik(const double* f, const double* df, int Q, int m, double sigma, double* part, cudaStream_t st);
+constexpr int LS_STEPS = 8;      // == NSTEP of laplace.cu: step sizes 1, 1/2, ..., 2^-7
+
+// scal[0..2] = omega.omega, omega.step, step.step ; scal[3] = max|step| ; scal[4] = max|omega| ; scal[8 + c] = sum_q part[c][q]
+__global__ void __launch_bounds__(1024) rff_ls_scalars_kernel(const double* __restrict__ omega, const double* __restrict__ step,
+                                                              int F, const double* __restrict__ part, int Q,
+                                                              double* __restrict__ scal) {
+    __shared__ double red[33];
+    __shared__ double mx[2][32];
+    double s0 = 0, s1 = 0, s2 = 0, m0 = 0, m1 = 0;
+    for (int i = threadIdx.x; i < F; i += 1024) {
+        const double o = omega[i], d = step[i];
+        s0 = fma(o, o, s0);
+        s1 = fma(o, d, s1);
+        s2 = fma(d, d, s2);
+        m0 = fmax(m0, fabs(d));
+        m1 = fmax(m1, fabs(o));
+    }
+    s0 = block_sum(s0, red);
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    }
+    if ((threadIdx.x & 31) == 0) { mx[0][threadIdx.x >> 5] = m0; mx[1][threadIdx.x >> 5] = m1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { m0 = fmax(m0, mx[0][w]); m1 = fmax(m1, mx[1][w]); }
+        scal[0] = s0; scal[1] = s1; scal[2] = s2; scal[3] = m0; scal[4] = m1;
+    }
+    for (int c = 0; c < LS_STEPS; ++c) {
+        double s = 0.0;
+        for (int q = threadIdx.x; q < Q; q += 1024) s += part[(long long)c * Q + q];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) scal[8 + c] = s;
+    }
+}
 
 }  // namespace ppbo
 
@@ -418,14 +457,15 @@ extern "C" int ppbo_rff_value_grad(const double* W, const double* b, int F, int 
 
 extern "C" long long ppbo_rff_workspace_bytes(int F, int Q, int m) {
     const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
-    return (2 * N + 2 * M + Q * 9 + 64 + (long long)F * M + ppbo_factor_doubles(F) + 4 * (long long)F + 2 * CHOL_NB) * 8;
+    return (3 * N + 2 * M + Q * 9 + 64 + (long long)F * M + ppbo_factor_doubles(F) + 4 * (long long)F + 2 * CHOL_NB) * 8;
 }
 
 struct RffWs {
-    double *fvals, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp;
+    double *fvals, *dfv, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp;
     void carve(double* p, int F, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
         fvals = p; p += N;
+        dfv = p; p += N;
         beta = p; p += N;
         arrow = p; p += 2 * M;
         setlik = p; p += 9LL * Q;
@@ -486,45 +526,75 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
     int* info_d = reinterpret_cast<int*>(ws.scal + 32);
     if (omega0) PPBO_CUDA_CHECK(cudaMemcpyAsync(omega_map, omega0, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
     else PPBO_CUDA_CHECK(cudaMemsetAsync(omega_map, 0, sizeof(double) * F, st));
-    int rc, it = 0, info = 0;
-    double h[16], S_cur = NAN, last_rel = INFINITY;
+    int rc, it = 0, info = 0, n_factor = 0, n_chord = 0;
+    double h[32], S_cur = NAN, last_rel = INFINITY;
+    const int N = Q * (m + 1);
+    double* part = ws.setlik + Q;                       // [LS_STEPS][Q]
+    const double CHORD_REL = 0.25;
+    const bool trace = getenv("PPBO_TRACE") != nullptr;
+    bool refactor = true;
     for (it = 0; it < max_iter; ++it) {
-        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, true, ws.scal + 8, st))) return rc;
-        PPBO_CL rff_psi_kernel<<<dim3(ceil_div(M, 256), F), 256, 0, st>>>(Phi_X, ld, Q, m, ws.arrow, ws.PsiT, M);
-        GemmOperands g{ws.PsiT, M, 0, ws.PsiT, M, 0, F, F, M};
-        StoreEpilogue ep{ws.H, F, 0, 1.0, 0.0, 0, 0, 0};
-        if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
-        PPBO_CL add_identity_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.H, F, F);
-        if ((rc = potrf_lower(ws.H, F, F, Hdinv, info_d, st))) return rc;
+        // gradient at omega (always fresh); Hessian factor only on Newton steps, reused on chord steps
+        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, refactor, ws.scal + 24, st))) return rc;
+        if (refactor) {
+            PPBO_CL rff_psi_kernel<<<dim3(ceil_div(M, 256), F), 256, 0, st>>>(Phi_X, ld, Q, m, ws.arrow, ws.PsiT, M);
+            GemmOperands g{ws.PsiT, M, 0, ws.PsiT, M, 0, F, F, M};
+            StoreEpilogue ep{ws.H, F, 0, 1.0, 0.0, 0, 0, 0};
+            if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
+            PPBO_CL add_identity_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.H, F, F);
+            if ((rc = potrf_lower(ws.H, F, F, Hdinv, info_d, st))) return rc;
+            ++n_factor;
+        } else {
+            ++n_chord;
+        }
         PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.step, ws.grad, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
         if ((rc = potrs_vec(ws.H, F, F, Hdinv, ws.step, st))) return rc;      // step = (-Hessian)^-1 grad  (ascent direction)
-        PPBO_CL rff_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, ws.scal);
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
+        // line search, all LS_STEPS step sizes in one pass: f(omega + s step) = f0 + s df, |omega + s step|^2 in closed form
+        PPBO_CL rff_fvals_kernel<<<ceil_div(N, 256), 256, 0, st>>>(Phi_X, ld, F, N, ws.step, ws.dfv);
+        if ((rc = launch_linesearch_lik(ws.fvals, ws.dfv, Q, m, sigma, part, st))) return rc;
+        PPBO_CL rff_ls_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, part, Q, ws.scal);
+        PPBO_LAUNCH_CHECK();
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
         PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
         PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
         if (info) { set_error("weight-space Hessian not positive definite (pivot %d)", info); return info; }
-        S_cur = h[0] - h[8] / m;
-        const double max_step = h[1], max_om = fmax(h[2], 1e-300);
-        double s = 1.0;
-        bool ok = false;
-        for (int c = 0; c < 12; ++c, s *= 0.5) {
-            PPBO_CL axpy_out_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.trial, omega_map, ws.step, s, F);
-            if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, ws.trial, ws, nullptr, nullptr, false, ws.scal + 8, st))) return rc;
-            PPBO_CL rff_scalars_kernel<<<1, 1024, 0, st>>>(ws.trial, nullptr, F, ws.scal);
-            PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
-            PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
-            const double S_try = h[0] - h[8] / m;
-            if (S_try >= S_cur - 1e-13 * fabs(S_cur)) { ok = true; S_cur = S_try; break; }
+        const double oo = h[0], od = h[1], dd = h[2], max_step = h[3], max_om = fmax(h[4], 1e-300);
+        if (std::isnan(S_cur)) S_cur = -0.5 * oo - h[24] / m;
+        int c;
+        double s = 1.0, S_new = S_cur;
+        for (c = 0; c < LS_STEPS; ++c) {
+            s = std::ldexp(1.0, -c);
+            const double S_try = -0.5 * (oo + 2.0 * s * od + s * s * dd) - h[8 + c] / m;
+            if (S_try >= S_cur - 1e-13 * fabs(S_cur)) { S_new = S_try; break; }
         }
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(omega_map, ws.trial, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
+        if (!refactor && c > 0) {            // damped chord direction: refactor at this point instead
+            refactor = true;
+            --it;
+            continue;
+        }
+        if (c == LS_STEPS) { s = std::ldexp(1.0, -(LS_STEPS - 1)); S_new = NAN; }
+        PPBO_CL axpy_kernel<<<ceil_div(F, 256), 256, 0, st>>>(omega_map, ws.step, s, F);
+        PPBO_LAUNCH_CHECK();
+        S_cur = S_new;
+        const double prev_rel = last_rel;
         last_rel = s * max_step / max_om;
-        if (ok && s == 1.0 && last_rel <= tol) { ++it; break; }
+        if (trace) fprintf(stderr, "[ppbo_rff_fit] it %d %s step %.3g rel %.3e S %.12g\n", it, refactor ? "newton" : "chord ", s, last_rel, S_cur);
+        if (c == 0 && last_rel <= tol) { ++it; break; }
+        if (refactor) refactor = !(c == 0 && last_rel <= CHORD_REL);
+        else refactor = !(last_rel <= 0.5 * prev_rel);
+    }
+    if (std::isnan(S_cur)) {                             // last step left S unevaluated: evaluate at the final point
+        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, nullptr, nullptr, false, ws.scal + 24, st))) return rc;
+        PPBO_CL rff_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, nullptr, F, ws.scal);
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        S_cur = h[0] - h[24] / m;
     }
     if (hess_diag) {
-        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, nullptr, hess_diag, true, ws.scal + 8, st))) return rc;
+        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, nullptr, hess_diag, true, ws.scal + 24, st))) return rc;
     }
     PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (stats_h) { stats_h[0] = it; stats_h[1] = last_rel; stats_h[2] = S_cur; stats_h[3] = 0; }
+    if (stats_h) { stats_h[0] = it; stats_h[1] = last_rel; stats_h[2] = S_cur; stats_h[3] = n_factor + 0.001 * n_chord; }
     return PPBO_OK;
 }
 

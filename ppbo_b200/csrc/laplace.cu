@@ -8,6 +8,7 @@
 //     alpha_new = b - B a+^1/2 (I + a+^1/2 G a+^1/2)^-1 a+^1/2 B^T Sigma b ,   b = B a+ B^T f + beta ,  f_new = Sigma alpha_new
 // where G = B^T Sigma B (Qm x Qm) is fixed during the fit.  One Cholesky of size Qm per step, no Sigma^-1.
 #include <cmath>
+#include <cstdlib>
 
 #include "../../include/ppbo_b200.h"
 #include "common.cuh"
@@ -193,6 +194,11 @@ int launch_lik_terms(const double* f, int Q, int m, double sigma, double* set_li
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
+int launch_linesearch_lik(const double* f, const double* df, int Q, int m, double sigma, double* part, cudaStream_t st) {
+    PPBO_CL linesearch_lik_kernel<<<dim3(ceil_div(Q, 8), NSTEP), 256, 0, st>>>(f, df, Q, m, sigma, part);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
 int launch_sum(const double* x, int n, double* out, cudaStream_t st) {
     PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(x, n, out);
     PPBO_LAUNCH_CHECK();
@@ -280,8 +286,10 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     int n_halvings_total = 0;
     // Newton steps refactor I + a+^1/2 G a+^1/2 at the current iterate; once the relative step is below CHORD_REL the factor
     // is kept and only the right-hand side is refreshed (chord steps: same fixed point Sigma^-1 f = beta(f), linear
-    // convergence at the rate of the relative change of a+, ~10x cheaper than a factorisation at Qm = 5000).
-    const double CHORD_REL = 1e-2;
+    // convergence at the rate of the relative change of a+; a chord step costs ~1/6 of a factorisation at Qm = 5000, so it
+    // is kept as long as it at least halves the step).
+    const double CHORD_REL = 0.25;
+    const bool trace = getenv("PPBO_TRACE") != nullptr;
     bool refactor = true, converged = false;
     for (it = 0; it < max_iter; ++it) {
         if (refactor) {
@@ -345,10 +353,11 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         const double prev_rel = last_rel;
         last_step = step * scal_h[4];
         last_rel = last_step / fscale;
+        if (trace) fprintf(stderr, "[ppbo_laplace_fit] it %d %s step %.3g rel %.3e T %.12g\n", it, refactor ? "newton" : "chord ", step, last_rel, T_cur);
         if (step == 1.0 && last_rel <= tol) { ++it; converged = true; break; }
         // chord steps while they contract fast enough (at least 4x per step); otherwise pay for a new factor
         if (refactor) refactor = !(step == 1.0 && last_rel <= CHORD_REL);
-        else refactor = !(last_rel <= 0.25 * prev_rel);
+        else refactor = !(last_rel <= 0.5 * prev_rel);
     }
     (void)converged;
     // consistent products at the mode: arrow (signed), factor of I + a+^1/2 G a+^1/2

@@ -99,14 +99,29 @@ class RFFFit:
     __slots__ = ("W", "b", "sigma_f", "Phi_X", "omega_map", "hess_diag", "stats")
 
 
-def rff_fit(X, W, b, theta, Q, m, omega0=None, max_iter=100, tol=1e-10):
+def rff_fit(X, W, b, theta, Q, m, omega0=None, max_iter=100, tol=1e-10, f_map=None):
+    """omega0=None with f_map given: start from the projection of the GP mode (rff_start_from_gp); else from omega0 / zero"""
     r = RFFFit()
     r.W, r.b, r.sigma_f = W, b, float(theta[2])
     r.Phi_X = ops.rff_features(W, b, X, theta[2], feature_major=True)
+    if omega0 is None and f_map is not None:
+        omega0 = rff_start_from_gp(r.Phi_X, f_map)
     r.omega_map, r.hess_diag, r.stats = ops.rff_fit(r.Phi_X, Q, m, theta[0], omega0=omega0, max_iter=max_iter, tol=tol)
     if r.stats["info"] != 0:
         raise PPBOError("RFF fit: weight-space Hessian not positive definite (info=%d)" % r.stats["info"])
     return r
+
+
+def rff_start_from_gp(Phi_X, f_map, ridge=1e-3):
+    """omega0 = argmin |Phi_X' omega - f_MAP|^2 + lambda |omega|^2: the weight vector whose function is closest to the GP mode.
+    The reference starts its weight-space optimiser at a random omega0 ~ N(0, I) (src/random_fourier_sampler.py:125); S is
+    not concave, so the start decides which optimum is reached -- this one is deterministic and a few Newton steps away."""
+    A = ops.gemm_nt(Phi_X, Phi_X)                      # F x F, contraction over the N design rows
+    ops.shrink_inplace(A, ridge)
+    info, ws = ops.potrf_lower(A)
+    if info != 0:
+        raise PPBOError("feature Gram matrix not positive definite (info=%d)" % info)
+    return ops.potrs_vec(A, ws, ops.gemv(Phi_X, f_map))
 
 
 def line_grids(xis, xs, alphas):
@@ -153,6 +168,8 @@ class IterationInputs:
     def __init__(self, X, f_init, W, b, omega0, grids):
         self.host = {}
         for k, v in zip(self.FIELDS, (X, f_init, W, b, omega0, grids)):
+            if v is None:
+                continue
             t = torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=np.float64)))
             self.host[k] = t.pin_memory() if torch.cuda.is_available() else t
 
@@ -186,7 +203,7 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         mark("gp_fit")
         mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
         mark("mustar")
-        rff = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+        rff = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol, f_map=gp.f_map)
         mark("rff_fit")
         pack[:Fdim].copy_(rff.omega_map)
         pack[Fdim:2 * Fdim].copy_(rff.hess_diag)

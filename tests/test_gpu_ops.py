@@ -270,3 +270,135 @@ def test_rff_map(ops, golden):
     assert gn <= max(np.linalg.norm(O.rff_S_grad(g["rff_omega_MAP"], PhiX, Q, m, sigma)), 1e-8)
     S_ours, S_ref = O.rff_S(wb, PhiX, Q, m, sigma), O.rff_S(g["rff_omega_MAP"], PhiX, Q, m, sigma)
     assert S_ours >= S_ref - 1e-9 * abs(S_ref), (S_ours, S_ref, stats_b)
+
+
+# ----------------------------------------------------------------------------------------------- device RNG / sampling / small ops
+def test_philox_normals_match_oracle(ops):
+    from oracle import ppbo_oracle as O
+    for seed, stream, offset, n in ((1234, 0, 0, 1000), (2**40 + 7, 3, 5, 257), (9, 1, 2**33 + 1, 64), (9, 1, 0, 1)):
+        z = _np(ops.normal_fill(seed, stream, offset, n))
+        ref = O.philox_normals(seed, stream, offset, n)
+        assert np.abs(z - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("F", [96, 97])
+def test_sample_omega_injected_and_sharded(ops, F):
+    from oracle import ppbo_oracle as O
+    rng = np.random.RandomState(F)
+    S = 37
+    w, h = rng.randn(F), -(0.5 + rng.rand(F))
+    Z = rng.randn(S, F)
+    Om = _np(ops.rff_sample_omega(ops.to_dev(w), ops.to_dev(h), S, Z=ops.to_dev(Z)))
+    assert relerr(Om, O.rff_sample_omega(w, h, Z)) < 1e-15
+    # counter-based draws: any split of the sample range reproduces the single-launch draw bit for bit
+    full = _np(ops.rff_sample_omega(ops.to_dev(w), ops.to_dev(h), S, seed=77))
+    ref = O.rff_sample_omega(w, h, O.philox_normals(77, 0, 0, S * F).reshape(S, F))
+    assert np.abs(full - ref).max() <= 1e-13 * np.abs(ref).max()
+    parts = [_np(ops.rff_sample_omega(ops.to_dev(w), ops.to_dev(h), hi - lo, seed=77, sample0=lo)) for lo, hi in ((0, 11), (11, 12), (12, 37))]
+    assert np.array_equal(np.vstack(parts), full)
+
+
+def test_vec_max_and_device_mustar_reduce(ops):
+    rng = np.random.RandomState(4)
+    x = rng.randn(5000)
+    out = ops.vec_max(ops.to_dev(x))
+    assert float(out) == x.max()
+    ops.vec_max(ops.to_dev(x[:10] + 100), out=out, accumulate=True)
+    assert float(out) == (x[:10] + 100).max()
+    fm = rng.randn(3, 777)
+    a = _np(ops.acq_reduce(ops.to_dev(fm), 0.25))
+    b = _np(ops.acq_reduce_dev(ops.to_dev(fm), ops.to_dev(np.array([0.25]))))
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n", [1, 100, 128, 129, 640, 1500])
+def test_potrs_vec_and_potri(ops, n):
+    rng = np.random.RandomState(n)
+    A0 = rng.randn(n, n)
+    A = A0 @ A0.T + n * np.eye(n)
+    Ad = ops.to_dev(A)
+    info, ws = ops.potrf_lower(Ad)
+    assert info == 0
+    b = rng.randn(n)
+    x = _np(ops.potrs_vec(Ad, ws, ops.to_dev(b)))
+    assert np.abs(A @ x - b).max() <= 1e-12 * n * np.abs(b).max()
+    Ainv = _np(ops.potri_lower(Ad, ws))
+    assert np.abs(Ainv @ A - np.eye(n)).max() <= 1e-11 * n
+
+
+def test_shrink_inplace(ops):
+    from oracle import ppbo_oracle as O
+    rng = np.random.RandomState(2)
+    K0 = rng.randn(50, 50)
+    K = K0 @ K0.T
+    out = _np(ops.shrink_inplace(ops.to_dev(K).clone(), 1e-3))
+    assert relerr(out, O.regularize_covariance(K, 1e-3, svd_roundtrip=False)) < 1e-14
+
+
+def test_rff_value_grad(ops, golden):
+    from oracle import ppbo_oracle as O
+    g = golden
+    if "rff_W" not in g:
+        pytest.skip("RFF basis exists for the SE kernel only")
+    W, b, sf = g["rff_W"], g["rff_b"], g["theta"][2]
+    om = g["rff_Omega"][0]
+    x = g["xstar"]
+    out = _np(ops.rff_value_grad(ops.to_dev(W), ops.to_dev(b), ops.to_dev(om), ops.to_dev(x), sf))
+    phi = O.rff_features(W, b, x.reshape(1, -1), sf)[:, 0]
+    assert abs(out[0] - phi @ om) <= 1e-13 * np.abs(phi).sum() * np.abs(om).max()
+    assert relerr(out[1:], O.rff_jacobian(W, b, x, sf).T @ om) < 1e-11
+
+
+def test_gemm_configs_agree(ops):
+    """every tile configuration of the FP64 GEMM building block gives the same product (tuning entry)"""
+    rng = np.random.RandomState(0)
+    A, B = rng.randn(300, 150), rng.randn(260, 150)
+    ref = A @ B.T
+    for cfg in range(6):
+        C = ops.to_dev(np.zeros((300, 260)))
+        ops.gemm_nt_cfg(cfg, ops.to_dev(A), ops.to_dev(B), C)
+        assert np.abs(_np(C) - ref).max() <= 1e-13 * 150 * np.abs(ref).max()
+
+
+def test_iteration_pipeline_matches_oracle(ops):
+    """the whole one-iteration pipeline (what bench.py times) on a small problem against the CPU oracle, and its sample
+    partition: 3 'ranks' evaluated one after the other give the single-rank sums"""
+    import torch
+    from oracle import ppbo_oracle as O
+    from ppbo_b200 import iteration, synthetic
+    prob = synthetic.make_problem("levy10d", Q=12, S=300, P=50, F=64)
+    theta, Q, m, S = prob["theta"], prob["Q"], prob["m"], prob["S"]
+    dev = torch.device("cuda", 0)
+    d = iteration.IterationInputs(prob["X"], None, prob["W"], prob["b"], None, prob["grids"]).to_device(dev)
+    sums, gp, rff = iteration.run_iteration(d, prob["kernel"], theta, Q, m, S, seed=5)
+    X = prob["X"]
+    Sigma = O.regularize_covariance(O.se_kernel(X, X, theta), svd_roundtrip=False)
+    f = _np(gp.f_map)
+    f_tight = O.fmap_tight(Sigma, Q, m, theta[0], f)
+    assert np.abs(f - f_tight).max() <= 1e-6 * np.abs(f_tight).max()
+    PhiX = O.rff_features(prob["W"], prob["b"], X, theta[2])
+    w = _np(rff.omega_map)
+    assert np.linalg.norm(O.rff_S_grad(w, PhiX, Q, m, theta[0])) <= 1e-7
+    hd = O.rff_S_hess_diag(w, PhiX, Q, m, theta[0])
+    Omega = O.rff_sample_omega(w, hd, O.philox_normals(5, 0, 0, S * prob["F"]).reshape(S, -1))
+    alpha = _np(gp.alpha)
+    mustar = max(f.max(), max(float((O.se_kernel(X, g, theta).T @ alpha).max()) for g in prob["grids"]))
+    ref = np.empty((prob["grids"].shape[0], 3))
+    for bi, g in enumerate(prob["grids"]):
+        mx, _ = O.rff_eval_argmax(Omega, O.rff_features(prob["W"], prob["b"], g, theta[2]))
+        ref[bi] = [np.maximum(mx - mustar, 0).sum(), mx.sum(), (mx ** 2).sum()]
+    got = _np(sums)
+    assert np.abs(got - ref).max() <= 1e-8 * np.abs(ref).max()
+    assert int(np.argmax(got[:, 0])) == int(np.argmax(ref[:, 0]))
+    # sample partition: emulate 3 ranks with fake shards (no process group), sum their partial results
+    PhiT = iteration.rff_grid_features(d["W"], d["b"], theta[2], d["grids"])
+    mu_dev = ops.to_dev(np.array([mustar]))
+    total = np.zeros_like(got)
+
+    class FakeShard(iteration.Shard):
+        def __init__(self, rank, world):
+            self.dist, self.group, self.rank, self.world = None, None, rank, world
+    for r in range(3):
+        part, _, _ = iteration.rff_acquisition(rff, PhiT, S, mu_dev, shard=FakeShard(r, 3), seed=5)
+        total += _np(part)
+    assert np.abs(total - got).max() <= 1e-12 * np.abs(got).max()
