@@ -163,14 +163,44 @@ __global__ void __launch_bounds__(256) rff_value_grad_kernel(const double* __res
         if (threadIdx.x == 0) out[1 + d] = amp * t;
     }
 }
-// y[i] = sum_f Phi[f][i] omega[f]   (feature-major Phi: coalesced over i)
-__global__ void __launch_bounds__(256) rff_fvals_kernel(const double* __restrict__ Phi, long long ld, int F, int N,
-                                                        const double* __restrict__ omega, double* __restrict__ y) {
+// y[i] = sum_f Phi[f][i] omega[f]   (feature-major Phi: coalesced over i).  HBM-bound (8 F N bytes): the feature range is cut
+// into FV_SLICES slices so that ~8 x N/128 CTAs stream concurrently; slice partials are combined in a fixed order.
+constexpr int FV_SLICES = 8, FV_COLS = 128;
+__global__ void __launch_bounds__(256) rff_fvals_partial_kernel(const double* __restrict__ Phi, long long ld, int F, int N,
+                                                                const double* __restrict__ omega, double* __restrict__ part) {
+    __shared__ double red[FV_COLS];
+    const int c = threadIdx.x & (FV_COLS - 1), half = threadIdx.x >> 7;          // 128 columns x 2 row phases
+    const int i = blockIdx.x * FV_COLS + c;
+    const int per = (F + FV_SLICES - 1) / FV_SLICES;
+    const int f0 = blockIdx.y * per, f1 = min(F, f0 + per);
+    double s0 = 0.0, s1 = 0.0;
+    if (i < N) {
+        int f = f0 + half;
+        for (; f + 2 < f1; f += 4) {
+            s0 = fma(Phi[(long long)f * ld + i], omega[f], s0);
+            s1 = fma(Phi[(long long)(f + 2) * ld + i], omega[f + 2], s1);
+        }
+        for (; f < f1; f += 2) s0 = fma(Phi[(long long)f * ld + i], omega[f], s0);
+    }
+    if (half == 1) red[c] = s0 + s1;
+    __syncthreads();
+    if (half == 0 && i < N) part[(long long)blockIdx.y * N + i] = (s0 + s1) + red[c];
+}
+__global__ void __launch_bounds__(256) rff_fvals_combine_kernel(const double* __restrict__ part, int N, double* __restrict__ y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     double s = 0.0;
-    for (int f = 0; f < F; ++f) s = fma(Phi[(long long)f * ld + i], omega[f], s);
+#pragma unroll
+    for (int k = 0; k < FV_SLICES; ++k) s += part[(long long)k * N + i];
     y[i] = s;
+}
+// part: FV_SLICES * N doubles of scratch
+static int launch_rff_fvals(const double* Phi, long long ld, int F, int N, const double* omega, double* part, double* y,
+                            cudaStream_t st) {
+    PPBO_CL rff_fvals_partial_kernel<<<dim3(ceil_div(N, FV_COLS), FV_SLICES), 256, 0, st>>>(Phi, ld, F, N, omega, part);
+    PPBO_CL rff_fvals_combine_kernel<<<ceil_div(N, 256), 256, 0, st>>>(part, N, y);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
 }
 // one warp per feature: grad[f] = -omega[f] + sum_rows beta[row] Phi[f][row]
 //                       hdiag[f] = -1 - sum_u arrow[u] (Phi[f][r(u)] - Phi[f][w(u)])^2
@@ -457,15 +487,16 @@ extern "C" int ppbo_rff_value_grad(const double* W, const double* b, int F, int 
 
 extern "C" long long ppbo_rff_workspace_bytes(int F, int Q, int m) {
     const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
-    return (3 * N + 2 * M + Q * 9 + 64 + (long long)F * M + ppbo_factor_doubles(F) + 4 * (long long)F + 2 * CHOL_NB) * 8;
+    return ((3 + FV_SLICES) * N + 2 * M + Q * 9 + 64 + (long long)F * M + ppbo_factor_doubles(F) + 4 * (long long)F + 2 * CHOL_NB) * 8;
 }
 
 struct RffWs {
-    double *fvals, *dfv, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp;
+    double *fvals, *dfv, *fpart, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp;
     void carve(double* p, int F, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
         fvals = p; p += N;
         dfv = p; p += N;
+        fpart = p; p += (long long)FV_SLICES * N;
         beta = p; p += N;
         arrow = p; p += 2 * M;
         setlik = p; p += 9LL * Q;
@@ -482,7 +513,7 @@ struct RffWs {
 static int rff_eval(const double* Phi, long long ld, int F, int Q, int m, double sigma, const double* omega, RffWs& ws,
                     double* grad, double* hdiag, bool want_arrow, double* lik_sum_dev, cudaStream_t st) {
     const int N = Q * (m + 1);
-    PPBO_CL rff_fvals_kernel<<<ceil_div(N, 256), 256, 0, st>>>(Phi, ld, F, N, omega, ws.fvals);
+    launch_rff_fvals(Phi, ld, F, N, omega, ws.fpart, ws.fvals, st);
     launch_lik_terms(ws.fvals, Q, m, sigma, ws.setlik, ws.beta, want_arrow ? ws.arrow : nullptr, nullptr, nullptr, st);
     launch_sum(ws.setlik, Q, lik_sum_dev, st);
     if (grad || hdiag)
@@ -550,7 +581,7 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
         PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.step, ws.grad, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
         if ((rc = potrs_vec(ws.H, F, F, Hdinv, ws.step, st))) return rc;      // step = (-Hessian)^-1 grad  (ascent direction)
         // line search, all LS_STEPS step sizes in one pass: f(omega + s step) = f0 + s df, |omega + s step|^2 in closed form
-        PPBO_CL rff_fvals_kernel<<<ceil_div(N, 256), 256, 0, st>>>(Phi_X, ld, F, N, ws.step, ws.dfv);
+        launch_rff_fvals(Phi_X, ld, F, N, ws.step, ws.fpart, ws.dfv, st);
         if ((rc = launch_linesearch_lik(ws.fvals, ws.dfv, Q, m, sigma, part, st))) return rc;
         PPBO_CL rff_ls_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, part, Q, ws.scal);
         PPBO_LAUNCH_CHECK();

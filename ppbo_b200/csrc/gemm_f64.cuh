@@ -196,13 +196,22 @@ struct RowMaxEpilogue {
     const double* bias; long long strideBias;   // [N] per batch, may be null
     double* out_max; int* out_arg;              // [batch][M]
     double* out_full; long long ld_full; long long strideFull;   // optional dense S x P output (tests), may be null
+    int batch, group_m;     // launch shape: 1-D grid over (row-tile group, batch entry, row tile in group), see the kernel
 };
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_rowmax_kernel(GemmOperands g, RowMaxEpilogue ep) {
     extern __shared__ __align__(16) double smem[];
-    const int m0 = blockIdx.x * Cfg::BM;
-    const int bz = blockIdx.y;
+    // CTA order: row tiles are taken in groups of group_m; inside a group all batch entries (query directions) are visited
+    // before moving on, so the group's A rows (group_m x BM x K doubles, sized to sit in L2) are reused `batch` times from L2
+    // and the B operand of one batch entry is shared by the ~SM-count CTAs running at the same time.
+    const int tiles_m = (g.M + Cfg::BM - 1) / Cfg::BM;
+    const int per_group = ep.group_m * ep.batch;
+    const int grp = blockIdx.x / per_group, rem = blockIdx.x % per_group;
+    const int rows_here = min(ep.group_m, tiles_m - grp * ep.group_m);
+    const int bz = rem / rows_here;
+    const int m0 = (grp * ep.group_m + rem % rows_here) * Cfg::BM;
+    if (bz >= ep.batch) return;                  // tail of the last (smaller) group
     const double* A = g.A + (long long)bz * g.strideA;
     const double* B = g.B + (long long)bz * g.strideB;
     const double* bias = ep.bias ? ep.bias + (long long)bz * ep.strideBias : nullptr;

@@ -2,6 +2,7 @@
 // Replaces the LAPACK/BLAS calls the reference reaches through numpy/scipy (dpotrf/dposv under
 // scipy.linalg.solve(assume_a='pos') in src/misc.py:96-100 and under scipy's trust-exact used by
 // src/gp_model.py:382-384; dgemm/dgemv under np.dot in src/gp_model.py:441-458).
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -96,10 +97,19 @@ int launch_gemm_nt(const GemmOperands& g, const StoreEpilogue& ep_in, int batch,
 }
 
 template <class Cfg>
-static int launch_rowmax_cfg(const GemmOperands& g, const RowMaxEpilogue& ep, int batch, cudaStream_t st) {
+static int launch_rowmax_cfg(const GemmOperands& g, const RowMaxEpilogue& ep_in, int batch, cudaStream_t st) {
     int rc = set_smem_attr_rowmax<Cfg>();
     if (rc) return rc;
-    dim3 grid(ceil_div(g.M, Cfg::BM), batch, 1);
+    RowMaxEpilogue ep = ep_in;
+    const int tiles_m = ceil_div(g.M, Cfg::BM);
+    // A rows of one group ~48 MB (L2 is 126 MB; the B operand of the 2-3 batch entries in flight takes another ~25 MB)
+    const long long tile_bytes = (long long)Cfg::BM * max(g.K, 1) * 8;
+    int group_m = (int)std::max<long long>(8, std::min<long long>(tiles_m, (48LL << 20) / tile_bytes));
+    if (g.strideA != 0) group_m = tiles_m;      // A differs per batch entry (exact-GP draws): nothing to reuse across entries
+    ep.batch = batch;
+    ep.group_m = group_m;
+    const int groups = ceil_div(tiles_m, group_m);
+    dim3 grid((unsigned)((long long)groups * group_m * batch), 1, 1);
     PPBO_CL gemm_nt_rowmax_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, ep);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
@@ -112,8 +122,10 @@ int launch_gemm_nt_rowmax(const GemmOperands& g, const RowMaxEpilogue& ep, int b
     PPBO_REQUIRE(g.N > 0 && g.K >= 0, "empty grid");
     const bool v2 = operands_vec2(g);
     const bool small = (long long)ceil_div(g.M, 128) * batch < PPBO_SM_COUNT;
-    if (v2 && !small && g_tuning[0] == 2) return launch_rowmax_cfg<CfgTall3>(g, ep, batch, st);
+    // default for large problems: 128 x 64 tiles, 2 CTAs / SM (32.0 TFLOP/s on the Ackley-20D contraction vs 29.7 for 128 x 128)
+    if (v2 && !small && g_tuning[0] == 1) return launch_rowmax_cfg<CfgBig>(g, ep, batch, st);
     if (v2 && !small && g_tuning[0] == 3) return launch_rowmax_cfg<CfgSq16>(g, ep, batch, st);
+    if (v2 && !small) return launch_rowmax_cfg<CfgTall3>(g, ep, batch, st);
     if (small) return v2 ? launch_rowmax_cfg<CfgSmall>(g, ep, batch, st) : launch_rowmax_cfg<CfgSmallU>(g, ep, batch, st);
     return v2 ? launch_rowmax_cfg<CfgBig>(g, ep, batch, st) : launch_rowmax_cfg<CfgBigU>(g, ep, batch, st);
 }
@@ -214,6 +226,51 @@ __device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, i
     }
 }
 
+// Same contract as smem_gemm, on the FP64 tensor pipe: each warp owns 16 x 16 output tiles (2 x 2 DMMA.8x8x4 tiles) and
+// loads one double per lane and fragment, i.e. 1/16 shared-memory load per FMA instead of 1 (the scalar version is
+// LDS-bandwidth bound and took ~33 us of the diagonal-block kernel).  m, n multiples of 16, K a multiple of 4.
+template <bool B_KMAJOR>
+__device__ __forceinline__ void smem_gemm_mma(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n,
+                                              int K, double sign, bool acc, bool lower_only) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+    const int tm = m >> 4, tn = n >> 4;
+    for (int t = warp; t < tm * tn; t += POTF2_THREADS / 32) {
+        const int ti = t % tm, tj = t / tm;
+        if (lower_only && ti < tj) continue;
+        const int i0 = ti * 16, j0 = tj * 16;
+        double c[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+        const double* a0 = A + (i0 + gq) * lda + t4;
+        const double* a1 = a0 + 8 * lda;
+#pragma unroll 4
+        for (int k = 0; k < K; k += 4) {
+            const double x0 = a0[k], x1 = a1[k];
+            double y0, y1;
+            if (B_KMAJOR) {
+                y0 = B[(k + t4) * ldb + j0 + gq];
+                y1 = B[(k + t4) * ldb + j0 + 8 + gq];
+            } else {
+                y0 = B[(j0 + gq) * ldb + k + t4];
+                y1 = B[(j0 + 8 + gq) * ldb + k + t4];
+            }
+            dmma884(c[0][0], x0, y0);
+            dmma884(c[0][1], x0, y1);
+            dmma884(c[1][0], x1, y0);
+            dmma884(c[1][1], x1, y1);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int i = i0 + mi * 8 + gq, j = j0 + ni * 8 + 2 * t4 + e;
+                    if (lower_only && i < j) continue;
+                    double* dst = C + i * ldc + j;
+                    *dst = (acc ? *dst : 0.0) + sign * c[mi][ni][e];
+                }
+    }
+}
+
 // warp-level Cholesky + inverse of a 32 x 32 block held in shared memory (row stride lds).  Lane i owns row i in registers;
 // column k of the running Schur complement is exchanged through a double-buffered shared-memory line read back as broadcast
 // loads (one __syncwarp per column, no shuffles).  wsm: 96 doubles of scratch.  Returns 0 or the 1-based index of the first
@@ -294,14 +351,14 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
         if (bad_s) break;                                   // uniform
         if (rem > 0) {
             // sub-panel: Tm[rem x 32] = A21 . inv(L11)^T ; copy back ; trailing: S22 -= L21 L21^T (lower)
-            smem_gemm<false>(Tm, POTF2_LDT, S + c1 * POTF2_LDS + c0, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, POTF2_LDR, rem,
+            smem_gemm_mma<false>(Tm, POTF2_LDT, S + c1 * POTF2_LDS + c0, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, POTF2_LDR, rem,
                              POTF2_SUB, POTF2_SUB, 1.0, false, false);
             __syncthreads();
             for (int e = tid; e < rem * POTF2_SUB; e += POTF2_THREADS) {
                 const int i = e >> 5, j = e & 31;
                 S[(c1 + i) * POTF2_LDS + c0 + j] = Tm[i * POTF2_LDT + j];
             }
-            smem_gemm<false>(S + c1 * POTF2_LDS + c1, POTF2_LDS, Tm, POTF2_LDT, Tm, POTF2_LDT, rem, rem, POTF2_SUB, -1.0, true, true);
+            smem_gemm_mma<false>(S + c1 * POTF2_LDS + c1, POTF2_LDS, Tm, POTF2_LDT, Tm, POTF2_LDT, rem, rem, POTF2_SUB, -1.0, true, true);
             __syncthreads();
         }
     }
@@ -318,13 +375,13 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     __syncthreads();
     for (int h = 0; h < 2; ++h) {          // Tm[h] = C . inv(A1)   (inv(A1) row-major [k][j])
         const int o = h * 64;
-        smem_gemm<true>(Tm + h * 32 * POTF2_LDT, POTF2_LDT, S + (o + 32) * POTF2_LDS + o, POTF2_LDS,
+        smem_gemm_mma<true>(Tm + h * 32 * POTF2_LDT, POTF2_LDT, S + (o + 32) * POTF2_LDS + o, POTF2_LDS,
                         Rd + (2 * h) * POTF2_SUB * POTF2_LDR, POTF2_LDR, 32, 32, 32, 1.0, false, false);
     }
     __syncthreads();
     for (int h = 0; h < 2; ++h) {          // C = -inv(A2) . Tm[h]
         const int o = h * 64;
-        smem_gemm<true>(S + (o + 32) * POTF2_LDS + o, POTF2_LDS, Rd + (2 * h + 1) * POTF2_SUB * POTF2_LDR, POTF2_LDR,
+        smem_gemm_mma<true>(S + (o + 32) * POTF2_LDS + o, POTF2_LDS, Rd + (2 * h + 1) * POTF2_SUB * POTF2_LDR, POTF2_LDR,
                         Tm + h * 32 * POTF2_LDT, POTF2_LDT, 32, 32, 32, -1.0, false, false);
     }
     __syncthreads();
@@ -335,9 +392,9 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     }
     __syncthreads();
     // level 2: C (rows 64.., cols 0..63) <- -inv(B) C inv(A), A = S[0:64,0:64], B = S[64:128,64:128] (both lower triangular)
-    smem_gemm<true>(Tm, POTF2_LDT, S + 64 * POTF2_LDS, POTF2_LDS, S, POTF2_LDS, 64, 64, 64, 1.0, false, false);
+    smem_gemm_mma<true>(Tm, POTF2_LDT, S + 64 * POTF2_LDS, POTF2_LDS, S, POTF2_LDS, 64, 64, 64, 1.0, false, false);
     __syncthreads();
-    smem_gemm<true>(S + 64 * POTF2_LDS, POTF2_LDS, S + 64 * POTF2_LDS + 64, POTF2_LDS, Tm, POTF2_LDT, 64, 64, 64, -1.0, false, false);
+    smem_gemm_mma<true>(S + 64 * POTF2_LDS, POTF2_LDS, S + 64 * POTF2_LDS + 64, POTF2_LDS, Tm, POTF2_LDT, 64, 64, 64, -1.0, false, false);
     __syncthreads();
     for (int e = tid; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS) {
         const int i = e >> 7, j = e & 127;
@@ -503,46 +560,51 @@ __global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ 
 // co-resident (nblk <= 128 <= SM count), and every CTA only waits on CTAs with a smaller blockIdx.
 constexpr int TRSV_THREADS = 512;
 
-__device__ __forceinline__ void trsv_wait(volatile int* flag) {
-    if (threadIdx.x == 0) {
-        while (*flag == 0) { __nanosleep(40); }
-    }
-    __syncthreads();
+// every lane polls (one transaction per warp); acquire so that the dependency's values are visible afterwards
+__device__ __forceinline__ void trsv_wait(const int* flag) {
+    int v;
+    do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == 0) __nanosleep(20);
+    } while (v == 0);
 }
-__device__ __forceinline__ void trsv_publish(volatile int* flag) {
+__device__ __forceinline__ void trsv_publish(int* flag) {
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) *flag = 1;
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
 }
 
-// forward: L y = t (in place).  CTA c: v = t_c - sum_{J<c} L[c,J] y_J ; y_c = inv(L_cc) v
+// forward: L y = t (in place).  CTA c: v = t_c - sum_{J<c} L[c,J] y_J ; y_c = inv(L_cc) v.
+// Warp w owns rows w, w+16, ... of the block; the L tile of dependency J is requested BEFORE the flag of J is polled, so on
+// the critical path (J = c-1) only the 128 values of y_J, one FMA sweep and the 128 x 128 triangular product remain.
+// No block-wide barrier inside the dependency loop.
 __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_chain(const double* __restrict__ L, long long ldl, int n,
                                                                const double* __restrict__ dinv, double* t, int* flags) {
     extern __shared__ double sm[];
     double* dtile = sm;                       // inv(L_cc), 128 x 128 row-major
-    double* yJ = sm + CHOL_NB * CHOL_NB;      // [128]
-    double* v = yJ + CHOL_NB;                 // [128]
+    double* v = sm + CHOL_NB * CHOL_NB;       // [128]
     const int c = blockIdx.x, j0 = c * CHOL_NB, jb = min(CHOL_NB, n - j0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double* dsrc = dinv + (long long)c * CHOL_NB * CHOL_NB;
     for (int e = tid; e < CHOL_NB * CHOL_NB; e += TRSV_THREADS) dtile[e] = dsrc[e];
-    double s[8];                              // warp w owns rows w, w+16, ... (8 rows); lanes stride over the 128 columns
+    double s[8];
 #pragma unroll
     for (int rr = 0; rr < 8; ++rr) s[rr] = 0.0;
     for (int J = 0; J < c; ++J) {
-        trsv_wait(flags + J);
-        if (tid < CHOL_NB) yJ[tid] = __ldcg(t + (long long)J * CHOL_NB + tid);
-        __syncthreads();
-        const double y0 = yJ[lane], y1 = yJ[lane + 32], y2 = yJ[lane + 64], y3 = yJ[lane + 96];
+        double l[8][4];
 #pragma unroll
         for (int rr = 0; rr < 8; ++rr) {
-            const int row = warp + 16 * rr;
-            if (row < jb) {
-                const double* lr = L + (long long)(j0 + row) * ldl + (long long)J * CHOL_NB;
-                s[rr] = fma(lr[lane], y0, fma(lr[lane + 32], y1, fma(lr[lane + 64], y2, fma(lr[lane + 96], y3, s[rr]))));
-            }
+            const int row = min(warp + 16 * rr, jb - 1);                     // clamp: rows >= jb are discarded below
+            const double* lr = L + (long long)(j0 + row) * ldl + (long long)J * CHOL_NB + lane;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) l[rr][q] = lr[32 * q];
         }
-        __syncthreads();
+        trsv_wait(flags + J);
+        const double* yJ = t + (long long)J * CHOL_NB + lane;
+        const double y0 = __ldcg(yJ), y1 = __ldcg(yJ + 32), y2 = __ldcg(yJ + 64), y3 = __ldcg(yJ + 96);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr)
+            s[rr] = fma(l[rr][0], y0, fma(l[rr][1], y1, fma(l[rr][2], y2, fma(l[rr][3], y3, s[rr]))));
     }
 #pragma unroll
     for (int rr = 0; rr < 8; ++rr) {
@@ -563,43 +625,49 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_fwd_chain(const double* __r
     trsv_publish(flags + c);
 }
 
-// backward: L^T x = y (in place).  blockIdx b handles block c = nblk-1-b: v = y_c - sum_{K>c} L[K,c]^T x_K ; x_c = inv(L_cc)^T v
+// backward: L^T x = y (in place).  blockIdx b handles block c = nblk-1-b: v = y_c - sum_{K>c} L[K,c]^T x_K ; x_c = inv(L_cc)^T v.
+// Thread (g, k): column k of the block, rows g*32 .. g*32+31 of every dependency tile; the 32 x-values a warp needs are one
+// coalesced load, broadcast by shuffle.  No block-wide barrier inside the dependency loop.
 __global__ void __launch_bounds__(TRSV_THREADS) trsv_bwd_chain(const double* __restrict__ L, long long ldl, int n, int nblk,
                                                                const double* __restrict__ dinv, double* t, int* flags) {
     extern __shared__ double sm[];
     double* dtile = sm;
-    double* xK = sm + CHOL_NB * CHOL_NB;      // [128]
-    double* part = xK + CHOL_NB;              // [4][128]
+    double* xv = sm + CHOL_NB * CHOL_NB;      // [128]
+    double* part = xv + CHOL_NB;              // [4][128]
     const int c = nblk - 1 - (int)blockIdx.x, j0 = c * CHOL_NB;
-    const int tid = threadIdx.x, g = tid >> 7, k = tid & 127;     // 4 row groups x 128 columns
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 7, k = tid & 127;     // 4 row groups x 128 columns
     const double* dsrc = dinv + (long long)c * CHOL_NB * CHOL_NB;
     for (int e = tid; e < CHOL_NB * CHOL_NB; e += TRSV_THREADS) dtile[e] = dsrc[e];
-    double acc = 0.0;
-    const bool col_ok = j0 + k < n;
+    double acc0 = 0.0, acc1 = 0.0;
+    const int col = min(j0 + k, n - 1);       // clamp: columns >= n are discarded below
     for (int K = nblk - 1; K > c; --K) {
-        trsv_wait(flags + K);
-        if (tid < CHOL_NB) xK[tid] = (K * CHOL_NB + tid < n) ? __ldcg(t + (long long)K * CHOL_NB + tid) : 0.0;
-        __syncthreads();
         const int kb = min(CHOL_NB, n - K * CHOL_NB);
-        if (col_ok) {
-            const double* lk = L + (long long)(K * CHOL_NB + g * 32) * ldl + j0 + k;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r)
-                if (g * 32 + r < kb) acc = fma(lk[(long long)r * ldl], xK[g * 32 + r], acc);
+        double l[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int row = min(K * CHOL_NB + g * 32 + r, n - 1);
+            l[r] = L[(long long)row * ldl + col];
         }
-        __syncthreads();
+        trsv_wait(flags + K);
+        const int xr = g * 32 + lane;
+        const double xmine = (xr < kb) ? __ldcg(t + (long long)K * CHOL_NB + xr) : 0.0;    // rows >= kb contribute nothing
+#pragma unroll
+        for (int r = 0; r < 32; r += 2) {
+            acc0 = fma(l[r], __shfl_sync(0xffffffffu, xmine, r), acc0);
+            acc1 = fma(l[r + 1], __shfl_sync(0xffffffffu, xmine, r + 1), acc1);
+        }
     }
-    part[g * CHOL_NB + k] = acc;
+    part[g * CHOL_NB + k] = acc0 + acc1;
     __syncthreads();
     if (tid < CHOL_NB) {
         const double a = part[tid] + part[CHOL_NB + tid] + part[2 * CHOL_NB + tid] + part[3 * CHOL_NB + tid];
-        xK[tid] = (j0 + tid < n) ? t[j0 + tid] - a : 0.0;          // v
+        xv[tid] = (j0 + tid < n) ? t[j0 + tid] - a : 0.0;          // v
     }
     __syncthreads();
     {   // x_c[k] = sum_{r >= k} dinv[r][k] v[r]; thread (g, k) takes rows r = g, g+4, ...
         double a = 0.0;
         for (int r = g; r < CHOL_NB; r += 4)
-            if (r >= k) a = fma(dtile[r * CHOL_NB + k], xK[r], a);
+            if (r >= k) a = fma(dtile[r * CHOL_NB + k], xv[r], a);
         part[g * CHOL_NB + k] = a;
     }
     __syncthreads();

@@ -1,0 +1,50 @@
+"""Summarise ncu outputs brought back in gpurun_out/ into small text files for profiles/ (run here, no GPU needed).
+  python scripts/ncu_summary.py launches gpurun_out/r01_launches.csv            -> per-kernel share table
+  python scripts/ncu_summary.py rep gpurun_out/r01_rowmax.ncu-rep               -> key raw metrics per captured launch"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fp64.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+        "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum"]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", r["Kernel Name"])
+        v = float(r["Metric Value"].replace(",", ""))
+        v = {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(r["Metric Unit"], v)
+        agg.setdefault(name, []).append(v)
+    tot = sum(sum(v) for v in agg.values())
+    print("# %d launches, %.1f us total (cold-cache, serialised: compare SHARES, not absolutes)" % (sum(len(v) for v in agg.values()), tot))
+    print("%-78s %6s %12s %9s %7s" % ("kernel", "n", "total_us", "mean_us", "share"))
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        print("%-78s %6d %12.1f %9.1f %6.1f%%" % (k[:78], len(v), sum(v), sum(v) / len(v), 100 * sum(v) / tot))
+
+
+def rep(path, keys=KEYS):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        print("== %s  grid=%s block=%s" % (re.sub(r"\(.*", "", r[col["Kernel Name"]])[:100], r[col.get("Grid Size", 0)], r[col.get("Block Size", 0)]))
+        for k in keys:
+            if k in col:
+                print("   %-70s %s %s" % (k, r[col[k]], units[col[k]]))
+
+
+if __name__ == "__main__":
+    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2])

@@ -61,7 +61,7 @@ def main():
     from ppbo_b200 import _lib
     Om = torch.randn(32768, 1000, dtype=torch.float64, device=dev)
     PhiT = torch.randn(20, 1024, 1000, dtype=torch.float64, device=dev)
-    for cfg in (0, 2, 3):
+    for cfg in (0, 1, 3):
         _lib.load().ppbo_set_tuning(0, cfg)
         t = timeit(lambda: ops.rff_eval_argmax(Om, PhiT), reps=3, warm=1)
         print("rowmax cfg %d S=32768 F=1000 P=1024 B=20: %.2f ms (%.2f TFLOP/s)" % (cfg, t, 2.0 * 32768 * 1000 * 1024 * 20 / t / 1e9))
