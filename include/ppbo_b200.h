@@ -182,6 +182,27 @@ int ppbo_rff_eval_argmax(const double* Omega, long long ldo, int S, int F, const
                          long long stridePhi, int P, int batch, double* fmax, int* arg, double* Fs_full,
                          void* stream);
 
+/* ---- K3 on the tcgen05 INT8 tensor pipe (csrc/ozaki.cu) -----------------------------------------------------------------
+ * The same contraction as ppbo_rff_eval_argmax (Hsampler.return_xstar's objective, src/random_fourier_sampler.py:166,170,
+ * batched over samples and grid points), evaluated to FP64 accuracy by error-free splitting: every operand row is scaled by a
+ * power of two and cut into `slices` balanced base-256 digit planes (INT8); slices (slices+1)/2 exact INT8 x INT8 -> INT32
+ * tensor-core GEMMs are recombined in INT64/FP64.  Deterministic and bit-reproducible (oracle: ppbo_oracle.ozaki_matmul).
+ * Truncation error <= (slices+1) K 2^(-8 slices - 2) |row|_max |col|_max (slices = 6: 1e-11 .. 1e-12 relative in practice). */
+/* tile height of the digit-plane layout: operand 0 = samples (A, 128 rows), 1 = grid points (B, 64 rows) */
+int ppbo_ozaki_tile_rows(int operand);
+/* bytes of the digit planes / doubles of the row scales for `batch` matrices of rows x K */
+long long ppbo_ozaki_plane_bytes(int rows, int K, int tile_rows, int batch, int slices);
+long long ppbo_ozaki_scale_doubles(int rows, int tile_rows, int batch);
+/* X[batch][rows x K] (row stride ldx, batch stride strideX) -> scale[batch][rows_pad] (powers of two) and the INT8 digit planes
+ * in the tiled shared-memory image of the tensor-core operand (layout: csrc/ozaki.cu, tile_offset) */
+int ppbo_ozaki_slice(const double* X, long long ldx, long long strideX, int rows, int K, int tile_rows, int batch, int slices,
+                     double* scale, signed char* planes, void* stream);
+/* fmax[batch][S], arg[batch][S] = per-sample max / first arg-max over the P grid points of A . B_b^T from digit planes
+ * (A sliced with tile_rows(0), batch 1; B with tile_rows(1), `batch` grids).  Fs_full (optional, tests): dense [batch][S x P].
+ * err_flag (optional, device int): set to the id of a starved pipeline wait before the kernel traps (never on a healthy run). */
+int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascale, int S, const signed char* Bplanes, const double* bscale,
+                      int P, int batch, int K, int slices, double* fmax, int* arg, double* Fs_full, int* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

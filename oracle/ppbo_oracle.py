@@ -361,3 +361,73 @@ def rff_sample_omega(omega_map, hess_diag, Z):
     """src/random_fourier_sampler.py:134-137,207-213 with the (diagonal) Laplace covariance 1 / -hess_diag and injected
     standard normals Z [S x F]."""
     return np.asarray(omega_map)[None, :] + np.asarray(Z) / np.sqrt(-np.asarray(hess_diag))[None, :]
+
+
+# --------------------------------------------------------------------------- INT8 error-free splitting (csrc/ozaki.cu)
+# Restatement of the arithmetic of the tcgen05 path of the sampling contraction (batched objective of
+# Hsampler.return_xstar, src/random_fourier_sampler.py:166,170).  Integer arithmetic is exact, so the CUDA kernels must
+# reproduce these functions bit for bit.
+OZAKI_KB = 64        # bytes of K per digit-plane tile
+
+
+def ozaki_rowscale(X):
+    """scale[r] = 2^(E+2), max_k |X[r,k]| = m 2^E with m in [1/2, 1); 1 for an all-zero row."""
+    amax = np.abs(np.asarray(X, dtype=np.float64)).max(axis=1)
+    _, e = np.frexp(amax)
+    return np.where(amax > 0, np.ldexp(1.0, e + 2), 1.0)
+
+
+def ozaki_digits(X, slices):
+    """(digits [slices, rows, K] int8, scale [rows]):  X[r,k] ~= scale[r] * sum_i digits[i,r,k] 256^-(i+1).
+    One rounding (half-to-even) to a fixed-point integer of 8*slices bits, then balanced base-256 digits in [-128, 127]."""
+    X = np.asarray(X, dtype=np.float64)
+    scale = ozaki_rowscale(X)
+    Y = np.rint(X * np.ldexp(1.0 / scale, 8 * slices)[:, None]).astype(np.int64)
+    digits = np.empty((slices,) + X.shape, dtype=np.int8)
+    for s in range(slices - 1, -1, -1):
+        d = ((Y + 128) & 255) - 128
+        Y = (Y - d) >> 8
+        digits[s] = d.astype(np.int8)
+    assert not Y.any()
+    return digits, scale
+
+
+def ozaki_planes(digits, tile_rows):
+    """byte image of the digit planes as the tensor-core operand reads them: [row tile][k block][slice][tile_rows x 64 B] with
+    the 8 x 16 B core matrices of the no-swizzle K-major UMMA layout (8-row groups 512 B apart, K chunks 128 B apart)."""
+    KS, rows, K = digits.shape
+    NT, KBLK = -(-rows // tile_rows), -(-K // OZAKI_KB)
+    pad = np.zeros((KS, NT * tile_rows, KBLK * OZAKI_KB), dtype=np.int8)
+    pad[:, :rows, :K] = digits
+    # (s, rt, rg, r8, kb, c, byte) -> (rt, kb, s, rg, c, r8, byte)
+    t = pad.reshape(KS, NT, tile_rows // 8, 8, KBLK, OZAKI_KB // 16, 16).transpose(1, 4, 0, 2, 5, 3, 6)
+    return np.ascontiguousarray(t).reshape(-1)
+
+
+def ozaki_matmul(A, B, slices):
+    """C = A . B^T through `slices` digit planes per operand: exact integer accumulators acc_d = sum_{i+j=d} A_i . B_j^T for
+    d < slices, recombined as (hi + lo) in INT64 -> FP64 with ONE rounding, then the two power-of-two row scales."""
+    da, sa = ozaki_digits(A, slices)
+    db, sb = ozaki_digits(B, slices)
+    g1 = min(3, slices)
+    hi = np.zeros((A.shape[0], B.shape[0]), dtype=np.int64)
+    lo = np.zeros_like(hi)
+    fa, fb = da.astype(np.float64), db.astype(np.float64)          # float64 BLAS on small integers is exact (< 2^53)
+    for d in range(slices):
+        acc = np.zeros(hi.shape)
+        for i in range(d + 1):
+            acc += fa[i] @ fb[d - i].T
+        acc = acc.astype(np.int64)
+        assert np.abs(acc).max() < 2 ** 31
+        if d < g1:
+            hi = hi * 256 + acc
+        else:
+            lo = lo * 256 + acc
+    v = lo.astype(np.float64) * np.ldexp(1.0, -8 * (slices + 1)) + hi.astype(np.float64) * np.ldexp(1.0, -8 * (g1 + 1))
+    return v * sb[None, :] * sa[:, None]
+
+
+def ozaki_eval_argmax(Omega, PhiT, slices):
+    """per-sample max / first arg-max of ozaki_matmul(Omega, PhiT): what ppbo_ozaki_rowmax returns for one grid"""
+    Fs = ozaki_matmul(Omega, PhiT, slices)
+    return Fs.max(axis=1), Fs.argmax(axis=1).astype(np.int32), Fs

@@ -64,6 +64,11 @@ _SIGNATURES = {
     "ppbo_normal_fill": (_I, [c_ulonglong, c_uint, _L, _P, _L, _P]),
     "ppbo_rff_sample_omega": (_I, [_P, _P, _P, _L, c_ulonglong, c_uint, _L, _I, _I, _P, _L, _P]),
     "ppbo_rff_eval_argmax": (_I, [_P, _L, _I, _I, _P, _L, _L, _I, _I, _P, _P, _P, _P]),
+    "ppbo_ozaki_tile_rows": (_I, [_I]),
+    "ppbo_ozaki_plane_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "ppbo_ozaki_scale_doubles": (_L, [_I, _I, _I]),
+    "ppbo_ozaki_slice": (_I, [_P, _L, _L, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "ppbo_ozaki_rowmax": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -1,0 +1,462 @@
+// ppbo_b200 -- K3 on the 5th-generation tensor cores: the RFF sampling contraction  Fs = Omega[S x F] . PhiT[P x F]^T
+// (batched form of the objective of Hsampler.return_xstar, src/random_fourier_sampler.py:166,170) evaluated to FP64 accuracy
+// with INT8 tcgen05.mma and INT32 accumulators in TMEM (error-free splitting, "Ozaki scheme"), fused with the per-sample
+// max / first arg-max over the grid.
+//
+// tcgen05 has no f64 kind; the FP64 DMMA pipe of sm_100a peaks at 37 TFLOP/s, the INT8 tensor pipe at ~4.5 POP/s.  Every row
+// of an operand is scaled by a power of two (|x| 2^-e < 1/4), rounded once to a fixed-point integer of 8 KS bits and cut into
+// KS balanced base-256 digits d_0..d_{KS-1} in [-128, 127]:
+//
+//      x  ~=  2^e * sum_i d_i 256^-(i+1)                                   (exact when the row's dynamic range fits 8 KS - 2 bits)
+//
+// The digit planes are INT8 matrices; products of digit planes are exact in INT32 (|sum| <= KS * Kpad * 2^14 < 2^31), so
+//
+//      C[r][c] = 2^(ea_r + eb_c) * sum_{d < KS} 256^-(d+2) * acc_d[r][c],    acc_d = sum_{i+j=d} A_i . B_j^T     (exact integers)
+//
+// drops only the digit pairs with i + j >= KS (relative weight 256^-KS against |row|_max |col|_max).  KS (KS+1)/2 INT8 GEMMs
+// replace one FP64 GEMM; the result is a deterministic function of the inputs (no dependence on tile shape, launch shape or
+// rank), which the oracle reproduces bit for bit with integer arithmetic (oracle/ppbo_oracle.py ozaki_*).
+//
+// Kernel structure (one persistent CTA per SM, 192 threads):
+//   warp 0      producer: one cp.async.bulk per operand and k-block (the digit planes are stored in HBM already in the
+//               shared-memory image the tensor core reads, see slice layout below) -> 3-stage mbarrier ring
+//   warp 1      one elected lane issues tcgen05.mma.kind::i8 (M=128, N=BN, K=32): KS accumulators of BN columns in TMEM
+//   warps 2..5  epilogue: tcgen05.ld the KS INT32 accumulators, recombine in INT64 -> FP64, scale, running row max/arg-max
+#include <cmath>
+#include <cstdint>
+#include <mutex>
+
+#include "../../include/ppbo_b200.h"
+#include "common.cuh"
+
+namespace ppbo {
+namespace oz {
+
+constexpr int BM = 128;                      // rows of the A tile = TMEM lanes
+constexpr int KB = 64;                       // bytes of K per pipeline stage and digit plane
+constexpr int UMMA_K = 32;                   // K of one tcgen05.mma.kind::i8
+constexpr int LBO = 128;                     // byte distance of K-adjacent 8 x 16 B core matrices
+constexpr int SBO = (KB / 16) * 128;         // byte distance of 8-row groups
+constexpr int MAX_KS = 7;
+
+// Slice layout in HBM for an operand of `batch` matrices with rows padded to tiles of TR rows and K padded to KBLK blocks of
+// KB bytes:  plane(b, rt, kb, s) is a contiguous TR x KB byte block at  ((((b NT + rt) KBLK + kb) KS + s) TR KB, stored in the
+// canonical no-swizzle K-major core-matrix order of the UMMA shared-memory descriptor:
+__host__ __device__ inline int tile_offset(int rr, int kk) { return (rr >> 3) * SBO + (kk >> 4) * LBO + (rr & 7) * 16 + (kk & 15); }
+
+// ------------------------------------------------------------------------------------------------ slicing
+// scale[b][r] = 2^(E+2) with max_k |x[r][k]| = m 2^E, m in [1/2, 1)   (1 for an all-zero or padding row; NaN if not finite)
+__global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const double* __restrict__ X, long long ldx, long long strideX,
+                                                             int rows, int rows_pad, int K, double* __restrict__ scale) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp, b = blockIdx.y;
+    if (r >= rows_pad) return;
+    double amax = 0.0;
+    if (r < rows) {
+        const double* x = X + (long long)b * strideX + (long long)r * ldx;
+        for (int k = lane; k < K; k += 32) {
+            const double v = fabs(x[k]);
+            amax = (v > amax || v != v) ? v : amax;                 // NaN sticks
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double w = __shfl_xor_sync(0xffffffffu, amax, o);
+            amax = (w > amax || w != w) ? w : amax;
+        }
+    }
+    if (lane == 0) {
+        double s = 1.0;
+        if (amax != amax || amax > 1.7e308) s = nan("");
+        else if (amax > 0.0) {
+            int e;
+            frexp(amax, &e);
+            s = ldexp(1.0, e + 2);
+        }
+        scale[(long long)b * rows_pad + r] = s;
+    }
+}
+
+// One warp = 8 rows x 4 sixteen-byte chunks = one (row group, k-block): its KS stores are 512 contiguous bytes each.
+template <int KS>
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ X, long long ldx, long long strideX,
+                                                          int rows, int rows_pad, int K, int KBLK, int TR,
+                                                          const double* __restrict__ scale, int8_t* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rg = blockIdx.x, b = blockIdx.y;               // row group of 8 rows
+    const int rr8 = lane & 7, c = lane >> 3;
+    const int r = rg * 8 + rr8;                              // row inside the batch entry (padded)
+    const int rt = r / TR, rr = r % TR;
+    const int NT = rows_pad / TR;
+    const double sc = scale[(long long)b * rows_pad + r];
+    const double mult = ldexp(1.0 / sc, 8 * KS);             // exact: power of two
+    const double* x = X + (long long)b * strideX + (long long)r * ldx;
+    for (int kb = blockIdx.z * 8 + warp; kb < KBLK; kb += gridDim.z * 8) {
+        const int k0 = kb * KB + c * 16;
+        uint32_t w[KS][4];
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[s][q] = 0u;
+        if (r < rows) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int k = k0 + e;
+                const double v = (k < K) ? x[k] : 0.0;
+                long long Y = __double2ll_rn(v * mult);      // |Y| < 2^(8 KS - 2)
+#pragma unroll
+                for (int s = KS - 1; s >= 0; --s) {
+                    const long long d = ((Y + 128) & 255) - 128;          // balanced digit in [-128, 127]
+                    Y = (Y - d) >> 8;
+                    w[s][e >> 2] |= (uint32_t)((uint8_t)(int8_t)d) << (8 * (e & 3));
+                }
+            }
+        }
+        int8_t* base = out + ((((long long)b * NT + rt) * KBLK + kb) * KS) * ((long long)TR * KB) + tile_offset(rr, c * 16);
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+            *reinterpret_cast<uint4*>(base + (long long)s * TR * KB) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A lost arrival must not hang the GPU box: after ~2 s of spinning the kernel records which wait starved and traps.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, INT8 x INT8 -> INT32
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns: thread t of the warp receives columns [col, col+16) of TMEM lane (lane_base + t)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, no swizzle (PTX ISA "matrix descriptor"; CUTLASS cute/arch/mma_sm100_desc.hpp):
+// [0,14) address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4, [46,48) version = 1, [61,64) layout 0
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+}
+
+template <int KS, int BN>
+struct Cfg {
+    static constexpr int A_PLANE = BM * KB, B_PLANE = BN * KB;
+    static constexpr int A_STAGE = KS * A_PLANE, B_STAGE = KS * B_PLANE;
+    static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
+    static constexpr int STAGES = (3 * STAGE_BYTES + 256 <= 232448) ? 3 : 2;
+    static constexpr int TMEM_USED = KS * BN;
+    static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 256;
+    static constexpr int G1 = KS < 3 ? KS : 3;               // accumulators recombined into the high INT64 word
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a/b format INT8 = 1 @7/@10, K-major A and B,
+    // N >> 3 @17, M >> 4 @24
+    static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static_assert(TMEM_USED <= 512, "accumulators exceed TMEM");
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+    static_assert(SMEM <= 232448, "shared memory");
+};
+
+struct Params {
+    const int8_t* A; const double* ascale; int S, MT;          // MT row tiles of BM samples
+    const int8_t* B; const double* bscale; int P, NT, batch;   // NT column tiles of BN grid points per batch entry
+    int KBLK;
+    double* fmax; int* arg;                                    // [batch][S]
+    double* full; long long ld_full, stride_full;              // optional dense output (tests)
+    int* err;
+};
+
+template <int KS, int BN>
+__global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
+    using C = Cfg<KS, BN>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + C::STAGES;
+    uint64_t* tfull_bar = bars + 2 * C::STAGES;
+    uint64_t* tempty_bar = tfull_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)C::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int items = p.MT * p.batch;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------- producer
+        uint32_t stage = 0, phase = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int b = item / p.MT, mt = item % p.MT;
+            const int8_t* Ab = p.A + (long long)mt * p.KBLK * C::A_STAGE;
+            for (int nt = 0; nt < p.NT; ++nt) {
+                const int8_t* Bb = p.B + ((long long)b * p.NT + nt) * p.KBLK * C::B_STAGE;
+                for (int kb = 0; kb < p.KBLK; ++kb) {
+                    mbar_wait(empty_bar + stage, phase ^ 1, p.err, 1);
+                    if (lane == 0) {
+                        const uint32_t dst = smem_u32(smem + stage * C::STAGE_BYTES);
+                        mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
+                        bulk_g2s(dst, Ab + (long long)kb * C::A_STAGE, C::A_STAGE, full_bar + stage);
+                        bulk_g2s(dst + C::A_STAGE, Bb + (long long)kb * C::B_STAGE, C::B_STAGE, full_bar + stage);
+                    }
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------- MMA issuer
+        uint32_t stage = 0, phase = 0, tile = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            for (int nt = 0; nt < p.NT; ++nt, ++tile) {
+                mbar_wait(tempty_bar, (tile & 1) ^ 1, p.err, 2);         // epilogue has drained the accumulators
+                tc_fence_after();
+                for (int kb = 0; kb < p.KBLK; ++kb) {
+                    mbar_wait(full_bar + stage, phase, p.err, 3);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES), b_base = a_base + C::A_STAGE;
+#pragma unroll
+                        for (int kk = 0; kk < KB / UMMA_K; ++kk) {
+#pragma unroll
+                            for (int i = 0; i < KS; ++i) {
+                                const uint64_t adesc = umma_desc(a_base + i * C::A_PLANE + kk * (UMMA_K / 16) * LBO);
+#pragma unroll
+                                for (int j = 0; j < KS - i; ++j) {
+                                    const uint64_t bdesc = umma_desc(b_base + j * C::B_PLANE + kk * (UMMA_K / 16) * LBO);
+                                    tc_mma_i8(tmem_base + (uint32_t)((i + j) * BN), adesc, bdesc, C::IDESC,
+                                              (uint32_t)((kb | kk | i) != 0));
+                                }
+                            }
+                        }
+                        tc_commit(empty_bar + stage);                    // frees the stage when these MMAs have read it
+                        if (kb == p.KBLK - 1) tc_commit(tfull_bar);      // accumulators complete
+                    }
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------- epilogue
+        const int q = warp & 3;                                          // TMEM lane quarter this warp may read
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const double c_hi = ldexp(1.0, -8 * (C::G1 + 1)), c_lo = ldexp(1.0, -8 * (KS + 1));
+        uint32_t tile = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int b = item / p.MT, mt = item % p.MT;
+            const int row = mt * BM + q * 32 + lane;
+            const double as = (row < p.S) ? p.ascale[row] : 1.0;
+            double best = -INFINITY;
+            int best_arg = 0;
+            for (int nt = 0; nt < p.NT; ++nt, ++tile) {
+                const double* bs = p.bscale + ((long long)b * p.NT + nt) * BN;
+                mbar_wait(tfull_bar, tile & 1, p.err, 4);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t acc[KS][16];
+#pragma unroll
+                    for (int d = 0; d < KS; ++d) tc_ld16(lane_addr + (uint32_t)(d * BN + c0), acc[d]);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        long long hi = 0, lo = 0;
+#pragma unroll
+                        for (int d = 0; d < C::G1; ++d) hi = hi * 256 + (long long)(int)acc[d][c];
+#pragma unroll
+                        for (int d = C::G1; d < KS; ++d) lo = lo * 256 + (long long)(int)acc[d][c];
+                        const int col = nt * BN + c0 + c;
+                        double v = fma((double)lo, c_lo, (double)hi * c_hi);
+                        v *= __ldg(bs + c0 + c);
+                        if (col < p.P) {
+                            if (p.full && row < p.S)
+                                p.full[(long long)b * p.stride_full + (long long)row * p.ld_full + col] = v * as;
+                            if (v > best) { best = v; best_arg = col; }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar);
+            }
+            if (row < p.S) {
+                p.fmax[(long long)b * p.S + row] = best * as;
+                p.arg[(long long)b * p.S + row] = best_arg;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+constexpr int BN_DEFAULT = 64;
+
+struct Shape {
+    int rows_pad, KBLK;
+    long long plane_bytes, scale_doubles;
+};
+static Shape shape_of(int rows, int K, int TR, int batch, int KS) {
+    Shape s;
+    s.rows_pad = ceil_div(rows, TR) * TR;
+    s.KBLK = ceil_div(K, KB);
+    s.plane_bytes = (long long)batch * s.rows_pad * s.KBLK * KB * KS;
+    s.scale_doubles = (long long)batch * s.rows_pad;
+    return s;
+}
+
+template <int KS>
+static int slice_launch(const double* X, long long ldx, long long strideX, int rows, int K, int TR, int batch, double* scale,
+                        int8_t* planes, cudaStream_t st) {
+    const Shape s = shape_of(rows, K, TR, batch, KS);
+    dim3 g1(s.rows_pad / 8, batch);
+    PPBO_CL ozaki_rowscale_kernel<<<g1, 256, 0, st>>>(X, ldx, strideX, rows, s.rows_pad, K, scale);
+    dim3 g2(s.rows_pad / 8, batch, min(8, ceil_div(s.KBLK, 8)));
+    PPBO_CL ozaki_slice_kernel<KS><<<g2, 256, 0, st>>>(X, ldx, strideX, rows, s.rows_pad, K, s.KBLK, TR, scale, planes);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+template <int KS, int BN>
+static int rowmax_launch(const Params& p, cudaStream_t st) {
+    using C = Cfg<KS, BN>;
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        err = cudaFuncSetAttribute(ozaki_rowmax_kernel<KS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    });
+    PPBO_CUDA_CHECK(err);
+    int dev = 0, sms = PPBO_SM_COUNT;
+    PPBO_CUDA_CHECK(cudaGetDevice(&dev));
+    PPBO_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int items = p.MT * p.batch;
+    if (items <= 0) return PPBO_OK;
+    PPBO_CL ozaki_rowmax_kernel<KS, BN><<<min(items, sms), 192, C::SMEM, st>>>(p);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+}  // namespace oz
+}  // namespace ppbo
+
+using namespace ppbo;
+
+extern "C" int ppbo_ozaki_tile_rows(int operand) { return operand == 0 ? oz::BM : oz::BN_DEFAULT; }
+
+extern "C" long long ppbo_ozaki_plane_bytes(int rows, int K, int tile_rows, int batch, int slices) {
+    if (rows < 0 || K < 1 || tile_rows < 8 || batch < 1 || slices < 1) return -1;
+    return oz::shape_of(rows, K, tile_rows, batch, slices).plane_bytes;
+}
+extern "C" long long ppbo_ozaki_scale_doubles(int rows, int tile_rows, int batch) {
+    if (rows < 0 || tile_rows < 8 || batch < 1) return -1;
+    return (long long)batch * ceil_div(rows, tile_rows) * tile_rows;
+}
+
+extern "C" int ppbo_ozaki_slice(const double* X, long long ldx, long long strideX, int rows, int K, int tile_rows, int batch,
+                                int slices, double* scale, signed char* planes, void* stream) {
+    PPBO_REQUIRE(rows >= 0 && K >= 1 && batch >= 1, "shape");
+    PPBO_REQUIRE(tile_rows >= 8 && tile_rows % 8 == 0, "tile_rows must be a multiple of 8");
+    PPBO_REQUIRE(slices >= 2 && slices <= oz::MAX_KS, "slices in [2, 7]");
+    PPBO_REQUIRE((reinterpret_cast<uintptr_t>(planes) & 15) == 0, "planes must be 16-byte aligned");
+    if (rows == 0) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int8_t* pl = reinterpret_cast<int8_t*>(planes);
+    switch (slices) {
+        case 2: return oz::slice_launch<2>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
+        case 3: return oz::slice_launch<3>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
+        case 4: return oz::slice_launch<4>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
+        case 5: return oz::slice_launch<5>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
+        case 6: return oz::slice_launch<6>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
+        default: return oz::slice_launch<7>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
+    }
+}
+
+extern "C" int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascale, int S, const signed char* Bplanes,
+                                 const double* bscale, int P, int batch, int K, int slices, double* fmax, int* arg,
+                                 double* Fs_full, int* err_flag, void* stream) {
+    PPBO_REQUIRE(S >= 0 && P >= 1 && batch >= 1 && K >= 1, "shape");
+    PPBO_REQUIRE(slices >= 5 && slices <= oz::MAX_KS, "slices in [5, 7]");
+    PPBO_REQUIRE(ceil_div(K, oz::KB) * oz::KB <= 16384, "K <= 16384 (INT32 accumulator range)");
+    PPBO_REQUIRE((reinterpret_cast<uintptr_t>(Aplanes) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bplanes) & 15) == 0,
+                 "digit planes must be 16-byte aligned");
+    if (S == 0) return PPBO_OK;
+    oz::Params p;
+    p.A = reinterpret_cast<const int8_t*>(Aplanes); p.ascale = ascale; p.S = S; p.MT = ceil_div(S, oz::BM);
+    p.B = reinterpret_cast<const int8_t*>(Bplanes); p.bscale = bscale; p.P = P; p.NT = ceil_div(P, oz::BN_DEFAULT); p.batch = batch;
+    p.KBLK = ceil_div(K, oz::KB);
+    p.fmax = fmax; p.arg = arg; p.full = Fs_full; p.ld_full = P; p.stride_full = (long long)S * P; p.err = err_flag;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (slices) {
+        case 5: return oz::rowmax_launch<5, oz::BN_DEFAULT>(p, st);
+        case 6: return oz::rowmax_launch<6, oz::BN_DEFAULT>(p, st);
+        default: return oz::rowmax_launch<7, oz::BN_DEFAULT>(p, st);
+    }
+}

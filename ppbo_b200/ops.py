@@ -303,6 +303,39 @@ def rff_eval_argmax(Omega, PhiT_grid, want_full=False):
     return fmax, arg, full
 
 
+def ozaki_slice(X, operand, slices=6):
+    """X [rows,K] (operand 0: samples) or [B,rows,K] (operand 1: grid points) -> (digit planes int8, row scales) in the
+    tensor-core operand layout of csrc/ozaki.cu"""
+    lib = _lib.load()
+    if X.dim() == 2:
+        X = X.unsqueeze(0)
+    B, rows, K = X.shape
+    if X.stride(2) != 1:
+        raise PPBOError("ozaki_slice: K must be contiguous")
+    tr = lib.ppbo_ozaki_tile_rows(operand)
+    planes = torch.empty(lib.ppbo_ozaki_plane_bytes(rows, K, tr, B, slices), dtype=torch.int8, device=X.device)
+    scale = torch.empty(lib.ppbo_ozaki_scale_doubles(rows, tr, B), dtype=F64, device=X.device)
+    check(lib.ppbo_ozaki_slice(_p(X), X.stride(1), X.stride(0), rows, K, tr, B, slices, _p(scale), _p(planes), _stream()),
+          "ppbo_ozaki_slice")
+    return planes, scale
+
+
+def rff_eval_argmax_i8(Omega, PhiT_grid, slices=6, want_full=False, sliced_grid=None):
+    """rff_eval_argmax on the tcgen05 INT8 tensor pipe (error-free splitting into `slices` digit planes per operand).
+    sliced_grid: (planes, scale) of PhiT_grid from ozaki_slice(PhiT_grid, 1, slices) when the caller reuses them."""
+    S, F = Omega.shape
+    B, P, _ = PhiT_grid.shape
+    fmax = torch.empty((B, S), dtype=F64, device=Omega.device)
+    arg = torch.empty((B, S), dtype=torch.int32, device=Omega.device)
+    full = torch.empty((B, S, P), dtype=F64, device=Omega.device) if want_full else None
+    ap, asc = ozaki_slice(Omega, 0, slices)
+    bp, bsc = sliced_grid if sliced_grid is not None else ozaki_slice(PhiT_grid, 1, slices)
+    err = torch.zeros(1, dtype=torch.int32, device=Omega.device)
+    check(_lib.load().ppbo_ozaki_rowmax(_p(ap), _p(asc), S, _p(bp), _p(bsc), P, B, F, slices, _p(fmax), _p(arg), _p(full),
+                                        _p(err), _stream()), "ppbo_ozaki_rowmax")
+    return fmax, arg, full
+
+
 def normal_fill(seed, stream_id, offset, n, dev=None):
     """n standard normals: numbers offset .. offset+n-1 of Philox stream `stream_id` under `seed` (device-side RNG)."""
     out = torch.empty(n, dtype=F64, device=dev or device())

@@ -1,0 +1,123 @@
+"""INT8 error-free splitting of the sampling contraction (csrc/ozaki.cu, tcgen05.mma.kind::i8).
+Host tests pin the oracle restatement (oracle/ppbo_oracle.py ozaki_*) against plain FP64; GPU tests require the CUDA path to
+reproduce the oracle BIT FOR BIT (integer arithmetic is exact) and to agree with the FP64 DMMA kernel on max / arg-max."""
+import numpy as np
+import pytest
+
+from oracle import ppbo_oracle as O
+
+torch = pytest.importorskip("torch")
+
+
+def _operands(S, F, P, seed=0, sigma_f=0.5):
+    rng = np.random.RandomState(seed)
+    Omega = 0.3 * rng.randn(S, F) + 0.05 * rng.randn(F)[None, :]
+    PhiT = np.sqrt(2.0 * sigma_f ** 2 / F) * np.cos(3.0 * rng.randn(P, F) + rng.uniform(0, 2 * np.pi, F)[None, :])
+    return Omega, PhiT
+
+
+# ----------------------------------------------------------------------------------------------- host
+@pytest.mark.parametrize("slices,tol", [(5, 2e-10), (6, 1e-12), (7, 1e-14)])
+def test_oracle_ozaki_accuracy(slices, tol):
+    Omega, PhiT = _operands(150, 1000, 96)
+    ref = Omega @ PhiT.T
+    C = O.ozaki_matmul(Omega, PhiT, slices)
+    assert np.abs(C - ref).max() <= tol * np.abs(ref).max()
+    # a-priori bound: dropped digit pairs (i + j >= slices) + one rounding of every operand entry to 8 slices - 2 bits
+    sa, sb = O.ozaki_rowscale(Omega), O.ozaki_rowscale(PhiT)
+    bound = (slices + 2) * Omega.shape[1] * 2.0 ** (-8 * slices - 2) * sa[:, None] * sb[None, :]
+    assert np.all(np.abs(C - ref) <= bound + 1e-15 * np.abs(ref).max())
+
+
+def test_oracle_ozaki_digits_roundtrip_and_range():
+    rng = np.random.RandomState(1)
+    X = rng.randn(40, 130) * np.exp(rng.randn(40, 1) * 5)
+    X[3] = 0.0
+    X[5, 7] = -X[5].__abs__().max() * 1.5          # a negative row maximum
+    for ks in (2, 5, 6, 7):
+        d, s = O.ozaki_digits(X, ks)
+        assert d.dtype == np.int8 and np.all(np.log2(s) == np.round(np.log2(s)))
+        rec = sum(d[i].astype(np.float64) * 256.0 ** -(i + 1) for i in range(ks)) * s[:, None]
+        assert np.abs(rec - X).max() <= (s * 2.0 ** (-8 * ks - 1)).max()
+        assert np.all(np.abs(d[0].astype(int)) <= 65)      # |x| / scale < 1/4 leaves headroom for the carry
+    d, s = O.ozaki_digits(X, 7)                            # 54 bits: exact for entries within 2^-1 of the row maximum
+    big = np.abs(X) >= 0.5 * np.abs(X).max(axis=1, keepdims=True)
+    rec = sum(d[i].astype(np.float64) * 256.0 ** -(i + 1) for i in range(7)) * s[:, None]
+    assert np.array_equal(rec[big], X[big])
+
+
+def test_oracle_ozaki_exact_power_of_two_scaling_and_layout():
+    Omega, PhiT = _operands(20, 100, 24, seed=3)
+    C = O.ozaki_matmul(Omega, PhiT, 6)
+    assert np.array_equal(O.ozaki_matmul(4.0 * Omega, PhiT, 6), 4.0 * C)          # linear in powers of two, exactly
+    assert np.array_equal(O.ozaki_matmul(Omega, 0.125 * PhiT, 6), 0.125 * C)
+    d, _ = O.ozaki_digits(Omega, 6)
+    img = O.ozaki_planes(d, 128)
+    assert img.size == 1 * 2 * 6 * 128 * 64
+    # element (r=13, k=70) of slice 2: row tile 0, k block 1, row group 1, chunk 0, row 5 of the group, byte 6
+    off = ((0 * 2 + 1) * 6 + 2) * 128 * 64 + (13 // 8) * 512 + ((70 % 64) // 16) * 128 + (13 % 8) * 16 + (70 % 16)
+    assert img[off] == d[2, 13, 70]
+
+
+# ----------------------------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from ppbo_b200 import ops as _ops
+    return _ops
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("slices", [5, 6, 7])
+def test_slice_kernel_bit_exact(ops, slices):
+    rng = np.random.RandomState(2)
+    X = rng.randn(300, 200) * np.exp(rng.randn(300, 1) * 3)
+    X[17] = 0.0
+    planes, scale = ops.ozaki_slice(ops.to_dev(X), 0, slices)
+    d, s = O.ozaki_digits(X, slices)
+    assert np.array_equal(_np(scale)[:300], s) and np.all(_np(scale)[300:] == 1.0)
+    assert np.array_equal(_np(planes), O.ozaki_planes(d, 128))
+    Xb = rng.randn(3, 100, 200)                                            # batched B operand, 64-row tiles
+    planes, scale = ops.ozaki_slice(ops.to_dev(Xb), 1, slices)
+    img = np.concatenate([O.ozaki_planes(O.ozaki_digits(Xb[b], slices)[0], 64) for b in range(3)])
+    assert np.array_equal(_np(planes), img)
+    assert np.array_equal(_np(scale).reshape(3, 128)[:, :100], np.stack([O.ozaki_rowscale(Xb[b]) for b in range(3)]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("slices", [5, 6, 7])
+@pytest.mark.parametrize("S,F,P,B", [(128, 64, 64, 1), (300, 200, 100, 2), (129, 1000, 70, 3), (1000, 333, 257, 2)])
+def test_rowmax_i8_bit_exact_vs_oracle(ops, slices, S, F, P, B):
+    Omega, _ = _operands(S, F, 8, seed=S)
+    grids = np.stack([_operands(8, F, P, seed=10 * b + P)[1] for b in range(B)])
+    Omega[S // 2] = 0.0
+    fmax, arg, full = ops.rff_eval_argmax_i8(ops.to_dev(Omega), ops.to_dev(grids), slices=slices, want_full=True)
+    torch.cuda.synchronize()
+    for b in range(B):
+        mx, am, Fs = O.ozaki_eval_argmax(Omega, grids[b], slices)
+        assert np.array_equal(_np(full)[b], Fs)
+        assert np.array_equal(_np(fmax)[b], mx)
+        assert np.array_equal(_np(arg)[b], am)
+
+
+@pytest.mark.gpu
+def test_rowmax_i8_matches_fp64_kernel(ops):
+    S, F, P, B = 4096, 1000, 1024, 3
+    Omega, _ = _operands(S, F, 8, seed=5)
+    grids = np.stack([_operands(8, F, P, seed=50 + b)[1] for b in range(B)])
+    Od, Gd = ops.to_dev(Omega), ops.to_dev(grids)
+    f64max, f64arg, _ = ops.rff_eval_argmax(Od, Gd)
+    for slices, tol in ((5, 1e-9), (6, 1e-11), (7, 1e-13)):
+        fmax, arg, _ = ops.rff_eval_argmax_i8(Od, Gd, slices=slices)
+        scale = float(np.abs(_np(f64max)).max())
+        assert np.abs(_np(fmax) - _np(f64max)).max() <= tol * scale
+        assert np.mean(_np(arg) == _np(f64arg)) > 0.9999            # arg-max flips only on ties at the rounding level
+    # repeatability: bit-identical across launches
+    a1 = ops.rff_eval_argmax_i8(Od, Gd, slices=6)[0]
+    a2 = ops.rff_eval_argmax_i8(Od, Gd, slices=6)[0]
+    assert torch.equal(a1, a2)
