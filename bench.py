@@ -154,6 +154,19 @@ def cpu_reference_sample(prob, fit_iters_full=None, q_sample=60, s_sample=512, t
     return total_ms, sample
 
 
+def int8_peak_tops():
+    """INT8 dense tensor peak in TOP/s: 2 x MEASURED_PEAKS.json's cuBLAS bf16 burst figure (kernel timed alone), else 2 x the
+    profiling guide's fallback of 1590 TFLOP/s."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            mp = json.load(fh)
+        return 2.0 * float(mp["bf16_tflops"]), ("2 x MEASURED_PEAKS.json bf16_tflops (%.1f, burst; sustained %.1f): INT8 runs on the "
+                                                "same tensor pipe at twice the K per instruction" % (mp["bf16_tflops"],
+                                                                                                      mp.get("bf16_tflops_sustained", float("nan"))))
+    except Exception:
+        return 2.0 * 1590.0, "2 x 1590 TFLOP/s bf16 (B200_PROFILING.md fallback; MEASURED_PEAKS.json absent)"
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -289,17 +302,49 @@ def main():
     rffs = out[2]
     Omega = ops.rff_sample_omega(rffs.omega_map, rffs.hess_diag, hi - lo, seed=1234, sample0=lo)
     PhiT = iteration.rff_grid_features(resident["W"], resident["b"], theta[2], resident["grids"])
+    engine = iteration.sampling_engine(hi - lo, P, Fdim)
+    ks = iteration.SAMPLING_SLICES
+    flops = 2.0 * (hi - lo) * Fdim * P * B                       # SURVEY.md 8d K3: 2 S F P per direction
+    if engine == "i8":
+        ap, asc = ops.ozaki_slice(Omega, 0, ks)
+        bp, bsc = ops.ozaki_slice(PhiT, 1, ks)
+        fm = torch.empty((B, hi - lo), dtype=torch.float64, device=dev)
+        am = torch.empty((B, hi - lo), dtype=torch.int32, device=dev)
+
+        def dominant():
+            ops.check(lib.ppbo_ozaki_rowmax(ops._p(ap), ops._p(asc), hi - lo, ops._p(bp), ops._p(bsc), P, B, Fdim, ks,
+                                            ops._p(fm), ops._p(am), None, None, ops._stream()), "ppbo_ozaki_rowmax")
+    else:
+        def dominant():
+            ops.rff_eval_argmax(Omega, PhiT)
     for i in range(3 + 5):
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        ops.rff_eval_argmax(Omega, PhiT)
+        dominant()
         b_.record()
         torch.cuda.synchronize()
         if i >= 3:
             gemm_ms.append(a.elapsed_time(b_))
     gemm_t = float(np.mean(gemm_ms))
-    flops = 2.0 * (hi - lo) * Fdim * P * B                       # SURVEY.md 8d K3: 2 S F P per direction
-    achieved = flops / (gemm_t * 1e-3) / 1e12
+    fp64_equiv = flops / (gemm_t * 1e-3) / 1e12
+    if engine == "i8":
+        # KS (KS+1)/2 exact INT8 plane products per FP64 product; INT8 dense peak = 2 x the measured bf16 peak (same tensor
+        # pipe, twice the K per instruction: nominal 4.5 POP/s against 2.25 PFLOP/s)
+        ops_per_launch = flops * ks * (ks + 1) / 2
+        achieved = ops_per_launch / (gemm_t * 1e-3) / 1e12
+        peak, peak_src = int8_peak_tops()
+        roof = {"kernel": "ozaki_rowmax_kernel<%d,64> (RFF sampling contraction on tcgen05.mma.kind::i8, %d digit planes per operand, "
+                          "fused per-sample max/arg-max)" % (ks, ks),
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": None,
+                "kernel_ms": gemm_t, "ops_per_launch": ops_per_launch, "fp64_equivalent_tflops": fp64_equiv,
+                "fp64_dmma_peak_tflops": FP64_TENSOR_PEAK_TFLOPS, "peak_source": peak_src}
+    else:
+        achieved = fp64_equiv
+        roof = {"kernel": "gemm_nt_rowmax_kernel (RFF sampling GEMM, fused per-sample max/arg-max)", "bound": "tensor",
+                "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
+                "traffic": None, "kernel_ms": gemm_t, "flops_per_launch": flops,
+                "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_fp64_peaks_ubench.txt); "
+                               "MEASURED_PEAKS.json has no FP64 figure (cuBLAS DGEMM 8192^3 reaches 35.5)"}
     sample_points_per_s = S * P * B / (float(np.mean(stage_ms["acquisition"])) * 1e-3) if shard.world == 1 else None
 
     if rank != 0:
@@ -314,11 +359,7 @@ def main():
                 "selected_direction": out2[0]},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"kernel": "gemm_nt_rowmax_kernel (RFF sampling GEMM, fused per-sample max/arg-max)", "bound": "tensor",
-                     "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
-                     "traffic": None, "kernel_ms": gemm_t, "flops_per_launch": flops,
-                     "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_fp64_peaks_ubench.txt); "
-                                    "MEASURED_PEAKS.json has no FP64 figure (cuBLAS DGEMM 8192^3 reaches 35.5)"},
+        "roofline": roof,
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
         "fit_newton_iterations": fit_iters, "rff_newton_iterations": rff_iters,
         "rff_sample_points_per_s": sample_points_per_s,

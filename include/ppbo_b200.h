@@ -202,6 +202,10 @@ int ppbo_ozaki_slice(const double* X, long long ldx, long long strideX, int rows
  * err_flag (optional, device int): set to the id of a starved pipeline wait before the kernel traps (never on a healthy run). */
 int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascale, int S, const signed char* Bplanes, const double* bscale,
                       int P, int batch, int K, int slices, double* fmax, int* arg, double* Fs_full, int* err_flag, void* stream);
+/* diagnostic: SM clocks for `iters` back-to-back 128 x N x 32 INT8 MMAs on `blocks` SMs, rotating over `nacc` accumulators
+ * (mode 0: A, B from shared memory; 1: A from TMEM; 2: B plane re-used); clocks_out[blocks] device int64.
+ * Used by scripts/ozaki_probe.py --ubench. */
+int ppbo_ozaki_mma_rate(int N, int mode, int nacc, int iters, int blocks, long long* clocks_out, void* stream);
 
 #ifdef __cplusplus
 }

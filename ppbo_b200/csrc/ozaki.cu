@@ -30,6 +30,7 @@
 #include "common.cuh"
 
 namespace ppbo {
+extern int g_tuning[8];
 namespace oz {
 
 constexpr int BM = 128;                      // rows of the A tile = TMEM lanes
@@ -170,6 +171,19 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from TMEM (lane = row, 32-bit column = 4 consecutive K bytes)
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory (128 rows x 32 B in core-matrix order) -> TMEM (128 lanes x 8 columns); ordered with tcgen05.mma in the pipe
+__device__ __forceinline__ void tc_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // 32 lanes x 16 consecutive 32-bit columns: thread t of the warp receives columns [col, col+16) of TMEM lane (lane_base + t)
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -186,20 +200,31 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
 }
+// The same descriptor `bytes` further into the buffer (bytes % 16 == 0): one 32-bit add on the low word, so the issuing thread
+// does not re-derive the address field for every MMA (a dependent shift/mask/or chain per instruction otherwise).
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) {
+    return (desc & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)desc + (bytes >> 4));
+}
 
-template <int KS, int BN>
+// TS: the A digit planes of a stage are copied once from shared memory into TMEM (tcgen05.cp) and every MMA reads A from
+// there; only the (narrow) B planes are re-read from shared memory.  With both operands in shared memory an M=128, N=64, K=32
+// MMA fetches 6 KB per 32 issue cycles = 1.5x the 128 B/clk shared-memory port: the ncu capture of that variant shows the
+// tensor-core shared-memory wavefronts as the top utilisation (61 %) with the tensor pipe at 27 %.
+template <int KS, int BN, bool TS = true>
 struct Cfg {
     static constexpr int A_PLANE = BM * KB, B_PLANE = BN * KB;
     static constexpr int A_STAGE = KS * A_PLANE, B_STAGE = KS * B_PLANE;
     static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
     static constexpr int STAGES = (3 * STAGE_BYTES + 256 <= 232448) ? 3 : 2;
-    static constexpr int TMEM_USED = KS * BN;
+    static constexpr int A_TMEM_COLS = TS ? KS * (KB / 4) : 0;      // KB bytes per lane and plane, 4 per column
+    static constexpr int TMEM_A0 = KS * BN;                         // first column of the A planes
+    static constexpr int TMEM_USED = KS * BN + A_TMEM_COLS;
     static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 256;
     static constexpr int G1 = KS < 3 ? KS : 3;               // accumulators recombined into the high INT64 word
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a/b format INT8 = 1 @7/@10, K-major A and B,
     // N >> 3 @17, M >> 4 @24
-    static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    static constexpr uint32_t IDESC_BASE = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);
     static_assert(TMEM_USED <= 512, "accumulators exceed TMEM");
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
     static_assert(SMEM <= 232448, "shared memory");
@@ -212,11 +237,12 @@ struct Params {
     double* fmax; int* arg;                                    // [batch][S]
     double* full; long long ld_full, stride_full;              // optional dense output (tests)
     int* err;
+    int diag;      // timing experiments only (tuning key 2): bit 0 = epilogue skips the TMEM reads, bit 1 = producer skips the copies
 };
 
-template <int KS, int BN>
+template <int KS, int BN, bool TS>
 __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
-    using C = Cfg<KS, BN>;
+    using C = Cfg<KS, BN, TS>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t* full_bar = bars;
@@ -246,6 +272,12 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int items = p.MT * p.batch;
+    long long clk0 = 0;
+    unsigned long long ns0 = 0;
+    if ((p.diag & 4) && threadIdx.x == 0) {
+        clk0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------- producer
@@ -257,7 +289,8 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
                 const int8_t* Bb = p.B + ((long long)b * p.NT + nt) * p.KBLK * C::B_STAGE;
                 for (int kb = 0; kb < p.KBLK; ++kb) {
                     mbar_wait(empty_bar + stage, phase ^ 1, p.err, 1);
-                    if (lane == 0) {
+                    if (lane == 0 && (p.diag & 2)) mbar_arrive(full_bar + stage);
+                    if (lane == 0 && !(p.diag & 2)) {
                         const uint32_t dst = smem_u32(smem + stage * C::STAGE_BYTES);
                         mbar_expect_tx(full_bar + stage, C::STAGE_BYTES);
                         bulk_g2s(dst, Ab + (long long)kb * C::A_STAGE, C::A_STAGE, full_bar + stage);
@@ -279,17 +312,39 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
                     mbar_wait(full_bar + stage, phase, p.err, 3);
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES), b_base = a_base + C::A_STAGE;
+                        const uint64_t a_desc0 = umma_desc(smem_u32(smem + stage * C::STAGE_BYTES));
+                        const uint64_t b_desc0 = umma_desc_advance(a_desc0, C::A_STAGE);
+                        if (TS) {
+#pragma unroll
+                            for (int i = 0; i < KS; ++i)
+#pragma unroll
+                                for (int kk = 0; kk < KB / UMMA_K; ++kk)
+                                    tc_cp_128x256b(tmem_base + (uint32_t)(C::TMEM_A0 + (i * (KB / UMMA_K) + kk) * (UMMA_K / 4)),
+                                                   umma_desc_advance(a_desc0, i * C::A_PLANE + kk * (UMMA_K / 16) * LBO));
+                        }
+                        // Digit plane A_i meets B_0 .. B_{KS-1-i}; those B planes are consecutive 8-row groups of one tall
+                        // K-major matrix in shared memory and their accumulators d = i .. KS-1 are consecutive TMEM columns, so
+                        // the KS - i products are ONE MMA of N = (KS - i) BN columns (cut into <= 256-column pieces).  A single
+                        // thread cannot issue N = 64 MMAs fast enough to fill the pipe (measured ~57 clk per instruction
+                        // against a 32 clk execution slot); wide instructions also read A once per (KS - i) BN columns.
 #pragma unroll
                         for (int kk = 0; kk < KB / UMMA_K; ++kk) {
 #pragma unroll
                             for (int i = 0; i < KS; ++i) {
-                                const uint64_t adesc = umma_desc(a_base + i * C::A_PLANE + kk * (UMMA_K / 16) * LBO);
+                                const uint64_t adesc = umma_desc_advance(a_desc0, i * C::A_PLANE + kk * (UMMA_K / 16) * LBO);
+                                const uint32_t a_tmem = tmem_base + (uint32_t)(C::TMEM_A0 + (i * (KB / UMMA_K) + kk) * (UMMA_K / 4));
+                                const int ncols = (KS - i) * BN;
+                                const int pieces = (ncols + 255) / 256;
+                                const int width = ((ncols + pieces - 1) / pieces + 15) / 16 * 16;
 #pragma unroll
-                                for (int j = 0; j < KS - i; ++j) {
-                                    const uint64_t bdesc = umma_desc(b_base + j * C::B_PLANE + kk * (UMMA_K / 16) * LBO);
-                                    tc_mma_i8(tmem_base + (uint32_t)((i + j) * BN), adesc, bdesc, C::IDESC,
-                                              (uint32_t)((kb | kk | i) != 0));
+                                for (int c0 = 0; c0 < ncols; c0 += width) {
+                                    const int n = (ncols - c0 < width) ? ncols - c0 : width;
+                                    const uint64_t bdesc = umma_desc_advance(b_desc0, c0 * KB + kk * (UMMA_K / 16) * LBO);
+                                    const uint32_t d_tmem = tmem_base + (uint32_t)(i * BN + c0);
+                                    const uint32_t accum = (uint32_t)((kb | kk | i) != 0);
+                                    const uint32_t idesc = C::IDESC_BASE | ((uint32_t)(n >> 3) << 17);
+                                    if (TS) tc_mma_i8_ts(d_tmem, a_tmem, bdesc, idesc, accum);
+                                    else tc_mma_i8(d_tmem, adesc, bdesc, idesc, accum);
                                 }
                             }
                         }
@@ -318,7 +373,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
                 mbar_wait(tfull_bar, tile & 1, p.err, 4);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 16) {
+                for (int c0 = 0; c0 < ((p.diag & 1) ? 0 : BN); c0 += 16) {
                     uint32_t acc[KS][16];
 #pragma unroll
                     for (int d = 0; d < KS; ++d) tc_ld16(lane_addr + (uint32_t)(d * BN + c0), acc[d]);
@@ -355,6 +410,12 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
     }
+    if ((p.diag & 4) && threadIdx.x == 0 && blockIdx.x == 0 && p.err) {      // SM clock actually sustained by this launch
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        reinterpret_cast<long long*>(p.err)[1] = clock64() - clk0;
+        reinterpret_cast<long long*>(p.err)[2] = (long long)(ns1 - ns0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -385,13 +446,13 @@ static int slice_launch(const double* X, long long ldx, long long strideX, int r
     return PPBO_OK;
 }
 
-template <int KS, int BN>
+template <int KS, int BN, bool TS>
 static int rowmax_launch(const Params& p, cudaStream_t st) {
-    using C = Cfg<KS, BN>;
+    using C = Cfg<KS, BN, TS>;
     static std::once_flag once;
     static cudaError_t err = cudaSuccess;
     std::call_once(once, [] {
-        err = cudaFuncSetAttribute(ozaki_rowmax_kernel<KS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        err = cudaFuncSetAttribute(ozaki_rowmax_kernel<KS, BN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     });
     PPBO_CUDA_CHECK(err);
     int dev = 0, sms = PPBO_SM_COUNT;
@@ -399,7 +460,82 @@ static int rowmax_launch(const Params& p, cudaStream_t st) {
     PPBO_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int items = p.MT * p.batch;
     if (items <= 0) return PPBO_OK;
-    PPBO_CL ozaki_rowmax_kernel<KS, BN><<<min(items, sms), 192, C::SMEM, st>>>(p);
+    PPBO_CL ozaki_rowmax_kernel<KS, BN, TS><<<min(items, sms), 192, C::SMEM, st>>>(p);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ issue-rate probe
+// Diagnostic (scripts/ozaki_probe.py --ubench): `iters` back-to-back tcgen05.mma.kind::i8 of shape 128 x N x 32 on resident
+// shared-memory operands, one issuing thread per SM; reports SM clocks per MMA.  mode 0: A and B from shared memory, 1: A from
+// TMEM, 2: as 0 but the same B plane re-used by consecutive MMAs (A alternates).
+template <int N>
+__global__ void __launch_bounds__(128, 1) ozaki_mma_rate_kernel(int mode, int nacc, int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (BM + N) * KB * 2 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    if (warp == 0) {
+        long long t0 = 0, t1 = 0;
+        const uint32_t a_base = smem_u32(smem), b_base = a_base + 2 * BM * KB;
+        if (lane == 0) {
+            tc_cp_128x256b(tmem_base + 448, umma_desc(a_base));
+            tc_cp_128x256b(tmem_base + 456, umma_desc(a_base + BM * KB));
+            tc_commit(&bar);
+        }
+        __syncwarp();
+        mbar_wait(&bar, 0, nullptr, 0);
+        tc_fence_after();
+        if (lane == 0) {
+            const uint64_t ad0 = umma_desc(a_base), bd0 = umma_desc(b_base);
+            t0 = clock64();
+            int acc = 0;
+            for (int it = 0; it < iters; it += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t d = tmem_base + (uint32_t)(acc * N);
+                    acc = (acc + 1 == nacc) ? 0 : acc + 1;
+                    const uint64_t ad = umma_desc_advance(ad0, (u & 1) * BM * KB + (u >> 1) * 2 * LBO);
+                    const uint64_t bd = umma_desc_advance(bd0, (mode == 2 ? 0 : (u & 1)) * N * KB + (u >> 1) * 2 * LBO);
+                    if (mode == 1) tc_mma_i8_ts(d, tmem_base + 448 + (u & 1) * 8, bd, IDESC, 1u);
+                    else tc_mma_i8(d, ad, bd, IDESC, 1u);
+                }
+            }
+            tc_commit(&bar);
+        }
+        __syncwarp();
+        mbar_wait(&bar, 1, nullptr, 0);
+        if (lane == 0) {
+            t1 = clock64();
+            out[blockIdx.x] = t1 - t0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+template <int N>
+static int mma_rate_launch(int mode, int nacc, int iters, int blocks, long long* out, cudaStream_t st) {
+    const int smem = (BM + N) * KB * 2;
+    PPBO_CUDA_CHECK(cudaFuncSetAttribute(ozaki_mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PPBO_CL ozaki_mma_rate_kernel<N><<<blocks, 128, smem, st>>>(mode, nacc, iters, out);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -408,6 +544,19 @@ static int rowmax_launch(const Params& p, cudaStream_t st) {
 }  // namespace ppbo
 
 using namespace ppbo;
+
+extern "C" int ppbo_ozaki_mma_rate(int N, int mode, int nacc, int iters, int blocks, long long* clocks_out, void* stream) {
+    PPBO_REQUIRE(iters >= 4 && iters % 4 == 0 && blocks >= 1 && mode >= 0 && mode <= 2, "arguments");
+    PPBO_REQUIRE(nacc >= 1 && nacc * N <= 448, "accumulators must fit 448 TMEM columns");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (N) {
+        case 32: return oz::mma_rate_launch<32>(mode, nacc, iters, blocks, clocks_out, st);
+        case 64: return oz::mma_rate_launch<64>(mode, nacc, iters, blocks, clocks_out, st);
+        case 128: return oz::mma_rate_launch<128>(mode, nacc, iters, blocks, clocks_out, st);
+        case 256: return oz::mma_rate_launch<256>(mode, nacc, iters, blocks, clocks_out, st);
+        default: PPBO_REQUIRE(false, "N in {32, 64, 128, 256}");
+    }
+}
 
 extern "C" int ppbo_ozaki_tile_rows(int operand) { return operand == 0 ? oz::BM : oz::BN_DEFAULT; }
 
@@ -453,10 +602,12 @@ extern "C" int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascal
     p.B = reinterpret_cast<const int8_t*>(Bplanes); p.bscale = bscale; p.P = P; p.NT = ceil_div(P, oz::BN_DEFAULT); p.batch = batch;
     p.KBLK = ceil_div(K, oz::KB);
     p.fmax = fmax; p.arg = arg; p.full = Fs_full; p.ld_full = P; p.stride_full = (long long)S * P; p.err = err_flag;
+    p.diag = g_tuning[2];
     cudaStream_t st = (cudaStream_t)stream;
+    const bool ts = g_tuning[1] == 0;          // tuning key 1: 1 = both operands from shared memory (comparison variant)
     switch (slices) {
-        case 5: return oz::rowmax_launch<5, oz::BN_DEFAULT>(p, st);
-        case 6: return oz::rowmax_launch<6, oz::BN_DEFAULT>(p, st);
-        default: return oz::rowmax_launch<7, oz::BN_DEFAULT>(p, st);
+        case 5: return ts ? oz::rowmax_launch<5, oz::BN_DEFAULT, true>(p, st) : oz::rowmax_launch<5, oz::BN_DEFAULT, false>(p, st);
+        case 6: return ts ? oz::rowmax_launch<6, oz::BN_DEFAULT, true>(p, st) : oz::rowmax_launch<6, oz::BN_DEFAULT, false>(p, st);
+        default: return oz::rowmax_launch<7, oz::BN_DEFAULT, false>(p, st);    // 7 x 64 + 7 x 16 columns exceed TMEM
     }
 }

@@ -24,6 +24,30 @@ from ._lib import PPBOError
 
 F64 = torch.float64
 SHRINKAGE = 1e-6          # GPModel.COVARIANCE_SHRINKAGE, src/gp_model.py:26
+# Sampling contraction Omega . PhiT^T: "i8" = tcgen05 INT8 tensor pipe with error-free splitting into SLICES base-256 digit
+# planes per operand (csrc/ozaki.cu; 6 planes: ~1e-13 relative, i.e. the accuracy of an FP64 GEMM of this depth), "f64" = the
+# FP64 DMMA kernel.  Small contractions (reference-size grids) stay on the FP64 kernel: a 128 x 64 INT8 tile would be mostly
+# padding there.
+SAMPLING_ENGINE = "i8"
+SAMPLING_SLICES = 6
+I8_MIN_WORK = 1 << 24     # S * P * F below which the FP64 kernel is used
+
+
+def sampling_engine(S, P, Fdim):
+    return "i8" if (SAMPLING_ENGINE == "i8" and S * P * Fdim >= I8_MIN_WORK) else "f64"
+
+
+class SlicedGrids:
+    """PhiT [B, P, F] together with its INT8 digit planes (computed once per iteration, before the fit is known)."""
+    __slots__ = ("PhiT", "planes", "scale", "slices")
+
+    def __init__(self, PhiT, slices=None):
+        self.PhiT, self.slices = PhiT, SAMPLING_SLICES if slices is None else slices
+        self.planes, self.scale = ops.ozaki_slice(PhiT, 1, self.slices)
+
+    @property
+    def shape(self):
+        return self.PhiT.shape
 
 
 class Shard:
@@ -146,7 +170,13 @@ def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_i
     lo, hi = shard.bounds(S)
     Zloc = None if Z is None else Z[lo:hi]
     Omega = ops.rff_sample_omega(r.omega_map, r.hess_diag, hi - lo, Z=Zloc, seed=seed, stream_id=stream_id, sample0=lo)
-    fmax, arg, _ = ops.rff_eval_argmax(Omega, PhiT)
+    sliced = PhiT if isinstance(PhiT, SlicedGrids) else None
+    PhiT = sliced.PhiT if sliced is not None else PhiT
+    if sliced is not None or sampling_engine(hi - lo, PhiT.shape[1], PhiT.shape[2]) == "i8":
+        fmax, arg, _ = ops.rff_eval_argmax_i8(Omega, PhiT, slices=sliced.slices if sliced else SAMPLING_SLICES,
+                                              sliced_grid=(sliced.planes, sliced.scale) if sliced else None)
+    else:
+        fmax, arg, _ = ops.rff_eval_argmax(Omega, PhiT)
     sums = ops.acq_reduce_dev(fmax, mustar_dev)
     shard.all_reduce_sum(sums)
     return sums, fmax, arg
@@ -195,6 +225,9 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
             timers.append((name, ev))
     mark("start")
     PhiT = rff_grid_features(W, b, theta[2], grids)           # independent of the fit: every rank, before the broadcast
+    lo, hi = shard.bounds(S)
+    if sampling_engine(hi - lo, P, Fdim) == "i8":
+        PhiT = SlicedGrids(PhiT)                              # digit planes of the grid features, also before the broadcast
     mark("grid_features")
     pack = torch.empty(2 * Fdim + 1, dtype=F64, device=X.device)
     gp = rff = None
