@@ -97,6 +97,15 @@ int ppbo_trsm_right_lower(const double* L, long long ldl, int n, double* X, long
 /* x <- (L L^T)^-1 x for one right-hand side; x must have room for n + 128 doubles (scratch tail).  Replaces cho_solve
  * under scipy's trust-exact (src/gp_model.py:382-384). */
 int ppbo_potrs_vec(const double* L, long long ldl, int n, double* x, void* workspace, long long workspace_bytes, void* stream);
+/* The same solve for a factor that serves MANY right-hand sides (chord steps of the Newton iterations): the diagonal blocks of
+ * L are inverted once at 1024 x 1024 granularity (from the 128 x 128 inverses ppbo_potrf_lower left in its workspace), after
+ * which each solve is n/1024 steps of two bandwidth-bound matrix-vector kernels instead of a 40-link dependency chain.
+ * Replaces the cho_solve calls inside scipy's trust-exact (src/gp_model.py:382, src/random_fourier_sampler.py:128). */
+long long ppbo_blockinv_bytes(int n);
+int ppbo_blockinv_build(const double* L, long long ldl, int n, const void* potrf_workspace, void* blockinv,
+                        long long blockinv_bytes, void* stream);
+int ppbo_potrs_vec_blockinv(const double* L, long long ldl, int n, void* blockinv, long long blockinv_bytes, double* x,
+                            void* stream);
 /* out = (L L^T)^-1 (dense, symmetric) from the factor and workspace of ppbo_potrf_lower; work: n*n doubles.
  * Replaces misc.pd_inverse (src/misc.py:96-100; LAPACK dposv with an identity right-hand side) where a caller reads an
  * explicit inverse (GPModel.Sigma_inv, posterior_covariance). */

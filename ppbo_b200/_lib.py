@@ -43,6 +43,9 @@ _SIGNATURES = {
     "ppbo_potrf_lower": (_I, [_P, _L, _I, _P, _L, _PI, _P]),
     "ppbo_trsm_right_lower": (_I, [_P, _L, _I, _P, _L, _I, _I, _P, _L, _P]),
     "ppbo_potrs_vec": (_I, [_P, _L, _I, _P, _P, _L, _P]),
+    "ppbo_blockinv_bytes": (_L, [_I]),
+    "ppbo_blockinv_build": (_I, [_P, _L, _I, _P, _P, _L, _P]),
+    "ppbo_potrs_vec_blockinv": (_I, [_P, _L, _I, _P, _L, _P, _P]),
     "ppbo_potri_lower": (_I, [_P, _L, _I, _P, _L, _P, _P, _L, _P]),
     "ppbo_shrink_inplace": (_I, [_P, _L, _I, _D, _P, _P]),
     "ppbo_gemv": (_I, [_P, _L, _I, _I, _P, _P, _P]),

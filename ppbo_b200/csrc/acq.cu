@@ -487,11 +487,12 @@ extern "C" int ppbo_rff_value_grad(const double* W, const double* b, int F, int 
 
 extern "C" long long ppbo_rff_workspace_bytes(int F, int Q, int m) {
     const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
-    return ((3 + FV_SLICES) * N + 2 * M + Q * 9 + 64 + (long long)F * M + ppbo_factor_doubles(F) + 4 * (long long)F + 2 * CHOL_NB) * 8;
+    return ((3 + FV_SLICES) * N + 2 * M + Q * 9 + 64 + (long long)F * M + ppbo_factor_doubles(F) + 4 * (long long)F + 2 * CHOL_NB +
+            blockinv_doubles(F)) * 8;
 }
 
 struct RffWs {
-    double *fvals, *dfv, *fpart, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp;
+    double *fvals, *dfv, *fpart, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp, *binv;
     void carve(double* p, int F, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
         fvals = p; p += N;
@@ -507,6 +508,7 @@ struct RffWs {
         step = p; p += F + CHOL_NB;
         trial = p; p += F;
         tmp = p; p += F;
+        binv = p;
     }
 };
 
@@ -563,7 +565,7 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
     double* part = ws.setlik + Q;                       // [LS_STEPS][Q]
     const double CHORD_REL = 0.25;
     const bool trace = getenv("PPBO_TRACE") != nullptr;
-    bool refactor = true;
+    bool refactor = true, binv_valid = false;
     for (it = 0; it < max_iter; ++it) {
         // gradient at omega (always fresh); Hessian factor only on Newton steps, reused on chord steps
         if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, refactor, ws.scal + 24, st))) return rc;
@@ -575,11 +577,18 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
             PPBO_CL add_identity_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.H, F, F);
             if ((rc = potrf_lower(ws.H, F, F, Hdinv, info_d, st))) return rc;
             ++n_factor;
+            binv_valid = false;
         } else {
             ++n_chord;
+            if (!binv_valid) {            // the factor is about to be reused: invert its diagonal blocks once (linalg.cu)
+                if ((rc = blockinv_build(ws.H, F, F, Hdinv, ws.binv, st))) return rc;
+                binv_valid = true;
+            }
         }
         PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.step, ws.grad, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
-        if ((rc = potrs_vec(ws.H, F, F, Hdinv, ws.step, st))) return rc;      // step = (-Hessian)^-1 grad  (ascent direction)
+        // step = (-Hessian)^-1 grad  (ascent direction)
+        rc = binv_valid ? potrs_vec_blockinv(ws.H, F, F, ws.binv, ws.step, st) : potrs_vec(ws.H, F, F, Hdinv, ws.step, st);
+        if (rc) return rc;
         // line search, all LS_STEPS step sizes in one pass: f(omega + s step) = f0 + s df, |omega + s step|^2 in closed form
         launch_rff_fvals(Phi_X, ld, F, N, ws.step, ws.fpart, ws.dfv, st);
         if ((rc = launch_linesearch_lik(ws.fvals, ws.dfv, Q, m, sigma, part, st))) return rc;

@@ -22,6 +22,8 @@ struct GemmOperands {
     const double* A; long long lda; long long strideA;   // A: M x K, row-major, batch stride
     const double* B; long long ldb; long long strideB;   // B: N x K, row-major, batch stride
     int M, N, K;
+    // optional two-level batching: batch entry z = zo * zinner + zi sits at zi * stride + zo * stride2 (zinner == 0: one level)
+    int zinner = 0; long long strideA2 = 0, strideB2 = 0;
 };
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -125,6 +127,7 @@ struct StoreEpilogue {
     int lower_only;      // 1: blockIdx.x enumerates tiles (ti >= tj) of a square tiling (BM == BN)
     int vec_ok;          // 1: C rows are 16-byte aligned at even columns (set by the launcher)
     int in_place;        // 1: C aliases A (row-panel update); launcher picks a tile with BN >= N == K
+    long long strideC2 = 0;   // outer batch stride (GemmOperands::zinner)
 };
 
 template <class Cfg>
@@ -145,9 +148,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_store_kernel(
         tn = blockIdx.y;
     }
     const int m0 = tm * Cfg::BM, n0 = tn * Cfg::BN;
-    const double* A = g.A + (long long)blockIdx.z * g.strideA;
-    const double* B = g.B + (long long)blockIdx.z * g.strideB;
-    double* C = ep.C + (long long)blockIdx.z * ep.strideC;
+    const long long zo = g.zinner ? blockIdx.z / g.zinner : 0, zi = g.zinner ? blockIdx.z % g.zinner : blockIdx.z;
+    const double* A = g.A + zi * g.strideA + zo * g.strideA2;
+    const double* B = g.B + zi * g.strideB + zo * g.strideB2;
+    double* C = ep.C + zi * ep.strideC + zo * ep.strideC2;
 
     double acc[Cfg::MI][Cfg::NI][2];
 #pragma unroll

@@ -206,11 +206,11 @@ int launch_sum(const double* x, int n, double* out, cudaStream_t st) {
 }
 
 struct FitWorkspace {
-    double *bvec, *sa, *ap, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp;
+    double *bvec, *sa, *ap, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp, *binv;
     int* info;
     static long long doubles(int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
-        return 4 * N + 3 * M + (M + CHOL_NB) + (long long)NSTEP * Q + 32 + 8 + 64;
+        return 4 * N + 3 * M + (M + CHOL_NB) + (long long)NSTEP * Q + 32 + 8 + 64 + blockinv_doubles((int)M);
     }
     void carve(double* base, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
@@ -226,6 +226,7 @@ struct FitWorkspace {
         set_part = p; p += (long long)NSTEP * Q;
         scal = p; p += 32;
         info = reinterpret_cast<int*>(p); p += 8;
+        binv = p;
     }
 };
 
@@ -291,19 +292,38 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     const double CHORD_REL = 0.25;
     const bool trace = getenv("PPBO_TRACE") != nullptr;
     bool refactor = true, converged = false;
+    // Cold start f = 0: every difference is 0, so a = -Delta phi~(Delta) / (2 m sigma^2) = 0 and the Newton matrix
+    // I + a+^1/2 G a+^1/2 is the identity: its factor is known, nothing to factorise and nothing to solve.
+    bool identity_factor = false;
+    // chord steps reuse one factor many times: its diagonal blocks are inverted at the first chord step (linalg.cu, block-inverse
+    // solves), which makes every later solve with that factor ~3x cheaper than the 40-link chained solve
+    bool binv_valid = false;
     for (it = 0; it < max_iter; ++it) {
         if (refactor) {
             PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, ws.sa, ws.bvec, nullptr, ws.ap);
-            if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
-            if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
-            ++n_factor;
+            identity_factor = (it == 0 && !have_start);
+            if (identity_factor) {
+                PPBO_CUDA_CHECK(cudaMemsetAsync(ws.info, 0, sizeof(int), st));
+            } else {
+                if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
+                if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
+                ++n_factor;
+                binv_valid = false;
+            }
         } else {
+            if (!binv_valid) {
+                if ((rc = blockinv_build(Lfac, M, M, Mdinv, ws.binv, st))) return rc;
+                binv_valid = true;
+            }
             PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr);
             ++n_chord;
         }
         if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
         PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
-        if ((rc = potrs_vec(Lfac, M, M, Mdinv, ws.t, st))) return rc;
+        if (!identity_factor) {
+            rc = binv_valid ? potrs_vec_blockinv(Lfac, M, M, ws.binv, ws.t, st) : potrs_vec(Lfac, M, M, Mdinv, ws.t, st);
+            if (rc) return rc;
+        }
         PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);
         if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st))) return rc;
         PPBO_LAUNCH_CHECK();
@@ -358,6 +378,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         // chord steps while they contract fast enough (at least 4x per step); otherwise pay for a new factor
         if (refactor) refactor = !(step == 1.0 && last_rel <= CHORD_REL);
         else refactor = !(last_rel <= 0.5 * prev_rel);
+        if (identity_factor) refactor = true;           // there is no stored factor to reuse after the identity step
     }
     (void)converged;
     // consistent products at the mode: arrow (signed), factor of I + a+^1/2 G a+^1/2

@@ -58,7 +58,8 @@ static int set_smem_attr_rowmax() {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool operands_vec2(const GemmOperands& g) {
-    return aligned16(g.A) && aligned16(g.B) && g.lda % 2 == 0 && g.ldb % 2 == 0 && g.strideA % 2 == 0 && g.strideB % 2 == 0;
+    return aligned16(g.A) && aligned16(g.B) && g.lda % 2 == 0 && g.ldb % 2 == 0 && g.strideA % 2 == 0 && g.strideB % 2 == 0 &&
+           g.strideA2 % 2 == 0 && g.strideB2 % 2 == 0;
 }
 
 template <class Cfg>
@@ -81,7 +82,7 @@ static int launch_store_cfg(const GemmOperands& g, StoreEpilogue ep, int batch, 
 int launch_gemm_nt(const GemmOperands& g, const StoreEpilogue& ep_in, int batch, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return PPBO_OK;
     StoreEpilogue ep = ep_in;
-    ep.vec_ok = aligned16(ep.C) && ep.ldc % 2 == 0 && ep.strideC % 2 == 0;
+    ep.vec_ok = aligned16(ep.C) && ep.ldc % 2 == 0 && ep.strideC % 2 == 0 && ep.strideC2 % 2 == 0;
     const bool v2 = operands_vec2(g);
     // small problems: more, smaller CTAs so the 148 SMs see work
     const long long big_tiles = (long long)ceil_div(g.M, 128) * ceil_div(g.N, 128) * batch;
@@ -405,12 +406,19 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
 long long potrf_dinv_doubles(int n) { return (long long)ceil_div(n, CHOL_NB) * CHOL_NB * CHOL_NB; }
 
 struct CholStreams {
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr, crit = nullptr;
     cudaEvent_t panel_done[2] = {nullptr, nullptr}, rest_done[2] = {nullptr, nullptr};
-    cudaEvent_t fork = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
     int init() {
         if (side) return PPBO_OK;
-        PPBO_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        // The block-column critical path (diagonal block, panel, next block column) runs on a high-priority stream and the
+        // bulk of the trailing update on a low-priority one: the trailing GEMM's ~1500 short CTAs otherwise occupy every SM
+        // and the one-CTA diagonal-block kernel of the next step queues behind them.
+        int lo = 0, hi = 0;
+        PPBO_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PPBO_CUDA_CHECK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo));
+        PPBO_CUDA_CHECK(cudaStreamCreateWithPriority(&crit, cudaStreamNonBlocking, hi));
+        PPBO_CUDA_CHECK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
             PPBO_CUDA_CHECK(cudaEventCreateWithFlags(&panel_done[i], cudaEventDisableTiming));
             PPBO_CUDA_CHECK(cudaEventCreateWithFlags(&rest_done[i], cudaEventDisableTiming));
@@ -423,7 +431,7 @@ static thread_local CholStreams g_chol;
 
 // Right-looking blocked Cholesky with one block column of look-ahead: the next diagonal block and panel are
 // factored on `st` while the bulk of the trailing update runs on a side stream.
-int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cudaStream_t st) {
+int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cudaStream_t caller) {
     if (n <= 0) return PPBO_OK;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -434,9 +442,15 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
     PPBO_CUDA_CHECK(attr_err);
     int rc = g_chol.init();
     if (rc) return rc;
-    PPBO_CUDA_CHECK(cudaMemsetAsync(info_d, 0, sizeof(int), st));
     const int nblk = ceil_div(n, CHOL_NB);
     const bool lookahead = nblk > 3;
+    cudaStream_t st = caller;
+    if (lookahead && g_tuning[3] == 0) {                  // tuning key 3: 1 = keep the critical path on the caller's stream
+        st = g_chol.crit;
+        PPBO_CUDA_CHECK(cudaEventRecord(g_chol.fork, caller));
+        PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.fork, 0));
+    }
+    PPBO_CUDA_CHECK(cudaMemsetAsync(info_d, 0, sizeof(int), st));
     bool side_busy = false;
     for (int b = 0; b < nblk; ++b) {
         const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0), j1 = j0 + jb, rem = n - j1;
@@ -489,6 +503,10 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
         }
     }
     if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[(nblk - 2) & 1], 0));
+    if (st != caller) {
+        PPBO_CUDA_CHECK(cudaEventRecord(g_chol.join, st));
+        PPBO_CUDA_CHECK(cudaStreamWaitEvent(caller, g_chol.join, 0));
+    }
     return PPBO_OK;
 }
 
@@ -714,6 +732,168 @@ int potrs_vec(const double* L, long long ldl, int n, const double* dinv, double*
     return PPBO_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------- block-inverse solves
+// A triangular solve with one right-hand side reads 8 n^2 / 2 bytes (100 MB at n = 5000: 16 us of HBM time) but the chained
+// kernel above pays ~6 us of dependency latency per 128-row block (40 links: 0.25 ms per direction).  When one factor serves
+// many solves (the chord steps of the Laplace / weight-space Newton iterations) the diagonal blocks of L are inverted at
+// BI = 1024 granularity once -- by doubling the 128 x 128 inverses of the factorisation,
+//   inv [[A, 0], [C, B]] = [[A^-1, 0], [-B^-1 C A^-1, B^-1]]    (three batched NT GEMMs per level, both A^-1 and A^-T kept),
+// and a solve becomes n / 1024 steps of two bandwidth-bound matrix-vector kernels on the whole GPU.
+constexpr int BI = 1024;
+
+long long blockinv_doubles(int n) {
+    const long long nbI = ceil_div(n, BI);
+    return nbI * (3LL * BI * BI + BI * BI / 4 + BI);
+}
+
+// per 1024-block J: Lpad = lower triangle of L's diagonal block (identity on the padding), Binv / BinvT = block diagonal of the
+// 128 x 128 inverses (and transposes) produced by potrf_lower
+__global__ void __launch_bounds__(256) blockinv_init_kernel(const double* __restrict__ L, long long ldl, int n,
+                                                            const double* __restrict__ dinv, double* __restrict__ Binv,
+                                                            double* __restrict__ BinvT, double* __restrict__ Lpad) {
+    const int J = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int i = e / BI, j = e % BI;
+    const int gi = J * BI + i, gj = J * BI + j;
+    const long long o = (long long)J * BI * BI + e;
+    double lp = (i == j) ? 1.0 : 0.0, bi = lp, bt = lp;
+    if (gi < n && gj < n) {
+        lp = (j <= i) ? L[(long long)gi * ldl + gj] : 0.0;
+        bi = bt = 0.0;
+        if ((i >> 7) == (j >> 7)) {
+            const double* d = dinv + (long long)(gi >> 7) * CHOL_NB * CHOL_NB;
+            bi = d[(i & 127) * CHOL_NB + (j & 127)];
+            bt = d[(j & 127) * CHOL_NB + (i & 127)];
+        }
+    } else if (gi < n || gj < n) {
+        lp = bi = bt = 0.0;
+    }
+    Lpad[o] = lp;
+    Binv[o] = bi;
+    BinvT[o] = bt;
+}
+
+int blockinv_build(const double* L, long long ldl, int n, const double* dinv, double* W, cudaStream_t st) {
+    const int nbI = ceil_div(n, BI);
+    const long long BB = (long long)BI * BI;
+    double* Binv = W;
+    double* BinvT = Binv + nbI * BB;
+    double* Lpad = BinvT + nbI * BB;
+    double* Tt = Lpad + nbI * BB;
+    PPBO_CL blockinv_init_kernel<<<dim3(BI * BI / 256, nbI), 256, 0, st>>>(L, ldl, n, dinv, Binv, BinvT, Lpad);
+    PPBO_LAUNCH_CHECK();
+    for (int s = CHOL_NB; s < BI; s *= 2) {
+        const int ppb = BI / (2 * s), nb = nbI * ppb;
+        const long long pair = 2LL * s * (BI + 1), ss = (long long)s * s;
+        int rc;
+        {   // Tt = (C A^-1)^T = A^-T . C^T
+            GemmOperands g{BinvT, BI, pair, Lpad + (long long)s * BI, BI, pair, s, s, s, ppb, BB, BB};
+            StoreEpilogue ep{Tt, s, ss, 1.0, 0.0, 0, 0, 0, ppb * ss};
+            if ((rc = launch_gemm_nt(g, ep, nb, st))) return rc;
+        }
+        {   // X = -B^-1 (C A^-1)   -> lower-left block of the inverse
+            GemmOperands g{Binv + (long long)s * (BI + 1), BI, pair, Tt, s, ss, s, s, s, ppb, BB, ppb * ss};
+            StoreEpilogue ep{Binv + (long long)s * BI, BI, pair, -1.0, 0.0, 0, 0, 0, BB};
+            if ((rc = launch_gemm_nt(g, ep, nb, st))) return rc;
+        }
+        {   // X^T -> upper-right block of the transposed inverse
+            GemmOperands g{Tt, s, ss, Binv + (long long)s * (BI + 1), BI, pair, s, s, s, ppb, ppb * ss, BB};
+            StoreEpilogue ep{BinvT + s, BI, pair, -1.0, 0.0, 0, 0, 0, BB};
+            if ((rc = launch_gemm_nt(g, ep, nb, st))) return rc;
+        }
+    }
+    return PPBO_OK;
+}
+
+// out[r] = sum_c Mat[r][c] v[c] over the triangle (lower: c <= r, upper: r <= c < rows) of one BI x BI block; warp per row
+__global__ void __launch_bounds__(256) blocktri_gemv_kernel(const double* __restrict__ Mat, const double* __restrict__ v,
+                                                            double* __restrict__ out, int rows, int upper) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r >= rows) return;
+    const double* m = Mat + (long long)r * BI;
+    const int c_lo = upper ? (r & ~31) : 0, c_hi = upper ? rows : r + 1;
+    double s0 = 0.0, s1 = 0.0;
+    int c = c_lo + lane;
+    for (; c + 32 < c_hi; c += 64) {
+        const double a0 = m[c], a1 = m[c + 32];          // the other triangle holds exact zeros
+        s0 = fma(a0, v[c], s0);
+        s1 = fma(a1, v[c + 32], s1);
+    }
+    if (c < c_hi) s0 = fma(m[c], v[c], s0);
+    double a = s0 + s1;
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) out[r] = a;
+}
+// forward sweep: t[r] -= sum_{c < cols} L[r][c0 + c] y[c] for r in [r0, n); warp per row
+__global__ void __launch_bounds__(256) blockrow_update_kernel(const double* __restrict__ L, long long ldl, int r0, int n, int c0,
+                                                              int cols, const double* __restrict__ y, double* __restrict__ t) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = r0 + blockIdx.x * 8 + warp;
+    if (r >= n) return;
+    const double* l = L + (long long)r * ldl + c0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = lane;
+    for (; c + 96 < cols; c += 128) {
+        s0 = fma(l[c], y[c], s0);
+        s1 = fma(l[c + 32], y[c + 32], s1);
+        s2 = fma(l[c + 64], y[c + 64], s2);
+        s3 = fma(l[c + 96], y[c + 96], s3);
+    }
+    for (; c < cols; c += 32) s0 = fma(l[c], y[c], s0);
+    double a = (s0 + s1) + (s2 + s3);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) t[r] -= a;
+}
+// backward sweep: y[c] -= sum_{r0 <= r < r1} L[r][c] x[r - r0] for c < c1; a CTA owns 32 columns, its 8 warps split the rows
+__global__ void __launch_bounds__(256) blockcol_update_kernel(const double* __restrict__ L, long long ldl, int r0, int r1, int c1,
+                                                              const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double part[8][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 32 + lane;
+    double s0 = 0.0, s1 = 0.0;
+    if (c < c1) {
+        int r = r0 + warp;
+        for (; r + 8 < r1; r += 16) {
+            s0 = fma(L[(long long)r * ldl + c], x[r - r0], s0);
+            s1 = fma(L[(long long)(r + 8) * ldl + c], x[r + 8 - r0], s1);
+        }
+        if (r < r1) s0 = fma(L[(long long)r * ldl + c], x[r - r0], s0);
+    }
+    part[warp][lane] = s0 + s1;
+    __syncthreads();
+    if (warp == 0 && c < c1) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += part[w][lane];
+        y[c] -= a;
+    }
+}
+
+// (L L^T) x = t in place with the block inverses W of blockinv_build
+int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st) {
+    const int nbI = ceil_div(n, BI);
+    const long long BB = (long long)BI * BI;
+    const double* Binv = W;
+    const double* BinvT = Binv + nbI * BB;
+    double* y = W + nbI * (3 * BB + BB / 4);
+    for (int J = 0; J < nbI; ++J) {                     // L y = t
+        const int j0 = J * BI, rows = min(BI, n - j0), j1 = j0 + rows;
+        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(Binv + J * BB, t + j0, y + j0, rows, 0);
+        if (j1 < n)
+            PPBO_CL blockrow_update_kernel<<<ceil_div(n - j1, 8), 256, 0, st>>>(L, ldl, j1, n, j0, rows, y + j0, t);
+    }
+    for (int J = nbI - 1; J >= 0; --J) {                // L^T x = y
+        const int j0 = J * BI, rows = min(BI, n - j0);
+        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(BinvT + J * BB, y + j0, t + j0, rows, 1);
+        if (j0 > 0)
+            PPBO_CL blockcol_update_kernel<<<ceil_div(j0, 32), 256, 0, st>>>(L, ldl, j0, j0 + rows, j0, t + j0, y);
+    }
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
 // ------------------------------------------------------------------------------------------- TRSM (many RHS, one per row)
 // X[nrhs x n] <- X . L^-T : column blocks ascending; Y_J = X_J . inv(L_JJ)^T ; X[:, J+1:] -= Y_J . L[J+1:, J]^T
 int trsm_right_lower_t(const double* L, long long ldl, int n, const double* dinv, double* X, long long ldx, int nrhs,
@@ -818,6 +998,23 @@ namespace ppbo { int set_identity(double* A, long long ld, int n, cudaStream_t s
 
 /* out = (L L^T)^-1 from the factor ppbo_potrf_lower left in A (lower) and its workspace: Y = I L^-T, out = Y Y^T.
  * work: n*n doubles.  Replaces misc.pd_inverse (src/misc.py:96-100) for the public attributes that are explicit inverses. */
+extern "C" long long ppbo_blockinv_bytes(int n) { return n > 0 ? blockinv_doubles(n) * 8 : 0; }
+
+extern "C" int ppbo_blockinv_build(const double* L, long long ldl, int n, const void* potrf_workspace, void* blockinv,
+                                   long long blockinv_bytes, void* stream) {
+    PPBO_REQUIRE(n >= 1 && ldl >= n, "shape");
+    PPBO_REQUIRE(blockinv_bytes >= ppbo_blockinv_bytes(n), "block-inverse workspace too small");
+    return blockinv_build(L, ldl, n, reinterpret_cast<const double*>(potrf_workspace), reinterpret_cast<double*>(blockinv),
+                          (cudaStream_t)stream);
+}
+
+extern "C" int ppbo_potrs_vec_blockinv(const double* L, long long ldl, int n, void* blockinv, long long blockinv_bytes,
+                                       double* x, void* stream) {
+    PPBO_REQUIRE(n >= 1 && ldl >= n, "shape");
+    PPBO_REQUIRE(blockinv_bytes >= ppbo_blockinv_bytes(n), "block-inverse workspace too small");
+    return potrs_vec_blockinv(L, ldl, n, reinterpret_cast<double*>(blockinv), x, (cudaStream_t)stream);
+}
+
 extern "C" int ppbo_potri_lower(const double* L, long long ldl, int n, void* workspace, long long workspace_bytes, double* work,
                                 double* out, long long ldo, void* stream) {
     PPBO_REQUIRE(n >= 0 && ldl >= n && ldo >= n, "shape");

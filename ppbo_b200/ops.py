@@ -101,7 +101,22 @@ def diffspace_gram(Sigma, Q, m):
 
 class LaplaceFit:
     """Device-resident products of the MAP fit (everything prediction / acquisition needs)."""
-    __slots__ = ("Q", "m", "sigma", "f_map", "alpha", "arrow", "G", "Lfac", "stats", "n_neg", "neg_corr", "info")
+    __slots__ = ("Q", "m", "sigma", "f_map", "alpha", "arrow", "G", "Lfac", "stats", "n_neg", "_neg_idx", "_neg_corr", "info")
+
+    @property
+    def neg_corr(self):
+        """Exact rank-r Woodbury correction of the posterior covariance for the r observations with a negative likelihood
+        curvature (W indefinite there; the factor carries a+ only).  Only prediction WITH covariance needs it, so it is
+        built on first use (r solves with the factor) instead of inside every fit."""
+        if self._neg_corr is None and self.n_neg > 0 and self.info == 0:
+            lib = _lib.load()
+            M = self.Q * self.m
+            self._neg_corr = torch.empty(lib.ppbo_neg_corr_doubles(M, self.n_neg), dtype=F64, device=self.G.device)
+            rc2 = check(lib.ppbo_neg_corr_build(_p(self.G), M, _p(self.arrow), _p(self.Lfac), self._neg_idx, self.n_neg,
+                                                _p(self._neg_corr), _stream()), "ppbo_neg_corr_build")
+            if rc2 > 0:
+                self.info = rc2
+        return self._neg_corr
 
 
 def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10):
@@ -124,17 +139,11 @@ def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10):
     fit.info = rc
     fit.stats = dict(iterations=int(stats[0]), last_step=stats[1], last_rel_step=stats[2], T=stats[3],
                      halvings=int(stats[4]), factorizations=int(stats[6]), chord_steps=int(stats[7]))
-    fit.n_neg, fit.neg_corr = 0, None
+    fit.n_neg, fit._neg_corr, fit._neg_idx = 0, None, None
     if rc == 0:
         idx = (ctypes.c_int * M)()
-        r = check(lib.ppbo_neg_count(_p(fit.arrow), M, idx, M, _stream()), "ppbo_neg_count")
-        if r > 0:
-            fit.neg_corr = torch.empty(lib.ppbo_neg_corr_doubles(M, r), dtype=F64, device=dev)
-            rc2 = check(lib.ppbo_neg_corr_build(_p(fit.G), M, _p(fit.arrow), _p(fit.Lfac), idx, r, _p(fit.neg_corr),
-                                                _stream()), "ppbo_neg_corr_build")
-            if rc2 > 0:
-                fit.info = rc2
-            fit.n_neg = r
+        fit.n_neg = check(lib.ppbo_neg_count(_p(fit.arrow), M, idx, M, _stream()), "ppbo_neg_count")
+        fit._neg_idx = idx
     return fit
 
 
@@ -187,6 +196,25 @@ def potrs_vec(L, ws, b):
     return x[:n]
 
 
+def blockinv_build(L, ws):
+    """1024 x 1024 block inverses of a factor from potrf_lower (for many solves with the same factor)"""
+    lib = _lib.load()
+    n = L.shape[0]
+    nbytes = lib.ppbo_blockinv_bytes(n)
+    W = torch.empty(nbytes // 8, dtype=F64, device=L.device)
+    check(lib.ppbo_blockinv_build(_p(L), L.stride(0), n, _p(ws), _p(W), nbytes, _stream()), "ppbo_blockinv_build")
+    return W
+
+
+def potrs_vec_blockinv(L, W, b):
+    """solve (L L^T) x = b with the block inverses W of blockinv_build; returns x (new tensor)"""
+    n = L.shape[0]
+    x = b.clone()
+    check(_lib.load().ppbo_potrs_vec_blockinv(_p(L), L.stride(0), n, _p(W), W.numel() * 8, _p(x), _stream()),
+          "ppbo_potrs_vec_blockinv")
+    return x
+
+
 def potri_lower(L, ws):
     """dense (L L^T)^-1 from a factor produced by potrf_lower"""
     lib = _lib.load()
@@ -221,8 +249,9 @@ def predict(kernel, X, lengthscales, sigma_f, shrinkage, fit, Xp, P, batch, want
     Sp = torch.empty((batch, P, P), dtype=F64, device=dev) if want_cov else None
     wbytes = lib.ppbo_predict_workspace_bytes(N, fit.Q, fit.m, P, batch)
     ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev)
+    neg_corr = fit.neg_corr if want_cov else None            # the mean needs alpha only
     check(lib.ppbo_predict(_kind(kernel), _p(X), N, D, _ls(lengthscales, D), float(sigma_f), float(shrinkage), fit.Q, fit.m,
-                           _p(fit.alpha), _p(fit.arrow), _p(fit.Lfac), _p(fit.neg_corr), fit.n_neg, _p(Xp), P, batch,
+                           _p(fit.alpha), _p(fit.arrow), _p(fit.Lfac), _p(neg_corr), fit.n_neg if want_cov else 0, _p(Xp), P, batch,
                            _p(mu), _p(Sp), _p(ws), wbytes, _stream()), "ppbo_predict")
     return mu.view(batch, P), Sp
 

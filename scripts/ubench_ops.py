@@ -3,7 +3,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from ppbo_b200 import ops, synthetic, iteration
+from ppbo_b200 import _lib, ops, synthetic, iteration
 
 dev = torch.device("cuda", 0)
 
@@ -28,6 +28,11 @@ def main():
         A0 = torch.randn(n, n, dtype=torch.float64, device=dev)
         A = A0 @ A0.T + n * torch.eye(n, dtype=torch.float64, device=dev)
         W = A.clone()
+        if n >= 2000:
+            _lib.load().ppbo_set_tuning(3, 1)
+            t1 = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
+            _lib.load().ppbo_set_tuning(3, 0)
+            print("potrf n=%d, critical path on the caller's stream (no priorities): %.3f ms" % (n, t1))
         t = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
         W.copy_(A)
         info, ws = ops.potrf_lower(W)
@@ -58,10 +63,9 @@ def main():
             err = float((C - ref).abs().max() / ref.abs().max())
             t = timeit(lambda: ops.gemm_nt_cfg(cfg, A, B, C, 1.0, 1.0))
             print("  cfg %d %dx%dx%d: %.3f ms (%.2f TFLOP/s) err=%.1e" % (cfg, M, N, K, t, 2.0 * M * N * K / t / 1e9, err))
-    from ppbo_b200 import _lib
     Om = torch.randn(32768, 1000, dtype=torch.float64, device=dev)
     PhiT = torch.randn(20, 1024, 1000, dtype=torch.float64, device=dev)
-    for cfg in (0, 1, 3):
+    for cfg in (() if "--no-rowmax" in sys.argv else (0, 1, 3)):
         _lib.load().ppbo_set_tuning(0, cfg)
         t = timeit(lambda: ops.rff_eval_argmax(Om, PhiT), reps=3, warm=1)
         print("rowmax cfg %d S=32768 F=1000 P=1024 B=20: %.2f ms (%.2f TFLOP/s)" % (cfg, t, 2.0 * 32768 * 1000 * 1024 * 20 / t / 1e9))

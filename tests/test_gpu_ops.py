@@ -326,6 +326,24 @@ def test_potrs_vec_and_potri(ops, n):
     assert np.abs(Ainv @ A - np.eye(n)).max() <= 1e-11 * n
 
 
+@pytest.mark.parametrize("n", [1, 100, 128, 129, 1000, 1024, 1025, 2500, 3072])
+def test_potrs_vec_blockinv(ops, n):
+    """block-inverse solve (1024 x 1024 inverted diagonal blocks) against the chained solve and the residual"""
+    rng = np.random.RandomState(n)
+    A0 = rng.randn(n, n)
+    A = A0 @ A0.T + n * np.eye(n)
+    Ad = ops.to_dev(A)
+    info, ws = ops.potrf_lower(Ad)
+    assert info == 0
+    W = ops.blockinv_build(Ad, ws)
+    for _ in range(2):                                   # the workspace is reusable
+        b = rng.randn(n)
+        x = _np(ops.potrs_vec_blockinv(Ad, W, ops.to_dev(b)))
+        assert np.abs(A @ x - b).max() <= 1e-12 * n * np.abs(b).max()
+        x2 = _np(ops.potrs_vec(Ad, ws, ops.to_dev(b)))
+        assert np.abs(x - x2).max() <= 1e-12 * np.abs(x2).max()
+
+
 def test_shrink_inplace(ops):
     from oracle import ppbo_oracle as O
     rng = np.random.RandomState(2)
