@@ -312,8 +312,7 @@ def main():
         am = torch.empty((B, hi - lo), dtype=torch.int32, device=dev)
 
         def dominant():
-            ops.check(lib.ppbo_ozaki_rowmax(ops._p(ap), ops._p(asc), hi - lo, ops._p(bp), ops._p(bsc), P, B, Fdim, ks,
-                                            ops._p(fm), ops._p(am), None, None, ops._stream()), "ppbo_ozaki_rowmax")
+            ops.ozaki_rowmax(ap, asc, hi - lo, bp, bsc, P, B, Fdim, ks, fmax=fm, arg=am)
     else:
         def dominant():
             ops.rff_eval_argmax(Omega, PhiT)

@@ -208,9 +208,12 @@ int ppbo_ozaki_slice(const double* X, long long ldx, long long strideX, int rows
                      double* scale, signed char* planes, void* stream);
 /* fmax[batch][S], arg[batch][S] = per-sample max / first arg-max over the P grid points of A . B_b^T from digit planes
  * (A sliced with tile_rows(0), batch 1; B with tile_rows(1), `batch` grids).  Fs_full (optional, tests): dense [batch][S x P].
+ * workspace: ppbo_ozaki_rowmax_workspace_bytes(S, P, batch) bytes (partial maxima of the column-tile groups).
  * err_flag (optional, device int): set to the id of a starved pipeline wait before the kernel traps (never on a healthy run). */
+long long ppbo_ozaki_rowmax_workspace_bytes(int S, int P, int batch);
 int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascale, int S, const signed char* Bplanes, const double* bscale,
-                      int P, int batch, int K, int slices, double* fmax, int* arg, double* Fs_full, int* err_flag, void* stream);
+                      int P, int batch, int K, int slices, double* fmax, int* arg, double* Fs_full, void* workspace,
+                      long long workspace_bytes, int* err_flag, void* stream);
 /* diagnostic: SM clocks for `iters` back-to-back 128 x N x 32 INT8 MMAs on `blocks` SMs, rotating over `nacc` accumulators
  * (mode 0: A, B from shared memory; 1: A from TMEM; 2: B plane re-used); clocks_out[blocks] device int64.
  * Used by scripts/ozaki_probe.py --ubench. */

@@ -234,7 +234,8 @@ struct Params {
     const int8_t* A; const double* ascale; int S, MT;          // MT row tiles of BM samples
     const int8_t* B; const double* bscale; int P, NT, batch;   // NT column tiles of BN grid points per batch entry
     int KBLK;
-    double* fmax; int* arg;                                    // [batch][S]
+    int NG, ntg;                                               // column tiles are taken in NG groups of ntg tiles: one work item each
+    double* fmax; int* arg;                                    // [batch][S] (NG == 1) or partial results [batch][NG][S]
     double* full; long long ld_full, stride_full;              // optional dense output (tests)
     int* err;
     int diag;      // timing experiments only (tuning key 2): bit 0 = epilogue skips the TMEM reads, bit 1 = producer skips the copies
@@ -271,7 +272,11 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int items = p.MT * p.batch;
+    // Work item = (grid b, row tile mt, column-tile group ng), ng fastest: the ~SM-count items in flight cover only
+    // SMs / NG row tiles, so their A planes (KBLK x A_STAGE = 768 KB per row tile at F = 1000) stay L2-resident while the NG
+    // CTAs of a row tile and the ntg column tiles of each CTA re-read them.  With NG = 1 every CTA streams its own row tile 16
+    // times: 113 MB of live A planes thrash the L2 (ncu: 62 GB of DRAM reads per launch, 12 % L2 hit rate).
+    const int items = p.MT * p.batch * p.NG;
     long long clk0 = 0;
     unsigned long long ns0 = 0;
     if ((p.diag & 4) && threadIdx.x == 0) {
@@ -283,9 +288,10 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
         // ------------------------------------------------------------------------------------- producer
         uint32_t stage = 0, phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int b = item / p.MT, mt = item % p.MT;
+            const int ng = item % p.NG, mt = (item / p.NG) % p.MT, b = item / (p.NG * p.MT);
+            const int nt0 = ng * p.ntg, nt1 = min(p.NT, nt0 + p.ntg);
             const int8_t* Ab = p.A + (long long)mt * p.KBLK * C::A_STAGE;
-            for (int nt = 0; nt < p.NT; ++nt) {
+            for (int nt = nt0; nt < nt1; ++nt) {
                 const int8_t* Bb = p.B + ((long long)b * p.NT + nt) * p.KBLK * C::B_STAGE;
                 for (int kb = 0; kb < p.KBLK; ++kb) {
                     mbar_wait(empty_bar + stage, phase ^ 1, p.err, 1);
@@ -305,7 +311,9 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
         // ------------------------------------------------------------------------------------- MMA issuer
         uint32_t stage = 0, phase = 0, tile = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            for (int nt = 0; nt < p.NT; ++nt, ++tile) {
+            const int ng = item % p.NG;
+            const int nt0 = ng * p.ntg, nt1 = min(p.NT, nt0 + p.ntg);
+            for (int nt = nt0; nt < nt1; ++nt, ++tile) {
                 mbar_wait(tempty_bar, (tile & 1) ^ 1, p.err, 2);         // epilogue has drained the accumulators
                 tc_fence_after();
                 for (int kb = 0; kb < p.KBLK; ++kb) {
@@ -363,12 +371,13 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
         const double c_hi = ldexp(1.0, -8 * (C::G1 + 1)), c_lo = ldexp(1.0, -8 * (KS + 1));
         uint32_t tile = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int b = item / p.MT, mt = item % p.MT;
+            const int ng = item % p.NG, mt = (item / p.NG) % p.MT, b = item / (p.NG * p.MT);
+            const int nt0 = ng * p.ntg, nt1 = min(p.NT, nt0 + p.ntg);
             const int row = mt * BM + q * 32 + lane;
             const double as = (row < p.S) ? p.ascale[row] : 1.0;
             double best = -INFINITY;
             int best_arg = 0;
-            for (int nt = 0; nt < p.NT; ++nt, ++tile) {
+            for (int nt = nt0; nt < nt1; ++nt, ++tile) {
                 const double* bs = p.bscale + ((long long)b * p.NT + nt) * BN;
                 mbar_wait(tfull_bar, tile & 1, p.err, 4);
                 tc_fence_after();
@@ -400,8 +409,8 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
                 if (lane == 0) mbar_arrive(tempty_bar);
             }
             if (row < p.S) {
-                p.fmax[(long long)b * p.S + row] = best * as;
-                p.arg[(long long)b * p.S + row] = best_arg;
+                p.fmax[((long long)b * p.NG + ng) * p.S + row] = best * as;
+                p.arg[((long long)b * p.NG + ng) * p.S + row] = best_arg;
             }
         }
     }
@@ -418,8 +427,35 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
     }
 }
 
+// per-sample max over the NG column-tile groups, lowest column index on ties (groups ascend in column index)
+__global__ void __launch_bounds__(256) ozaki_merge_kernel(const double* __restrict__ pmax, const int* __restrict__ parg, int NG,
+                                                          int S, double* __restrict__ fmax, int* __restrict__ arg) {
+    const int s = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+    if (s >= S) return;
+    double best = -INFINITY;
+    int ba = 0;
+    for (int g = 0; g < NG; ++g) {
+        const double v = pmax[((long long)b * NG + g) * S + s];
+        if (v > best) { best = v; ba = parg[((long long)b * NG + g) * S + s]; }
+    }
+    fmax[(long long)b * S + s] = best;
+    arg[(long long)b * S + s] = ba;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 constexpr int BN_DEFAULT = 64;
+// Number of column-tile groups: the fewest for which the A planes of the row tiles in flight (SMs / NG of them, KBLK x KS x 8 KB
+// each) fit in about half of the 126 MB L2 (measured at F = 1000, 6 planes: NG = 1 12.1 ms, 2 9.2 ms, 4 9.8 ms, 8 10.3 ms).
+static int column_groups(int NT, int KBLK, int KS) {
+    int want = g_tuning[4];                                   // tuning key 4 overrides
+    if (want <= 0) {
+        const long long tile_bytes = (long long)KBLK * KS * BM * KB;
+        want = (int)ceil_div_ll((long long)PPBO_SM_COUNT * tile_bytes, 64LL << 20);
+    }
+    want = want < 1 ? 1 : (want > NT ? NT : want);
+    const int ntg = ceil_div(NT, want);
+    return ceil_div(NT, ntg);
+}
 
 struct Shape {
     int rows_pad, KBLK;
@@ -458,7 +494,7 @@ static int rowmax_launch(const Params& p, cudaStream_t st) {
     int dev = 0, sms = PPBO_SM_COUNT;
     PPBO_CUDA_CHECK(cudaGetDevice(&dev));
     PPBO_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int items = p.MT * p.batch;
+    const int items = p.MT * p.batch * p.NG;
     if (items <= 0) return PPBO_OK;
     PPBO_CL ozaki_rowmax_kernel<KS, BN, TS><<<min(items, sms), 192, C::SMEM, st>>>(p);
     PPBO_LAUNCH_CHECK();
@@ -588,9 +624,15 @@ extern "C" int ppbo_ozaki_slice(const double* X, long long ldx, long long stride
     }
 }
 
+extern "C" long long ppbo_ozaki_rowmax_workspace_bytes(int S, int P, int batch) {
+    if (S < 0 || P < 1 || batch < 1) return -1;
+    const int NT = ceil_div(P, oz::BN_DEFAULT);               // room for any grouping
+    return NT > 1 ? (long long)batch * NT * S * 12 + 16 : 0;
+}
+
 extern "C" int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascale, int S, const signed char* Bplanes,
                                  const double* bscale, int P, int batch, int K, int slices, double* fmax, int* arg,
-                                 double* Fs_full, int* err_flag, void* stream) {
+                                 double* Fs_full, void* workspace, long long workspace_bytes, int* err_flag, void* stream) {
     PPBO_REQUIRE(S >= 0 && P >= 1 && batch >= 1 && K >= 1, "shape");
     PPBO_REQUIRE(slices >= 5 && slices <= oz::MAX_KS, "slices in [5, 7]");
     PPBO_REQUIRE(ceil_div(K, oz::KB) * oz::KB <= 16384, "K <= 16384 (INT32 accumulator range)");
@@ -601,13 +643,26 @@ extern "C" int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascal
     p.A = reinterpret_cast<const int8_t*>(Aplanes); p.ascale = ascale; p.S = S; p.MT = ceil_div(S, oz::BM);
     p.B = reinterpret_cast<const int8_t*>(Bplanes); p.bscale = bscale; p.P = P; p.NT = ceil_div(P, oz::BN_DEFAULT); p.batch = batch;
     p.KBLK = ceil_div(K, oz::KB);
-    p.fmax = fmax; p.arg = arg; p.full = Fs_full; p.ld_full = P; p.stride_full = (long long)S * P; p.err = err_flag;
+    p.NG = oz::column_groups(p.NT, p.KBLK, slices);
+    p.ntg = ceil_div(p.NT, p.NG);
+    PPBO_REQUIRE(workspace_bytes >= ppbo_ozaki_rowmax_workspace_bytes(S, P, batch), "workspace too small");
+    PPBO_REQUIRE(p.NG == 1 || workspace != nullptr, "workspace missing");
+    double* pmax = reinterpret_cast<double*>(workspace);
+    int* parg = reinterpret_cast<int*>(pmax + (long long)batch * p.NG * S);
+    p.fmax = p.NG > 1 ? pmax : fmax; p.arg = p.NG > 1 ? parg : arg; p.full = Fs_full; p.ld_full = P; p.stride_full = (long long)S * P; p.err = err_flag;
     p.diag = g_tuning[2];
     cudaStream_t st = (cudaStream_t)stream;
-    const bool ts = g_tuning[1] == 0;          // tuning key 1: 1 = both operands from shared memory (comparison variant)
+    const bool ts = g_tuning[1] == 1;          // tuning key 1: 1 = A planes staged in TMEM (comparison variant, slower)
+    int rc;
     switch (slices) {
-        case 5: return ts ? oz::rowmax_launch<5, oz::BN_DEFAULT, true>(p, st) : oz::rowmax_launch<5, oz::BN_DEFAULT, false>(p, st);
-        case 6: return ts ? oz::rowmax_launch<6, oz::BN_DEFAULT, true>(p, st) : oz::rowmax_launch<6, oz::BN_DEFAULT, false>(p, st);
-        default: return oz::rowmax_launch<7, oz::BN_DEFAULT, false>(p, st);    // 7 x 64 + 7 x 16 columns exceed TMEM
+        case 5: rc = ts ? oz::rowmax_launch<5, oz::BN_DEFAULT, true>(p, st) : oz::rowmax_launch<5, oz::BN_DEFAULT, false>(p, st); break;
+        case 6: rc = ts ? oz::rowmax_launch<6, oz::BN_DEFAULT, true>(p, st) : oz::rowmax_launch<6, oz::BN_DEFAULT, false>(p, st); break;
+        default: rc = oz::rowmax_launch<7, oz::BN_DEFAULT, false>(p, st); break;   // 7 x 64 + 7 x 16 columns exceed TMEM
     }
+    if (rc) return rc;
+    if (p.NG > 1) {
+        PPBO_CL oz::ozaki_merge_kernel<<<dim3(ceil_div(S, 256), batch), 256, 0, st>>>(pmax, parg, p.NG, S, fmax, arg);
+        PPBO_LAUNCH_CHECK();
+    }
+    return PPBO_OK;
 }

@@ -349,20 +349,29 @@ def ozaki_slice(X, operand, slices=6):
     return planes, scale
 
 
+def ozaki_rowmax(ap, asc, S, bp, bsc, P, B, F, slices, fmax=None, arg=None, want_full=False, err=None):
+    """fused INT8 GEMM + per-sample max / first arg-max from digit planes (ppbo_ozaki_rowmax)"""
+    lib = _lib.load()
+    dev = ap.device
+    fmax = torch.empty((B, S), dtype=F64, device=dev) if fmax is None else fmax
+    arg = torch.empty((B, S), dtype=torch.int32, device=dev) if arg is None else arg
+    full = torch.empty((B, S, P), dtype=F64, device=dev) if want_full else None
+    wbytes = lib.ppbo_ozaki_rowmax_workspace_bytes(S, P, B)
+    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev) if wbytes > 0 else None
+    check(lib.ppbo_ozaki_rowmax(_p(ap), _p(asc), S, _p(bp), _p(bsc), P, B, F, slices, _p(fmax), _p(arg), _p(full), _p(ws), wbytes,
+                                _p(err), _stream()), "ppbo_ozaki_rowmax")
+    return fmax, arg, full
+
+
 def rff_eval_argmax_i8(Omega, PhiT_grid, slices=6, want_full=False, sliced_grid=None):
     """rff_eval_argmax on the tcgen05 INT8 tensor pipe (error-free splitting into `slices` digit planes per operand).
     sliced_grid: (planes, scale) of PhiT_grid from ozaki_slice(PhiT_grid, 1, slices) when the caller reuses them."""
     S, F = Omega.shape
     B, P, _ = PhiT_grid.shape
-    fmax = torch.empty((B, S), dtype=F64, device=Omega.device)
-    arg = torch.empty((B, S), dtype=torch.int32, device=Omega.device)
-    full = torch.empty((B, S, P), dtype=F64, device=Omega.device) if want_full else None
     ap, asc = ozaki_slice(Omega, 0, slices)
     bp, bsc = sliced_grid if sliced_grid is not None else ozaki_slice(PhiT_grid, 1, slices)
     err = torch.zeros(1, dtype=torch.int32, device=Omega.device)
-    check(_lib.load().ppbo_ozaki_rowmax(_p(ap), _p(asc), S, _p(bp), _p(bsc), P, B, F, slices, _p(fmax), _p(arg), _p(full),
-                                        _p(err), _stream()), "ppbo_ozaki_rowmax")
-    return fmax, arg, full
+    return ozaki_rowmax(ap, asc, S, bp, bsc, P, B, F, slices, want_full=want_full, err=err)
 
 
 def normal_fill(seed, stream_id, offset, n, dev=None):

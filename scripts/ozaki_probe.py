@@ -49,19 +49,18 @@ def diag(dev):
     fmax = torch.empty((B, S), dtype=torch.float64, device=dev)
     arg = torch.empty((B, S), dtype=torch.int32, device=dev)
     dbg = torch.zeros(8, dtype=torch.int64, device=dev)
-    for ts in (1, 0):
+    for ts in (0,):
         lib.ppbo_set_tuning(1, ts)
         for d in (0, 1, 2, 3):
             lib.ppbo_set_tuning(2, d | 4)
-            t = timeit(lambda: ops.check(lib.ppbo_ozaki_rowmax(ops._p(ap), ops._p(asc), S, ops._p(bp), ops._p(bsc), P, B, F, ks,
-                                                               ops._p(fmax), ops._p(arg), None, ops._p(dbg), ops._stream()), "rowmax"),
-                       reps=5, warm=2)
+            t = timeit(lambda: ops.ozaki_rowmax(ap, asc, S, bp, bsc, P, B, F, ks, fmax=fmax, arg=arg, err=dbg), reps=5, warm=2)
             mmas = (S // 128) * B * (P // 64) * 16 * 42 / 148
             clk, ns = dbg[1].item(), dbg[2].item()
             print("smem-A=%d diag=%d: %.3f ms; block 0: %.3f ms at %.0f MHz -> %.1f clk per 128x64x32 MMA (floor 32)" % (
                 ts, d, t, ns * 1e-6, clk / ns * 1e3, clk / mmas), flush=True)
     lib.ppbo_set_tuning(2, 0)
     lib.ppbo_set_tuning(1, 0)
+    lib.ppbo_set_tuning(4, 0)
 
 
 def main():
@@ -78,8 +77,9 @@ def main():
     PhiT = 0.02 * torch.cos(3 * torch.randn(B, P, F, dtype=torch.float64, device=dev))
     lib = _lib.load()
     ref = ops.rff_eval_argmax(Om, PhiT)
-    for ks, ss in ((5, 0), (6, 0), (5, 1), (6, 1), (7, 0)):
+    for ks, ss, ng in ((6, 0, 1), (6, 0, 2), (6, 0, 4), (6, 0, 8), (6, 0, 16), (5, 0, 4), (7, 0, 4), (6, 1, 4)):
         lib.ppbo_set_tuning(1, ss)
+        lib.ppbo_set_tuning(4, ng)
         ta = timeit(lambda: ops.ozaki_slice(Om, 0, ks))
         tb = timeit(lambda: ops.ozaki_slice(PhiT, 1, ks))
         ap, asc = ops.ozaki_slice(Om, 0, ks)
@@ -89,15 +89,16 @@ def main():
         err = torch.zeros(1, dtype=torch.int32, device=dev)
 
         def run():
-            ops.check(lib.ppbo_ozaki_rowmax(ops._p(ap), ops._p(asc), S, ops._p(bp), ops._p(bsc), P, B, F, ks, ops._p(fmax),
-                                            ops._p(arg), None, ops._p(err), ops._stream()), "ozaki_rowmax")
+            ops.ozaki_rowmax(ap, asc, S, bp, bsc, P, B, F, ks, fmax=fmax, arg=arg, err=err)
         t = timeit(run, reps=3, warm=1)
         flop = 2.0 * S * F * P * B
         iops = flop * ks * (ks + 1) / 2
         d = (fmax - ref[0]).abs().max().item() / ref[0].abs().max().item()
         same = (arg == ref[1]).double().mean().item()
-        print("slices=%d%s: slice A %.3f ms, slice B %.3f ms, gemm+rowmax %.3f ms = %.1f TFLOP/s FP64-equivalent, %.0f TOP/s int8; "
-              "max rel diff vs DMMA %.2e, same argmax %.6f" % (ks, " (A,B in smem)" if ss else "", ta, tb, t, flop / t / 1e9, iops / t / 1e9, d, same), flush=True)
+        print("slices=%d groups=%d%s: slice A %.3f ms, slice B %.3f ms, gemm+rowmax %.3f ms = %.1f TFLOP/s FP64-equivalent, %.0f TOP/s int8; "
+              "max rel diff vs DMMA %.2e, same argmax %.6f" % (ks, ng, " (A staged in TMEM)" if ss else "", ta, tb, t, flop / t / 1e9, iops / t / 1e9, d, same), flush=True)
+    lib.ppbo_set_tuning(1, 0)
+    lib.ppbo_set_tuning(4, 0)
 
 
 if __name__ == "__main__":
