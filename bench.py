@@ -196,14 +196,21 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def iteration_slices():
+    from ppbo_b200 import iteration
+    return iteration.SAMPLING_SLICES
+
+
 def workload_config(prob, n_gpus):
     return {"workload": "%s: D=%d, Q=%d queries x m=%d (N=%d rows, %d pseudo-observations), %s theta=%s, F=%d RFF features, "
                         "%d query directions x P=%d xi-grid points, S=%d samples" % (
                             prob["name"], prob["D"], prob["Q"], prob["m"], prob["N"], prob["Q"] * prob["m"], prob["kernel"],
                             prob["theta"], prob["F"], prob["grids"].shape[0], prob["P"], prob["S"]),
-            "parallelism": "fit on rank 0 + broadcast; S sharded over %d rank(s); one all-reduce of 3 x directions doubles" % n_gpus,
+            "parallelism": "GP fit on rank 0, weight-space fit on rank %d, broadcast of (omega_MAP, diag Hessian, mu*); S sharded over %d "
+                           "rank(s); one all-reduce of 3 x directions doubles" % (1 if n_gpus > 1 else 0, n_gpus),
             "l2_policy": "working set per step (Sigma, G, factor, Omega, PhiT: > 1 GB) exceeds the 126 MB L2; no explicit flush",
-            "fit_start": "cold: GP Newton from f = 0; weight-space Newton from the ridge projection of the GP mode"}
+            "fit_start": "cold: GP Newton from f = 0; weight-space Newton from omega = 0, concurrently with the GP fit",
+            "sampling_engine": "tcgen05 INT8, %d digit planes per operand (error-free splitting; FP64-GEMM accuracy)" % iteration_slices()}
 
 
 # ------------------------------------------------------------------------------------------------- our arm

@@ -193,6 +193,12 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, no swizzle (PTX ISA "matrix descriptor"; CUTLASS cute/arch/mma_sm100_desc.hpp):
@@ -240,6 +246,45 @@ struct Params {
     int* err;
     int diag;      // timing experiments only (tuning key 2): bit 0 = epilogue skips the TMEM reads, bit 1 = producer skips the copies
 };
+
+// 16 columns of one row: recombine the KS INT32 accumulators into two exact INT64 words (hi: diagonals < G1, lo: the rest),
+// convert, add with ONE rounding, scale by the column's power of two and update the running max / first arg-max.
+// v = (hi + lo 2^-8(KS-G1)) * bs;  the common factor 2^-8(G1+1) and the row scale are applied once per row by the caller.
+// For KS <= 6 both words stay below 2^44 and are converted by adding them to the bit pattern of 2^52 + 2^51 (exact; the
+// INT64 -> FP64 convert instruction is a quarter-rate op and was a third of the epilogue's issue slots).
+template <int KS, int G1, bool CHECKED, int NC>
+__device__ __forceinline__ void epi_columns(const uint32_t (&acc)[KS][NC], const double* __restrict__ bs, int col0, int P,
+                                            double* __restrict__ full_row, double as2, double& best, int& best_arg) {
+    constexpr long long MAGIC = 0x4338000000000000LL;             // bits of 2^52 + 2^51
+    const double magic_d = 6755399441055744.0, lo_w = 1.0 / (double)(1ull << (8 * (KS - G1)));
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        long long hi = (KS <= 6) ? MAGIC : 0, lo = hi;
+#pragma unroll
+        for (int d = 0; d < G1; ++d) hi += (long long)(int)acc[d][c] << (8 * (G1 - 1 - d));
+#pragma unroll
+        for (int d = G1; d < KS; ++d) lo += (long long)(int)acc[d][c] << (8 * (KS - 1 - d));
+        double hd, ld;
+        if (KS <= 6) {
+            hd = __longlong_as_double(hi) - magic_d;
+            ld = __longlong_as_double(lo) - magic_d;
+        } else {
+            hd = (double)hi;
+            ld = (double)lo;
+        }
+        const double v = fma(ld, lo_w, hd) * __ldg(bs + c);
+        const int col = col0 + c;
+        if (CHECKED) {
+            if (col < P) {
+                if (full_row) full_row[col] = v * as2;
+                if (v > best) { best = v; best_arg = col; }
+            }
+        } else if (v > best) {
+            best = v;
+            best_arg = col;
+        }
+    }
+}
 
 template <int KS, int BN, bool TS>
 __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
@@ -368,40 +413,36 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
         // ------------------------------------------------------------------------------------- epilogue
         const int q = warp & 3;                                          // TMEM lane quarter this warp may read
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const double c_hi = ldexp(1.0, -8 * (C::G1 + 1)), c_lo = ldexp(1.0, -8 * (KS + 1));
+        const double c_hi = ldexp(1.0, -8 * (C::G1 + 1));
         uint32_t tile = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int ng = item % p.NG, mt = (item / p.NG) % p.MT, b = item / (p.NG * p.MT);
             const int nt0 = ng * p.ntg, nt1 = min(p.NT, nt0 + p.ntg);
             const int row = mt * BM + q * 32 + lane;
-            const double as = (row < p.S) ? p.ascale[row] : 1.0;
+            const double as2 = ((row < p.S) ? p.ascale[row] : 1.0) * c_hi;     // row scale and the weight of the high word
             double best = -INFINITY;
             int best_arg = 0;
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
                 const double* bs = p.bscale + ((long long)b * p.NT + nt) * BN;
                 mbar_wait(tfull_bar, tile & 1, p.err, 4);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < ((p.diag & 1) ? 0 : BN); c0 += 16) {
-                    uint32_t acc[KS][16];
+                const bool checked = p.full != nullptr || (nt + 1) * BN > p.P;     // partial tile or dense output wanted
+                double* full_row = (p.full && row < p.S) ? p.full + (long long)b * p.stride_full + (long long)row * p.ld_full : nullptr;
+                // 8-column chunks, double-buffered in registers: the TMEM loads of chunk k+1 are in flight while chunk k is
+                // recombined (tcgen05.wait::ld waits for every outstanding load, so the wait sits right before the next issue)
+                if (!(p.diag & 1)) {
+                    uint32_t acc[2][KS][8];
 #pragma unroll
-                    for (int d = 0; d < KS; ++d) tc_ld16(lane_addr + (uint32_t)(d * BN + c0), acc[d]);
-                    tc_ld_wait();
+                    for (int d = 0; d < KS; ++d) tc_ld8(lane_addr + (uint32_t)(d * BN), acc[0][d]);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        long long hi = 0, lo = 0;
+                    for (int k = 0; k < BN / 8; ++k) {
+                        tc_ld_wait();
+                        if (k + 1 < BN / 8) {
 #pragma unroll
-                        for (int d = 0; d < C::G1; ++d) hi = hi * 256 + (long long)(int)acc[d][c];
-#pragma unroll
-                        for (int d = C::G1; d < KS; ++d) lo = lo * 256 + (long long)(int)acc[d][c];
-                        const int col = nt * BN + c0 + c;
-                        double v = fma((double)lo, c_lo, (double)hi * c_hi);
-                        v *= __ldg(bs + c0 + c);
-                        if (col < p.P) {
-                            if (p.full && row < p.S)
-                                p.full[(long long)b * p.stride_full + (long long)row * p.ld_full + col] = v * as;
-                            if (v > best) { best = v; best_arg = col; }
+                            for (int d = 0; d < KS; ++d) tc_ld8(lane_addr + (uint32_t)(d * BN + (k + 1) * 8), acc[(k + 1) & 1][d]);
                         }
+                        if (checked) epi_columns<KS, C::G1, true, 8>(acc[k & 1], bs + k * 8, nt * BN + k * 8, p.P, full_row, as2, best, best_arg);
+                        else epi_columns<KS, C::G1, false, 8>(acc[k & 1], bs + k * 8, nt * BN + k * 8, p.P, nullptr, as2, best, best_arg);
                     }
                 }
                 tc_fence_before();
@@ -409,7 +450,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
                 if (lane == 0) mbar_arrive(tempty_bar);
             }
             if (row < p.S) {
-                p.fmax[((long long)b * p.NG + ng) * p.S + row] = best * as;
+                p.fmax[((long long)b * p.NG + ng) * p.S + row] = best * as2;
                 p.arg[((long long)b * p.NG + ng) * p.S + row] = best_arg;
             }
         }

@@ -256,12 +256,11 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
     mark("grid_features")
     pack = torch.empty(2 * Fdim + 1, dtype=F64, device=X.device)
     gp = rff = None
-    if shard.rank == 0 and CONCURRENT_FITS:
+    rff_rank = 1 if (CONCURRENT_FITS and shard.world > 1) else 0      # with more than one GPU the two fits run on two of them
+    if shard.rank == 0 and CONCURRENT_FITS and shard.world == 1:
         main = torch.cuda.current_stream()
         side = _side_stream(X.device)
         side.wait_stream(main)
-        gp_stream = _side_stream(X.device, GP_STREAM_PRIORITY) if GP_STREAM_PRIORITY is not None else main
-        gp_stream.wait_stream(main)
         box = {}
 
         def weight_space_fit():
@@ -274,14 +273,9 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         th = threading.Thread(target=weight_space_fit, name="ppbo-rff-fit")
         th.start()
         try:
-            with torch.cuda.stream(gp_stream):
-                gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
-                mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
-            main.wait_stream(gp_stream)
-            if gp_stream is not main:
-                for t in (gp.Sigma, gp.lap.G, gp.lap.Lfac, gp.lap.f_map, gp.lap.alpha, gp.lap.arrow, mustar):
-                    t.record_stream(main)
+            gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
             mark("gp_fit")
+            mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
             mark("mustar")
         finally:
             th.join()
@@ -292,18 +286,26 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         for t in (rff.omega_map, rff.hess_diag, rff.Phi_X):
             t.record_stream(main)
         mark("rff_fit")                        # what is left of the weight-space fit after the GP fit has finished
-    elif shard.rank == 0:
-        gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
-        mark("gp_fit")
-        mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
-        mark("mustar")
-        rff = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol, f_map=gp.f_map)
-        mark("rff_fit")
-    if shard.rank == 0:
+    else:
+        if shard.rank == 0:
+            gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
+            mark("gp_fit")
+            mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
+            mark("mustar")
+        if shard.rank == rff_rank:
+            rff = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol,
+                          f_map=gp.f_map if (gp is not None and not CONCURRENT_FITS) else None)
+            mark("rff_fit")
+    if shard.rank == rff_rank:
         pack[:Fdim].copy_(rff.omega_map)
         pack[Fdim:2 * Fdim].copy_(rff.hess_diag)
+    if shard.rank == 0:
         pack[2 * Fdim:].copy_(mustar)
-    shard.broadcast(pack, src=0)
+    if rff_rank == 0:
+        shard.broadcast(pack, src=0)
+    else:
+        shard.broadcast(pack[:2 * Fdim], src=rff_rank)
+        shard.broadcast(pack[2 * Fdim:], src=0)
     if rff is None:
         rff = RFFFit()
         rff.W, rff.b, rff.sigma_f, rff.Phi_X, rff.stats = W, b, float(theta[2]), None, None

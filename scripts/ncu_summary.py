@@ -14,7 +14,13 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
         "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
-        "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum"]
+        "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
+        # tcgen05 kernels (csrc/ozaki.cu)
+        "gpc__cycles_elapsed.max", "sm__cycles_active.avg", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_writes.sum.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "sm__inst_executed_pipe_uniform_realtime.avg.pct_of_peak_sustained_elapsed"]
 
 
 def launches(path):
@@ -37,7 +43,7 @@ def launches(path):
 def rep(path, keys=KEYS):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, units = rows[0], rows[1]
+    hdr, units = [re.sub(r"^[A-Z_]+\.Triage[A-Za-z]*\.", "", h) for h in rows[0]], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     for r in rows[2:]:
         print("== %s  grid=%s block=%s" % (re.sub(r"\(.*", "", r[col["Kernel Name"]])[:100], r[col.get("Grid Size", 0)], r[col.get("Block Size", 0)]))
