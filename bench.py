@@ -341,7 +341,11 @@ def main():
         peak, peak_src = int8_peak_tops()
         roof = {"kernel": "ozaki_rowmax_kernel<%d,64> (RFF sampling contraction on tcgen05.mma.kind::i8, %d digit planes per operand, "
                           "fused per-sample max/arg-max)" % (ks, ks),
-                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": None,
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape (profiles/r01_ncu_ozaki_rowmax.txt);
+                # algorithmic HBM bytes: the A digit planes once per grid + the B planes = 20 x 201 MB + 126 MB = 4.15 GB
+                "traffic": (4.501766e9 + 2.0655e7) if (args.config == "ackley20d" and hi - lo == 32768 and ks == 6 and P == 1024) else None,
+                "traffic_unit": "bytes per launch (ncu)",
                 "kernel_ms": gemm_t, "ops_per_launch": ops_per_launch, "fp64_equivalent_tflops": fp64_equiv,
                 "fp64_dmma_peak_tflops": FP64_TENSOR_PEAK_TFLOPS, "peak_source": peak_src}
     else:

@@ -230,20 +230,27 @@ __device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, i
 // Same contract as smem_gemm, on the FP64 tensor pipe: each warp owns 16 x 16 output tiles (2 x 2 DMMA.8x8x4 tiles) and
 // loads one double per lane and fragment, i.e. 1/16 shared-memory load per FMA instead of 1 (the scalar version is
 // LDS-bandwidth bound and took ~33 us of the diagonal-block kernel).  m, n multiples of 16, K a multiple of 4.
-template <bool B_KMAJOR>
+// KR restricts the k range of a tile when one operand is triangular (one SM delivers only ~127 FP64 tensor flop per clock, so
+// skipping the structural zeros is worth it): KR_GE_J: B[k][j] = 0 for k < j;  KR_LE_I: A[i][k] = 0 for k > i.
+// Warps [warp0, warp0 + nwarps) take part.
+enum { KR_FULL = 0, KR_GE_J = 1, KR_LE_I = 2 };
+template <bool B_KMAJOR, int KR = KR_FULL>
 __device__ __forceinline__ void smem_gemm_mma(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n,
-                                              int K, double sign, bool acc, bool lower_only) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+                                              int K, double sign, bool acc, bool lower_only, int warp0 = 0,
+                                              int nwarps = 16) {
+    const int warp = (threadIdx.x >> 5) - warp0, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+    if (warp < 0 || warp >= nwarps) return;
     const int tm = m >> 4, tn = n >> 4;
-    for (int t = warp; t < tm * tn; t += POTF2_THREADS / 32) {
+    for (int t = warp; t < tm * tn; t += nwarps) {
         const int ti = t % tm, tj = t / tm;
         if (lower_only && ti < tj) continue;
         const int i0 = ti * 16, j0 = tj * 16;
+        const int k_lo = (KR == KR_GE_J) ? j0 : 0, k_hi = (KR == KR_LE_I) ? min(K, i0 + 16) : K;
         double c[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
         const double* a0 = A + (i0 + gq) * lda + t4;
         const double* a1 = a0 + 8 * lda;
 #pragma unroll 4
-        for (int k = 0; k < K; k += 4) {
+        for (int k = k_lo; k < k_hi; k += 4) {
             const double x0 = a0[k], x1 = a1[k];
             double y0, y1;
             if (B_KMAJOR) {
@@ -272,32 +279,40 @@ __device__ __forceinline__ void smem_gemm_mma(double* C, int ldc, const double* 
     }
 }
 
-// warp-level Cholesky + inverse of a 32 x 32 block held in shared memory (row stride lds).  Lane i owns row i in registers;
+// warp-level Cholesky of a 32 x 32 block held in shared memory (row stride lds), in place.  Lane i owns row i in registers;
 // column k of the running Schur complement is exchanged through a double-buffered shared-memory line read back as broadcast
-// loads (one __syncwarp per column, no shuffles).  wsm: 96 doubles of scratch.  Returns 0 or the 1-based index of the first
-// non-positive pivot (same value in every lane).
-__device__ __forceinline__ int warp_potrf_inv32(double* Sb, int lds, double* Rb, double* wsm) {
+// loads (one __syncwarp per column).  The multipliers use 1/d (on the dependency chain), the 1/sqrt(d) scaling of the finished
+// column is off it.  wsm: [0,96) exchange lines, [96,128) 1 / L[k][k].  Returns 0 or the 1-based index of the first non-positive
+// pivot (same value in every lane).
+__device__ __forceinline__ int warp_potrf32(double* Sb, int lds, double* wsm) {
     const int lane = threadIdx.x & 31;
-    double* col = wsm;            // [2][32]
-    double* idiag = wsm + 64;     // [32]  1 / L[k][k]
+    double* idiag = wsm + 96;     // [32]  1 / L[k][k];  wsm[0,96): three exchange lines
     double r[POTF2_SUB];
 #pragma unroll
     for (int j = 0; j < POTF2_SUB; ++j) r[j] = (j <= lane) ? Sb[lane * lds + j] : 0.0;
     int bad = 0;
+    wsm[lane] = r[0];
+    __syncwarp();
+    // Software-pipelined: column k+1 is published (one FMA after the multiplier is known) BEFORE the remaining updates of column
+    // k are issued, so the shared-memory round trip of the exchange overlaps with them.  Three exchange lines: the line written in
+    // step k was last read in step k-2, with the __syncwarp of step k-1 in between.
 #pragma unroll
     for (int k = 0; k < POTF2_SUB; ++k) {
-        double* c = col + (k & 1) * 32;
-        c[lane] = r[k];                           // lanes < k hold 0 there
-        __syncwarp();
+        const double* c = wsm + (k % 3) * 32;
         double d = c[k];
         if (!(d > 0.0)) {                         // also catches NaN; uniform across the warp
             if (!bad) bad = k + 1;
             d = 1.0;
         }
-        const double isd = rsqrt(d);
-        const double mine = r[k] * (isd * isd);
+        const double mine = r[k] * __drcp_rn(d);
+        if (k + 1 < POTF2_SUB) {
+            r[k + 1] = fma(-mine, c[k + 1], r[k + 1]);
+            wsm[((k + 1) % 3) * 32 + lane] = r[k + 1];             // lanes <= k hold 0 there
+            __syncwarp();
+        }
 #pragma unroll
-        for (int j = k + 1; j < POTF2_SUB; ++j) r[j] = fma(-mine, c[j], r[j]);   // rows < j only touch their (unused) upper part
+        for (int j = k + 2; j < POTF2_SUB; ++j) r[j] = fma(-mine, c[j], r[j]);   // rows < j only touch their (unused) upper part
+        const double isd = rsqrt(d);
         r[k] = (lane == k) ? d * isd : r[k] * isd;
         if (lane == 0) idiag[k] = isd;
     }
@@ -305,7 +320,13 @@ __device__ __forceinline__ int warp_potrf_inv32(double* Sb, int lds, double* Rb,
     for (int j = 0; j < POTF2_SUB; ++j)
         if (j <= lane) Sb[lane * lds + j] = r[j];
     __syncwarp();
-    // inverse: lane c owns column c of R = L^-1;  R[i][c] = ((i == c) - sum_{c <= p < i} L[i][p] R[p][c]) / L[i][i]
+    return bad;
+}
+
+// inverse of the 32 x 32 lower-triangular block Sb (one warp): lane c owns column c of R = L^-1,
+// R[i][c] = ((i == c) - sum_{c <= p < i} L[i][p] R[p][c]) / L[i][i];  Rb row stride POTF2_LDR
+__device__ __forceinline__ void warp_inv32(const double* Sb, int lds, double* Rb, const double* idiag) {
+    const int lane = threadIdx.x & 31;
     double x[POTF2_SUB];
 #pragma unroll
     for (int i = 0; i < POTF2_SUB; ++i) {
@@ -320,21 +341,53 @@ __device__ __forceinline__ int warp_potrf_inv32(double* Sb, int lds, double* Rb,
     }
 #pragma unroll
     for (int j = 0; j < POTF2_SUB; ++j) Rb[j * POTF2_LDR + lane] = x[j];          // row j, column lane
-    return bad;
 }
 
+// one row of the sub-panel: x = a . inv(L11)^T by forward substitution in registers (column-oriented: the dependency chain is
+// one multiply + one FMA per column); L11 entries are broadcast shared-memory loads.  Writes the row back and into the scratch
+// matrix that feeds the trailing update.
+__device__ __forceinline__ void row_trsv32(double* arow, const double* L11, int lds, const double* idiag, double* trow) {
+    double a[POTF2_SUB];
+#pragma unroll
+    for (int j = 0; j < POTF2_SUB; ++j) a[j] = arow[j];
+#pragma unroll
+    for (int j = 0; j < POTF2_SUB; ++j) {
+        const double x = a[j] * idiag[j];
+        a[j] = x;
+#pragma unroll
+        for (int q = j + 1; q < POTF2_SUB; ++q) a[q] = fma(-x, L11[q * lds + j], a[q]);
+    }
+#pragma unroll
+    for (int j = 0; j < POTF2_SUB; ++j) {
+        arow[j] = a[j];
+        trow[j] = a[j];
+    }
+}
+
+__device__ __forceinline__ void potf2_named_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Phases of one 32-column sub-step (c0 = 32 sb):  warp 0 factors the 32 x 32 diagonal piece;  then warp 0 inverts it WHILE
+// warps 1..15 solve the sub-panel row by row and apply the trailing update (they need L11, not its inverse).  The inverses of
+// the four pieces are only needed by the final assembly, so the serial inversion (~5k clocks each) leaves the critical path.
 __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __restrict__ A, long long lda, int jb,
                                                                   double* __restrict__ dinv, int* __restrict__ info,
-                                                                  int block_offset) {
+                                                                  int block_offset, long long* __restrict__ dbg) {
     extern __shared__ double sm[];
+    int dbg_i = 0;
+#define POTF2_STAMP() do { if (dbg && threadIdx.x == 0) dbg[dbg_i++] = clock64(); } while (0)
+    POTF2_STAMP();
     double* S = sm;                                         // 128 x 128 work matrix (lower), identity-padded beyond jb
     double* Rd = S + CHOL_NB * POTF2_LDS;                   // 4 inverted 32 x 32 diagonal pieces
     double* Tm = Rd + 4 * POTF2_SUB * POTF2_LDR;            // scratch
     __shared__ int bad_s;
-    __shared__ double wsm[96];
-    const int tid = threadIdx.x;
+    __shared__ double wsm[128];
+    const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) bad_s = 0;
-    for (int e = tid; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS) {
+#pragma unroll 8
+    for (int q = 0; q < CHOL_NB * CHOL_NB / POTF2_THREADS; ++q) {
+        const int e = tid + q * POTF2_THREADS;
         const int i = e >> 7, j = e & 127;
         double v = 0.0;
         if (i < jb && j <= i) v = A[(long long)i * lda + j];
@@ -342,48 +395,53 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
         S[i * POTF2_LDS + j] = v;
     }
     __syncthreads();
+    POTF2_STAMP();
     for (int sb = 0; sb < 4; ++sb) {
         const int c0 = sb * POTF2_SUB, c1 = c0 + POTF2_SUB, rem = CHOL_NB - c1;
-        if (tid < 32) {
-            const int bad = warp_potrf_inv32(S + c0 * POTF2_LDS + c0, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, wsm);
+        double* S11 = S + c0 * POTF2_LDS + c0;
+        if (warp == 0) {
+            const int bad = warp_potrf32(S11, POTF2_LDS, wsm);
             if (bad && tid == 0 && !bad_s) bad_s = c0 + bad;
         }
         __syncthreads();
+        POTF2_STAMP();
         if (bad_s) break;                                   // uniform
-        if (rem > 0) {
-            // sub-panel: Tm[rem x 32] = A21 . inv(L11)^T ; copy back ; trailing: S22 -= L21 L21^T (lower)
-            smem_gemm_mma<false>(Tm, POTF2_LDT, S + c1 * POTF2_LDS + c0, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, POTF2_LDR, rem,
-                             POTF2_SUB, POTF2_SUB, 1.0, false, false);
-            __syncthreads();
-            for (int e = tid; e < rem * POTF2_SUB; e += POTF2_THREADS) {
-                const int i = e >> 5, j = e & 31;
-                S[(c1 + i) * POTF2_LDS + c0 + j] = Tm[i * POTF2_LDT + j];
+        if (warp == 0) {
+            warp_inv32(S11, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, wsm + 96);
+        } else if (rem > 0) {
+            const int i = tid - 32;
+            if (i < rem) row_trsv32(S + (c1 + i) * POTF2_LDS + c0, S11, POTF2_LDS, wsm + 96, Tm + i * POTF2_LDT);
+            potf2_named_barrier(1, POTF2_THREADS - 32);
+            // trailing: S22 -= L21 L21^T (lower), warps 1..15
+            smem_gemm_mma<false>(S + c1 * POTF2_LDS + c1, POTF2_LDS, Tm, POTF2_LDT, Tm, POTF2_LDT, rem, rem, POTF2_SUB, -1.0, true, true,
+                                 1, POTF2_THREADS / 32 - 1);
+        } else {
+            // last sub-step: the factor is complete -- write it back while warp 0 inverts the last piece
+            for (int e = tid - 32; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS - 32) {
+                const int i = e >> 7, j = e & 127;
+                if (i < jb && j <= i) A[(long long)i * lda + j] = S[i * POTF2_LDS + j];
             }
-            smem_gemm_mma<false>(S + c1 * POTF2_LDS + c1, POTF2_LDS, Tm, POTF2_LDT, Tm, POTF2_LDT, rem, rem, POTF2_SUB, -1.0, true, true);
-            __syncthreads();
         }
+        __syncthreads();
+        POTF2_STAMP();
     }
     if (bad_s) {
         if (tid == 0) atomicCAS(info, 0, block_offset + bad_s);
         return;
     }
-    for (int e = tid; e < jb * jb; e += POTF2_THREADS) {
-        const int i = e / jb, j = e % jb;
-        if (j <= i) A[(long long)i * lda + j] = S[i * POTF2_LDS + j];
-    }
     // ---- inverse assembly, in place in S (strictly-lower blocks), diagonal pieces stay in Rd
     // level 1: for the two 64 x 64 diagonal blocks, C <- -inv(A2) C inv(A1) with 32 x 32 pieces
-    __syncthreads();
-    for (int h = 0; h < 2; ++h) {          // Tm[h] = C . inv(A1)   (inv(A1) row-major [k][j])
+    POTF2_STAMP();
+    for (int h = 0; h < 2; ++h) {          // Tm[h] = C . inv(A1)   (inv(A1) row-major [k][j], zero for k < j); warps 8h .. 8h+7
         const int o = h * 64;
-        smem_gemm_mma<true>(Tm + h * 32 * POTF2_LDT, POTF2_LDT, S + (o + 32) * POTF2_LDS + o, POTF2_LDS,
-                        Rd + (2 * h) * POTF2_SUB * POTF2_LDR, POTF2_LDR, 32, 32, 32, 1.0, false, false);
+        smem_gemm_mma<true, KR_GE_J>(Tm + h * 32 * POTF2_LDT, POTF2_LDT, S + (o + 32) * POTF2_LDS + o, POTF2_LDS,
+                                     Rd + (2 * h) * POTF2_SUB * POTF2_LDR, POTF2_LDR, 32, 32, 32, 1.0, false, false, 8 * h, 8);
     }
     __syncthreads();
-    for (int h = 0; h < 2; ++h) {          // C = -inv(A2) . Tm[h]
+    for (int h = 0; h < 2; ++h) {          // C = -inv(A2) . Tm[h]   (inv(A2)[i][k] zero for k > i)
         const int o = h * 64;
-        smem_gemm_mma<true>(S + (o + 32) * POTF2_LDS + o, POTF2_LDS, Rd + (2 * h + 1) * POTF2_SUB * POTF2_LDR, POTF2_LDR,
-                        Tm + h * 32 * POTF2_LDT, POTF2_LDT, 32, 32, 32, -1.0, false, false);
+        smem_gemm_mma<true, KR_LE_I>(S + (o + 32) * POTF2_LDS + o, POTF2_LDS, Rd + (2 * h + 1) * POTF2_SUB * POTF2_LDR, POTF2_LDR,
+                                     Tm + h * 32 * POTF2_LDT, POTF2_LDT, 32, 32, 32, -1.0, false, false, 8 * h, 8);
     }
     __syncthreads();
     // the diagonal 32 x 32 pieces of S now get their inverses so that the 64 x 64 diagonal blocks of S are complete inverses
@@ -393,17 +451,26 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     }
     __syncthreads();
     // level 2: C (rows 64.., cols 0..63) <- -inv(B) C inv(A), A = S[0:64,0:64], B = S[64:128,64:128] (both lower triangular)
-    smem_gemm_mma<true>(Tm, POTF2_LDT, S + 64 * POTF2_LDS, POTF2_LDS, S, POTF2_LDS, 64, 64, 64, 1.0, false, false);
+    POTF2_STAMP();
+    smem_gemm_mma<true, KR_GE_J>(Tm, POTF2_LDT, S + 64 * POTF2_LDS, POTF2_LDS, S, POTF2_LDS, 64, 64, 64, 1.0, false, false);
     __syncthreads();
-    smem_gemm_mma<true>(S + 64 * POTF2_LDS, POTF2_LDS, S + 64 * POTF2_LDS + 64, POTF2_LDS, Tm, POTF2_LDT, 64, 64, 64, -1.0, false, false);
+    smem_gemm_mma<true, KR_LE_I>(S + 64 * POTF2_LDS, POTF2_LDS, S + 64 * POTF2_LDS + 64, POTF2_LDS, Tm, POTF2_LDT, 64, 64, 64, -1.0, false,
+                                 false);
     __syncthreads();
-    for (int e = tid; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS) {
+    POTF2_STAMP();
+#pragma unroll 8
+    for (int q = 0; q < CHOL_NB * CHOL_NB / POTF2_THREADS; ++q) {
+        const int e = tid + q * POTF2_THREADS;
         const int i = e >> 7, j = e & 127;
         dinv[e] = (i < jb && j <= i) ? S[i * POTF2_LDS + j] : 0.0;
     }
+    POTF2_STAMP();
+#undef POTF2_STAMP
 }
 
 long long potrf_dinv_doubles(int n) { return (long long)ceil_div(n, CHOL_NB) * CHOL_NB * CHOL_NB; }
+
+static long long* g_potf2_dbg = nullptr;     // device buffer for the phase clocks of one diagonal-block kernel (timeline mode)
 
 struct CholStreams {
     cudaStream_t side = nullptr, crit = nullptr;
@@ -452,12 +519,30 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
     }
     PPBO_CUDA_CHECK(cudaMemsetAsync(info_d, 0, sizeof(int), st));
     bool side_busy = false;
+    // tuning key 5 = 1: record a timeline (start of every diagonal block, after panel, after look-ahead; start/end of the bulk
+    // trailing updates) and print it to stderr after a device synchronise -- diagnostics only
+    const bool tl = g_tuning[5] == 1 && nblk <= 64;
+    static cudaEvent_t ev_d[64], ev_p[64], ev_l[64], ev_r0[64], ev_r1[64], ev_end;
+    static bool ev_init = false;
+    if (tl && !g_potf2_dbg) cudaMalloc(&g_potf2_dbg, 64 * sizeof(long long));
+    if (tl && !ev_init) {
+        for (int i = 0; i < 64; ++i) {
+            cudaEventCreate(&ev_d[i]); cudaEventCreate(&ev_p[i]); cudaEventCreate(&ev_l[i]);
+            cudaEventCreate(&ev_r0[i]); cudaEventCreate(&ev_r1[i]);
+        }
+        cudaEventCreate(&ev_end);
+        ev_init = true;
+    }
+    bool has_l[64] = {false}, has_r[64] = {false};
     for (int b = 0; b < nblk; ++b) {
         const int j0 = b * CHOL_NB, jb = min(CHOL_NB, n - j0), j1 = j0 + jb, rem = n - j1;
         double* Ajj = A + (long long)j0 * lda + j0;
         double* dinv_b = dinv + (long long)b * CHOL_NB * CHOL_NB;
-        PPBO_CL potf2_inv_kernel<<<1, POTF2_THREADS, potf2_smem, st>>>(Ajj, lda, jb, dinv_b, info_d, j0);
+        if (tl) cudaEventRecord(ev_d[b], st);
+        PPBO_CL potf2_inv_kernel<<<1, POTF2_THREADS, potf2_smem, st>>>(Ajj, lda, jb, dinv_b, info_d, j0,
+                                                                         (tl && b == 20) ? g_potf2_dbg : nullptr);
         PPBO_LAUNCH_CHECK();
+        if (tl) cudaEventRecord(ev_p[b], st);
         if (rem <= 0) break;
         // panel: L21 = A21 . inv(L11)^T   (in place: each CTA owns whole rows, K == jb <= BN)
         double* A21 = A + (long long)j1 * lda + j0;
@@ -479,8 +564,10 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
                 rc = launch_gemm_nt(g, ep, 1, st);
                 if (rc) return rc;
             }
+            if (tl) { cudaEventRecord(ev_l[b], st); has_l[b] = true; }
             // (b) the rest of the trailing matrix on the side stream (lower tiles only)
             PPBO_CUDA_CHECK(cudaStreamWaitEvent(g_chol.side, g_chol.panel_done[b & 1], 0));
+            if (tl) { cudaEventRecord(ev_r0[b], g_chol.side); has_r[b] = true; }
             {
                 const int r2 = rem - nb1;
                 const double* P2 = A21 + (long long)nb1 * lda;
@@ -490,6 +577,7 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
                 if (rc) return rc;
             }
             PPBO_CUDA_CHECK(cudaEventRecord(g_chol.rest_done[b & 1], g_chol.side));
+            if (tl) cudaEventRecord(ev_r1[b], g_chol.side);
             side_busy = true;
         } else {
             if (side_busy) {
@@ -503,6 +591,29 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
         }
     }
     if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[(nblk - 2) & 1], 0));
+    if (tl) {
+        cudaEventRecord(ev_end, st);
+        cudaDeviceSynchronize();
+        float t_end = 0;
+        cudaEventElapsedTime(&t_end, ev_d[0], ev_end);
+        if (nblk > 20) {
+            long long h[16];
+            cudaMemcpy(h, g_potf2_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[potf2 phases, block 20, SM clocks] load %lld | ", h[1] - h[0]);
+            for (int sb = 0; sb < 4; ++sb) fprintf(stderr, "sub%d: warp potrf %lld, inverse || solve+trailing %lld | ", sb, h[2 + 2 * sb] - h[1 + 2 * sb], h[3 + 2 * sb] - h[2 + 2 * sb]);
+            fprintf(stderr, "inverse level 1 %lld | level 2 %lld | store dinv %lld | total %lld\n", h[11] - h[10],
+                    h[12] - h[11], h[13] - h[12], h[13] - h[0]);
+        }
+        fprintf(stderr, "[potrf timeline n=%d] total %.1f us; per step: start | potf2 | panel+lookahead-issue | rest start..end (us)\n", n, t_end * 1e3);
+        for (int b = 0; b < nblk; ++b) {
+            float t0 = 0, t1 = 0, t2 = 0, r0 = 0, r1 = 0;
+            cudaEventElapsedTime(&t0, ev_d[0], ev_d[b]);
+            cudaEventElapsedTime(&t1, ev_d[b], ev_p[b]);
+            if (has_l[b]) cudaEventElapsedTime(&t2, ev_p[b], ev_l[b]);
+            if (has_r[b]) { cudaEventElapsedTime(&r0, ev_d[0], ev_r0[b]); cudaEventElapsedTime(&r1, ev_d[0], ev_r1[b]); }
+            fprintf(stderr, "  b=%2d  %7.1f | %5.1f | %5.1f | %7.1f .. %7.1f (%.1f)\n", b, t0 * 1e3, t1 * 1e3, t2 * 1e3, r0 * 1e3, r1 * 1e3, (r1 - r0) * 1e3);
+        }
+    }
     if (st != caller) {
         PPBO_CUDA_CHECK(cudaEventRecord(g_chol.join, st));
         PPBO_CUDA_CHECK(cudaStreamWaitEvent(caller, g_chol.join, 0));

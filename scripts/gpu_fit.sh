@@ -1,4 +1,3 @@
 set -x
-python -m pytest tests/test_gpu_ops.py tests/test_src_gpu.py -m gpu -q -x 2>&1 | tail -4
-python scripts/ubench_ops.py --no-rowmax 2>&1 | grep -v "  cfg\|rowmax\|gemm_nt\|trsm"
-timeout 400 python scripts/fit_overlap_probe.py 2>&1 | head -3
+python -m pytest tests/test_gpu_ops.py -m gpu -q -x 2>&1 | tail -3
+python scripts/ubench_ops.py --no-rowmax --timeline 2>&1 | grep "potf2 phases\|potrf n=\|laplace_fit max_iter=100\|rff_fit max_iter=100\|total"

@@ -34,6 +34,11 @@ def main():
             _lib.load().ppbo_set_tuning(3, 0)
             print("potrf n=%d, critical path on the caller's stream (no priorities): %.3f ms" % (n, t1))
         t = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
+        if "--timeline" in sys.argv:
+            W.copy_(A)
+            _lib.load().ppbo_set_tuning(5, 1)
+            ops.potrf_lower(W)
+            _lib.load().ppbo_set_tuning(5, 0)
         W.copy_(A)
         info, ws = ops.potrf_lower(W)
         L = torch.tril(W)
