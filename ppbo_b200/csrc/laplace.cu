@@ -170,6 +170,73 @@ __global__ void axpy2_kernel(double* __restrict__ alpha, const double* __restric
     }
 }
 
+// Device-side acceptance test of one chord step, so that a batch of chord steps runs without a host round trip (a host decision
+// per step left the launch queue empty after every synchronise: ~0.5 ms per step against ~0.3 ms of kernel time).
+//   state[0] T at the current iterate   state[1] relative size of the last step   state[2] the one before   state[3] last |step|
+//   state[4] 0 = keep going, 1 = converged, 2 = step taken but contraction too slow (refactor), 3 = step rejected (refactor)
+//   state[5] chord steps taken in this batch      state[6] tolerance            hist[2i], hist[2i+1] = (rel, T) of step i
+// A chord step is only ever taken at full length: T(alpha + dalpha) must not fall below T (same rule as the host line search
+// with c == 0).  When state[4] != 0 the kernel does nothing; the other kernels of a queued step only write scratch vectors.
+__global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__ alpha, const double* __restrict__ dalpha,
+                                                            double* __restrict__ f, const double* __restrict__ df, int N,
+                                                            const double* __restrict__ part, int Q, int m,
+                                                            double* __restrict__ state, double* __restrict__ hist) {
+    __shared__ double red[33];
+    __shared__ double mx[2][32];
+    __shared__ int accept_s;
+    if (state[4] != 0.0) return;                    // uniform: state[4] is only written after the barriers below
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mdf = 0, mf = 0, lik = 0;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const double a = alpha[i], da = dalpha[i], fi = f[i], dfi = df[i];
+        s0 = fma(a, fi, s0);
+        s1 = fma(a, dfi, s1);
+        s2 = fma(da, fi, s2);
+        s3 = fma(da, dfi, s3);
+        mdf = fmax(mdf, fabs(dfi));
+        mf = fmax(mf, fabs(fi));
+    }
+    for (int q = threadIdx.x; q < Q; q += 1024) lik += part[q];
+    s0 = block_sum(s0, red);
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    s3 = block_sum(s3, red);
+    lik = block_sum(lik, red);
+    for (int o = 16; o > 0; o >>= 1) {
+        mdf = fmax(mdf, __shfl_xor_sync(0xffffffffu, mdf, o));
+        mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+    }
+    if ((threadIdx.x & 31) == 0) { mx[0][threadIdx.x >> 5] = mdf; mx[1][threadIdx.x >> 5] = mf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { mdf = fmax(mdf, mx[0][w]); mf = fmax(mf, mx[1][w]); }
+        const double T_cur = state[0];
+        const double T1 = -0.5 * (s0 + (s1 + s2) + s3) - lik / m;
+        const int accept = T1 >= T_cur - 1e-13 * fabs(T_cur);
+        accept_s = accept;
+        if (!accept) {
+            state[4] = 3.0;
+        } else {
+            const double rel = mdf / fmax(mf, 1e-300), prev = state[1];
+            const int n = (int)state[5];
+            state[0] = T1;
+            state[2] = prev;
+            state[1] = rel;
+            state[3] = mdf;
+            state[5] = n + 1;
+            hist[2 * n] = rel;
+            hist[2 * n + 1] = T1;
+            if (rel <= state[6]) state[4] = 1.0;
+            else if (!(rel <= 0.5 * prev)) state[4] = 2.0;
+        }
+    }
+    __syncthreads();
+    if (!accept_s) return;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        alpha[i] += dalpha[i];
+        f[i] += df[i];
+    }
+}
+
 // dense Lambda (public attr GPModel.Lambda_MAP): one thread per row of the output
 __global__ void lambda_dense_kernel(const double* __restrict__ arrow, int Q, int m, double* __restrict__ out, long long ld) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,12 +272,15 @@ int launch_sum(const double* x, int n, double* out, cudaStream_t st) {
     return PPBO_OK;
 }
 
+constexpr int CHORD_STATE = 8, CHORD_BATCH_MAX = 16;
+
 struct FitWorkspace {
-    double *bvec, *sa, *ap, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp, *binv;
+    double *bvec, *sa, *ap, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp, *binv, *state, *hist;
     int* info;
     static long long doubles(int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
-        return 4 * N + 3 * M + (M + CHOL_NB) + (long long)NSTEP * Q + 32 + 8 + 64 + blockinv_doubles((int)M);
+        return 4 * N + 3 * M + (M + CHOL_NB) + (long long)NSTEP * Q + 32 + 8 + 64 + CHORD_STATE + 2 * CHORD_BATCH_MAX +
+               blockinv_doubles((int)M);
     }
     void carve(double* base, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
@@ -226,6 +296,8 @@ struct FitWorkspace {
         set_part = p; p += (long long)NSTEP * Q;
         scal = p; p += 32;
         info = reinterpret_cast<int*>(p); p += 8;
+        state = p; p += CHORD_STATE;
+        hist = p; p += 2 * CHORD_BATCH_MAX;
         binv = p;
     }
 };
@@ -282,7 +354,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     const int set_blocks = ceil_div(Q, 8);
     double scal_h[32];
     int it = 0, info = 0, n_factor = 0, n_chord = 0;
-    double last_step = 0.0, last_rel = INFINITY, T_cur = NAN;
+    double last_step = 0.0, last_rel = INFINITY, T_cur = NAN, prev_rel_h = INFINITY;
     bool alpha_known = !have_start;          // alpha = Sigma^-1 f is known (== 0) only for the zero start
     int n_halvings_total = 0;
     // Newton steps refactor I + a+^1/2 G a+^1/2 at the current iterate; once the relative step is below CHORD_REL the factor
@@ -298,31 +370,70 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     // chord steps reuse one factor many times: its diagonal blocks are inverted at the first chord step (linalg.cu, block-inverse
     // solves), which makes every later solve with that factor ~3x cheaper than the 40-link chained solve
     bool binv_valid = false;
-    for (it = 0; it < max_iter; ++it) {
-        if (refactor) {
-            PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, ws.sa, ws.bvec, nullptr, ws.ap);
-            identity_factor = (it == 0 && !have_start);
-            if (identity_factor) {
-                PPBO_CUDA_CHECK(cudaMemsetAsync(ws.info, 0, sizeof(int), st));
-            } else {
-                if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
-                if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
-                ++n_factor;
-                binv_valid = false;
-            }
-        } else {
+    bool first_chord_batch = true;
+    while (it < max_iter) {
+        if (!refactor) {
+            // ---- a batch of chord steps: the factor is kept, only the right-hand side is refreshed; acceptance, the convergence
+            // test and the contraction test run on the device (chord_decide_kernel), one host synchronise per batch.  The batch
+            // length is the number of steps the observed contraction rate predicts (the first batch is short: it measures the rate).
             if (!binv_valid) {
                 if ((rc = blockinv_build(Lfac, M, M, Mdinv, ws.binv, st))) return rc;
                 binv_valid = true;
             }
-            PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr);
-            ++n_chord;
+            double rho = (std::isfinite(prev_rel_h) && last_rel < prev_rel_h) ? last_rel / prev_rel_h : 0.2;
+            rho = std::fmin(std::fmax(rho, 0.02), 0.5);
+            int kb = (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
+            if (first_chord_batch) kb = std::min(kb, 3);
+            kb = std::max(1, std::min(kb, std::min(CHORD_BATCH_MAX, max_iter - it)));
+            first_chord_batch = false;
+            double state_h[CHORD_STATE] = {T_cur, last_rel, prev_rel_h, last_step, 0.0, 0.0, tol, 0.0};
+            double hist_h[2 * CHORD_BATCH_MAX];
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.state, state_h, sizeof(state_h), cudaMemcpyHostToDevice, st));
+            for (int i = 0; i < kb; ++i) {
+                PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr);
+                if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
+                PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
+                if ((rc = potrs_vec_blockinv(Lfac, M, M, ws.binv, ws.t, st))) return rc;
+                PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);
+                if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st))) return rc;
+                PPBO_CL linesearch_lik_kernel<<<dim3(set_blocks, 1), 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.set_part);
+                PPBO_CL chord_decide_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, m, ws.state, ws.hist);
+            }
+            PPBO_LAUNCH_CHECK();
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(state_h, ws.state, sizeof(state_h), cudaMemcpyDeviceToHost, st));
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(hist_h, ws.hist, sizeof(double) * 2 * kb, cudaMemcpyDeviceToHost, st));
+            PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+            const int taken = (int)state_h[5], stop = (int)state_h[4];
+            if (trace)
+                for (int i = 0; i < taken; ++i)
+                    fprintf(stderr, "[ppbo_laplace_fit] it %d chord  step 1 rel %.3e T %.12g (batch of %d)\n", it + i, hist_h[2 * i], hist_h[2 * i + 1], kb);
+            it += taken;
+            n_chord += taken;
+            if (taken > 0) {
+                T_cur = state_h[0];
+                last_rel = state_h[1];
+                prev_rel_h = state_h[2];
+                last_step = state_h[3];
+            }
+            if (stop == 1) { converged = true; break; }
+            if (stop == 2 || stop == 3) refactor = true;      // contraction too slow / step rejected: pay for a new factor
+            continue;
+        }
+        // ---- Newton step: refactor I + a+^1/2 G a+^1/2 at the current iterate
+        PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, ws.sa, ws.bvec, nullptr, ws.ap);
+        identity_factor = (it == 0 && !have_start);
+        if (identity_factor) {
+            PPBO_CUDA_CHECK(cudaMemsetAsync(ws.info, 0, sizeof(int), st));
+        } else {
+            if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
+            if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
+            ++n_factor;
+            binv_valid = false;
         }
         if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
         PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
         if (!identity_factor) {
-            rc = binv_valid ? potrs_vec_blockinv(Lfac, M, M, ws.binv, ws.t, st) : potrs_vec(Lfac, M, M, Mdinv, ws.t, st);
-            if (rc) return rc;
+            if ((rc = potrs_vec(Lfac, M, M, Mdinv, ws.t, st))) return rc;
         }
         PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);
         if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st))) return rc;
@@ -336,6 +447,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
             PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
             if (info) { set_error("Newton system not positive definite at pivot %d (iteration %d)", info, it); return info; }
+            ++it;
             continue;
         }
         // line search over s = 1, 1/2, ..., 2^-7 on T(alpha + s dalpha) = -1/2 (alpha+s dalpha).(f+s df) - lik(f+s df)/m
@@ -360,25 +472,19 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             if (Ts >= T_cur - 1e-13 * std::fabs(T_cur)) { step = s; T_new = Ts; break; }
         }
         const double fscale = std::fmax(scal_h[5], 1e-300);
-        if (!refactor && c > 0) {            // a chord direction that needs damping is not worth taking: refactor here instead
-            refactor = true;
-            --it;
-            continue;
-        }
         if (c == NSTEP) { step = std::ldexp(1.0, -(NSTEP - 1)); T_new = NAN; }   // keep moving; T re-evaluated next round
         n_halvings_total += (c == NSTEP) ? NSTEP : c;
         PPBO_CL axpy2_kernel<<<ceil_div(N, 256), 256, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, step, N);
         PPBO_LAUNCH_CHECK();
         T_cur = T_new;
-        const double prev_rel = last_rel;
+        prev_rel_h = last_rel;
         last_step = step * scal_h[4];
         last_rel = last_step / fscale;
-        if (trace) fprintf(stderr, "[ppbo_laplace_fit] it %d %s step %.3g rel %.3e T %.12g\n", it, refactor ? "newton" : "chord ", step, last_rel, T_cur);
-        if (step == 1.0 && last_rel <= tol) { ++it; converged = true; break; }
-        // chord steps while they contract fast enough (at least 4x per step); otherwise pay for a new factor
-        if (refactor) refactor = !(step == 1.0 && last_rel <= CHORD_REL);
-        else refactor = !(last_rel <= 0.5 * prev_rel);
-        if (identity_factor) refactor = true;           // there is no stored factor to reuse after the identity step
+        if (trace) fprintf(stderr, "[ppbo_laplace_fit] it %d newton step %.3g rel %.3e T %.12g\n", it, step, last_rel, T_cur);
+        ++it;
+        if (step == 1.0 && last_rel <= tol) { converged = true; break; }
+        // chord steps once the Newton iteration is in its contraction region and a factor exists to reuse
+        refactor = !(step == 1.0 && last_rel <= CHORD_REL) || identity_factor;
     }
     (void)converged;
     // consistent products at the mode: arrow (signed), factor of I + a+^1/2 G a+^1/2

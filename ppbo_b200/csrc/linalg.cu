@@ -144,11 +144,23 @@ __global__ void __launch_bounds__(256) gemv_kernel(const double* __restrict__ A,
             const double2* a2 = reinterpret_cast<const double2*>(a);
             const double2* x2 = reinterpret_cast<const double2*>(x);
             const int n2 = N >> 1;
-            for (int j = lane; j < n2; j += 32) {
+            int j = lane;
+            double s2 = 0.0, s3 = 0.0;
+            for (; j + 96 < n2; j += 128) {               // 4 x 16-byte loads of the matrix row in flight per lane
+                const double2 a0 = __ldcs(a2 + j), a1 = __ldcs(a2 + j + 32), a2v = __ldcs(a2 + j + 64), a3 = __ldcs(a2 + j + 96);
+                const double2 x0 = x2[j], x1 = x2[j + 32], x2v = x2[j + 64], x3 = x2[j + 96];
+                s0 = fma(a0.x, x0.x, s0); s1 = fma(a0.y, x0.y, s1);
+                s2 = fma(a1.x, x1.x, s2); s3 = fma(a1.y, x1.y, s3);
+                s0 = fma(a2v.x, x2v.x, s0); s1 = fma(a2v.y, x2v.y, s1);
+                s2 = fma(a3.x, x3.x, s2); s3 = fma(a3.y, x3.y, s3);
+            }
+            for (; j < n2; j += 32) {
                 const double2 av = a2[j], xv = x2[j];
                 s0 = fma(av.x, xv.x, s0);
                 s1 = fma(av.y, xv.y, s1);
             }
+            s0 += s2;
+            s1 += s3;
             if ((N & 1) && lane == 0) s0 = fma(a[N - 1], x[N - 1], s0);
         } else {
             for (int j = lane; j < N; j += 32) s0 = fma(a[j], x[j], s0);
@@ -177,6 +189,7 @@ int gemv(const double* A, long long lda, int M, int N, const double* x, double* 
 // sub-panel L21 = A21 inv(L11)^T and the trailing update as small shared-memory GEMMs.  The 128 x 128 inverse is assembled from
 // the four 32 x 32 inverses by two levels of  inv([[A,0],[C,B]]) = [[A^-1,0],[-B^-1 C A^-1, B^-1]].
 // ~35 us per block against ~300 us for a column-by-column version with three block barriers per column.
+constexpr int PAIR_MIN_REM = 2048;                    // remainders above this defer / pair their trailing updates (K = 256)
 constexpr int POTF2_THREADS = 512;
 constexpr int POTF2_LDS = CHOL_NB + 1;                 // row stride of the 128 x 128 work matrix
 constexpr int POTF2_SUB = 32;
@@ -234,11 +247,11 @@ __device__ __forceinline__ void smem_gemm(double* C, int ldc, const double* A, i
 // skipping the structural zeros is worth it): KR_GE_J: B[k][j] = 0 for k < j;  KR_LE_I: A[i][k] = 0 for k > i.
 // Warps [warp0, warp0 + nwarps) take part.
 enum { KR_FULL = 0, KR_GE_J = 1, KR_LE_I = 2 };
+// smem_gemm_mma_w: the calling warp is participant `warp` of `nwarps` (warp < 0: not taking part).
 template <bool B_KMAJOR, int KR = KR_FULL>
-__device__ __forceinline__ void smem_gemm_mma(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n,
-                                              int K, double sign, bool acc, bool lower_only, int warp0 = 0,
-                                              int nwarps = 16) {
-    const int warp = (threadIdx.x >> 5) - warp0, lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
+__device__ __forceinline__ void smem_gemm_mma_w(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n,
+                                                int K, double sign, bool acc, bool lower_only, int warp, int nwarps) {
+    const int lane = threadIdx.x & 31, gq = lane >> 2, t4 = lane & 3;
     if (warp < 0 || warp >= nwarps) return;
     const int tm = m >> 4, tn = n >> 4;
     for (int t = warp; t < tm * tn; t += nwarps) {
@@ -279,48 +292,95 @@ __device__ __forceinline__ void smem_gemm_mma(double* C, int ldc, const double* 
     }
 }
 
+template <bool B_KMAJOR, int KR = KR_FULL>
+__device__ __forceinline__ void smem_gemm_mma(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int m, int n,
+                                              int K, double sign, bool acc, bool lower_only, int warp0 = 0,
+                                              int nwarps = 16) {
+    smem_gemm_mma_w<B_KMAJOR, KR>(C, ldc, A, lda, B, ldb, m, n, K, sign, acc, lower_only, (int)(threadIdx.x >> 5) - warp0, nwarps);
+}
+
+// Helper warps of the diagonal-block kernel: the 12 warps that do NOT share a scheduler / FP64 pipe with warp 0 (warp w runs on
+// sub-partition w & 3).  Work that runs concurrently with warp 0's pivot chain is confined to them: with all 15 other warps the
+// chain of the last piece slowed from 3.7k to 8.6k clocks.
+constexpr int POTF2_HELPERS = 12;
+__device__ __forceinline__ int potf2_helper_index() {
+    const int w = threadIdx.x >> 5;
+    return (w & 3) ? (w >> 2) * 3 + (w & 3) - 1 : -1;
+}
+
+// Branch-free FP64 reciprocal / reciprocal square root for the pivot chain: MUFU seed (>= 20 bits) + the Newton sequence CUDA's
+// own division / rsqrt use, WITHOUT their slow-path branches (denormal / huge operands cannot occur for a pivot that passes the
+// d > 0 test; a failed pivot is reported, its garbage is never used).  The library versions put a BRA / CALL into every column of
+// the unrolled factorisation, which splits it into basic blocks and keeps ptxas from overlapping the pivot chain of column k+1
+// with the rank-1 update of column k (measured: 380-680 clocks per column instead of the ~150 of the dependency chain).
+__device__ __forceinline__ double rcp_nr(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    e = fma(e, e, e);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
+__device__ __forceinline__ double rsqrt_nr(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d * y, y, 1.0);                       // 1 - d y^2
+    y = fma(y * e, fma(e, 0.375, 0.5), y);                // y (1 + e/2 + 3 e^2 / 8)
+    e = fma(-d * y, y, 1.0);
+    return fma(y * e, 0.5, y);
+}
+
 // warp-level Cholesky of a 32 x 32 block held in shared memory (row stride lds), in place.  Lane i owns row i in registers;
-// column k of the running Schur complement is exchanged through a double-buffered shared-memory line read back as broadcast
-// loads (one __syncwarp per column).  The multipliers use 1/d (on the dependency chain), the 1/sqrt(d) scaling of the finished
-// column is off it.  wsm: [0,96) exchange lines, [96,128) 1 / L[k][k].  Returns 0 or the 1-based index of the first non-positive
-// pivot (same value in every lane).
-__device__ __forceinline__ int warp_potrf32(double* Sb, int lds, double* wsm) {
+// column k of the running Schur complement is exchanged through a triple-buffered shared-memory line read back as broadcast
+// loads (one __syncwarp per column).  The rows stay UNSCALED during the elimination (r[i][k] = L[i][k] L[k][k]): the dependency
+// chain of a column is  LDS pivot -> reciprocal -> one FMA -> STS -> __syncwarp, everything else (rank-1 update of the other
+// columns, square roots, scaling) is off it; the 32 reciprocal square roots are taken afterwards, one per lane.
+// wsm: [0,96) exchange lines, [96,128) 1 / L[k][k], [128,160) pivots.  Returns 0 or the 1-based index of the first non-positive
+// (or NaN) pivot, same value in every lane.
+__device__ __forceinline__ int warp_potrf32(double* Sb, int lds, double* wsm, long long* tdbg = nullptr) {
     const int lane = threadIdx.x & 31;
-    double* idiag = wsm + 96;     // [32]  1 / L[k][k];  wsm[0,96): three exchange lines
+    if (tdbg && lane == 0) tdbg[0] = clock64();
+    double* idiag = wsm + 96;
+    double* piv = wsm + 128;
     double r[POTF2_SUB];
 #pragma unroll
     for (int j = 0; j < POTF2_SUB; ++j) r[j] = (j <= lane) ? Sb[lane * lds + j] : 0.0;
-    int bad = 0;
     wsm[lane] = r[0];
     __syncwarp();
-    // Software-pipelined: column k+1 is published (one FMA after the multiplier is known) BEFORE the remaining updates of column
-    // k are issued, so the shared-memory round trip of the exchange overlaps with them.  Three exchange lines: the line written in
-    // step k was last read in step k-2, with the __syncwarp of step k-1 in between.
+    if (tdbg && lane == 0) tdbg[1] = clock64();
 #pragma unroll
     for (int k = 0; k < POTF2_SUB; ++k) {
         const double* c = wsm + (k % 3) * 32;
-        double d = c[k];
-        if (!(d > 0.0)) {                         // also catches NaN; uniform across the warp
-            if (!bad) bad = k + 1;
-            d = 1.0;
-        }
-        const double mine = r[k] * __drcp_rn(d);
+        const double d = c[k];
+        const double inv = rcp_nr(d);
         if (k + 1 < POTF2_SUB) {
-            r[k + 1] = fma(-mine, c[k + 1], r[k + 1]);
-            wsm[((k + 1) % 3) * 32 + lane] = r[k + 1];             // lanes <= k hold 0 there
+            // publish column k+1 first: the line written in step k was last read in step k-2, with the __syncwarp of step k-1
+            // in between
+            const double t = r[k] * c[k + 1];                          // independent of the reciprocal
+            r[k + 1] = fma(-t, inv, r[k + 1]);
+            wsm[((k + 1) % 3) * 32 + lane] = r[k + 1];                 // lanes <= k hold 0 there
             __syncwarp();
         }
+        const double mine = r[k] * inv;
 #pragma unroll
         for (int j = k + 2; j < POTF2_SUB; ++j) r[j] = fma(-mine, c[j], r[j]);   // rows < j only touch their (unused) upper part
-        const double isd = rsqrt(d);
-        r[k] = (lane == k) ? d * isd : r[k] * isd;
-        if (lane == 0) idiag[k] = isd;
+        if (lane == 0) piv[k] = d;
     }
+    __syncwarp();
+    if (tdbg && lane == 0) tdbg[2] = clock64();
+    const double dk = piv[lane];
+    const bool ok = dk > 0.0;                                          // false for NaN
+    const unsigned badmask = __ballot_sync(0xffffffffu, !ok);
+    const double isd = rsqrt_nr(ok ? dk : 1.0);
+    idiag[lane] = isd;
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < POTF2_SUB; ++j)
-        if (j <= lane) Sb[lane * lds + j] = r[j];
+        if (j <= lane) Sb[lane * lds + j] = r[j] * idiag[j];           // diagonal: d / sqrt(d)
     __syncwarp();
-    return bad;
+    if (tdbg && lane == 0) tdbg[3] = clock64();
+    return badmask ? __ffs(badmask) : 0;
 }
 
 // inverse of the 32 x 32 lower-triangular block Sb (one warp): lane c owns column c of R = L^-1,
@@ -368,9 +428,56 @@ __device__ __forceinline__ void potf2_named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Phases of one 32-column sub-step (c0 = 32 sb):  warp 0 factors the 32 x 32 diagonal piece;  then warp 0 inverts it WHILE
-// warps 1..15 solve the sub-panel row by row and apply the trailing update (they need L11, not its inverse).  The inverses of
-// the four pieces are only needed by the final assembly, so the serial inversion (~5k clocks each) leaves the critical path.
+// Diagonal-block kernel.  Per 32-column sub-step sb (c0 = 32 sb):
+//   phase 1: warp 0 factors the 32 x 32 diagonal piece  ||  warps 1..15 finish block row sb-1 (see below)
+//   phase 2: warp 0 inverts the piece (R_sb)            ||  warps 1..15 solve the sub-panel row by row and apply the trailing update
+// Block row i of the factor (L_i0 .. L_ii) is final once its diagonal piece is factored, and R_i exists after phase 2 of sub-step i.
+// "Finishing" block row i (finish_block_row) is everything that used to follow the factorisation as a serial tail:
+//   write L's block row back to A;  X_i,0:i-1 = -R_i (L_i,0:i-1 X_0:i-1,0:i-1)  (block row i of X = inv(L), by forward substitution
+//   over the earlier block rows of X, which overwrite L in S);  X_ii = R_i;  store the block row of X to dinv.
+// Rows 0..2 are finished while warp 0 factors the next piece (the other 15 warps would be idle), so only row 3 remains after
+// the last piece: the old tail (two levels of block inversion + a 128 KB store: 22k clocks) shrinks to ~5k.
+// dinv must be zero above the diagonal and beyond jb on entry (potrf_lower clears it): only the lower triangle is stored.
+__device__ __forceinline__ void potf2_helper_barrier() { potf2_named_barrier(2, POTF2_HELPERS * 32); }
+
+// T = L_i,0:i-1 . X_0:i-1,0:i-1 -> Tm (row stride ldt); helper warps, no barrier inside
+__device__ __forceinline__ void potf2_row_product(const double* S, double* Tm, int ldt, int i) {
+    smem_gemm_mma_w<true, KR_GE_J>(Tm, ldt, S + (32 * i) * POTF2_LDS, POTF2_LDS, S, POTF2_LDS, 32, 32 * i, 32 * i, 1.0, false, false,
+                                   potf2_helper_index(), POTF2_HELPERS);
+}
+
+// lower triangle of rows [r0, r0 + 32) of S (columns 0 .. row) -> global dst (row stride ldd), rows < jb only; the calling
+// thread is participant t of nthr
+__device__ __forceinline__ void potf2_store_rows(const double* S, double* __restrict__ dst, long long ldd, int r0, int jb, int t,
+                                                 int nthr) {
+    const int ncol = r0 + 32;
+    for (int e = t; e < 32 * ncol; e += nthr) {
+        const int i = r0 + e / ncol, j = e % ncol;
+        if (i < jb && j <= i) dst[(long long)i * ldd + j] = S[i * POTF2_LDS + j];
+    }
+}
+
+// helper warps: finish block row i (0 <= i <= 2) while warp 0 factors piece i + 1.  Tm is free in phase 1.
+__device__ __forceinline__ void potf2_finish_block_row(double* S, const double* Rd, double* Tm, int i, double* __restrict__ A,
+                                                       long long lda, double* __restrict__ dinv, int jb) {
+    const int hw = potf2_helper_index();
+    if (hw < 0) return;
+    const int t0 = hw * 32 + (threadIdx.x & 31), nthr = POTF2_HELPERS * 32, r0 = 32 * i;
+    potf2_store_rows(S, A, lda, r0, jb, t0, nthr);                              // factor rows -> A
+    if (i > 0) potf2_row_product(S, Tm, POTF2_LDT, i);
+    potf2_helper_barrier();                                                      // L_i* no longer needed in S
+    const double* Ri = Rd + i * POTF2_SUB * POTF2_LDR;
+    if (i > 0)                                                                   // X_i,0:i-1 = -R_i T   (R_i[r][k] = 0 for k > r)
+        smem_gemm_mma_w<true, KR_LE_I>(S + r0 * POTF2_LDS, POTF2_LDS, Ri, POTF2_LDR, Tm, POTF2_LDT, 32, r0, 32, -1.0, false, false, hw,
+                                       POTF2_HELPERS);
+    for (int e = t0; e < POTF2_SUB * POTF2_SUB; e += nthr) {                     // X_ii = R_i (zeros above the diagonal)
+        const int r = e >> 5, c = e & 31;
+        S[(r0 + r) * POTF2_LDS + r0 + c] = Ri[r * POTF2_LDR + c];
+    }
+    potf2_helper_barrier();
+    potf2_store_rows(S, dinv, CHOL_NB, r0, jb, t0, nthr);                        // inverse rows -> dinv
+}
+
 __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __restrict__ A, long long lda, int jb,
                                                                   double* __restrict__ dinv, int* __restrict__ info,
                                                                   int block_offset, long long* __restrict__ dbg) {
@@ -382,7 +489,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     double* Rd = S + CHOL_NB * POTF2_LDS;                   // 4 inverted 32 x 32 diagonal pieces
     double* Tm = Rd + 4 * POTF2_SUB * POTF2_LDR;            // scratch
     __shared__ int bad_s;
-    __shared__ double wsm[128];
+    __shared__ double wsm[160];
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) bad_s = 0;
 #pragma unroll 8
@@ -396,12 +503,15 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     }
     __syncthreads();
     POTF2_STAMP();
+    constexpr int LDT3 = 97;                                // row stride of the 32 x 96 product of the last block row
     for (int sb = 0; sb < 4; ++sb) {
         const int c0 = sb * POTF2_SUB, c1 = c0 + POTF2_SUB, rem = CHOL_NB - c1;
         double* S11 = S + c0 * POTF2_LDS + c0;
         if (warp == 0) {
-            const int bad = warp_potrf32(S11, POTF2_LDS, wsm);
+            const int bad = warp_potrf32(S11, POTF2_LDS, wsm, dbg ? dbg + 16 + 4 * sb : nullptr);
             if (bad && tid == 0 && !bad_s) bad_s = c0 + bad;
+        } else if (sb > 0) {
+            potf2_finish_block_row(S, Rd, Tm, sb - 1, A, lda, dinv, jb);
         }
         __syncthreads();
         POTF2_STAMP();
@@ -416,11 +526,11 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
             smem_gemm_mma<false>(S + c1 * POTF2_LDS + c1, POTF2_LDS, Tm, POTF2_LDT, Tm, POTF2_LDT, rem, rem, POTF2_SUB, -1.0, true, true,
                                  1, POTF2_THREADS / 32 - 1);
         } else {
-            // last sub-step: the factor is complete -- write it back while warp 0 inverts the last piece
-            for (int e = tid - 32; e < CHOL_NB * CHOL_NB; e += POTF2_THREADS - 32) {
-                const int i = e >> 7, j = e & 127;
-                if (i < jb && j <= i) A[(long long)i * lda + j] = S[i * POTF2_LDS + j];
-            }
+            // last sub-step: the factor is complete.  While warp 0 inverts the last piece: write the last block row back and
+            // form T = L_3,0:2 X_0:2,0:2 (it does not need R_3)
+            const int hw = potf2_helper_index();
+            if (hw >= 0) potf2_store_rows(S, A, lda, c0, jb, hw * 32 + (tid & 31), POTF2_HELPERS * 32);
+            potf2_row_product(S, Tm, LDT3, 3);
         }
         __syncthreads();
         POTF2_STAMP();
@@ -429,40 +539,16 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
         if (tid == 0) atomicCAS(info, 0, block_offset + bad_s);
         return;
     }
-    // ---- inverse assembly, in place in S (strictly-lower blocks), diagonal pieces stay in Rd
-    // level 1: for the two 64 x 64 diagonal blocks, C <- -inv(A2) C inv(A1) with 32 x 32 pieces
     POTF2_STAMP();
-    for (int h = 0; h < 2; ++h) {          // Tm[h] = C . inv(A1)   (inv(A1) row-major [k][j], zero for k < j); warps 8h .. 8h+7
-        const int o = h * 64;
-        smem_gemm_mma<true, KR_GE_J>(Tm + h * 32 * POTF2_LDT, POTF2_LDT, S + (o + 32) * POTF2_LDS + o, POTF2_LDS,
-                                     Rd + (2 * h) * POTF2_SUB * POTF2_LDR, POTF2_LDR, 32, 32, 32, 1.0, false, false, 8 * h, 8);
-    }
-    __syncthreads();
-    for (int h = 0; h < 2; ++h) {          // C = -inv(A2) . Tm[h]   (inv(A2)[i][k] zero for k > i)
-        const int o = h * 64;
-        smem_gemm_mma<true, KR_LE_I>(S + (o + 32) * POTF2_LDS + o, POTF2_LDS, Rd + (2 * h + 1) * POTF2_SUB * POTF2_LDR, POTF2_LDR,
-                                     Tm + h * 32 * POTF2_LDT, POTF2_LDT, 32, 32, 32, -1.0, false, false, 8 * h, 8);
-    }
-    __syncthreads();
-    // the diagonal 32 x 32 pieces of S now get their inverses so that the 64 x 64 diagonal blocks of S are complete inverses
-    for (int e = tid; e < 4 * POTF2_SUB * POTF2_SUB; e += POTF2_THREADS) {
-        const int b = e >> 10, i = (e >> 5) & 31, j = e & 31;
-        S[(b * 32 + i) * POTF2_LDS + b * 32 + j] = Rd[b * POTF2_SUB * POTF2_LDR + i * POTF2_LDR + j];   // zeros above the diagonal
-    }
-    __syncthreads();
-    // level 2: C (rows 64.., cols 0..63) <- -inv(B) C inv(A), A = S[0:64,0:64], B = S[64:128,64:128] (both lower triangular)
-    POTF2_STAMP();
-    smem_gemm_mma<true, KR_GE_J>(Tm, POTF2_LDT, S + 64 * POTF2_LDS, POTF2_LDS, S, POTF2_LDS, 64, 64, 64, 1.0, false, false);
-    __syncthreads();
-    smem_gemm_mma<true, KR_LE_I>(S + 64 * POTF2_LDS, POTF2_LDS, S + 64 * POTF2_LDS + 64, POTF2_LDS, Tm, POTF2_LDT, 64, 64, 64, -1.0, false,
-                                 false);
+    // ---- tail: X_3,0:2 = -R_3 T (all 16 warps), then the last block row of the inverse goes to dinv (its diagonal piece from Rd)
+    const double* R3 = Rd + 3 * POTF2_SUB * POTF2_LDR;
+    smem_gemm_mma<true, KR_LE_I>(S + 96 * POTF2_LDS, POTF2_LDS, R3, POTF2_LDR, Tm, LDT3, 32, 96, 32, -1.0, false, false);
     __syncthreads();
     POTF2_STAMP();
-#pragma unroll 8
-    for (int q = 0; q < CHOL_NB * CHOL_NB / POTF2_THREADS; ++q) {
-        const int e = tid + q * POTF2_THREADS;
-        const int i = e >> 7, j = e & 127;
-        dinv[e] = (i < jb && j <= i) ? S[i * POTF2_LDS + j] : 0.0;
+    POTF2_STAMP();
+    for (int e = tid; e < 32 * CHOL_NB; e += POTF2_THREADS) {
+        const int r = e >> 7, j = e & 127, i = 96 + r;
+        if (i < jb && j <= i) dinv[i * CHOL_NB + j] = (j < 96) ? S[i * POTF2_LDS + j] : R3[r * POTF2_LDR + (j - 96)];
     }
     POTF2_STAMP();
 #undef POTF2_STAMP
@@ -518,7 +604,10 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
         PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.fork, 0));
     }
     PPBO_CUDA_CHECK(cudaMemsetAsync(info_d, 0, sizeof(int), st));
-    bool side_busy = false;
+    // the diagonal-block kernel only stores the lower triangles of the inverted blocks
+    PPBO_CUDA_CHECK(cudaMemsetAsync(dinv, 0, sizeof(double) * potrf_dinv_doubles(n), st));
+    bool side_busy = false, pair_open = false;
+    int last_rest = 0;
     // tuning key 5 = 1: record a timeline (start of every diagonal block, after panel, after look-ahead; start/end of the bulk
     // trailing updates) and print it to stderr after a device synchronise -- diagnostics only
     const bool tl = g_tuning[5] == 1 && nblk <= 64;
@@ -555,33 +644,51 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
         double* A22 = A + (long long)j1 * lda + j1;
         const int nb1 = min(CHOL_NB, rem);           // width of the next block column
         if (lookahead && rem > nb1) {
-            // (a) next block column on the main stream: A22[:, 0:nb1] -= L21 . L21[0:nb1]^T
-            if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[(b + 1) & 1], 0));
-            PPBO_CUDA_CHECK(cudaEventRecord(g_chol.panel_done[b & 1], st));
+            // While the trailing update is the bottleneck (large remainders) two block columns are applied together: a rank-128
+            // update moves 320 KB through L2 per 128 x 64 tile for 2.1 MFLOP and runs at ~55 % of the DMMA peak, the rank-256
+            // update of a pair moves 512 KB for 4.2 MFLOP.  Even step of a pair: only the next block column is brought up to
+            // date (look-ahead, K = 128) and the bulk is deferred; odd step: look-ahead and bulk with K = 256 over both panels,
+            // which are adjacent columns of A.  Small remainders (bulk hidden behind the critical path) keep K = 128.
+            // Measured at n = 5000: 4.01 ms paired against 3.94 ms unpaired -- the look-ahead of the even step has to wait for the
+            // paired bulk update (it writes the same block column), which costs more than the better GEMM rate returns; kept
+            // behind tuning key 6 = 1.
+            const bool pair_second = pair_open;
+            const bool pair_first = !pair_open && g_tuning[6] == 1 && jb == CHOL_NB && rem > PAIR_MIN_REM;   // opt-in, see below
+            const int kcols = pair_second ? 2 * CHOL_NB : jb;                    // K of this step's updates
+            const double* P = pair_second ? A21 - CHOL_NB : A21;                 // [rem x kcols] panel(s), row stride lda
+            // (a) next block column on the main stream: A22[:, 0:nb1] -= P . P[0:nb1]^T
+            if (!pair_first) PPBO_CUDA_CHECK(cudaEventRecord(g_chol.panel_done[b & 1], st));     // panels final: (b) may start
+            if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[last_rest], 0));
             {
-                GemmOperands g{A21, lda, 0, A21, lda, 0, rem, nb1, jb};
+                GemmOperands g{P, lda, 0, P, lda, 0, rem, nb1, kcols};
                 StoreEpilogue ep{A22, lda, 0, -1.0, 1.0, 0, 0};
                 rc = launch_gemm_nt(g, ep, 1, st);
                 if (rc) return rc;
             }
             if (tl) { cudaEventRecord(ev_l[b], st); has_l[b] = true; }
-            // (b) the rest of the trailing matrix on the side stream (lower tiles only)
-            PPBO_CUDA_CHECK(cudaStreamWaitEvent(g_chol.side, g_chol.panel_done[b & 1], 0));
-            if (tl) { cudaEventRecord(ev_r0[b], g_chol.side); has_r[b] = true; }
-            {
-                const int r2 = rem - nb1;
-                const double* P2 = A21 + (long long)nb1 * lda;
-                GemmOperands g{P2, lda, 0, P2, lda, 0, r2, r2, jb};
-                StoreEpilogue ep{A22 + (long long)nb1 * lda + nb1, lda, 0, -1.0, 1.0, 1, 0};
-                rc = launch_gemm_nt(g, ep, 1, g_chol.side);
-                if (rc) return rc;
+            if (pair_first) {
+                pair_open = true;                    // bulk deferred to the next step
+            } else {
+                pair_open = false;
+                // (b) the rest of the trailing matrix on the side stream (lower tiles only); it needs the panel(s), not (a)
+                PPBO_CUDA_CHECK(cudaStreamWaitEvent(g_chol.side, g_chol.panel_done[b & 1], 0));
+                if (tl) { cudaEventRecord(ev_r0[b], g_chol.side); has_r[b] = true; }
+                {
+                    const int r2 = rem - nb1;
+                    const double* P2 = P + (long long)nb1 * lda;
+                    GemmOperands g{P2, lda, 0, P2, lda, 0, r2, r2, kcols};
+                    StoreEpilogue ep{A22 + (long long)nb1 * lda + nb1, lda, 0, -1.0, 1.0, 1, 0};
+                    rc = launch_gemm_nt(g, ep, 1, g_chol.side);
+                    if (rc) return rc;
+                }
+                last_rest ^= 1;
+                PPBO_CUDA_CHECK(cudaEventRecord(g_chol.rest_done[last_rest], g_chol.side));
+                if (tl) cudaEventRecord(ev_r1[b], g_chol.side);
+                side_busy = true;
             }
-            PPBO_CUDA_CHECK(cudaEventRecord(g_chol.rest_done[b & 1], g_chol.side));
-            if (tl) cudaEventRecord(ev_r1[b], g_chol.side);
-            side_busy = true;
         } else {
             if (side_busy) {
-                PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[(b + 1) & 1], 0));
+                PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[last_rest], 0));
                 side_busy = false;
             }
             GemmOperands g{A21, lda, 0, A21, lda, 0, rem, rem, jb};
@@ -590,19 +697,22 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
             if (rc) return rc;
         }
     }
-    if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[(nblk - 2) & 1], 0));
+    if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[last_rest], 0));
     if (tl) {
         cudaEventRecord(ev_end, st);
         cudaDeviceSynchronize();
         float t_end = 0;
         cudaEventElapsedTime(&t_end, ev_d[0], ev_end);
         if (nblk > 20) {
-            long long h[16];
+            long long h[32];
             cudaMemcpy(h, g_potf2_dbg, sizeof(h), cudaMemcpyDeviceToHost);
             fprintf(stderr, "[potf2 phases, block 20, SM clocks] load %lld | ", h[1] - h[0]);
             for (int sb = 0; sb < 4; ++sb) fprintf(stderr, "sub%d: warp potrf %lld, inverse || solve+trailing %lld | ", sb, h[2 + 2 * sb] - h[1 + 2 * sb], h[3 + 2 * sb] - h[2 + 2 * sb]);
-            fprintf(stderr, "inverse level 1 %lld | level 2 %lld | store dinv %lld | total %lld\n", h[11] - h[10],
-                    h[12] - h[11], h[13] - h[12], h[13] - h[0]);
+            fprintf(stderr, "tail: last block row of the inverse %lld | store %lld | total %lld\n", h[11] - h[10], h[13] - h[12], h[13] - h[0]);
+            for (int sb = 0; sb < 4; ++sb)
+                fprintf(stderr, "[warp potrf32 sub%d] enter +%lld | load %lld | columns %lld | scale+store %lld | to barrier exit %lld\n", sb,
+                        h[16 + 4 * sb] - h[1 + 2 * sb], h[17 + 4 * sb] - h[16 + 4 * sb], h[18 + 4 * sb] - h[17 + 4 * sb],
+                        h[19 + 4 * sb] - h[18 + 4 * sb], h[2 + 2 * sb] - h[19 + 4 * sb]);
         }
         fprintf(stderr, "[potrf timeline n=%d] total %.1f us; per step: start | potf2 | panel+lookahead-issue | rest start..end (us)\n", n, t_end * 1e3);
         for (int b = 0; b < nblk; ++b) {
@@ -917,7 +1027,8 @@ int blockinv_build(const double* L, long long ldl, int n, const double* dinv, do
     return PPBO_OK;
 }
 
-// out[r] = sum_c Mat[r][c] v[c] over the triangle (lower: c <= r, upper: r <= c < rows) of one BI x BI block; warp per row
+// out[r] = sum_c Mat[r][c] v[c] over the triangle (lower: c <= r, upper: r <= c < rows) of one BI x BI block; warp per row,
+// four rows of loads in flight per lane (the kernel is a latency-bound 4 MB read: 128 CTAs, one pass)
 __global__ void __launch_bounds__(256) blocktri_gemv_kernel(const double* __restrict__ Mat, const double* __restrict__ v,
                                                             double* __restrict__ out, int rows, int upper) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -925,15 +1036,17 @@ __global__ void __launch_bounds__(256) blocktri_gemv_kernel(const double* __rest
     if (r >= rows) return;
     const double* m = Mat + (long long)r * BI;
     const int c_lo = upper ? (r & ~31) : 0, c_hi = upper ? rows : r + 1;
-    double s0 = 0.0, s1 = 0.0;
-    int c = c_lo + lane;
-    for (; c + 32 < c_hi; c += 64) {
-        const double a0 = m[c], a1 = m[c + 32];          // the other triangle holds exact zeros
-        s0 = fma(a0, v[c], s0);
-        s1 = fma(a1, v[c + 32], s1);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int c = c_lo + lane; c < c_hi; c += 128) {                  // the other triangle holds exact zeros
+        const bool p1 = c + 32 < c_hi, p2 = c + 64 < c_hi, p3 = c + 96 < c_hi;
+        const double a0 = m[c], a1 = p1 ? m[c + 32] : 0.0, a2 = p2 ? m[c + 64] : 0.0, a3 = p3 ? m[c + 96] : 0.0;
+        const double v0 = v[c], v1 = p1 ? v[c + 32] : 0.0, v2 = p2 ? v[c + 64] : 0.0, v3 = p3 ? v[c + 96] : 0.0;
+        s0 = fma(a0, v0, s0);
+        s1 = fma(a1, v1, s1);
+        s2 = fma(a2, v2, s2);
+        s3 = fma(a3, v3, s3);
     }
-    if (c < c_hi) s0 = fma(m[c], v[c], s0);
-    double a = s0 + s1;
+    double a = (s0 + s1) + (s2 + s3);
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) out[r] = a;
 }
@@ -957,27 +1070,39 @@ __global__ void __launch_bounds__(256) blockrow_update_kernel(const double* __re
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) t[r] -= a;
 }
-// backward sweep: y[c] -= sum_{r0 <= r < r1} L[r][c] x[r - r0] for c < c1; a CTA owns 32 columns, its 8 warps split the rows
-__global__ void __launch_bounds__(256) blockcol_update_kernel(const double* __restrict__ L, long long ldl, int r0, int r1, int c1,
-                                                              const double* __restrict__ x, double* __restrict__ y) {
-    __shared__ double part[8][33];
+// backward sweep: y[c] -= sum_{r0 <= r < r1} L[r][c] x[r - r0] for c < c1; a CTA owns 32 columns, its 32 warps split the rows
+// and keep 8 row segments (256 B each) in flight per warp -- the one-warp-per-128-rows version with two loads in flight was
+// latency-bound at ~0.9 TB/s
+constexpr int BCOL_WARPS = 32;
+__global__ void __launch_bounds__(BCOL_WARPS * 32) blockcol_update_kernel(const double* __restrict__ L, long long ldl, int r0, int r1,
+                                                                          int c1, const double* __restrict__ x,
+                                                                          double* __restrict__ y) {
+    __shared__ double part[BCOL_WARPS][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * 32 + lane;
-    double s0 = 0.0, s1 = 0.0;
+    double s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] = 0.0;
     if (c < c1) {
-        int r = r0 + warp;
-        for (; r + 8 < r1; r += 16) {
-            s0 = fma(L[(long long)r * ldl + c], x[r - r0], s0);
-            s1 = fma(L[(long long)(r + 8) * ldl + c], x[r + 8 - r0], s1);
+        for (int r = r0 + warp; r < r1; r += 8 * BCOL_WARPS) {
+            double l[8], xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r + u * BCOL_WARPS;
+                const bool ok = rr < r1;
+                l[u] = ok ? __ldcs(L + (long long)rr * ldl + c) : 0.0;
+                xv[u] = ok ? x[rr - r0] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] = fma(l[u], xv[u], s[u]);
         }
-        if (r < r1) s0 = fma(L[(long long)r * ldl + c], x[r - r0], s0);
     }
-    part[warp][lane] = s0 + s1;
+    part[warp][lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
     __syncthreads();
     if (warp == 0 && c < c1) {
         double a = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) a += part[w][lane];
+        for (int w = 0; w < BCOL_WARPS; ++w) a += part[w][lane];
         y[c] -= a;
     }
 }
@@ -999,7 +1124,7 @@ int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double*
         const int j0 = J * BI, rows = min(BI, n - j0);
         PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(BinvT + J * BB, y + j0, t + j0, rows, 1);
         if (j0 > 0)
-            PPBO_CL blockcol_update_kernel<<<ceil_div(j0, 32), 256, 0, st>>>(L, ldl, j0, j0 + rows, j0, t + j0, y);
+            PPBO_CL blockcol_update_kernel<<<ceil_div(j0, 32), BCOL_WARPS * 32, 0, st>>>(L, ldl, j0, j0 + rows, j0, t + j0, y);
     }
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;

@@ -33,6 +33,11 @@ def main():
             t1 = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
             _lib.load().ppbo_set_tuning(3, 0)
             print("potrf n=%d, critical path on the caller's stream (no priorities): %.3f ms" % (n, t1))
+        if n >= 2000:
+            _lib.load().ppbo_set_tuning(6, 1)
+            t1 = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
+            _lib.load().ppbo_set_tuning(6, 0)
+            print("potrf n=%d, paired (rank-256) trailing updates for large remainders: %.3f ms" % (n, t1))
         t = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
         if "--timeline" in sys.argv:
             W.copy_(A)
@@ -44,21 +49,32 @@ def main():
         L = torch.tril(W)
         err = float((L @ L.T - A).abs().max() / A.abs().max())
         print("potrf n=%d: %.3f ms  (%.2f TFLOP/s)  info=%d relerr=%.2e" % (n, t, n ** 3 / 3 / t / 1e9, info, err))
+        if "--potrf-only" in sys.argv:
+            continue
         b = torch.randn(n, dtype=torch.float64, device=dev)
         t = timeit(lambda: ops.potrs_vec(W, ws, b))
         x = ops.potrs_vec(W, ws, b)
         print("potrs_vec n=%d: %.3f ms  resid=%.2e" % (n, t, float((A @ x - b).abs().max() / b.abs().max())))
+        Wb = ops.blockinv_build(W, ws)
+        t = timeit(lambda: ops.potrs_vec_blockinv(W, Wb, b))
+        x = ops.potrs_vec_blockinv(W, Wb, b)
+        print("potrs_vec_blockinv n=%d: %.3f ms  resid=%.2e" % (n, t, float((A @ x - b).abs().max() / b.abs().max())))
         X = torch.randn(2048, n, dtype=torch.float64, device=dev)
         t = timeit(lambda: ops.trsm_right_lower(W, ws, X))
         print("trsm nrhs=2048 n=%d: %.3f ms (%.2f TFLOP/s)" % (n, t, 2048 * n * n / t / 1e9))
         t = timeit(lambda: ops.gemv(A, b))
         print("gemv n=%d: %.3f ms (%.0f GB/s)" % (n, t, 8 * n * n / t / 1e6))
+    if "--potrf-only" in sys.argv:
+        return
     for (M, N, K) in ((5000, 5000, 128), (5000, 5000, 5000), (1000, 1000, 5000), (4096, 4096, 4096)):
         A = torch.randn(M, K, dtype=torch.float64, device=dev); B = torch.randn(N, K, dtype=torch.float64, device=dev)
         C = torch.zeros(M, N, dtype=torch.float64, device=dev)
         t = timeit(lambda: ops.gemm_nt(A, B, C, 1.0, 1.0))
         print("gemm_nt %dx%dx%d: %.3f ms (%.2f TFLOP/s)" % (M, N, K, t, 2.0 * M * N * K / t / 1e9))
-    for (M, N, K) in ((5000, 5000, 128), (2500, 2500, 128), (5000, 128, 5000), (4096, 4096, 4096), (1000, 1000, 5000)):
+    shapes = ((5000, 5000, 128), (5000, 5000, 256), (2500, 2500, 128), (2500, 2500, 256), (5000, 128, 128), (5000, 128, 256))
+    if "--all-gemm" in sys.argv:
+        shapes += ((5000, 128, 5000), (4096, 4096, 4096), (1000, 1000, 5000))
+    for (M, N, K) in shapes:
         A = torch.randn(M, K, dtype=torch.float64, device=dev); B = torch.randn(N, K, dtype=torch.float64, device=dev)
         C = torch.zeros(M, N, dtype=torch.float64, device=dev)
         ref = A @ B.T
