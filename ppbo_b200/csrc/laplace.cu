@@ -361,7 +361,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     // is kept and only the right-hand side is refreshed (chord steps: same fixed point Sigma^-1 f = beta(f), linear
     // convergence at the rate of the relative change of a+; a chord step costs ~1/6 of a factorisation at Qm = 5000, so it
     // is kept as long as it at least halves the step).
-    const double CHORD_REL = 0.25;
+    const double CHORD_REL = getenv("PPBO_CHORD_REL") ? atof(getenv("PPBO_CHORD_REL")) : 0.25;   // env override: diagnostics only
     const bool trace = getenv("PPBO_TRACE") != nullptr;
     bool refactor = true, converged = false;
     // Cold start f = 0: every difference is 0, so a = -Delta phi~(Delta) / (2 m sigma^2) = 0 and the Newton matrix

@@ -62,6 +62,8 @@ static bool operands_vec2(const GemmOperands& g) {
            g.strideA2 % 2 == 0 && g.strideB2 % 2 == 0;
 }
 
+static thread_local bool g_launch_pdl = false;      // set by potrf_lower around the launches of its critical path
+
 template <class Cfg>
 static int launch_store_cfg(const GemmOperands& g, StoreEpilogue ep, int batch, cudaStream_t st) {
     int rc = set_smem_attr_store<Cfg>();
@@ -73,6 +75,23 @@ static int launch_store_cfg(const GemmOperands& g, StoreEpilogue ep, int batch, 
         grid = dim3((unsigned)((long long)R * tm * (tm + 1) / 2), 1, batch);
     } else {
         grid = dim3(tm, tn, batch);
+    }
+    if (g_launch_pdl) {
+        // critical path of the blocked Cholesky: this kernel may become resident while its predecessor in the stream is still
+        // running (it waits at griddepcontrol.wait before touching memory), which hides launch and scheduling latency
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(Cfg::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ++g_launch_count;
+        PPBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_nt_store_kernel<Cfg>, g, ep));
+        return PPBO_OK;
     }
     PPBO_CL gemm_nt_store_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, ep);
     PPBO_LAUNCH_CHECK();
@@ -144,23 +163,11 @@ __global__ void __launch_bounds__(256) gemv_kernel(const double* __restrict__ A,
             const double2* a2 = reinterpret_cast<const double2*>(a);
             const double2* x2 = reinterpret_cast<const double2*>(x);
             const int n2 = N >> 1;
-            int j = lane;
-            double s2 = 0.0, s3 = 0.0;
-            for (; j + 96 < n2; j += 128) {               // 4 x 16-byte loads of the matrix row in flight per lane
-                const double2 a0 = __ldcs(a2 + j), a1 = __ldcs(a2 + j + 32), a2v = __ldcs(a2 + j + 64), a3 = __ldcs(a2 + j + 96);
-                const double2 x0 = x2[j], x1 = x2[j + 32], x2v = x2[j + 64], x3 = x2[j + 96];
-                s0 = fma(a0.x, x0.x, s0); s1 = fma(a0.y, x0.y, s1);
-                s2 = fma(a1.x, x1.x, s2); s3 = fma(a1.y, x1.y, s3);
-                s0 = fma(a2v.x, x2v.x, s0); s1 = fma(a2v.y, x2v.y, s1);
-                s2 = fma(a3.x, x3.x, s2); s3 = fma(a3.y, x3.y, s3);
-            }
-            for (; j < n2; j += 32) {
+            for (int j = lane; j < n2; j += 32) {
                 const double2 av = a2[j], xv = x2[j];
                 s0 = fma(av.x, xv.x, s0);
                 s1 = fma(av.y, xv.y, s1);
             }
-            s0 += s2;
-            s1 += s3;
             if ((N & 1) && lane == 0) s0 = fma(a[N - 1], x[N - 1], s0);
         } else {
             for (int j = lane; j < N; j += 32) s0 = fma(a[j], x[j], s0);
@@ -331,18 +338,23 @@ __device__ __forceinline__ double rsqrt_nr(double d) {
     return fma(y * e, 0.5, y);
 }
 
-// warp-level Cholesky of a 32 x 32 block held in shared memory (row stride lds), in place.  Lane i owns row i in registers;
-// column k of the running Schur complement is exchanged through a triple-buffered shared-memory line read back as broadcast
-// loads (one __syncwarp per column).  The rows stay UNSCALED during the elimination (r[i][k] = L[i][k] L[k][k]): the dependency
-// chain of a column is  LDS pivot -> reciprocal -> one FMA -> STS -> __syncwarp, everything else (rank-1 update of the other
-// columns, square roots, scaling) is off it; the 32 reciprocal square roots are taken afterwards, one per lane.
-// wsm: [0,96) exchange lines, [96,128) 1 / L[k][k], [128,160) pivots.  Returns 0 or the 1-based index of the first non-positive
+// warp-level Cholesky of a 32 x 32 block held in shared memory (row stride lds), in place, UNSCALED: on return the block holds
+// r[i][k] = L[i][k] L[k][k] (lower triangle) and idiag[k] = 1 / L[k][k]; the caller scales column k by idiag[k] (all threads, after
+// its barrier).  Lane i owns row i in registers; column k of the running Schur complement is exchanged through a ring of eight
+// shared-memory lines read back as broadcast loads (one __syncwarp per column).
+// The dependency chain of a column is  LDS pivot -> reciprocal -> one FMA -> STS -> __syncwarp.  To keep that chain free of other
+// work whatever ptxas decides to do (measured: 116 to 294 clocks per column for the same source in three builds, depending on
+// how the rank-1 updates of the other columns were interleaved), the columns are processed in blocks of four with DELAYED
+// updates: inside a block only the block's own columns are updated per step (<= 2 FMAs next to the chain), and the rank-4 update
+// of all later columns follows as one throughput-bound stretch.  Finished columns leave the registers at once.
+// wsm: [0,256) exchange lines, [256,288) 1 / L[k][k], [288,320) pivots.  Returns 0 or the 1-based index of the first non-positive
 // (or NaN) pivot, same value in every lane.
+constexpr int POTF2_WSM = 320, POTF2_IDIAG = 256, POTF2_PIV = 288;
 __device__ __forceinline__ int warp_potrf32(double* Sb, int lds, double* wsm, long long* tdbg = nullptr) {
     const int lane = threadIdx.x & 31;
     if (tdbg && lane == 0) tdbg[0] = clock64();
-    double* idiag = wsm + 96;
-    double* piv = wsm + 128;
+    double* idiag = wsm + POTF2_IDIAG;
+    double* piv = wsm + POTF2_PIV;
     double r[POTF2_SUB];
 #pragma unroll
     for (int j = 0; j < POTF2_SUB; ++j) r[j] = (j <= lane) ? Sb[lane * lds + j] : 0.0;
@@ -350,37 +362,52 @@ __device__ __forceinline__ int warp_potrf32(double* Sb, int lds, double* wsm, lo
     __syncwarp();
     if (tdbg && lane == 0) tdbg[1] = clock64();
 #pragma unroll
-    for (int k = 0; k < POTF2_SUB; ++k) {
-        const double* c = wsm + (k % 3) * 32;
-        const double d = c[k];
-        const double inv = rcp_nr(d);
-        if (k + 1 < POTF2_SUB) {
-            // publish column k+1 first: the line written in step k was last read in step k-2, with the __syncwarp of step k-1
-            // in between
-            const double t = r[k] * c[k + 1];                          // independent of the reciprocal
-            r[k + 1] = fma(-t, inv, r[k + 1]);
-            wsm[((k + 1) % 3) * 32 + lane] = r[k + 1];                 // lanes <= k hold 0 there
-            __syncwarp();
-        }
-        const double mine = r[k] * inv;
+    for (int b = 0; b < POTF2_SUB / 4; ++b) {
+        double mine[4];
 #pragma unroll
-        for (int j = k + 2; j < POTF2_SUB; ++j) r[j] = fma(-mine, c[j], r[j]);   // rows < j only touch their (unused) upper part
-        if (lane == 0) piv[k] = d;
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = 4 * b + kk;
+            const double* c = wsm + (k & 7) * 32;
+            const double d = c[k];
+            const double inv = rcp_nr(d);
+            if (k + 1 < POTF2_SUB) {
+                if (kk == 3) {               // first column of the next block: the three pending updates do not wait for `inv`
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) r[k + 1] = fma(-mine[q], wsm[((4 * b + q) & 7) * 32 + k + 1], r[k + 1]);
+                }
+                const double t = r[k] * c[k + 1];
+                r[k + 1] = fma(-t, inv, r[k + 1]);
+                wsm[((k + 1) & 7) * 32 + lane] = r[k + 1];      // lanes <= k hold 0 there; slot last read 8 columns ago
+                __syncwarp();
+            }
+            mine[kk] = r[k] * inv;
+#pragma unroll
+            for (int j = k + 2; j < 4 * b + 4; ++j) r[j] = fma(-mine[kk], c[j], r[j]);
+            if (lane == 0) piv[k] = d;
+            if (k <= lane) Sb[lane * lds + k] = r[k];           // final (unscaled)
+        }
+        const double* c0 = wsm + ((4 * b) & 7) * 32;            // slots 4b .. 4b+3 of the ring are consecutive
+#pragma unroll
+        for (int j = 4 * b + 5; j < POTF2_SUB; ++j)
+            r[j] = fma(-mine[3], c0[96 + j], fma(-mine[2], c0[64 + j], fma(-mine[1], c0[32 + j], fma(-mine[0], c0[j], r[j]))));
     }
     __syncwarp();
     if (tdbg && lane == 0) tdbg[2] = clock64();
     const double dk = piv[lane];
     const bool ok = dk > 0.0;                                          // false for NaN
     const unsigned badmask = __ballot_sync(0xffffffffu, !ok);
-    const double isd = rsqrt_nr(ok ? dk : 1.0);
-    idiag[lane] = isd;
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < POTF2_SUB; ++j)
-        if (j <= lane) Sb[lane * lds + j] = r[j] * idiag[j];           // diagonal: d / sqrt(d)
+    idiag[lane] = rsqrt_nr(ok ? dk : 1.0);
     __syncwarp();
     if (tdbg && lane == 0) tdbg[3] = clock64();
     return badmask ? __ffs(badmask) : 0;
+}
+
+// all threads: L11[i][j] = r[i][j] / L[j][j] on the lower triangle of the 32 x 32 piece warp_potrf32 left unscaled
+__device__ __forceinline__ void potf2_scale_piece(double* Sb, int lds, const double* idiag) {
+    for (int e = threadIdx.x; e < POTF2_SUB * POTF2_SUB; e += POTF2_THREADS) {
+        const int i = e >> 5, j = e & 31;
+        if (j <= i) Sb[i * lds + j] *= idiag[j];
+    }
 }
 
 // inverse of the 32 x 32 lower-triangular block Sb (one warp): lane c owns column c of R = L^-1,
@@ -482,6 +509,8 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
                                                                   double* __restrict__ dinv, int* __restrict__ info,
                                                                   int block_offset, long long* __restrict__ dbg) {
     extern __shared__ double sm[];
+    asm volatile("griddepcontrol.launch_dependents;");       // see gemm_nt_store_kernel: no-ops for an ordinary launch
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int dbg_i = 0;
 #define POTF2_STAMP() do { if (dbg && threadIdx.x == 0) dbg[dbg_i++] = clock64(); } while (0)
     POTF2_STAMP();
@@ -489,7 +518,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     double* Rd = S + CHOL_NB * POTF2_LDS;                   // 4 inverted 32 x 32 diagonal pieces
     double* Tm = Rd + 4 * POTF2_SUB * POTF2_LDR;            // scratch
     __shared__ int bad_s;
-    __shared__ double wsm[160];
+    __shared__ double wsm[POTF2_WSM];
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) bad_s = 0;
 #pragma unroll 8
@@ -514,13 +543,15 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
             potf2_finish_block_row(S, Rd, Tm, sb - 1, A, lda, dinv, jb);
         }
         __syncthreads();
-        POTF2_STAMP();
         if (bad_s) break;                                   // uniform
+        potf2_scale_piece(S11, POTF2_LDS, wsm + POTF2_IDIAG);
+        __syncthreads();
+        POTF2_STAMP();
         if (warp == 0) {
-            warp_inv32(S11, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, wsm + 96);
+            warp_inv32(S11, POTF2_LDS, Rd + sb * POTF2_SUB * POTF2_LDR, wsm + POTF2_IDIAG);
         } else if (rem > 0) {
             const int i = tid - 32;
-            if (i < rem) row_trsv32(S + (c1 + i) * POTF2_LDS + c0, S11, POTF2_LDS, wsm + 96, Tm + i * POTF2_LDT);
+            if (i < rem) row_trsv32(S + (c1 + i) * POTF2_LDS + c0, S11, POTF2_LDS, wsm + POTF2_IDIAG, Tm + i * POTF2_LDT);
             potf2_named_barrier(1, POTF2_THREADS - 32);
             // trailing: S22 -= L21 L21^T (lower), warps 1..15
             smem_gemm_mma<false>(S + c1 * POTF2_LDS + c1, POTF2_LDS, Tm, POTF2_LDT, Tm, POTF2_LDT, rem, rem, POTF2_SUB, -1.0, true, true,
@@ -611,6 +642,9 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
     // tuning key 5 = 1: record a timeline (start of every diagonal block, after panel, after look-ahead; start/end of the bulk
     // trailing updates) and print it to stderr after a device synchronise -- diagnostics only
     const bool tl = g_tuning[5] == 1 && nblk <= 64;
+    // tuning key 7 = 1: programmatic dependent launch on the critical path.  Measured at n = 5000: 4.19 ms with it against
+    // 4.05 ms without (the early-resident CTAs take SM slots from the trailing update), so it is off by default.
+    const bool pdl = lookahead && g_tuning[7] == 1;
     static cudaEvent_t ev_d[64], ev_p[64], ev_l[64], ev_r0[64], ev_r1[64], ev_end;
     static bool ev_init = false;
     if (tl && !g_potf2_dbg) cudaMalloc(&g_potf2_dbg, 64 * sizeof(long long));
@@ -628,9 +662,25 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
         double* Ajj = A + (long long)j0 * lda + j0;
         double* dinv_b = dinv + (long long)b * CHOL_NB * CHOL_NB;
         if (tl) cudaEventRecord(ev_d[b], st);
-        PPBO_CL potf2_inv_kernel<<<1, POTF2_THREADS, potf2_smem, st>>>(Ajj, lda, jb, dinv_b, info_d, j0,
-                                                                         (tl && b == 20) ? g_potf2_dbg : nullptr);
-        PPBO_LAUNCH_CHECK();
+        if (pdl) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(1);
+            cfg.blockDim = dim3(POTF2_THREADS);
+            cfg.dynamicSmemBytes = potf2_smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            ++g_launch_count;
+            PPBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, potf2_inv_kernel, Ajj, lda, jb, dinv_b, info_d, j0,
+                                               (long long*)((tl && b == 20) ? g_potf2_dbg : nullptr)));
+        } else {
+            PPBO_CL potf2_inv_kernel<<<1, POTF2_THREADS, potf2_smem, st>>>(Ajj, lda, jb, dinv_b, info_d, j0,
+                                                                             (tl && b == 20) ? g_potf2_dbg : nullptr);
+            PPBO_LAUNCH_CHECK();
+        }
         if (tl) cudaEventRecord(ev_p[b], st);
         if (rem <= 0) break;
         // panel: L21 = A21 . inv(L11)^T   (in place: each CTA owns whole rows, K == jb <= BN)
@@ -638,7 +688,9 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
         {
             GemmOperands g{A21, lda, 0, dinv_b, CHOL_NB, 0, rem, jb, jb};
             StoreEpilogue ep{A21, lda, 0, 1.0, 0.0, 0, 0, 1};
+            g_launch_pdl = pdl;
             rc = launch_gemm_nt(g, ep, 1, st);
+            g_launch_pdl = false;
             if (rc) return rc;
         }
         double* A22 = A + (long long)j1 * lda + j1;
@@ -662,7 +714,9 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
             {
                 GemmOperands g{P, lda, 0, P, lda, 0, rem, nb1, kcols};
                 StoreEpilogue ep{A22, lda, 0, -1.0, 1.0, 0, 0};
-                rc = launch_gemm_nt(g, ep, 1, st);
+                g_launch_pdl = pdl;
+            rc = launch_gemm_nt(g, ep, 1, st);
+            g_launch_pdl = false;
                 if (rc) return rc;
             }
             if (tl) { cudaEventRecord(ev_l[b], st); has_l[b] = true; }
@@ -693,7 +747,9 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
             }
             GemmOperands g{A21, lda, 0, A21, lda, 0, rem, rem, jb};
             StoreEpilogue ep{A22, lda, 0, -1.0, 1.0, 1, 0};
+            g_launch_pdl = pdl;
             rc = launch_gemm_nt(g, ep, 1, st);
+            g_launch_pdl = false;
             if (rc) return rc;
         }
     }
@@ -1027,28 +1083,39 @@ int blockinv_build(const double* L, long long ldl, int n, const double* dinv, do
     return PPBO_OK;
 }
 
-// out[r] = sum_c Mat[r][c] v[c] over the triangle (lower: c <= r, upper: r <= c < rows) of one BI x BI block; warp per row,
-// four rows of loads in flight per lane (the kernel is a latency-bound 4 MB read: 128 CTAs, one pass)
-__global__ void __launch_bounds__(256) blocktri_gemv_kernel(const double* __restrict__ Mat, const double* __restrict__ v,
-                                                            double* __restrict__ out, int rows, int upper) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * 8 + warp;
-    if (r >= rows) return;
-    const double* m = Mat + (long long)r * BI;
-    const int c_lo = upper ? (r & ~31) : 0, c_hi = upper ? rows : r + 1;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int c = c_lo + lane; c < c_hi; c += 128) {                  // the other triangle holds exact zeros
-        const bool p1 = c + 32 < c_hi, p2 = c + 64 < c_hi, p3 = c + 96 < c_hi;
-        const double a0 = m[c], a1 = p1 ? m[c + 32] : 0.0, a2 = p2 ? m[c + 64] : 0.0, a3 = p3 ? m[c + 96] : 0.0;
-        const double v0 = v[c], v1 = p1 ? v[c + 32] : 0.0, v2 = p2 ? v[c + 64] : 0.0, v3 = p3 ? v[c + 96] : 0.0;
-        s0 = fma(a0, v0, s0);
-        s1 = fma(a1, v1, s1);
-        s2 = fma(a2, v2, s2);
-        s3 = fma(a3, v3, s3);
+// out[r] = sum_c Mat[r][c] v[c] over the triangle (lower: c <= r, upper: r <= c < rows) of one BI x BI block.
+// 128 threads per row, two rows per CTA; every thread issues its (up to) four 16-byte loads of the row at once, so the whole
+// 4 MB triangle is one DRAM round trip deep (the warp-per-row version walked a 1024-element row in 8 dependent rounds: 15 us).
+// The other triangle of Mat holds exact zeros; v is only read inside [c_lo, c_hi) (the tail behind the block may hold anything).
+constexpr int BTRI_ROWS = 2;
+__global__ void __launch_bounds__(128 * BTRI_ROWS) blocktri_gemv_kernel(const double* __restrict__ Mat, const double* __restrict__ v,
+                                                                        double* __restrict__ out, int rows, int upper) {
+    __shared__ double part[BTRI_ROWS][4];
+    const int sub = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, w = t >> 5;
+    const int r = blockIdx.x * BTRI_ROWS + sub;
+    const bool vec = (reinterpret_cast<uintptr_t>(Mat) & 15) == 0;          // workspace carving may leave Mat 8-byte aligned
+    double s = 0.0;
+    if (r < rows) {
+        const double* m = Mat + (long long)r * BI;
+        const int c_lo = upper ? r : 0, c_hi = upper ? rows : r + 1;           // columns [c_lo, c_hi)
+        double2 a[4];
+        double x0[4], x1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = 2 * t + 256 * q;                                      // even column of this thread's pair
+            const bool p0 = c >= c_lo && c < c_hi, p1 = c + 1 >= c_lo && c + 1 < c_hi;
+            if (vec) a[q] = (p0 || p1) ? *reinterpret_cast<const double2*>(m + c) : make_double2(0.0, 0.0);
+            else a[q] = make_double2(p0 ? m[c] : 0.0, p1 ? m[c + 1] : 0.0);
+            x0[q] = p0 ? v[c] : 0.0;
+            x1[q] = p1 ? v[c + 1] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s = fma(a[q].x, x0[q], fma(a[q].y, x1[q], s));
     }
-    double a = (s0 + s1) + (s2 + s3);
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) out[r] = a;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) part[sub][w] = s;
+    __syncthreads();
+    if (t == 0 && r < rows) out[r] = (part[sub][0] + part[sub][1]) + (part[sub][2] + part[sub][3]);
 }
 // forward sweep: t[r] -= sum_{c < cols} L[r][c0 + c] y[c] for r in [r0, n); warp per row
 __global__ void __launch_bounds__(256) blockrow_update_kernel(const double* __restrict__ L, long long ldl, int r0, int n, int c0,
@@ -1116,13 +1183,13 @@ int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double*
     double* y = W + nbI * (3 * BB + BB / 4);
     for (int J = 0; J < nbI; ++J) {                     // L y = t
         const int j0 = J * BI, rows = min(BI, n - j0), j1 = j0 + rows;
-        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(Binv + J * BB, t + j0, y + j0, rows, 0);
+        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, BTRI_ROWS), 128 * BTRI_ROWS, 0, st>>>(Binv + J * BB, t + j0, y + j0, rows, 0);
         if (j1 < n)
             PPBO_CL blockrow_update_kernel<<<ceil_div(n - j1, 8), 256, 0, st>>>(L, ldl, j1, n, j0, rows, y + j0, t);
     }
     for (int J = nbI - 1; J >= 0; --J) {                // L^T x = y
         const int j0 = J * BI, rows = min(BI, n - j0);
-        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(BinvT + J * BB, y + j0, t + j0, rows, 1);
+        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, BTRI_ROWS), 128 * BTRI_ROWS, 0, st>>>(BinvT + J * BB, y + j0, t + j0, rows, 1);
         if (j0 > 0)
             PPBO_CL blockcol_update_kernel<<<ceil_div(j0, 32), BCOL_WARPS * 32, 0, st>>>(L, ldl, j0, j0 + rows, j0, t + j0, y);
     }
