@@ -29,6 +29,9 @@ int ppbo_device_sm_count(int dev);
 long long ppbo_launch_count(void);
 /* tuning switches for benchmarking (key 0: tile configuration of the row-max GEMM; 0 = default) */
 int ppbo_set_tuning(int key, int value);
+/* host-thread role for concurrent fits (no reference counterpart: the reference is single-threaded, ppbo_numerical_main.py:192);
+ * background threads get lowest-priority internal streams */
+int ppbo_set_thread_background(int on);
 
 /* ---- K1: covariance matrices -------------------------------------------------------------------- */
 /* out[n1 x n2] = k(X1_i, X2_j).  Replaces kernels.SE_kernel / RQ_kernel / camphor_copper_kernel and

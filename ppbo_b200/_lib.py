@@ -28,6 +28,7 @@ _SIGNATURES = {
     "ppbo_device_sm_count": (_I, [_I]),
     "ppbo_launch_count": (_L, []),
     "ppbo_set_tuning": (_I, [_I, _I]),
+    "ppbo_set_thread_background": (_I, [_I]),
     "ppbo_kernel_matrix": (_I, [_I, _P, _I, _P, _I, _I, _PD, _D, _P, _L, _P]),
     "ppbo_gram_regularized": (_I, [_I, _P, _I, _I, _PD, _D, _D, _P, _L, _P]),
     "ppbo_kernel_se_grad": (_I, [_P, _I, _P, _I, _I, _PD, _D, _P, _L, _L, _P]),

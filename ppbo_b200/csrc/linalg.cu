@@ -589,6 +589,8 @@ long long potrf_dinv_doubles(int n) { return (long long)ceil_div(n, CHOL_NB) * C
 
 static long long* g_potf2_dbg = nullptr;     // device buffer for the phase clocks of one diagonal-block kernel (timeline mode)
 
+static thread_local bool g_thread_background = false;
+
 struct CholStreams {
     cudaStream_t side = nullptr, crit = nullptr;
     cudaEvent_t panel_done[2] = {nullptr, nullptr}, rest_done[2] = {nullptr, nullptr};
@@ -598,10 +600,14 @@ struct CholStreams {
         // The block-column critical path (diagonal block, panel, next block column) runs on a high-priority stream and the
         // bulk of the trailing update on a low-priority one: the trailing GEMM's ~1500 short CTAs otherwise occupy every SM
         // and the one-CTA diagonal-block kernel of the next step queues behind them.
+        // A background thread (ppbo_set_thread_background: the weight-space fit that runs concurrently with the GP fit) keeps
+        // everything at the lowest priority; a foreground thread puts its bulk one level above that, so that its trailing updates
+        // are not queued behind the background work either.
         int lo = 0, hi = 0;
-        PPBO_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        PPBO_CUDA_CHECK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo));
-        PPBO_CUDA_CHECK(cudaStreamCreateWithPriority(&crit, cudaStreamNonBlocking, hi));
+        PPBO_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));        // lo: lowest priority (largest number)
+        const int mid = (hi < lo) ? lo - 1 : lo;
+        PPBO_CUDA_CHECK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, g_thread_background ? lo : mid));
+        PPBO_CUDA_CHECK(cudaStreamCreateWithPriority(&crit, cudaStreamNonBlocking, g_thread_background ? lo : hi));
         PPBO_CUDA_CHECK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) {
             PPBO_CUDA_CHECK(cudaEventCreateWithFlags(&panel_done[i], cudaEventDisableTiming));
@@ -1233,6 +1239,12 @@ extern "C" int ppbo_set_tuning(int key, int value) {
     return PPBO_OK;
 }
 extern "C" const char* ppbo_last_error(void) { return g_err; }
+/* Marks the calling host thread as background work: the streams the library creates for it (Cholesky critical path / bulk) get the
+ * lowest priority.  Must be called before the thread's first factorisation. */
+extern "C" int ppbo_set_thread_background(int on) {
+    g_thread_background = on != 0;
+    return PPBO_OK;
+}
 extern "C" int ppbo_device_sm_count(int dev) {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;

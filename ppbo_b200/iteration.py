@@ -220,13 +220,28 @@ class IterationInputs:
 
 
 _SIDE_STREAMS = {}
-# The GP fit is the critical path of the iteration: its launches go to a high-priority stream so that the concurrent
-# weight-space fit (default priority) only fills the SMs the GP fit leaves idle.  None: stay on the caller's stream.
-GP_STREAM_PRIORITY = None    # measured: -1 slows the GP fit from 23.6 to 39.6 ms (it starves its own low-priority trailing updates)
+# The GP fit is the critical path of the iteration: its launches go to a stream one level above the default priority, its
+# Cholesky bulk (library-internal side stream) sits at the same level, and the background weight-space fit keeps the default
+# (lowest) priority for everything (ppbo_set_thread_background), so it only fills the SMs the GP fit leaves idle.
+# None / 0: stay on the caller's stream.
+GP_STREAM_PRIORITY = -1
+_WORKER = None
 
 
-def _side_stream(dev, priority=0):
-    key = (dev.type, dev.index, priority)
+def _background_worker():
+    """One persistent host thread for the concurrent weight-space fit (the library keeps per-thread streams: a fresh thread per
+    iteration would create new ones every time).  Marked as background before its first launch."""
+    global _WORKER
+    if _WORKER is None:
+        from concurrent.futures import ThreadPoolExecutor
+        from . import _lib
+        _WORKER = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ppbo-rff-fit",
+                                     initializer=lambda: _lib.load().ppbo_set_thread_background(1))
+    return _WORKER
+
+
+def _side_stream(dev, priority=0, tag=""):
+    key = (dev.type, dev.index, priority, tag)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=priority)
     return _SIDE_STREAMS[key]
@@ -249,39 +264,47 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
             ev.record()
             timers.append((name, ev))
     mark("start")
-    PhiT = rff_grid_features(W, b, theta[2], grids)           # independent of the fit: every rank, before the broadcast
     lo, hi = shard.bounds(S)
-    if sampling_engine(hi - lo, P, Fdim) == "i8":
-        PhiT = SlicedGrids(PhiT)                              # digit planes of the grid features, also before the broadcast
+    # The grid features (and their digit planes) do not depend on the fit.  On the rank that runs the latency-bound GP fit they
+    # go to the side stream and fill SMs the fit leaves idle; the other ranks compute them while they wait for the broadcast.
+    main = torch.cuda.current_stream()
+    grid_stream = _side_stream(X.device, tag="grid") if shard.rank == 0 else main
+    if grid_stream is not main:
+        grid_stream.wait_stream(main)
+    with torch.cuda.stream(grid_stream):
+        PhiT = rff_grid_features(W, b, theta[2], grids)
+        if sampling_engine(hi - lo, P, Fdim) == "i8":
+            PhiT = SlicedGrids(PhiT)                          # digit planes of the grid features
     mark("grid_features")
     pack = torch.empty(2 * Fdim + 1, dtype=F64, device=X.device)
     gp = rff = None
     rff_rank = 1 if (CONCURRENT_FITS and shard.world > 1) else 0      # with more than one GPU the two fits run on two of them
     if shard.rank == 0 and CONCURRENT_FITS and shard.world == 1:
-        main = torch.cuda.current_stream()
+        # GP fit: foreground, on a stream one priority level above the default; weight-space fit: a persistent background host
+        # thread whose streams all sit at the lowest priority, so it only takes the SMs the GP fit leaves idle.
         side = _side_stream(X.device)
         side.wait_stream(main)
-        box = {}
+        gp_stream = _side_stream(X.device, priority=GP_STREAM_PRIORITY, tag="gp") if GP_STREAM_PRIORITY else main
+        if gp_stream is not main:
+            gp_stream.wait_stream(main)
 
         def weight_space_fit():
-            try:
-                torch.cuda.set_device(X.device)
-                with torch.cuda.stream(side):
-                    box["rff"] = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
-            except BaseException as e:          # re-raised on the calling thread
-                box["error"] = e
-        th = threading.Thread(target=weight_space_fit, name="ppbo-rff-fit")
-        th.start()
+            torch.cuda.set_device(X.device)
+            with torch.cuda.stream(side):
+                return rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+        fut = _background_worker().submit(weight_space_fit)
         try:
-            gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
-            mark("gp_fit")
-            mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
-            mark("mustar")
+            with torch.cuda.stream(gp_stream):
+                gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
+                mark("gp_fit")
+                mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
+                mark("mustar")
         finally:
-            th.join()
-        if "error" in box:
-            raise box["error"]
-        rff = box["rff"]
+            rff = fut.result()                 # re-raises on this thread
+        if gp_stream is not main:
+            main.wait_stream(gp_stream)
+            for t in (gp.Sigma, gp.lap.G, gp.lap.Lfac, gp.lap.f_map, gp.lap.alpha, gp.lap.arrow, mustar):
+                t.record_stream(main)
         main.wait_stream(side)
         for t in (rff.omega_map, rff.hess_diag, rff.Phi_X):
             t.record_stream(main)
@@ -310,6 +333,10 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         rff = RFFFit()
         rff.W, rff.b, rff.sigma_f, rff.Phi_X, rff.stats = W, b, float(theta[2]), None, None
     rff.omega_map, rff.hess_diag = pack[:Fdim], pack[Fdim:2 * Fdim]
+    if grid_stream is not main:
+        main.wait_stream(grid_stream)
+        for t in ((PhiT.PhiT, PhiT.planes, PhiT.scale) if isinstance(PhiT, SlicedGrids) else (PhiT,)):
+            t.record_stream(main)
     sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed)
     mark("acquisition")
     return sums, gp, rff
