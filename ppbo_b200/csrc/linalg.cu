@@ -135,7 +135,7 @@ static int launch_rowmax_cfg(const GemmOperands& g, const RowMaxEpilogue& ep_in,
     return PPBO_OK;
 }
 
-int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // [0]: row-max GEMM tile configuration (0 = default)
+int g_tuning[16] = {0};     // [0]: row-max GEMM tile configuration (0 = default)
 
 int launch_gemm_nt_rowmax(const GemmOperands& g, const RowMaxEpilogue& ep, int batch, cudaStream_t st) {
     if (g.M <= 0 || batch <= 0) return PPBO_OK;
@@ -148,6 +148,115 @@ int launch_gemm_nt_rowmax(const GemmOperands& g, const RowMaxEpilogue& ep, int b
     if (v2 && !small) return launch_rowmax_cfg<CfgTall3>(g, ep, batch, st);
     if (small) return v2 ? launch_rowmax_cfg<CfgSmall>(g, ep, batch, st) : launch_rowmax_cfg<CfgSmallU>(g, ep, batch, st);
     return v2 ? launch_rowmax_cfg<CfgBig>(g, ep, batch, st) : launch_rowmax_cfg<CfgBigU>(g, ep, batch, st);
+}
+
+// ------------------------------------------------------------------------------------------- row panel x 128 x 128 block
+// out[r][0:128] = alpha * sum_k A[r][k] Bm[j][k] + beta * C[r][j]   for r < M, with N = K = 128 fixed.
+// The two GEMMs on the critical path of every Cholesky step have this shape (panel L21 = A21 inv(L11)^T, in place; look-ahead
+// A22[:, 0:128] -= L21 L21[0:128]^T).  The general kernel spends ~15-20 us on each (3-stage pipeline fill, 8 barrier-gated
+// k-tiles of 16, C read only in the epilogue) for 4 us of DMMA work per SM.  Here the whole 128 x 128 block and the CTA's R rows go
+// to shared memory in four 32-column cp.async groups (compute on group g while g+1.. are in flight), the C fragments are
+// requested before the main loop, and rows are padded to 132 doubles (== 4 mod 16: the 8-byte fragment loads of a half-warp
+// hit 16 distinct bank pairs).  `out` may alias A (each CTA has read its own rows completely before it stores).
+constexpr int RP_LD = 132, RP_THREADS = 256;
+template <int R>
+__global__ void __launch_bounds__(RP_THREADS) rowpanel128_kernel(const double* __restrict__ A, long long lda,
+                                                                 const double* __restrict__ Bm, long long ldb,
+                                                                 const double* C, long long ldc, double* out, long long ldo,
+                                                                 int M, double alpha, double beta) {
+    extern __shared__ __align__(16) double rp_smem[];
+    double* Bs = rp_smem;                      // [128][RP_LD]
+    double* As = rp_smem + 128 * RP_LD;        // [R][RP_LD]
+    constexpr int MI = R / 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+    const int r0 = blockIdx.x * R;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {          // 128 rows x 16 chunks of 16 bytes
+            const int c = tid + i * RP_THREADS, row = c >> 4, kc = (c & 15) * 2 + 32 * g;
+            cp_async_zfill<16>(Bs + row * RP_LD + kc, Bm + (long long)row * ldb + kc, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < (R * 16 + RP_THREADS - 1) / RP_THREADS; ++i) {
+            const int c = tid + i * RP_THREADS;
+            if (c < R * 16) {
+                const int row = c >> 4, kc = (c & 15) * 2 + 32 * g, gr = r0 + row;
+                cp_async_zfill<16>(As + row * RP_LD + kc, gr < M ? A + (long long)gr * lda + kc : A, gr < M ? 16 : 0);
+            }
+        }
+        cp_async_commit();
+    }
+    const int n0 = warp * 16;
+    double2 cin[MI][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+            const int r = r0 + mi * 8 + gq;
+            cin[mi][ni] = (beta != 0.0 && r < M) ? *reinterpret_cast<const double2*>(C + (long long)r * ldc + n0 + ni * 8 + 2 * t4)
+                                                 : make_double2(0.0, 0.0);
+        }
+    double acc[MI][2][2];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const double* Ap = As + gq * RP_LD + t4;
+    const double* Bp = Bs + (n0 + gq) * RP_LD + t4;
+    auto chunk = [&](int g) {
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+            const int k = 32 * g + 4 * k4;
+            double a[MI], b[2];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) a[mi] = Ap[mi * 8 * RP_LD + k];
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) b[ni] = Bp[ni * 8 * RP_LD + k];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+        }
+    };
+    cp_async_wait<3>(); __syncthreads(); chunk(0);
+    cp_async_wait<2>(); __syncthreads(); chunk(1);
+    cp_async_wait<1>(); __syncthreads(); chunk(2);
+    cp_async_wait<0>(); __syncthreads(); chunk(3);
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+            const int r = r0 + mi * 8 + gq;
+            if (r < M)
+                *reinterpret_cast<double2*>(out + (long long)r * ldo + n0 + ni * 8 + 2 * t4) =
+                    make_double2(fma(alpha, acc[mi][ni][0], beta * cin[mi][ni].x), fma(alpha, acc[mi][ni][1], beta * cin[mi][ni].y));
+        }
+}
+
+// returns 1 when the specialised kernel was launched, 0 when the operands do not qualify (caller falls back), < 0 on error
+static int launch_rowpanel128(const double* A, long long lda, const double* Bm, long long ldb, const double* C, long long ldc,
+                              double* out, long long ldo, int M, double alpha, double beta, cudaStream_t st) {
+    if (g_tuning[8] == 1) return 0;                       // tuning key 8 = 1: general GEMM kernel (comparison)
+    if (M <= 0) return 1;
+    if (!(aligned16(A) && aligned16(Bm) && aligned16(out) && (C == nullptr || aligned16(C)) && lda % 2 == 0 && ldb % 2 == 0 &&
+          ldc % 2 == 0 && ldo % 2 == 0))
+        return 0;
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        err = cudaFuncSetAttribute(rowpanel128_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + 32) * RP_LD * 8);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(rowpanel128_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + 16) * RP_LD * 8);
+    });
+    PPBO_CUDA_CHECK(err);
+    if (C == nullptr) { C = out; ldc = ldo; }
+    if (M > PPBO_SM_COUNT * 16)
+        PPBO_CL rowpanel128_kernel<32><<<ceil_div(M, 32), RP_THREADS, (128 + 32) * RP_LD * 8, st>>>(A, lda, Bm, ldb, C, ldc, out, ldo, M, alpha, beta);
+    else
+        PPBO_CL rowpanel128_kernel<16><<<ceil_div(M, 16), RP_THREADS, (128 + 16) * RP_LD * 8, st>>>(A, lda, Bm, ldb, C, ldc, out, ldo, M, alpha, beta);
+    PPBO_LAUNCH_CHECK();
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------- GEMV
@@ -691,7 +800,9 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
         if (rem <= 0) break;
         // panel: L21 = A21 . inv(L11)^T   (in place: each CTA owns whole rows, K == jb <= BN)
         double* A21 = A + (long long)j1 * lda + j0;
-        {
+        rc = (jb == CHOL_NB && !pdl) ? launch_rowpanel128(A21, lda, dinv_b, CHOL_NB, nullptr, 0, A21, lda, rem, 1.0, 0.0, st) : 0;
+        if (rc < 0) return rc;
+        if (rc == 0) {
             GemmOperands g{A21, lda, 0, dinv_b, CHOL_NB, 0, rem, jb, jb};
             StoreEpilogue ep{A21, lda, 0, 1.0, 0.0, 0, 0, 1};
             g_launch_pdl = pdl;
@@ -707,22 +818,28 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
             // update of a pair moves 512 KB for 4.2 MFLOP.  Even step of a pair: only the next block column is brought up to
             // date (look-ahead, K = 128) and the bulk is deferred; odd step: look-ahead and bulk with K = 256 over both panels,
             // which are adjacent columns of A.  Small remainders (bulk hidden behind the critical path) keep K = 128.
-            // Measured at n = 5000: 4.01 ms paired against 3.94 ms unpaired -- the look-ahead of the even step has to wait for the
-            // paired bulk update (it writes the same block column), which costs more than the better GEMM rate returns; kept
-            // behind tuning key 6 = 1.
+            // The look-ahead of the odd step covers TWO block columns, so that the even step of the next pair (which brings the
+            // second of them up to date) never touches what the paired bulk update is writing and does not have to wait for it.
+            // Measured at n = 5000: 4.03 ms paired against 4.04 ms unpaired -- the rank-256 CTAs live twice as long, and the
+            // one-CTA diagonal-block kernel (215 KB of shared memory: it needs a whole SM) then waits ~25 us for an SM to drain
+            // at every other step, which returns what the better GEMM rate gains.  Opt-in: tuning key 6 = 1.
             const bool pair_second = pair_open;
-            const bool pair_first = !pair_open && g_tuning[6] == 1 && jb == CHOL_NB && rem > PAIR_MIN_REM;   // opt-in, see below
+            const bool pair_first = !pair_open && g_tuning[6] == 1 && jb == CHOL_NB && rem > PAIR_MIN_REM;
+            const int la_cols = pair_second ? min(2 * CHOL_NB, rem) : nb1;       // width of the look-ahead
             const int kcols = pair_second ? 2 * CHOL_NB : jb;                    // K of this step's updates
             const double* P = pair_second ? A21 - CHOL_NB : A21;                 // [rem x kcols] panel(s), row stride lda
-            // (a) next block column on the main stream: A22[:, 0:nb1] -= P . P[0:nb1]^T
+            // (a) next block column(s) on the main stream: A22[:, 0:la_cols] -= P . P[0:la_cols]^T
             if (!pair_first) PPBO_CUDA_CHECK(cudaEventRecord(g_chol.panel_done[b & 1], st));     // panels final: (b) may start
-            if (side_busy) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[last_rest], 0));
-            {
-                GemmOperands g{P, lda, 0, P, lda, 0, rem, nb1, kcols};
+            if (side_busy && !pair_first) PPBO_CUDA_CHECK(cudaStreamWaitEvent(st, g_chol.rest_done[last_rest], 0));
+            rc = (la_cols == CHOL_NB && kcols == CHOL_NB && !pdl)
+                     ? launch_rowpanel128(P, lda, P, lda, A22, lda, A22, lda, rem, -1.0, 1.0, st) : 0;
+            if (rc < 0) return rc;
+            if (rc == 0) {
+                GemmOperands g{P, lda, 0, P, lda, 0, rem, la_cols, kcols};
                 StoreEpilogue ep{A22, lda, 0, -1.0, 1.0, 0, 0};
                 g_launch_pdl = pdl;
-            rc = launch_gemm_nt(g, ep, 1, st);
-            g_launch_pdl = false;
+                rc = launch_gemm_nt(g, ep, 1, st);
+                g_launch_pdl = false;
                 if (rc) return rc;
             }
             if (tl) { cudaEventRecord(ev_l[b], st); has_l[b] = true; }
@@ -734,10 +851,10 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
                 PPBO_CUDA_CHECK(cudaStreamWaitEvent(g_chol.side, g_chol.panel_done[b & 1], 0));
                 if (tl) { cudaEventRecord(ev_r0[b], g_chol.side); has_r[b] = true; }
                 {
-                    const int r2 = rem - nb1;
-                    const double* P2 = P + (long long)nb1 * lda;
+                    const int r2 = rem - la_cols;
+                    const double* P2 = P + (long long)la_cols * lda;
                     GemmOperands g{P2, lda, 0, P2, lda, 0, r2, r2, kcols};
-                    StoreEpilogue ep{A22 + (long long)nb1 * lda + nb1, lda, 0, -1.0, 1.0, 1, 0};
+                    StoreEpilogue ep{A22 + (long long)la_cols * lda + la_cols, lda, 0, -1.0, 1.0, 1, 0};
                     rc = launch_gemm_nt(g, ep, 1, g_chol.side);
                     if (rc) return rc;
                 }
@@ -1234,7 +1351,7 @@ using namespace ppbo;
 extern "C" int ppbo_version(void) { return 100; }
 extern "C" long long ppbo_launch_count(void) { return g_launch_count; }
 extern "C" int ppbo_set_tuning(int key, int value) {
-    PPBO_REQUIRE(key >= 0 && key < 8, "tuning key");
+    PPBO_REQUIRE(key >= 0 && key < 16, "tuning key");
     g_tuning[key] = value;
     return PPBO_OK;
 }

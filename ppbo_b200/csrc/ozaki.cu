@@ -30,7 +30,7 @@
 #include "common.cuh"
 
 namespace ppbo {
-extern int g_tuning[8];
+extern int g_tuning[16];
 namespace oz {
 
 constexpr int BM = 128;                      // rows of the A tile = TMEM lanes

@@ -37,12 +37,17 @@ def main():
             _lib.load().ppbo_set_tuning(6, 1)
             t1 = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
             _lib.load().ppbo_set_tuning(6, 0)
-            print("potrf n=%d, paired (rank-256) trailing updates for large remainders: %.3f ms" % (n, t1))
+            print("potrf n=%d, paired rank-256 trailing updates with a two-column look-ahead: %.3f ms" % (n, t1))
         if n >= 2000:
             _lib.load().ppbo_set_tuning(7, 1)
             t1 = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
             _lib.load().ppbo_set_tuning(7, 0)
             print("potrf n=%d, programmatic dependent launch on the critical path: %.3f ms" % (n, t1))
+        if n >= 2000:
+            _lib.load().ppbo_set_tuning(8, 1)
+            t1 = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
+            _lib.load().ppbo_set_tuning(8, 0)
+            print("potrf n=%d, general GEMM kernel for panel and look-ahead: %.3f ms" % (n, t1))
         t = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
         if "--timeline" in sys.argv:
             W.copy_(A)
