@@ -307,10 +307,17 @@ int gemv(const double* A, long long lda, int M, int N, const double* x, double* 
 // ~35 us per block against ~300 us for a column-by-column version with three block barriers per column.
 constexpr int PAIR_MIN_REM = 2048;                    // remainders above this defer / pair their trailing updates (K = 256)
 constexpr int POTF2_THREADS = 512;
-constexpr int POTF2_LDS = CHOL_NB + 1;                 // row stride of the 128 x 128 work matrix
+// Row strides == 4 (mod 16) doubles: the 8-byte DMMA fragment loads of a half-warp (8 rows x 4 consecutive k, or 4 k-rows x 8
+// columns) then hit 16 distinct bank pairs.  With the odd strides used before (129 / 65 / 33) they were 3-4-way conflicted and the
+// tensor-pipe phases of the diagonal-block kernel were shared-memory bound (80.6k -> 70.5k clocks per block); lane-per-row accesses
+// (the warp Cholesky's 32 loads and stores, the row-wise sub-panel solve) are 4-way conflicted instead.
+// Tried and not kept (measured): sub-panel on the tensor pipe after the inversion (73.0k: the extra accumulators push the
+// kernel over its 128-register budget and the inversion spills), block rows of the inverse finished next to the inversion instead
+// of next to the pivot chain (85.4k).
+constexpr int POTF2_LDS = CHOL_NB + 4;                 // row stride of the 128 x 128 work matrix
 constexpr int POTF2_SUB = 32;
-constexpr int POTF2_LDR = POTF2_SUB + 1;               // row stride of the 32 x 32 inverse blocks
-constexpr int POTF2_LDT = 64 + 1;                      // row stride of the scratch matrix (up to 96 x 32 or 64 x 64)
+constexpr int POTF2_LDR = POTF2_SUB + 4;               // row stride of the 32 x 32 inverse blocks
+constexpr int POTF2_LDT = 64 + 4;                      // row stride of the scratch matrix (up to 96 x 32 or 64 x 64)
 constexpr int POTF2_SMEM_DOUBLES = CHOL_NB * POTF2_LDS + 4 * POTF2_SUB * POTF2_LDR + 96 * POTF2_LDT;
 
 // C[i][j] = (acc ? C[i][j] : 0) + sign * sum_k A[i][k] * (B_KMAJOR ? B[k][j] : B[j][k]),  i < m, j < n, all in shared memory.
@@ -641,7 +648,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) potf2_inv_kernel(double* __rest
     }
     __syncthreads();
     POTF2_STAMP();
-    constexpr int LDT3 = 97;                                // row stride of the 32 x 96 product of the last block row
+    constexpr int LDT3 = 100;                               // row stride of the 32 x 96 product of the last block row
     for (int sb = 0; sb < 4; ++sb) {
         const int c0 = sb * POTF2_SUB, c1 = c0 + POTF2_SUB, rem = CHOL_NB - c1;
         double* S11 = S + c0 * POTF2_LDS + c0;
