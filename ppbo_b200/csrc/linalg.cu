@@ -259,6 +259,110 @@ static int launch_rowpanel128(const double* A, long long lda, const double* Bm, 
     return 1;
 }
 
+// ------------------------------------------------------------------------------------------- rank-128 update of the trailing matrix
+// C[lower tiles] -= P P^T with P = [n x 128] (row stride ldp), C = [n x n] (row stride ldc): the bulk of every Cholesky step.
+// The general kernel runs this shape at ~17-20 TFLOP/s (55 % of the DMMA peak): with K = 128 a 128 x 64 tile moves 320 KB
+// through L2 for 2.1 MFLOP, its 3-stage ring is barely filled before the 8 k-tiles are over, and C is only requested in the
+// epilogue.  Here a CTA takes a 128 x 64 tile, brings both operand panels completely into shared memory (four 32-column
+// cp.async groups, compute starts on the first), requests its C fragments up front and gives every warp a 32 x 32 register tile
+// (8 fragment loads per 16 DMMA).  Tiles that touch the lower triangle only; a tile on the diagonal is computed in full (the
+// strictly upper part of the matrix is never read).
+constexpr int SY_BM = 128, SY_BN = 64, SY_THREADS = 256;
+constexpr int SY_SMEM_BYTES = (SY_BM + SY_BN) * RP_LD * 8;
+__global__ void __launch_bounds__(SY_THREADS) syrk128_kernel(const double* __restrict__ P, long long ldp, double* __restrict__ C,
+                                                             long long ldc, int n) {
+    extern __shared__ __align__(16) double sy_smem[];
+    double* As = sy_smem;                      // [128][RP_LD]  rows of the row tile
+    double* Bs = sy_smem + SY_BM * RP_LD;      // [64][RP_LD]   rows of the column tile
+    // tile (ti, tj): row tile ti owns column tiles 0 .. 2 ti + 1
+    const long long L = blockIdx.x;
+    int ti = (int)((sqrt(1.0 + 4.0 * (double)L) - 1.0) * 0.5);
+    while ((long long)(ti + 1) * (ti + 2) <= L) ++ti;
+    while ((long long)ti * (ti + 1) > L) --ti;
+    const int tj = (int)(L - (long long)ti * (ti + 1));
+    const int m0 = ti * SY_BM, n0 = tj * SY_BN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int i = 0; i < SY_BM * 16 / SY_THREADS; ++i) {
+            const int c = tid + i * SY_THREADS, row = c >> 4, kc = (c & 15) * 2 + 32 * g, gr = m0 + row;
+            cp_async_zfill<16>(As + row * RP_LD + kc, gr < n ? P + (long long)gr * ldp + kc : P, gr < n ? 16 : 0);
+        }
+#pragma unroll
+        for (int i = 0; i < SY_BN * 16 / SY_THREADS; ++i) {
+            const int c = tid + i * SY_THREADS, row = c >> 4, kc = (c & 15) * 2 + 32 * g, gr = n0 + row;
+            cp_async_zfill<16>(Bs + row * RP_LD + kc, gr < n ? P + (long long)gr * ldp + kc : P, gr < n ? 16 : 0);
+        }
+        cp_async_commit();
+    }
+    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;       // 4 x 2 warps, 32 x 32 each
+    double2 cin[4][4];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int r = m0 + wm0 + mi * 8 + gq, c = n0 + wn0 + ni * 8 + 2 * t4;
+            cin[mi][ni] = (r < n && c + 1 < n) ? *reinterpret_cast<const double2*>(C + (long long)r * ldc + c)
+                                               : make_double2((r < n && c < n) ? C[(long long)r * ldc + c] : 0.0, 0.0);
+        }
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const double* Ap = As + (wm0 + gq) * RP_LD + t4;
+    const double* Bp = Bs + (wn0 + gq) * RP_LD + t4;
+    auto chunk = [&](int g) {
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+            const int k = 32 * g + 4 * k4;
+            double a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * RP_LD + k];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[ni * 8 * RP_LD + k];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+        }
+    };
+    cp_async_wait<3>(); __syncthreads(); chunk(0);
+    cp_async_wait<2>(); __syncthreads(); chunk(1);
+    cp_async_wait<1>(); __syncthreads(); chunk(2);
+    cp_async_wait<0>(); __syncthreads(); chunk(3);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int r = m0 + wm0 + mi * 8 + gq, c = n0 + wn0 + ni * 8 + 2 * t4;
+            if (r >= n) continue;
+            double* o = C + (long long)r * ldc + c;
+            if (c + 1 < n) *reinterpret_cast<double2*>(o) = make_double2(cin[mi][ni].x - acc[mi][ni][0], cin[mi][ni].y - acc[mi][ni][1]);
+            else if (c < n) o[0] = cin[mi][ni].x - acc[mi][ni][0];
+        }
+}
+
+// 1: launched, 0: operands do not qualify (caller falls back to the general kernel), < 0: error
+static int launch_syrk128(const double* P, long long ldp, double* C, long long ldc, int n, cudaStream_t st) {
+    if (g_tuning[9] == 1) return 0;                       // tuning key 9 = 1: general GEMM kernel (comparison)
+    if (n <= 0) return 1;
+    if (!(aligned16(P) && aligned16(C) && ldp % 2 == 0 && ldc % 2 == 0)) return 0;
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] { err = cudaFuncSetAttribute(syrk128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES); });
+    PPBO_CUDA_CHECK(err);
+    const long long tm = ceil_div(n, SY_BM);
+    long long tiles = 0;                                  // row tile ti: column tiles 0 .. min(2 ti + 1, last)
+    const long long tn = ceil_div(n, SY_BN);
+    (void)tn;
+    tiles = tm * (tm + 1);                                // sum over ti of 2 (ti + 1); a last, partly empty column tile only costs zeros
+    PPBO_CL syrk128_kernel<<<(unsigned)tiles, SY_THREADS, SY_SMEM_BYTES, st>>>(P, ldp, C, ldc, n);
+    PPBO_LAUNCH_CHECK();
+    return 1;
+}
+
 // ------------------------------------------------------------------------------------------- GEMV
 // y = A x, row-major A: one warp per row, 16-byte loads when aligned.  HBM-bound (8 M N bytes).
 __global__ void __launch_bounds__(256) gemv_kernel(const double* __restrict__ A, long long lda, int M, int N,
@@ -860,10 +964,15 @@ int potrf_lower(double* A, long long lda, int n, double* dinv, int* info_d, cuda
                 {
                     const int r2 = rem - la_cols;
                     const double* P2 = P + (long long)la_cols * lda;
-                    GemmOperands g{P2, lda, 0, P2, lda, 0, r2, r2, kcols};
-                    StoreEpilogue ep{A22 + (long long)la_cols * lda + la_cols, lda, 0, -1.0, 1.0, 1, 0};
-                    rc = launch_gemm_nt(g, ep, 1, g_chol.side);
-                    if (rc) return rc;
+                    double* C2 = A22 + (long long)la_cols * lda + la_cols;
+                    rc = (kcols == CHOL_NB) ? launch_syrk128(P2, lda, C2, lda, r2, g_chol.side) : 0;
+                    if (rc < 0) return rc;
+                    if (rc == 0) {
+                        GemmOperands g{P2, lda, 0, P2, lda, 0, r2, r2, kcols};
+                        StoreEpilogue ep{C2, lda, 0, -1.0, 1.0, 1, 0};
+                        rc = launch_gemm_nt(g, ep, 1, g_chol.side);
+                        if (rc) return rc;
+                    }
                 }
                 last_rest ^= 1;
                 PPBO_CUDA_CHECK(cudaEventRecord(g_chol.rest_done[last_rest], g_chol.side));
