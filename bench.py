@@ -206,8 +206,10 @@ def workload_config(prob, n_gpus):
                         "%d query directions x P=%d xi-grid points, S=%d samples" % (
                             prob["name"], prob["D"], prob["Q"], prob["m"], prob["N"], prob["Q"] * prob["m"], prob["kernel"],
                             prob["theta"], prob["F"], prob["grids"].shape[0], prob["P"], prob["S"]),
-            "parallelism": "GP fit on rank 0, weight-space fit on rank %d, broadcast of (omega_MAP, diag Hessian, mu*); S sharded over %d "
-                           "rank(s); one all-reduce of 3 x directions doubles" % (1 if n_gpus > 1 else 0, n_gpus),
+            "parallelism": ("GP fit + weight-space fit (background thread) + all S samples on one GPU" if n_gpus == 1 else
+                            "GP fit on rank 0 (no samples: it is the critical path), weight-space fit on rank 1, broadcast of (omega_MAP, "
+                            "diag Hessian); S sharded over ranks 1..%d, which sample while rank 0 fits; broadcast of mu*; one "
+                            "all-reduce of 3 x directions doubles" % (n_gpus - 1)),
             "l2_policy": "working set per step (Sigma, G, factor, Omega, PhiT: > 1 GB) exceeds the 126 MB L2; no explicit flush",
             "fit_start": "cold: GP Newton from f = 0; weight-space Newton from omega = 0, concurrently with the GP fit",
             "sampling_engine": "tcgen05 INT8, %d digit planes per operand (error-free splitting; FP64-GEMM accuracy)" % iteration_slices()}
@@ -305,7 +307,9 @@ def main():
         torch.cuda.synchronize()
         for (n0, a), (n1, b_) in zip(timers[:-1], timers[1:]):
             stage_ms.setdefault(n1, []).append(a.elapsed_time(b_))
-    lo, hi = shard.bounds(S)
+    lo, hi = shard.sample_bounds(S)
+    if hi == lo:                      # rank 0 of several takes no samples: time the launch a sampling rank performs
+        lo, hi = 0, S // max(1, world - 1)
     rffs = out[2]
     Omega = ops.rff_sample_omega(rffs.omega_map, rffs.hess_diag, hi - lo, seed=1234, sample0=lo)
     PhiT = iteration.rff_grid_features(resident["W"], resident["b"], theta[2], resident["grids"])

@@ -74,6 +74,17 @@ class Shard:
         hi = (S * (self.rank + 1)) // self.world
         return lo, hi
 
+    def sample_bounds(self, S):
+        """Partition of the Monte-Carlo samples inside run_iteration.  With more than one rank the rank that runs the GP fit
+        (rank 0) takes none: the sampling contraction does not depend on the GP fit -- only the final reduction needs mu* --
+        so the other ranks evaluate all samples WHILE rank 0 fits, and the GP fit is the critical path of the iteration anyway."""
+        if self.world == 1:
+            return 0, S
+        if self.rank == 0:
+            return 0, 0
+        w = self.world - 1
+        return (S * (self.rank - 1)) // w, (S * self.rank) // w
+
     def broadcast(self, t, src=0):
         if self.dist and self.world > 1:
             self.dist.broadcast(t, src=src, group=self.group)
@@ -171,12 +182,11 @@ def rff_grid_features(W, b, sigma_f, grids):
     return ops.rff_features(W, b, grids.reshape(B * P, D), sigma_f, feature_major=False).view(B, P, -1)
 
 
-def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_id=0):
-    """Sampled acquisition on B grids: per grid b the sums over the S samples of max(fmax - mu*, 0), fmax and fmax^2
-    (acquisition.EI / varmax, src/acquisition.py:78-81,176-178, with RFF posterior draws in place of the exact-GP MVN).
-    Returns (sums [B,3] reduced over all ranks, fmax [B,S_loc], arg [B,S_loc])."""
-    shard = shard or Shard()
-    lo, hi = shard.bounds(S)
+def rff_sampled_maxima(r, PhiT, lo, hi, Z=None, seed=0, stream_id=0):
+    """Posterior weight draws [lo, hi) of the sample stream evaluated on every grid: per-sample max and first arg-max over the grid
+    points, (fmax [B, hi-lo], arg [B, hi-lo]); (None, None) for an empty slice.  Needs the weight-space fit only -- not mu*."""
+    if hi <= lo:
+        return None, None
     Zloc = None if Z is None else Z[lo:hi]
     Omega = ops.rff_sample_omega(r.omega_map, r.hess_diag, hi - lo, Z=Zloc, seed=seed, stream_id=stream_id, sample0=lo)
     sliced = PhiT if isinstance(PhiT, SlicedGrids) else None
@@ -186,9 +196,29 @@ def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_i
                                               sliced_grid=(sliced.planes, sliced.scale) if sliced else None)
     else:
         fmax, arg, _ = ops.rff_eval_argmax(Omega, PhiT)
-    sums = ops.acq_reduce_dev(fmax, mustar_dev)
+    return fmax, arg
+
+
+def rff_reduce(fmax, mustar_dev, n_grids, shard=None):
+    """sums [B, 3] over all ranks' samples of max(fmax - mu*, 0), fmax, fmax^2 (one all-reduce of 3 B doubles)"""
+    shard = shard or Shard()
+    if fmax is not None:
+        sums = ops.acq_reduce_dev(fmax, mustar_dev)
+    else:
+        sums = torch.zeros((n_grids, 3), dtype=F64, device=mustar_dev.device)
     shard.all_reduce_sum(sums)
-    return sums, fmax, arg
+    return sums
+
+
+def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_id=0, bounds=None):
+    """Sampled acquisition on B grids: per grid b the sums over the S samples of max(fmax - mu*, 0), fmax and fmax^2
+    (acquisition.EI / varmax, src/acquisition.py:78-81,176-178, with RFF posterior draws in place of the exact-GP MVN).
+    Returns (sums [B,3] reduced over all ranks, fmax [B,S_loc], arg [B,S_loc]); bounds: this rank's samples (default: even split)."""
+    shard = shard or Shard()
+    lo, hi = bounds if bounds is not None else shard.bounds(S)
+    fmax, arg = rff_sampled_maxima(r, PhiT, lo, hi, Z=Z, seed=seed, stream_id=stream_id)
+    n_grids = (PhiT.PhiT if isinstance(PhiT, SlicedGrids) else PhiT).shape[0]
+    return rff_reduce(fmax, mustar_dev, n_grids, shard), fmax, arg
 
 
 def acquisition_values(sums, S):
@@ -264,17 +294,19 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
             ev.record()
             timers.append((name, ev))
     mark("start")
-    lo, hi = shard.bounds(S)
+    lo, hi = shard.sample_bounds(S)
     # The grid features (and their digit planes) do not depend on the fit.  On the rank that runs the latency-bound GP fit they
     # go to the side stream and fill SMs the fit leaves idle; the other ranks compute them while they wait for the broadcast.
     main = torch.cuda.current_stream()
     grid_stream = _side_stream(X.device, tag="grid") if shard.rank == 0 else main
     if grid_stream is not main:
         grid_stream.wait_stream(main)
+    PhiT = None
     with torch.cuda.stream(grid_stream):
-        PhiT = rff_grid_features(W, b, theta[2], grids)
-        if sampling_engine(hi - lo, P, Fdim) == "i8":
-            PhiT = SlicedGrids(PhiT)                          # digit planes of the grid features
+        if hi > lo:                                           # a rank without samples (rank 0 of several) needs no grid features
+            PhiT = rff_grid_features(W, b, theta[2], grids)
+            if sampling_engine(hi - lo, P, Fdim) == "i8":
+                PhiT = SlicedGrids(PhiT)                      # digit planes of the grid features
     mark("grid_features")
     pack = torch.empty(2 * Fdim + 1, dtype=F64, device=X.device)
     gp = rff = None
@@ -309,6 +341,43 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         for t in (rff.omega_map, rff.hess_diag, rff.Phi_X):
             t.record_stream(main)
         mark("rff_fit")                        # what is left of the weight-space fit after the GP fit has finished
+    elif shard.world > 1 and CONCURRENT_FITS:
+        # Several ranks: rank 0 runs the GP fit and nothing else; rank 1 runs the weight-space fit and broadcasts it; ranks >= 1
+        # draw and evaluate ALL samples while rank 0 is still fitting (the contraction needs the weight-space fit only); when
+        # mu* arrives from rank 0 only the reduction and the all-reduce of 3 B doubles are left.
+        pack_rff, mu_t = pack[:2 * Fdim], pack[2 * Fdim:]
+        if shard.rank == 0:
+            bstream = _side_stream(X.device, tag="bcast")     # rank 0 joins the first broadcast off its critical path
+            bstream.wait_stream(main)
+            pack.record_stream(bstream)
+            with torch.cuda.stream(bstream):
+                shard.broadcast(pack_rff, src=rff_rank)
+            gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
+            mark("gp_fit")
+            mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
+            mark("mustar")
+            mu_t.copy_(mustar)
+            main.wait_stream(bstream)
+            shard.broadcast(mu_t, src=0)
+            fmax = None
+        else:
+            if shard.rank == rff_rank:
+                rff = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+                mark("rff_fit")
+                pack_rff[:Fdim].copy_(rff.omega_map)
+                pack_rff[Fdim:].copy_(rff.hess_diag)
+            shard.broadcast(pack_rff, src=rff_rank)
+        if rff is None:
+            rff = RFFFit()
+            rff.W, rff.b, rff.sigma_f, rff.Phi_X, rff.stats = W, b, float(theta[2]), None, None
+        rff.omega_map, rff.hess_diag = pack_rff[:Fdim], pack_rff[Fdim:]
+        if shard.rank != 0:
+            fmax, _ = rff_sampled_maxima(rff, PhiT, lo, hi, seed=seed)
+            mark("sampling")
+            shard.broadcast(mu_t, src=0)
+        sums = rff_reduce(fmax, mu_t, B, shard)
+        mark("acquisition")
+        return sums, gp, rff
     else:
         if shard.rank == 0:
             gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
@@ -335,8 +404,9 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
     rff.omega_map, rff.hess_diag = pack[:Fdim], pack[Fdim:2 * Fdim]
     if grid_stream is not main:
         main.wait_stream(grid_stream)
-        for t in ((PhiT.PhiT, PhiT.planes, PhiT.scale) if isinstance(PhiT, SlicedGrids) else (PhiT,)):
-            t.record_stream(main)
-    sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed)
+        if PhiT is not None:
+            for t in ((PhiT.PhiT, PhiT.planes, PhiT.scale) if isinstance(PhiT, SlicedGrids) else (PhiT,)):
+                t.record_stream(main)
+    sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed, bounds=(lo, hi))
     mark("acquisition")
     return sums, gp, rff

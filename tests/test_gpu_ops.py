@@ -96,6 +96,34 @@ def test_potrf_and_trsm(ops, n):
     assert relerr(Y @ L.T, X) < 1e-11
 
 
+@pytest.mark.parametrize("n", [640, 1537, 2500, 4100])
+def test_potrf_specialised_kernels_match_general(ops, n):
+    """the row-panel x 128 x 128 kernel (panel, look-ahead) and the rank-128 trailing-update kernel against the general DMMA GEMM
+    kernel they replace on the Cholesky critical path (tuning keys 8 / 9), and both against the residual; odd n: general path only"""
+    from ppbo_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(n)
+    A0 = rng.randn(n, n // 2 + 1)
+    A = A0 @ A0.T + n * np.eye(n)
+    Ad = ops.to_dev(A)
+    info, ws = ops.potrf_lower(Ad)
+    assert info == 0
+    L1 = np.tril(_np(Ad))
+    lib.ppbo_set_tuning(8, 1)
+    lib.ppbo_set_tuning(9, 1)
+    try:
+        Bd = ops.to_dev(A)
+        info2, ws2 = ops.potrf_lower(Bd)
+    finally:
+        lib.ppbo_set_tuning(8, 0)
+        lib.ppbo_set_tuning(9, 0)
+    assert info2 == 0
+    L2 = np.tril(_np(Bd))
+    assert relerr(L1 @ L1.T, A) < 1e-13
+    assert relerr(L1, L2) < 1e-13
+    assert relerr(_np(ws)[: ((n + 127) // 128) * 128 * 128], _np(ws2)[: ((n + 127) // 128) * 128 * 128]) < 1e-12    # inverted diagonal blocks
+
+
 def test_potrf_reports_bad_pivot(ops):
     A = np.eye(200)
     A[150, 150] = -1.0

@@ -31,15 +31,21 @@ def _problem():
     return dict(F=F, D=D, P=P, B=B, S=S, W=W, b=b, grids=grids, omega_map=omega_map, hess=hess, mustar=0.01, sf=0.2, seed=99)
 
 
-def _partial_sums(p, lo, hi):
-    """what one rank computes: its samples [lo, hi) of the Philox stream on every grid"""
+def _sample_maxima(p, lo, hi):
+    """what one rank computes before mu* is known: the per-sample maxima of its samples [lo, hi) of the Philox stream on every grid"""
+    if hi <= lo:
+        return np.zeros((p["B"], 0))
     Z = O.philox_normals(p["seed"], 0, lo * p["F"], (hi - lo) * p["F"]).reshape(hi - lo, p["F"])
     Omega = O.rff_sample_omega(p["omega_map"], p["hess"], Z)
-    out = np.zeros((p["B"], 3))
-    for bi in range(p["B"]):
-        mx, _ = O.rff_eval_argmax(Omega, O.rff_features(p["W"], p["b"], p["grids"][bi], p["sf"]))
-        out[bi] = [np.maximum(mx - p["mustar"], 0).sum(), mx.sum(), (mx ** 2).sum()]
-    return out
+    return np.stack([O.rff_eval_argmax(Omega, O.rff_features(p["W"], p["b"], p["grids"][bi], p["sf"]))[0] for bi in range(p["B"])])
+
+
+def _reduce(mx, p):
+    return np.stack([np.maximum(mx - p["mustar"], 0).sum(1), mx.sum(1), (mx ** 2).sum(1)], axis=1)
+
+
+def _partial_sums(p, lo, hi):
+    return _reduce(_sample_maxima(p, lo, hi), p)
 
 
 def _worker(rank, world, port, q):
@@ -50,17 +56,23 @@ def _worker(rank, world, port, q):
         shard = Shard()
         assert (shard.rank, shard.world) == (rank, world)
         p = _problem()
-        # rank 0 "fits" and broadcasts (omega_MAP, hess_diag, mu*); the others start from garbage
+        # the protocol of iteration.run_iteration: rank 1 "fits" the weights and broadcasts (omega_MAP, hess_diag); ranks >= 1
+        # evaluate all samples; rank 0 "fits" the GP and broadcasts mu*; reduction + one all-reduce.  The others start from garbage.
         F = p["F"]
         pack = torch.zeros(2 * F + 1, dtype=torch.float64)
-        if rank == 0:
+        if rank == 1:
             pack[:F] = torch.from_numpy(p["omega_map"])
             pack[F:2 * F] = torch.from_numpy(p["hess"])
+        if rank == 0:
             pack[2 * F] = p["mustar"]
-        shard.broadcast(pack, src=0)
-        p["omega_map"], p["hess"], p["mustar"] = pack[:F].numpy(), pack[F:2 * F].numpy(), float(pack[2 * F])
-        lo, hi = shard.bounds(p["S"])
-        sums = torch.from_numpy(_partial_sums(p, lo, hi))
+        shard.broadcast(pack[:2 * F], src=1)
+        p["omega_map"], p["hess"] = pack[:F].numpy(), pack[F:2 * F].numpy()
+        lo, hi = shard.sample_bounds(p["S"])
+        assert (hi == lo) == (rank == 0)
+        Zmax = _sample_maxima(p, lo, hi)                     # before mu* is known
+        shard.broadcast(pack[2 * F:], src=0)
+        p["mustar"] = float(pack[2 * F])
+        sums = torch.from_numpy(_reduce(Zmax, p))
         shard.all_reduce_sum(sums)
         q.put((rank, lo, hi, sums.numpy()))
     finally:
@@ -81,7 +93,7 @@ def test_sample_sharding_reproduces_single_rank(world):
         assert pr.exitcode == 0
     p = _problem()
     full = _partial_sums(p, 0, p["S"])
-    res.sort()
+    res.sort(key=lambda t: t[0])
     assert res[0][1] == 0 and res[-1][2] == p["S"]
     for (r0, lo0, hi0, _), (r1, lo1, hi1, _) in zip(res[:-1], res[1:]):
         assert hi0 == lo1                                                   # contiguous, disjoint, complete
@@ -103,6 +115,13 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+            # the sample partition of run_iteration: the GP-fit rank takes none when there is more than one rank
+            edges = [Fake(r, world).sample_bounds(S) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == S
+            assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            if world > 1:
+                assert sizes[0] == 0 and max(sizes[1:]) - min(sizes[1:]) <= 1
 
 
 def test_philox_known_answers():
