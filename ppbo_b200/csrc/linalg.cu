@@ -344,21 +344,126 @@ __global__ void __launch_bounds__(SY_THREADS) syrk128_kernel(const double* __res
         }
 }
 
+// Strip version: ncu showed the tile kernel above with the tensor pipe active only 58 % of the time -- 31k clocks per 128 x 64 tile for
+// 16.4k clocks of DMMA, because a CTA that owns one tile (and the whole SM: 203 KB) cannot overlap its operand loads, its C
+// read-modify-write and its launch with anything.  Here a CTA keeps the 128-row operand panel resident and walks along a strip of up
+// to SY_STRIP column tiles of 32: the next 32 x 128 column panel (cp.async, double buffered) and the next C fragments are requested
+// while the current tile is on the tensor pipe, so the prologue is paid once per strip.
+constexpr int SYS_BN = 32, SY_STRIP = 8;
+constexpr int SYS_SMEM_BYTES = (SY_BM + 2 * SYS_BN) * RP_LD * 8;
+__global__ void __launch_bounds__(SY_THREADS) syrk128_strip_kernel(const double* __restrict__ P, long long ldp, double* __restrict__ C,
+                                                                   long long ldc, int n, int strip) {
+    extern __shared__ __align__(16) double sy_smem[];
+    double* As = sy_smem;                      // [128][RP_LD]
+    double* Bs = sy_smem + SY_BM * RP_LD;      // 2 x [32][RP_LD]
+    const int ti = gridDim.y - 1 - blockIdx.y, m0 = ti * SY_BM;    // long rows first: the tail of the launch is made of short strips
+    const int ncols = min(m0 + SY_BM, n);                          // columns 0 .. ncols-1 touch the lower triangle of this row tile
+    const int tiles = (ncols + SYS_BN - 1) / SYS_BN;
+    const int t_begin = blockIdx.x * strip, t_end = min(t_begin + strip, tiles);
+    if (t_begin >= tiles) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+    auto load_b = [&](int t, int buf) {                             // column panel of tile t: rows 32 t .. 32 t + 31 of P
+        double* dst = Bs + buf * SYS_BN * RP_LD;
+#pragma unroll
+        for (int i = 0; i < SYS_BN * 64 / SY_THREADS; ++i) {        // 32 rows x 64 chunks of 16 bytes
+            const int c = tid + i * SY_THREADS, row = c >> 6, kc = (c & 63) * 2, gr = t * SYS_BN + row;
+            cp_async_zfill<16>(dst + row * RP_LD + kc, gr < n ? P + (long long)gr * ldp + kc : P, gr < n ? 16 : 0);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < SY_BM * 64 / SY_THREADS; ++i) {
+        const int c = tid + i * SY_THREADS, row = c >> 6, kc = (c & 63) * 2, gr = m0 + row;
+        cp_async_zfill<16>(As + row * RP_LD + kc, gr < n ? P + (long long)gr * ldp + kc : P, gr < n ? 16 : 0);
+    }
+    load_b(t_begin, 0);
+    cp_async_commit();
+    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 16;       // 4 x 2 warps, 32 x 16 each
+    auto load_c = [&](int t, double2 (&cin)[4][2]) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const int r = m0 + wm0 + mi * 8 + gq, c = t * SYS_BN + wn0 + ni * 8 + 2 * t4;
+                cin[mi][ni] = (r < n && c + 1 < n) ? *reinterpret_cast<const double2*>(C + (long long)r * ldc + c)
+                                                   : make_double2((r < n && c < n) ? C[(long long)r * ldc + c] : 0.0, 0.0);
+            }
+    };
+    double2 cin[4][2], cnext[4][2];
+    load_c(t_begin, cin);
+    const double* Ap = As + (wm0 + gq) * RP_LD + t4;
+    for (int t = t_begin; t < t_end; ++t) {
+        const int buf = (t - t_begin) & 1;
+        cp_async_wait<0>();
+        __syncthreads();                                            // panel of tile t has landed; everyone is done with tile t-1
+        if (t + 1 < t_end) {
+            load_b(t + 1, buf ^ 1);
+            load_c(t + 1, cnext);
+        }
+        cp_async_commit();
+        double acc[4][2][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        const double* Bp = Bs + buf * SYS_BN * RP_LD + (wn0 + gq) * RP_LD + t4;
+#pragma unroll 8
+        for (int k = 0; k < 128; k += 4) {
+            double a[4], b[2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * RP_LD + k];
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) b[ni] = Bp[ni * 8 * RP_LD + k];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const int r = m0 + wm0 + mi * 8 + gq, c = t * SYS_BN + wn0 + ni * 8 + 2 * t4;
+                if (r < n) {
+                    double* o = C + (long long)r * ldc + c;
+                    if (c + 1 < n) *reinterpret_cast<double2*>(o) = make_double2(cin[mi][ni].x - acc[mi][ni][0], cin[mi][ni].y - acc[mi][ni][1]);
+                    else if (c < n) o[0] = cin[mi][ni].x - acc[mi][ni][0];
+                }
+                cin[mi][ni] = cnext[mi][ni];
+            }
+    }
+}
+
 // 1: launched, 0: operands do not qualify (caller falls back to the general kernel), < 0: error
 static int launch_syrk128(const double* P, long long ldp, double* C, long long ldc, int n, cudaStream_t st) {
-    if (g_tuning[9] == 1) return 0;                       // tuning key 9 = 1: general GEMM kernel (comparison)
+    if (g_tuning[9] == 1) return 0;                       // tuning key 9 = 1: general GEMM kernel; 2: one tile per CTA (comparison)
     if (n <= 0) return 1;
     if (!(aligned16(P) && aligned16(C) && ldp % 2 == 0 && ldc % 2 == 0)) return 0;
     static std::once_flag once;
     static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] { err = cudaFuncSetAttribute(syrk128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES); });
+    std::call_once(once, [] {
+        err = cudaFuncSetAttribute(syrk128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM_BYTES);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(syrk128_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SYS_SMEM_BYTES);
+    });
     PPBO_CUDA_CHECK(err);
-    const long long tm = ceil_div(n, SY_BM);
-    long long tiles = 0;                                  // row tile ti: column tiles 0 .. min(2 ti + 1, last)
-    const long long tn = ceil_div(n, SY_BN);
-    (void)tn;
-    tiles = tm * (tm + 1);                                // sum over ti of 2 (ti + 1); a last, partly empty column tile only costs zeros
-    PPBO_CL syrk128_kernel<<<(unsigned)tiles, SY_THREADS, SY_SMEM_BYTES, st>>>(P, ldp, C, ldc, n);
+    const int tm = ceil_div(n, SY_BM);
+    if (g_tuning[9] == 2) {
+        PPBO_CL syrk128_kernel<<<(unsigned)((long long)tm * (tm + 1)), SY_THREADS, SY_SMEM_BYTES, st>>>(P, ldp, C, ldc, n);
+    } else {
+        // strip length: one CTA per SM, so the launch takes ceil(items / SMs) rounds of (strip tiles + one panel load); pick the
+        // length that minimises that (ncu: 26 % of the SM time was idle tail with a fixed length of 8 at n = 4480)
+        int strip = SY_STRIP;
+        double best = 1e300;
+        for (int sl = 3; sl <= 12; ++sl) {
+            long long items = 0;
+            for (int t = 0; t < tm; ++t) items += ceil_div(ceil_div(min((t + 1) * SY_BM, n), SYS_BN), sl);
+            const double cost = (double)ceil_div_ll(items, PPBO_SM_COUNT) * (sl * 8.2 + 6.0);
+            if (cost < best) { best = cost; strip = sl; }
+        }
+        if (g_tuning[10] > 0) strip = g_tuning[10];
+        const int max_strips = ceil_div(ceil_div(min(tm * SY_BM, n), SYS_BN), strip);
+        PPBO_CL syrk128_strip_kernel<<<dim3(max_strips, tm), SY_THREADS, SYS_SMEM_BYTES, st>>>(P, ldp, C, ldc, n, strip);
+    }
     PPBO_LAUNCH_CHECK();
     return 1;
 }

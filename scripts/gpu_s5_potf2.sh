@@ -1,1 +1,2 @@
-python scripts/ubench_ops.py --no-rowmax --timeline --potrf-only > gpurun_out/ubench_potf2.log 2>&1; grep "potf2 phases\|potrf n=5000:\|warp potrf32 sub0\|phase 2" gpurun_out/ubench_potf2.log | head -60
+python scripts/ubench_ops.py --no-rowmax --timeline --potrf-only > gpurun_out/ubench_potf2.log 2>&1; grep "potrf n=" gpurun_out/ubench_potf2.log | head -20
+grep -A 42 "potrf timeline n=5000" gpurun_out/ubench_potf2.log | awk 'NR==1||NR%4==2'

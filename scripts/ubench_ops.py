@@ -48,6 +48,13 @@ def main():
             t1 = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
             _lib.load().ppbo_set_tuning(8, 0)
             print("potrf n=%d, general GEMM kernel for panel and look-ahead: %.3f ms" % (n, t1))
+        if n >= 2000:
+            for key, val, label in ((9, 1, "general GEMM kernel for the trailing update"), (9, 2, "one-tile trailing-update kernel"),
+                                    (10, 4, "strip trailing-update kernel, strips of 4"), (10, 16, "strip trailing-update kernel, strips of 16")):
+                _lib.load().ppbo_set_tuning(key, val)
+                t1 = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
+                _lib.load().ppbo_set_tuning(key, 0)
+                print("potrf n=%d, %s: %.3f ms" % (n, label, t1))
         t = timeit(lambda: ops.potrf_lower(W), setup=lambda: W.copy_(A))
         if "--timeline" in sys.argv:
             W.copy_(A)
