@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(256) lik_terms_kernel(const double* __restrict
                                                         double* __restrict__ set_lik, double* __restrict__ beta,
                                                         double* __restrict__ arrow, double* __restrict__ sa,
                                                         double* __restrict__ bvec, const double* __restrict__ ap_fixed = nullptr,
-                                                        double* __restrict__ ap_out = nullptr) {
+                                                        double* __restrict__ ap_out = nullptr, const double* __restrict__ skip = nullptr) {
+    if (skip && *skip != 0.0) return;          // queued chord step behind the one that stopped the batch
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= Q) return;
     const long long base = (long long)q * (m + 1);
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ x,
 
 // t[u] = sa[u] * (v[r(u)] - v[w(u)])                       (a+^1/2 B^T v)
 __global__ void diff_scale_kernel(const double* __restrict__ v, const double* __restrict__ sa, int Q, int m,
-                                  double* __restrict__ t) {
+                                  double* __restrict__ t, const double* __restrict__ skip = nullptr) {
+    if (skip && *skip != 0.0) return;
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= Q * m) return;
     const int q = u / m, j = u % m;
@@ -90,7 +92,9 @@ __global__ void diff_scale_kernel(const double* __restrict__ v, const double* __
 // alpha_new = b - B (sa .* y);  dalpha = alpha_new - alpha  (one warp per set)
 __global__ void __launch_bounds__(256) alpha_update_kernel(const double* __restrict__ bvec, const double* __restrict__ sa,
                                                            const double* __restrict__ y, const double* __restrict__ alpha,
-                                                           int Q, int m, double* __restrict__ dalpha) {
+                                                           int Q, int m, double* __restrict__ dalpha,
+                                                           const double* __restrict__ skip = nullptr) {
+    if (skip && *skip != 0.0) return;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= Q) return;
     const long long base = (long long)q * (m + 1);
@@ -170,21 +174,45 @@ __global__ void axpy2_kernel(double* __restrict__ alpha, const double* __restric
     }
 }
 
+// Likelihood sums of a queued chord step at its step length omega = state[7]:  part[q] = sum_j Phi~(Delta_qj(f + omega df))
+__global__ void __launch_bounds__(256) chord_lik_kernel(const double* __restrict__ f, const double* __restrict__ df, int Q, int m,
+                                                        double sigma, const double* __restrict__ state, double* __restrict__ part) {
+    if (state[4] != 0.0) return;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const double step = state[7];
+    const long long base = (long long)q * (m + 1);
+    const double fw = f[base] + step * df[base];
+    const double inv_s = 1.0 / sigma;
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) s += Phi_tilde((f[base + 1 + j] + step * df[base + 1 + j] - fw) * inv_s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) part[q] = s;
+}
+
 // Device-side acceptance test of one chord step, so that a batch of chord steps runs without a host round trip (a host decision
-// per step left the launch queue empty after every synchronise: ~0.5 ms per step against ~0.3 ms of kernel time).
-//   state[0] T at the current iterate   state[1] relative size of the last step   state[2] the one before   state[3] last |step|
-//   state[4] 0 = keep going, 1 = converged, 2 = step taken but contraction too slow (refactor), 3 = step rejected (refactor)
-//   state[5] chord steps taken in this batch      state[6] tolerance            hist[2i], hist[2i+1] = (rel, T) of step i
-// A chord step is only ever taken at full length: T(alpha + dalpha) must not fall below T (same rule as the host line search
-// with c == 0).  When state[4] != 0 the kernel does nothing; the other kernels of a queued step only write scratch vectors.
+// per step left the launch queue empty after every synchronise: ~0.5 ms per step against ~0.25 ms of kernel time).
+//   state[0] T at the current iterate   state[1] relative size of the last residual   state[2] the one before   state[3] last |df|
+//   state[4] 0 = keep going, 1 = converged, 2 = contraction too slow (refactor), 3 = full step rejected (refactor)
+//   state[5] chord steps taken in this batch      state[6] tolerance         state[7] step length omega of the queued step
+//   state[8] previous contraction ratio           state[9] steps to wait before the next extrapolation
+//   hist[2i], hist[2i+1] = (rel, T) of step i
+// A chord step of length 1 is only taken when T(alpha + dalpha) does not fall below T (same rule as the host line search with
+// c == 0).  When state[4] != 0 this kernel and every other kernel of a queued step return at once (skip flag).
+//
+// Extrapolation: the chord iteration is a linear fixed-point iteration near the mode; once two successive contraction ratios
+// agree to 8 % a single eigen-direction dominates the error and the NEXT step is taken with omega = 1 / (1 - ratio) (Aitken's
+// delta-squared written as a step length, capped at 2), which removes that direction in one step.  An extrapolated step that
+// lowers T is not taken: the step is repeated with omega = 1.
 __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__ alpha, const double* __restrict__ dalpha,
                                                             double* __restrict__ f, const double* __restrict__ df, int N,
                                                             const double* __restrict__ part, int Q, int m,
-                                                            double* __restrict__ state, double* __restrict__ hist) {
+                                                            double* __restrict__ state, double* __restrict__ hist, int extrapolate) {
     __shared__ double red[33];
     __shared__ double mx[2][32];
-    __shared__ int accept_s;
+    __shared__ double step_s;
     if (state[4] != 0.0) return;                    // uniform: state[4] is only written after the barriers below
+    const double omega = state[7];
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mdf = 0, mf = 0, lik = 0;
     for (int i = threadIdx.x; i < N; i += 1024) {
         const double a = alpha[i], da = dalpha[i], fi = f[i], dfi = df[i];
@@ -210,12 +238,14 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
     if (threadIdx.x == 0) {
         for (int w = 1; w < 32; ++w) { mdf = fmax(mdf, mx[0][w]); mf = fmax(mf, mx[1][w]); }
         const double T_cur = state[0];
-        const double T1 = -0.5 * (s0 + (s1 + s2) + s3) - lik / m;
-        const int accept = T1 >= T_cur - 1e-13 * fabs(T_cur);
-        accept_s = accept;
+        const double T1 = -0.5 * (s0 + omega * (s1 + s2) + omega * omega * s3) - lik / m;
+        const bool accept = T1 >= T_cur - 1e-13 * fabs(T_cur);
+        double step = 0.0;
         if (!accept) {
-            state[4] = 3.0;
+            if (omega != 1.0) { state[7] = 1.0; state[9] = 4.0; }      // repeat this step at full length, no extrapolation for a while
+            else state[4] = 3.0;
         } else {
+            step = omega;
             const double rel = mdf / fmax(mf, 1e-300), prev = state[1];
             const int n = (int)state[5];
             state[0] = T1;
@@ -225,15 +255,32 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
             state[5] = n + 1;
             hist[2 * n] = rel;
             hist[2 * n + 1] = T1;
-            if (rel <= state[6]) state[4] = 1.0;
-            else if (!(rel <= 0.5 * prev)) state[4] = 2.0;
+            const double ratio = rel / prev, ratio_prev = state[8];
+            double wait = state[9], next_omega = 1.0;
+            const bool after_extrapolation = omega != 1.0;
+            if (rel <= state[6]) {
+                state[4] = 1.0;
+            } else if (!after_extrapolation && wait <= 0.0 && !(rel <= 0.5 * prev)) {
+                state[4] = 2.0;                                        // plain steps contract too slowly: pay for a new factor
+            } else if (wait > 0.0 && !(rel <= 4.0 * prev)) {
+                state[4] = 2.0;                                        // residual grows after an extrapolation: give up on this factor
+            } else if (extrapolate && !after_extrapolation && wait <= 0.0 && ratio > 0.02 && ratio < 0.6 &&
+                       fabs(ratio - ratio_prev) <= 0.08 * ratio) {
+                next_omega = fmin(1.0 / (1.0 - ratio), 2.0);
+                wait = 3.0;                                            // the ratios right after an extrapolation say nothing
+            }
+            state[8] = after_extrapolation ? 0.0 : ratio;
+            state[9] = fmax(wait - 1.0, 0.0);
+            state[7] = next_omega;
         }
+        step_s = step;
     }
     __syncthreads();
-    if (!accept_s) return;
+    const double step = step_s;
+    if (step == 0.0) return;
     for (int i = threadIdx.x; i < N; i += 1024) {
-        alpha[i] += dalpha[i];
-        f[i] += df[i];
+        alpha[i] = fma(step, dalpha[i], alpha[i]);
+        f[i] = fma(step, df[i], f[i]);
     }
 }
 
@@ -272,7 +319,7 @@ int launch_sum(const double* x, int n, double* out, cudaStream_t st) {
     return PPBO_OK;
 }
 
-constexpr int CHORD_STATE = 8, CHORD_BATCH_MAX = 16;
+constexpr int CHORD_STATE = 16, CHORD_BATCH_MAX = 16;
 
 struct FitWorkspace {
     double *bvec, *sa, *ap, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp, *binv, *state, *hist;
@@ -371,6 +418,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     // solves), which makes every later solve with that factor ~3x cheaper than the 40-link chained solve
     bool binv_valid = false;
     bool first_chord_batch = true;
+    // tuning: PPBO_CHORD_EXTRAPOLATE=0 switches the Aitken step lengths off (diagnostics)
+    const bool chord_extrapolate = !(getenv("PPBO_CHORD_EXTRAPOLATE") && atoi(getenv("PPBO_CHORD_EXTRAPOLATE")) == 0);
+    double chord_omega = 1.0, chord_ratio = 0.0, chord_wait = 0.0;
     while (it < max_iter) {
         if (!refactor) {
             // ---- a batch of chord steps: the factor is kept, only the right-hand side is refreshed; acceptance, the convergence
@@ -386,18 +436,20 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             if (first_chord_batch) kb = std::min(kb, 3);
             kb = std::max(1, std::min(kb, std::min(CHORD_BATCH_MAX, max_iter - it)));
             first_chord_batch = false;
-            double state_h[CHORD_STATE] = {T_cur, last_rel, prev_rel_h, last_step, 0.0, 0.0, tol, 0.0};
+            double state_h[CHORD_STATE] = {T_cur, last_rel, prev_rel_h, last_step, 0.0, 0.0, tol, chord_omega, chord_ratio, chord_wait};
             double hist_h[2 * CHORD_BATCH_MAX];
             PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.state, state_h, sizeof(state_h), cudaMemcpyHostToDevice, st));
+            const double* skip = ws.state + 4;               // non-zero once a step of the batch has stopped it
             for (int i = 0; i < kb; ++i) {
-                PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr);
-                if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
-                PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
-                if ((rc = potrs_vec_blockinv(Lfac, M, M, ws.binv, ws.t, st))) return rc;
-                PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);
-                if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st))) return rc;
-                PPBO_CL linesearch_lik_kernel<<<dim3(set_blocks, 1), 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.set_part);
-                PPBO_CL chord_decide_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, m, ws.state, ws.hist);
+                PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr, skip);
+                if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st, skip))) return rc;
+                PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t, skip);
+                if ((rc = potrs_vec_blockinv(Lfac, M, M, ws.binv, ws.t, st, skip))) return rc;
+                PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha, skip);
+                if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st, skip))) return rc;
+                PPBO_CL chord_lik_kernel<<<set_blocks, 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.state, ws.set_part);
+                PPBO_CL chord_decide_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, m, ws.state, ws.hist,
+                                                                  chord_extrapolate ? 1 : 0);
             }
             PPBO_LAUNCH_CHECK();
             PPBO_CUDA_CHECK(cudaMemcpyAsync(state_h, ws.state, sizeof(state_h), cudaMemcpyDeviceToHost, st));
@@ -415,6 +467,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 prev_rel_h = state_h[2];
                 last_step = state_h[3];
             }
+            chord_omega = state_h[7];
+            chord_ratio = state_h[8];
+            chord_wait = state_h[9];
             if (stop == 1) { converged = true; break; }
             if (stop == 2 || stop == 3) refactor = true;      // contraction too slow / step rejected: pay for a new factor
             continue;
@@ -429,6 +484,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
             ++n_factor;
             binv_valid = false;
+            chord_omega = 1.0;                   // a new factor: new iteration matrix, forget the contraction history
+            chord_ratio = 0.0;
+            chord_wait = 0.0;
         }
         if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
         PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);

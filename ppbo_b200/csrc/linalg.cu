@@ -470,8 +470,12 @@ static int launch_syrk128(const double* P, long long ldp, double* C, long long l
 
 // ------------------------------------------------------------------------------------------- GEMV
 // y = A x, row-major A: one warp per row, 16-byte loads when aligned.  HBM-bound (8 M N bytes).
+// skip (here and in the block-inverse solve kernels): optional device flag; a non-zero value turns the launch into a no-op.  The
+// chord steps of the Newton iterations are queued in batches, and the steps behind the one that converged must cost nothing.
 __global__ void __launch_bounds__(256) gemv_kernel(const double* __restrict__ A, long long lda, int M, int N,
-                                                   const double* __restrict__ x, double* __restrict__ y, int vec) {
+                                                   const double* __restrict__ x, double* __restrict__ y, int vec,
+                                                   const double* __restrict__ skip) {
+    if (skip && *skip != 0.0) return;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int row = warp; row < M; row += nwarps) {
@@ -496,11 +500,11 @@ __global__ void __launch_bounds__(256) gemv_kernel(const double* __restrict__ A,
     }
 }
 
-int gemv(const double* A, long long lda, int M, int N, const double* x, double* y, cudaStream_t st) {
+int gemv(const double* A, long long lda, int M, int N, const double* x, double* y, cudaStream_t st, const double* skip) {
     if (M <= 0) return PPBO_OK;
     const int vec = aligned16(A) && aligned16(x) && lda % 2 == 0;
     const int blocks = min(ceil_div(M, 8), PPBO_SM_COUNT * 8);
-    PPBO_CL gemv_kernel<<<blocks, 256, 0, st>>>(A, lda, M, N, x, y, vec);
+    PPBO_CL gemv_kernel<<<blocks, 256, 0, st>>>(A, lda, M, N, x, y, vec, skip);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -1433,8 +1437,10 @@ int blockinv_build(const double* L, long long ldl, int n, const double* dinv, do
 // The other triangle of Mat holds exact zeros; v is only read inside [c_lo, c_hi) (the tail behind the block may hold anything).
 constexpr int BTRI_ROWS = 2;
 __global__ void __launch_bounds__(128 * BTRI_ROWS) blocktri_gemv_kernel(const double* __restrict__ Mat, const double* __restrict__ v,
-                                                                        double* __restrict__ out, int rows, int upper) {
+                                                                        double* __restrict__ out, int rows, int upper,
+                                                                        const double* __restrict__ skip) {
     __shared__ double part[BTRI_ROWS][4];
+    if (skip && *skip != 0.0) return;
     const int sub = threadIdx.x >> 7, t = threadIdx.x & 127, lane = threadIdx.x & 31, w = t >> 5;
     const int r = blockIdx.x * BTRI_ROWS + sub;
     const bool vec = (reinterpret_cast<uintptr_t>(Mat) & 15) == 0;          // workspace carving may leave Mat 8-byte aligned
@@ -1463,7 +1469,9 @@ __global__ void __launch_bounds__(128 * BTRI_ROWS) blocktri_gemv_kernel(const do
 }
 // forward sweep: t[r] -= sum_{c < cols} L[r][c0 + c] y[c] for r in [r0, n); warp per row
 __global__ void __launch_bounds__(256) blockrow_update_kernel(const double* __restrict__ L, long long ldl, int r0, int n, int c0,
-                                                              int cols, const double* __restrict__ y, double* __restrict__ t) {
+                                                              int cols, const double* __restrict__ y, double* __restrict__ t,
+                                                              const double* __restrict__ skip) {
+    if (skip && *skip != 0.0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = r0 + blockIdx.x * 8 + warp;
     if (r >= n) return;
@@ -1487,8 +1495,9 @@ __global__ void __launch_bounds__(256) blockrow_update_kernel(const double* __re
 constexpr int BCOL_WARPS = 32;
 __global__ void __launch_bounds__(BCOL_WARPS * 32) blockcol_update_kernel(const double* __restrict__ L, long long ldl, int r0, int r1,
                                                                           int c1, const double* __restrict__ x,
-                                                                          double* __restrict__ y) {
+                                                                          double* __restrict__ y, const double* __restrict__ skip) {
     __shared__ double part[BCOL_WARPS][33];
+    if (skip && *skip != 0.0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * 32 + lane;
     double s[8];
@@ -1519,7 +1528,7 @@ __global__ void __launch_bounds__(BCOL_WARPS * 32) blockcol_update_kernel(const 
 }
 
 // (L L^T) x = t in place with the block inverses W of blockinv_build
-int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st) {
+int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip) {
     const int nbI = ceil_div(n, BI);
     const long long BB = (long long)BI * BI;
     const double* Binv = W;
@@ -1527,15 +1536,15 @@ int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double*
     double* y = W + nbI * (3 * BB + BB / 4);
     for (int J = 0; J < nbI; ++J) {                     // L y = t
         const int j0 = J * BI, rows = min(BI, n - j0), j1 = j0 + rows;
-        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, BTRI_ROWS), 128 * BTRI_ROWS, 0, st>>>(Binv + J * BB, t + j0, y + j0, rows, 0);
+        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, BTRI_ROWS), 128 * BTRI_ROWS, 0, st>>>(Binv + J * BB, t + j0, y + j0, rows, 0, skip);
         if (j1 < n)
-            PPBO_CL blockrow_update_kernel<<<ceil_div(n - j1, 8), 256, 0, st>>>(L, ldl, j1, n, j0, rows, y + j0, t);
+            PPBO_CL blockrow_update_kernel<<<ceil_div(n - j1, 8), 256, 0, st>>>(L, ldl, j1, n, j0, rows, y + j0, t, skip);
     }
     for (int J = nbI - 1; J >= 0; --J) {                // L^T x = y
         const int j0 = J * BI, rows = min(BI, n - j0);
-        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, BTRI_ROWS), 128 * BTRI_ROWS, 0, st>>>(BinvT + J * BB, y + j0, t + j0, rows, 1);
+        PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, BTRI_ROWS), 128 * BTRI_ROWS, 0, st>>>(BinvT + J * BB, y + j0, t + j0, rows, 1, skip);
         if (j0 > 0)
-            PPBO_CL blockcol_update_kernel<<<ceil_div(j0, 32), BCOL_WARPS * 32, 0, st>>>(L, ldl, j0, j0 + rows, j0, t + j0, y);
+            PPBO_CL blockcol_update_kernel<<<ceil_div(j0, 32), BCOL_WARPS * 32, 0, st>>>(L, ldl, j0, j0 + rows, j0, t + j0, y, skip);
     }
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;

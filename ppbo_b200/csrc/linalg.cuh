@@ -17,7 +17,7 @@ int trsm_right_lower_t(const double* L, long long ldl, int n, const double* dinv
 // block-inverse solves for factors that serve many right-hand sides (see linalg.cu)
 long long blockinv_doubles(int n);
 int blockinv_build(const double* L, long long ldl, int n, const double* dinv, double* W, cudaStream_t st);
-int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st);
-int gemv(const double* A, long long lda, int M, int N, const double* x, double* y, cudaStream_t st);
+int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip = nullptr);
+int gemv(const double* A, long long lda, int M, int N, const double* x, double* y, cudaStream_t st, const double* skip = nullptr);
 
 }  // namespace ppbo
