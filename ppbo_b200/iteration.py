@@ -182,20 +182,43 @@ def rff_grid_features(W, b, sigma_f, grids):
     return ops.rff_features(W, b, grids.reshape(B * P, D), sigma_f, feature_major=False).view(B, P, -1)
 
 
-def rff_sampled_maxima(r, PhiT, lo, hi, Z=None, seed=0, stream_id=0):
-    """Posterior weight draws [lo, hi) of the sample stream evaluated on every grid: per-sample max and first arg-max over the grid
-    points, (fmax [B, hi-lo], arg [B, hi-lo]); (None, None) for an empty slice.  Needs the weight-space fit only -- not mu*."""
+class SlicedSamples:
+    """Digit planes of the posterior weight draws [lo, hi) (the A operand of the INT8 sampling contraction)."""
+    __slots__ = ("planes", "scale", "count", "slices")
+
+    def __init__(self, Omega, slices=None):
+        self.slices = SAMPLING_SLICES if slices is None else slices
+        self.count = Omega.shape[0]
+        self.planes, self.scale = ops.ozaki_slice(Omega, 0, self.slices)
+
+
+def rff_prepare_samples(r, lo, hi, P, Z=None, seed=0, stream_id=0):
+    """Draws [lo, hi) of the sample stream, already in the form the contraction consumes (digit planes for the INT8 engine, the
+    FP64 matrix otherwise).  Needs the weight-space fit only, so run_iteration does this while the GP fit is still running."""
     if hi <= lo:
-        return None, None
+        return None
     Zloc = None if Z is None else Z[lo:hi]
     Omega = ops.rff_sample_omega(r.omega_map, r.hess_diag, hi - lo, Z=Zloc, seed=seed, stream_id=stream_id, sample0=lo)
+    return SlicedSamples(Omega) if sampling_engine(hi - lo, P, r.omega_map.shape[0]) == "i8" else Omega
+
+
+def rff_sampled_maxima(r, PhiT, lo, hi, Z=None, seed=0, stream_id=0, prepared=None):
+    """Posterior weight draws [lo, hi) of the sample stream evaluated on every grid: per-sample max and first arg-max over the grid
+    points, (fmax [B, hi-lo], arg [B, hi-lo]); (None, None) for an empty slice.  Needs the weight-space fit only -- not mu*.
+    prepared: the result of rff_prepare_samples for the same slice."""
+    if hi <= lo:
+        return None, None
     sliced = PhiT if isinstance(PhiT, SlicedGrids) else None
     PhiT = sliced.PhiT if sliced is not None else PhiT
-    if sliced is not None or sampling_engine(hi - lo, PhiT.shape[1], PhiT.shape[2]) == "i8":
-        fmax, arg, _ = ops.rff_eval_argmax_i8(Omega, PhiT, slices=sliced.slices if sliced else SAMPLING_SLICES,
-                                              sliced_grid=(sliced.planes, sliced.scale) if sliced else None)
+    B, P, Fdim = PhiT.shape
+    if prepared is None:
+        prepared = rff_prepare_samples(r, lo, hi, P, Z=Z, seed=seed, stream_id=stream_id)
+    if isinstance(prepared, SlicedSamples):
+        bp, bsc = (sliced.planes, sliced.scale) if sliced is not None else ops.ozaki_slice(PhiT, 1, prepared.slices)
+        err = torch.zeros(1, dtype=torch.int32, device=PhiT.device)
+        fmax, arg, _ = ops.ozaki_rowmax(prepared.planes, prepared.scale, prepared.count, bp, bsc, P, B, Fdim, prepared.slices, err=err)
     else:
-        fmax, arg, _ = ops.rff_eval_argmax(Omega, PhiT)
+        fmax, arg, _ = ops.rff_eval_argmax(prepared, PhiT)
     return fmax, arg
 
 
@@ -210,13 +233,13 @@ def rff_reduce(fmax, mustar_dev, n_grids, shard=None):
     return sums
 
 
-def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_id=0, bounds=None):
+def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_id=0, bounds=None, prepared=None):
     """Sampled acquisition on B grids: per grid b the sums over the S samples of max(fmax - mu*, 0), fmax and fmax^2
     (acquisition.EI / varmax, src/acquisition.py:78-81,176-178, with RFF posterior draws in place of the exact-GP MVN).
     Returns (sums [B,3] reduced over all ranks, fmax [B,S_loc], arg [B,S_loc]); bounds: this rank's samples (default: even split)."""
     shard = shard or Shard()
     lo, hi = bounds if bounds is not None else shard.bounds(S)
-    fmax, arg = rff_sampled_maxima(r, PhiT, lo, hi, Z=Z, seed=seed, stream_id=stream_id)
+    fmax, arg = rff_sampled_maxima(r, PhiT, lo, hi, Z=Z, seed=seed, stream_id=stream_id, prepared=prepared)
     n_grids = (PhiT.PhiT if isinstance(PhiT, SlicedGrids) else PhiT).shape[0]
     return rff_reduce(fmax, mustar_dev, n_grids, shard), fmax, arg
 
@@ -309,7 +332,7 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
                 PhiT = SlicedGrids(PhiT)                      # digit planes of the grid features
     mark("grid_features")
     pack = torch.empty(2 * Fdim + 1, dtype=F64, device=X.device)
-    gp = rff = None
+    gp = rff = prepared = None
     rff_rank = 1 if (CONCURRENT_FITS and shard.world > 1) else 0      # with more than one GPU the two fits run on two of them
     if shard.rank == 0 and CONCURRENT_FITS and shard.world == 1:
         # GP fit: foreground, on a stream one priority level above the default; weight-space fit: a persistent background host
@@ -323,7 +346,9 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         def weight_space_fit():
             torch.cuda.set_device(X.device)
             with torch.cuda.stream(side):
-                return rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+                fit = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+                # the draws and their digit planes need this fit only: done here, behind the GP fit
+                return fit, rff_prepare_samples(fit, lo, hi, P, seed=seed)
         fut = _background_worker().submit(weight_space_fit)
         try:
             with torch.cuda.stream(gp_stream):
@@ -332,13 +357,14 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
                 mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
                 mark("mustar")
         finally:
-            rff = fut.result()                 # re-raises on this thread
+            rff, prepared = fut.result()       # re-raises on this thread
         if gp_stream is not main:
             main.wait_stream(gp_stream)
             for t in (gp.Sigma, gp.lap.G, gp.lap.Lfac, gp.lap.f_map, gp.lap.alpha, gp.lap.arrow, mustar):
                 t.record_stream(main)
         main.wait_stream(side)
-        for t in (rff.omega_map, rff.hess_diag, rff.Phi_X):
+        for t in (rff.omega_map, rff.hess_diag, rff.Phi_X) + ((prepared.planes, prepared.scale) if isinstance(prepared, SlicedSamples)
+                                                              else ((prepared,) if prepared is not None else ())):
             t.record_stream(main)
         mark("rff_fit")                        # what is left of the weight-space fit after the GP fit has finished
     elif shard.world > 1 and CONCURRENT_FITS:
@@ -407,6 +433,6 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         if PhiT is not None:
             for t in ((PhiT.PhiT, PhiT.planes, PhiT.scale) if isinstance(PhiT, SlicedGrids) else (PhiT,)):
                 t.record_stream(main)
-    sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed, bounds=(lo, hi))
+    sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed, bounds=(lo, hi), prepared=prepared)
     mark("acquisition")
     return sums, gp, rff
