@@ -14,6 +14,8 @@
 
 namespace ppbo {
 
+int kernel_matvec(int kind, const double* X1, int n1, const double* X2, int n2, int D, const double* ls_h, double sigma_f,
+                  const double* alpha, double* mu, double* partial, cudaStream_t st);
 int kernel_matrix_raw(int kind, const double* X1, int n1, const double* X2, int n2, int D, const double* ls_h,
                       double sigma_f, double scale, double diag_add, double* out, long long ld, cudaStream_t st);
 
@@ -389,6 +391,12 @@ extern "C" int ppbo_predict(int kind, const double* X, int N, int D, const doubl
     double* Ut = Kc + (long long)PT * N;             // [PT x M]
     double* Ud = Ut + (long long)PT * M;             // [PT x r]
     int rc;
+    if (!Sigma_p) {                                  // mean only: no need for the PT x N cross-covariance in memory
+        if (!mu) return PPBO_OK;
+        rc = kernel_matvec(kind, Xp, PT, X, N, D, lengthscales_h, sigma_f, alpha, mu, Kc, st);
+        if (rc < 0) return rc;
+        if (rc == 1) return PPBO_OK;
+    }
     if ((rc = kernel_matrix_raw(kind, Xp, PT, X, N, D, lengthscales_h, sigma_f, 1.0, 0.0, Kc, N, st))) return rc;
     if (mu && (rc = gemv(Kc, N, PT, N, alpha, mu, st))) return rc;
     if (!Sigma_p) return PPBO_OK;

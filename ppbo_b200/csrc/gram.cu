@@ -9,8 +9,11 @@
 // coalesced stores.
 #include "../../include/ppbo_b200.h"
 #include "common.cuh"
+#include "gemm_f64.cuh"
 
 namespace ppbo {
+
+extern int g_tuning[16];
 
 struct KernelParams {
     int kind, D;
@@ -178,6 +181,164 @@ __global__ void __launch_bounds__(KT_THREADS, 2) kernel_matrix_tiled_kernel(cons
     }
 }
 
+// ---- SE / RQ kernels on the FP64 tensor pipe ------------------------------------------------------------------------------
+// The scaled squared distance is formed the way the reference's kernels.dist does (src/kernels.py:3-11),
+//   r2 = |x|^2 + |y|^2 - 2 x.y   clipped at 0,
+// with the cross term as a DMMA product (D FMAs per pair instead of the 2 D of the difference form, 0.03 shared-memory loads per
+// FMA).  Both point sets are shifted by the first point of X2 before scaling, which keeps |x|^2 (and with it the cancellation
+// error 2.2e-16 (|x|^2 + |y|^2) of the expansion) at the squared diameter of the data in length-scale units.  What is left per
+// entry is one exp: the kernel is bound by the FP64 exp rate (801 G/s measured) and the store bandwidth.
+// Modes:  KM_STORE     out[i][j] = k(x_i, y_j)                              (cross-covariances)
+//         KM_SYMMETRIC X1 == X2: lower tiles only, every off-diagonal tile is also written transposed (+ fused shrinkage)
+//         KM_MATVEC    partial[i][tile] = sum_{j in tile} k(x_i, y_j) alpha_j   (posterior mean without materialising the matrix)
+constexpr int KM_B = 128, KM_BN = 64, KM_THREADS = 256;        // 128 x 64 tiles, 8 warps of 32 x 32: two CTAs per SM, so that
+                                                                  // one CTA's stores overlap the other's exps
+enum { KM_STORE = 0, KM_SYMMETRIC = 1, KM_MATVEC = 2 };
+__host__ __device__ inline int km_ldx(int D) { const int Dp = (D + 3) / 4 * 4; return (Dp % 8 == 4) ? Dp : Dp + 4; }
+
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_mma_kernel(const double* __restrict__ X1, int n1,
+                                                                       const double* __restrict__ X2, int n2, KernelParams p,
+                                                                       double* __restrict__ out, long long ld,
+                                                                       const double* __restrict__ alpha, int ntile_cols) {
+    extern __shared__ __align__(16) double sm[];
+    const int D = p.D, Dp = (D + 3) / 4 * 4, LDX = km_ldx(D);
+    double* Xs = sm;                       // [128][LDX] rows of X1: (x - c) / l, zero-padded dims
+    double* Ys = Xs + KM_B * LDX;          // [64][LDX] rows of X2
+    double* nx = Ys + KM_BN * LDX;         // [128] squared norms
+    double* ny = nx + KM_B;                // [64]
+    int ti, tj;
+    if (MODE == KM_SYMMETRIC) {            // tiles that touch the lower triangle, row-tile major: row tile ti owns column tiles 0 .. 2 ti + 1
+        const long long L = blockIdx.x;
+        ti = (int)((sqrt(1.0 + 4.0 * (double)L) - 1.0) * 0.5);
+        while ((long long)(ti + 1) * (ti + 2) <= L) ++ti;
+        while ((long long)ti * (ti + 1) > L) --ti;
+        tj = (int)(L - (long long)ti * (ti + 1));
+    } else {
+        ti = blockIdx.y;
+        tj = blockIdx.x;
+    }
+    const int m0 = ti * KM_B, c0 = tj * KM_BN;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < KM_B * LDX; e += KM_THREADS) {
+        const int r = e / LDX, d = e % LDX, g1 = m0 + r, g2 = c0 + r;
+        const double c = d < D ? X2[d] : 0.0;                                  // shift: first point of X2
+        Xs[e] = (g1 < n1 && d < D) ? (X1[(long long)g1 * D + d] - c) * p.inv_ls[d] : 0.0;
+        if (r < KM_BN) Ys[e] = (g2 < n2 && d < D) ? (X2[(long long)g2 * D + d] - c) * p.inv_ls[d] : 0.0;
+    }
+    __syncthreads();
+    if (tid < KM_B + KM_BN) {
+        const double* v = tid < KM_B ? Xs + tid * LDX : Ys + (tid - KM_B) * LDX;
+        double s = 0.0;
+        for (int d = 0; d < Dp; ++d) s = fma(v[d], v[d], s);
+        if (tid < KM_B) nx[tid] = s;
+        else ny[tid - KM_B] = s;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;       // 4 x 2 warps
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const double* Ap = Xs + (wm0 + gq) * LDX + t4;
+    const double* Bp = Ys + (wn0 + gq) * LDX + t4;
+    for (int k = 0; k < Dp; k += 4) {
+        double a[4], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * LDX + k];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[ni * 8 * LDX + k];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+    }
+    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        const int il = wm0 + mi * 8 + gq, gr = m0 + il;
+        const double ni2 = nx[il];
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) {
+            const int jl = wn0 + nn * 8 + 2 * t4, gc = c0 + jl;
+            double kv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double r2 = fmax(ni2 + ny[jl + e] - 2.0 * acc[mi][nn][e], 0.0);
+                kv[e] = p.diag_scale * kernel_from_sums(KIND, r2, p.sf2);
+                if (MODE == KM_SYMMETRIC && gr == gc + e) kv[e] = p.diag_scale * p.sf2 + p.diag_add;     // exact diagonal
+            }
+            if (MODE == KM_MATVEC) {
+                if (gc < n2) rowsum[mi] = fma(kv[0], alpha[gc], rowsum[mi]);
+                if (gc + 1 < n2) rowsum[mi] = fma(kv[1], alpha[gc + 1], rowsum[mi]);
+            } else {
+                if (gr < n1) {
+                    double* o = out + (long long)gr * ld + gc;
+                    if (gc + 1 < n2 && vec_ok) *reinterpret_cast<double2*>(o) = make_double2(kv[0], kv[1]);
+                    else {
+                        if (gc < n2) o[0] = kv[0];
+                        if (gc + 1 < n2) o[1] = kv[1];
+                    }
+                }
+                if (MODE == KM_SYMMETRIC && c0 + KM_BN <= m0 && gr < n1) {  // tile strictly below the diagonal block: mirror
+                                                                            // (8 consecutive doubles per (t4, e) across gq)
+                    if (gc < n2) out[(long long)gc * ld + gr] = kv[0];
+                    if (gc + 1 < n2) out[(long long)(gc + 1) * ld + gr] = kv[1];
+                }
+            }
+        }
+    }
+    if (MODE == KM_MATVEC) {
+        __syncthreads();                                   // Xs is dead: reuse it as the [128][2] cross-warp buffer
+        double* red = Xs;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            double v = rowsum[mi];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t4 == 0) red[(wm0 + mi * 8 + gq) * 2 + (warp & 1)] = v;
+        }
+        __syncthreads();
+        if (tid < KM_B && m0 + tid < n1)
+            out[(long long)(m0 + tid) * ntile_cols + tj] = red[tid * 2] + red[tid * 2 + 1];
+    }
+}
+
+// mu[r] = sum_c partial[r][c] in a fixed order
+__global__ void __launch_bounds__(256) km_rowsum_kernel(const double* __restrict__ partial, int n, int nc, double* __restrict__ mu) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < nc; ++c) s += partial[(long long)r * nc + c];
+    mu[r] = s;
+}
+
+template <int KIND>
+static int launch_kernel_matrix_mma(const KernelParams& p, const double* X1, int n1, const double* X2, int n2, double* out,
+                                    long long ld, int mode, const double* alpha, cudaStream_t st) {
+    const size_t smem = (size_t)((KM_B + KM_BN) * km_ldx(p.D) + KM_B + KM_BN) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        const int max_smem = ((KM_B + KM_BN) * km_ldx(PPBO_MAX_D) + KM_B + KM_BN) * (int)sizeof(double);
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_mma_kernel<KIND, KM_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_mma_kernel<KIND, KM_SYMMETRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_mma_kernel<KIND, KM_MATVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_done = true;
+    }
+    const int tm = ceil_div(n1, KM_B), tn = ceil_div(n2, KM_BN);
+    if (mode == KM_SYMMETRIC)
+        PPBO_CL kernel_matrix_mma_kernel<KIND, KM_SYMMETRIC><<<(unsigned)((long long)tm * (tm + 1)), KM_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, nullptr, 0);
+    else if (mode == KM_MATVEC)
+        PPBO_CL kernel_matrix_mma_kernel<KIND, KM_MATVEC><<<dim3(tn, tm), KM_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, alpha, tn);
+    else
+        PPBO_CL kernel_matrix_mma_kernel<KIND, KM_STORE><<<dim3(tn, tm), KM_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, nullptr, 0);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
 static int fill_params(KernelParams& p, int kind, int D, const double* ls_h, double sigma_f) {
     PPBO_REQUIRE(kind >= 0 && kind <= 2, "unknown kernel kind");
     PPBO_REQUIRE(D >= 1 && D <= PPBO_MAX_D, "D must be in [1, 64]");
@@ -212,6 +373,15 @@ int kernel_matrix(const KernelParams& p, const double* X1, int n1, const double*
         PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_tiled_kernel<PPBO_KERNEL_RQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_done = true;
     }
+    if (g_tuning[11] == 0 && (p.kind == PPBO_KERNEL_SE || p.kind == PPBO_KERNEL_RQ)) {     // tuning key 11 = 1: difference-form kernels
+        const int mode = (symmetric_diag && X1 == X2 && n1 == n2) ? KM_SYMMETRIC : KM_STORE;
+        KernelParams q = p;
+        if (mode != KM_SYMMETRIC) q.diag_add = 0.0;
+        if (symmetric_diag && mode != KM_SYMMETRIC) goto general;       // diagonal term on a non-aliased pair: keep the old path
+        return p.kind == PPBO_KERNEL_SE ? launch_kernel_matrix_mma<PPBO_KERNEL_SE>(q, X1, n1, X2, n2, out, ld, mode, nullptr, st)
+                                        : launch_kernel_matrix_mma<PPBO_KERNEL_RQ>(q, X1, n1, X2, n2, out, ld, mode, nullptr, st);
+    }
+general:
     const int Dp = (p.D + KR_DC - 1) / KR_DC * KR_DC;
     const size_t smem_t = (size_t)(KT_M + KT_N) * Dp * sizeof(double);
     switch (p.kind) {
@@ -237,6 +407,23 @@ int kernel_matrix_raw(int kind, const double* X1, int n1, const double* X2, int 
     p.diag_scale = scale;
     p.diag_add = diag_add;
     return kernel_matrix(p, X1, n1, X2, n2, out, ld, diag_add != 0.0, st);
+}
+
+// mu[i] = sum_j k(X1_i, X2_j) alpha_j without materialising the n1 x n2 matrix (GPModel.mu_pred batched, src/gp_model.py:454-458);
+// partial: n1 * ceil(n2 / 64) doubles of scratch.  Returns 1 when done, 0 when the kernel kind has no tensor-pipe version.
+int kernel_matvec(int kind, const double* X1, int n1, const double* X2, int n2, int D, const double* ls_h, double sigma_f,
+                  const double* alpha, double* mu, double* partial, cudaStream_t st) {
+    if (g_tuning[11] != 0 || !(kind == PPBO_KERNEL_SE || kind == PPBO_KERNEL_RQ)) return 0;
+    KernelParams p;
+    int rc = fill_params(p, kind, D, ls_h, sigma_f);
+    if (rc) return rc;
+    if (n1 <= 0) return 1;
+    rc = kind == PPBO_KERNEL_SE ? launch_kernel_matrix_mma<PPBO_KERNEL_SE>(p, X1, n1, X2, n2, partial, 0, KM_MATVEC, alpha, st)
+                                : launch_kernel_matrix_mma<PPBO_KERNEL_RQ>(p, X1, n1, X2, n2, partial, 0, KM_MATVEC, alpha, st);
+    if (rc) return rc;
+    PPBO_CL km_rowsum_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(partial, n1, ceil_div(n2, KM_BN), mu);
+    PPBO_LAUNCH_CHECK();
+    return 1;
 }
 
 // ---- SE kernel gradients w.r.t. log length-scales and log sigma_f --------------------------------------
