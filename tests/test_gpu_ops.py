@@ -50,6 +50,39 @@ def test_kernel_matrix_ragged_and_empty(ops):
             assert relerr(K, O.se_kernel(X1, X2, [0, 0.3, 0.7])) < 1e-12
 
 
+@pytest.mark.parametrize("kernel", ["SE_kernel", "RQ_kernel"])
+def test_kernel_matrix_tensor_pipe_vs_difference_form(ops, kernel):
+    """the DMMA kernels (|x|^2 + |y|^2 - 2 x.y, shifted; lower tiles + mirrored stores; mat-vec mode for the posterior mean)
+    against the difference-form kernels they replace (tuning key 11) and the oracle, on ragged sizes"""
+    import torch
+    from oracle import ppbo_oracle as O
+    from ppbo_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(3)
+    for n, n2, D, ls in ((1, 1, 1, 0.3), (63, 65, 2, 0.26), (129, 200, 6, 0.26), (700, 333, 20, 0.3), (517, 1, 7, 0.05)):
+        X, Y = ops.to_dev(rng.rand(n, D)), ops.to_dev(rng.rand(n2, D))
+        alpha = ops.to_dev(rng.randn(n))
+        res = {}
+        for key in (1, 0):
+            lib.ppbo_set_tuning(11, key)
+            try:
+                S = ops.gram_regularized(kernel, X, ls, 0.7, 1e-6)
+                K = ops.kernel_matrix(kernel, Y, X, ls, 0.7)
+                res[key] = (_np(S), _np(K))
+            finally:
+                lib.ppbo_set_tuning(11, 0)
+        assert relerr(res[0][0], res[1][0]) < 1e-12 and relerr(res[0][1], res[1][1]) < 1e-12
+        assert np.array_equal(res[0][0], res[0][0].T)                      # symmetric by construction
+        assert np.all(np.diag(res[0][0]) == np.diag(res[1][0]))            # exact diagonal (kernel value + shrinkage term)
+        if kernel == "SE_kernel":
+            assert relerr(res[0][1], O.se_kernel(_np(Y), _np(X), [0, ls, 0.7])) < 1e-12
+            # mat-vec mode (mean-only prediction) against the materialised product
+            fit = type("F", (), dict(Q=n, m=0, alpha=alpha, arrow=None, Lfac=None, neg_corr=None, n_neg=0))()
+            mu, _ = ops.predict(kernel, X, ls, 0.7, 1e-6, fit, Y, n2, 1, want_cov=False)
+            ref = res[1][1] @ _np(alpha)
+            assert np.abs(_np(mu).ravel() - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300) + 1e-13 * np.abs(_np(alpha)).sum()
+
+
 def test_se_kernel_ard_and_gradients(ops):
     """ARD generalises the reference's isotropic kernel; gradients are checked by finite differences of the oracle."""
     from oracle import ppbo_oracle as O
