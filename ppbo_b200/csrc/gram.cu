@@ -191,8 +191,9 @@ __global__ void __launch_bounds__(KT_THREADS, 2) kernel_matrix_tiled_kernel(cons
 // Modes:  KM_STORE     out[i][j] = k(x_i, y_j)                              (cross-covariances)
 //         KM_SYMMETRIC X1 == X2: lower tiles only, every off-diagonal tile is also written transposed (+ fused shrinkage)
 //         KM_MATVEC    partial[i][tile] = sum_{j in tile} k(x_i, y_j) alpha_j   (posterior mean without materialising the matrix)
-constexpr int KM_B = 128, KM_BN = 64, KM_THREADS = 256;        // 128 x 64 tiles, 8 warps of 32 x 32: two CTAs per SM, so that
-                                                                  // one CTA's stores overlap the other's exps
+constexpr int KM_B = 128, KM_BN = 64, KM_THREADS = 512;        // 128 x 64 tiles, 16 warps of 32 x 16, two CTAs per SM: the exp
+                                                                  // polynomials of the epilogue are bound by FP64 latency, so the
+                                                                  // kernel wants resident warps (32 per SM) more than big register tiles
 enum { KM_STORE = 0, KM_SYMMETRIC = 1, KM_MATVEC = 2 };
 __host__ __device__ inline int km_ldx(int D) { const int Dp = (D + 3) / 4 * 4; return (Dp % 8 == 4) ? Dp : Dp + 4; }
 
@@ -236,24 +237,24 @@ __global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_mma_kernel(const 
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
-    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;       // 4 x 2 warps
-    double acc[4][4][2];
+    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;       // 4 x 4 warps, 32 x 16 each
+    double acc[4][2][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     const double* Ap = Xs + (wm0 + gq) * LDX + t4;
     const double* Bp = Ys + (wn0 + gq) * LDX + t4;
     for (int k = 0; k < Dp; k += 4) {
-        double a[4], b[4];
+        double a[4], b[2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * LDX + k];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[ni * 8 * LDX + k];
+        for (int ni = 0; ni < 2; ++ni) b[ni] = Bp[ni * 8 * LDX + k];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+            for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
     }
     const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_mma_kernel(const 
         const int il = wm0 + mi * 8 + gq, gr = m0 + il;
         const double ni2 = nx[il];
 #pragma unroll
-        for (int nn = 0; nn < 4; ++nn) {
+        for (int nn = 0; nn < 2; ++nn) {
             const int jl = wn0 + nn * 8 + 2 * t4, gc = c0 + jl;
             double kv[2];
 #pragma unroll
@@ -292,18 +293,18 @@ __global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_mma_kernel(const 
         }
     }
     if (MODE == KM_MATVEC) {
-        __syncthreads();                                   // Xs is dead: reuse it as the [128][2] cross-warp buffer
+        __syncthreads();                                   // Xs is dead: reuse it as the [128][4] cross-warp buffer
         double* red = Xs;
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
             double v = rowsum[mi];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (t4 == 0) red[(wm0 + mi * 8 + gq) * 2 + (warp & 1)] = v;
+            if (t4 == 0) red[(wm0 + mi * 8 + gq) * 4 + (warp & 3)] = v;
         }
         __syncthreads();
         if (tid < KM_B && m0 + tid < n1)
-            out[(long long)(m0 + tid) * ntile_cols + tj] = red[tid * 2] + red[tid * 2 + 1];
+            out[(long long)(m0 + tid) * ntile_cols + tj] = (red[tid * 4] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
     }
 }
 

@@ -1,2 +1,2 @@
 python scripts/gram_probe.py 2>&1 | tail -12
-python -m pytest tests -m gpu -q -x 2>&1 > gpurun_out/pytest_full.log; tail -3 gpurun_out/pytest_full.log
+python -m pytest tests/test_gpu_ops.py -m gpu -q -x -k "kernel or predict" 2>&1 | tail -3
