@@ -261,18 +261,27 @@ def main():
             return int(np.argmax(ei)), gp, rff
         return sums, gp, rff
 
+    step_marks = {}
+
     def timed_run(resident):
+        import gc
+        gc.collect()
+        gc.disable()                       # a generation-2 collection inside the timed region is a host hiccup, not the workload
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.ppbo_launch_count()
+        marks = [time.perf_counter()]
         e0.record()
         out = None
         for _ in range(args.steps):
             out = step(resident)
+            marks.append(time.perf_counter())      # host time after the step was issued (e2e: after its result arrived)
         e1.record()
         torch.cuda.synchronize()
+        gc.enable()
         ms = e0.elapsed_time(e1)
         launches = lib.ppbo_launch_count() - l0
+        step_marks["resident" if resident is not None else "e2e"] = [1e3 * (b - a) for a, b in zip(marks[:-1], marks[1:])]
         barrier()
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -375,6 +384,7 @@ def main():
         "clocks": clk,
         "roofline": roof,
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
+        "e2e_host_ms_per_step": [round(t, 2) for t in step_marks.get("e2e", [])],      # diagnostic: spread of the e2e steps
         "fit_newton_iterations": fit_iters, "rff_newton_iterations": rff_iters,
         "rff_sample_points_per_s": sample_points_per_s,
     }
