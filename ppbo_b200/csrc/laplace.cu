@@ -264,8 +264,10 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
                 state[4] = 2.0;                                        // plain steps contract too slowly: pay for a new factor
             } else if (wait > 0.0 && !(rel <= 4.0 * prev)) {
                 state[4] = 2.0;                                        // residual grows after an extrapolation: give up on this factor
-            } else if (extrapolate && !after_extrapolation && wait <= 0.0 && ratio > 0.02 && ratio < 0.6 &&
+            } else if (extrapolate && !after_extrapolation && wait <= 0.0 && ratio > 0.02 && ratio < 0.4 &&
                        fabs(ratio - ratio_prev) <= 0.08 * ratio) {
+                // (ratio < 0.4: with slower contraction the error is spread over many eigen-directions and the long step
+                // overshoots the others -- measured on a factor that contracted at 0.45: the residual rose after every extrapolation)
                 next_omega = fmin(1.0 / (1.0 - ratio), 2.0);
                 wait = 3.0;                                            // the ratios right after an extrapolation say nothing
             }
