@@ -169,8 +169,10 @@ __global__ void __launch_bounds__(256) rff_value_grad_kernel(const double* __res
 // into FV_SLICES slices so that ~8 x N/128 CTAs stream concurrently; slice partials are combined in a fixed order.
 constexpr int FV_SLICES = 8, FV_COLS = 128;
 __global__ void __launch_bounds__(256) rff_fvals_partial_kernel(const double* __restrict__ Phi, long long ld, int F, int N,
-                                                                const double* __restrict__ omega, double* __restrict__ part) {
+                                                                const double* __restrict__ omega, double* __restrict__ part,
+                                                                const double* __restrict__ skip) {
     __shared__ double red[FV_COLS];
+    if (skip && *skip != 0.0) return;          // queued chord step behind the one that stopped the batch (see ppbo_rff_fit)
     const int c = threadIdx.x & (FV_COLS - 1), half = threadIdx.x >> 7;          // 128 columns x 2 row phases
     const int i = blockIdx.x * FV_COLS + c;
     const int per = (F + FV_SLICES - 1) / FV_SLICES;
@@ -198,8 +200,8 @@ __global__ void __launch_bounds__(256) rff_fvals_combine_kernel(const double* __
 }
 // part: FV_SLICES * N doubles of scratch
 static int launch_rff_fvals(const double* Phi, long long ld, int F, int N, const double* omega, double* part, double* y,
-                            cudaStream_t st) {
-    PPBO_CL rff_fvals_partial_kernel<<<dim3(ceil_div(N, FV_COLS), FV_SLICES), 256, 0, st>>>(Phi, ld, F, N, omega, part);
+                            cudaStream_t st, const double* skip = nullptr) {
+    PPBO_CL rff_fvals_partial_kernel<<<dim3(ceil_div(N, FV_COLS), FV_SLICES), 256, 0, st>>>(Phi, ld, F, N, omega, part, skip);
     PPBO_CL rff_fvals_combine_kernel<<<ceil_div(N, 256), 256, 0, st>>>(part, N, y);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
@@ -209,7 +211,8 @@ static int launch_rff_fvals(const double* Phi, long long ld, int F, int N, const
 __global__ void __launch_bounds__(256) rff_grad_hess_kernel(const double* __restrict__ Phi, long long ld, int F, int Q, int m,
                                                             const double* __restrict__ omega, const double* __restrict__ beta,
                                                             const double* __restrict__ arrow, double* __restrict__ grad,
-                                                            double* __restrict__ hdiag) {
+                                                            double* __restrict__ hdiag, const double* __restrict__ skip) {
+    if (skip && *skip != 0.0) return;
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (f >= F) return;
     const double* ph = Phi + (long long)f * ld;
@@ -318,6 +321,43 @@ __global__ void __launch_bounds__(1024) rff_ls_scalars_kernel(const double* __re
         s = block_sum(s, red);
         if (threadIdx.x == 0) scal[8 + c] = s;
     }
+}
+
+// Device-side acceptance test of one weight-space chord step (same scheme as chord_decide_kernel of laplace.cu): the full step is
+// taken when S does not fall, convergence and contraction are tested here, and the host synchronises once per batch.
+//   state[0] S at the current iterate  state[1] relative size of the last step  state[2] the one before
+//   state[4] 0 = keep going, 1 = converged, 2 = contraction too slow (refactor), 3 = full step rejected (refactor)
+//   state[5] chord steps taken in this batch   state[6] tolerance    hist[2i], hist[2i+1] = (rel, S) of step i
+// scal: output of rff_ls_scalars_kernel for this step.
+__global__ void __launch_bounds__(256) rff_chord_decide_kernel(double* __restrict__ omega, const double* __restrict__ step, int F,
+                                                               const double* __restrict__ scal, int m, double* __restrict__ state,
+                                                               double* __restrict__ hist) {
+    __shared__ int accept_s;
+    if (state[4] != 0.0) return;
+    if (threadIdx.x == 0) {
+        const double oo = scal[0], od = scal[1], dd = scal[2], max_step = scal[3], max_om = fmax(scal[4], 1e-300);
+        const double S_cur = state[0];
+        const double S1 = -0.5 * (oo + 2.0 * od + dd) - scal[8] / m;
+        const int accept = S1 >= S_cur - 1e-13 * fabs(S_cur);
+        accept_s = accept;
+        if (!accept) {
+            state[4] = 3.0;
+        } else {
+            const double rel = max_step / max_om, prev = state[1];
+            const int n = (int)state[5];
+            state[0] = S1;
+            state[2] = prev;
+            state[1] = rel;
+            state[5] = n + 1;
+            hist[2 * n] = rel;
+            hist[2 * n + 1] = S1;
+            if (rel <= state[6]) state[4] = 1.0;
+            else if (!(rel <= 0.5 * prev)) state[4] = 2.0;
+        }
+    }
+    __syncthreads();
+    if (!accept_s) return;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) omega[i] += step[i];
 }
 
 }  // namespace ppbo
@@ -521,13 +561,13 @@ struct RffWs {
 };
 
 static int rff_eval(const double* Phi, long long ld, int F, int Q, int m, double sigma, const double* omega, RffWs& ws,
-                    double* grad, double* hdiag, bool want_arrow, double* lik_sum_dev, cudaStream_t st) {
+                    double* grad, double* hdiag, bool want_arrow, double* lik_sum_dev, cudaStream_t st, const double* skip = nullptr) {
     const int N = Q * (m + 1);
-    launch_rff_fvals(Phi, ld, F, N, omega, ws.fpart, ws.fvals, st);
+    launch_rff_fvals(Phi, ld, F, N, omega, ws.fpart, ws.fvals, st, skip);
     launch_lik_terms(ws.fvals, Q, m, sigma, ws.setlik, ws.beta, want_arrow ? ws.arrow : nullptr, nullptr, nullptr, st);
     launch_sum(ws.setlik, Q, lik_sum_dev, st);
     if (grad || hdiag)
-        PPBO_CL rff_grad_hess_kernel<<<ceil_div(F, 8), 256, 0, st>>>(Phi, ld, F, Q, m, omega, ws.beta, ws.arrow, grad, hdiag);
+        PPBO_CL rff_grad_hess_kernel<<<ceil_div(F, 8), 256, 0, st>>>(Phi, ld, F, Q, m, omega, ws.beta, ws.arrow, grad, hdiag, skip);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }
@@ -574,7 +614,57 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
     const double CHORD_REL = 0.25;
     const bool trace = getenv("PPBO_TRACE") != nullptr;
     bool refactor = true, binv_valid = false;
+    constexpr int RFF_BATCH_MAX = 8;
+    double* state_d = ws.scal + 40;                     // [8] batch state, [16] history (scal holds 64 doubles)
+    double* hist_d = ws.scal + 48;
+    double prev_rel_h = INFINITY;
+    bool first_batch = true;
     for (it = 0; it < max_iter; ++it) {
+        if (!refactor && !std::isnan(S_cur)) {
+            // ---- a batch of chord steps with the device-side acceptance test: one host synchronise per batch (a host decision per
+            // step cost ~0.29 ms per step for ~0.1 ms of kernels)
+            if (!binv_valid) {
+                if ((rc = blockinv_build(ws.H, F, F, Hdinv, ws.binv, st))) return rc;
+                binv_valid = true;
+            }
+            double rho = (std::isfinite(prev_rel_h) && last_rel < prev_rel_h) ? last_rel / prev_rel_h : 0.2;
+            rho = std::fmin(std::fmax(rho, 0.02), 0.5);
+            int kb = (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
+            if (first_batch) kb = std::min(kb, 3);
+            kb = std::max(1, std::min(kb, std::min(RFF_BATCH_MAX, max_iter - it)));
+            first_batch = false;
+            double state_h[8] = {S_cur, last_rel, prev_rel_h, 0.0, 0.0, 0.0, tol, 0.0}, hist_h[2 * RFF_BATCH_MAX];
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(state_d, state_h, sizeof(state_h), cudaMemcpyHostToDevice, st));
+            const double* skip = state_d + 4;
+            for (int i = 0; i < kb; ++i) {
+                if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, false, ws.scal + 24, st, skip))) return rc;
+                PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.step, ws.grad, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
+                if ((rc = potrs_vec_blockinv(ws.H, F, F, ws.binv, ws.step, st, skip))) return rc;
+                launch_rff_fvals(Phi_X, ld, F, N, ws.step, ws.fpart, ws.dfv, st, skip);
+                if ((rc = launch_linesearch_lik(ws.fvals, ws.dfv, Q, m, sigma, part, st))) return rc;
+                PPBO_CL rff_ls_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, part, Q, ws.scal);
+                PPBO_CL rff_chord_decide_kernel<<<1, 256, 0, st>>>(omega_map, ws.step, F, ws.scal, m, state_d, hist_d);
+            }
+            PPBO_LAUNCH_CHECK();
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(state_h, state_d, sizeof(state_h), cudaMemcpyDeviceToHost, st));
+            PPBO_CUDA_CHECK(cudaMemcpyAsync(hist_h, hist_d, sizeof(double) * 2 * kb, cudaMemcpyDeviceToHost, st));
+            PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+            const int taken = (int)state_h[5], stop = (int)state_h[4];
+            if (trace)
+                for (int i = 0; i < taken; ++i)
+                    fprintf(stderr, "[ppbo_rff_fit] it %d chord  step 1 rel %.3e S %.12g (batch of %d)\n", it + i, hist_h[2 * i], hist_h[2 * i + 1], kb);
+            n_chord += taken;
+            if (taken > 0) {
+                S_cur = state_h[0];
+                last_rel = state_h[1];
+                prev_rel_h = state_h[2];
+            }
+            it += taken;
+            if (stop == 1) break;
+            if (stop == 2 || stop == 3) refactor = true;
+            --it;                                        // the loop header adds one
+            continue;
+        }
         // gradient at omega (always fresh); Hessian factor only on Newton steps, reused on chord steps
         if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, refactor, ws.scal + 24, st))) return rc;
         if (refactor) {
@@ -625,6 +715,7 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
         PPBO_LAUNCH_CHECK();
         S_cur = S_new;
         const double prev_rel = last_rel;
+        prev_rel_h = last_rel;
         last_rel = s * max_step / max_om;
         if (trace) fprintf(stderr, "[ppbo_rff_fit] it %d %s step %.3g rel %.3e S %.12g\n", it, refactor ? "newton" : "chord ", s, last_rel, S_cur);
         if (c == 0 && last_rel <= tol) { ++it; break; }

@@ -17,3 +17,14 @@ for _ in range(5):
     a.record(); fit = ops.laplace_fit(Sigma, Q, m, th[0], tol=tol); b.record(); torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 print("%s CHORD_REL=%s tol=%g: %.2f ms %s" % (name, os.environ.get("PPBO_CHORD_REL", "default"), tol, float(np.median(ts)), fit.stats))
+W = ops.to_dev(prob["W"]); b = ops.to_dev(prob["b"])
+Phi = ops.rff_features(W, b, X, th[2], feature_major=True)
+for _ in range(2):
+    r = ops.rff_fit(Phi, Q, m, th[0], tol=tol)
+torch.cuda.synchronize()
+ts = []
+for _ in range(5):
+    a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); r = ops.rff_fit(Phi, Q, m, th[0], tol=tol); b2.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b2))
+print("%s rff_fit tol=%g: %.2f ms %s" % (name, tol, float(np.median(ts)), r[2]))
