@@ -233,14 +233,15 @@ def rff_reduce(fmax, mustar_dev, n_grids, shard=None):
     return sums
 
 
-def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_id=0, bounds=None, prepared=None):
+def rff_acquisition(r, PhiT, S, mustar_dev, shard=None, Z=None, seed=0, stream_id=0, bounds=None, prepared=None, n_grids=None):
     """Sampled acquisition on B grids: per grid b the sums over the S samples of max(fmax - mu*, 0), fmax and fmax^2
     (acquisition.EI / varmax, src/acquisition.py:78-81,176-178, with RFF posterior draws in place of the exact-GP MVN).
     Returns (sums [B,3] reduced over all ranks, fmax [B,S_loc], arg [B,S_loc]); bounds: this rank's samples (default: even split)."""
     shard = shard or Shard()
     lo, hi = bounds if bounds is not None else shard.bounds(S)
     fmax, arg = rff_sampled_maxima(r, PhiT, lo, hi, Z=Z, seed=seed, stream_id=stream_id, prepared=prepared)
-    n_grids = (PhiT.PhiT if isinstance(PhiT, SlicedGrids) else PhiT).shape[0]
+    if n_grids is None:                 # (a rank without samples has no grid features: the caller passes the count)
+        n_grids = (PhiT.PhiT if isinstance(PhiT, SlicedGrids) else PhiT).shape[0]
     return rff_reduce(fmax, mustar_dev, n_grids, shard), fmax, arg
 
 
@@ -433,6 +434,7 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         if PhiT is not None:
             for t in ((PhiT.PhiT, PhiT.planes, PhiT.scale) if isinstance(PhiT, SlicedGrids) else (PhiT,)):
                 t.record_stream(main)
-    sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed, bounds=(lo, hi), prepared=prepared)
+    sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed, bounds=(lo, hi), prepared=prepared,
+                                      n_grids=B)
     mark("acquisition")
     return sums, gp, rff
