@@ -1,6 +1,8 @@
 """CPU tests of the host side of the drop-in package src/ (no GPU): the design-matrix builder must consume the global
 RNG exactly like the reference (golden X / X_full were produced by the executed reference), the settings object must
 carry the reference's attributes, and the coordinate strategies of next_query are pure host logic."""
+import os
+import sys
 import types
 
 import numpy as np
@@ -142,3 +144,30 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(PPBOError):
         ops.device()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) on this host: one JSON line with the contract's keys"""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "ppbo_iteration_ms" and line["unit"] == "ms"
+    assert line["higher_is_better"] is False and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
+
+
+def test_bench_refuses_to_run_our_arm_without_a_gpu():
+    """no CPU fallback: our arm exits with an error when there is no CUDA device"""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a host without a GPU")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
