@@ -46,6 +46,13 @@ int ppbo_gram_regularized(int kind, const double* X, int n, int D, const double*
 /* K <- (1-s) K + s (tr K / n) I in place for an arbitrary square matrix (misc.regularize_covariance on a caller-supplied
  * matrix, src/misc.py:71-88).  scratch1: one device double. */
 int ppbo_shrink_inplace(double* K, long long ld, int n, double shrinkage, double* scratch1, void* stream);
+/* Rows / columns [n_old, n_new) of the regularised covariance of X[0 : n_new] written in place into out (leading dimension
+ * ld >= n_new); the leading n_old x n_old block is not touched.  One (m+1)-row block is appended per PPBO iteration
+ * (FeedbackProcessing.update_X, src/feedback_processing.py:133-154) while the reference rebuilds Sigma from scratch
+ * (GPModel.update_Sigma, src/gp_model.py:157); the shrinkage term is N-independent for these stationary kernels, so the old
+ * matrix is the leading block of the new one.  Bit-identical to ppbo_gram_regularized on X[0 : n_new]. */
+int ppbo_gram_append(int kind, const double* X, int n_old, int n_new, int D, const double* lengthscales_h, double sigma_f,
+                     double shrinkage, double* out, long long ld, void* stream);
 /* analytic dK/dlog(l_d) and dK/dlog(sigma_f) for the SE kernel (north_star piece 1; the reference has
  * no gradient -- checked against finite differences of SE_kernel).  dK: [(D+1)][n1 x n2] */
 int ppbo_kernel_se_grad(const double* X1, int n1, const double* X2, int n2, int D,
@@ -65,21 +72,56 @@ int ppbo_lambda_dense(const double* arrow, int Q, int m, double* out, long long 
 /* G[Qm x Qm] = B^T Sigma B, the prior covariance of the latent differences f_j - f_winner */
 int ppbo_diffspace_gram(const double* Sigma, long long lds, int Q, int m, double* G, long long ldg, void* stream);
 
-/* doubles in a "factor object": n*n matrix followed by the inverted 128x128 diagonal blocks */
+/* the same for appended comparison sets: entries of G with a row or a column in [Q_old m, Q_new m), in place (bit-identical to
+ * ppbo_diffspace_gram on the grown Sigma) */
+int ppbo_diffspace_gram_append(const double* Sigma, long long lds, int Q_old, int Q_new, int m, double* G, long long ldg,
+                               void* stream);
+
+/* doubles in a "factor object" of capacity n: n*n matrix (leading dimension n) followed by the inverted 128x128 diagonal blocks */
 long long ppbo_factor_doubles(int n);
 /* workspace (bytes) needed by ppbo_laplace_fit */
 long long ppbo_laplace_workspace_bytes(int Q, int m);
 /* MAP of T(f) = -1/2 f' Sigma^-1 f - (1/m) sum Phi(Delta/sqrt2)  (GPModel.update_fMAP, src/gp_model.py:354-389,
- * replaces scipy trust-exact): damped Newton in difference space, every step one Cholesky of
- * I + a^1/2 (B' Sigma B) a^1/2 (size Qm).  f_init may be NULL (start at 0).
- * Outputs: f_map[N], alpha[N] = Sigma^-1 f_map, arrow[Qm] (true coefficients at the mode),
- *          Lfac: "factor object" of ppbo_factor_doubles(Qm) doubles = [Qm x Qm lower Cholesky factor of
- *          I + a+^1/2 G a+^1/2 at the mode (a+ = max(a,0)) | inverted diagonal blocks used by the solves],
- *          stats_h[8] host doubles: iterations, last step inf-norm, last relative step, T(f_map), line-search halvings,
- *          info, Cholesky factorisations, chord (factor-reusing) steps */
+ * replaces scipy trust-exact): damped Newton in difference space, every Newton step one Cholesky of
+ * I + a^1/2 (B' Sigma B) a^1/2 (size Qm), followed by factor-reusing chord steps.  f_init may be NULL (start at 0).
+ * G [>= Qm x Qm, leading dimension ldg] and Lfac (factor object of capacity cap >= Qm) may be larger than the problem so that a
+ * model can grow in place.  flags:
+ *   PPBO_FIT_G_READY        G already holds B' Sigma B (ppbo_diffspace_gram / _append); otherwise it is formed here
+ *   PPBO_FIT_FACTOR_WARM    Lfac holds chol(I + s G s) for s = sa_fac (a previous fit's factor, grown by ppbo_factor_extend):
+ *                           the fit starts with chord steps from f_init and factorises only if they contract too slowly
+ *                           (the reference's warm start pads the previous fMAP, src/gp_model.py:375-377)
+ *   PPBO_FIT_FACTOR_AT_MODE finish with the factor of I + a+^1/2 G a+^1/2 AT the mode (what ppbo_predict with covariance and
+ *                           ppbo_neg_corr_build need); without it Lfac keeps the last factor used and ppbo_laplace_refactor
+ *                           builds the mode factor on demand (the posterior mean needs alpha only)
+ * Outputs: f_map[N], alpha[N] = Sigma^-1 f_map, arrow[Qm] (signed coefficients at the mode), sa_fac[Qm] (may be NULL) = the
+ *          clamped square roots the factor left in Lfac was built with,
+ *          stats_h[12] host doubles: iterations, last step inf-norm, last relative step, T(f_map), line-search halvings,
+ *          info, Cholesky factorisations, chord steps, factor state (2 at the mode / 1 last Newton or warm factor / 0 none),
+ *          converged (1/0), relative size of the first warm step */
+#define PPBO_FIT_G_READY 1
+#define PPBO_FIT_FACTOR_WARM 2
+#define PPBO_FIT_FACTOR_AT_MODE 4
 int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
-                     int max_iter, double tol, double* G, double* Lfac, double* f_map, double* alpha,
-                     double* arrow, void* workspace, long long workspace_bytes, double* stats_h, void* stream);
+                     int max_iter, double tol, int flags, double* G, long long ldg, double* Lfac, int cap, double* sa_fac,
+                     double* f_map, double* alpha, double* arrow, void* workspace, long long workspace_bytes, double* stats_h,
+                     void* stream);
+/* factor of I + a+^1/2 G a+^1/2 for the coefficients `arrow` (a fit that skipped PPBO_FIT_FACTOR_AT_MODE); sa_fac[M] receives
+ * sqrt(max(arrow, 0)).  Returns 0 or the index of the first non-positive pivot. */
+int ppbo_laplace_refactor(const double* G, long long ldg, int M, const double* arrow, double* Lfac, int cap, double* sa_fac,
+                          void* stream);
+/* Grow chol(I + s G s) from M_old to M_new rows after comparison sets were appended (G grown by ppbo_diffspace_gram_append).
+ * The coefficients of the new rows, sa_fac[M_old : M_new), are taken as given (f_new_sets == NULL) or computed here from the
+ * warm-start values f_new_sets[(M_new - M_old) / m * (m + 1)] of the appended sets (winner first), s = sqrt(max(a(f), 0)).
+ * Only the block rows from the last 128-row boundary on are recomputed -- O(M^2 m) work instead of the O(M^3 / 3) of a new
+ * factorisation.  The reference refactors its N x N Hessian from scratch inside every trust-exact iteration
+ * (src/gp_model.py:382-384).  Returns 0 or the first non-positive pivot. */
+int ppbo_factor_extend(const double* G, long long ldg, int M_old, int M_new, double* sa_fac, const double* f_new_sets, int m,
+                       double sigma, double* Lfac, int cap, void* stream);
+
+/* out[N x N] = I + Sigma W (reference_sign = 0) or I - Sigma W = I + Sigma Lambda_MAP (reference_sign = 1: the matrix
+ * GPModel.evidence factors, src/gp_model.py:301-302), W = B diag(arrow) B' with the SIGNED coefficients. */
+int ppbo_evidence_matrix(const double* Sigma, long long lds, int Q, int m, const double* arrow, int reference_sign, double* out,
+                         long long ldo, void* stream);
 
 /* ---- dense FP64 linear algebra (replaces the LAPACK/BLAS calls under numpy/scipy) ---------------- */
 /* C[M x N] = alpha * A[M x K] . B[N x K]^T + beta * C   (row-major, K contiguous in A and B) */
@@ -114,6 +156,11 @@ int ppbo_potrs_vec_blockinv(const double* L, long long ldl, int n, void* blockin
  * explicit inverse (GPModel.Sigma_inv, posterior_covariance). */
 int ppbo_potri_lower(const double* L, long long ldl, int n, void* workspace, long long workspace_bytes, double* work,
                      double* out, long long ldo, void* stream);
+/* In-place LU with partial pivoting (largest magnitude, first index on ties -- LAPACK dgetrf's rule) of A[n x n];
+ * result_h[3] = { sign(det U), log|det A|, sign of the row permutation }.  Replaces scipy.linalg.lu + numpy.linalg.slogdet in
+ * GPModel.evidence (src/gp_model.py:303-308).  Returns 1 when a pivot is exactly zero. */
+long long ppbo_lu_workspace_bytes(int n);
+int ppbo_lu_logdet(double* A, long long lda, int n, void* workspace, long long workspace_bytes, double* result_h, void* stream);
 /* y = A x for row-major A[M x N] */
 int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, double* y, void* stream);
 
@@ -128,12 +175,18 @@ long long ppbo_predict_workspace_bytes(int N, int Q, int m, int P, int batch);
  * (Woodbury on the r negative columns) that ppbo_predict adds: count (host sync; indices to idx_h), size, build. */
 int ppbo_neg_count(const double* arrow, int M, int* idx_h, int idx_capacity, void* stream);
 long long ppbo_neg_corr_doubles(int M, int r);
-int ppbo_neg_corr_build(const double* G, int M, const double* arrow, const double* Lfac, const int* idx_h, int r,
-                        double* neg_corr, void* stream);
+int ppbo_neg_corr_build(const double* G, long long ldg, int M, const double* arrow, const double* Lfac, int cap,
+                        const int* idx_h, int r, double* neg_corr, void* stream);
+/* Lfac: factor object of capacity cap holding the factor AT the mode (only read when Sigma_p != NULL) */
 int ppbo_predict(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f,
-                 double shrinkage, int Q, int m, const double* alpha, const double* arrow, const double* Lfac,
+                 double shrinkage, int Q, int m, const double* alpha, const double* arrow, const double* Lfac, int cap,
                  const double* neg_corr, int n_neg, const double* Xp, int P, int batch, double* mu,
                  double* Sigma_p, void* workspace, long long workspace_bytes, void* stream);
+/* mu_h[0] = k(x, X) alpha for ONE point given and returned in HOST memory (x_h[D], mu_h[1]); one launch, no allocation, the
+ * call returns when the value is on the host.  Replaces GPModel.mu_pred (src/gp_model.py:454-458) inside the sequential
+ * differential evolution of GPModel.mu_star (src/gp_model.py:415-437: ~10^4 dependent evaluations per model update). */
+int ppbo_mu_pred_point(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f, const double* alpha,
+                       const double* x_h, double* mu_h, void* stream);
 /* fmax[b][s] = max_p ( mu[b][p] + sum_k Z[b][s][k] Fac[b][p][k] ), arg[b][s] = first arg-max.
  * Replaces the S calls of np.random.multivariate_normal + np.max in acquisition.EI / varmax
  * (src/acquisition.py:78-80, 175-177); Fac is the (P x P) sampling factor (row p = coefficients of point p). */

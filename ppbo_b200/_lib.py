@@ -10,6 +10,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_longlong, c_uint, c_ulo
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libppbo_b200.so")
 
+FIT_G_READY, FIT_FACTOR_WARM, FIT_FACTOR_AT_MODE = 1, 2, 4
 KERNEL_KINDS = {"SE_kernel": 0, "RQ_kernel": 1, "camphor_copper_kernel": 2}
 
 
@@ -37,7 +38,11 @@ _SIGNATURES = {
     "ppbo_diffspace_gram": (_I, [_P, _L, _I, _I, _P, _L, _P]),
     "ppbo_factor_doubles": (_L, [_I]),
     "ppbo_laplace_workspace_bytes": (_L, [_I, _I]),
-    "ppbo_laplace_fit": (_I, [_P, _L, _I, _I, _D, _P, _I, _D, _P, _P, _P, _P, _P, _P, _L, _PD, _P]),
+    "ppbo_gram_append": (_I, [_I, _P, _I, _I, _I, _PD, _D, _D, _P, _L, _P]),
+    "ppbo_diffspace_gram_append": (_I, [_P, _L, _I, _I, _I, _P, _L, _P]),
+    "ppbo_laplace_fit": (_I, [_P, _L, _I, _I, _D, _P, _I, _D, _I, _P, _L, _P, _I, _P, _P, _P, _P, _P, _L, _PD, _P]),
+    "ppbo_laplace_refactor": (_I, [_P, _L, _I, _P, _P, _I, _P, _P]),
+    "ppbo_factor_extend": (_I, [_P, _L, _I, _I, _P, _P, _I, _D, _P, _I, _P]),
     "ppbo_gemm_nt": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _D, _D, _P]),
     "ppbo_gemm_nt_cfg": (_I, [_I, _P, _L, _P, _L, _P, _L, _I, _I, _I, _D, _D, _P]),
     "ppbo_potrf_workspace_bytes": (_L, [_I]),
@@ -49,12 +54,16 @@ _SIGNATURES = {
     "ppbo_potrs_vec_blockinv": (_I, [_P, _L, _I, _P, _L, _P, _P]),
     "ppbo_potri_lower": (_I, [_P, _L, _I, _P, _L, _P, _P, _L, _P]),
     "ppbo_shrink_inplace": (_I, [_P, _L, _I, _D, _P, _P]),
+    "ppbo_evidence_matrix": (_I, [_P, _L, _I, _I, _P, _I, _P, _L, _P]),
+    "ppbo_lu_workspace_bytes": (_L, [_I]),
+    "ppbo_lu_logdet": (_I, [_P, _L, _I, _P, _L, _PD, _P]),
     "ppbo_gemv": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "ppbo_neg_count": (_I, [_P, _I, _PI, _I, _P]),
     "ppbo_neg_corr_doubles": (_L, [_I, _I]),
-    "ppbo_neg_corr_build": (_I, [_P, _I, _P, _P, _PI, _I, _P, _P]),
+    "ppbo_neg_corr_build": (_I, [_P, _L, _I, _P, _P, _I, _PI, _I, _P, _P]),
     "ppbo_predict_workspace_bytes": (_L, [_I, _I, _I, _I, _I]),
-    "ppbo_predict": (_I, [_I, _P, _I, _I, _PD, _D, _D, _I, _I, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P, _P, _L, _P]),
+    "ppbo_predict": (_I, [_I, _P, _I, _I, _PD, _D, _D, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _L, _P]),
+    "ppbo_mu_pred_point": (_I, [_I, _P, _I, _I, _PD, _D, _P, _PD, _PD, _P]),
     "ppbo_mvn_rowmax": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P]),
     "ppbo_acq_reduce": (_I, [_P, _I, _I, _D, _P, _P]),
     "ppbo_acq_reduce_dev": (_I, [_P, _I, _I, _P, _P, _P]),

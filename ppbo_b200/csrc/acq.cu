@@ -387,9 +387,10 @@ extern "C" int ppbo_neg_count(const double* arrow, int M, int* idx_h, int idx_ca
 extern "C" long long ppbo_neg_corr_doubles(int M, int r) {
     return (long long)((r + 1) / 2) + (long long)r * M + ppbo_factor_doubles(r) + 2;
 }
-extern "C" int ppbo_neg_corr_build(const double* G, int M, const double* arrow, const double* Lfac, const int* idx_h, int r,
-                                   double* neg_corr, void* stream) {
+extern "C" int ppbo_neg_corr_build(const double* G, long long ldg, int M, const double* arrow, const double* Lfac, int cap,
+                                   const int* idx_h, int r, double* neg_corr, void* stream) {
     if (r <= 0) return PPBO_OK;
+    PPBO_REQUIRE(cap >= M && ldg >= M, "capacity / leading dimension below M");
     cudaStream_t st = (cudaStream_t)stream;
     int* idx = reinterpret_cast<int*>(neg_corr);
     double* Ht = neg_corr + (r + 1) / 2;
@@ -397,9 +398,9 @@ extern "C" int ppbo_neg_corr_build(const double* G, int M, const double* arrow, 
     double* Rdinv = R + (long long)r * r;
     int* info_d = reinterpret_cast<int*>(neg_corr + ppbo_neg_corr_doubles(M, r) - 1);
     PPBO_CUDA_CHECK(cudaMemcpyAsync(idx, idx_h, sizeof(int) * r, cudaMemcpyHostToDevice, st));
-    PPBO_CL neg_rows_kernel<<<dim3(ceil_div(M, 256), r), 256, 0, st>>>(G, M, M, arrow, idx, r, Ht, R, r);
+    PPBO_CL neg_rows_kernel<<<dim3(ceil_div(M, 256), r), 256, 0, st>>>(G, ldg, M, arrow, idx, r, Ht, R, r);
     PPBO_LAUNCH_CHECK();
-    int rc = trsm_right_lower_t(Lfac, M, M, Lfac + (long long)M * M, Ht, M, r, st);   // Ht <- Ht L^-T
+    int rc = trsm_right_lower_t(Lfac, cap, M, Lfac + (long long)cap * cap, Ht, M, r, st);   // Ht <- Ht L^-T
     if (rc) return rc;
     GemmOperands g{Ht, M, 0, Ht, M, 0, r, r, M};
     StoreEpilogue ep{R, r, 0, 1.0, 1.0, 0, 0, 0};                                      // R += Ht Ht^T
@@ -419,10 +420,11 @@ extern "C" long long ppbo_predict_workspace_bytes(int N, int Q, int m, int P, in
 }
 
 extern "C" int ppbo_predict(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f,
-                            double shrinkage, int Q, int m, const double* alpha, const double* arrow, const double* Lfac,
+                            double shrinkage, int Q, int m, const double* alpha, const double* arrow, const double* Lfac, int cap,
                             const double* neg_corr, int n_neg, const double* Xp, int P, int batch, double* mu,
                             double* Sigma_p, void* workspace, long long workspace_bytes, void* stream) {
     PPBO_REQUIRE(N == Q * (m + 1), "N must equal Q (m+1)");
+    PPBO_REQUIRE(Sigma_p == nullptr || cap >= Q * m, "factor capacity below Q m");
     PPBO_REQUIRE(P >= 1 && batch >= 1, "empty grid");
     PPBO_REQUIRE(workspace_bytes >= ppbo_predict_workspace_bytes(N, Q, m, P, batch), "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -442,7 +444,7 @@ extern "C" int ppbo_predict(int kind, const double* X, int N, int D, const doubl
     if (!Sigma_p) return PPBO_OK;
     PPBO_CL pred_diff_kernel<<<dim3(ceil_div(M, 256), PT), 256, 0, st>>>(Kc, N, PT, Q, m, arrow, Ut, M);
     PPBO_LAUNCH_CHECK();
-    if ((rc = trsm_right_lower_t(Lfac, M, M, Lfac + (long long)M * M, Ut, M, PT, st))) return rc;   // Yt = Ut L^-T
+    if ((rc = trsm_right_lower_t(Lfac, cap, M, Lfac + (long long)cap * cap, Ut, M, PT, st))) return rc;   // Yt = Ut L^-T
     for (int b = 0; b < batch; ++b) {     // reg(K**) per grid (diagonal shrinkage needs the square form)
         const double* xb = Xp + (long long)b * P * D;
         if ((rc = kernel_matrix_raw(kind, xb, P, xb, P, D, lengthscales_h, sigma_f, 1.0 - shrinkage,

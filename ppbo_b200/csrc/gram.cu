@@ -427,6 +427,58 @@ int kernel_matvec(int kind, const double* X1, int n1, const double* X2, int n2, 
     return 1;
 }
 
+// ---- posterior mean at ONE point with host-resident argument and result ------------------------------------------------------
+// GPModel.mu_star (src/gp_model.py:415-437) drives ~10^4 SEQUENTIAL evaluations of mu_pred (src/gp_model.py:454-458) from scipy's
+// differential evolution ('immediate' updating: every trial depends on the previous accept / reject, so the evaluations cannot be
+// batched without changing the reference's RNG trajectory).  Per evaluation the general path paid a tensor allocation, a pageable
+// H2D copy, two launches and a D2H copy.  Here the point and the result live in mapped pinned host memory (one small buffer per
+// host thread): the host writes x, one single-CTA launch reads it over PCIe, accumulates sum_i k(x, X_i) alpha_i in a fixed order
+// (difference form, like kernel_matrix_kernel) and writes the mean back; the host waits on the stream.
+template <int KIND>
+__global__ void __launch_bounds__(1024) mu_pred_point_kernel(const double* __restrict__ X, int N, KernelParams p,
+                                                             const double* __restrict__ alpha, const double* __restrict__ x_in,
+                                                             double* __restrict__ out) {
+    __shared__ double xs[PPBO_MAX_D];
+    __shared__ double red[33];
+    const int D = p.D;
+    for (int d = threadIdx.x; d < D; d += 1024) xs[d] = x_in[d];
+    __syncthreads();
+    double s = 0.0;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const double* xi = X + (long long)i * D;
+        double a = 0.0;
+        if (KIND == PPBO_KERNEL_CAMPHOR) {
+            const double il = p.inv_ls[0], il2 = il * il, ilz = p.inv_ls[2];
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+                const double d0 = fabs(xs[d] - xi[d]);
+                if (d == 2) a += 0.5 * d0 * d0 * ilz * ilz;
+                else { const double q0 = sinpi(d0); a += 2.0 * q0 * q0 * il2; }
+            }
+        } else {
+            for (int d = 0; d < D; ++d) {
+                const double t = (xs[d] - xi[d]) * p.inv_ls[d];
+                a = fma(t, t, a);
+            }
+        }
+        s = fma(kernel_from_sums(KIND, a, p.sf2), alpha[i], s);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+struct PinnedPoint {
+    double* host = nullptr;
+    double* dev = nullptr;
+    int init() {
+        if (host) return PPBO_OK;
+        PPBO_CUDA_CHECK(cudaHostAlloc(&host, sizeof(double) * (PPBO_MAX_D + 8), cudaHostAllocMapped));
+        PPBO_CUDA_CHECK(cudaHostGetDevicePointer(&dev, host, 0));
+        return PPBO_OK;
+    }
+};
+static thread_local PinnedPoint g_point;
+
 // ---- SE kernel gradients w.r.t. log length-scales and log sigma_f --------------------------------------
 __global__ void __launch_bounds__(256) se_grad_kernel(const double* __restrict__ X1, int n1, const double* __restrict__ X2,
                                                       int n2, KernelParams p, double* __restrict__ dK, long long ld,
@@ -511,6 +563,46 @@ int diffspace_gram(const double* S, long long lds, int Q, int m, double* G, long
     return PPBO_OK;
 }
 
+// Appended comparison sets: every entry of G with a row or a column in [M_old, M_new), by the expression of
+// diffspace_gram_kernel (so the grown matrix is bit-identical to a from-scratch one).  blockIdx.y enumerates the new rows first
+// (full rows), then the old rows (new columns only).
+__global__ void __launch_bounds__(256) diffspace_gram_append_kernel(const double* __restrict__ S, long long lds, int M_old, int M_new,
+                                                                    int m, double* __restrict__ G, long long ldg) {
+    const int nn = M_new - M_old;
+    int u, v;
+    if ((int)blockIdx.y < nn) {
+        u = M_old + blockIdx.y;
+        v = blockIdx.x * blockDim.x + threadIdx.x;
+        if (v >= M_new) return;
+    } else {
+        u = blockIdx.y - nn;
+        v = M_old + blockIdx.x * blockDim.x + threadIdx.x;
+        if (v >= M_new) return;
+    }
+    const int qu = u / m, ju = u % m, qv = v / m, jv = v % m;
+    const long long ru = (long long)qu * (m + 1) + 1 + ju, wu = (long long)qu * (m + 1);
+    const long long rv = (long long)qv * (m + 1) + 1 + jv, wv = (long long)qv * (m + 1);
+    G[(long long)u * ldg + v] = (S[ru * lds + rv] - S[ru * lds + wv]) - (S[wu * lds + rv] - S[wu * lds + wv]);
+}
+
+int diffspace_gram_append(const double* S, long long lds, int Q_old, int Q_new, int m, double* G, long long ldg, cudaStream_t st) {
+    const int M_old = Q_old * m, M_new = Q_new * m;
+    if (M_new <= M_old) return PPBO_OK;
+    PPBO_CL diffspace_gram_append_kernel<<<dim3(ceil_div(M_new, 256), M_new), 256, 0, st>>>(S, lds, M_old, M_new, m, G, ldg);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+// out[j][i] = out[i][j] for the appended rows i in [n_old, n_new) and all j < i; the diagonal of the appended rows is set to the
+// exact value every from-scratch kernel stores there
+__global__ void __launch_bounds__(256) gram_mirror_kernel(double* __restrict__ out, long long ld, int n_old, int n_new,
+                                                          double diag_scale, double sf2, double diag_add) {
+    const int i = n_old + blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_new || j > i) return;
+    if (j == i) out[(long long)i * ld + i] = diag_scale * sf2 + diag_add;       // same expression as the from-scratch kernels
+    else out[(long long)j * ld + i] = out[(long long)i * ld + j];
+}
+
 int newton_matrix(const double* G, long long ldg, int M, const double* sa, double* out, long long ldo, cudaStream_t st) {
     if (M <= 0) return PPBO_OK;
     dim3 grid(ceil_div(M, 256), M);
@@ -536,6 +628,47 @@ extern "C" int ppbo_gram_regularized(int kind, const double* X, int n, int D, co
     // (1-s) K + s (tr K / n) I with tr K / n = sigma_f^2 (stationary kernels, k(x,x) = sigma_f^2)
     return kernel_matrix_raw(kind, X, n, X, n, D, lengthscales_h, sigma_f, 1.0 - shrinkage,
                              shrinkage * sigma_f * sigma_f, out, ld, (cudaStream_t)stream);
+}
+
+/* Rows / columns [n_old, n_new) of the regularised covariance of X[0:n_new] in place (leading dimension ld >= n_new): the
+ * leading n_old x n_old block is untouched -- the shrinkage is N-independent for these stationary kernels, so
+ * Sigma_old is the leading principal block of Sigma_new.  One (m+1)-row block is appended per PPBO iteration
+ * (src/feedback_processing.py:133-154, src/gp_model.py:157 rebuilds everything).  Bit-identical to ppbo_gram_regularized. */
+extern "C" int ppbo_gram_append(int kind, const double* X, int n_old, int n_new, int D, const double* lengthscales_h,
+                                double sigma_f, double shrinkage, double* out, long long ld, void* stream) {
+    PPBO_REQUIRE(n_old >= 0 && n_new >= n_old && ld >= n_new, "shape");
+    PPBO_REQUIRE(shrinkage >= 0.0 && shrinkage < 1.0, "shrinkage in [0,1)");
+    if (n_new == n_old) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // appended rows against all points: same per-entry arithmetic as the symmetric kernel (same shift point X[0], same scaling)
+    int rc = kernel_matrix_raw(kind, X + (long long)n_old * D, n_new - n_old, X, n_new, D, lengthscales_h, sigma_f, 1.0 - shrinkage, 0.0,
+                               out + (long long)n_old * ld, ld, st);
+    if (rc) return rc;
+    PPBO_CL gram_mirror_kernel<<<dim3(ceil_div(n_new, 256), n_new - n_old), 256, 0, st>>>(out, ld, n_old, n_new, 1.0 - shrinkage,
+                                                                                             sigma_f * sigma_f, shrinkage * sigma_f * sigma_f);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_mu_pred_point(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f,
+                                   const double* alpha, const double* x_h, double* mu_h, void* stream) {
+    KernelParams p;
+    int rc = fill_params(p, kind, D, lengthscales_h, sigma_f);
+    if (rc) return rc;
+    PPBO_REQUIRE(N >= 0 && x_h != nullptr && mu_h != nullptr, "arguments");
+    if ((rc = g_point.init())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int d = 0; d < D; ++d) g_point.host[d] = x_h[d];
+    double* out = g_point.dev + PPBO_MAX_D;
+    switch (kind) {
+        case PPBO_KERNEL_SE: PPBO_CL mu_pred_point_kernel<PPBO_KERNEL_SE><<<1, 1024, 0, st>>>(X, N, p, alpha, g_point.dev, out); break;
+        case PPBO_KERNEL_RQ: PPBO_CL mu_pred_point_kernel<PPBO_KERNEL_RQ><<<1, 1024, 0, st>>>(X, N, p, alpha, g_point.dev, out); break;
+        default: PPBO_CL mu_pred_point_kernel<PPBO_KERNEL_CAMPHOR><<<1, 1024, 0, st>>>(X, N, p, alpha, g_point.dev, out);
+    }
+    PPBO_LAUNCH_CHECK();
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    *mu_h = g_point.host[PPBO_MAX_D];
+    return PPBO_OK;
 }
 
 extern "C" int ppbo_kernel_se_grad(const double* X1, int n1, const double* X2, int n2, int D,

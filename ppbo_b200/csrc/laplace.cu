@@ -12,6 +12,7 @@
 
 #include "../../include/ppbo_b200.h"
 #include "common.cuh"
+#include "gemm_f64.cuh"
 #include "linalg.cuh"
 
 namespace ppbo {
@@ -74,6 +75,16 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* __restrict__ x,
     __shared__ double red[33];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 1024) s += x[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// out[0] = x . y in a fixed order (single CTA)
+__global__ void __launch_bounds__(1024) dot_kernel(const double* __restrict__ x, const double* __restrict__ y, int n,
+                                                   double* __restrict__ out) {
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s = fma(x[i], y[i], s);
     s = block_sum(s, red);
     if (threadIdx.x == 0) out[0] = s;
 }
@@ -304,6 +315,30 @@ __global__ void lambda_dense_kernel(const double* __restrict__ arrow, int Q, int
     out[(long long)i * ld + j] = v;
 }
 
+// out = I + sign * Sigma W with W = B diag(a) B' = -Lambda (signed coefficients): the matrix whose determinant enters the
+// Laplace evidence.  sign = +1: I + Sigma W (posterior precision times prior covariance); sign = -1: I + Sigma Lambda, the matrix
+// the reference factors (src/gp_model.py:301-302).  Column c of set q:  winner:  sum_j a_j (S[i][w] - S[i][r_j]);  pseudo-observation
+// j:  a_j (S[i][r_j] - S[i][w]).
+__global__ void __launch_bounds__(256) evidence_matrix_kernel(const double* __restrict__ S, long long lds, int Q, int m,
+                                                              const double* __restrict__ arrow, double sign, double* __restrict__ out,
+                                                              long long ldo) {
+    const int N = Q * (m + 1);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (c >= N) return;
+    const int q = c / (m + 1), rc = c % (m + 1);
+    const long long w = (long long)q * (m + 1);
+    const double* si = S + (long long)i * lds;
+    const double* a = arrow + (long long)q * m;
+    double v = 0.0;
+    if (rc == 0) {
+        const double sw = si[w];
+        for (int j = 0; j < m; ++j) v = fma(a[j], sw - si[w + 1 + j], v);
+    } else {
+        v = a[rc - 1] * (si[c] - si[w]);
+    }
+    out[(long long)i * ldo + c] = ((i == c) ? 1.0 : 0.0) + sign * v;
+}
+
 int launch_lik_terms(const double* f, int Q, int m, double sigma, double* set_lik, double* beta, double* arrow, double* sa,
                      double* bvec, cudaStream_t st) {
     PPBO_CL lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, set_lik, beta, arrow, sa, bvec);
@@ -322,6 +357,50 @@ int launch_sum(const double* x, int n, double* out, cudaStream_t st) {
 }
 
 constexpr int CHORD_STATE = 16, CHORD_BATCH_MAX = 16;
+
+// sa[u] = sqrt(max(arrow[u], 0))
+__global__ void sqrt_clamp_kernel(const double* __restrict__ arrow, int M, double* __restrict__ sa) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < M) sa[u] = sqrt(fmax(arrow[u], 0.0));
+}
+// ap[u] = sa[u]^2 (the clamped coefficients a factor was built with)
+__global__ void square_kernel(const double* __restrict__ sa, int M, double* __restrict__ ap) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < M) ap[u] = sa[u] * sa[u];
+}
+// scal[4] = max|f_new - f_old|, scal[5] = max|f_new|  (relative size of the first step from a warm start; single CTA)
+__global__ void __launch_bounds__(1024) warm_step_size_kernel(const double* __restrict__ f_old, const double* __restrict__ f_new,
+                                                              int N, double* __restrict__ scal) {
+    __shared__ double mx[2][32];
+    double md = 0.0, mf = 0.0;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        md = fmax(md, fabs(f_new[i] - f_old[i]));
+        mf = fmax(mf, fabs(f_new[i]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+        mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+    }
+    if ((threadIdx.x & 31) == 0) { mx[0][threadIdx.x >> 5] = md; mx[1][threadIdx.x >> 5] = mf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) { md = fmax(md, mx[0][w]); mf = fmax(mf, mx[1][w]); }
+        scal[4] = md;
+        scal[5] = mf;
+    }
+}
+// rows [r_lo, r_hi) of the Newton matrix I + sa G sa, columns [c_lo(row), row]: c_lo = c_old for rows < r_split (rows whose
+// leading columns already hold factor entries that must survive), 0 for the appended rows
+__global__ void __launch_bounds__(256) newton_rows_kernel(const double* __restrict__ G, long long ldg, const double* __restrict__ sa,
+                                                          int r_lo, int r_hi, int r_split, int c_old, double* __restrict__ out,
+                                                          long long ldo) {
+    const int u = r_lo + blockIdx.y, v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= r_hi || v > u) return;
+    if (u < r_split && v < c_old) return;
+    double x = sa[u] * G[(long long)u * ldg + v] * sa[v];
+    if (u == v) x += 1.0;
+    out[(long long)u * ldo + v] = x;
+}
 
 struct FitWorkspace {
     double *bvec, *sa, *ap, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp, *binv, *state, *hist;
@@ -380,20 +459,109 @@ extern "C" int ppbo_lambda_dense(const double* arrow, int Q, int m, double* out,
     return PPBO_OK;
 }
 
+extern "C" int ppbo_evidence_matrix(const double* Sigma, long long lds, int Q, int m, const double* arrow, int reference_sign,
+                                    double* out, long long ldo, void* stream) {
+    PPBO_REQUIRE(Q >= 1 && m >= 1 && ldo >= (long long)Q * (m + 1), "shape");
+    const int N = Q * (m + 1);
+    PPBO_CL evidence_matrix_kernel<<<dim3(ceil_div(N, 256), N), 256, 0, (cudaStream_t)stream>>>(Sigma, lds, Q, m, arrow,
+                                                                                                reference_sign ? -1.0 : 1.0, out, ldo);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
 extern "C" long long ppbo_laplace_workspace_bytes(int Q, int m) { return FitWorkspace::doubles(Q, m) * 8; }
 
+namespace ppbo {
+int diffspace_gram_append(const double* S, long long lds, int Q_old, int Q_new, int m, double* G, long long ldg, cudaStream_t st);
+}
+
+extern "C" int ppbo_diffspace_gram_append(const double* Sigma, long long lds, int Q_old, int Q_new, int m, double* G,
+                                          long long ldg, void* stream) {
+    PPBO_REQUIRE(Q_old >= 0 && Q_new >= Q_old && m >= 1 && ldg >= (long long)Q_new * m, "shape");
+    return diffspace_gram_append(Sigma, lds, Q_old, Q_new, m, G, ldg, (cudaStream_t)stream);
+}
+
+/* Factor at the mode on demand (ppbo_laplace_fit without PPBO_FIT_FACTOR_AT_MODE leaves the last Newton factor behind):
+ * sa_fac = sqrt(max(arrow, 0)), Lfac = chol(I + sa_fac G sa_fac).  Returns 0 / pivot index (host sync). */
+extern "C" int ppbo_laplace_refactor(const double* G, long long ldg, int M, const double* arrow, double* Lfac, int cap,
+                                     double* sa_fac, void* stream) {
+    PPBO_REQUIRE(M >= 1 && cap >= M && ldg >= M, "shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* dinv = Lfac + (long long)cap * cap;
+    int* info_d = nullptr;
+    PPBO_CUDA_CHECK(cudaMallocAsync(&info_d, sizeof(int), st));
+    PPBO_CL sqrt_clamp_kernel<<<ceil_div(M, 256), 256, 0, st>>>(arrow, M, sa_fac);
+    int rc;
+    if ((rc = newton_matrix(G, ldg, M, sa_fac, Lfac, cap, st))) return rc;
+    if ((rc = potrf_lower(Lfac, cap, M, dinv, info_d, st))) return rc;
+    int info = 0;
+    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(cudaFreeAsync(info_d, st));
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (info) set_error("mode system not positive definite at pivot %d", info);
+    return info;
+}
+
+/* Grow a factor by the rows of appended comparison sets.  On entry Lfac holds chol(I + sa G sa) of size M_old for the first
+ * M_old entries of sa_fac; sa_fac[M_old .. M_new) hold the coefficients chosen for the new rows (ppbo_lik_terms at the warm
+ * start).  On return Lfac is the factor of the M_new system with those coefficients: the block rows from the last 128-boundary
+ * b0 <= M_old on are recomputed (new rows: L21 = A21 L11^-T by a 25-row triangular solve; Schur complement of the <= 2 trailing
+ * diagonal blocks; their Cholesky) -- O(M^2 m) instead of O(M^3 / 3).  (src/feedback_processing.py:133-154 appends one (m+1)-row
+ * block per iteration) */
+extern "C" int ppbo_factor_extend(const double* G, long long ldg, int M_old, int M_new, double* sa_fac, const double* f_new_sets,
+                                  int m, double sigma, double* Lfac, int cap, void* stream) {
+    PPBO_REQUIRE(M_old >= 0 && M_new >= M_old && cap >= M_new && ldg >= M_new, "shape");
+    if (M_new == M_old) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f_new_sets) {      // coefficients of the appended sets at the warm start: sa = sqrt(max(a(f), 0))
+        PPBO_REQUIRE(m >= 1 && sigma > 0 && (M_new - M_old) % m == 0, "appended rows must be whole comparison sets");
+        const int Qn = (M_new - M_old) / m;
+        PPBO_CL lik_terms_kernel<<<ceil_div(Qn, 8), 256, 0, st>>>(f_new_sets, Qn, m, sigma, nullptr, nullptr, nullptr, sa_fac + M_old, nullptr);
+        PPBO_LAUNCH_CHECK();
+    }
+    double* dinv = Lfac + (long long)cap * cap;
+    const int b0 = (M_old / CHOL_NB) * CHOL_NB, nt = M_new - b0;
+    int rc;
+    int* info_d = nullptr;
+    PPBO_CUDA_CHECK(cudaMallocAsync(&info_d, sizeof(int), st));
+    PPBO_CL newton_rows_kernel<<<dim3(ceil_div(M_new, 256), nt), 256, 0, st>>>(G, ldg, sa_fac, b0, M_new, M_old, b0, Lfac, cap);
+    PPBO_LAUNCH_CHECK();
+    if (b0 > 0) {
+        double* Lnew = Lfac + (long long)M_old * cap;          // appended rows, columns [0, b0): A21 -> A21 L11^-T
+        if ((rc = trsm_right_lower_t(Lfac, cap, b0, dinv, Lnew, cap, M_new - M_old, st))) return rc;
+        double* Lt = Lfac + (long long)b0 * cap;               // rows [b0, M_new): S = A[b0:, b0:] - L[b0:, :b0] L[b0:, :b0]^T
+        GemmOperands g{Lt, cap, 0, Lt, cap, 0, nt, nt, b0};
+        StoreEpilogue ep{Lt + b0, cap, 0, -1.0, 1.0, 1, 0};
+        if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
+    }
+    if ((rc = potrf_lower(Lfac + (long long)b0 * cap + b0, cap, nt, dinv + (long long)(b0 / CHOL_NB) * CHOL_NB * CHOL_NB, info_d, st)))
+        return rc;
+    int info = 0;
+    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(cudaFreeAsync(info_d, st));
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (info) { info += b0; set_error("extended factor not positive definite at pivot %d", info); }
+    return info;
+}
+
 extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
-                                int max_iter, double tol, double* G, double* Lfac, double* f_map, double* alpha,
-                                double* arrow, void* workspace, long long workspace_bytes, double* stats_h, void* stream) {
+                                int max_iter, double tol, int flags, double* G, long long ldg, double* Lfac, int cap,
+                                double* sa_fac, double* f_map, double* alpha, double* arrow, void* workspace,
+                                long long workspace_bytes, double* stats_h, void* stream) {
     PPBO_REQUIRE(Q >= 1 && m >= 1 && sigma > 0, "shape / sigma");
     PPBO_REQUIRE(workspace_bytes >= ppbo_laplace_workspace_bytes(Q, m), "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = Q * (m + 1), M = Q * m;
+    PPBO_REQUIRE(cap >= M && ldg >= M, "capacity / leading dimension below Q m");
+    const bool g_ready = (flags & PPBO_FIT_G_READY) != 0, warm_factor = (flags & PPBO_FIT_FACTOR_WARM) != 0;
+    const bool factor_at_mode = (flags & PPBO_FIT_FACTOR_AT_MODE) != 0;
+    PPBO_REQUIRE(!warm_factor || (f_init != nullptr && sa_fac != nullptr), "a warm factor needs f_init and sa_fac");
     FitWorkspace ws;
     ws.carve((double*)workspace, Q, m);
-    double* Mdinv = Lfac + (long long)M * M;      // factor object = [M x M lower factor | inverted diagonal blocks]
+    const long long ldl = cap;
+    double* Mdinv = Lfac + (long long)cap * cap;  // factor object = [cap x cap lower factor | inverted diagonal blocks]
     int rc;
-    if ((rc = diffspace_gram(Sigma, lds, Q, m, G, M, st))) return rc;
+    if (!g_ready && (rc = diffspace_gram(Sigma, lds, Q, m, G, ldg, st))) return rc;
 
     const bool have_start = f_init != nullptr;
     if (have_start) PPBO_CUDA_CHECK(cudaMemcpyAsync(f_map, f_init, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
@@ -423,13 +591,50 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     // tuning: PPBO_CHORD_EXTRAPOLATE=0 switches the Aitken step lengths off (diagnostics)
     const bool chord_extrapolate = !(getenv("PPBO_CHORD_EXTRAPOLATE") && atoi(getenv("PPBO_CHORD_EXTRAPOLATE")) == 0);
     double chord_omega = 1.0, chord_ratio = 0.0, chord_wait = 0.0;
-    while (it < max_iter) {
+    bool factor_current = false;         // Lfac is the factor for the coefficients in ws.sa / ws.ap
+    double warm_first_rel = NAN;
+    if (warm_factor) {
+        // Warm start with a usable factor (previous iteration's factor, grown by ppbo_factor_extend): no factorisation at all.
+        // First step: alpha is unknown for an arbitrary start, so the full chord step is taken (it only depends on f):
+        //   b = B a0 B' f + beta(f),  alpha <- b - B s0 (I + s0 G s0)^-1 s0 B' Sigma b,  f <- Sigma alpha
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.sa, sa_fac, sizeof(double) * M, cudaMemcpyDeviceToDevice, st));
+        PPBO_CL square_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.sa, M, ws.ap);
+        PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr, nullptr);
+        if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
+        PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
+        if ((rc = blockinv_build(Lfac, ldl, M, Mdinv, ws.binv, st))) return rc;
+        binv_valid = true;
+        if ((rc = potrs_vec_blockinv(Lfac, ldl, M, ws.binv, ws.t, st))) return rc;
+        PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);   // alpha == 0: dalpha = alpha_new
+        if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st))) return rc;
+        PPBO_CL warm_step_size_kernel<<<1, 1024, 0, st>>>(f_map, ws.df, N, ws.scal);
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(alpha, ws.dalpha, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(f_map, ws.df, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+        // T at the new point (the chord acceptance test compares against it)
+        PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, nullptr, nullptr, nullptr);
+        PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
+        PPBO_CL dot_kernel<<<1, 1024, 0, st>>>(alpha, f_map, N, ws.scal);
+        PPBO_LAUNCH_CHECK();
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(scal_h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        T_cur = -0.5 * scal_h[0] - scal_h[24] / m;
+        last_step = scal_h[4];
+        last_rel = warm_first_rel = scal_h[4] / std::fmax(scal_h[5], 1e-300);
+        alpha_known = true;
+        factor_current = true;
+        refactor = false;
+        ++it;
+        ++n_chord;
+        if (trace) fprintf(stderr, "[ppbo_laplace_fit] it 0 warm chord step rel %.3e T %.12g\n", last_rel, T_cur);
+        if (last_rel <= tol) converged = true;
+    }
+    while (it < max_iter && !converged) {
         if (!refactor) {
             // ---- a batch of chord steps: the factor is kept, only the right-hand side is refreshed; acceptance, the convergence
             // test and the contraction test run on the device (chord_decide_kernel), one host synchronise per batch.  The batch
             // length is the number of steps the observed contraction rate predicts (the first batch is short: it measures the rate).
             if (!binv_valid) {
-                if ((rc = blockinv_build(Lfac, M, M, Mdinv, ws.binv, st))) return rc;
+                if ((rc = blockinv_build(Lfac, ldl, M, Mdinv, ws.binv, st))) return rc;
                 binv_valid = true;
             }
             double rho = (std::isfinite(prev_rel_h) && last_rel < prev_rel_h) ? last_rel / prev_rel_h : 0.2;
@@ -446,7 +651,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr, skip);
                 if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st, skip))) return rc;
                 PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t, skip);
-                if ((rc = potrs_vec_blockinv(Lfac, M, M, ws.binv, ws.t, st, skip))) return rc;
+                if ((rc = potrs_vec_blockinv(Lfac, ldl, M, ws.binv, ws.t, st, skip))) return rc;
                 PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha, skip);
                 if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st, skip))) return rc;
                 PPBO_CL chord_lik_kernel<<<set_blocks, 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.state, ws.set_part);
@@ -482,10 +687,11 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         if (identity_factor) {
             PPBO_CUDA_CHECK(cudaMemsetAsync(ws.info, 0, sizeof(int), st));
         } else {
-            if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
-            if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
+            if ((rc = newton_matrix(G, ldg, M, ws.sa, Lfac, ldl, st))) return rc;
+            if ((rc = potrf_lower(Lfac, ldl, M, Mdinv, ws.info, st))) return rc;
             ++n_factor;
             binv_valid = false;
+            factor_current = true;
             chord_omega = 1.0;                   // a new factor: new iteration matrix, forget the contraction history
             chord_ratio = 0.0;
             chord_wait = 0.0;
@@ -496,10 +702,10 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             // From the second factorisation on the factor is very likely reused by chord steps, which need the 1024-block
             // inverses anyway: build them now and let this solve use them too (0.16 ms against 0.48 ms for the chained solve).
             if (n_factor >= 2 && M >= 2048 && !binv_valid) {
-                if ((rc = blockinv_build(Lfac, M, M, Mdinv, ws.binv, st))) return rc;
+                if ((rc = blockinv_build(Lfac, ldl, M, Mdinv, ws.binv, st))) return rc;
                 binv_valid = true;
             }
-            rc = binv_valid ? potrs_vec_blockinv(Lfac, M, M, ws.binv, ws.t, st) : potrs_vec(Lfac, M, M, Mdinv, ws.t, st);
+            rc = binv_valid ? potrs_vec_blockinv(Lfac, ldl, M, ws.binv, ws.t, st) : potrs_vec(Lfac, ldl, M, Mdinv, ws.t, st);
             if (rc) return rc;
         }
         PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);
@@ -553,14 +759,23 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         // chord steps once the Newton iteration is in its contraction region and a factor exists to reuse
         refactor = !(step == 1.0 && last_rel <= CHORD_REL) || identity_factor;
     }
-    (void)converged;
-    // consistent products at the mode: arrow (signed), factor of I + a+^1/2 G a+^1/2
+    // The factor a later warm fit can reuse is the one the last Newton step built (or the warm one it was handed): its
+    // coefficients go to sa_fac.  (An identity "factor" -- cold start that converged at once -- is not a factor object.)
+    bool have_factor = factor_current && !identity_factor;
+    if (sa_fac && have_factor && !factor_at_mode)
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(sa_fac, ws.sa, sizeof(double) * M, cudaMemcpyDeviceToDevice, st));
+    // consistent products at the mode: arrow (signed); with PPBO_FIT_FACTOR_AT_MODE also the factor of I + a+^1/2 G a+^1/2 there
+    // (what prediction WITH covariance needs -- ppbo_laplace_refactor builds it later otherwise)
     PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, arrow, ws.sa, nullptr);
     PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
-    if ((rc = newton_matrix(G, M, M, ws.sa, Lfac, M, st))) return rc;
-    if ((rc = potrf_lower(Lfac, M, M, Mdinv, ws.info, st))) return rc;
-    ++n_factor;
-    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (factor_at_mode) {
+        if ((rc = newton_matrix(G, ldg, M, ws.sa, Lfac, ldl, st))) return rc;
+        if ((rc = potrf_lower(Lfac, ldl, M, Mdinv, ws.info, st))) return rc;
+        ++n_factor;
+        have_factor = true;
+        if (sa_fac) PPBO_CUDA_CHECK(cudaMemcpyAsync(sa_fac, ws.sa, sizeof(double) * M, cudaMemcpyDeviceToDevice, st));
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
     PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
     if (stats_h) {
         stats_h[0] = it;
@@ -571,6 +786,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         stats_h[5] = info;
         stats_h[6] = n_factor;
         stats_h[7] = n_chord;
+        stats_h[8] = factor_at_mode ? 2.0 : (have_factor ? 1.0 : 0.0);   // 2: factor at the mode, 1: last Newton / warm factor, 0: none
+        stats_h[9] = converged ? 1.0 : 0.0;
+        stats_h[10] = warm_first_rel;
     }
     if (info) { set_error("mode system not positive definite at pivot %d", info); return info; }
     return PPBO_OK;

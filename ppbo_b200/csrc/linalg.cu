@@ -1573,6 +1573,163 @@ int trsm_right_lower_t(const double* L, long long ldl, int n, const double* dinv
     return PPBO_OK;
 }
 
+// ------------------------------------------------------------------------------------------- LU with partial pivoting (log-determinant)
+// GPModel.evidence (src/gp_model.py:301-308) takes the log-determinant of the NON-symmetric, possibly indefinite matrix
+// I + Sigma Lambda_MAP through scipy.linalg.lu (LAPACK dgetrf: row pivoting by largest magnitude, first index on ties).  Blocked
+// right-looking LU with the same pivoting rule: per 64-column panel one CTA factors the panel column by column (the panel stays in
+// L2), the row interchanges are applied to the rest of the matrix, U12 = L11^-1 A12 by one thread per column (written transposed as
+// well: the K-contiguous operand of the update), and A22 -= L21 U12 on the FP64 tensor pipe (gemm_nt_store_kernel).  Off the hot
+// path (hyper-parameter search, off by default: ppbo_numerical_main.py:188-190): written for clarity, ~2/3 n^3 flop.
+constexpr int LU_NB = 64;
+
+// one CTA: factor the panel A[j0:n, j0:j0+jb] in place with row pivoting; piv[c] = row chosen for column j0 + c (global index);
+// stat[0] += number of interchanges, stat[1] = 1 if an exactly zero pivot was met
+__global__ void __launch_bounds__(1024) lu_panel_kernel(double* __restrict__ A, long long lda, int n, int j0, int jb,
+                                                        int* __restrict__ piv, int* __restrict__ stat) {
+    __shared__ double vmax[32];
+    __shared__ int imax[32];
+    __shared__ double prow[LU_NB];
+    __shared__ int psel;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = 0; c < jb; ++c) {
+        const int col = j0 + c;
+        // (a) pivot search over rows col .. n-1 : largest |value|, smallest row index on ties
+        double best = -1.0;
+        int bi = col;
+        for (int r = col + tid; r < n; r += 1024) {
+            const double v = fabs(A[(long long)r * lda + col]);
+            if (v > best) { best = v; bi = r; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { vmax[warp] = best; imax[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 32; ++w)
+                if (vmax[w] > best || (vmax[w] == best && imax[w] < bi)) { best = vmax[w]; bi = imax[w]; }
+            psel = bi;
+            piv[c] = bi;
+            if (bi != col) atomicAdd(stat, 1);
+            if (best == 0.0) stat[1] = 1;
+        }
+        __syncthreads();
+        const int pr = psel;
+        // (b) interchange inside the panel, keep the pivot row in shared memory
+        if (tid < jb) {
+            double* a = A + (long long)col * lda + j0 + tid;
+            double* b = A + (long long)pr * lda + j0 + tid;
+            const double va = *a, vb = *b;
+            *a = vb;
+            *b = va;
+            prow[tid] = vb;
+        }
+        __syncthreads();
+        const double inv = 1.0 / prow[c];
+        // (c) multipliers and the rank-1 update of the remaining panel columns: thread = (row, 8 columns)
+        const int rem = jb - c - 1;
+        for (int r = col + 1 + warp; r < n; r += 32) {
+            double* row = A + (long long)r * lda + col;
+            const double l = row[0] * inv;
+            __syncwarp();
+            if (lane == 0) row[0] = l;
+            for (int k = 1 + lane; k <= rem; k += 32) row[k] = fma(-l, prow[c + k], row[k]);
+        }
+        __syncthreads();
+    }
+}
+// apply the panel's interchanges to the columns outside the panel (in order)
+__global__ void __launch_bounds__(256) lu_swap_kernel(double* __restrict__ A, long long lda, int n, int j0, int jb,
+                                                      const int* __restrict__ piv) {
+    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= j0) col += jb;
+    if (col >= n) return;
+    for (int c = 0; c < jb; ++c) {
+        const int p = piv[c];
+        if (p != j0 + c) {
+            const double a = A[(long long)(j0 + c) * lda + col], b = A[(long long)p * lda + col];
+            A[(long long)(j0 + c) * lda + col] = b;
+            A[(long long)p * lda + col] = a;
+        }
+    }
+}
+// U12 = L11^-1 A12 (unit lower L11, jb x jb) for the columns right of the panel; Ut[col - j1][k] = U12[k][col]
+__global__ void __launch_bounds__(128) lu_u12_kernel(double* __restrict__ A, long long lda, int n, int j0, int jb,
+                                                     double* __restrict__ Ut) {
+    __shared__ double L11[LU_NB][LU_NB + 1];
+    for (int e = threadIdx.x; e < jb * jb; e += blockDim.x) L11[e / jb][e % jb] = A[(long long)(j0 + e / jb) * lda + j0 + e % jb];
+    __syncthreads();
+    const int j1 = j0 + jb;
+    const int col = j1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n) return;
+    double u[LU_NB];
+#pragma unroll 8
+    for (int k = 0; k < LU_NB; ++k) u[k] = (k < jb) ? A[(long long)(j0 + k) * lda + col] : 0.0;
+#pragma unroll 4
+    for (int k = 0; k < LU_NB; ++k) {
+        if (k >= jb) break;
+        const double x = u[k];
+        for (int r = k + 1; r < jb; ++r) u[r] = fma(-L11[r][k], x, u[r]);
+    }
+    for (int k = 0; k < jb; ++k) {
+        A[(long long)(j0 + k) * lda + col] = u[k];
+        Ut[(long long)(col - j1) * LU_NB + k] = u[k];
+    }
+}
+// out[0] = sign of prod_i A[i][i], out[1] = sum_i log |A[i][i]|   (single CTA, fixed order)
+__global__ void __launch_bounds__(1024) lu_diag_logdet_kernel(const double* __restrict__ A, long long lda, int n, double* __restrict__ out) {
+    __shared__ double red[33];
+    double s = 0.0, neg = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const double d = A[(long long)i * lda + i];
+        s += log(fabs(d));
+        if (d < 0.0) neg += 1.0;
+    }
+    s = block_sum(s, red);
+    neg = block_sum(neg, red);
+    if (threadIdx.x == 0) {
+        out[0] = (fmod(neg, 2.0) == 0.0) ? 1.0 : -1.0;
+        out[1] = s;
+    }
+}
+
+long long lu_workspace_doubles(int n) { return (long long)n * LU_NB + 8 + LU_NB; }
+
+// in-place LU of A[n x n]; res_h[0] = sign(det U), res_h[1] = log|det U| = log|det A|, res_h[2] = sign of the row permutation
+int lu_logdet(double* A, long long lda, int n, double* ws, double* res_h, cudaStream_t st) {
+    double* Ut = ws;
+    double* outd = ws + (long long)n * LU_NB;
+    int* piv = reinterpret_cast<int*>(outd + 4);
+    int* stat = piv + LU_NB;
+    PPBO_CUDA_CHECK(cudaMemsetAsync(stat, 0, 2 * sizeof(int), st));
+    for (int j0 = 0; j0 < n; j0 += LU_NB) {
+        const int jb = min(LU_NB, n - j0), j1 = j0 + jb;
+        PPBO_CL lu_panel_kernel<<<1, 1024, 0, st>>>(A, lda, n, j0, jb, piv, stat);
+        if (n - jb > 0) PPBO_CL lu_swap_kernel<<<ceil_div(n - jb, 256), 256, 0, st>>>(A, lda, n, j0, jb, piv);
+        if (j1 < n) {
+            PPBO_CL lu_u12_kernel<<<ceil_div(n - j1, 128), 128, 0, st>>>(A, lda, n, j0, jb, Ut);
+            PPBO_LAUNCH_CHECK();
+            GemmOperands g{A + (long long)j1 * lda + j0, lda, 0, Ut, LU_NB, 0, n - j1, n - j1, jb};
+            StoreEpilogue ep{A + (long long)j1 * lda + j1, lda, 0, -1.0, 1.0, 0, 0, 0};
+            int rc = launch_gemm_nt(g, ep, 1, st);
+            if (rc) return rc;
+        }
+    }
+    PPBO_CL lu_diag_logdet_kernel<<<1, 1024, 0, st>>>(A, lda, n, outd);
+    PPBO_LAUNCH_CHECK();
+    double h[2];
+    int sh[2];
+    PPBO_CUDA_CHECK(cudaMemcpyAsync(h, outd, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(cudaMemcpyAsync(sh, stat, sizeof(sh), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    res_h[0] = h[0];
+    res_h[1] = h[1];
+    res_h[2] = (sh[0] % 2 == 0) ? 1.0 : -1.0;
+    return sh[1] ? 1 : PPBO_OK;          // 1: exactly singular
+}
+
 }  // namespace ppbo
 
 // =========================================================================================== C ABI
@@ -1689,6 +1846,18 @@ extern "C" int ppbo_potri_lower(const double* L, long long ldl, int n, void* wor
     GemmOperands g{work, n, 0, work, n, 0, n, n, n};
     StoreEpilogue ep{out, ldo, 0, 1.0, 0.0, 0, 0, 0};
     return launch_gemm_nt(g, ep, 1, st);
+}
+
+extern "C" long long ppbo_lu_workspace_bytes(int n) { return n > 0 ? lu_workspace_doubles(n) * 8 : 0; }
+
+/* In-place LU with partial pivoting of A[n x n]; result_h[3] = { sign(det U), log|det A|, sign of the row permutation }.
+ * Replaces scipy.linalg.lu + numpy.linalg.slogdet in GPModel.evidence (src/gp_model.py:303-308).  Returns 1 when a pivot is
+ * exactly zero. */
+extern "C" int ppbo_lu_logdet(double* A, long long lda, int n, void* workspace, long long workspace_bytes, double* result_h,
+                              void* stream) {
+    PPBO_REQUIRE(n >= 1 && lda >= n && result_h != nullptr, "shape");
+    PPBO_REQUIRE(workspace_bytes >= ppbo_lu_workspace_bytes(n), "workspace too small");
+    return lu_logdet(A, lda, n, reinterpret_cast<double*>(workspace), result_h, (cudaStream_t)stream);
 }
 
 extern "C" int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, double* y, void* stream) {

@@ -74,16 +74,23 @@ class Shard:
         hi = (S * (self.rank + 1)) // self.world
         return lo, hi
 
-    def sample_bounds(self, S):
-        """Partition of the Monte-Carlo samples inside run_iteration.  With more than one rank the rank that runs the GP fit
-        (rank 0) takes none: the sampling contraction does not depend on the GP fit -- only the final reduction needs mu* --
-        so the other ranks evaluate all samples WHILE rank 0 fits, and the GP fit is the critical path of the iteration anyway."""
+    def sample_bounds(self, S, shares=None):
+        """Partition of the Monte-Carlo samples inside run_iteration.  shares: one non-negative weight per rank (plan_shares);
+        the default gives the rank that runs the GP fit (rank 0) none: the sampling contraction does not depend on the GP fit
+        -- only the final reduction needs mu* -- so the other ranks evaluate all samples WHILE rank 0 fits.  Boundaries are
+        multiples of 128 samples (one row tile of the tensor-core kernel) except the last."""
         if self.world == 1:
             return 0, S
-        if self.rank == 0:
-            return 0, 0
-        w = self.world - 1
-        return (S * (self.rank - 1)) // w, (S * self.rank) // w
+        if shares is None:
+            shares = [0.0] + [1.0] * (self.world - 1)
+        tot = float(sum(shares))
+        cum, edges = 0.0, [0]
+        for w in shares:
+            cum += w
+            e = int(round(S * cum / tot / 128.0)) * 128
+            edges.append(min(S, max(edges[-1], e)))
+        edges[-1] = S
+        return edges[self.rank], edges[self.rank + 1]
 
     def broadcast(self, t, src=0):
         if self.dist and self.world > 1:
@@ -94,6 +101,28 @@ class Shard:
         if self.dist and self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def all_reduce_max(self, t):
+        if self.dist and self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+
+def plan_shares(world, t_gp, t_rff, t_sampling, rff_rank=1):
+    """Sample shares per rank from measured stage times (ms): rank 0 is busy with the GP fit + mu* for t_gp, every other rank can
+    start sampling when the weight-space fit (t_rff, on rff_rank) has been broadcast, and the whole sample set costs t_sampling
+    on one GPU.  Water-filling: all ranks that sample finish together at time t with sum_r max(0, t - start_r) = t_sampling."""
+    if world == 1:
+        return [1.0]
+    starts = [t_gp if r == 0 else t_rff for r in range(world)]
+    order = sorted(range(world), key=lambda r: starts[r])
+    t = starts[order[0]]
+    for k in range(1, world + 1):
+        active = order[:k]
+        t = (t_sampling + sum(starts[r] for r in active)) / k
+        if k == world or t <= starts[order[k]]:
+            break
+    return [max(0.0, t - starts[r]) for r in range(world)]
 
 
 class GPFit:
@@ -109,18 +138,101 @@ class GPFit:
         return self.lap.alpha
 
 
-def gp_fit(X, kernel, theta, Q, m, f_init=None, lengthscales=None, max_iter=100, tol=1e-10, shrinkage=SHRINKAGE):
-    """Sigma = reg(K(X,X)) and the Laplace mode of T (update_Sigma + update_fMAP + Lambda_MAP, src/gp_model.py:157,354,111)."""
+def gp_fit(X, kernel, theta, Q, m, f_init=None, lengthscales=None, max_iter=100, tol=1e-10, shrinkage=SHRINKAGE,
+           factor_at_mode=False):
+    """Sigma = reg(K(X,X)) and the Laplace mode of T (update_Sigma + update_fMAP + Lambda_MAP, src/gp_model.py:157,354,111).
+    factor_at_mode: also leave the Cholesky factor of the Newton matrix AT the mode behind (prediction with covariance needs it;
+    the RFF acquisition and mu* do not -- LaplaceFit builds it on first use otherwise)."""
     g = GPFit()
     g.X, g.kernel, g.theta, g.Q, g.m = X, kernel, [float(t) for t in theta], Q, m
     g.lengthscales = theta[1] if lengthscales is None else lengthscales
     if X.shape[0] != Q * (m + 1):
         raise PPBOError("X must have Q (m+1) rows")
     g.Sigma = ops.gram_regularized(kernel, X, g.lengthscales, theta[2], shrinkage)
-    g.lap = ops.laplace_fit(g.Sigma, Q, m, theta[0], f_init=f_init, max_iter=max_iter, tol=tol)
+    g.lap = ops.laplace_fit(g.Sigma, Q, m, theta[0], f_init=f_init, max_iter=max_iter, tol=tol, factor_at_mode=factor_at_mode)
     if g.lap.info != 0:
         raise PPBOError("Laplace fit: system not positive definite (info=%d)" % g.lap.info)
     return g
+
+
+class GPState(GPFit):
+    """A GP model that grows in place (FeedbackProcessing.update_X appends one (m+1)-row block per
+    iteration, src/feedback_processing.py:133-154).  Capacity buffers for X, Sigma, G = B' Sigma B and the factor object; `append`
+    adds comparison sets in O(N^2 m): new rows of Sigma and G, the factor of the previous iteration grown by the new rows, and
+    a chord iteration from the previous mode (new points start at their posterior mean) -- no O(N^3) factorisation unless the
+    chord steps contract too slowly (ppbo_laplace_fit falls back to a Newton step by itself)."""
+    __slots__ = ("Q_cap", "X_cap", "Sigma_cap", "f_buf", "alpha_buf", "arrow_buf", "f_init_buf", "shrinkage", "max_iter", "tol")
+
+    def __init__(self, kernel, theta, D, m, Q_cap, dev, lengthscales=None, max_iter=100, tol=1e-8, shrinkage=SHRINKAGE):
+        lib = ops._lib.load()
+        self.kernel, self.theta, self.m, self.Q, self.Q_cap = kernel, [float(t) for t in theta], m, 0, Q_cap
+        self.lengthscales = theta[1] if lengthscales is None else lengthscales
+        self.shrinkage, self.max_iter, self.tol = shrinkage, max_iter, tol
+        Nc, Mc = Q_cap * (m + 1), Q_cap * m
+        self.X_cap = torch.empty((Nc, D), dtype=F64, device=dev)
+        self.Sigma_cap = torch.empty((Nc, Nc), dtype=F64, device=dev)
+        self.f_buf, self.alpha_buf, self.f_init_buf = (torch.empty(Nc, dtype=F64, device=dev) for _ in range(3))
+        self.arrow_buf = torch.empty(Mc, dtype=F64, device=dev)
+        lap = ops.LaplaceFit()
+        lap.cap = lap.ldg = Mc
+        lap.G = torch.empty((Mc, Mc), dtype=F64, device=dev)
+        lap._Lfac = torch.empty(lib.ppbo_factor_doubles(Mc), dtype=F64, device=dev)
+        lap.sa_fac = torch.empty(Mc, dtype=F64, device=dev)
+        lap.m, lap.Q, lap.sigma, lap.info, lap.factor_state = m, 0, float(theta[0]), 0, 0
+        self.lap = lap
+        self.X = self.Sigma = None
+
+    def _views(self, Q):
+        N, M = Q * (self.m + 1), Q * self.m
+        self.X, self.Sigma = self.X_cap[:N], self.Sigma_cap[:N, :N]
+        self.lap.f_map, self.lap.alpha, self.lap.arrow = self.f_buf[:N], self.alpha_buf[:N], self.arrow_buf[:M]
+        return N, M
+
+    def cold(self, X, f_init=None, factor_at_mode=False):
+        """fit from scratch on X [Q (m+1) x D] (device)"""
+        Q = X.shape[0] // (self.m + 1)
+        if Q > self.Q_cap or Q * (self.m + 1) != X.shape[0]:
+            raise PPBOError("X must have Q (m+1) rows with Q <= capacity")
+        N, _ = self._views(Q)
+        self.X_cap[:N].copy_(X)
+        ops.gram_regularized(self.kernel, self.X, self.lengthscales, self.theta[2], self.shrinkage, out=self.Sigma)
+        ops.laplace_fit(self.Sigma, Q, self.m, self.theta[0], f_init=f_init, max_iter=self.max_iter, tol=self.tol,
+                        factor_at_mode=factor_at_mode, into=self.lap)
+        if self.lap.info != 0:
+            raise PPBOError("Laplace fit: system not positive definite (info=%d)" % self.lap.info)
+        self.Q = Q
+        return self
+
+    def append(self, X_block, factor_at_mode=False):
+        """add the comparison sets X_block [q (m+1) x D] (device) and refit from the previous mode"""
+        if self.Q == 0:
+            return self.cold(X_block, factor_at_mode=factor_at_mode)
+        m, Q_old = self.m, self.Q
+        Q_new = Q_old + X_block.shape[0] // (m + 1)
+        if Q_new > self.Q_cap or X_block.shape[0] % (m + 1):
+            raise PPBOError("appended rows must be whole comparison sets within the capacity")
+        N_old, M_old = Q_old * (m + 1), Q_old * m
+        alpha_old = self.alpha_buf[:N_old]
+        warm = self.lap.factor_state >= 1 and self.lap.info == 0
+        N, M = self._views(Q_new)
+        self.X_cap[N_old:N].copy_(X_block)
+        ops.gram_append(self.kernel, self.X, N_old, self.lengthscales, self.theta[2], self.shrinkage, self.Sigma_cap)
+        ops.diffspace_gram_append(self.Sigma, Q_old, Q_new, m, self.lap.G)
+        # warm start: the previous mode on the old rows, the posterior mean k(x_new, X_old) alpha_old on the new ones (the
+        # reference pads with the mean of fMAP, src/gp_model.py:375-377; both are starts for the same fixed point)
+        f_init = self.f_init_buf[:N]
+        f_init[:N_old].copy_(self.f_buf[:N_old])
+        ops.gemv(self.Sigma_cap[N_old:N, :N_old], alpha_old, out=f_init[N_old:])
+        self.lap.Q = Q_new
+        if warm:
+            info = ops.factor_extend(self.lap, M_old, M, f_new_sets=f_init[N_old:], sigma=self.theta[0])
+            warm = info == 0
+        ops.laplace_fit(self.Sigma, Q_new, m, self.theta[0], f_init=f_init, max_iter=self.max_iter, tol=self.tol,
+                        factor_at_mode=factor_at_mode, into=self.lap, g_ready=True, warm_factor=warm)
+        if self.lap.info != 0:
+            raise PPBOError("Laplace fit: system not positive definite (info=%d)" % self.lap.info)
+        self.Q = Q_new
+        return self
 
 
 def posterior_mean(g, Xp):
@@ -154,6 +266,40 @@ def rff_fit(X, W, b, theta, Q, m, omega0=None, max_iter=100, tol=1e-10, f_map=No
     if r.stats["info"] != 0:
         raise PPBOError("RFF fit: weight-space Hessian not positive definite (info=%d)" % r.stats["info"])
     return r
+
+
+class RFFState:
+    """Weight-space model that grows with the design: capacity buffer for Phi_X [F x N_cap]; `append` adds the features of the new
+    rows and refits from the previous omega_MAP."""
+
+    def __init__(self, W, b, theta, m, Q_cap, max_iter=100, tol=1e-8):
+        self.W, self.b, self.theta, self.m, self.Q, self.Q_cap = W, b, [float(t) for t in theta], m, 0, Q_cap
+        self.max_iter, self.tol = max_iter, tol
+        self.Phi_cap = torch.empty((W.shape[0], Q_cap * (m + 1)), dtype=F64, device=W.device)
+        self.fit = None
+
+    def _fit(self, Q, omega0):
+        r = RFFFit()
+        r.W, r.b, r.sigma_f = self.W, self.b, self.theta[2]
+        r.Phi_X = self.Phi_cap[:, :Q * (self.m + 1)]
+        r.omega_map, r.hess_diag, r.stats = ops.rff_fit(r.Phi_X, Q, self.m, self.theta[0], omega0=omega0, max_iter=self.max_iter,
+                                                        tol=self.tol)
+        if r.stats["info"] != 0:
+            raise PPBOError("RFF fit: weight-space Hessian not positive definite (info=%d)" % r.stats["info"])
+        self.Q, self.fit = Q, r
+        return r
+
+    def cold(self, X, omega0=None):
+        Q = X.shape[0] // (self.m + 1)
+        ops.rff_features(self.W, self.b, X, self.theta[2], True, out=self.Phi_cap[:, :X.shape[0]])
+        return self._fit(Q, omega0)
+
+    def append(self, X_block):
+        if self.Q == 0:
+            return self.cold(X_block)
+        N_old = self.Q * (self.m + 1)
+        ops.rff_features(self.W, self.b, X_block, self.theta[2], True, out=self.Phi_cap[:, N_old:N_old + X_block.shape[0]])
+        return self._fit(self.Q + X_block.shape[0] // (self.m + 1), self.fit.omega_map)
 
 
 def rff_start_from_gp(Phi_X, f_map, ridge=1e-3):
@@ -301,28 +447,93 @@ def _side_stream(dev, priority=0, tag=""):
     return _SIDE_STREAMS[key]
 
 
-def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, tol=1e-8, timers=None):
+class IterationState:
+    """What persists between the iterations of one PPBO run on this rank: the growing GP model (rank 0) and the growing
+    weight-space model (the rank that runs the weight-space fit)."""
+
+    def __init__(self, kernel, theta, D, m, Q_cap, dev, W, b, shard=None, fit_iters=100, tol=1e-8):
+        shard = shard or Shard()
+        rff_rank = 1 if (CONCURRENT_FITS and shard.world > 1) else 0
+        self.gp = GPState(kernel, theta, D, m, Q_cap, dev, max_iter=fit_iters, tol=tol) if shard.rank == 0 else None
+        self.rff = RFFState(W, b, theta, m, Q_cap, max_iter=fit_iters, tol=tol) if shard.rank == rff_rank else None
+        self.Q, self.m = 0, m
+        self.X_cap = torch.empty((Q_cap * (m + 1), D), dtype=F64, device=dev)       # the design, on every rank (mu* slices)
+
+    def design(self, Q):
+        return self.X_cap[:Q * (self.m + 1)]
+
+
+def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, tol=1e-8, timers=None, state=None, shares=None,
+                  factor_at_mode=False):
     """d: dict of device tensors (IterationInputs.to_device).  Returns (sums [B,3] device, gp, rff).
     Rank 0 fits; the others receive (omega_MAP, hess_diag, mu*) by broadcast while they compute the grid features.
     tol: both Newton iterations stop when the last full step is below tol relative to the iterate.  The chord steps contract
     by ~5x per step, so the distance to the mode is ~tol/4 = 2.5e-9 at the default: 400x inside the 1e-6 parity bound of
-    BASELINE.json and far below the reference's own stopping rule (|grad T| < 1e-4, src/gp_model.py:382)."""
+    BASELINE.json and far below the reference's own stopping rule (|grad T| < 1e-4, src/gp_model.py:382).
+    state: an IterationState makes the models persistent: the first call fits from scratch into its capacity buffers (d["X"]),
+    later calls APPEND the comparison sets d["block"] (Q is the new total) and refit from the previous modes.
+    shares: sample share per rank (plan_shares); default: rank 0 of several takes none.
+    factor_at_mode: also produce the Cholesky factor at the GP mode (only prediction with covariance needs it)."""
     shard = shard or Shard()
-    X, W, b, grids = d["X"], d["W"], d["b"], d["grids"]
+    W, b, grids = d["W"], d["b"], d["grids"]
+    dev = W.device
     Fdim = W.shape[0]
     B, P, D = grids.shape
+    warm = state is not None and state.Q > 0
+    X = None if warm else d["X"]
+    block = d["block"] if warm else None
+    if state is not None:
+        if warm:
+            state.X_cap[state.Q * (m + 1):Q * (m + 1)].copy_(block)
+        else:
+            state.X_cap[:Q * (m + 1)].copy_(X)
 
     def mark(name):
         if timers is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             timers.append((name, ev))
+
+    def fit_gp():
+        if state is None:
+            return gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol, factor_at_mode=factor_at_mode)
+        if warm:
+            return state.gp.append(block, factor_at_mode=factor_at_mode)
+        return state.gp.cold(X, f_init=d.get("f_init"), factor_at_mode=factor_at_mode)
+
+    def fit_rff():
+        if state is None:
+            return rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+        if warm:
+            return state.rff.append(block)
+        return state.rff.cold(X, omega0=d.get("omega0"))
+
+    def mu_star(gp, cand):
+        """max posterior mean over the design rows and the candidate points; with >= 3 ranks every rank takes a slice of the
+        candidates (alpha travels by broadcast) and one all-reduce(max) follows"""
+        if shard.world < 3:
+            return mustar_over_candidates(gp, cand) if shard.rank == 0 else None
+        Qn = Q
+        N = Qn * (m + 1)
+        pack_a = torch.empty(N + 1, dtype=F64, device=dev)          # alpha and max f_MAP
+        if shard.rank == 0:
+            pack_a[:N].copy_(gp.alpha)
+            ops.vec_max(gp.f_map, out=pack_a[N:])
+        shard.broadcast(pack_a, src=0)
+        lo_c, hi_c = shard.bounds(cand.shape[0])
+        out = pack_a[N:].clone()
+        if hi_c > lo_c:
+            Xd = state.design(Q) if state is not None else X
+            mu = ops.posterior_mean(kernel, Xd, theta[1], theta[2], pack_a[:N], cand[lo_c:hi_c])
+            ops.vec_max(mu, out=out, accumulate=True)
+        shard.all_reduce_max(out)
+        return out
     mark("start")
-    lo, hi = shard.sample_bounds(S)
+    lo, hi = shard.sample_bounds(S, shares)
     # The grid features (and their digit planes) do not depend on the fit.  On the rank that runs the latency-bound GP fit they
     # go to the side stream and fill SMs the fit leaves idle; the other ranks compute them while they wait for the broadcast.
     main = torch.cuda.current_stream()
-    grid_stream = _side_stream(X.device, tag="grid") if shard.rank == 0 else main
+    grid_stream = _side_stream(dev, tag="grid") if shard.rank == 0 else main
     if grid_stream is not main:
         grid_stream.wait_stream(main)
     PhiT = None
@@ -332,36 +543,37 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
             if sampling_engine(hi - lo, P, Fdim) == "i8":
                 PhiT = SlicedGrids(PhiT)                      # digit planes of the grid features
     mark("grid_features")
-    pack = torch.empty(2 * Fdim + 1, dtype=F64, device=X.device)
+    pack = torch.empty(2 * Fdim + 1, dtype=F64, device=dev)
     gp = rff = prepared = None
+    cand = grids.reshape(B * P, D)
     rff_rank = 1 if (CONCURRENT_FITS and shard.world > 1) else 0      # with more than one GPU the two fits run on two of them
     if shard.rank == 0 and CONCURRENT_FITS and shard.world == 1:
         # GP fit: foreground, on a stream one priority level above the default; weight-space fit: a persistent background host
         # thread whose streams all sit at the lowest priority, so it only takes the SMs the GP fit leaves idle.
-        side = _side_stream(X.device)
+        side = _side_stream(dev)
         side.wait_stream(main)
-        gp_stream = _side_stream(X.device, priority=GP_STREAM_PRIORITY, tag="gp") if GP_STREAM_PRIORITY else main
+        gp_stream = _side_stream(dev, priority=GP_STREAM_PRIORITY, tag="gp") if GP_STREAM_PRIORITY else main
         if gp_stream is not main:
             gp_stream.wait_stream(main)
 
         def weight_space_fit():
-            torch.cuda.set_device(X.device)
+            torch.cuda.set_device(dev)
             with torch.cuda.stream(side):
-                fit = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+                fit = fit_rff()
                 # the draws and their digit planes need this fit only: done here, behind the GP fit
                 return fit, rff_prepare_samples(fit, lo, hi, P, seed=seed)
         fut = _background_worker().submit(weight_space_fit)
         try:
             with torch.cuda.stream(gp_stream):
-                gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
+                gp = fit_gp()
                 mark("gp_fit")
-                mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
+                mustar = mustar_over_candidates(gp, cand)
                 mark("mustar")
         finally:
             rff, prepared = fut.result()       # re-raises on this thread
         if gp_stream is not main:
             main.wait_stream(gp_stream)
-            for t in (gp.Sigma, gp.lap.G, gp.lap.Lfac, gp.lap.f_map, gp.lap.alpha, gp.lap.arrow, mustar):
+            for t in (gp.Sigma, gp.lap.G, gp.lap._Lfac, gp.lap.f_map, gp.lap.alpha, gp.lap.arrow, mustar):
                 t.record_stream(main)
         main.wait_stream(side)
         for t in (rff.omega_map, rff.hess_diag, rff.Phi_X) + ((prepared.planes, prepared.scale) if isinstance(prepared, SlicedSamples)
@@ -369,27 +581,23 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
             t.record_stream(main)
         mark("rff_fit")                        # what is left of the weight-space fit after the GP fit has finished
     elif shard.world > 1 and CONCURRENT_FITS:
-        # Several ranks: rank 0 runs the GP fit and nothing else; rank 1 runs the weight-space fit and broadcasts it; ranks >= 1
-        # draw and evaluate ALL samples while rank 0 is still fitting (the contraction needs the weight-space fit only); when
-        # mu* arrives from rank 0 only the reduction and the all-reduce of 3 B doubles are left.
+        # Several ranks: rank 0 runs the GP fit; rank 1 runs the weight-space fit and broadcasts it; every rank with a sample share
+        # draws and evaluates its samples as soon as the weight-space fit has arrived (the contraction needs that fit only) --
+        # rank 0 after its GP fit; when mu* is known only the reduction and the all-reduce of 3 B doubles are left.
         pack_rff, mu_t = pack[:2 * Fdim], pack[2 * Fdim:]
+        fmax = None
         if shard.rank == 0:
-            bstream = _side_stream(X.device, tag="bcast")     # rank 0 joins the first broadcast off its critical path
+            bstream = _side_stream(dev, tag="bcast")     # rank 0 joins the first broadcast off its critical path
             bstream.wait_stream(main)
             pack.record_stream(bstream)
             with torch.cuda.stream(bstream):
                 shard.broadcast(pack_rff, src=rff_rank)
-            gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
+            gp = fit_gp()
             mark("gp_fit")
-            mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
-            mark("mustar")
-            mu_t.copy_(mustar)
             main.wait_stream(bstream)
-            shard.broadcast(mu_t, src=0)
-            fmax = None
         else:
             if shard.rank == rff_rank:
-                rff = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol)
+                rff = fit_rff()
                 mark("rff_fit")
                 pack_rff[:Fdim].copy_(rff.omega_map)
                 pack_rff[Fdim:].copy_(rff.hess_diag)
@@ -398,22 +606,37 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
             rff = RFFFit()
             rff.W, rff.b, rff.sigma_f, rff.Phi_X, rff.stats = W, b, float(theta[2]), None, None
         rff.omega_map, rff.hess_diag = pack_rff[:Fdim], pack_rff[Fdim:]
-        if shard.rank != 0:
+        if shard.rank != 0 and hi > lo:
             fmax, _ = rff_sampled_maxima(rff, PhiT, lo, hi, seed=seed)
             mark("sampling")
+        if shard.world >= 3:
+            mustar = mu_star(gp, cand)
+            mu_t.copy_(mustar)
+        else:
+            if shard.rank == 0:
+                mu_t.copy_(mustar_over_candidates(gp, cand))
             shard.broadcast(mu_t, src=0)
+        mark("mustar")
+        if shard.rank == 0 and hi > lo:
+            if grid_stream is not main:
+                main.wait_stream(grid_stream)
+                for t in ((PhiT.PhiT, PhiT.planes, PhiT.scale) if isinstance(PhiT, SlicedGrids) else (PhiT,)):
+                    t.record_stream(main)
+            fmax, _ = rff_sampled_maxima(rff, PhiT, lo, hi, seed=seed)
+            mark("sampling")
         sums = rff_reduce(fmax, mu_t, B, shard)
         mark("acquisition")
+        if state is not None:
+            state.Q = Q
         return sums, gp, rff
     else:
         if shard.rank == 0:
-            gp = gp_fit(X, kernel, theta, Q, m, f_init=d.get("f_init"), max_iter=fit_iters, tol=tol)
+            gp = fit_gp()
             mark("gp_fit")
-            mustar = mustar_over_candidates(gp, grids.reshape(B * P, D))
+            mustar = mustar_over_candidates(gp, cand)
             mark("mustar")
         if shard.rank == rff_rank:
-            rff = rff_fit(X, W, b, theta, Q, m, omega0=d.get("omega0"), max_iter=fit_iters, tol=tol,
-                          f_map=gp.f_map if (gp is not None and not CONCURRENT_FITS) else None)
+            rff = fit_rff()
             mark("rff_fit")
     if shard.rank == rff_rank:
         pack[:Fdim].copy_(rff.omega_map)
@@ -437,4 +660,6 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
     sums, fmax, arg = rff_acquisition(rff, PhiT, S, pack[2 * Fdim:], shard=shard, seed=seed, bounds=(lo, hi), prepared=prepared,
                                       n_grids=B)
     mark("acquisition")
+    if state is not None:
+        state.Q = Q
     return sums, gp, rff

@@ -62,7 +62,7 @@ def gram_regularized(kernel, X, lengthscales, sigma_f, shrinkage, out=None):
     n, D = X.shape
     out = torch.empty((n, n), dtype=F64, device=X.device) if out is None else out
     check(_lib.load().ppbo_gram_regularized(_kind(kernel), _p(X), n, D, _ls(lengthscales, D), float(sigma_f),
-                                            float(shrinkage), _p(out), max(n, 1), _stream()), "ppbo_gram_regularized")
+                                            float(shrinkage), _p(out), max(out.stride(0), 1), _stream()), "ppbo_gram_regularized")
     return out
 
 
@@ -100,51 +100,124 @@ def diffspace_gram(Sigma, Q, m):
 
 
 class LaplaceFit:
-    """Device-resident products of the MAP fit (everything prediction / acquisition needs)."""
-    __slots__ = ("Q", "m", "sigma", "f_map", "alpha", "arrow", "G", "Lfac", "stats", "n_neg", "_neg_idx", "_neg_corr", "info")
+    """Device-resident products of the MAP fit (everything prediction / acquisition needs).
+
+    G and the factor object may have a capacity larger than the problem (`cap` >= Q m, leading dimensions `ldg`, `cap`), so that
+    a model can grow in place (ModelState in iteration.py).  The factor AT the mode is only needed by prediction with covariance:
+    it is built on first read of `Lfac` when the fit skipped it (`factor_state` < 2)."""
+    __slots__ = ("Q", "m", "sigma", "f_map", "alpha", "arrow", "G", "ldg", "cap", "_Lfac", "sa_fac", "factor_state", "stats",
+                 "n_neg", "_neg_idx", "_neg_corr", "info")
+
+    @property
+    def M(self):
+        return self.Q * self.m
+
+    @property
+    def Lfac(self):
+        """factor object holding chol(I + a+^1/2 G a+^1/2) at the mode"""
+        if self.factor_state < 2 and self.info == 0:
+            rc = check(_lib.load().ppbo_laplace_refactor(_p(self.G), self.ldg, self.M, _p(self.arrow), _p(self._Lfac), self.cap,
+                                                         _p(self.sa_fac), _stream()), "ppbo_laplace_refactor")
+            if rc > 0:
+                self.info = rc
+                raise PPBOError("mode system not positive definite (pivot %d)" % rc)
+            self.factor_state = 2
+        return self._Lfac
+
+    @property
+    def L(self):
+        """the M x M lower factor at the mode as a strided view"""
+        buf = self.Lfac
+        return buf[:self.cap * self.cap].view(self.cap, self.cap)[:self.M, :self.M]
+
+    def count_negative(self):
+        """number (and indices) of negative likelihood-curvature coefficients at the mode; host sync"""
+        if self._neg_idx is None:
+            idx = (ctypes.c_int * self.M)()
+            self.n_neg = check(_lib.load().ppbo_neg_count(_p(self.arrow), self.M, idx, self.M, _stream()), "ppbo_neg_count")
+            self._neg_idx = idx
+        return self.n_neg
 
     @property
     def neg_corr(self):
         """Exact rank-r Woodbury correction of the posterior covariance for the r observations with a negative likelihood
         curvature (W indefinite there; the factor carries a+ only).  Only prediction WITH covariance needs it, so it is
         built on first use (r solves with the factor) instead of inside every fit."""
+        self.count_negative()
         if self._neg_corr is None and self.n_neg > 0 and self.info == 0:
             lib = _lib.load()
-            M = self.Q * self.m
+            M = self.M
+            Lf = self.Lfac
             self._neg_corr = torch.empty(lib.ppbo_neg_corr_doubles(M, self.n_neg), dtype=F64, device=self.G.device)
-            rc2 = check(lib.ppbo_neg_corr_build(_p(self.G), M, _p(self.arrow), _p(self.Lfac), self._neg_idx, self.n_neg,
-                                                _p(self._neg_corr), _stream()), "ppbo_neg_corr_build")
+            rc2 = check(lib.ppbo_neg_corr_build(_p(self.G), self.ldg, M, _p(self.arrow), _p(Lf), self.cap, self._neg_idx,
+                                                self.n_neg, _p(self._neg_corr), _stream()), "ppbo_neg_corr_build")
             if rc2 > 0:
                 self.info = rc2
         return self._neg_corr
 
 
-def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10):
+_STATS = ("iterations", "last_step", "last_rel_step", "T", "halvings", "info", "factorizations", "chord_steps", "factor_state",
+          "converged", "warm_first_rel")
+
+
+def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10, factor_at_mode=False, into=None, g_ready=False,
+                warm_factor=False):
+    """MAP fit.  `into`: a LaplaceFit whose (capacity) buffers G / factor / sa_fac are reused -- with g_ready the grown G is
+    taken as is, with warm_factor the factor left by the previous fit (grown by factor_extend) starts the chord iteration."""
     lib = _lib.load()
     dev = Sigma.device
     N, M = Q * (m + 1), Q * m
-    fit = LaplaceFit()
+    if into is None:
+        fit = LaplaceFit()
+        fit.cap = fit.ldg = M
+        fit.G = torch.empty((M, M), dtype=F64, device=dev)
+        fit._Lfac = torch.empty(lib.ppbo_factor_doubles(M), dtype=F64, device=dev)
+        fit.sa_fac = torch.empty(M, dtype=F64, device=dev)
+        fit.f_map = torch.empty(N, dtype=F64, device=dev)
+        fit.alpha = torch.empty(N, dtype=F64, device=dev)
+        fit.arrow = torch.empty(M, dtype=F64, device=dev)
+    else:
+        fit = into
+        if fit.cap < M:
+            raise PPBOError("model capacity %d below Q m = %d" % (fit.cap, M))
     fit.Q, fit.m, fit.sigma = Q, m, float(sigma)
-    fit.G = torch.empty((M, M), dtype=F64, device=dev)
-    fit.Lfac = torch.empty(lib.ppbo_factor_doubles(M), dtype=F64, device=dev)
-    fit.f_map = torch.empty(N, dtype=F64, device=dev)
-    fit.alpha = torch.empty(N, dtype=F64, device=dev)
-    fit.arrow = torch.empty(M, dtype=F64, device=dev)
+    flags = (_lib.FIT_G_READY if g_ready else 0) | (_lib.FIT_FACTOR_WARM if warm_factor else 0) | \
+            (_lib.FIT_FACTOR_AT_MODE if factor_at_mode else 0)
     wbytes = lib.ppbo_laplace_workspace_bytes(Q, m)
     ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev)
-    stats = (ctypes.c_double * 8)()
-    rc = check(lib.ppbo_laplace_fit(_p(Sigma), Sigma.stride(0), Q, m, float(sigma), _p(f_init), int(max_iter), float(tol),
-                                    _p(fit.G), _p(fit.Lfac), _p(fit.f_map), _p(fit.alpha), _p(fit.arrow), _p(ws), wbytes,
-                                    stats, _stream()), "ppbo_laplace_fit")
+    stats = (ctypes.c_double * 12)()
+    rc = check(lib.ppbo_laplace_fit(_p(Sigma), Sigma.stride(0), Q, m, float(sigma), _p(f_init), int(max_iter), float(tol), flags,
+                                    _p(fit.G), fit.ldg, _p(fit._Lfac), fit.cap, _p(fit.sa_fac), _p(fit.f_map), _p(fit.alpha),
+                                    _p(fit.arrow), _p(ws), wbytes, stats, _stream()), "ppbo_laplace_fit")
     fit.info = rc
-    fit.stats = dict(iterations=int(stats[0]), last_step=stats[1], last_rel_step=stats[2], T=stats[3],
-                     halvings=int(stats[4]), factorizations=int(stats[6]), chord_steps=int(stats[7]))
+    fit.stats = {k: stats[i] for i, k in enumerate(_STATS)}
+    for k in ("iterations", "halvings", "factorizations", "chord_steps", "converged"):
+        fit.stats[k] = int(fit.stats[k])
+    fit.factor_state = int(stats[8]) if rc == 0 else 0
     fit.n_neg, fit._neg_corr, fit._neg_idx = 0, None, None
-    if rc == 0:
-        idx = (ctypes.c_int * M)()
-        fit.n_neg = check(lib.ppbo_neg_count(_p(fit.arrow), M, idx, M, _stream()), "ppbo_neg_count")
-        fit._neg_idx = idx
     return fit
+
+
+def gram_append(kernel, X, n_old, lengthscales, sigma_f, shrinkage, Sigma_cap):
+    """rows / columns [n_old, n) of the regularised covariance of X [n x D] written into the capacity buffer Sigma_cap in place"""
+    n, D = X.shape
+    check(_lib.load().ppbo_gram_append(_kind(kernel), _p(X), int(n_old), n, D, _ls(lengthscales, D), float(sigma_f), float(shrinkage),
+                                       _p(Sigma_cap), Sigma_cap.stride(0), _stream()), "ppbo_gram_append")
+    return Sigma_cap
+
+
+def diffspace_gram_append(Sigma, Q_old, Q_new, m, G_cap):
+    check(_lib.load().ppbo_diffspace_gram_append(_p(Sigma), Sigma.stride(0), int(Q_old), int(Q_new), m, _p(G_cap), G_cap.stride(0),
+                                                 _stream()), "ppbo_diffspace_gram_append")
+    return G_cap
+
+
+def factor_extend(fit, M_old, M_new, f_new_sets=None, sigma=None):
+    """grow fit's factor object from M_old to M_new rows; the coefficients of the new rows come from the warm-start values
+    f_new_sets of the appended comparison sets (or are already in fit.sa_fac[M_old:M_new]); returns LAPACK-style info"""
+    return check(_lib.load().ppbo_factor_extend(_p(fit.G), fit.ldg, int(M_old), int(M_new), _p(fit.sa_fac), _p(f_new_sets), fit.m,
+                                                float(fit.sigma if sigma is None else sigma), _p(fit._Lfac), fit.cap, _stream()),
+                 "ppbo_factor_extend")
 
 
 # ------------------------------------------------------------------------------------------- dense linear algebra
@@ -226,6 +299,27 @@ def potri_lower(L, ws):
     return out
 
 
+def lu_logdet(A):
+    """LU with partial pivoting of the square device matrix A (overwritten): (sign det U, log|det A|, sign of the row permutation)"""
+    lib = _lib.load()
+    n = A.shape[0]
+    wbytes = lib.ppbo_lu_workspace_bytes(n)
+    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=A.device)
+    res = (ctypes.c_double * 3)()
+    rc = check(lib.ppbo_lu_logdet(_p(A), A.stride(0), n, _p(ws), wbytes, res, _stream()), "ppbo_lu_logdet")
+    return res[0], res[1], res[2], rc
+
+
+def evidence_logdet(Sigma, Q, m, arrow, reference=True):
+    """LU log-determinant of I + Sigma Lambda (reference=True: the matrix GPModel.evidence factors, src/gp_model.py:301-308)
+    or of I + Sigma W (the Laplace normaliser) for the signed coefficients `arrow`"""
+    N = Q * (m + 1)
+    A = torch.empty((N, N), dtype=F64, device=Sigma.device)
+    check(_lib.load().ppbo_evidence_matrix(_p(Sigma), Sigma.stride(0), Q, m, _p(arrow), 1 if reference else 0, _p(A), N, _stream()),
+          "ppbo_evidence_matrix")
+    return lu_logdet(A)
+
+
 def shrink_inplace(K, shrinkage):
     n = K.shape[0]
     scratch = torch.empty(1, dtype=F64, device=K.device)
@@ -234,8 +328,8 @@ def shrink_inplace(K, shrinkage):
     return K
 
 
-def gemv(A, x):
-    y = torch.empty(A.shape[0], dtype=F64, device=A.device)
+def gemv(A, x, out=None):
+    y = torch.empty(A.shape[0], dtype=F64, device=A.device) if out is None else out
     check(_lib.load().ppbo_gemv(_p(A), A.stride(0), A.shape[0], A.shape[1], _p(x), _p(y), _stream()), "ppbo_gemv")
     return y
 
@@ -249,11 +343,50 @@ def predict(kernel, X, lengthscales, sigma_f, shrinkage, fit, Xp, P, batch, want
     Sp = torch.empty((batch, P, P), dtype=F64, device=dev) if want_cov else None
     wbytes = lib.ppbo_predict_workspace_bytes(N, fit.Q, fit.m, P, batch)
     ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev)
-    neg_corr = fit.neg_corr if want_cov else None            # the mean needs alpha only
+    neg_corr = fit.neg_corr if want_cov else None            # the mean needs alpha only (no factor, no Woodbury term)
+    Lfac = fit.Lfac if want_cov else None
     check(lib.ppbo_predict(_kind(kernel), _p(X), N, D, _ls(lengthscales, D), float(sigma_f), float(shrinkage), fit.Q, fit.m,
-                           _p(fit.alpha), _p(fit.arrow), _p(fit.Lfac), _p(neg_corr), fit.n_neg if want_cov else 0, _p(Xp), P, batch,
-                           _p(mu), _p(Sp), _p(ws), wbytes, _stream()), "ppbo_predict")
+                           _p(fit.alpha), _p(fit.arrow), _p(Lfac), fit.cap, _p(neg_corr), fit.n_neg if want_cov else 0, _p(Xp), P,
+                           batch, _p(mu), _p(Sp), _p(ws), wbytes, _stream()), "ppbo_predict")
     return mu.view(batch, P), Sp
+
+
+def posterior_mean(kernel, X, lengthscales, sigma_f, alpha, Xp):
+    """mu(Xp) = k(Xp, X) alpha without a fit object (GPModel.mu_pred batched, src/gp_model.py:454-458)"""
+    lib = _lib.load()
+    N, D = X.shape
+    P = Xp.shape[0]
+    mu = torch.empty(P, dtype=F64, device=X.device)
+    wbytes = lib.ppbo_predict_workspace_bytes(N, N, 0, P, 1)
+    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=X.device)
+    check(lib.ppbo_predict(_kind(kernel), _p(X), N, D, _ls(lengthscales, D), float(sigma_f), 0.0, N, 0, _p(alpha), None, None, 0,
+                           None, 0, _p(Xp), P, 1, _p(mu), None, _p(ws), wbytes, _stream()), "ppbo_predict")
+    return mu
+
+
+class PointMean:
+    """mu(x) = k(x, X) alpha for one host point per call (ppbo_mu_pred_point): the objective of GPModel.mu_star's sequential
+    search.  Everything that does not change between calls is prepared once."""
+
+    def __init__(self, kernel, X, lengthscales, sigma_f, alpha):
+        self.lib = _lib.load()
+        self.kind, self.X, self.alpha = _kind(kernel), X, alpha
+        self.N, self.D = X.shape
+        self.ls, self.sigma_f = _ls(lengthscales, self.D), float(sigma_f)
+        self.out = ctypes.c_double(0.0)
+        self.out_ref = ctypes.byref(self.out)
+        self.buf = (ctypes.c_double * self.D)()
+        self.Xp, self.ap = _p(X), _p(alpha)
+        self.calls = 0
+
+    def __call__(self, x):
+        self.buf[:] = x
+        rc = self.lib.ppbo_mu_pred_point(self.kind, self.Xp, self.N, self.D, self.ls, self.sigma_f, self.ap, self.buf,
+                                         ctypes.cast(self.out_ref, ctypes.POINTER(ctypes.c_double)), _stream())
+        if rc:
+            check(rc, "ppbo_mu_pred_point")
+        self.calls += 1
+        return self.out.value
 
 
 def mvn_rowmax(Z, Fac, mu):
@@ -275,10 +408,11 @@ def acq_reduce(fmax, mustar):
 
 
 # ------------------------------------------------------------------------------------------- K3
-def rff_features(W, b, X, sigma_f, feature_major):
+def rff_features(W, b, X, sigma_f, feature_major, out=None):
     F, D = W.shape
     n = X.shape[0]
-    out = torch.empty((F, n) if feature_major else (n, F), dtype=F64, device=W.device)
+    if out is None:
+        out = torch.empty((F, n) if feature_major else (n, F), dtype=F64, device=W.device)
     check(_lib.load().ppbo_rff_features(_p(W), _p(b), F, D, _p(X), n, float(sigma_f), _p(out), out.stride(0),
                                         1 if feature_major else 0, _stream()), "ppbo_rff_features")
     return out

@@ -251,29 +251,43 @@ class GPModel:
         start = time.time()
         Q, N = self._Q(), int(self.N)
         best = None
-        for _ in range(fmap_finding_trials):
+        Lsig = None
+        for trial in range(fmap_finding_trials):
             prev = None if self.fMAP is None else np.asarray(self.fMAP, dtype=np.float64).ravel()
             draws_random = prev is None or random_initial_vector or len(prev) > N
+            z = None
             if draws_random:
-                np.random.standard_normal(N)        # the reference's N(0, Sigma) start consumes N normals here (:374,:381)
+                z = np.random.standard_normal(N)    # the reference's N(0, Sigma) start consumes N normals here (:374,:381)
             if prev is None or len(prev) > N:
                 f0 = None
             elif len(prev) < N:
                 f0 = np.concatenate([prev, np.full(N - len(prev), prev.mean())])        # :375-377
             else:
                 f0 = prev
+            f0_dev = None if f0 is None else ops.to_dev(f0)
+            if trial > 0 and z is not None:
+                # multi-start (the reference's last iteration runs 10 random starts on a non-concave T, :96-97): trials after the
+                # first start from the consumed draw, f0 = chol(Sigma) z ~ N(0, Sigma) (the reference uses an SVD factor)
+                if Lsig is None:
+                    Lsig = self._Sigma_dev.clone()
+                    info, _ws = ops.potrf_lower(Lsig)
+                    Lsig = Lsig.tril_() if info == 0 else False
+                if Lsig is not False:
+                    f0_dev = ops.gemv(Lsig, ops.to_dev(z))
             # approx_optimization (gtol=100 in the reference ~ a single Newton step, :365-366)
             iters = 2 if approx_optimization else self.newton_max_iter
-            fit = ops.laplace_fit(self._Sigma_dev, Q, self.m, self.theta[0], f_init=None if f0 is None else ops.to_dev(f0),
-                                  max_iter=iters, tol=self.newton_tol)
+            fit = ops.laplace_fit(self._Sigma_dev, Q, self.m, self.theta[0], f_init=f0_dev, max_iter=iters, tol=self.newton_tol)
             if fit.info != 0:
                 print('---!!!--- Newton system is not positive definite (info=%d) ---!!!---' % fit.info)
+            elif not approx_optimization and not fit.stats["converged"]:
+                print('---!!!--- MAP iteration stopped at max_iter with relative step %.2e ---!!!---' % fit.stats["last_rel_step"])
             if self.verbose:
                 print('... this took ' + str(time.time() - start) + ' seconds.')
             if best is None or fit.stats["T"] > best.stats["T"]:
                 best = fit
         self._fit = best
         self.fit_stats = best.stats
+        self._point_mean = None
         self.fMAP = best.f_map.cpu().numpy()
         self._invalidate("Lambda_MAP", "posterior_covariance", "posterior_covariance_inv")
 
@@ -338,38 +352,77 @@ class GPModel:
             print("... this took " + str(time.time() - start) + " seconds.")
 
     # ------------------------------------------------------------------ evidence (src/gp_model.py:278-413)
-    def evidence(self, theta, f_initial=None):
-        """Laplace log-evidence + log-prior of theta: T(fMAP) - 1/2 log det(I + Sigma W) with the log-determinant read off
-        the Cholesky factor of I + a^1/2 G a^1/2 (equal by Sylvester's identity; the reference uses an LU of I + Sigma Lambda)."""
-        import scipy.stats
-        np.random.standard_normal(int(self.N))                 # RNG alignment with the reference's random start (:294)
+    def _evidence_terms(self, theta, f=None):
+        """(T(f), sign of det U, log|det|, sign of the row permutation, info) at hyper-parameters theta; f: the mode to evaluate
+        at (None: found here by the device Newton iteration from f = 0).  `evidence_formula`:
+          'reference' (default): LU of I + Sigma Lambda_MAP exactly as the reference (src/gp_model.py:301-308) -- with
+                       Lambda = -W this is det(I - Sigma W), not the Laplace normaliser; reproduced for drop-in parity
+          'laplace'  : LU of I + Sigma W, the determinant the Laplace approximation of the evidence calls for."""
         Q = self._Q()
         Sigma_ = ops.gram_regularized(self._kernel_name(), self._Xd(), theta[1], theta[2], self.COVARIANCE_SHRINKAGE)
-        fit = ops.laplace_fit(Sigma_, Q, self.m, theta[0], max_iter=self.newton_max_iter, tol=self.newton_tol)
-        M = Q * self.m
-        L = fit.Lfac[:M * M].view(M, M)
-        logdet = 2.0 * float(L.diagonal().log().sum())
-        value = fit.stats["T"] - 0.5 * logdet
+        if f is None:
+            fit = ops.laplace_fit(Sigma_, Q, self.m, theta[0], max_iter=self.newton_max_iter, tol=self.newton_tol)
+            if fit.info != 0:
+                return np.nan, 1.0, np.nan, 1.0, fit.info
+            T_map, arrow = fit.stats["T"], fit.arrow
+        else:
+            fd = ops.to_dev(np.asarray(f, dtype=np.float64).ravel())
+            s, _, arrow = ops.lik_terms(fd, Q, self.m, theta[0], True, False, True)
+            A = Sigma_.clone()
+            info, ws = ops.potrf_lower(A)
+            if info:
+                return np.nan, 1.0, np.nan, 1.0, info
+            fh = np.asarray(f, dtype=np.float64).ravel()
+            T_map = float(-0.5 * fh @ ops.potrs_vec(A, ws, fd).cpu().numpy() - float(s) / self.m)
+        sign_u, logabs, sign_p, info = ops.evidence_logdet(Sigma_, Q, self.m, arrow,
+                                                            reference=getattr(self, "evidence_formula", "reference") == "reference")
+        return T_map, sign_u, logabs, sign_p, info
+
+    def evidence(self, theta, f_initial=None):
+        """log-evidence + log-prior of theta (src/gp_model.py:278-319): T(fMAP) - 1/2 (sign U) log|det(I + Sigma Lambda_MAP)| with
+        the determinant from an LU with partial pivoting on the device.  The reference's random start consumes N normals from the
+        global RNG (:294, `f_initial` is ignored there too); the mode itself is found deterministically from f = 0."""
+        import scipy.stats
+        np.random.standard_normal(int(self.N))                 # RNG alignment with the reference's random start (:294)
+        T_map, sign_u, logabs, _, info = self._evidence_terms(theta)
         lp = (np.log(scipy.stats.lognorm.pdf(theta[0], s=1, scale=np.exp(1))) +
               np.log(scipy.stats.lognorm.pdf(theta[1], s=0.5, scale=np.exp(-1.4))) +
               np.log(scipy.stats.lognorm.pdf(theta[2], s=0.5, scale=np.exp(1.7))))
-        value = value + lp
-        if fit.info != 0 or fit.n_neg > 0 or not np.isfinite(value):
+        value = T_map - 0.5 * sign_u * logabs + lp
+        if info != 0 or np.isnan(value) or not np.isfinite(value):
             if self.verbose:
                 print('Nan log-evidence!')
             return -500
+        if self.verbose:
+            print('(scaled) Log-evidence + Log-prior: ' + str(value))
         return float(value)
 
     def optimize_theta(self):
-        """Hyper-parameter search over (l, sigma_f) by maximising `evidence` (src/gp_model.py:391-413).  The reference drives
-        this with GPyOpt (not installable here); the same bounds are searched with scipy's differential evolution."""
+        """Hyper-parameter search by maximising `evidence` (src/gp_model.py:391-413): sigma pinned to 1, l in (0.01, 2),
+        sigma_f in (0.1, 15) as in the reference.  The reference drives this with GPyOpt (20 initial + 40 sequential evaluations);
+        GPyOpt is used when importable, otherwise the same bounds and a comparable evaluation budget go to scipy's differential
+        evolution."""
         if self.verbose:
             print("Hyperparameter optimization begins...")
-        sigma = self.theta[0]
-        res = scipy.optimize.differential_evolution(lambda t: -self.evidence([sigma, t[0], t[1]], None),
-                                                    [(0.01, 2), (0.1, 15)], maxiter=3, popsize=5, polish=False)
-        self.theta = [sigma, float(res.x[0]), float(res.x[1])]
+        start = time.time()
+        try:
+            from GPyOpt.methods import BayesianOptimization
+        except Exception:
+            BayesianOptimization = None
+        if BayesianOptimization is not None:
+            bounds = [{'name': 'sigma', 'type': 'continuous', 'domain': (1, 1)},
+                      {'name': 'leghtscale', 'type': 'continuous', 'domain': (0.01, 2)},
+                      {'name': 'sigma_f', 'type': 'continuous', 'domain': (0.1, 15)}]
+            BO = BayesianOptimization(lambda theta: -self.evidence(theta[0], self.fMAP), domain=bounds, optimize_restarts=3,
+                                      normalize_Y=True, initial_design_numdata=20)
+            BO.run_optimization(max_iter=40)
+            self.theta = BO.x_opt
+        else:
+            res = scipy.optimize.differential_evolution(lambda t: -self.evidence([1.0, t[0], t[1]], None),
+                                                        [(0.01, 2), (0.1, 15)], maxiter=5, popsize=5, polish=False)
+            self.theta = [1.0, float(res.x[0]), float(res.x[1])]
         if self.verbose:
+            print('Optimization of hyperparameters took ' + str(time.time() - start) + ' seconds.')
             print("The optimized theta is " + str(self.theta))
 
     # ------------------------------------------------------------------ maximiser of the posterior mean (src/gp_model.py:415-437)
@@ -407,9 +460,14 @@ class GPModel:
         return mu[0].cpu().numpy(), Sp[0].cpu().numpy()
 
     def mu_pred(self, X_pred):
-        x = np.asarray(X_pred, dtype=np.float64).reshape(1, self.D)
-        mu, _ = self._predict_dev(ops.to_dev(x), 1, 1, want_cov=False)
-        return float(mu.cpu().numpy().ravel()[0])
+        """posterior mean at one point: one launch with the point and the result in mapped host memory (ops.PointMean) -- the
+        objective of mu_star's sequential search, ~10^4 evaluations per model update"""
+        pm = self.__dict__.get("_point_mean")
+        if pm is None or pm.alpha is not self._fit.alpha:
+            theta = self.theta
+            pm = self._point_mean = ops.PointMean(self._kernel_name(), self._Xd(), theta[1], theta[2], self._fit.alpha)
+        self.mu_pred_calls = getattr(self, "mu_pred_calls", 0) + 1
+        return pm(np.asarray(X_pred, dtype=np.float64).reshape(self.D))
 
     def mu_pred_neq(self, X_pred):
         return -self.mu_pred(X_pred)

@@ -77,8 +77,7 @@ def test_kernel_matrix_tensor_pipe_vs_difference_form(ops, kernel):
         if kernel == "SE_kernel":
             assert relerr(res[0][1], O.se_kernel(_np(Y), _np(X), [0, ls, 0.7])) < 1e-12
             # mat-vec mode (mean-only prediction) against the materialised product
-            fit = type("F", (), dict(Q=n, m=0, alpha=alpha, arrow=None, Lfac=None, neg_corr=None, n_neg=0))()
-            mu, _ = ops.predict(kernel, X, ls, 0.7, 1e-6, fit, Y, n2, 1, want_cov=False)
+            mu = ops.posterior_mean(kernel, X, ls, 0.7, alpha, Y)
             ref = res[1][1] @ _np(alpha)
             assert np.abs(_np(mu).ravel() - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300) + 1e-13 * np.abs(_np(alpha)).sum()
 
@@ -439,21 +438,25 @@ def test_gemm_configs_agree(ops):
         assert np.abs(_np(C) - ref).max() <= 1e-13 * 150 * np.abs(ref).max()
 
 
-def test_iteration_pipeline_matches_oracle(ops):
-    """the whole one-iteration pipeline (what bench.py times) on a small problem against the CPU oracle, and its sample
-    partition: 3 'ranks' evaluated one after the other give the single-rank sums"""
+@pytest.mark.parametrize("sizes,engine", [(dict(Q=12, S=300, P=50, F=64), "f64"), (dict(Q=12, S=1024, P=128, F=256), "i8")])
+def test_iteration_pipeline_matches_oracle(ops, sizes, engine):
+    """the whole one-iteration pipeline (what bench.py times) on a small problem against the CPU oracle -- with the FP64 and with
+    the tcgen05 INT8 sampling engine -- and its sample partition: 3 'ranks' evaluated one after the other give the single-rank
+    sums.  The mode yard-stick is found by the oracle alone: scipy trust-exact from f = 0, tightened by the oracle's Newton."""
     import torch
     from oracle import ppbo_oracle as O
     from ppbo_b200 import iteration, synthetic
-    prob = synthetic.make_problem("levy10d", Q=12, S=300, P=50, F=64)
+    prob = synthetic.make_problem("levy10d", **sizes)
     theta, Q, m, S = prob["theta"], prob["Q"], prob["m"], prob["S"]
+    assert iteration.sampling_engine(S, prob["P"], prob["F"]) == engine
     dev = torch.device("cuda", 0)
     d = iteration.IterationInputs(prob["X"], None, prob["W"], prob["b"], None, prob["grids"]).to_device(dev)
     sums, gp, rff = iteration.run_iteration(d, prob["kernel"], theta, Q, m, S, seed=5)
     X = prob["X"]
     Sigma = O.regularize_covariance(O.se_kernel(X, X, theta), svd_roundtrip=False)
     f = _np(gp.f_map)
-    f_tight = O.fmap_tight(Sigma, Q, m, theta[0], f)
+    f_te, _ = O.fmap_trust_exact(O.pd_inverse(Sigma), Q, m, theta[0], np.zeros(X.shape[0]))
+    f_tight = O.fmap_tight(Sigma, Q, m, theta[0], f_te)                 # independent of the CUDA result
     assert np.abs(f - f_tight).max() <= 1e-6 * np.abs(f_tight).max()
     PhiX = O.rff_features(prob["W"], prob["b"], X, theta[2])
     w = _np(rff.omega_map)

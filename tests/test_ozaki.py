@@ -106,17 +106,32 @@ def test_rowmax_i8_bit_exact_vs_oracle(ops, slices, S, F, P, B):
 
 
 @pytest.mark.gpu
-def test_rowmax_i8_matches_fp64_kernel(ops):
+def test_rowmax_i8_bench_shape_vs_fp64_oracle(ops):
+    """the bench's contraction shape (F = 1000, P = 1024) against the ORACLE's FP64 product (numpy, host): values to the error bound
+    of the digit count, arg-max identical wherever the oracle's gap to the runner-up exceeds that bound (tie rule), and the FP64
+    DMMA kernel held to the same standard"""
     S, F, P, B = 4096, 1000, 1024, 3
     Omega, _ = _operands(S, F, 8, seed=5)
     grids = np.stack([_operands(8, F, P, seed=50 + b)[1] for b in range(B)])
     Od, Gd = ops.to_dev(Omega), ops.to_dev(grids)
+    ref_max, ref_arg, ref_gap = [], [], []
+    for b in range(B):
+        Fs = Omega @ grids[b].T
+        idx = Fs.argmax(axis=1)
+        top = Fs[np.arange(S), idx]
+        Fs[np.arange(S), idx] = -np.inf
+        ref_max.append(top), ref_arg.append(idx), ref_gap.append(top - Fs.max(axis=1))
+    ref_max, ref_arg, ref_gap = np.array(ref_max), np.array(ref_arg), np.array(ref_gap)
+    scale = float(np.abs(ref_max).max())
     f64max, f64arg, _ = ops.rff_eval_argmax(Od, Gd)
-    for slices, tol in ((5, 1e-9), (6, 1e-11), (7, 1e-13)):
-        fmax, arg, _ = ops.rff_eval_argmax_i8(Od, Gd, slices=slices)
-        scale = float(np.abs(_np(f64max)).max())
-        assert np.abs(_np(fmax) - _np(f64max)).max() <= tol * scale
-        assert np.mean(_np(arg) == _np(f64arg)) > 0.9999            # arg-max flips only on ties at the rounding level
+    for name, fmax, arg, tol in [("f64", f64max, f64arg, 1e-12)] + [
+            ("i8-%d" % k, *ops.rff_eval_argmax_i8(Od, Gd, slices=k)[:2], t) for k, t in ((5, 1e-9), (6, 1e-11), (7, 1e-12))]:
+        fmax, arg = _np(fmax), _np(arg)
+        assert np.abs(fmax - ref_max).max() <= tol * scale, name
+        decided = ref_gap > 4 * tol * scale
+        assert decided.mean() > 0.999, name
+        assert np.array_equal(arg[decided], ref_arg[decided]), name     # identical arg-max; below the bound either index is one
+        assert np.all(fmax[~decided] >= ref_max[~decided] - tol * scale), name
     # repeatability: bit-identical across launches
     a1 = ops.rff_eval_argmax_i8(Od, Gd, slices=6)[0]
     a2 = ops.rff_eval_argmax_i8(Od, Gd, slices=6)[0]
