@@ -6,11 +6,17 @@
 
 A "step" is one full iteration on synthetic inputs of the named BASELINE.json shape (default: Ackley-20D, 200 queries x
 m = 25 -> N = 5200 rows / 5000 pseudo-observations, F = 1000 features, 20 directions x 1024 grid points, 32768 samples):
-  value : ms per iteration, inputs already resident in HBM (max over ranks, CUDA events)
+  value : ms per iteration from a COLD start (f = 0, omega = 0 -- what the reference's default random start corresponds to),
+          inputs already resident in HBM (max over ranks, CUDA events)
   e2e   : the same iteration through the public host API with pinned HOST buffers: H2D of the inputs and D2H of the
           per-direction sums inside the timed region, followed by the host arg-max over directions
-Only the Monte-Carlo samples are partitioned over the ranks (fixed total work -> "scaling": "strong").
-Prints ONE JSON line on rank 0.
+  steady_state : what every iteration after the first costs: one comparison set is APPENDED to the fitted 200-query model
+          (rows of Sigma and G, factor grown by 25 rows, chord iteration from the previous mode, warm weight-space fit), end to
+          end with host buffers; K consecutive appends (queries 201 ... 200 + K)
+  parity_gate : after the timed regions, the cold step's results against the committed oracle fixture
+          (tests/golden/full_<config>.npz, made by oracle/make_full_fixtures.py on the host) and the host gradient formula
+Only the Monte-Carlo samples (and, from 3 ranks on, the mu* candidates) are partitioned over the ranks (fixed total work ->
+"scaling": "strong").  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -28,8 +34,10 @@ sys.path.insert(0, ROOT)
 METRIC = "ppbo_iteration_ms"
 UNIT = "ms"
 # FP64 tensor (DMMA) pipe peak measured on this pool's B200 by scratch/ubench.cu (profiles/r01_fp64_peaks_ubench.txt):
-# register-resident mma.sync.m8n8k4.f64 loop, 37.1 TFLOP/s; MEASURED_PEAKS.json carries no FP64 figure.
+# register-resident mma.sync.m8n8k4.f64 loop, 37.1 TFLOP/s; MEASURED_PEAKS.json carries no FP64 figure.  The bench also measures
+# its own FP64 GEMM rate (roofline.fp64_gemm_measured_tflops).
 FP64_TENSOR_PEAK_TFLOPS = 37.1
+SEED = 1234
 
 
 def parse_args():
@@ -40,8 +48,10 @@ def parse_args():
     ap.add_argument("--config", default="ackley20d")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api-leg", action="store_true", help="skip the src/ API timing at configs 1-3")
     ap.add_argument("--samples", type=int, default=None, help="override S (debug)")
-    ap.add_argument("--profile", action="store_true", help="1 warm-up + --steps resident steps, no JSON (for ncu)")
+    ap.add_argument("--profile", default=None, choices=[None, "cold", "steady"],
+                    help="1 warm-up + --steps resident steps of the named kind, no JSON (for ncu)")
     return ap.parse_args()
 
 
@@ -90,88 +100,134 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_sample(prob, fit_iters_full=None, q_sample=60, s_sample=512, threads=None):
-    """The reference algorithm (oracle port, numpy/scipy + multi-threaded BLAS) on a BOUNDED sample of the workload,
-    extrapolated to one full iteration in ms.  What is timed and how it is scaled is returned in `sample`.
-
-    Reference recipe per iteration: Sigma = reg(K) ; Sigma^-1 (dposv) ; trust-exact on the dense N x N
-    Hessian (one T_hessian + >= 1 dpotrf per outer iteration, ~100-150 outer iterations from the reference's random
-    start, probe in SURVEY.md 3.2) ; posterior covariance (dposv) ; RFF: Phi_X, weight-space trust-exact, Omega,
-    Phi_grid, Fs = Omega Phi_grid, per-sample max.  N^3 pieces are timed at N_s = q_sample (m+1) rows and scaled by
-    (N/N_s)^3, N^2 pieces by (N/N_s)^2, the sampling GEMM at s_sample samples and scaled by S/s_sample."""
-    from oracle import ppbo_oracle as O
-    import scipy.linalg
-    D, Q, m, S, P, F = prob["D"], prob["Q"], prob["m"], prob["S"], prob["P"], prob["F"]
-    theta = prob["theta"]
-    qs = min(Q, q_sample)
-    Ns, N = qs * (m + 1), Q * (m + 1)
-    Xs = prob["X"][:Ns]
-    c3, c2 = (N / Ns) ** 3, (N / Ns) ** 2
-    parts = {}
-
-    def timed(name, scale, fn):
-        t0 = time.perf_counter()
-        out = fn()
-        parts[name] = (time.perf_counter() - t0) * scale
-        return out
-    Sigma = timed("gram_regularize_closed_form", c2, lambda: O.regularize_covariance(O.se_kernel(Xs, Xs, theta), svd_roundtrip=False))
-    Sinv = timed("Sigma_inverse_dposv", c3, lambda: O.pd_inverse(Sigma))
-    f = np.zeros(Ns)
-    outer = 120 if fit_iters_full is None else fit_iters_full      # reference outer iterations (SURVEY.md 3.2: 95-156)
-
-    def one_outer():
-        H = -O.T_hessian(f, Sinv, qs, m, theta[0])
-        g = -O.T_grad(f, Sinv, qs, m, theta[0])
-        c, low = scipy.linalg.cho_factor(H, lower=True)
-        return scipy.linalg.cho_solve((c, low), -g) + O.T_value(f, Sinv, qs, m, theta[0], quadrature=False)
-    timed("trust_exact_outer_iterations(x%d)" % outer, c3 * outer, one_outer)
-    timed("posterior_covariance_dposv", c3, lambda: O.pd_inverse(Sinv - O.create_Lambda(f, qs, m, theta[0])))
-    if F:
-        W, b = prob["W"], prob["b"]
-        PhiX = timed("rff_features_design", N / Ns, lambda: O.rff_features(W, b, Xs, theta[2]))
-        w = np.zeros(F)
-        timed("rff_trust_exact_outer_iterations(x30)", 30 * N / Ns, lambda: (O.rff_S_grad(w, PhiX, qs, m, theta[0]),
-                                                                          O.rff_S_hess_diag(w, PhiX, qs, m, theta[0]),
-                                                                          O.rff_S(w, PhiX, qs, m, theta[0], quadrature=False)))
-        ss = min(S, s_sample)
-        rng = np.random.RandomState(0)
-        Omega = rng.randn(ss, F)
-
-        def sampling():
-            out = 0.0
-            for d in range(prob["grids"].shape[0]):
-                Phi = O.rff_features(W, b, prob["grids"][d], theta[2])
-                mx, _ = O.rff_eval_argmax(Omega, Phi)
-                out += np.maximum(mx, 0).sum()
-            return out
-        timed("rff_sampling_gemm_rowmax", S / ss, sampling)
-    total_ms = 1e3 * sum(parts.values())
-    sample = ("oracle port (numpy/scipy, closed-form regularisation, GH quadrature replaced by ndtr) timed at N_s=%d rows "
-              "(N^3 parts x%.1f, N^2 parts x%.1f), 1 trust-exact outer iteration x%d, %d of %d samples on all %d grids; "
-              "extrapolated parts ms: %s" % (Ns, c3, c2, outer, min(S, s_sample), S, prob["grids"].shape[0],
-                                             {k: round(1e3 * v, 1) for k, v in parts.items()}))
-    return total_ms, sample
-
-
-def int8_peak_tops():
-    """INT8 dense tensor peak in TOP/s: 2 x MEASURED_PEAKS.json's cuBLAS bf16 burst figure (kernel timed alone), else 2 x the
-    profiling guide's fallback of 1590 TFLOP/s."""
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            mp = json.load(fh)
-        return 2.0 * float(mp["bf16_tflops"]), ("2 x MEASURED_PEAKS.json bf16_tflops (%.1f, burst; sustained %.1f): INT8 runs on the "
-                                                "same tensor pipe at twice the K per instruction" % (mp["bf16_tflops"],
-                                                                                                      mp.get("bf16_tflops_sustained", float("nan"))))
-    except Exception:
-        return 2.0 * 1590.0, "2 x 1590 TFLOP/s bf16 (B200_PROFILING.md fallback; MEASURED_PEAKS.json absent)"
-
-
+# ------------------------------------------------------------------------------------------------- CPU reference arm
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def blas_threads(n=None):
+    """pin (n given) and report the BLAS/OpenMP thread count of numpy/scipy"""
+    try:
+        import threadpoolctl
+        if n is not None:
+            threadpoolctl.threadpool_limits(limits=n)
+        info = threadpoolctl.threadpool_info()
+        return max([i.get("num_threads", 1) for i in info] or [1])
+    except Exception:
+        return None
+
+
+def recorded_outer_iterations(name):
+    """outer-iteration count of the oracle's trust-exact fit at FULL N from the reference's random start, measured once in the build
+    container by oracle/make_full_fixtures.py record (profiles/r02_reference_full_fit_<name>.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_reference_full_fit_%s.json" % name)) as fh:
+            rec = json.load(fh)
+        full = max(rec["runs"], key=lambda r: r["N"])
+        return int(full["trust_exact_nit"]), "profiles/r02_reference_full_fit_%s.json (N=%d: %d outer iterations, %.1f s each on %d threads there)" % (
+            name, full["N"], full["trust_exact_nit"], full["trust_exact_s_per_iteration"], rec.get("host_threads", 0))
+    except Exception:
+        return 12, "no record file: 12 outer iterations assumed (the count measured for ackley20d)"
+
+
+class ReferenceArm:
+    """The reference's algorithm (oracle port: numpy/scipy + multi-threaded BLAS) on the named workload at FULL size.
+
+    One timed step = ONE real outer iteration of scipy trust-exact on the dense N x N Hessian at full N from the reference's random
+    start (objective, gradient, Hessian assembly, More-Sorensen subproblem with its Cholesky factorisations) -- the unit the
+    reference's fit repeats.  The one-off N^3 pieces (Sigma^-1 by dposv, posterior covariance), the weight-space fit and a bounded
+    slice of the sampling contraction are timed once at start-up.  One full iteration = one-off pieces + per-iteration time x the
+    outer-iteration count RECORDED from a complete run of the same fit (recorded_outer_iterations); that product is an
+    extrapolation and is labelled as one."""
+
+    def __init__(self, prob, s_sample=256):
+        from oracle import ppbo_oracle as O
+        self.O, self.prob = O, prob
+        self.threads = blas_threads()
+        D, Q, m, S, F = prob["D"], prob["Q"], prob["m"], prob["S"], prob["F"]
+        theta, X = prob["theta"], prob["X"]
+        self.parts = {}
+
+        def timed(name, scale, fn):
+            t0 = time.perf_counter()
+            out = fn()
+            self.parts[name] = (time.perf_counter() - t0) * scale * 1e3
+            return out
+        Sigma = timed("gram_regularize_closed_form", 1.0, lambda: O.regularize_covariance(O.se_kernel(X, X, theta), svd_roundtrip=False))
+        self.Sinv = timed("Sigma_inverse_dposv", 1.0, lambda: O.pd_inverse(Sigma))
+        rng = np.random.RandomState(0)
+        self.f0 = np.linalg.cholesky(Sigma) @ rng.standard_normal(X.shape[0])          # f ~ N(0, Sigma), the reference's start (:374)
+        timed("posterior_covariance_dposv", 1.0, lambda: O.posterior_covariance(self.Sinv, self.f0 * 0.0, Q, m, theta[0]))
+        del Sigma
+        if F:
+            W, b = prob["W"], prob["b"]
+            PhiX = timed("rff_features_design", 1.0, lambda: O.rff_features(W, b, X, theta[2]))
+            t0 = time.perf_counter()
+            _, res = O.rff_omega_map(PhiX, Q, m, theta[0], np.zeros(F))
+            self.parts["rff_trust_exact_fit(%d outer iterations, measured in full)" % res.nit] = (time.perf_counter() - t0) * 1e3
+            ss = min(S, s_sample)
+            Omega = np.random.RandomState(1).randn(ss, F)
+
+            def sampling():
+                out = 0.0
+                for d in range(prob["grids"].shape[0]):
+                    mx, _ = O.rff_eval_argmax(Omega, O.rff_features(W, b, prob["grids"][d], theta[2]))
+                    out += np.maximum(mx, 0).sum()
+                return out
+            timed("rff_sampling_gemm_rowmax(%d of %d samples, scaled)" % (ss, S), S / ss, sampling)
+        self.nit, self.nit_source = recorded_outer_iterations(prob["name"])
+
+    def step(self):
+        """one real trust-exact outer iteration at full N; returns its wall time in ms"""
+        import scipy.optimize
+        O, p = self.O, self.prob
+        Q, m, sigma = p["Q"], p["m"], p["theta"][0]
+        t0 = time.perf_counter()
+        scipy.optimize.minimize(lambda f: -O.T_value(f, self.Sinv, Q, m, sigma, quadrature=False), self.f0, method="trust-exact",
+                                jac=lambda f: -O.T_grad(f, self.Sinv, Q, m, sigma), hess=lambda f: -O.T_hessian(f, self.Sinv, Q, m, sigma),
+                                options={"maxiter": 1})
+        return (time.perf_counter() - t0) * 1e3
+
+    def iteration_ms(self, per_iteration_ms):
+        return sum(self.parts.values()) + per_iteration_ms * self.nit
+
+    def sample_text(self, per_iteration_ms):
+        return ("oracle port (numpy/scipy, BLAS threads = %s of %d host threads) at FULL N = %d: one trust-exact outer iteration measured per "
+                "step = %.0f ms; iteration = one-off parts + that x %d outer iterations [%s] -- EXTRAPOLATED by the recorded count; one-off "
+                "parts ms: %s" % (self.threads, host_threads(), self.prob["N"], per_iteration_ms, self.nit, self.nit_source,
+                                  {k: round(v, 1) for k, v in self.parts.items()}))
+
+
+def single_thread_ratio(prob_name):
+    """the reference's own policy is BLAS threads = 1 (numerical_experiments/run.slrm:6-9): ratio of one trust-exact outer iteration
+    with 1 thread to all threads, measured at a quarter of the problem (N = 1300 for ackley20d)"""
+    try:
+        import threadpoolctl
+        from ppbo_b200 import synthetic
+        from oracle import ppbo_oracle as O
+        import scipy.optimize
+        cfg = synthetic.CONFIGS[prob_name]
+        p = synthetic.make_problem(prob_name, Q=max(4, cfg["Q"] // 4), S=8, P=8)
+        Sigma = O.regularize_covariance(O.se_kernel(p["X"], p["X"], p["theta"]), svd_roundtrip=False)
+        Sinv = O.pd_inverse(Sigma)
+        f0 = np.linalg.cholesky(Sigma) @ np.random.RandomState(0).standard_normal(p["N"])
+
+        def one():
+            t0 = time.perf_counter()
+            scipy.optimize.minimize(lambda f: -O.T_value(f, Sinv, p["Q"], p["m"], p["theta"][0], quadrature=False), f0, method="trust-exact",
+                                    jac=lambda f: -O.T_grad(f, Sinv, p["Q"], p["m"], p["theta"][0]),
+                                    hess=lambda f: -O.T_hessian(f, Sinv, p["Q"], p["m"], p["theta"][0]), options={"maxiter": 1})
+            return (time.perf_counter() - t0) * 1e3
+        one()
+        t_all = one()
+        with threadpoolctl.threadpool_limits(limits=1):
+            t_one = one()
+        return {"N": p["N"], "outer_iteration_ms_all_threads": t_all, "outer_iteration_ms_1_thread": t_one, "ratio": t_one / t_all}
+    except Exception as e:       # pragma: no cover
+        return {"error": str(e)}
 
 
 def run_reference(args):
@@ -181,18 +237,22 @@ def run_reference(args):
         return
     from ppbo_b200 import synthetic
     prob = synthetic.make_problem(args.config, S=args.samples)
-    vals = []
-    sample = ""
+    arm = ReferenceArm(prob)
+    per = []
     for i in range(args.warmup + args.steps):
-        v, sample = cpu_reference_sample(prob)
+        t = arm.step()
         if i >= args.warmup:
-            vals.append(v)
-    v = float(np.mean(vals))
+            per.append(t)
+    per_it = float(np.mean(per))
+    v = arm.iteration_ms(per_it)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(prob, args.gpus),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.threads or host_threads(), "kind": "port", "sample": arm.sample_text(per_it)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extrapolated": True, "measured_step_ms": per_it, "measured_step": "one trust-exact outer iteration at full N",
+            "outer_iterations_recorded": arm.nit, "one_off_parts_ms": {k: round(v_, 1) for k, v_ in arm.parts.items()},
+            "blas_threads": arm.threads, "single_thread": single_thread_ratio(args.config)}
     print(json.dumps(line))
 
 
@@ -207,12 +267,162 @@ def workload_config(prob, n_gpus):
                             prob["name"], prob["D"], prob["Q"], prob["m"], prob["N"], prob["Q"] * prob["m"], prob["kernel"],
                             prob["theta"], prob["F"], prob["grids"].shape[0], prob["P"], prob["S"]),
             "parallelism": ("GP fit + weight-space fit (background thread) + all S samples on one GPU" if n_gpus == 1 else
-                            "GP fit on rank 0 (no samples: it is the critical path), weight-space fit on rank 1, broadcast of (omega_MAP, "
-                            "diag Hessian); S sharded over ranks 1..%d, which sample while rank 0 fits; broadcast of mu*; one "
-                            "all-reduce of 3 x directions doubles" % (n_gpus - 1)),
+                            "GP fit on rank 0, weight-space fit on rank 1, broadcast of (omega_MAP, diag Hessian); S sharded over the "
+                            "ranks by measured stage times (rank 0 samples only if its fit ends before the others would); mu* candidates "
+                            "sharded from 3 ranks on (all-reduce max); one all-reduce of 3 x directions doubles"),
             "l2_policy": "working set per step (Sigma, G, factor, Omega, PhiT: > 1 GB) exceeds the 126 MB L2; no explicit flush",
-            "fit_start": "cold: GP Newton from f = 0; weight-space Newton from omega = 0, concurrently with the GP fit",
+            "fit_start": "value / e2e: cold (GP Newton from f = 0; weight-space Newton from omega = 0); steady_state: warm (appended model)",
             "sampling_engine": "tcgen05 INT8, %d digit planes per operand (error-free splitting; FP64-GEMM accuracy)" % iteration_slices()}
+
+
+# ------------------------------------------------------------------------------------------------- measured peaks
+def measure_int8_peak(lib, torch, dev, sms):
+    """INT8 tensor-pipe rate of back-to-back tcgen05.mma.kind::i8 on resident shared-memory operands, one issuing thread per SM,
+    all SMs (ppbo_ozaki_mma_rate), timed with CUDA events: the pipe's own ceiling for the sampling kernel's instruction shape"""
+    import ctypes
+    best, best_cfg = 0.0, None
+    out = torch.zeros(sms, dtype=torch.int64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for N, nacc in ((256, 1), (128, 3), (192 if False else 64, 6)):
+        iters = 1 << 16
+        for rep in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = lib.ppbo_ozaki_mma_rate(N, 0, nacc, iters, sms, ctypes.c_void_p(out.data_ptr()), st)
+            b.record()
+            torch.cuda.synchronize()
+            if rc != 0:
+                break
+            tops = sms * iters * 2.0 * 128 * N * 32 / (a.elapsed_time(b) * 1e-3) / 1e12
+            if rep > 0 and tops > best:
+                best, best_cfg = tops, "M=128 N=%d K=32, %d accumulators" % (N, nacc)
+    return best, best_cfg
+
+
+def measure_fp64_gemm(ops, torch, dev, n=4096):
+    A = torch.randn((n, n), dtype=torch.float64, device=dev)
+    B = torch.randn((n, n), dtype=torch.float64, device=dev)
+    C = torch.empty((n, n), dtype=torch.float64, device=dev)
+    best = 0.0
+    for rep in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.gemm_nt(A, B, C)
+        b.record()
+        torch.cuda.synchronize()
+        if rep:
+            best = max(best, 2.0 * n ** 3 / (a.elapsed_time(b) * 1e-3) / 1e12)
+    return best
+
+
+def recorded_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/traffic.json, written by
+    scripts/ncu_summary.py from the .ncu-rep of the same launch); None when no capture is recorded for this shape"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            rec = json.load(fh)
+        e = rec.get(kernel_key)
+        return (e["dram_bytes"], e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+# ------------------------------------------------------------------------------------------------- parity gate
+def parity_gate(prob, gp, rff, sums_full, S, iteration, ops, torch):
+    """The timed cold iteration's results against the committed oracle fixture and the reference's gradient formula, on the host."""
+    import scipy.linalg
+    from oracle import ppbo_oracle as O
+    path = os.path.join(ROOT, "tests", "golden", "full_%s.npz" % prob["name"])
+    gate = {"fixture": os.path.relpath(path, ROOT) if os.path.exists(path) else None}
+    X, theta, Q, m = prob["X"], prob["theta"], prob["Q"], prob["m"]
+    f = gp.f_map.cpu().numpy()
+    Sigma = O.regularize_covariance(O.se_kernel(X, X, theta), svd_roundtrip=False)
+    a = scipy.linalg.cho_solve(scipy.linalg.cho_factor(Sigma, lower=True), f)
+    gate["grad_norm_ref_formula"] = float(np.linalg.norm(-a + O.lik_beta(f, Q, m, theta[0])))      # src/gp_model.py:228-240
+    ei_full, _ = iteration.acquisition_values(sums_full.cpu().numpy(), S)
+    gate["direction_full_S"] = int(np.argmax(ei_full))
+    if gate["fixture"] is None:
+        return gate
+    z = np.load(path)
+    gate["mode_rel"] = float(np.abs(f - z["f_tight"]).max() / np.abs(z["f_tight"]).max())
+    gate["grad_norm_oracle_mode"] = float(z["grad_norm_tight"])
+    w = rff.omega_map.cpu().numpy()
+    gate["omega_rel"] = float(np.abs(w - z["omega_tight"]).max() / np.abs(z["omega_tight"]).max())
+    # sampled acquisition on the fixture's slice of the Philox stream, with the pipeline's own fits
+    Ss = int(z["slice_samples"])
+    dev = gp.f_map.device
+    grids = ops.to_dev(prob["grids"])
+    B, P, D = prob["grids"].shape
+    PhiT = iteration.SlicedGrids(iteration.rff_grid_features(rff.W, rff.b, theta[2], grids))
+    mustar = iteration.mustar_over_candidates(gp, grids.reshape(B * P, D))
+    gate["mustar_rel"] = float(abs(float(mustar.cpu()[0]) - float(z["mustar"])) / abs(float(z["mustar"])))
+    sums, fmax, arg = iteration.rff_acquisition(rff, PhiT, Ss, mustar, seed=int(z["seed"]), bounds=(0, Ss))
+    sums = sums.cpu().numpy()
+    ref = z["slice_sums"]
+    gate["slice_samples"] = Ss
+    gate["slice_sums_rel"] = float(np.abs(sums - ref).max() / np.abs(ref).max())
+    gate["direction_slice"] = int(np.argmax(sums[:, 0]))
+    gate["direction_oracle"] = int(z["slice_direction"])
+    gate["direction_matches_oracle"] = bool(gate["direction_slice"] == gate["direction_oracle"])
+    decided = z["slice_gap"] > 1e-9 * np.abs(z["slice_fmax"]).max()
+    gate["argmax_identical_frac"] = float(np.mean(arg.cpu().numpy()[decided] == z["slice_arg"].astype(np.int32)[decided]))
+    gate["pass"] = bool(gate["mode_rel"] <= 1e-6 and gate["omega_rel"] <= 1e-6 and gate["slice_sums_rel"] <= 1e-6 and
+                        gate["direction_matches_oracle"] and gate["argmax_identical_frac"] == 1.0)
+    return gate
+
+
+# ------------------------------------------------------------------------------------------------- src/ API leg (configs 1-3)
+def api_leg(torch):
+    """BASELINE configs 1-3 through the reference's own API (ppbo_numerical_main.py:102-124): update_feedback_processing_object ->
+    update_data -> update_model -> next_query('EI-EXT-FAST'), host numpy arrays in and out, host wall clock.  The model is fitted
+    on Q - 1 queries first, the timed iteration appends the last one (the warm start pads the previous mode, src/gp_model.py:375-377);
+    a cold update_model at the full size is timed beside it."""
+    src = os.path.join(ROOT, "src")
+    if src not in sys.path:
+        sys.path.insert(1, src)
+    import acquisition
+    from gp_model import GPModel
+    from ppbo_settings import PPBO_settings
+    from ppbo_b200 import synthetic
+    out = {}
+    for name in ("camel2d", "hartmann6d", "camphor6d"):
+        cfg = synthetic.CONFIGS[name]
+        D, Q, m = cfg["D"], cfg["Q"], cfg["m"]
+        _, log, _ = synthetic.make_design(D, Q, m, seed=0)
+        rows = np.array([np.concatenate([a * xi + x, xi, [a]]) for xi, x, a in log])           # bounds (0,1)^D: scaled == original units
+        res = {"N": Q * (m + 1)}
+        try:
+            for mode in ("cold", "append"):
+                np.random.seed(0)
+                st = PPBO_settings(D=D, bounds=((0, 1),) * D, xi_acquisition_function="EI-EXT-FAST", m=m, theta_initial=list(cfg["theta"]),
+                                   kernel=cfg["kernel"], verbose=False, alpha_grid_distribution="equispaced")
+                gp = GPModel(st)
+                if mode == "append":
+                    gp.update_feedback_processing_object(rows[:-1])
+                    gp.update_data()
+                    gp.turn_initialization_off()
+                    gp.update_model()
+                    gp.fMAP_random_initial_vector = False
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                gp.update_feedback_processing_object(rows)
+                gp.update_data()
+                if mode == "cold":
+                    gp.turn_initialization_off()
+                t1 = time.perf_counter()
+                calls0 = getattr(gp, "mu_pred_calls", 0)
+                gp.update_model()
+                t2 = time.perf_counter()
+                xi, x = acquisition.next_query(st, gp, unscale=True)
+                t3 = time.perf_counter()
+                res[mode] = {"total_ms": 1e3 * (t3 - t0), "feedback_ms": 1e3 * (t1 - t0), "update_model_ms": 1e3 * (t2 - t1),
+                             "fit_ms": 1e3 * gp.timing.get("fit", float("nan")), "mu_star_ms": 1e3 * gp.timing.get("mu_star", float("nan")),
+                             "mu_pred_evaluations": getattr(gp, "mu_pred_calls", 0) - calls0, "next_query_ms": 1e3 * (t3 - t2),
+                             "fit_iterations": gp.fit_stats["iterations"], "selected_direction": int(np.argmax(xi != 0))}
+        except Exception as e:       # the leg is a report, never a reason to lose the bench line
+            res["error"] = "%s: %s" % (type(e).__name__, e)
+        out[name] = res
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -235,25 +445,34 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     shard = iteration.Shard()
+    W_steps, K = max(args.warmup, 3), args.steps
 
+    cfg = synthetic.CONFIGS[args.config]
+    Q0 = cfg["Q"]
+    n_extra = W_steps + K
+    big = synthetic.make_problem(args.config, S=args.samples, Q=Q0 + n_extra)      # the first Q0 queries are the base problem
     prob = synthetic.make_problem(args.config, S=args.samples)
-    kernel, theta, Q, m, S = prob["kernel"], prob["theta"], prob["Q"], prob["m"], prob["S"]
+    kernel, theta, m, S = prob["kernel"], prob["theta"], prob["m"], prob["S"]
+    n0 = Q0 * (m + 1)
+    assert np.array_equal(big["X"][:n0], prob["X"])
     B, P, D = prob["grids"].shape
     Fdim = prob["F"]
-    # f_init = None: cold start of the GP Newton iteration at f = 0; omega0 = None: weight-space start projected from the GP mode
+    # f_init = None: cold start of the GP Newton iteration at f = 0; omega0 = None: weight-space Newton from omega = 0
     inputs = iteration.IterationInputs(prob["X"], None, prob["W"], prob["b"], None, prob["grids"])
     sums_host = torch.empty((B, 3), dtype=torch.float64).pin_memory()
+    blocks_host = [torch.from_numpy(np.ascontiguousarray(big["X"][(Q0 + i) * (m + 1):(Q0 + i + 1) * (m + 1)])).pin_memory()
+                   for i in range(n_extra)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    gemm_events = []
+    shares = [None]
 
     def step(resident=None, timers=None):
         d = resident if resident is not None else inputs.to_device(dev)
-        sums, gp, rff = iteration.run_iteration(d, kernel, theta, Q, m, S, shard=shard, seed=1234, timers=timers)
+        sums, gp, rff = iteration.run_iteration(d, kernel, theta, Q0, m, S, shard=shard, seed=SEED, timers=timers, shares=shares[0])
         if resident is None:
             sums_host.copy_(sums, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -274,7 +493,7 @@ def main():
         marks = [time.perf_counter()]
         e0.record()
         out, held[0] = held[0], None       # the previous step's products stay alive until the next step has replaced them,
-        for _ in range(args.steps):        # in the warm-up as in the timed steps: the allocator pool is in its steady state
+        for _ in range(K):                 # in the warm-up as in the timed steps: the allocator pool is in its steady state
             out = step(resident)
             marks.append(time.perf_counter())      # host time after the step was issued (e2e: after its result arrived)
         held[0] = out
@@ -288,56 +507,179 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / args.steps, launches, out
+        return float(t.item()) / K, launches, out
+
+    def stage_times(run, reps):
+        """mean ms between the stage marks of `reps` runs on this rank"""
+        acc = {}
+        for _ in range(reps):
+            timers = []
+            run(timers)
+            torch.cuda.synchronize()
+            for (n0_, a), (n1_, b_) in zip(timers[:-1], timers[1:]):
+                acc.setdefault(n1_, []).append(a.elapsed_time(b_))
+        return {k: float(np.mean(v)) for k, v in acc.items()}
+
+    def all_gather_stage(local_dict):
+        if world == 1:
+            return [local_dict]
+        out = [None] * world
+        dist.all_gather_object(out, local_dict)
+        return out
+
+    # ---- steady state: a persistent model that grows by one comparison set per iteration
+    state = [None]
+
+    def steady_reset():
+        state[0] = iteration.IterationState(kernel, theta, D, m, Q0 + n_extra, dev, resident["W"], resident["b"], shard=shard)
+        iteration.run_iteration(resident, kernel, theta, Q0, m, S, shard=shard, seed=SEED, state=state[0], shares=shares[0])
+        torch.cuda.synchronize()
+
+    def steady_step(i, timers=None, host=True):
+        """append query Q0 + i to the model and run the iteration; host=True: the block, the grids and the basis come from pinned
+        host memory and the result goes back to the host (the e2e definition)"""
+        if host:
+            d = {"block": blocks_host[i].to(dev, non_blocking=True), "W": inputs.host["W"].to(dev, non_blocking=True),
+                 "b": inputs.host["b"].to(dev, non_blocking=True), "grids": inputs.host["grids"].to(dev, non_blocking=True)}
+        else:
+            d = {"block": blocks_dev[i], "W": resident["W"], "b": resident["b"], "grids": resident["grids"]}
+        sums, gp, rff = iteration.run_iteration(d, kernel, theta, Q0 + i + 1, m, S, shard=shard, seed=SEED, timers=timers,
+                                                state=state[0], shares=steady_shares[0])
+        if host:
+            sums_host.copy_(sums, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            ei, var = iteration.acquisition_values(sums_host.numpy(), S)
+            return int(np.argmax(ei)), gp, rff
+        return sums, gp, rff
 
     resident = inputs.to_device(dev)
+    blocks_dev = [b_.to(dev) for b_ in blocks_host]
+    steady_shares = [None]
     if args.profile:
-        for _ in range(1 + args.steps):
-            step(resident)
+        if args.profile == "cold":
+            for _ in range(1 + K):
+                step(resident)
+        else:
+            steady_reset()
+            for i in range(min(n_extra, 1 + K)):
+                steady_step(i, host=False)
         torch.cuda.synchronize()
         return
-    for _ in range(max(args.warmup, 3)):
+
+    # ---- calibration of the sample shares (several ranks): measured stage times of one cold iteration with the default partition
+    for _ in range(2):
+        held[0] = step(resident)
+    if world > 1:
+        st_all = all_gather_stage(stage_times(lambda tm: step(resident, tm), 2))
+        t_gp = st_all[0].get("gp_fit", 0.0) + st_all[0].get("mustar", 0.0)
+        t_rff = st_all[1].get("rff_fit", 0.0)
+        samp = [s_.get("sampling", 0.0) for s_ in st_all[1:]]
+        t_sampling_all = float(np.sum(samp))                         # the default partition gives every rank >= 1 an equal share
+        shares[0] = iteration.plan_shares(world, t_gp, t_rff, t_sampling_all)
+    for _ in range(W_steps):
         held[0] = step(resident)           # (a warm-up that drops its products at once leaves the second timed step to
     clocks = ClockSampler(local)           # cudaMalloc a second set of 200 MB buffers: +1 ms on one GPU, up to +10 ms on two)
     if rank == 0:
         clocks.start()
     ms_dev, launches, out = timed_run(resident)
-    fit_iters = out[1].lap.stats["iterations"] if out[1] is not None else None
+    fit_stats = out[1].lap.stats if out[1] is not None else None
     rff_iters = out[2].stats["iterations"] if (out[2] is not None and out[2].stats) else None
     for _ in range(2):
         held[0] = step(None)
     ms_e2e, _, out2 = timed_run(None)
     clk = clocks.stop() if rank == 0 else None
 
-    # stage breakdown + the dominant kernel (sampling GEMM with fused row max) timed with CUDA events on its stream
+    # stage breakdown of the cold iteration (every rank; rank 0 reports its own and the sampling ranks' mean)
     barrier()
-    stage_ms, gemm_ms = {}, []
-    for _ in range(max(3, min(args.steps, 5))):
-        timers = []
-        step(resident, timers)
-        torch.cuda.synchronize()
-        for (n0, a), (n1, b_) in zip(timers[:-1], timers[1:]):
-            stage_ms.setdefault(n1, []).append(a.elapsed_time(b_))
-    lo, hi = shard.sample_bounds(S)
-    if hi == lo:                      # rank 0 of several takes no samples: time the launch a sampling rank performs
-        lo, hi = 0, S // max(1, world - 1)
+    cold_stages = all_gather_stage(stage_times(lambda tm: step(resident, tm), max(3, min(K, 5))))
+
+    # ---- steady state
+    held[0] = None
+    steady_reset()
+    if world > 1:
+        st_all = all_gather_stage(stage_times(lambda tm: steady_step(0, tm, host=False), 1))
+        steady_reset()
+        t_gp = st_all[0].get("gp_fit", 0.0) + st_all[0].get("mustar", 0.0)
+        t_rff = st_all[1].get("rff_fit", 0.0)
+        steady_shares[0] = iteration.plan_shares(world, t_gp, t_rff, t_sampling_all)
+        steady_reset()
+    sel = []
+    for i in range(W_steps):
+        steady_step(i)
+    import gc
+    gc.collect()
+    gc.disable()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.ppbo_launch_count()
+    e0.record()
+    steady_fits = []
+    for i in range(W_steps, W_steps + K):
+        o = steady_step(i)
+        sel.append(o[0])
+        if o[1] is not None:
+            steady_fits.append(dict(o[1].lap.stats))
+    e1.record()
+    torch.cuda.synchronize()
+    gc.enable()
+    steady_launches = lib.ppbo_launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_steady = float(t.item()) / K
+    # warm model against a cold fit at the final size (GPU against GPU: consistency of the incremental path, not an oracle check)
+    warm_vs_cold = None
+    if rank == 0:
+        Qf = Q0 + n_extra
+        gfin = iteration.gp_fit(ops.to_dev(big["X"]), kernel, theta, Qf, m, tol=1e-9)
+        fw, fc = state[0].gp.f_map.cpu().numpy(), gfin.f_map.cpu().numpy()
+        warm_vs_cold = float(np.abs(fw - fc).max() / np.abs(fc).max())
+        del gfin
+    # one more append on a fresh state for its stage breakdown
+    steady_reset()
+    steady_stages = all_gather_stage(stage_times(lambda tm: steady_step(0, tm, host=False), 1))
+    state[0] = None
+
+    # ---- acquisition stage alone: S samples x P points x B directions, even shares over ALL ranks (sample-points / s)
     rffs = out[2]
-    Omega = ops.rff_sample_omega(rffs.omega_map, rffs.hess_diag, hi - lo, seed=1234, sample0=lo)
+    if rffs is None or rffs.omega_map is None:
+        raise SystemExit("no weight-space fit on this rank")
+    lo, hi = shard.bounds(S)
     PhiT = iteration.rff_grid_features(resident["W"], resident["b"], theta[2], resident["grids"])
     engine = iteration.sampling_engine(hi - lo, P, Fdim)
+    PhiS = iteration.SlicedGrids(PhiT) if engine == "i8" else PhiT
+    mu_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    acq_ms = []
+    for i in range(3 + 5):
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        iteration.rff_acquisition(rffs, PhiS, S, mu_dev, shard=shard, seed=SEED, bounds=(lo, hi))
+        b_.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            acq_ms.append(a.elapsed_time(b_))
+    t = torch.tensor([float(np.mean(acq_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    acq_t = float(t.item())
+    sample_points_per_s = S * P * B / (acq_t * 1e-3)
+
+    # ---- the dominant kernel (sampling contraction with fused row max) timed with CUDA events on its stream
     ks = iteration.SAMPLING_SLICES
+    Omega = ops.rff_sample_omega(rffs.omega_map, rffs.hess_diag, hi - lo, seed=SEED, sample0=lo)
     flops = 2.0 * (hi - lo) * Fdim * P * B                       # SURVEY.md 8d K3: 2 S F P per direction
     if engine == "i8":
         ap, asc = ops.ozaki_slice(Omega, 0, ks)
-        bp, bsc = ops.ozaki_slice(PhiT, 1, ks)
         fm = torch.empty((B, hi - lo), dtype=torch.float64, device=dev)
         am = torch.empty((B, hi - lo), dtype=torch.int32, device=dev)
 
         def dominant():
-            ops.ozaki_rowmax(ap, asc, hi - lo, bp, bsc, P, B, Fdim, ks, fmax=fm, arg=am)
+            ops.ozaki_rowmax(ap, asc, hi - lo, PhiS.planes, PhiS.scale, P, B, Fdim, ks, fmax=fm, arg=am)
     else:
         def dominant():
             ops.rff_eval_argmax(Omega, PhiT)
+    gemm_ms = []
     for i in range(3 + 5):
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -348,36 +690,57 @@ def main():
             gemm_ms.append(a.elapsed_time(b_))
     gemm_t = float(np.mean(gemm_ms))
     fp64_equiv = flops / (gemm_t * 1e-3) / 1e12
-    if engine == "i8":
-        # KS (KS+1)/2 exact INT8 plane products per FP64 product; INT8 dense peak = 2 x the measured bf16 peak (same tensor
-        # pipe, twice the K per instruction: nominal 4.5 POP/s against 2.25 PFLOP/s)
-        ops_per_launch = flops * ks * (ks + 1) / 2
-        achieved = ops_per_launch / (gemm_t * 1e-3) / 1e12
-        peak, peak_src = int8_peak_tops()
-        roof = {"kernel": "ozaki_rowmax_kernel<%d,64> (RFF sampling contraction on tcgen05.mma.kind::i8, %d digit planes per operand, "
-                          "fused per-sample max/arg-max)" % (ks, ks),
-                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape (profiles/r01_ncu_ozaki_rowmax.txt);
-                # algorithmic HBM bytes: the A digit planes once per grid + the B planes = 20 x 201 MB + 126 MB = 4.15 GB
-                "traffic": (4.501766e9 + 2.0655e7) if (args.config == "ackley20d" and hi - lo == 32768 and ks == 6 and P == 1024) else None,
-                "traffic_unit": "bytes per launch (ncu)",
-                "kernel_ms": gemm_t, "ops_per_launch": ops_per_launch, "fp64_equivalent_tflops": fp64_equiv,
-                "fp64_dmma_peak_tflops": FP64_TENSOR_PEAK_TFLOPS, "peak_source": peak_src}
-    else:
-        achieved = fp64_equiv
-        roof = {"kernel": "gemm_nt_rowmax_kernel (RFF sampling GEMM, fused per-sample max/arg-max)", "bound": "tensor",
-                "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
-                "traffic": None, "kernel_ms": gemm_t, "flops_per_launch": flops,
-                "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_fp64_peaks_ubench.txt); "
-                               "MEASURED_PEAKS.json has no FP64 figure (cuBLAS DGEMM 8192^3 reaches 35.5)"}
-    sample_points_per_s = S * P * B / (float(np.mean(stage_ms["acquisition"])) * 1e-3) if shard.world == 1 else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    sms = lib.ppbo_device_sm_count(local)
+    fp64_gemm = measure_fp64_gemm(ops, torch, dev)
+    if engine == "i8":
+        # KS (KS+1)/2 exact INT8 plane products per FP64 product
+        ops_per_launch = flops * ks * (ks + 1) / 2
+        achieved = ops_per_launch / (gemm_t * 1e-3) / 1e12
+        peak, peak_cfg = measure_int8_peak(lib, torch, dev, sms)
+        bf16 = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                bf16 = float(json.load(fh)["bf16_tflops"])
+        except Exception:
+            pass
+        key = "ozaki_rowmax_kernel<%d,64>@%s/S=%d/P=%d/B=%d" % (ks, args.config, hi - lo, P, B)
+        traffic, traffic_src = recorded_traffic(key)
+        roof = {"kernel": "ozaki_rowmax_kernel<%d,64> (RFF sampling contraction on tcgen05.mma.kind::i8, %d digit planes per operand, "
+                          "fused per-sample max/arg-max)" % (ks, ks),
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None,
+                "peak_source": "measured in this run: back-to-back tcgen05.mma.kind::i8 on all %d SMs (ppbo_ozaki_mma_rate, %s)" % (sms, peak_cfg),
+                "frac_of_2x_bf16_measured": achieved / (2 * bf16) if bf16 else None,
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)",
+                "traffic_source": traffic_src,
+                "algorithmic_bytes": float(ap.numel() + PhiS.planes.numel()),      # every digit plane read once
+                "kernel_ms": gemm_t, "ops_per_launch": ops_per_launch, "fp64_equivalent_tflops": fp64_equiv,
+                "fp64_dmma_peak_tflops": FP64_TENSOR_PEAK_TFLOPS, "fp64_gemm_measured_tflops": fp64_gemm}
+    else:
+        achieved = fp64_equiv
+        roof = {"kernel": "gemm_nt_rowmax_kernel (RFF sampling GEMM, fused per-sample max/arg-max)", "bound": "tensor",
+                "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
+                "traffic": None, "kernel_ms": gemm_t, "flops_per_launch": flops, "fp64_gemm_measured_tflops": fp64_gemm,
+                "peak_source": "FP64 DMMA pipe measured on this pool (profiles/r01_fp64_peaks_ubench.txt); "
+                               "MEASURED_PEAKS.json has no FP64 figure"}
+
+    def merge(stages):
+        """rank 0's own stages plus the mean sampling time of the ranks that sample"""
+        o = dict(stages[0])
+        samp_ = [s_["sampling"] for s_ in stages[1:] if "sampling" in s_]
+        if samp_:
+            o["sampling_other_ranks_mean"] = float(np.mean(samp_))
+        if len(stages) > 1 and "rff_fit" in stages[1]:
+            o["rff_fit_rank1"] = stages[1]["rff_fit"]
+        return o
+
+    gate = parity_gate(prob, out[1], out[2], out[0], S, iteration, ops, torch) if out[1] is not None else None
     line = {
-        "metric": METRIC, "value": ms_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": ms_dev, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_steps,
         "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(prob, world),
         "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": inputs.nbytes(), "d2h_bytes_per_step": B * 3 * 8,
@@ -385,16 +748,34 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roof,
-        "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
+        "stages_ms": merge(cold_stages),
+        "steady_state": {"value": ms_steady, "unit": UNIT, "what": "e2e (pinned host buffers in, sums out) per appended query, queries %d..%d "
+                         "appended to the fitted %d-query model" % (Q0 + W_steps + 1, Q0 + W_steps + K, Q0),
+                         "h2d_bytes_per_step": int(blocks_host[0].numel() * 8 + sum(inputs.host[k].numel() * 8 for k in ("W", "b", "grids"))),
+                         "d2h_bytes_per_step": B * 3 * 8, "gpu_launches": int(steady_launches), "stages_ms": merge(steady_stages),
+                         "factorizations_per_step": [int(s_["factorizations"]) for s_ in steady_fits],
+                         "chord_steps_per_step": [int(s_["chord_steps"]) for s_ in steady_fits],
+                         "selected_directions": sel, "warm_vs_cold_mode_rel": warm_vs_cold,
+                         "sample_shares": steady_shares[0]},
+        "sample_shares": shares[0],
         # diagnostics: host time per issued step (resident steps are issued asynchronously, e2e steps end with the result on the host)
-        "resident_host_ms_per_step": [round(t, 2) for t in step_marks.get("resident", [])],
-        "e2e_host_ms_per_step": [round(t, 2) for t in step_marks.get("e2e", [])],
-        "fit_newton_iterations": fit_iters, "rff_newton_iterations": rff_iters,
-        "rff_sample_points_per_s": sample_points_per_s,
+        "resident_host_ms_per_step": [round(t_, 2) for t_ in step_marks.get("resident", [])],
+        "e2e_host_ms_per_step": [round(t_, 2) for t_ in step_marks.get("e2e", [])],
+        "fit_newton_iterations": fit_stats["iterations"] if fit_stats else None,
+        "fit_factorizations": fit_stats["factorizations"] if fit_stats else None,
+        "rff_newton_iterations": rff_iters,
+        "rff_sample_points_per_s": sample_points_per_s, "rff_sample_points_per_s_per_gpu": sample_points_per_s / world,
+        "acquisition_stage_ms_even_shares": acq_t,
+        "parity_gate": gate,
     }
+    if world == 1 and not args.no_api_leg:
+        line["e2e_api"] = api_leg(torch)
     if world == 1 and not args.no_cpu_baseline:
-        v, sample = cpu_reference_sample(prob)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample}
+        arm = ReferenceArm(prob)
+        per = [arm.step() for _ in range(2)]
+        v = arm.iteration_ms(float(np.mean(per)))
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": arm.threads or host_threads(), "kind": "port",
+                                "sample": arm.sample_text(float(np.mean(per))), "extrapolated": True}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -87,24 +87,29 @@ long long ppbo_laplace_workspace_bytes(int Q, int m);
  * G [>= Qm x Qm, leading dimension ldg] and Lfac (factor object of capacity cap >= Qm) may be larger than the problem so that a
  * model can grow in place.  flags:
  *   PPBO_FIT_G_READY        G already holds B' Sigma B (ppbo_diffspace_gram / _append); otherwise it is formed here
- *   PPBO_FIT_FACTOR_WARM    Lfac holds chol(I + s G s) for s = sa_fac (a previous fit's factor, grown by ppbo_factor_extend):
- *                           the fit starts with chord steps from f_init and factorises only if they contract too slowly
+ *   PPBO_FIT_FACTOR_WARM    Lfac holds chol(I + s G s) of the leading warm_rows x warm_rows system for s = sa_fac (the previous
+ *                           iteration's factor; warm_rows = Qm when nothing was appended).  The fit starts with chord steps
+ *                           from (f_init, alpha_init = Sigma^-1 f_init) and factorises only if they contract too slowly; up to
+ *                           64 appended rows are carried as a BORDER of the old factor (Schur complement of the new rows with
+ *                           their current coefficients in every step), so the steady-state iteration is O(M^2 m)
  *                           (the reference's warm start pads the previous fMAP, src/gp_model.py:375-377)
  *   PPBO_FIT_FACTOR_AT_MODE finish with the factor of I + a+^1/2 G a+^1/2 AT the mode (what ppbo_predict with covariance and
  *                           ppbo_neg_corr_build need); without it Lfac keeps the last factor used and ppbo_laplace_refactor
  *                           builds the mode factor on demand (the posterior mean needs alpha only)
+ * alpha_init (may be NULL): Sigma^-1 f_init when the caller knows it (a warm start from the previous (f, alpha) with zeros
+ *          appended to alpha and Sigma_new,old alpha_old appended to f is consistent by construction).
  * Outputs: f_map[N], alpha[N] = Sigma^-1 f_map, arrow[Qm] (signed coefficients at the mode), sa_fac[Qm] (may be NULL) = the
- *          clamped square roots the factor left in Lfac was built with,
+ *          clamped square roots the factor left in Lfac was built with (a bordered fit writes the grown factor back),
  *          stats_h[12] host doubles: iterations, last step inf-norm, last relative step, T(f_map), line-search halvings,
  *          info, Cholesky factorisations, chord steps, factor state (2 at the mode / 1 last Newton or warm factor / 0 none),
- *          converged (1/0), relative size of the first warm step */
+ *          converged (1/0), relative size of the first warm step, border rows */
 #define PPBO_FIT_G_READY 1
 #define PPBO_FIT_FACTOR_WARM 2
 #define PPBO_FIT_FACTOR_AT_MODE 4
 int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
-                     int max_iter, double tol, int flags, double* G, long long ldg, double* Lfac, int cap, double* sa_fac,
-                     double* f_map, double* alpha, double* arrow, void* workspace, long long workspace_bytes, double* stats_h,
-                     void* stream);
+                     const double* alpha_init, int max_iter, double tol, int flags, double* G, long long ldg, double* Lfac,
+                     int cap, double* sa_fac, int warm_rows, double* f_map, double* alpha, double* arrow, void* workspace,
+                     long long workspace_bytes, double* stats_h, void* stream);
 /* factor of I + a+^1/2 G a+^1/2 for the coefficients `arrow` (a fit that skipped PPBO_FIT_FACTOR_AT_MODE); sa_fac[M] receives
  * sqrt(max(arrow, 0)).  Returns 0 or the index of the first non-positive pivot. */
 int ppbo_laplace_refactor(const double* G, long long ldg, int M, const double* arrow, double* Lfac, int cap, double* sa_fac,

@@ -40,7 +40,7 @@ _SIGNATURES = {
     "ppbo_laplace_workspace_bytes": (_L, [_I, _I]),
     "ppbo_gram_append": (_I, [_I, _P, _I, _I, _I, _PD, _D, _D, _P, _L, _P]),
     "ppbo_diffspace_gram_append": (_I, [_P, _L, _I, _I, _I, _P, _L, _P]),
-    "ppbo_laplace_fit": (_I, [_P, _L, _I, _I, _D, _P, _I, _D, _I, _P, _L, _P, _I, _P, _P, _P, _P, _P, _L, _PD, _P]),
+    "ppbo_laplace_fit": (_I, [_P, _L, _I, _I, _D, _P, _P, _I, _D, _I, _P, _L, _P, _I, _P, _I, _P, _P, _P, _P, _L, _PD, _P]),
     "ppbo_laplace_refactor": (_I, [_P, _L, _I, _P, _P, _I, _P, _P]),
     "ppbo_factor_extend": (_I, [_P, _L, _I, _I, _P, _P, _I, _D, _P, _I, _P]),
     "ppbo_gemm_nt": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _D, _D, _P]),

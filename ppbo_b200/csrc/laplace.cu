@@ -339,6 +339,100 @@ __global__ void __launch_bounds__(256) evidence_matrix_kernel(const double* __re
     out[(long long)i * ldo + c] = ((i == c) ? 1.0 : 0.0) + sign * v;
 }
 
+// ---- bordered warm start ---------------------------------------------------------------------------------------------------
+// After comparison sets were appended the Newton matrix is  A = [[A11, A21'], [A21, A22]]  with A11 = I + s_o G_oo s_o the system
+// the previous iteration factored (L11), A21 = s_n G_no s_o and A22 = I + s_n G_nn s_n for the nb new rows.  With
+//     R = (G_no s_o) L11^-T   (nb x M_old, computed ONCE per append)      C = G_nn - R R'      (nb x nb)
+// the Schur complement of the new rows is  S = I + s_n C s_n  for ANY current coefficients s_n, so a solve A y = t is
+//     z = L11^-1 t_o ;   y_n = S^-1 (t_n - s_n R z) ;   y_o = L11^-T (z - R' (s_n y_n))
+// i.e. the old factor's two sweeps plus nb-sized work.  The new rows therefore always carry their CURRENT coefficients (a Newton
+// step for them -- they start at the prior mean, where a = 0, and move by O(sigma_f)) while the old rows keep the coefficients their
+// factor was built with (chord step).  This is the O(M^2 m) iteration of SURVEY.md 8f rank 2.
+constexpr int BORDER_MAX = 64;           // new rows handled as a border (2 comparison sets of m = 25; more -> plain refactorisation)
+
+// T[u][v] = G[M_old + u][v] sa[v]   (u < nb, v < M_old)
+__global__ void __launch_bounds__(256) border_rows_kernel(const double* __restrict__ G, long long ldg, const double* __restrict__ sa,
+                                                          int M_old, int nb, double* __restrict__ T, long long ldt) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x, u = blockIdx.y;
+    if (v < M_old) T[(long long)u * ldt + v] = G[(long long)(M_old + u) * ldg + v] * sa[v];
+}
+// Cb[u][w] = G[M_old + u][M_old + w]
+__global__ void border_corner_kernel(const double* __restrict__ G, long long ldg, int M_old, int nb, double* __restrict__ Cb) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nb * nb) Cb[e] = G[(long long)(M_old + e / nb) * ldg + M_old + e % nb];
+}
+// One CTA: r = t_n - s_n (R z);  S = I + s_n C s_n;  y_n = S^-1 r  (Cholesky in shared memory);  t_n <- y_n,  w <- s_n y_n
+__global__ void __launch_bounds__(1024) border_solve_kernel(const double* __restrict__ R, long long ldr, const double* __restrict__ Cb,
+                                                            const double* __restrict__ s_new, const double* __restrict__ z, int M_old,
+                                                            int nb, double* __restrict__ t_new, double* __restrict__ w,
+                                                            const double* __restrict__ skip) {
+    __shared__ double S[BORDER_MAX][BORDER_MAX + 1];
+    __shared__ double r[BORDER_MAX];
+    if (skip && *skip != 0.0) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int u = warp; u < nb; u += 32) {
+        const double* Ru = R + (long long)u * ldr;
+        double a = 0.0;
+        for (int v = lane; v < M_old; v += 32) a = fma(Ru[v], z[v], a);
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) r[u] = t_new[u] - s_new[u] * a;
+    }
+    for (int e = tid; e < nb * nb; e += 1024) {
+        const int u = e / nb, v = e % nb;
+        S[u][v] = ((u == v) ? 1.0 : 0.0) + s_new[u] * Cb[e] * s_new[v];
+    }
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {                         // right-looking Cholesky, lower triangle
+        if (tid == 0) S[k][k] = sqrt(S[k][k]);
+        __syncthreads();
+        const double d = S[k][k];
+        for (int i = k + 1 + tid; i < nb; i += 1024) S[i][k] /= d;
+        __syncthreads();
+        const int rem = nb - k - 1;
+        for (int e = tid; e < rem * rem; e += 1024) {
+            const int i = k + 1 + e / rem, j = k + 1 + e % rem;
+            if (j <= i) S[i][j] = fma(-S[i][k], S[j][k], S[i][j]);
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {                                       // two triangular solves by one warp
+        for (int i = 0; i < nb; ++i) {
+            double a = 0.0;
+            for (int k = lane; k < i; k += 32) a = fma(S[i][k], r[k], a);
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) r[i] = (r[i] - a) / S[i][i];
+            __syncwarp();
+        }
+        for (int i = nb - 1; i >= 0; --i) {
+            double a = 0.0;
+            for (int k = i + 1 + lane; k < nb; k += 32) a = fma(S[k][i], r[k], a);
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) r[i] = (r[i] - a) / S[i][i];
+            __syncwarp();
+        }
+        for (int u = lane; u < nb; u += 32) {
+            t_new[u] = r[u];
+            w[u] = s_new[u] * r[u];
+        }
+    }
+}
+// z[v] -= sum_u R[u][v] w[u]
+__global__ void __launch_bounds__(256) border_update_kernel(const double* __restrict__ R, long long ldr, const double* __restrict__ w,
+                                                            int M_old, int nb, double* __restrict__ z, const double* __restrict__ skip) {
+    if (skip && *skip != 0.0) return;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= M_old) return;
+    double a = 0.0;
+    for (int u = 0; u < nb; ++u) a = fma(R[(long long)u * ldr + v], w[u], a);
+    z[v] -= a;
+}
+// L[M_old + u][v] = s_new[u] R[u][v] for v < b0: the appended rows of the grown factor left of the last diagonal block
+__global__ void __launch_bounds__(256) border_write_rows_kernel(const double* __restrict__ R, long long ldr, const double* __restrict__ s_new,
+                                                                int M_old, int nb, int b0, double* __restrict__ L, long long ldl) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x, u = blockIdx.y;
+    if (v < b0) L[(long long)(M_old + u) * ldl + v] = s_new[u] * R[(long long)u * ldr + v];
+}
+
 int launch_lik_terms(const double* f, int Q, int m, double sigma, double* set_lik, double* beta, double* arrow, double* sa,
                      double* bvec, cudaStream_t st) {
     PPBO_CL lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, set_lik, beta, arrow, sa, bvec);
@@ -404,11 +498,12 @@ __global__ void __launch_bounds__(256) newton_rows_kernel(const double* __restri
 
 struct FitWorkspace {
     double *bvec, *sa, *ap, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp, *binv, *state, *hist;
+    double *bR, *bT, *bC, *bw;           // bordered warm start: R [BORDER_MAX x M], scratch T [BORDER_MAX x M], C [BORDER_MAX^2], w
     int* info;
     static long long doubles(int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
         return 4 * N + 3 * M + (M + CHOL_NB) + (long long)NSTEP * Q + 32 + 8 + 64 + CHORD_STATE + 2 * CHORD_BATCH_MAX +
-               blockinv_doubles((int)M);
+               blockinv_doubles((int)M) + 2LL * BORDER_MAX * (M + 2) + (long long)BORDER_MAX * BORDER_MAX + BORDER_MAX + 8;
     }
     void carve(double* base, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
@@ -426,7 +521,13 @@ struct FitWorkspace {
         info = reinterpret_cast<int*>(p); p += 8;
         state = p; p += CHORD_STATE;
         hist = p; p += 2 * CHORD_BATCH_MAX;
-        binv = p;
+        binv = p; p += blockinv_doubles((int)M);
+        if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) ++p;           // 16-byte alignment for the GEMM operands
+        const long long Mp = (M + 1) / 2 * 2;
+        bR = p; p += BORDER_MAX * Mp;
+        bT = p; p += BORDER_MAX * Mp;
+        bC = p; p += (long long)BORDER_MAX * BORDER_MAX;
+        bw = p;
     }
 };
 
@@ -545,9 +646,9 @@ extern "C" int ppbo_factor_extend(const double* G, long long ldg, int M_old, int
 }
 
 extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
-                                int max_iter, double tol, int flags, double* G, long long ldg, double* Lfac, int cap,
-                                double* sa_fac, double* f_map, double* alpha, double* arrow, void* workspace,
-                                long long workspace_bytes, double* stats_h, void* stream) {
+                                const double* alpha_init, int max_iter, double tol, int flags, double* G, long long ldg,
+                                double* Lfac, int cap, double* sa_fac, int warm_rows, double* f_map, double* alpha, double* arrow,
+                                void* workspace, long long workspace_bytes, double* stats_h, void* stream) {
     PPBO_REQUIRE(Q >= 1 && m >= 1 && sigma > 0, "shape / sigma");
     PPBO_REQUIRE(workspace_bytes >= ppbo_laplace_workspace_bytes(Q, m), "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -555,7 +656,10 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     PPBO_REQUIRE(cap >= M && ldg >= M, "capacity / leading dimension below Q m");
     const bool g_ready = (flags & PPBO_FIT_G_READY) != 0, warm_factor = (flags & PPBO_FIT_FACTOR_WARM) != 0;
     const bool factor_at_mode = (flags & PPBO_FIT_FACTOR_AT_MODE) != 0;
-    PPBO_REQUIRE(!warm_factor || (f_init != nullptr && sa_fac != nullptr), "a warm factor needs f_init and sa_fac");
+    PPBO_REQUIRE(!warm_factor || (f_init != nullptr && alpha_init != nullptr && sa_fac != nullptr),
+                 "a warm factor needs f_init, alpha_init = Sigma^-1 f_init and sa_fac");
+    PPBO_REQUIRE(!warm_factor || (warm_rows >= 1 && warm_rows <= M), "warm_rows: size of the system the warm factor belongs to");
+    PPBO_REQUIRE(alpha_init == nullptr || f_init != nullptr, "alpha_init without f_init");
     FitWorkspace ws;
     ws.carve((double*)workspace, Q, m);
     const long long ldl = cap;
@@ -566,13 +670,14 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     const bool have_start = f_init != nullptr;
     if (have_start) PPBO_CUDA_CHECK(cudaMemcpyAsync(f_map, f_init, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
     else PPBO_CUDA_CHECK(cudaMemsetAsync(f_map, 0, sizeof(double) * N, st));
-    PPBO_CUDA_CHECK(cudaMemsetAsync(alpha, 0, sizeof(double) * N, st));
+    if (alpha_init) PPBO_CUDA_CHECK(cudaMemcpyAsync(alpha, alpha_init, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+    else PPBO_CUDA_CHECK(cudaMemsetAsync(alpha, 0, sizeof(double) * N, st));
 
     const int set_blocks = ceil_div(Q, 8);
     double scal_h[32];
     int it = 0, info = 0, n_factor = 0, n_chord = 0;
     double last_step = 0.0, last_rel = INFINITY, T_cur = NAN, prev_rel_h = INFINITY;
-    bool alpha_known = !have_start;          // alpha = Sigma^-1 f is known (== 0) only for the zero start
+    bool alpha_known = !have_start || alpha_init != nullptr;   // alpha = Sigma^-1 f is known for the zero start or when handed in
     int n_halvings_total = 0;
     // Newton steps refactor I + a+^1/2 G a+^1/2 at the current iterate; once the relative step is below CHORD_REL the factor
     // is kept and only the right-hand side is refreshed (chord steps: same fixed point Sigma^-1 f = beta(f), linear
@@ -593,24 +698,28 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     double chord_omega = 1.0, chord_ratio = 0.0, chord_wait = 0.0;
     bool factor_current = false;         // Lfac is the factor for the coefficients in ws.sa / ws.ap
     double warm_first_rel = NAN;
-    if (warm_factor) {
-        // Warm start with a usable factor (previous iteration's factor, grown by ppbo_factor_extend): no factorisation at all.
-        // First step: alpha is unknown for an arbitrary start, so the full chord step is taken (it only depends on f):
-        //   b = B a0 B' f + beta(f),  alpha <- b - B s0 (I + s0 G s0)^-1 s0 B' Sigma b,  f <- Sigma alpha
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.sa, sa_fac, sizeof(double) * M, cudaMemcpyDeviceToDevice, st));
-        PPBO_CL square_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.sa, M, ws.ap);
-        PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr, nullptr);
-        if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
-        PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
-        if ((rc = blockinv_build(Lfac, ldl, M, Mdinv, ws.binv, st))) return rc;
+    // ---- warm start with the previous iteration's factor (bordered, see border_solve_kernel): chord steps from (f_init, alpha_init)
+    int M_old = M, nb = 0;               // bordered: the factor in Lfac covers the first M_old rows, the last nb are the border
+    bool bordered = false;
+    if (warm_factor && M - warm_rows <= BORDER_MAX && (M - warm_rows) % m == 0) {
+        M_old = warm_rows;
+        nb = M - M_old;
+        bordered = nb > 0;
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.sa, sa_fac, sizeof(double) * M_old, cudaMemcpyDeviceToDevice, st));
+        PPBO_CL square_kernel<<<ceil_div(M_old, 256), 256, 0, st>>>(ws.sa, M_old, ws.ap);
+        if ((rc = blockinv_build(Lfac, ldl, M_old, Mdinv, ws.binv, st))) return rc;
         binv_valid = true;
-        if ((rc = potrs_vec_blockinv(Lfac, ldl, M, ws.binv, ws.t, st))) return rc;
-        PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha);   // alpha == 0: dalpha = alpha_new
-        if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st))) return rc;
-        PPBO_CL warm_step_size_kernel<<<1, 1024, 0, st>>>(f_map, ws.df, N, ws.scal);
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(alpha, ws.dalpha, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(f_map, ws.df, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
-        // T at the new point (the chord acceptance test compares against it)
+        if (bordered) {
+            const long long Mp = (M + 1) / 2 * 2;
+            PPBO_CL border_rows_kernel<<<dim3(ceil_div(M_old, 256), nb), 256, 0, st>>>(G, ldg, ws.sa, M_old, nb, ws.bT, Mp);
+            PPBO_CL border_corner_kernel<<<ceil_div(nb * nb, 256), 256, 0, st>>>(G, ldg, M_old, nb, ws.bC);
+            PPBO_LAUNCH_CHECK();
+            if ((rc = trsm_right_blockinv(Lfac, ldl, M_old, ws.binv, ws.bT, Mp, ws.bR, Mp, nb, st))) return rc;
+            GemmOperands g{ws.bR, Mp, 0, ws.bR, Mp, 0, nb, nb, M_old};
+            StoreEpilogue ep{ws.bC, nb, 0, -1.0, 1.0, 0, 0, 0};
+            if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;                 // C = G_nn - R R'
+        }
+        // T at the start (the chord acceptance test compares against it): -1/2 alpha.f - lik(f)/m
         PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, nullptr, nullptr, nullptr);
         PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
         PPBO_CL dot_kernel<<<1, 1024, 0, st>>>(alpha, f_map, N, ws.scal);
@@ -618,16 +727,28 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         PPBO_CUDA_CHECK(cudaMemcpyAsync(scal_h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
         PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
         T_cur = -0.5 * scal_h[0] - scal_h[24] / m;
-        last_step = scal_h[4];
-        last_rel = warm_first_rel = scal_h[4] / std::fmax(scal_h[5], 1e-300);
-        alpha_known = true;
-        factor_current = true;
+        last_rel = INFINITY;                 // unknown yet: the first batch (3 steps) measures the contraction
+        factor_current = !bordered;          // a bordered factor is not a factor object of the whole system (finalised below)
         refactor = false;
-        ++it;
-        ++n_chord;
-        if (trace) fprintf(stderr, "[ppbo_laplace_fit] it 0 warm chord step rel %.3e T %.12g\n", last_rel, T_cur);
-        if (last_rel <= tol) converged = true;
+        if (trace) fprintf(stderr, "[ppbo_laplace_fit] warm start: factor of %d rows, border %d, T %.12g\n", M_old, nb, T_cur);
     }
+    // coefficients of the border rows at the current iterate (their own Newton step inside every chord step)
+    auto refresh_border = [&](const double* skip) {
+        const int Qn = nb / m, Qo = M_old / m;
+        PPBO_CL lik_terms_kernel<<<ceil_div(Qn, 8), 256, 0, st>>>(f_map + (long long)Qo * (m + 1), Qn, m, sigma, nullptr, nullptr, nullptr,
+                                                                    ws.sa + M_old, nullptr, nullptr, ws.ap + M_old, skip);
+    };
+    // (I + s G s) y = t in place with the factor in Lfac (+ border)
+    auto chord_solve = [&](const double* skip) -> int {
+        int r_;
+        if (!bordered) return potrs_vec_blockinv(Lfac, ldl, M, ws.binv, ws.t, st, skip);
+        const long long Mp = (M + 1) / 2 * 2;
+        double* z = blockinv_y(ws.binv, M_old);
+        if ((r_ = potrs_fwd_blockinv(Lfac, ldl, M_old, ws.binv, ws.t, st, skip))) return r_;
+        PPBO_CL border_solve_kernel<<<1, 1024, 0, st>>>(ws.bR, Mp, ws.bC, ws.sa + M_old, z, M_old, nb, ws.t + M_old, ws.bw, skip);
+        PPBO_CL border_update_kernel<<<ceil_div(M_old, 256), 256, 0, st>>>(ws.bR, Mp, ws.bw, M_old, nb, z, skip);
+        return potrs_bwd_blockinv(Lfac, ldl, M_old, ws.binv, ws.t, st, skip);
+    };
     while (it < max_iter && !converged) {
         if (!refactor) {
             // ---- a batch of chord steps: the factor is kept, only the right-hand side is refreshed; acceptance, the convergence
@@ -639,7 +760,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             }
             double rho = (std::isfinite(prev_rel_h) && last_rel < prev_rel_h) ? last_rel / prev_rel_h : 0.2;
             rho = std::fmin(std::fmax(rho, 0.02), 0.5);
-            int kb = (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
+            int kb = !std::isfinite(last_rel) ? 3 : (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
             if (first_chord_batch) kb = std::min(kb, 3);
             kb = std::max(1, std::min(kb, std::min(CHORD_BATCH_MAX, max_iter - it)));
             first_chord_batch = false;
@@ -648,10 +769,11 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.state, state_h, sizeof(state_h), cudaMemcpyHostToDevice, st));
             const double* skip = ws.state + 4;               // non-zero once a step of the batch has stopped it
             for (int i = 0; i < kb; ++i) {
+                if (bordered) refresh_border(skip);
                 PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr, skip);
                 if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st, skip))) return rc;
                 PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t, skip);
-                if ((rc = potrs_vec_blockinv(Lfac, ldl, M, ws.binv, ws.t, st, skip))) return rc;
+                if ((rc = chord_solve(skip))) return rc;
                 PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha, skip);
                 if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st, skip))) return rc;
                 PPBO_CL chord_lik_kernel<<<set_blocks, 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.state, ws.set_part);
@@ -668,6 +790,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                     fprintf(stderr, "[ppbo_laplace_fit] it %d chord  step 1 rel %.3e T %.12g (batch of %d)\n", it + i, hist_h[2 * i], hist_h[2 * i + 1], kb);
             it += taken;
             n_chord += taken;
+            if (warm_factor && std::isnan(warm_first_rel) && taken > 0) warm_first_rel = hist_h[0];
             if (taken > 0) {
                 T_cur = state_h[0];
                 last_rel = state_h[1];
@@ -692,6 +815,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             ++n_factor;
             binv_valid = false;
             factor_current = true;
+            bordered = false;                    // a full factor of the grown system replaces the bordered one
             chord_omega = 1.0;                   // a new factor: new iteration matrix, forget the contraction history
             chord_ratio = 0.0;
             chord_wait = 0.0;
@@ -761,6 +885,27 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     }
     // The factor a later warm fit can reuse is the one the last Newton step built (or the warm one it was handed): its
     // coefficients go to sa_fac.  (An identity "factor" -- cold start that converged at once -- is not a factor object.)
+    if (bordered && !factor_at_mode) {
+        // grow the factor object by the border rows with their final coefficients (the next iteration's "old" factor):
+        // L[new, 0:b0] = s_n R[:, 0:b0]; the block rows from the last 128-boundary on are refactored from their Schur complement
+        const long long Mp = (M + 1) / 2 * 2;
+        const int b0 = (M_old / CHOL_NB) * CHOL_NB, nt = M - b0;
+        if (b0 > 0) PPBO_CL border_write_rows_kernel<<<dim3(ceil_div(b0, 256), nb), 256, 0, st>>>(ws.bR, Mp, ws.sa + M_old, M_old, nb, b0, Lfac, ldl);
+        PPBO_CL newton_rows_kernel<<<dim3(ceil_div(M, 256), nt), 256, 0, st>>>(G, ldg, ws.sa, b0, M, M, b0, Lfac, ldl);
+        PPBO_LAUNCH_CHECK();
+        if (b0 > 0) {
+            double* Lt = Lfac + (long long)b0 * ldl;
+            GemmOperands g{Lt, ldl, 0, Lt, ldl, 0, nt, nt, b0};
+            StoreEpilogue ep{Lt + b0, ldl, 0, -1.0, 1.0, 1, 0};
+            if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
+        }
+        if ((rc = potrf_lower(Lfac + (long long)b0 * ldl + b0, ldl, nt, Mdinv + (long long)(b0 / CHOL_NB) * CHOL_NB * CHOL_NB, ws.info, st)))
+            return rc;
+        PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        factor_current = info == 0;
+        info = 0;
+    }
     bool have_factor = factor_current && !identity_factor;
     if (sa_fac && have_factor && !factor_at_mode)
         PPBO_CUDA_CHECK(cudaMemcpyAsync(sa_fac, ws.sa, sizeof(double) * M, cudaMemcpyDeviceToDevice, st));
@@ -789,6 +934,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         stats_h[8] = factor_at_mode ? 2.0 : (have_factor ? 1.0 : 0.0);   // 2: factor at the mode, 1: last Newton / warm factor, 0: none
         stats_h[9] = converged ? 1.0 : 0.0;
         stats_h[10] = warm_first_rel;
+        stats_h[11] = nb;
     }
     if (info) { set_error("mode system not positive definite at pivot %d", info); return info; }
     return PPBO_OK;

@@ -1527,19 +1527,32 @@ __global__ void __launch_bounds__(BCOL_WARPS * 32) blockcol_update_kernel(const 
     }
 }
 
-// (L L^T) x = t in place with the block inverses W of blockinv_build
-int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip) {
+// scratch vector of the block-inverse solves (behind the inverses; layout fixed by the n the inverses were built for)
+double* blockinv_y(double* W, int n) {
+    const int nbI = ceil_div(n, BI);
+    return W + nbI * (3LL * BI * BI + BI * BI / 4);
+}
+// forward half: y = L^-1 t  (t is consumed; y = blockinv_y(W, n))
+int potrs_fwd_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip) {
     const int nbI = ceil_div(n, BI);
     const long long BB = (long long)BI * BI;
     const double* Binv = W;
-    const double* BinvT = Binv + nbI * BB;
-    double* y = W + nbI * (3 * BB + BB / 4);
+    double* y = blockinv_y(W, n);
     for (int J = 0; J < nbI; ++J) {                     // L y = t
         const int j0 = J * BI, rows = min(BI, n - j0), j1 = j0 + rows;
         PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, BTRI_ROWS), 128 * BTRI_ROWS, 0, st>>>(Binv + J * BB, t + j0, y + j0, rows, 0, skip);
         if (j1 < n)
             PPBO_CL blockrow_update_kernel<<<ceil_div(n - j1, 8), 256, 0, st>>>(L, ldl, j1, n, j0, rows, y + j0, t, skip);
     }
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+// backward half: t = L^-T y  (y is consumed)
+int potrs_bwd_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip) {
+    const int nbI = ceil_div(n, BI);
+    const long long BB = (long long)BI * BI;
+    const double* BinvT = W + nbI * BB;
+    double* y = blockinv_y(W, n);
     for (int J = nbI - 1; J >= 0; --J) {                // L^T x = y
         const int j0 = J * BI, rows = min(BI, n - j0);
         PPBO_CL blocktri_gemv_kernel<<<ceil_div(rows, BTRI_ROWS), 128 * BTRI_ROWS, 0, st>>>(BinvT + J * BB, y + j0, t + j0, rows, 1, skip);
@@ -1547,6 +1560,36 @@ int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double*
             PPBO_CL blockcol_update_kernel<<<ceil_div(j0, 32), BCOL_WARPS * 32, 0, st>>>(L, ldl, j0, j0 + rows, j0, t + j0, y, skip);
     }
     PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+// (L L^T) x = t in place with the block inverses W of blockinv_build
+int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip) {
+    int rc = potrs_fwd_blockinv(L, ldl, n, W, t, st, skip);
+    if (rc) return rc;
+    return potrs_bwd_blockinv(L, ldl, n, W, t, st, skip);
+}
+
+// R[nrhs x n] = T . L^-T with the 1024-block inverses (T is destroyed): n / 1024 steps of two GEMMs instead of the n / 128 steps of
+// trsm_right_lower_t -- the few-row triangular solve of the bordered warm start (laplace.cu) is launch-bound, not flop-bound
+int trsm_right_blockinv(const double* L, long long ldl, int n, const double* W, double* T, long long ldt, double* R, long long ldr,
+                        int nrhs, cudaStream_t st) {
+    const int nbI = ceil_div(n, BI);
+    const long long BB = (long long)BI * BI;
+    for (int J = 0; J < nbI; ++J) {
+        const int j0 = J * BI, rows = min(BI, n - j0), j1 = j0 + rows;
+        {
+            GemmOperands g{T + j0, ldt, 0, W + J * BB, BI, 0, nrhs, rows, rows};
+            StoreEpilogue ep{R + j0, ldr, 0, 1.0, 0.0, 0, 0, 0};
+            int rc = launch_gemm_nt(g, ep, 1, st);
+            if (rc) return rc;
+        }
+        if (j1 < n) {
+            GemmOperands g{R + j0, ldr, 0, L + (long long)j1 * ldl + j0, ldl, 0, nrhs, n - j1, rows};
+            StoreEpilogue ep{T + j1, ldt, 0, -1.0, 1.0, 0, 0, 0};
+            int rc = launch_gemm_nt(g, ep, 1, st);
+            if (rc) return rc;
+        }
+    }
     return PPBO_OK;
 }
 

@@ -18,6 +18,12 @@ int trsm_right_lower_t(const double* L, long long ldl, int n, const double* dinv
 long long blockinv_doubles(int n);
 int blockinv_build(const double* L, long long ldl, int n, const double* dinv, double* W, cudaStream_t st);
 int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip = nullptr);
+// the two halves of potrs_vec_blockinv (y = L^-1 t lands in blockinv_y(W, n); t = L^-T y) and the few-row right solve
+double* blockinv_y(double* W, int n);
+int potrs_fwd_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip = nullptr);
+int potrs_bwd_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip = nullptr);
+int trsm_right_blockinv(const double* L, long long ldl, int n, const double* W, double* T, long long ldt, double* R, long long ldr,
+                        int nrhs, cudaStream_t st);
 int gemv(const double* A, long long lda, int M, int N, const double* x, double* y, cudaStream_t st, const double* skip = nullptr);
 
 }  // namespace ppbo

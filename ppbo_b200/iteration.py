@@ -161,7 +161,8 @@ class GPState(GPFit):
     adds comparison sets in O(N^2 m): new rows of Sigma and G, the factor of the previous iteration grown by the new rows, and
     a chord iteration from the previous mode (new points start at their posterior mean) -- no O(N^3) factorisation unless the
     chord steps contract too slowly (ppbo_laplace_fit falls back to a Newton step by itself)."""
-    __slots__ = ("Q_cap", "X_cap", "Sigma_cap", "f_buf", "alpha_buf", "arrow_buf", "f_init_buf", "shrinkage", "max_iter", "tol")
+    __slots__ = ("Q_cap", "X_cap", "Sigma_cap", "f_buf", "alpha_buf", "arrow_buf", "f_init_buf", "alpha_init_buf", "shrinkage",
+                 "max_iter", "tol")
 
     def __init__(self, kernel, theta, D, m, Q_cap, dev, lengthscales=None, max_iter=100, tol=1e-8, shrinkage=SHRINKAGE):
         lib = ops._lib.load()
@@ -171,7 +172,7 @@ class GPState(GPFit):
         Nc, Mc = Q_cap * (m + 1), Q_cap * m
         self.X_cap = torch.empty((Nc, D), dtype=F64, device=dev)
         self.Sigma_cap = torch.empty((Nc, Nc), dtype=F64, device=dev)
-        self.f_buf, self.alpha_buf, self.f_init_buf = (torch.empty(Nc, dtype=F64, device=dev) for _ in range(3))
+        self.f_buf, self.alpha_buf, self.f_init_buf, self.alpha_init_buf = (torch.empty(Nc, dtype=F64, device=dev) for _ in range(4))
         self.arrow_buf = torch.empty(Mc, dtype=F64, device=dev)
         lap = ops.LaplaceFit()
         lap.cap = lap.ldg = Mc
@@ -218,17 +219,18 @@ class GPState(GPFit):
         self.X_cap[N_old:N].copy_(X_block)
         ops.gram_append(self.kernel, self.X, N_old, self.lengthscales, self.theta[2], self.shrinkage, self.Sigma_cap)
         ops.diffspace_gram_append(self.Sigma, Q_old, Q_new, m, self.lap.G)
-        # warm start: the previous mode on the old rows, the posterior mean k(x_new, X_old) alpha_old on the new ones (the
-        # reference pads with the mean of fMAP, src/gp_model.py:375-377; both are starts for the same fixed point)
-        f_init = self.f_init_buf[:N]
+        # warm start: alpha = [alpha_old, 0] and f = Sigma_new alpha, i.e. the previous mode on the old rows and the posterior mean
+        # k(x_new, X_old) alpha_old on the new ones -- consistent by construction, so the chord iteration (with its acceptance
+        # test) starts at once.  (The reference pads fMAP with its mean, src/gp_model.py:375-377; both are starts for the same
+        # fixed point.)
+        f_init, alpha_init = self.f_init_buf[:N], self.alpha_init_buf[:N]
         f_init[:N_old].copy_(self.f_buf[:N_old])
         ops.gemv(self.Sigma_cap[N_old:N, :N_old], alpha_old, out=f_init[N_old:])
+        alpha_init[:N_old].copy_(alpha_old)
+        alpha_init[N_old:].zero_()
         self.lap.Q = Q_new
-        if warm:
-            info = ops.factor_extend(self.lap, M_old, M, f_new_sets=f_init[N_old:], sigma=self.theta[0])
-            warm = info == 0
-        ops.laplace_fit(self.Sigma, Q_new, m, self.theta[0], f_init=f_init, max_iter=self.max_iter, tol=self.tol,
-                        factor_at_mode=factor_at_mode, into=self.lap, g_ready=True, warm_factor=warm)
+        ops.laplace_fit(self.Sigma, Q_new, m, self.theta[0], f_init=f_init, alpha_init=alpha_init, max_iter=self.max_iter,
+                        tol=self.tol, factor_at_mode=factor_at_mode, into=self.lap, g_ready=True, warm_rows=M_old if warm else 0)
         if self.lap.info != 0:
             raise PPBOError("Laplace fit: system not positive definite (info=%d)" % self.lap.info)
         self.Q = Q_new

@@ -157,13 +157,15 @@ class LaplaceFit:
 
 
 _STATS = ("iterations", "last_step", "last_rel_step", "T", "halvings", "info", "factorizations", "chord_steps", "factor_state",
-          "converged", "warm_first_rel")
+          "converged", "warm_first_rel", "border_rows")
 
 
 def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10, factor_at_mode=False, into=None, g_ready=False,
-                warm_factor=False):
+                warm_rows=0, alpha_init=None):
     """MAP fit.  `into`: a LaplaceFit whose (capacity) buffers G / factor / sa_fac are reused -- with g_ready the grown G is
-    taken as is, with warm_factor the factor left by the previous fit (grown by factor_extend) starts the chord iteration."""
+    taken as is; warm_rows > 0: the factor object holds the factor of the leading warm_rows x warm_rows system (the previous
+    iteration's) and the chord iteration starts from (f_init, alpha_init) with the appended rows carried as a border."""
+    warm_factor = warm_rows > 0
     lib = _lib.load()
     dev = Sigma.device
     N, M = Q * (m + 1), Q * m
@@ -186,12 +188,13 @@ def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10, factor
     wbytes = lib.ppbo_laplace_workspace_bytes(Q, m)
     ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev)
     stats = (ctypes.c_double * 12)()
-    rc = check(lib.ppbo_laplace_fit(_p(Sigma), Sigma.stride(0), Q, m, float(sigma), _p(f_init), int(max_iter), float(tol), flags,
-                                    _p(fit.G), fit.ldg, _p(fit._Lfac), fit.cap, _p(fit.sa_fac), _p(fit.f_map), _p(fit.alpha),
-                                    _p(fit.arrow), _p(ws), wbytes, stats, _stream()), "ppbo_laplace_fit")
+    rc = check(lib.ppbo_laplace_fit(_p(Sigma), Sigma.stride(0), Q, m, float(sigma), _p(f_init), _p(alpha_init), int(max_iter),
+                                    float(tol), flags, _p(fit.G), fit.ldg, _p(fit._Lfac), fit.cap, _p(fit.sa_fac), int(warm_rows),
+                                    _p(fit.f_map), _p(fit.alpha), _p(fit.arrow), _p(ws), wbytes, stats, _stream()),
+               "ppbo_laplace_fit")
     fit.info = rc
     fit.stats = {k: stats[i] for i, k in enumerate(_STATS)}
-    for k in ("iterations", "halvings", "factorizations", "chord_steps", "converged"):
+    for k in ("iterations", "halvings", "factorizations", "chord_steps", "converged", "border_rows"):
         fit.stats[k] = int(fit.stats[k])
     fit.factor_state = int(stats[8]) if rc == 0 else 0
     fit.n_neg, fit._neg_corr, fit._neg_idx = 0, None, None
