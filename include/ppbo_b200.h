@@ -171,6 +171,8 @@ int ppbo_gemv(const double* A, long long lda, int M, int N, const double* x, dou
 
 /* ---- K4: prediction and exact-GP acquisition ----------------------------------------------------- */
 long long ppbo_predict_workspace_bytes(int N, int Q, int m, int P, int batch);
+/* workspace of a mean-only call (Sigma_p == NULL): the SE / RQ tensor-pipe path never materialises the cross-covariance */
+long long ppbo_predict_mean_workspace_bytes(int kind, int N, int P, int batch);
 /* Posterior mean and covariance on `batch` grids of P points each (Xp: [batch*P x D]).
  * mu = k*' alpha ; Sigma_p = reg(K**) - k*' (Sigma^-1 - Sigma^-1 Post Sigma^-1) k*  evaluated as
  * reg(K**) - Y'Y (+ low-rank term for negative arrow coefficients), Y = Lfac^-1 a+^1/2 B' k*.

@@ -59,7 +59,10 @@ def synthetic_queries(ref, D, bounds, Q, utility_centre):
         if q < D or q % 3:
             xi[q % D] = hi[q % D] if hi[q % D] != 0 else 1.0
         else:                                   # a few genuinely projective (multi-coordinate) queries
-            dims = np.random.choice(D, size=min(D, 2), replace=False)
+            # (only over coordinates whose range contains 0: alpha xi must be able to stay inside the box together with x = 0
+            # there -- the camphor problem's height coordinate (4, 7) cannot be part of a multi-coordinate direction)
+            ok = np.where((lo <= 0) & (hi >= 0))[0]
+            dims = np.random.choice(D if len(ok) == D else ok, size=min(len(ok), 2), replace=False)
             xi[dims] = np.random.uniform(0.2, 1.0, size=len(dims)) * np.abs(hi[dims])
         x = np.random.uniform(lo, hi)
         x[xi != 0] = 0

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "ppbo_neg_corr_doubles": (_L, [_I, _I]),
     "ppbo_neg_corr_build": (_I, [_P, _L, _I, _P, _P, _I, _PI, _I, _P, _P]),
     "ppbo_predict_workspace_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "ppbo_predict_mean_workspace_bytes": (_L, [_I, _I, _I, _I]),
     "ppbo_predict": (_I, [_I, _P, _I, _I, _PD, _D, _D, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _I, _P, _P, _P, _L, _P]),
     "ppbo_mu_pred_point": (_I, [_I, _P, _I, _I, _PD, _D, _P, _PD, _PD, _P]),
     "ppbo_mvn_rowmax": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P]),

@@ -14,6 +14,7 @@
 
 namespace ppbo {
 
+extern int g_tuning[16];
 int kernel_matvec(int kind, const double* X1, int n1, const double* X2, int n2, int D, const double* ls_h, double sigma_f,
                   const double* alpha, double* mu, double* partial, cudaStream_t st);
 int kernel_matrix_raw(int kind, const double* X1, int n1, const double* X2, int n2, int D, const double* ls_h,
@@ -419,6 +420,13 @@ extern "C" long long ppbo_predict_workspace_bytes(int N, int Q, int m, int P, in
     return (PT * N + PT * M + PT * M + 64) * 8;     // Kc, Ut, (Ud | Zs up to r <= M columns)
 }
 
+/* workspace of a mean-only call (Sigma_p == NULL): the tensor-pipe kernels never materialise the cross-covariance */
+extern "C" long long ppbo_predict_mean_workspace_bytes(int kind, int N, int P, int batch) {
+    const long long PT = (long long)P * batch;
+    if (kind == PPBO_KERNEL_SE || kind == PPBO_KERNEL_RQ) return (PT * ((N + 63) / 64) + 64) * 8;
+    return (PT * N + 64) * 8;
+}
+
 extern "C" int ppbo_predict(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f,
                             double shrinkage, int Q, int m, const double* alpha, const double* arrow, const double* Lfac, int cap,
                             const double* neg_corr, int n_neg, const double* Xp, int P, int batch, double* mu,
@@ -426,7 +434,9 @@ extern "C" int ppbo_predict(int kind, const double* X, int N, int D, const doubl
     PPBO_REQUIRE(N == Q * (m + 1), "N must equal Q (m+1)");
     PPBO_REQUIRE(Sigma_p == nullptr || cap >= Q * m, "factor capacity below Q m");
     PPBO_REQUIRE(P >= 1 && batch >= 1, "empty grid");
-    PPBO_REQUIRE(workspace_bytes >= ppbo_predict_workspace_bytes(N, Q, m, P, batch), "workspace too small");
+    PPBO_REQUIRE(workspace_bytes >= (Sigma_p ? ppbo_predict_workspace_bytes(N, Q, m, P, batch)
+                                             : ppbo_predict_mean_workspace_bytes(g_tuning[11] ? PPBO_KERNEL_CAMPHOR : kind, N, P, batch)),
+                 "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int PT = P * batch, M = Q * m;
     double* Kc = (double*)workspace;                 // [PT x N]   k(x*_p, X_i)

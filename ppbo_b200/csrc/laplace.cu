@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(256) chord_lik_kernel(const double* __restrict
 //   state[4] 0 = keep going, 1 = converged, 2 = contraction too slow (refactor), 3 = full step rejected (refactor)
 //   state[5] chord steps taken in this batch      state[6] tolerance         state[7] step length omega of the queued step
 //   state[8] previous contraction ratio           state[9] steps to wait before the next extrapolation
+//   state[10] slowest contraction per step that is still cheaper than a new factor (0.5 after a Newton step of this fit; 0.85 for
+//             the factor of the previous PPBO iteration: a chord step costs ~1/12 of a factorisation there and a refactorisation
+//             is followed by one or two more)
 //   hist[2i], hist[2i+1] = (rel, T) of step i
 // A chord step of length 1 is only taken when T(alpha + dalpha) does not fall below T (same rule as the host line search with
 // c == 0).  When state[4] != 0 this kernel and every other kernel of a queued step return at once (skip flag).
@@ -253,7 +256,10 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
         const bool accept = T1 >= T_cur - 1e-13 * fabs(T_cur);
         double step = 0.0;
         if (!accept) {
-            if (omega != 1.0) { state[7] = 1.0; state[9] = 4.0; }      // repeat this step at full length, no extrapolation for a while
+            if (omega > 1.0) { state[7] = 1.0; state[9] = 4.0; }       // repeat this step at full length, no extrapolation for a while
+            else if (omega > 0.2) { state[7] = 0.5 * omega; state[9] = 4.0; }   // backtrack along the same direction (appended rows start
+                                                                        // where the likelihood curvature vanishes: their first
+                                                                        // Newton step overshoots like the cold start's does)
             else state[4] = 3.0;
         } else {
             step = omega;
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
             const bool after_extrapolation = omega != 1.0;
             if (rel <= state[6]) {
                 state[4] = 1.0;
-            } else if (!after_extrapolation && wait <= 0.0 && !(rel <= 0.5 * prev)) {
+            } else if (!after_extrapolation && wait <= 0.0 && !(rel <= state[10] * prev)) {
                 state[4] = 2.0;                                        // plain steps contract too slowly: pay for a new factor
             } else if (wait > 0.0 && !(rel <= 4.0 * prev)) {
                 state[4] = 2.0;                                        // residual grows after an extrapolation: give up on this factor
@@ -759,12 +765,13 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 binv_valid = true;
             }
             double rho = (std::isfinite(prev_rel_h) && last_rel < prev_rel_h) ? last_rel / prev_rel_h : 0.2;
-            rho = std::fmin(std::fmax(rho, 0.02), 0.5);
+            rho = std::fmin(std::fmax(rho, 0.02), (warm_factor && n_factor == 0) ? 0.85 : 0.5);
             int kb = !std::isfinite(last_rel) ? 3 : (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
             if (first_chord_batch) kb = std::min(kb, 3);
             kb = std::max(1, std::min(kb, std::min(CHORD_BATCH_MAX, max_iter - it)));
             first_chord_batch = false;
-            double state_h[CHORD_STATE] = {T_cur, last_rel, prev_rel_h, last_step, 0.0, 0.0, tol, chord_omega, chord_ratio, chord_wait};
+            const double slow = (warm_factor && n_factor == 0) ? 0.85 : 0.5;
+            double state_h[CHORD_STATE] = {T_cur, last_rel, prev_rel_h, last_step, 0.0, 0.0, tol, chord_omega, chord_ratio, chord_wait, slow};
             double hist_h[2 * CHORD_BATCH_MAX];
             PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.state, state_h, sizeof(state_h), cudaMemcpyHostToDevice, st));
             const double* skip = ws.state + 4;               // non-zero once a step of the batch has stopped it

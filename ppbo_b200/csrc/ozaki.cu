@@ -22,6 +22,7 @@
 //               shared-memory image the tensor core reads, see slice layout below) -> 3-stage mbarrier ring
 //   warp 1      one elected lane issues tcgen05.mma.kind::i8 (M=128, N=BN, K=32): KS accumulators of BN columns in TMEM
 //   warps 2..5  epilogue: tcgen05.ld the KS INT32 accumulators, recombine in INT64 -> FP64, scale, running row max/arg-max
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <mutex>
@@ -241,11 +242,31 @@ struct Params {
     const int8_t* B; const double* bscale; int P, NT, batch;   // NT column tiles of BN grid points per batch entry
     int KBLK;
     int NG, ntg;                                               // column tiles are taken in NG groups of ntg tiles: one work item each
+    int GB;                                                    // grids are visited in blocks of GB (work order, see decode_item)
     double* fmax; int* arg;                                    // [batch][S] (NG == 1) or partial results [batch][NG][S]
     double* full; long long ld_full, stride_full;              // optional dense output (tests)
     int* err;
     int diag;      // timing experiments only (tuning key 2): bit 0 = epilogue skips the TMEM reads, bit 1 = producer skips the copies
 };
+
+// Work order.  item -> (grid b, row tile mt, column-tile group ng):  grids in blocks of GB; inside a block the row tiles; inside a
+// row tile the GB grids of the block; inside a grid the NG column groups (fastest).  The ~SM-count items in flight then cover
+// SMs / (GB NG) row tiles (their A planes, KBLK x A_STAGE = 768 KB each at F = 1000, are read from DRAM once per grid BLOCK and from
+// L2 by the GB NG items that share them) and the B planes of GB grids (GB x 6.3 MB, L2-resident for the whole block).  With the
+// earlier order (grid outermost) every grid re-streamed all A planes from DRAM: 4.5 GB of DRAM reads per launch at B = 20 against
+// 0.33 GB of planes (profiles/r01_ncu_ozaki_rowmax.txt).
+__device__ __forceinline__ void decode_item(const Params& p, int item, int& b, int& mt, int& ng) {
+    const int per_grid_row = p.NG, full = p.batch / p.GB, rem = p.batch - full * p.GB;
+    const int block_items = p.GB * p.MT * per_grid_row, items_full = full * block_items;
+    int gb, nb_, r;
+    if (item < items_full) { gb = item / block_items; r = item - gb * block_items; nb_ = p.GB; }
+    else { gb = full; r = item - items_full; nb_ = rem; }
+    mt = r / (nb_ * per_grid_row);
+    const int r2 = r - mt * nb_ * per_grid_row;
+    const int bl = r2 / per_grid_row;
+    ng = r2 - bl * per_grid_row;
+    b = gb * p.GB + bl;
+}
 
 // 16 columns of one row: recombine the KS INT32 accumulators into two exact INT64 words (hi: diagonals < G1, lo: the rest),
 // convert, add with ONE rounding, scale by the column's power of two and update the running max / first arg-max.
@@ -333,7 +354,8 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
         // ------------------------------------------------------------------------------------- producer
         uint32_t stage = 0, phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int ng = item % p.NG, mt = (item / p.NG) % p.MT, b = item / (p.NG * p.MT);
+            int ng, mt, b;
+            decode_item(p, item, b, mt, ng);
             const int nt0 = ng * p.ntg, nt1 = min(p.NT, nt0 + p.ntg);
             const int8_t* Ab = p.A + (long long)mt * p.KBLK * C::A_STAGE;
             for (int nt = nt0; nt < nt1; ++nt) {
@@ -356,7 +378,8 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
         // ------------------------------------------------------------------------------------- MMA issuer
         uint32_t stage = 0, phase = 0, tile = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int ng = item % p.NG;
+            int ng, mt, b;
+            decode_item(p, item, b, mt, ng);
             const int nt0 = ng * p.ntg, nt1 = min(p.NT, nt0 + p.ntg);
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
                 mbar_wait(tempty_bar, (tile & 1) ^ 1, p.err, 2);         // epilogue has drained the accumulators
@@ -416,7 +439,8 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
         const double c_hi = ldexp(1.0, -8 * (C::G1 + 1));
         uint32_t tile = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int ng = item % p.NG, mt = (item / p.NG) % p.MT, b = item / (p.NG * p.MT);
+            int ng, mt, b;
+            decode_item(p, item, b, mt, ng);
             const int nt0 = ng * p.ntg, nt1 = min(p.NT, nt0 + p.ntg);
             const int row = mt * BM + q * 32 + lane;
             const double as2 = ((row < p.S) ? p.ascale[row] : 1.0) * c_hi;     // row scale and the weight of the high word
@@ -686,6 +710,12 @@ extern "C" int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascal
     p.KBLK = ceil_div(K, oz::KB);
     p.NG = oz::column_groups(p.NT, p.KBLK, slices);
     p.ntg = ceil_div(p.NT, p.NG);
+    // grids per block: as many as keep the block's B planes within ~48 MB of L2 (tuning key 12 overrides; 1 = the earlier order)
+    {
+        const long long grid_bytes = (long long)p.NT * p.KBLK * slices * oz::BN_DEFAULT * oz::KB;
+        int gbk = g_tuning[12] > 0 ? g_tuning[12] : (int)std::max<long long>(1, (48LL << 20) / std::max<long long>(grid_bytes, 1));
+        p.GB = std::min(std::max(gbk, 1), batch);
+    }
     PPBO_REQUIRE(workspace_bytes >= ppbo_ozaki_rowmax_workspace_bytes(S, P, batch), "workspace too small");
     PPBO_REQUIRE(p.NG == 1 || workspace != nullptr, "workspace missing");
     double* pmax = reinterpret_cast<double*>(workspace);

@@ -27,6 +27,23 @@ def _p(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+_SCRATCH = {}
+
+
+def _scratch(purpose, nbytes, dev):
+    """Workspace of at least nbytes for `purpose`: one buffer per (purpose, device, host thread, stream), kept between calls and
+    grown with 25 % headroom.  A model that grows by one comparison set per iteration asks for a slightly larger workspace every
+    time; fresh allocations would miss the caching allocator's pool each iteration (a cudaMalloc of up to hundreds of MB, and the
+    cached smaller block is never reused).  Calls with the same key are ordered on their stream, so reuse is safe."""
+    import threading
+    key = (purpose, dev.index, threading.get_ident(), torch.cuda.current_stream(dev).cuda_stream)
+    buf = _SCRATCH.get(key)
+    need = nbytes // 8 + 2
+    if buf is None or buf.numel() < need:
+        buf = _SCRATCH[key] = torch.empty(int(need * 1.25) + 16, dtype=F64, device=dev)
+    return buf
+
+
 def to_dev(a, dev=None):
     """host array-like -> contiguous float64 CUDA tensor"""
     if isinstance(a, torch.Tensor):
@@ -186,7 +203,7 @@ def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10, factor
     flags = (_lib.FIT_G_READY if g_ready else 0) | (_lib.FIT_FACTOR_WARM if warm_factor else 0) | \
             (_lib.FIT_FACTOR_AT_MODE if factor_at_mode else 0)
     wbytes = lib.ppbo_laplace_workspace_bytes(Q, m)
-    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev)
+    ws = _scratch("laplace", wbytes, dev)
     stats = (ctypes.c_double * 12)()
     rc = check(lib.ppbo_laplace_fit(_p(Sigma), Sigma.stride(0), Q, m, float(sigma), _p(f_init), _p(alpha_init), int(max_iter),
                                     float(tol), flags, _p(fit.G), fit.ldg, _p(fit._Lfac), fit.cap, _p(fit.sa_fac), int(warm_rows),
@@ -344,8 +361,9 @@ def predict(kernel, X, lengthscales, sigma_f, shrinkage, fit, Xp, P, batch, want
     dev = X.device
     mu = torch.empty(P * batch, dtype=F64, device=dev)
     Sp = torch.empty((batch, P, P), dtype=F64, device=dev) if want_cov else None
-    wbytes = lib.ppbo_predict_workspace_bytes(N, fit.Q, fit.m, P, batch)
-    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev)
+    wbytes = (lib.ppbo_predict_workspace_bytes(N, fit.Q, fit.m, P, batch) if want_cov else
+              lib.ppbo_predict_mean_workspace_bytes(_kind(kernel), N, P, batch))
+    ws = _scratch("predict" if want_cov else "predict_mean", wbytes, dev)
     neg_corr = fit.neg_corr if want_cov else None            # the mean needs alpha only (no factor, no Woodbury term)
     Lfac = fit.Lfac if want_cov else None
     check(lib.ppbo_predict(_kind(kernel), _p(X), N, D, _ls(lengthscales, D), float(sigma_f), float(shrinkage), fit.Q, fit.m,
@@ -360,8 +378,8 @@ def posterior_mean(kernel, X, lengthscales, sigma_f, alpha, Xp):
     N, D = X.shape
     P = Xp.shape[0]
     mu = torch.empty(P, dtype=F64, device=X.device)
-    wbytes = lib.ppbo_predict_workspace_bytes(N, N, 0, P, 1)
-    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=X.device)
+    wbytes = lib.ppbo_predict_mean_workspace_bytes(_kind(kernel), N, P, 1)
+    ws = _scratch("predict_mean", wbytes, X.device)
     check(lib.ppbo_predict(_kind(kernel), _p(X), N, D, _ls(lengthscales, D), float(sigma_f), 0.0, N, 0, _p(alpha), None, None, 0,
                            None, 0, _p(Xp), P, 1, _p(mu), None, _p(ws), wbytes, _stream()), "ppbo_predict")
     return mu
@@ -430,7 +448,7 @@ def rff_jacobian(W, b, x, sigma_f):
 
 def _rff_ws(F, Q, m, dev):
     wbytes = _lib.load().ppbo_rff_workspace_bytes(F, Q, m)
-    return torch.empty(wbytes // 8 + 1, dtype=F64, device=dev), wbytes
+    return _scratch("rff", wbytes, dev), wbytes
 
 
 def rff_objective(Phi_X, Q, m, sigma, omega, want_S=True, want_grad=True, want_hess=True):
@@ -494,7 +512,7 @@ def ozaki_rowmax(ap, asc, S, bp, bsc, P, B, F, slices, fmax=None, arg=None, want
     arg = torch.empty((B, S), dtype=torch.int32, device=dev) if arg is None else arg
     full = torch.empty((B, S, P), dtype=F64, device=dev) if want_full else None
     wbytes = lib.ppbo_ozaki_rowmax_workspace_bytes(S, P, B)
-    ws = torch.empty(wbytes // 8 + 1, dtype=F64, device=dev) if wbytes > 0 else None
+    ws = _scratch("ozaki_rowmax", wbytes, dev) if wbytes > 0 else None
     check(lib.ppbo_ozaki_rowmax(_p(ap), _p(asc), S, _p(bp), _p(bsc), P, B, F, slices, _p(fmax), _p(arg), _p(full), _p(ws), wbytes,
                                 _p(err), _stream()), "ppbo_ozaki_rowmax")
     return fmax, arg, full

@@ -98,6 +98,7 @@ class GPModel:
         self._Sigma_dev = None       # [N x N]
         self._fit = None             # ops.LaplaceFit (f_map, alpha, arrow, G, Lfac, neg_corr)
         self.fit_stats = None
+        self.timing = {}             # seconds spent in the last update_model: 'fit' (covariance + MAP), 'mu_star' 
 
     # ------------------------------------------------------------------ wrappers (src/gp_model.py:73-85)
     def update_feedback_processing_object(self, X_obs):
@@ -317,6 +318,7 @@ class GPModel:
 
     # ------------------------------------------------------------------ model update (src/gp_model.py:87-132)
     def update_model(self, optimize_theta=False):
+        t_fit = time.time()
         if self.theta is None:
             self.set_theta()
         self.update_Sigma(self.theta)
@@ -340,6 +342,7 @@ class GPModel:
         if self.verbose:
             print("Computing mu_star and x_star ...")
         start = time.time()
+        self.timing["fit"] = start - t_fit
         if init_light and not self.skip_xstaroptimization_during_initialization:
             self.xstar, self.mustar, self.xstars_local = self.mu_star(mustar_finding_trials=1)
         elif self.initialization_running and self.skip_xstaroptimization_during_initialization:
@@ -348,6 +351,7 @@ class GPModel:
             self.xstar, self.mustar, self.xstars_local = self.mu_star(mustar_finding_trials=20)
         else:
             self.xstar, self.mustar, self.xstars_local = self.mu_star()
+        self.timing["mu_star"] = time.time() - start
         if self.verbose:
             print("... this took " + str(time.time() - start) + " seconds.")
 
