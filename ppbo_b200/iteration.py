@@ -77,17 +77,18 @@ class Shard:
     def sample_bounds(self, S, shares=None):
         """Partition of the Monte-Carlo samples inside run_iteration.  shares: one non-negative weight per rank (plan_shares);
         the default gives the rank that runs the GP fit (rank 0) none: the sampling contraction does not depend on the GP fit
-        -- only the final reduction needs mu* -- so the other ranks evaluate all samples WHILE rank 0 fits.  Boundaries are
-        multiples of 128 samples (one row tile of the tensor-core kernel) except the last."""
+        -- only the final reduction needs mu* -- so the other ranks evaluate all samples WHILE rank 0 fits.  For large S the
+        boundaries are multiples of 128 samples (one row tile of the tensor-core kernel) except the last."""
         if self.world == 1:
             return 0, S
         if shares is None:
             shares = [0.0] + [1.0] * (self.world - 1)
         tot = float(sum(shares))
+        align = 128 if S >= 512 * self.world else 1
         cum, edges = 0.0, [0]
         for w in shares:
             cum += w
-            e = int(round(S * cum / tot / 128.0)) * 128
+            e = int(round(S * cum / tot / align)) * align
             edges.append(min(S, max(edges[-1], e)))
         edges[-1] = S
         return edges[self.rank], edges[self.rank + 1]

@@ -27,9 +27,20 @@ GRID_POINTS = 70          # hard-coded in the reference (src/acquisition.py:73,1
 
 
 # ------------------------------------------------------------------------------------------------ batched MC engine
+try:
+    from threadpoolctl import threadpool_limits as _blas_limits
+except Exception:        # pragma: no cover
+    _blas_limits = None
+
+
 def _svd_factor(cov):
-    """(P x P) F with F[p][k] = sqrt(s_k) V[k][p]: numpy's legacy multivariate_normal factor, transposed for the GEMM"""
-    _, s, v = np.linalg.svd(cov)
+    """(P x P) F with F[p][k] = sqrt(s_k) V[k][p]: numpy's legacy multivariate_normal factor, transposed for the GEMM.
+    One BLAS thread: a 70 x 70 SVD on a many-core host otherwise spends its time waking and parking the thread pool."""
+    if _blas_limits is not None:
+        with _blas_limits(limits=1):
+            _, s, v = np.linalg.svd(cov)
+    else:
+        _, s, v = np.linalg.svd(cov)
     return np.ascontiguousarray((np.sqrt(s)[:, None] * v).T)
 
 
@@ -47,6 +58,8 @@ def _device_factor(Sp_dev):
             if info == 0:
                 break
             jitter = max(10 * jitter, 1e-12 * float(Sp_dev[b].diagonal().max()))
+        else:
+            raise np.linalg.LinAlgError("predictive covariance of grid %d is not positive definite even with jitter %g" % (b, jitter))
         out[b] = A.tril()
     return out
 
@@ -55,18 +68,26 @@ def sampled_max_batch(pairs, GP_model, mc_samples):
     """For every (xi, x) in `pairs`: f_max of `mc_samples` posterior draws on the 70-point projected grid.
     Returns fmax [B, S] on the device.  RNG order per pair = reference order inside EI / varmax (:73-79)."""
     B, S, P = len(pairs), int(mc_samples), GRID_POINTS
+    t0 = time.time()
     grids = np.empty((B, P, GP_model.D))
     Z = np.empty((B, S, P))
     for b, (xi, x) in enumerate(pairs):
         grids[b] = GP_model.FP.xi_grid(xi=xi, x=x, alpha_grid_distribution='equispaced', alpha_star=None, m=P, is_scaled=True)
         Z[b] = np.random.standard_normal((S, P))            # == S successive multivariate_normal draws of size P
+    t1 = time.time()
     mu, Sp = GP_model._predict_dev(ops.to_dev(grids.reshape(B * P, -1)), P, B)
     if getattr(GP_model, "mvn_factor", "svd-host") == "device":
         Fac = _device_factor(Sp)
+        t2 = t3 = time.time()
     else:
         Sp_h = Sp.cpu().numpy()
+        t2 = time.time()
         Fac = ops.to_dev(np.stack([_svd_factor(Sp_h[b]) for b in range(B)]))
+        t3 = time.time()
     fmax, _arg = ops.mvn_rowmax(ops.to_dev(Z), Fac, mu)
+    tm = getattr(GP_model, "timing", None)
+    if tm is not None:       # seconds: host draws / device prediction (incl. the factor at the mode on first use) / host SVD factors
+        tm["acq_draws"], tm["acq_predict"], tm["acq_svd"] = t1 - t0, t2 - t1, t3 - t2
     return fmax
 
 

@@ -120,8 +120,31 @@ def test_shard_bounds_cover_everything():
             assert edges[0][0] == 0 and edges[-1][1] == S
             assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
             sizes = [hi - lo for lo, hi in edges]
+            if world > 1:       # large S: boundaries are multiples of 128 samples (one row tile of the tensor-core kernel)
+                assert sizes[0] == 0 and max(sizes[1:]) - min(sizes[1:]) <= (128 if S >= 512 * world else 1)
+                assert S < 512 * world or all(lo % 128 == 0 for lo, hi in edges)
+            # weighted shares (plan_shares): complete, ordered, proportional up to one row tile per boundary
             if world > 1:
-                assert sizes[0] == 0 and max(sizes[1:]) - min(sizes[1:]) <= 1
+                shares = [0.25] + [1.0] * (world - 1)
+                edges = [Fake(r, world).sample_bounds(S, shares) for r in range(world)]
+                assert edges[0][0] == 0 and edges[-1][1] == S
+                assert all(a[1] == b[0] for a, b in zip(edges[:-1], edges[1:]))
+                tot = sum(shares)
+                for (lo, hi), w in zip(edges, shares):
+                    assert abs((hi - lo) - S * w / tot) <= 256
+
+
+def test_plan_shares_water_filling():
+    """every rank that samples finishes at the same time; a rank whose fit ends after that time takes no samples"""
+    from ppbo_b200.iteration import plan_shares
+    assert plan_shares(1, 10.0, 5.0, 9.0) == [1.0]
+    sh = plan_shares(2, 10.0, 6.0, 9.0)                    # rank 1 alone would end at 15 > 10: rank 0 helps from t = 10
+    ends = [s_ + st for s_, st in zip(sh, (10.0, 6.0))]
+    assert abs(ends[0] - ends[1]) < 1e-12 and abs(sum(sh) - 9.0) < 1e-12 and sh[0] > 0
+    sh = plan_shares(8, 10.0, 6.0, 9.0)                    # seven ranks finish at 6 + 9/7 < 10: rank 0 takes none
+    assert sh[0] == 0.0 and all(abs(x - 9.0 / 7) < 1e-12 for x in sh[1:])
+    sh = plan_shares(4, 3.0, 2.0, 9.0)                     # steady state: short fits, everybody samples
+    assert all(x > 0 for x in sh) and abs(sum(sh) - 9.0) < 1e-12 and abs((sh[1] - sh[0]) - 1.0) < 1e-12
 
 
 def test_philox_known_answers():
