@@ -356,7 +356,10 @@ def parity_gate(prob, gp, rff, sums_full, S, iteration, ops, torch):
     PhiT = iteration.SlicedGrids(iteration.rff_grid_features(rff.W, rff.b, theta[2], grids))
     mustar = iteration.mustar_over_candidates(gp, grids.reshape(B * P, D))
     gate["mustar_rel"] = float(abs(float(mustar.cpu()[0]) - float(z["mustar"])) / abs(float(z["mustar"])))
-    sums, fmax, arg = iteration.rff_acquisition(rff, PhiT, Ss, mustar, seed=int(z["seed"]), bounds=(0, Ss))
+    class _OneRank(iteration.Shard):          # the gate runs on rank 0 alone: no collective
+        def __init__(self):
+            self.dist, self.group, self.rank, self.world = None, None, 0, 1
+    sums, fmax, arg = iteration.rff_acquisition(rff, PhiT, Ss, mustar, shard=_OneRank(), seed=int(z["seed"]), bounds=(0, Ss))
     sums = sums.cpu().numpy()
     ref = z["slice_sums"]
     gate["slice_samples"] = Ss
@@ -445,7 +448,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
     lib = _lib.load()
     shard = iteration.Shard()
     W_steps, K = max(args.warmup, 3), args.steps
@@ -600,6 +604,8 @@ def main():
     held[0] = None
     steady_reset()
     if world > 1:
+        steady_step(0, host=False)            # (first append on a fresh process: one-time workspace growth)
+        steady_reset()
         st_all = all_gather_stage(stage_times(lambda tm: steady_step(0, tm, host=False), 1))
         steady_reset()
         t_gp = st_all[0].get("gp_fit", 0.0) + st_all[0].get("mustar", 0.0)

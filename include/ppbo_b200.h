@@ -67,6 +67,8 @@ int ppbo_kernel_se_grad(const double* X1, int n1, const double* X2, int n2, int 
  *   arrow[Q*m]  = a_qj = -Delta phi~(Delta) / (2 m sigma^2)      (GPModel.create_Lambda, src/gp_model.py:249-274) */
 int ppbo_lik_terms(const double* f, int Q, int m, double sigma, double* lik_sum, double* beta,
                    double* arrow, void* stream);
+/* set_sums[Q]: the per-comparison-set values sum_j Phi(Delta_qj / sqrt 2) (GPModel.sum_Phi_vec order 0, src/gp_model.py:206-218) */
+int ppbo_lik_set_sums(const double* f, int Q, int m, double sigma, double* set_sums, void* stream);
 /* dense Lambda[N x N] from the arrow coefficients (public attr GPModel.Lambda_MAP) */
 int ppbo_lambda_dense(const double* arrow, int Q, int m, double* out, long long ld, void* stream);
 /* G[Qm x Qm] = B^T Sigma B, the prior covariance of the latent differences f_j - f_winner */
@@ -96,6 +98,8 @@ long long ppbo_laplace_workspace_bytes(int Q, int m);
  *   PPBO_FIT_FACTOR_AT_MODE finish with the factor of I + a+^1/2 G a+^1/2 AT the mode (what ppbo_predict with covariance and
  *                           ppbo_neg_corr_build need); without it Lfac keeps the last factor used and ppbo_laplace_refactor
  *                           builds the mode factor on demand (the posterior mean needs alpha only)
+ * binv_cache (may be NULL; ppbo_blockinv_bytes(cap) bytes) with binv_state_h[2] (host, in/out; {0, 0} initially): persistent home
+ *          of the factor's 1024-block inverses -- a factor that only grows at its end keeps its leading blocks between fits.
  * alpha_init (may be NULL): Sigma^-1 f_init when the caller knows it (a warm start from the previous (f, alpha) with zeros
  *          appended to alpha and Sigma_new,old alpha_old appended to f is consistent by construction).
  * Outputs: f_map[N], alpha[N] = Sigma^-1 f_map, arrow[Qm] (signed coefficients at the mode), sa_fac[Qm] (may be NULL) = the
@@ -108,8 +112,8 @@ long long ppbo_laplace_workspace_bytes(int Q, int m);
 #define PPBO_FIT_FACTOR_AT_MODE 4
 int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
                      const double* alpha_init, int max_iter, double tol, int flags, double* G, long long ldg, double* Lfac,
-                     int cap, double* sa_fac, int warm_rows, double* f_map, double* alpha, double* arrow, void* workspace,
-                     long long workspace_bytes, double* stats_h, void* stream);
+                     int cap, double* sa_fac, int warm_rows, double* binv_cache, int* binv_state_h, double* f_map, double* alpha,
+                     double* arrow, void* workspace, long long workspace_bytes, double* stats_h, void* stream);
 /* factor of I + a+^1/2 G a+^1/2 for the coefficients `arrow` (a fit that skipped PPBO_FIT_FACTOR_AT_MODE); sa_fac[M] receives
  * sqrt(max(arrow, 0)).  Returns 0 or the index of the first non-positive pivot. */
 int ppbo_laplace_refactor(const double* G, long long ldg, int M, const double* arrow, double* Lfac, int cap, double* sa_fac,
@@ -222,6 +226,12 @@ int ppbo_rff_jacobian(const double* W, const double* b, int F, int D, const doub
  * src/random_fourier_sampler.py:166-167). */
 int ppbo_rff_value_grad(const double* W, const double* b, int F, int D, const double* omega, const double* x, double sigma_f,
                         double* out, void* stream);
+/* Maximisers of S sampled functions g_s(x) = phi(x)' Omega[s] over [0,1]^D, R restarts each from X0[S][R][D]: one CTA per
+ * (sample, restart) runs projected gradient ascent (Barzilai-Borwein steps, Armijo backtracking) until the projected gradient is
+ * below gtol or max_iter; xbest[S][D], fbest[S] = the best restart per sample.  work: S R (D + 1) doubles.  Batched form of
+ * Hsampler.return_xstar / sample_xstar (src/random_fourier_sampler.py:143-178,215-220: sequential scipy L-BFGS-B restarts). */
+int ppbo_rff_maximize(const double* W, const double* b, int F, int D, double sigma_f, const double* Omega, long long ldo, int S,
+                      const double* X0, int R, int max_iter, double gtol, double* xbest, double* fbest, double* work, void* stream);
 /* weight-space objective pieces (Hsampler.S / S_grad / S_hessian, src/random_fourier_sampler.py:106-122):
  * f = Phi_X' omega (Phi_X feature-major [F x N]); S = -1/2|omega|^2 - lik_sum/m (host double); grad[F];
  * hess_diag[F] (the reference Hessian is diagonal).  Any output may be NULL. */

@@ -34,13 +34,14 @@ _SIGNATURES = {
     "ppbo_gram_regularized": (_I, [_I, _P, _I, _I, _PD, _D, _D, _P, _L, _P]),
     "ppbo_kernel_se_grad": (_I, [_P, _I, _P, _I, _I, _PD, _D, _P, _L, _L, _P]),
     "ppbo_lik_terms": (_I, [_P, _I, _I, _D, _P, _P, _P, _P]),
+    "ppbo_lik_set_sums": (_I, [_P, _I, _I, _D, _P, _P]),
     "ppbo_lambda_dense": (_I, [_P, _I, _I, _P, _L, _P]),
     "ppbo_diffspace_gram": (_I, [_P, _L, _I, _I, _P, _L, _P]),
     "ppbo_factor_doubles": (_L, [_I]),
     "ppbo_laplace_workspace_bytes": (_L, [_I, _I]),
     "ppbo_gram_append": (_I, [_I, _P, _I, _I, _I, _PD, _D, _D, _P, _L, _P]),
     "ppbo_diffspace_gram_append": (_I, [_P, _L, _I, _I, _I, _P, _L, _P]),
-    "ppbo_laplace_fit": (_I, [_P, _L, _I, _I, _D, _P, _P, _I, _D, _I, _P, _L, _P, _I, _P, _I, _P, _P, _P, _P, _L, _PD, _P]),
+    "ppbo_laplace_fit": (_I, [_P, _L, _I, _I, _D, _P, _P, _I, _D, _I, _P, _L, _P, _I, _P, _I, _P, _PI, _P, _P, _P, _P, _L, _PD, _P]),
     "ppbo_laplace_refactor": (_I, [_P, _L, _I, _P, _P, _I, _P, _P]),
     "ppbo_factor_extend": (_I, [_P, _L, _I, _I, _P, _P, _I, _D, _P, _I, _P]),
     "ppbo_gemm_nt": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _D, _D, _P]),
@@ -72,6 +73,7 @@ _SIGNATURES = {
     "ppbo_rff_features": (_I, [_P, _P, _I, _I, _P, _I, _D, _P, _L, _I, _P]),
     "ppbo_rff_jacobian": (_I, [_P, _P, _I, _I, _P, _D, _P, _P]),
     "ppbo_rff_value_grad": (_I, [_P, _P, _I, _I, _P, _P, _D, _P, _P]),
+    "ppbo_rff_maximize": (_I, [_P, _P, _I, _I, _D, _P, _L, _I, _P, _I, _I, _D, _P, _P, _P, _P]),
     "ppbo_rff_workspace_bytes": (_L, [_I, _I, _I]),
     "ppbo_rff_objective": (_I, [_P, _L, _I, _I, _I, _D, _P, _PD, _P, _P, _P, _L, _P]),
     "ppbo_rff_fit": (_I, [_P, _L, _I, _I, _I, _D, _P, _I, _D, _P, _P, _P, _L, _PD, _P]),

@@ -166,6 +166,121 @@ __global__ void __launch_bounds__(256) rff_value_grad_kernel(const double* __res
         if (threadIdx.x == 0) out[1 + d] = amp * t;
     }
 }
+// ---- batched maximiser of sampled functions --------------------------------------------------------------------------------
+// Hsampler.return_xstar (src/random_fourier_sampler.py:143-178) maximises ONE sampled function g(x) = phi(x)' omega over [0,1]^D with
+// 5-30 sequential scipy L-BFGS-B restarts, every objective / gradient evaluation a Python call.  Here every (sample s, restart r)
+// pair is one CTA: projected gradient ascent with Barzilai-Borwein step lengths and Armijo backtracking on the box, the objective and
+// its gradient evaluated together (each thread owns F / 128 features; one block reduction of D + 1 numbers per evaluation).
+// Stationarity is measured by the projected gradient |clip(x + grad) - x|_inf.  A second kernel keeps the best restart per sample.
+constexpr int RM_THREADS = 128, RM_MAX_D = 32;
+__global__ void __launch_bounds__(RM_THREADS) rff_maximize_kernel(const double* __restrict__ W, const double* __restrict__ b, int F, int D,
+                                                                  double amp, const double* __restrict__ Omega, long long ldo,
+                                                                  const double* __restrict__ X0, int R, int max_iter, double gtol,
+                                                                  double* __restrict__ xout, double* __restrict__ fout,
+                                                                  int* __restrict__ iters_out) {
+    __shared__ double x[RM_MAX_D], g[RM_MAX_D], xt[RM_MAX_D], gt[RM_MAX_D];
+    __shared__ double red[RM_THREADS / 32][RM_MAX_D + 1];
+    __shared__ double fval_s;
+    const int s = blockIdx.x / R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* om = Omega + (long long)s * ldo;
+    const double* x0 = X0 + (long long)blockIdx.x * D;
+    // value and gradient of g at xv (shared) -> fval_s, gv (shared)
+    auto eval = [&](const double* xv, double* gv) {
+        double val = 0.0, gl[RM_MAX_D];
+#pragma unroll
+        for (int d = 0; d < RM_MAX_D; ++d) gl[d] = 0.0;
+        for (int f = tid; f < F; f += RM_THREADS) {
+            const double* w = W + (long long)f * D;
+            double a = b[f];
+            for (int d = 0; d < D; ++d) a = fma(w[d], xv[d], a);
+            double sn, cs;
+            sincos(a, &sn, &cs);
+            const double o = om[f];
+            val = fma(o, cs, val);
+            const double c = -o * sn;
+#pragma unroll
+            for (int d = 0; d < RM_MAX_D; ++d)
+                if (d < D) gl[d] = fma(c, w[d], gl[d]);
+        }
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if (lane == 0) red[warp][RM_MAX_D] = val;
+#pragma unroll
+        for (int d = 0; d < RM_MAX_D; ++d) {
+            if (d < D) {
+                double v = gl[d];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[warp][d] = v;
+            }
+        }
+        __syncthreads();
+        if (tid <= D) {
+            const int k = (tid == D) ? RM_MAX_D : tid;
+            const double v = amp * ((red[0][k] + red[1][k]) + (red[2][k] + red[3][k]));
+            if (tid == D) fval_s = v;
+            else gv[tid] = v;
+        }
+        __syncthreads();
+    };
+    if (tid < D) x[tid] = fmin(fmax(x0[tid], 0.0), 1.0);
+    __syncthreads();
+    eval(x, g);
+    double f = fval_s;
+    double gmax = 0.0;
+    for (int d = 0; d < D; ++d) gmax = fmax(gmax, fabs(g[d]));
+    double t = 0.05 / fmax(gmax, 1e-12);               // first step: at most 5 % of the box
+    int it = 0;
+    for (; it < max_iter; ++it) {
+        double pg = 0.0;                                // projected-gradient stationarity measure
+        for (int d = 0; d < D; ++d) pg = fmax(pg, fabs(fmin(fmax(x[d] + g[d], 0.0), 1.0) - x[d]));
+        if (pg <= gtol) break;
+        double ft = f, slope = 0.0;
+        int tries = 0;
+        for (;; ++tries) {
+            __syncthreads();
+            if (tid < D) xt[tid] = fmin(fmax(x[tid] + t * g[tid], 0.0), 1.0);
+            __syncthreads();
+            slope = 0.0;
+            for (int d = 0; d < D; ++d) slope = fma(g[d], xt[d] - x[d], slope);
+            eval(xt, gt);
+            ft = fval_s;
+            if (ft >= f + 1e-4 * slope || tries >= 30) break;
+            t *= 0.5;
+        }
+        if (!(ft >= f)) break;                          // no ascent possible at this resolution
+        double ss = 0.0, sy = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double sd = xt[d] - x[d], yd = gt[d] - g[d];
+            ss = fma(sd, sd, ss);
+            sy = fma(sd, yd, sy);
+        }
+        __syncthreads();
+        if (tid < D) { x[tid] = xt[tid]; g[tid] = gt[tid]; }
+        __syncthreads();
+        f = ft;
+        t = (sy < 0.0) ? fmin(fmax(-ss / sy, 1e-8), 1e4) : 2.0 * t;       // Barzilai-Borwein (concave along s), else expand
+        if (ss == 0.0) break;
+    }
+    if (tid < D) xout[(long long)blockIdx.x * D + tid] = x[tid];
+    if (tid == 0) {
+        fout[blockIdx.x] = f;
+        if (iters_out) iters_out[blockIdx.x] = it;
+    }
+}
+// best restart per sample (first maximum)
+__global__ void rff_maximize_select_kernel(const double* __restrict__ xall, const double* __restrict__ fall, int S, int R, int D,
+                                           double* __restrict__ xbest, double* __restrict__ fbest) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int br = 0;
+    double bf = fall[(long long)s * R];
+    for (int r = 1; r < R; ++r) {
+        const double v = fall[(long long)s * R + r];
+        if (v > bf) { bf = v; br = r; }
+    }
+    fbest[s] = bf;
+    for (int d = 0; d < D; ++d) xbest[(long long)s * D + d] = xall[((long long)s * R + br) * D + d];
+}
+
 // y[i] = sum_f Phi[f][i] omega[f]   (feature-major Phi: coalesced over i).  HBM-bound (8 F N bytes): the feature range is cut
 // into FV_SLICES slices so that ~8 x N/128 CTAs stream concurrently; slice partials are combined in a fixed order.
 constexpr int FV_SLICES = 8, FV_COLS = 128;
@@ -541,6 +656,22 @@ extern "C" int ppbo_rff_value_grad(const double* W, const double* b, int F, int 
     PPBO_REQUIRE(F >= 1 && D >= 1 && D <= PPBO_MAX_D, "shape");
     const double amp = sqrt(2.0 * sigma_f * sigma_f / F);
     PPBO_CL rff_value_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(W, b, F, D, omega, x, amp, out);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_rff_maximize(const double* W, const double* b, int F, int D, double sigma_f, const double* Omega, long long ldo,
+                                 int S, const double* X0, int R, int max_iter, double gtol, double* xbest, double* fbest,
+                                 double* work, void* stream) {
+    PPBO_REQUIRE(F >= 1 && D >= 1 && D <= RM_MAX_D, "D must be in [1, 32]");
+    PPBO_REQUIRE(S >= 0 && R >= 1 && max_iter >= 0 && gtol >= 0 && work != nullptr, "arguments");
+    if (S == 0) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double amp = sqrt(2.0 * sigma_f * sigma_f / F);
+    double* xall = work;                                  // [S][R][D]
+    double* fall = work + (long long)S * R * D;          // [S][R]
+    PPBO_CL rff_maximize_kernel<<<S * R, RM_THREADS, 0, st>>>(W, b, F, D, amp, Omega, ldo, X0, R, max_iter, gtol, xall, fall, nullptr);
+    PPBO_CL rff_maximize_select_kernel<<<ceil_div(S, 128), 128, 0, st>>>(xall, fall, S, R, D, xbest, fbest);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }

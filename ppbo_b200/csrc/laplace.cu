@@ -7,6 +7,7 @@
 // W = B diag(a) B^T with a_qj = -Delta phi~(Delta) / (2 m sigma^2).  A damped Newton step with a+ = max(a,0) is
 //     alpha_new = b - B a+^1/2 (I + a+^1/2 G a+^1/2)^-1 a+^1/2 B^T Sigma b ,   b = B a+ B^T f + beta ,  f_new = Sigma alpha_new
 // where G = B^T Sigma B (Qm x Qm) is fixed during the fit.  One Cholesky of size Qm per step, no Sigma^-1.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -558,6 +559,15 @@ extern "C" int ppbo_lik_terms(const double* f, int Q, int m, double sigma, doubl
     return PPBO_OK;
 }
 
+/* set_sums[q] = sum_j Phi(Delta_qj / sqrt 2): GPModel.sum_Phi_vec(0, ...) for all comparison sets in one launch (src/gp_model.py:206-218) */
+extern "C" int ppbo_lik_set_sums(const double* f, int Q, int m, double sigma, double* set_sums, void* stream) {
+    PPBO_REQUIRE(Q >= 0 && m >= 1 && sigma > 0 && set_sums != nullptr, "shape / sigma");
+    if (Q == 0) return PPBO_OK;
+    PPBO_CL lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, (cudaStream_t)stream>>>(f, Q, m, sigma, set_sums, nullptr, nullptr, nullptr, nullptr);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+
 extern "C" int ppbo_lambda_dense(const double* arrow, int Q, int m, double* out, long long ld, void* stream) {
     const long long N = (long long)Q * (m + 1);
     if (N == 0) return PPBO_OK;
@@ -653,8 +663,9 @@ extern "C" int ppbo_factor_extend(const double* G, long long ldg, int M_old, int
 
 extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m, double sigma, const double* f_init,
                                 const double* alpha_init, int max_iter, double tol, int flags, double* G, long long ldg,
-                                double* Lfac, int cap, double* sa_fac, int warm_rows, double* f_map, double* alpha, double* arrow,
-                                void* workspace, long long workspace_bytes, double* stats_h, void* stream) {
+                                double* Lfac, int cap, double* sa_fac, int warm_rows, double* binv_cache, int* binv_state_h,
+                                double* f_map, double* alpha, double* arrow, void* workspace, long long workspace_bytes,
+                                double* stats_h, void* stream) {
     PPBO_REQUIRE(Q >= 1 && m >= 1 && sigma > 0, "shape / sigma");
     PPBO_REQUIRE(workspace_bytes >= ppbo_laplace_workspace_bytes(Q, m), "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -668,6 +679,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     PPBO_REQUIRE(alpha_init == nullptr || f_init != nullptr, "alpha_init without f_init");
     FitWorkspace ws;
     ws.carve((double*)workspace, Q, m);
+    // block inverses of the factor: in the caller's persistent buffer when given (a factor that only grows at its end keeps its
+    // leading 1024-blocks: binv_state_h = {leading rows unchanged since the build, ceil(rows / 1024) of that build})
+    if (binv_cache) ws.binv = binv_cache;
     const long long ldl = cap;
     double* Mdinv = Lfac + (long long)cap * cap;  // factor object = [cap x cap lower factor | inverted diagonal blocks]
     int rc;
@@ -713,7 +727,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         bordered = nb > 0;
         PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.sa, sa_fac, sizeof(double) * M_old, cudaMemcpyDeviceToDevice, st));
         PPBO_CL square_kernel<<<ceil_div(M_old, 256), 256, 0, st>>>(ws.sa, M_old, ws.ap);
-        if ((rc = blockinv_build(Lfac, ldl, M_old, Mdinv, ws.binv, st))) return rc;
+        int first_block = 0;
+        if (binv_cache && binv_state_h && binv_state_h[1] == ceil_div(M_old, 1024)) first_block = std::min(binv_state_h[0], M_old) / 1024;
+        if ((rc = blockinv_build(Lfac, ldl, M_old, Mdinv, ws.binv, st, first_block))) return rc;
         binv_valid = true;
         if (bordered) {
             const long long Mp = (M + 1) / 2 * 2;
@@ -912,6 +928,17 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
         factor_current = info == 0;
         info = 0;
+    }
+    if (binv_state_h) {
+        if (bordered && !factor_at_mode) {      // cache built for the old factor; the finalisation rewrote rows >= the last 128-boundary
+            binv_state_h[0] = (M_old / CHOL_NB) * CHOL_NB;
+            binv_state_h[1] = ceil_div(M_old, 1024);
+        } else if (binv_valid && !factor_at_mode && !identity_factor) {
+            binv_state_h[0] = M;
+            binv_state_h[1] = ceil_div(M, 1024);
+        } else {
+            binv_state_h[0] = binv_state_h[1] = 0;
+        }
     }
     bool have_factor = factor_current && !identity_factor;
     if (sa_fac && have_factor && !factor_at_mode)

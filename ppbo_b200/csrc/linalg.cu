@@ -1399,17 +1399,24 @@ __global__ void __launch_bounds__(256) blockinv_init_kernel(const double* __rest
     BinvT[o] = bt;
 }
 
-int blockinv_build(const double* L, long long ldl, int n, const double* dinv, double* W, cudaStream_t st) {
+// first_block > 0: the 1024-blocks below it are still valid from an earlier build with the same ceil(n / 1024) (a factor that only
+// grew at its end, laplace.cu bordered warm start) and are skipped
+int blockinv_build(const double* L, long long ldl, int n, const double* dinv, double* W, cudaStream_t st, int first_block) {
     const int nbI = ceil_div(n, BI);
     const long long BB = (long long)BI * BI;
-    double* Binv = W;
-    double* BinvT = Binv + nbI * BB;
-    double* Lpad = BinvT + nbI * BB;
-    double* Tt = Lpad + nbI * BB;
-    PPBO_CL blockinv_init_kernel<<<dim3(BI * BI / 256, nbI), 256, 0, st>>>(L, ldl, n, dinv, Binv, BinvT, Lpad);
+    if (first_block >= nbI) return PPBO_OK;
+    const int nbuild = nbI - first_block;
+    double* Binv = W + first_block * BB;
+    double* BinvT = W + nbI * BB + first_block * BB;
+    double* Lpad = W + 2 * nbI * BB + first_block * BB;
+    double* Tt = W + 3 * nbI * BB + first_block * (BB / 4);
+    L += (long long)first_block * BI * (ldl + 1);
+    dinv += (long long)first_block * (BI / CHOL_NB) * CHOL_NB * CHOL_NB;
+    n -= first_block * BI;
+    PPBO_CL blockinv_init_kernel<<<dim3(BI * BI / 256, nbuild), 256, 0, st>>>(L, ldl, n, dinv, Binv, BinvT, Lpad);
     PPBO_LAUNCH_CHECK();
     for (int s = CHOL_NB; s < BI; s *= 2) {
-        const int ppb = BI / (2 * s), nb = nbI * ppb;
+        const int ppb = BI / (2 * s), nb = nbuild * ppb;
         const long long pair = 2LL * s * (BI + 1), ss = (long long)s * s;
         int rc;
         {   // Tt = (C A^-1)^T = A^-T . C^T

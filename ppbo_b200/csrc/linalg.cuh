@@ -16,7 +16,7 @@ int trsm_right_lower_t(const double* L, long long ldl, int n, const double* dinv
                        cudaStream_t st);
 // block-inverse solves for factors that serve many right-hand sides (see linalg.cu)
 long long blockinv_doubles(int n);
-int blockinv_build(const double* L, long long ldl, int n, const double* dinv, double* W, cudaStream_t st);
+int blockinv_build(const double* L, long long ldl, int n, const double* dinv, double* W, cudaStream_t st, int first_block = 0);
 int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip = nullptr);
 // the two halves of potrs_vec_blockinv (y = L^-1 t lands in blockinv_y(W, n); t = L^-T y) and the few-row right solve
 double* blockinv_y(double* W, int n);

@@ -710,12 +710,12 @@ extern "C" int ppbo_ozaki_rowmax(const signed char* Aplanes, const double* ascal
     p.KBLK = ceil_div(K, oz::KB);
     p.NG = oz::column_groups(p.NT, p.KBLK, slices);
     p.ntg = ceil_div(p.NT, p.NG);
-    // grids per block: as many as keep the block's B planes within ~28 MB of L2 (tuning key 12 overrides; 1 = the earlier order).
+    // grids per block: as many as keep the block's B planes within ~48 MB of L2 (tuning key 12 overrides; 1 = the earlier order).
     // Measured on the bench shape under sustained load (scripts/ozaki_order_sweep.py, round-robin): 1 -> 9.79 ms, 2 -> 9.77, 4 -> 9.68,
     // 7 -> 9.83, 20 -> 10.28: the kernel is bound by the tensor pipe under the power cap, the order only moves DRAM traffic.
     {
         const long long grid_bytes = (long long)p.NT * p.KBLK * slices * oz::BN_DEFAULT * oz::KB;
-        int gbk = g_tuning[12] > 0 ? g_tuning[12] : (int)std::max<long long>(1, (28LL << 20) / std::max<long long>(grid_bytes, 1));
+        int gbk = g_tuning[12] > 0 ? g_tuning[12] : (int)std::max<long long>(1, (48LL << 20) / std::max<long long>(grid_bytes, 1));
         p.GB = std::min(std::max(gbk, 1), batch);
     }
     PPBO_REQUIRE(workspace_bytes >= ppbo_ozaki_rowmax_workspace_bytes(S, P, batch), "workspace too small");

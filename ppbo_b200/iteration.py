@@ -170,8 +170,9 @@ class GPState(GPFit):
         self.kernel, self.theta, self.m, self.Q, self.Q_cap = kernel, [float(t) for t in theta], m, 0, Q_cap
         self.lengthscales = theta[1] if lengthscales is None else lengthscales
         self.shrinkage, self.max_iter, self.tol = shrinkage, max_iter, tol
-        Nc, Mc = Q_cap * (m + 1), Q_cap * m
-        self.X_cap = torch.empty((Nc, D), dtype=F64, device=dev)
+        Nr, Mc = Q_cap * (m + 1), (Q_cap * m + 15) // 16 * 16     # leading dimensions: multiples of 16 doubles (the specialised
+        Nc = (Nr + 15) // 16 * 16                                   # Cholesky / GEMM kernels want 16-byte aligned rows)
+        self.X_cap = torch.empty((Nr, D), dtype=F64, device=dev)
         self.Sigma_cap = torch.empty((Nc, Nc), dtype=F64, device=dev)
         self.f_buf, self.alpha_buf, self.f_init_buf, self.alpha_init_buf = (torch.empty(Nc, dtype=F64, device=dev) for _ in range(4))
         self.arrow_buf = torch.empty(Mc, dtype=F64, device=dev)
@@ -180,6 +181,9 @@ class GPState(GPFit):
         lap.G = torch.empty((Mc, Mc), dtype=F64, device=dev)
         lap._Lfac = torch.empty(lib.ppbo_factor_doubles(Mc), dtype=F64, device=dev)
         lap.sa_fac = torch.empty(Mc, dtype=F64, device=dev)
+        lap.binv_cache = torch.empty(lib.ppbo_blockinv_bytes(Mc) // 8 + 2, dtype=F64, device=dev)
+        import ctypes
+        lap.binv_state = (ctypes.c_int * 2)(0, 0)
         lap.m, lap.Q, lap.sigma, lap.info, lap.factor_state = m, 0, float(theta[0]), 0, 0
         self.lap = lap
         self.X = self.Sigma = None

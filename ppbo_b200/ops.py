@@ -102,6 +102,12 @@ def lik_terms(f, Q, m, sigma, want_sum=True, want_beta=True, want_arrow=True):
     return s, beta, arrow
 
 
+def lik_set_sums(f, Q, m, sigma):
+    out = torch.empty(Q, dtype=F64, device=f.device)
+    check(_lib.load().ppbo_lik_set_sums(_p(f), Q, m, float(sigma), _p(out), _stream()), "ppbo_lik_set_sums")
+    return out
+
+
 def lambda_dense(arrow, Q, m):
     N = Q * (m + 1)
     out = torch.empty((N, N), dtype=F64, device=arrow.device)
@@ -123,7 +129,7 @@ class LaplaceFit:
     a model can grow in place (ModelState in iteration.py).  The factor AT the mode is only needed by prediction with covariance:
     it is built on first read of `Lfac` when the fit skipped it (`factor_state` < 2)."""
     __slots__ = ("Q", "m", "sigma", "f_map", "alpha", "arrow", "G", "ldg", "cap", "_Lfac", "sa_fac", "factor_state", "stats",
-                 "n_neg", "_neg_idx", "_neg_corr", "info")
+                 "n_neg", "_neg_idx", "_neg_corr", "info", "binv_cache", "binv_state")
 
     @property
     def M(self):
@@ -189,6 +195,7 @@ def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10, factor
     if into is None:
         fit = LaplaceFit()
         fit.cap = fit.ldg = M
+        fit.binv_cache, fit.binv_state = None, None
         fit.G = torch.empty((M, M), dtype=F64, device=dev)
         fit._Lfac = torch.empty(lib.ppbo_factor_doubles(M), dtype=F64, device=dev)
         fit.sa_fac = torch.empty(M, dtype=F64, device=dev)
@@ -205,8 +212,10 @@ def laplace_fit(Sigma, Q, m, sigma, f_init=None, max_iter=100, tol=1e-10, factor
     wbytes = lib.ppbo_laplace_workspace_bytes(Q, m)
     ws = _scratch("laplace", wbytes, dev)
     stats = (ctypes.c_double * 12)()
+    binv_cache = getattr(fit, "binv_cache", None)
     rc = check(lib.ppbo_laplace_fit(_p(Sigma), Sigma.stride(0), Q, m, float(sigma), _p(f_init), _p(alpha_init), int(max_iter),
                                     float(tol), flags, _p(fit.G), fit.ldg, _p(fit._Lfac), fit.cap, _p(fit.sa_fac), int(warm_rows),
+                                    _p(binv_cache), fit.binv_state if binv_cache is not None else None,
                                     _p(fit.f_map), _p(fit.alpha), _p(fit.arrow), _p(ws), wbytes, stats, _stream()),
                "ppbo_laplace_fit")
     fit.info = rc
@@ -444,6 +453,19 @@ def rff_jacobian(W, b, x, sigma_f):
     J = torch.empty((F, D), dtype=F64, device=W.device)
     check(_lib.load().ppbo_rff_jacobian(_p(W), _p(b), F, D, _p(x), float(sigma_f), _p(J), _stream()), "ppbo_rff_jacobian")
     return J
+
+
+def rff_maximize(W, b, sigma_f, Omega, X0, max_iter=500, gtol=1e-9):
+    """Omega [S,F], starts X0 [S,R,D] -> (xbest [S,D], fbest [S]): maximisers of the sampled functions phi(x)' Omega[s] on [0,1]^D"""
+    Fdim, D = W.shape
+    S, R, _ = X0.shape
+    dev = W.device
+    xbest = torch.empty((S, D), dtype=F64, device=dev)
+    fbest = torch.empty(S, dtype=F64, device=dev)
+    work = _scratch("rff_maximize", S * R * (D + 1) * 8, dev)
+    check(_lib.load().ppbo_rff_maximize(_p(W), _p(b), Fdim, D, float(sigma_f), _p(Omega), Omega.stride(0), S, _p(X0.contiguous()), R,
+                                        int(max_iter), float(gtol), _p(xbest), _p(fbest), _p(work), _stream()), "ppbo_rff_maximize")
+    return xbest, fbest
 
 
 def _rff_ws(F, Q, m, dev):

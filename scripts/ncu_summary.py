@@ -52,5 +52,33 @@ def rep(path, keys=KEYS):
                 print("   %-70s %s %s" % (k, r[col[k]], units[col[k]]))
 
 
+def traffic(path, key, out_json="profiles/traffic.json", pattern=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the (first matching) captured launch -> profiles/traffic.json[key]"""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        if pattern and pattern not in r[col["Kernel Name"]]:
+            continue
+        def val(name):
+            v = float(r[col[name]].replace(",", ""))
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[col[name]], 1)
+        rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+        rec = json.load(open(out_json)) if os.path.exists(out_json) else {}
+        rec[key] = {"dram_bytes": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr, "kernel": r[col["Kernel Name"]][:120],
+                    "duration_ns_under_ncu": r[col["gpu__time_duration.sum"]] if "gpu__time_duration.sum" in col else None,
+                    "source": "ncu --set full of " + os.path.basename(path)}
+        json.dump(rec, open(out_json, "w"), indent=1)
+        print(key, rec[key])
+        return
+    print("no matching launch in", path)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:])
+    else:
+        {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2])

@@ -192,10 +192,7 @@ class GPModel:
         Q, m = self._Q(), self.m
         fd = ops.to_dev(np.asarray(f, dtype=np.float64).ravel())
         if order_of_derivative == 0:
-            # per-set values: evaluate the total on the N rows of each set separately is wasteful; one launch gives beta/arrow,
-            # the per-set sums follow from them
-            F = np.asarray(f, dtype=float).ravel().reshape(Q, m + 1)
-            out = np.array([float(ops.lik_terms(ops.to_dev(F[q]), 1, m, sigma, True, False, False)[0]) for q in range(Q)])
+            out = ops.lik_set_sums(fd, Q, m, sigma).cpu().numpy()          # all comparison sets in one launch
         elif order_of_derivative == 1:
             _, beta, _ = ops.lik_terms(fd, Q, m, sigma, False, True, False)
             out = beta.cpu().numpy().reshape(Q, m + 1)[:, 0] * (sigma * m)

@@ -205,6 +205,30 @@ class Hsampler:
         sums, _, _ = _it.rff_acquisition(rff, PhiT, n_samples, ops.to_dev(np.array([float(mustar)])), shard=shard, seed=seed)
         return sums.cpu().numpy()
 
+    # ------------------------------------------------------------------ batched maximiser (north_star piece 3)
+    def return_xstar_batch(self, omegas, n_restarts=16, max_iter=500, gtol=1e-9):
+        """maximisers of many sampled functions at once: omegas [S, F] -> (xstars [S, D], values [S]).  Starts per sample: like
+        return_xstar, random GP local maximisers + 0.01 U(0,1) jitter for the first quarter of the restarts, uniform points for the
+        rest (drawn from the global RNG: n_restarts randint + uniform draws per sample, sample by sample).  Every (sample, restart)
+        is one CTA of ppbo_rff_maximize."""
+        omegas = np.atleast_2d(np.asarray(omegas, dtype=np.float64))
+        S, D = omegas.shape[0], self.D
+        n_local = max(1, n_restarts // 4)
+        X0 = np.empty((S, n_restarts, D))
+        loc = np.atleast_2d(self.GP_xstars_local)
+        for s in range(S):
+            for r in range(n_restarts):
+                if r < n_local:
+                    X0[s, r] = np.clip(loc[np.random.randint(loc.shape[0])] + 0.01 * np.random.uniform(0, 1, size=D), 0, 1)
+                else:
+                    X0[s, r] = np.random.uniform(0, 1, size=D)
+        xb, fb = ops.rff_maximize(self._d("W"), self._d("b"), self.theta[2], ops.to_dev(omegas), ops.to_dev(X0), max_iter=max_iter, gtol=gtol)
+        return xb.cpu().numpy(), fb.cpu().numpy()
+
+    def sample_xstars(self, n, n_restarts=16):
+        """n posterior draws of the maximiser location (batched sample_xstar): omega ~ N(omega_MAP, covariance), x* = argmax phi(x)' omega"""
+        return self.return_xstar_batch(self.sample_omegas(n), n_restarts=n_restarts)[0]
+
     # ------------------------------------------------------------------ maximiser of one sampled function (:143-204)
     def _value_grad(self, omega_dev, x):
         out = ops.rff_value_grad(self._d("W"), self._d("b"), omega_dev, ops.to_dev(np.asarray(x, dtype=np.float64)), self.theta[2])

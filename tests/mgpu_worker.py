@@ -21,7 +21,8 @@ def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
     shard = iteration.Shard()
     prob = synthetic.make_problem("levy10d", Q=13, S=4096, P=128, F=256)          # large enough for the INT8 sampling engine
     m, theta, kernel, S = prob["m"], prob["theta"], prob["kernel"], prob["S"]
