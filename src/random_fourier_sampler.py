@@ -207,10 +207,11 @@ class Hsampler:
 
     # ------------------------------------------------------------------ batched maximiser (north_star piece 3)
     def return_xstar_batch(self, omegas, n_restarts=16, max_iter=500, gtol=1e-9):
-        """maximisers of many sampled functions at once: omegas [S, F] -> (xstars [S, D], values [S]).  Starts per sample: like
-        return_xstar, random GP local maximisers + 0.01 U(0,1) jitter for the first quarter of the restarts, uniform points for the
-        rest (drawn from the global RNG: n_restarts randint + uniform draws per sample, sample by sample).  Every (sample, restart)
-        is one CTA of ppbo_rff_maximize."""
+        """maximisers of many sampled functions at once: omegas [S, F] -> (xstars [S, D], values [S]).  Starts per sample (drawn from
+        the global RNG, sample by sample): a quarter like return_xstar -- a random GP local maximiser + 0.01 U(0,1) jitter; a quarter
+        on the diagonal, (c, ..., c) + jitter with c a random coordinate of a local maximiser (what the reference's return_xstar
+        actually starts from: its mu_star leaves xstars_local one-dimensional, src/gp_model.py:425-435, so indexing it yields a
+        scalar); the rest uniform in the box.  Every (sample, restart) is one CTA of ppbo_rff_maximize."""
         omegas = np.atleast_2d(np.asarray(omegas, dtype=np.float64))
         S, D = omegas.shape[0], self.D
         n_local = max(1, n_restarts // 4)
@@ -220,6 +221,8 @@ class Hsampler:
             for r in range(n_restarts):
                 if r < n_local:
                     X0[s, r] = np.clip(loc[np.random.randint(loc.shape[0])] + 0.01 * np.random.uniform(0, 1, size=D), 0, 1)
+                elif r < 2 * n_local:
+                    X0[s, r] = np.clip(loc.ravel()[np.random.randint(loc.size)] + 0.01 * np.random.uniform(0, 1, size=D), 0, 1)
                 else:
                     X0[s, r] = np.random.uniform(0, 1, size=D)
         xb, fb = ops.rff_maximize(self._d("W"), self._d("b"), self.theta[2], ops.to_dev(omegas), ops.to_dev(X0), max_iter=max_iter, gtol=gtol)

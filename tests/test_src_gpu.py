@@ -285,7 +285,7 @@ def test_batched_rff_maximiser_vs_reference(golden):
     assert np.array_equal(h.W, g["rff_W"])
     om = g["rff_Omega"][:g["rff_xstar"].shape[0]]
     np.random.seed(123)
-    xs, vals = h.return_xstar_batch(om, n_restarts=32, max_iter=2000, gtol=1e-10)
+    xs, vals = h.return_xstar_batch(om, n_restarts=128, max_iter=2000, gtol=1e-10)
     assert xs.shape == g["rff_xstar"].shape and np.all((xs >= 0) & (xs <= 1))
     host_vals = np.array([float(h.phi(x) @ w) for x, w in zip(xs, om)])
     assert np.abs(host_vals - vals).max() <= 1e-12 * max(np.abs(vals).max(), 1e-300)
