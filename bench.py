@@ -475,11 +475,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    shares = [None]
+    shares, smu = [None], [None]
 
     def step(resident=None, timers=None):
         d = resident if resident is not None else inputs.to_device(dev)
-        sums, gp, rff = iteration.run_iteration(d, kernel, theta, Q0, m, S, shard=shard, seed=SEED, timers=timers, shares=shares[0])
+        sums, gp, rff = iteration.run_iteration(d, kernel, theta, Q0, m, S, shard=shard, seed=SEED, timers=timers, shares=shares[0],
+                                                shard_mustar=smu[0])
         if resident is None:
             sums_host.copy_(sums, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -551,7 +552,7 @@ def main():
         else:
             d = {"block": blocks_dev[i], "W": resident["W"], "b": resident["b"], "grids": resident["grids"]}
         sums, gp, rff = iteration.run_iteration(d, kernel, theta, Q0 + i + 1, m, S, shard=shard, seed=SEED, timers=timers,
-                                                state=state[0], shares=steady_shares[0])
+                                                state=state[0], shares=steady_shares[0], shard_mustar=steady_smu[0])
         if host:
             sums_host.copy_(sums, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -561,7 +562,16 @@ def main():
 
     resident = inputs.to_device(dev)
     blocks_dev = [b_.to(dev) for b_ in blocks_host]
-    steady_shares = [None]
+    steady_shares, steady_smu = [None], [None]
+
+    def plan(st_all):
+        """sample shares and the mu* mode from the per-rank stage times of one iteration with the default partition"""
+        t_gp = st_all[0].get("gp_fit", 0.0) + st_all[0].get("mustar", 0.0)
+        t_rff = st_all[1].get("rff_fit", 0.0)
+        sh = iteration.plan_shares(world, t_gp, t_rff, t_sampling_all[0])
+        others_done = t_rff + max(sh[1:])                   # when the ranks >= 1 finish their samples
+        return sh, bool(world >= 3 and st_all[0].get("gp_fit", 0.0) >= others_done)
+    t_sampling_all = [0.0]
     if args.profile:
         if args.profile == "cold":
             for _ in range(1 + K):
@@ -578,11 +588,9 @@ def main():
         held[0] = step(resident)
     if world > 1:
         st_all = all_gather_stage(stage_times(lambda tm: step(resident, tm), 2))
-        t_gp = st_all[0].get("gp_fit", 0.0) + st_all[0].get("mustar", 0.0)
-        t_rff = st_all[1].get("rff_fit", 0.0)
-        samp = [s_.get("sampling", 0.0) for s_ in st_all[1:]]
-        t_sampling_all = float(np.sum(samp))                         # the default partition gives every rank >= 1 an equal share
-        shares[0] = iteration.plan_shares(world, t_gp, t_rff, t_sampling_all)
+        # the default partition gives every rank >= 1 an equal share: the whole sample set costs the sum of their sampling stages
+        t_sampling_all[0] = float(np.sum([s_.get("sampling", 0.0) for s_ in st_all[1:]]))
+        shares[0], smu[0] = plan(st_all)
     for _ in range(W_steps):
         held[0] = step(resident)           # (a warm-up that drops its products at once leaves the second timed step to
     clocks = ClockSampler(local)           # cudaMalloc a second set of 200 MB buffers: +1 ms on one GPU, up to +10 ms on two)
@@ -606,11 +614,9 @@ def main():
     if world > 1:
         steady_step(0, host=False)            # (first append on a fresh process: one-time workspace growth)
         steady_reset()
+        steady_smu[0] = False
         st_all = all_gather_stage(stage_times(lambda tm: steady_step(0, tm, host=False), 1))
-        steady_reset()
-        t_gp = st_all[0].get("gp_fit", 0.0) + st_all[0].get("mustar", 0.0)
-        t_rff = st_all[1].get("rff_fit", 0.0)
-        steady_shares[0] = iteration.plan_shares(world, t_gp, t_rff, t_sampling_all)
+        steady_shares[0], steady_smu[0] = plan(st_all)
         steady_reset()
     sel = []
     for i in range(W_steps):
@@ -767,8 +773,8 @@ def main():
                          "chord_steps_per_step": [int(s_["chord_steps"]) for s_ in steady_fits],
                          "host_ms_per_step": [round(1e3 * (b_ - a_), 2) for a_, b_ in zip(steady_marks[:-1], steady_marks[1:])],
                          "selected_directions": sel, "warm_vs_cold_mode_rel": warm_vs_cold,
-                         "sample_shares": steady_shares[0]},
-        "sample_shares": shares[0],
+                         "sample_shares": steady_shares[0], "mustar_sharded": steady_smu[0]},
+        "sample_shares": shares[0], "mustar_sharded": smu[0],
         # diagnostics: host time per issued step (resident steps are issued asynchronously, e2e steps end with the result on the host)
         "resident_host_ms_per_step": [round(t_, 2) for t_ in step_marks.get("resident", [])],
         "e2e_host_ms_per_step": [round(t_, 2) for t_ in step_marks.get("e2e", [])],

@@ -279,6 +279,12 @@ long long ppbo_ozaki_scale_doubles(int rows, int tile_rows, int batch);
  * in the tiled shared-memory image of the tensor-core operand (layout: csrc/ozaki.cu, tile_offset) */
 int ppbo_ozaki_slice(const double* X, long long ldx, long long strideX, int rows, int K, int tile_rows, int batch, int slices,
                      double* scale, signed char* planes, void* stream);
+/* The S posterior weight draws of ppbo_rff_sample_omega (Philox path) written directly as the A-operand digit planes and row
+ * scales (sized by ppbo_ozaki_plane_bytes / ppbo_ozaki_scale_doubles for S rows, K = F, tile_rows(0), batch 1): the draws are
+ * generated in shared memory and never reach HBM.  Bit-identical to ppbo_rff_sample_omega followed by ppbo_ozaki_slice.
+ * (Hsampler.sample_omega, src/random_fourier_sampler.py:207-213, batched over S samples.) */
+int ppbo_ozaki_sample_slice(const double* omega_map, const double* hess_diag, unsigned long long seed, unsigned int stream_id,
+                            long long sample0, int S, int F, int slices, double* scale, signed char* planes, void* stream);
 /* fmax[batch][S], arg[batch][S] = per-sample max / first arg-max over the P grid points of A . B_b^T from digit planes
  * (A sliced with tile_rows(0), batch 1; B with tile_rows(1), `batch` grids).  Fs_full (optional, tests): dense [batch][S x P].
  * workspace: ppbo_ozaki_rowmax_workspace_bytes(S, P, batch) bytes (partial maxima of the column-tile groups).

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "ppbo_ozaki_plane_bytes": (_L, [_I, _I, _I, _I, _I]),
     "ppbo_ozaki_scale_doubles": (_L, [_I, _I, _I]),
     "ppbo_ozaki_slice": (_I, [_P, _L, _L, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "ppbo_ozaki_sample_slice": (_I, [_P, _P, c_ulonglong, c_uint, _L, _I, _I, _I, _P, _P, _P]),
     "ppbo_ozaki_mma_rate": (_I, [_I, _I, _I, _I, _I, _P, _P]),
     "ppbo_ozaki_rowmax_workspace_bytes": (_L, [_I, _I, _I]),
     "ppbo_ozaki_rowmax": (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _L, _P, _P]),

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "gemm_f64.cuh"
 #include "linalg.cuh"
+#include "philox.cuh"
 
 namespace ppbo {
 
@@ -891,33 +892,6 @@ extern "C" int ppbo_rff_eval_argmax(const double* Omega, long long ldo, int S, i
 
 // ------------------------------------------------------------------------------------------------ posterior weight samples
 namespace ppbo {
-
-// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): counter-based, so sample s of
-// feature f gets the same normal whatever the grid shape or the rank that owns row s (multi-GPU invariance).
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
-        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
-// two standard normals from counter `idx` of stream `stream` under `seed` (Box-Muller on two 53-bit uniforms in (0,1))
-__device__ __forceinline__ void philox_normal2(unsigned long long seed, unsigned long long idx, uint32_t stream,
-                                               double& z0, double& z1) {
-    uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), stream, 0u};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double u1 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
-    const double u2 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
-    const double r = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    z0 = r * cs;
-    z1 = r * sn;
-}
 
 // out[i] = normal number (offset + i) of the stream; element e lives in counter e/2, slot e%2
 __global__ void __launch_bounds__(256) normal_fill_kernel(unsigned long long seed, uint32_t stream, long long offset,

@@ -29,6 +29,7 @@
 
 #include "../../include/ppbo_b200.h"
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace ppbo {
 extern int g_tuning[16];
@@ -116,6 +117,102 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
 #pragma unroll
         for (int s = 0; s < KS; ++s)
             *reinterpret_cast<uint4*>(base + (long long)s * TR * KB) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+    }
+}
+
+// Posterior weight draws straight into digit planes: Omega[s][f] = omega_map[f] + z[s][f] / sqrt(-hess_diag[f]) (sample_omega_kernel,
+// acq.cu; z = normal number (sample0 + s) F + f of the Philox stream) is generated into shared memory (one warp per row, 8 rows per
+// CTA), its row scale is taken there, and the planes are cut from shared memory exactly as ozaki_slice_kernel does from HBM.  The
+// S x F matrix of draws (262 MB at S = 32768, F = 1000) never exists: 8 B written + 16 B read per element become 0.
+// Bit-identical to sample_omega_kernel -> ozaki_rowscale_kernel -> ozaki_slice_kernel (same expressions, same rounding).
+template <int KS>
+__global__ void __launch_bounds__(256) ozaki_sample_slice_kernel(const double* __restrict__ omega_map, const double* __restrict__ hess_diag,
+                                                                 unsigned long long seed, uint32_t stream_id, long long sample0, int S,
+                                                                 int rows_pad, int F, int KBLK, double* __restrict__ scale,
+                                                                 int8_t* __restrict__ out) {
+    extern __shared__ double xs[];                           // [8][KBLK * KB] draws of this row group, zero-padded in K
+    __shared__ double sc_s[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rg = blockIdx.x, Kp = KBLK * KB;
+    {   // ---- phase 1: warp w draws row rg * 8 + w
+        const int r = rg * 8 + warp;
+        double* x = xs + warp * Kp;
+        double amax = 0.0;
+        for (int k = F + lane; k < Kp; k += 32) x[k] = 0.0;
+        if (r < S) {
+            for (int fp = lane; 2 * fp < F; fp += 32) {
+                const int f0 = 2 * fp;
+                double z0, z1 = 0.0;
+                const long long e = (sample0 + r) * (long long)F + f0;   // global normal index of (r, f0)
+                if ((e & 1) == 0) {
+                    philox_normal2(seed, (unsigned long long)(e >> 1), stream_id, z0, z1);
+                } else {                                                  // odd F: the pair straddles two counters
+                    double a, b;
+                    philox_normal2(seed, (unsigned long long)(e >> 1), stream_id, a, b);
+                    z0 = b;
+                    philox_normal2(seed, (unsigned long long)((e + 1) >> 1), stream_id, a, b);
+                    z1 = a;
+                }
+                const double v0 = omega_map[f0] + z0 * rsqrt(-hess_diag[f0]);
+                x[f0] = v0;
+                double v = fabs(v0);
+                amax = (v > amax || v != v) ? v : amax;
+                if (f0 + 1 < F) {
+                    const double v1 = omega_map[f0 + 1] + z1 * rsqrt(-hess_diag[f0 + 1]);
+                    x[f0 + 1] = v1;
+                    v = fabs(v1);
+                    amax = (v > amax || v != v) ? v : amax;
+                }
+            }
+        } else {
+            for (int k = lane; k < F; k += 32) x[k] = 0.0;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double w = __shfl_xor_sync(0xffffffffu, amax, o);
+            amax = (w > amax || w != w) ? w : amax;
+        }
+        if (lane == 0) {
+            double s = 1.0;
+            if (amax != amax || amax > 1.7e308) s = nan("");
+            else if (amax > 0.0) {
+                int ex;
+                frexp(amax, &ex);
+                s = ldexp(1.0, ex + 2);
+            }
+            sc_s[warp] = s;
+            scale[r] = s;
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: one warp = 8 rows x 4 sixteen-byte chunks = one k-block (ozaki_slice_kernel)
+    const int rr8 = lane & 7, c = lane >> 3;
+    const int r = rg * 8 + rr8;
+    const int rt = r / BM, rr = r % BM;
+    const double mult = ldexp(1.0 / sc_s[rr8], 8 * KS);
+    const double* x = xs + rr8 * Kp;
+    for (int kb = warp; kb < KBLK; kb += 8) {
+        const int k0 = kb * KB + c * 16;
+        uint32_t w[KS][4];
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[s][q] = 0u;
+        if (r < S) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                long long Y = __double2ll_rn(x[k0 + e] * mult);
+#pragma unroll
+                for (int s = KS - 1; s >= 0; --s) {
+                    const long long d = ((Y + 128) & 255) - 128;
+                    Y = (Y - d) >> 8;
+                    w[s][e >> 2] |= (uint32_t)((uint8_t)(int8_t)d) << (8 * (e & 3));
+                }
+            }
+        }
+        int8_t* base = out + (((long long)rt * KBLK + kb) * KS) * ((long long)BM * KB) + tile_offset(rr, c * 16);
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+            *reinterpret_cast<uint4*>(base + (long long)s * BM * KB) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
     }
 }
 
@@ -686,6 +783,39 @@ extern "C" int ppbo_ozaki_slice(const double* X, long long ldx, long long stride
         case 5: return oz::slice_launch<5>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
         case 6: return oz::slice_launch<6>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
         default: return oz::slice_launch<7>(X, ldx, strideX, rows, K, tile_rows, batch, scale, pl, st);
+    }
+}
+
+namespace ppbo { namespace oz {
+template <int KS>
+static int sample_slice_launch(const double* omega_map, const double* hess_diag, unsigned long long seed, unsigned int stream_id,
+                               long long sample0, int S, int F, double* scale, int8_t* planes, cudaStream_t st) {
+    const Shape s = shape_of(S, F, BM, 1, KS);
+    const int smem = 8 * s.KBLK * KB * (int)sizeof(double);
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] { err = cudaFuncSetAttribute(ozaki_sample_slice_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    PPBO_CUDA_CHECK(err);
+    PPBO_REQUIRE(smem <= 200 * 1024, "F too large for the fused draw (8 rows of F doubles must fit shared memory)");
+    PPBO_CL ozaki_sample_slice_kernel<KS><<<s.rows_pad / 8, 256, smem, st>>>(omega_map, hess_diag, seed, stream_id, sample0, S, s.rows_pad, F,
+                                                                              s.KBLK, scale, planes);
+    PPBO_LAUNCH_CHECK();
+    return PPBO_OK;
+}
+}}
+
+extern "C" int ppbo_ozaki_sample_slice(const double* omega_map, const double* hess_diag, unsigned long long seed, unsigned int stream_id,
+                                       long long sample0, int S, int F, int slices, double* scale, signed char* planes, void* stream) {
+    PPBO_REQUIRE(S >= 0 && F >= 1, "shape");
+    PPBO_REQUIRE(slices >= 5 && slices <= oz::MAX_KS, "slices in [5, 7]");
+    PPBO_REQUIRE((reinterpret_cast<uintptr_t>(planes) & 15) == 0, "planes must be 16-byte aligned");
+    if (S == 0) return PPBO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int8_t* pl = reinterpret_cast<int8_t*>(planes);
+    switch (slices) {
+        case 5: return oz::sample_slice_launch<5>(omega_map, hess_diag, seed, stream_id, sample0, S, F, scale, pl, st);
+        case 6: return oz::sample_slice_launch<6>(omega_map, hess_diag, seed, stream_id, sample0, S, F, scale, pl, st);
+        default: return oz::sample_slice_launch<7>(omega_map, hess_diag, seed, stream_id, sample0, S, F, scale, pl, st);
     }
 }
 

@@ -339,10 +339,14 @@ class SlicedSamples:
     """Digit planes of the posterior weight draws [lo, hi) (the A operand of the INT8 sampling contraction)."""
     __slots__ = ("planes", "scale", "count", "slices")
 
-    def __init__(self, Omega, slices=None):
+    def __init__(self, Omega=None, slices=None, drawn=None, count=None):
         self.slices = SAMPLING_SLICES if slices is None else slices
-        self.count = Omega.shape[0]
-        self.planes, self.scale = ops.ozaki_slice(Omega, 0, self.slices)
+        if drawn is not None:                       # (planes, scale) straight from the fused draw
+            self.planes, self.scale = drawn
+            self.count = count
+        else:
+            self.count = Omega.shape[0]
+            self.planes, self.scale = ops.ozaki_slice(Omega, 0, self.slices)
 
 
 def rff_prepare_samples(r, lo, hi, P, Z=None, seed=0, stream_id=0):
@@ -350,9 +354,14 @@ def rff_prepare_samples(r, lo, hi, P, Z=None, seed=0, stream_id=0):
     FP64 matrix otherwise).  Needs the weight-space fit only, so run_iteration does this while the GP fit is still running."""
     if hi <= lo:
         return None
+    Fdim = r.omega_map.shape[0]
+    if Z is None and sampling_engine(hi - lo, P, Fdim) == "i8" and Fdim * 64 <= 200 * 1024:
+        # draws and digit planes in one kernel: the S x F matrix of draws never reaches HBM
+        return SlicedSamples(drawn=ops.ozaki_sample_slice(r.omega_map, r.hess_diag, hi - lo, seed=seed, stream_id=stream_id, sample0=lo,
+                                                          slices=SAMPLING_SLICES), count=hi - lo)
     Zloc = None if Z is None else Z[lo:hi]
     Omega = ops.rff_sample_omega(r.omega_map, r.hess_diag, hi - lo, Z=Zloc, seed=seed, stream_id=stream_id, sample0=lo)
-    return SlicedSamples(Omega) if sampling_engine(hi - lo, P, r.omega_map.shape[0]) == "i8" else Omega
+    return SlicedSamples(Omega) if sampling_engine(hi - lo, P, Fdim) == "i8" else Omega
 
 
 def rff_sampled_maxima(r, PhiT, lo, hi, Z=None, seed=0, stream_id=0, prepared=None):
@@ -471,7 +480,7 @@ class IterationState:
 
 
 def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, tol=1e-8, timers=None, state=None, shares=None,
-                  factor_at_mode=False):
+                  factor_at_mode=False, shard_mustar=None):
     """d: dict of device tensors (IterationInputs.to_device).  Returns (sums [B,3] device, gp, rff).
     Rank 0 fits; the others receive (omega_MAP, hess_diag, mu*) by broadcast while they compute the grid features.
     tol: both Newton iterations stop when the last full step is below tol relative to the iterate.  The chord steps contract
@@ -480,13 +489,18 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
     state: an IterationState makes the models persistent: the first call fits from scratch into its capacity buffers (d["X"]),
     later calls APPEND the comparison sets d["block"] (Q is the new total) and refit from the previous modes.
     shares: sample share per rank (plan_shares); default: rank 0 of several takes none.
-    factor_at_mode: also produce the Cholesky factor at the GP mode (only prediction with covariance needs it)."""
+    factor_at_mode: also produce the Cholesky factor at the GP mode (only prediction with covariance needs it).
+    shard_mustar: split the mu* candidates over the ranks (alpha by broadcast, one all-reduce(max)).  Pays when the other ranks are
+    idle by the time the GP fit ends (default: 3 or more ranks and a cold fit); when they are still sampling, rank 0 would wait for
+    them inside the collective."""
     shard = shard or Shard()
     W, b, grids = d["W"], d["b"], d["grids"]
     dev = W.device
     Fdim = W.shape[0]
     B, P, D = grids.shape
     warm = state is not None and state.Q > 0
+    if shard_mustar is None:
+        shard_mustar = shard.world >= 3 and not warm
     X = None if warm else d["X"]
     block = d["block"] if warm else None
     if state is not None:
@@ -518,7 +532,7 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
     def mu_star(gp, cand):
         """max posterior mean over the design rows and the candidate points; with >= 3 ranks every rank takes a slice of the
         candidates (alpha travels by broadcast) and one all-reduce(max) follows"""
-        if shard.world < 3:
+        if not shard_mustar:
             return mustar_over_candidates(gp, cand) if shard.rank == 0 else None
         Qn = Q
         N = Qn * (m + 1)
@@ -609,6 +623,7 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
                 pack_rff[:Fdim].copy_(rff.omega_map)
                 pack_rff[Fdim:].copy_(rff.hess_diag)
             shard.broadcast(pack_rff, src=rff_rank)
+            mark("rff_received")
         if rff is None:
             rff = RFFFit()
             rff.W, rff.b, rff.sigma_f, rff.Phi_X, rff.stats = W, b, float(theta[2]), None, None
@@ -616,7 +631,7 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
         if shard.rank != 0 and hi > lo:
             fmax, _ = rff_sampled_maxima(rff, PhiT, lo, hi, seed=seed)
             mark("sampling")
-        if shard.world >= 3:
+        if shard_mustar:
             mustar = mu_star(gp, cand)
             mu_t.copy_(mustar)
         else:

@@ -526,6 +526,18 @@ def ozaki_slice(X, operand, slices=6):
     return planes, scale
 
 
+def ozaki_sample_slice(omega_map, hess_diag, S, seed=0, stream_id=0, sample0=0, slices=6):
+    """(digit planes, row scales) of the S Philox draws Omega ~ N(omega_map, diag(1 / -hess_diag)) without materialising Omega"""
+    lib = _lib.load()
+    Fdim = omega_map.shape[0]
+    tr = lib.ppbo_ozaki_tile_rows(0)
+    planes = torch.empty(lib.ppbo_ozaki_plane_bytes(S, Fdim, tr, 1, slices), dtype=torch.int8, device=omega_map.device)
+    scale = torch.empty(lib.ppbo_ozaki_scale_doubles(S, tr, 1), dtype=F64, device=omega_map.device)
+    check(lib.ppbo_ozaki_sample_slice(_p(omega_map), _p(hess_diag), int(seed), int(stream_id), int(sample0), S, Fdim, slices,
+                                      _p(scale), _p(planes), _stream()), "ppbo_ozaki_sample_slice")
+    return planes, scale
+
+
 def ozaki_rowmax(ap, asc, S, bp, bsc, P, B, F, slices, fmax=None, arg=None, want_full=False, err=None):
     """fused INT8 GEMM + per-sample max / first arg-max from digit planes (ppbo_ozaki_rowmax)"""
     lib = _lib.load()

@@ -136,3 +136,19 @@ def test_rowmax_i8_bench_shape_vs_fp64_oracle(ops):
     a1 = ops.rff_eval_argmax_i8(Od, Gd, slices=6)[0]
     a2 = ops.rff_eval_argmax_i8(Od, Gd, slices=6)[0]
     assert torch.equal(a1, a2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,F,sample0", [(128, 64, 0), (300, 1000, 0), (257, 333, 7), (1000, 96, 12345), (8, 65, 1)])
+def test_fused_draw_and_slice_bit_identical(ops, S, F, sample0):
+    """ppbo_ozaki_sample_slice (draws generated in shared memory, never written to HBM) against ppbo_rff_sample_omega followed by
+    ppbo_ozaki_slice: identical digit planes and row scales, for ragged S, odd F and an offset into the Philox stream"""
+    rng = np.random.RandomState(F)
+    om = ops.to_dev(rng.randn(F) * 0.3)
+    hd = ops.to_dev(-(1.0 + 5 * rng.rand(F)))
+    for slices in (5, 6, 7):
+        Omega = ops.rff_sample_omega(om, hd, S, seed=42, stream_id=3, sample0=sample0)
+        p0, s0 = ops.ozaki_slice(Omega, 0, slices)
+        p1, s1 = ops.ozaki_sample_slice(om, hd, S, seed=42, stream_id=3, sample0=sample0, slices=slices)
+        assert torch.equal(s0, s1)
+        assert torch.equal(p0, p1)
