@@ -612,10 +612,9 @@ def main():
     held[0] = None
     steady_reset()
     if world > 1:
-        steady_step(0, host=False)            # (first append on a fresh process: one-time workspace growth)
-        steady_reset()
-        steady_smu[0] = False
-        st_all = all_gather_stage(stage_times(lambda tm: steady_step(0, tm, host=False), 1))
+        steady_step(0, host=False)            # (first append on a fresh process: one-time workspace growth; it also follows a cold
+        steady_smu[0] = False                 # fit, whose single factor is stale: the calibration uses the second append)
+        st_all = all_gather_stage(stage_times(lambda tm: steady_step(1, tm, host=False), 1))
         steady_shares[0], steady_smu[0] = plan(st_all)
         steady_reset()
     sel = []
@@ -651,9 +650,11 @@ def main():
         fw, fc = state[0].gp.f_map.cpu().numpy(), gfin.f_map.cpu().numpy()
         warm_vs_cold = float(np.abs(fw - fc).max() / np.abs(fc).max())
         del gfin
-    # one more append on a fresh state for its stage breakdown
+    # stage breakdown of a steady-state append: the SECOND append on a fresh state (the first one follows a cold fit, whose factor is
+    # the stale one of its single factorisation)
     steady_reset()
-    steady_stages = all_gather_stage(stage_times(lambda tm: steady_step(0, tm, host=False), 1))
+    steady_step(0, host=False)
+    steady_stages = all_gather_stage(stage_times(lambda tm: steady_step(1, tm, host=False), 1))
     state[0] = None
 
     # ---- acquisition stage alone: S samples x P points x B directions, even shares over ALL ranks (sample-points / s)

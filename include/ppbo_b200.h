@@ -20,6 +20,7 @@ extern "C" {
 #define PPBO_KERNEL_SE 0       /* src/kernels.py:19-25 (ARD generalisation: one length-scale per dim) */
 #define PPBO_KERNEL_RQ 1       /* src/kernels.py:27-34 (alpha = 2)                                     */
 #define PPBO_KERNEL_CAMPHOR 2  /* src/kernels.py:36-53                                                 */
+#define PPBO_KERNEL_SQDIST 3   /* internal: squared Euclidean distance (ppbo_sqdist)                   */
 
 int ppbo_version(void);
 const char* ppbo_last_error(void);
@@ -38,6 +39,8 @@ int ppbo_set_thread_background(int on);
  * GPModel.create_Gramian_nonsquare (src/gp_model.py:153-155).  lengthscales_h: D host doubles. */
 int ppbo_kernel_matrix(int kind, const double* X1, int n1, const double* X2, int n2, int D,
                        const double* lengthscales_h, double sigma_f, double* out, long long ld, void* stream);
+/* out[n1 x n2] = |X1_i - X2_j|^2.  Replaces kernels.dist (src/kernels.py:3-11). */
+int ppbo_sqdist(const double* X1, int n1, const double* X2, int n2, int D, double* out, long long ld, void* stream);
 /* out[n x n] = (1-s) K(X,X) + s * (tr K / n) I, tr K / n == sigma_f^2 for these stationary kernels.
  * Replaces GPModel.create_Gramian = kernel + misc.regularize_covariance (src/gp_model.py:147-151,
  * src/misc.py:71-88: the SVD round trip is the identity, the shrinkage is fused). */

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "ppbo_set_tuning": (_I, [_I, _I]),
     "ppbo_set_thread_background": (_I, [_I]),
     "ppbo_kernel_matrix": (_I, [_I, _P, _I, _P, _I, _I, _PD, _D, _P, _L, _P]),
+    "ppbo_sqdist": (_I, [_P, _I, _P, _I, _I, _P, _L, _P]),
     "ppbo_gram_regularized": (_I, [_I, _P, _I, _I, _PD, _D, _D, _P, _L, _P]),
     "ppbo_kernel_se_grad": (_I, [_P, _I, _P, _I, _I, _PD, _D, _P, _L, _L, _P]),
     "ppbo_lik_terms": (_I, [_P, _I, _I, _D, _P, _P, _P, _P]),

@@ -28,6 +28,7 @@ __device__ __forceinline__ double kernel_from_sums(int kind, double r2, double s
     // r2: scaled squared distance (SE / RQ) or the summed exponent (camphor)
     if (kind == PPBO_KERNEL_SE) return sf2 * exp(-0.5 * r2);
     if (kind == PPBO_KERNEL_RQ) { const double t = 1.0 + 0.25 * r2; return sf2 / (t * t); }   // alpha = 2
+    if (kind == PPBO_KERNEL_SQDIST) return r2;                                                // kernels.dist: the distance itself
     return sf2 * exp(-r2);
 }
 
@@ -341,7 +342,7 @@ static int launch_kernel_matrix_mma(const KernelParams& p, const double* X1, int
 }
 
 static int fill_params(KernelParams& p, int kind, int D, const double* ls_h, double sigma_f) {
-    PPBO_REQUIRE(kind >= 0 && kind <= 2, "unknown kernel kind");
+    PPBO_REQUIRE(kind >= 0 && kind <= 3, "unknown kernel kind");
     PPBO_REQUIRE(D >= 1 && D <= PPBO_MAX_D, "D must be in [1, 64]");
     PPBO_REQUIRE(kind != PPBO_KERNEL_CAMPHOR || D == 6, "camphor_copper_kernel is defined for D = 6 only");
     PPBO_REQUIRE(ls_h != nullptr && sigma_f > 0, "hyper-parameters");
@@ -372,7 +373,15 @@ int kernel_matrix(const KernelParams& p, const double* X1, int n1, const double*
         PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_kernel<PPBO_KERNEL_CAMPHOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_tiled_kernel<PPBO_KERNEL_SE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_tiled_kernel<PPBO_KERNEL_RQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_tiled_kernel<PPBO_KERNEL_SQDIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_done = true;
+    }
+    if (p.kind == PPBO_KERNEL_SQDIST) {         // squared distances: difference form (no cancellation), no tensor-pipe variant
+        const int Dp = (p.D + KR_DC - 1) / KR_DC * KR_DC;
+        PPBO_CL kernel_matrix_tiled_kernel<PPBO_KERNEL_SQDIST><<<grid, KT_THREADS, (size_t)(KT_M + KT_N) * Dp * sizeof(double), st>>>(
+            X1, n1, X2, n2, p, out, ld, 0);
+        PPBO_LAUNCH_CHECK();
+        return PPBO_OK;
     }
     if (g_tuning[11] == 0 && (p.kind == PPBO_KERNEL_SE || p.kind == PPBO_KERNEL_RQ)) {     // tuning key 11 = 1: difference-form kernels
         const int mode = (symmetric_diag && X1 == X2 && n1 == n2) ? KM_SYMMETRIC : KM_STORE;
@@ -619,6 +628,15 @@ extern "C" int ppbo_kernel_matrix(int kind, const double* X1, int n1, const doub
                                   const double* lengthscales_h, double sigma_f, double* out, long long ld, void* stream) {
     PPBO_REQUIRE(n1 >= 0 && n2 >= 0 && ld >= n2, "shape");
     return kernel_matrix_raw(kind, X1, n1, X2, n2, D, lengthscales_h, sigma_f, 1.0, 0.0, out, ld, (cudaStream_t)stream);
+}
+
+/* out[n1 x n2] = |X1_i - X2_j|^2 (kernels.dist, src/kernels.py:3-11: the reference expands |x|^2 + |y|^2 - 2 x.y and clips at 0; the
+ * difference form used here has no cancellation, so the clip never acts) */
+extern "C" int ppbo_sqdist(const double* X1, int n1, const double* X2, int n2, int D, double* out, long long ld, void* stream) {
+    PPBO_REQUIRE(n1 >= 0 && n2 >= 0 && ld >= n2 && D >= 1 && D <= PPBO_MAX_D, "shape");
+    double ones[PPBO_MAX_D];
+    for (int d = 0; d < PPBO_MAX_D; ++d) ones[d] = 1.0;
+    return kernel_matrix_raw(PPBO_KERNEL_SQDIST, X1, n1, X2, n2, D, ones, 1.0, 1.0, 0.0, out, ld, (cudaStream_t)stream);
 }
 
 extern "C" int ppbo_gram_regularized(int kind, const double* X, int n, int D, const double* lengthscales_h,

@@ -18,6 +18,7 @@
 
 namespace ppbo {
 
+extern int g_tuning[16];
 int diffspace_gram(const double* S, long long lds, int Q, int m, double* G, long long ldg, cudaStream_t st);
 int newton_matrix(const double* G, long long ldg, int M, const double* sa, double* out, long long ldo, cudaStream_t st);
 
@@ -186,20 +187,32 @@ __global__ void axpy2_kernel(double* __restrict__ alpha, const double* __restric
     }
 }
 
-// Likelihood sums of a queued chord step at its step length omega = state[7]:  part[q] = sum_j Phi~(Delta_qj(f + omega df))
+// Likelihood sums of a queued chord step at its step length omega = state[7]:  part[q] = sum_j Phi~(Delta_qj(f + omega df)) and,
+// when part0 is given, the sums at the current iterate f (T there is then recomputed every step instead of being carried)
 __global__ void __launch_bounds__(256) chord_lik_kernel(const double* __restrict__ f, const double* __restrict__ df, int Q, int m,
-                                                        double sigma, const double* __restrict__ state, double* __restrict__ part) {
+                                                        double sigma, const double* __restrict__ state, double* __restrict__ part,
+                                                        double* __restrict__ part0) {
     if (state[4] != 0.0) return;
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (q >= Q) return;
     const double step = state[7];
     const long long base = (long long)q * (m + 1);
-    const double fw = f[base] + step * df[base];
+    const double fw0 = f[base], fw = fw0 + step * df[base];
     const double inv_s = 1.0 / sigma;
-    double s = 0.0;
-    for (int j = lane; j < m; j += 32) s += Phi_tilde((f[base + 1 + j] + step * df[base + 1 + j] - fw) * inv_s);
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) part[q] = s;
+    double s = 0.0, s0 = 0.0;
+    for (int j = lane; j < m; j += 32) {
+        const double fj = f[base + 1 + j];
+        s += Phi_tilde((fj + step * df[base + 1 + j] - fw) * inv_s);
+        if (part0) s0 += Phi_tilde((fj - fw0) * inv_s);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    }
+    if (lane == 0) {
+        part[q] = s;
+        if (part0) part0[q] = s0;
+    }
 }
 
 // Device-side acceptance test of one chord step, so that a batch of chord steps runs without a host round trip (a host decision
@@ -211,6 +224,8 @@ __global__ void __launch_bounds__(256) chord_lik_kernel(const double* __restrict
 //   state[10] slowest contraction per step that is still cheaper than a new factor (0.5 after a Newton step of this fit; 0.85 for
 //             the factor of the previous PPBO iteration: a chord step costs ~1/12 of a factorisation there and a refactorisation
 //             is followed by one or two more)
+//   state[11] residual three accepted steps ago    state[13] 1 = the steps of this batch are mixed by chord_anderson_kernel
+//   state[14] 1 = the last call took a plain full step
 //   hist[2i], hist[2i+1] = (rel, T) of step i
 // A chord step of length 1 is only taken when T(alpha + dalpha) does not fall below T (same rule as the host line search with
 // c == 0).  When state[4] != 0 this kernel and every other kernel of a queued step return at once (skip flag).
@@ -222,13 +237,14 @@ __global__ void __launch_bounds__(256) chord_lik_kernel(const double* __restrict
 __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__ alpha, const double* __restrict__ dalpha,
                                                             double* __restrict__ f, const double* __restrict__ df, int N,
                                                             const double* __restrict__ part, int Q, int m,
-                                                            double* __restrict__ state, double* __restrict__ hist, int extrapolate) {
+                                                            double* __restrict__ state, double* __restrict__ hist, int extrapolate,
+                                                            const double* __restrict__ part0) {
     __shared__ double red[33];
     __shared__ double mx[2][32];
     __shared__ double step_s;
     if (state[4] != 0.0) return;                    // uniform: state[4] is only written after the barriers below
     const double omega = state[7];
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mdf = 0, mf = 0, lik = 0;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mdf = 0, mf = 0, lik = 0, lik0 = 0;
     for (int i = threadIdx.x; i < N; i += 1024) {
         const double a = alpha[i], da = dalpha[i], fi = f[i], dfi = df[i];
         s0 = fma(a, fi, s0);
@@ -238,12 +254,16 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
         mdf = fmax(mdf, fabs(dfi));
         mf = fmax(mf, fabs(fi));
     }
-    for (int q = threadIdx.x; q < Q; q += 1024) lik += part[q];
+    for (int q = threadIdx.x; q < Q; q += 1024) {
+        lik += part[q];
+        if (part0) lik0 += part0[q];
+    }
     s0 = block_sum(s0, red);
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
     s3 = block_sum(s3, red);
     lik = block_sum(lik, red);
+    if (part0) lik0 = block_sum(lik0, red);
     for (int o = 16; o > 0; o >>= 1) {
         mdf = fmax(mdf, __shfl_xor_sync(0xffffffffu, mdf, o));
         mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
@@ -252,10 +272,11 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 32; ++w) { mdf = fmax(mdf, mx[0][w]); mf = fmax(mf, mx[1][w]); }
-        const double T_cur = state[0];
+        const double T_cur = part0 ? (-0.5 * s0 - lik0 / m) : state[0];
         const double T1 = -0.5 * (s0 + omega * (s1 + s2) + omega * omega * s3) - lik / m;
         const bool accept = T1 >= T_cur - 1e-13 * fabs(T_cur);
         double step = 0.0;
+        state[14] = (accept && omega == 1.0) ? 1.0 : 0.0;               // a plain full step was taken (chord_anderson_kernel)
         if (!accept) {
             if (omega > 1.0) { state[7] = 1.0; state[9] = 4.0; }       // repeat this step at full length, no extrapolation for a while
             else if (omega > 0.2) { state[7] = 0.5 * omega; state[9] = 4.0; }   // backtrack along the same direction (appended rows start
@@ -266,6 +287,8 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
             step = omega;
             const double rel = mdf / fmax(mf, 1e-300), prev = state[1];
             const int n = (int)state[5];
+            const double rel3 = state[11];                                 // residual three accepted steps ago
+            state[11] = state[2];
             state[0] = T1;
             state[2] = prev;
             state[1] = rel;
@@ -278,6 +301,9 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
             const bool after_extrapolation = omega != 1.0;
             if (rel <= state[6]) {
                 state[4] = 1.0;
+            } else if (state[13] == 1.0) {
+                // mixed (Anderson) steps are not monotone step by step: judge them over three steps
+                if (rel3 < 1e300 && !(rel <= 0.5 * rel3)) state[4] = 2.0;
             } else if (!after_extrapolation && wait <= 0.0 && !(rel <= state[10] * prev)) {
                 state[4] = 2.0;                                        // plain steps contract too slowly: pay for a new factor
             } else if (wait > 0.0 && !(rel <= 4.0 * prev)) {
@@ -301,6 +327,119 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
     for (int i = threadIdx.x; i < N; i += 1024) {
         alpha[i] = fma(step, dalpha[i], alpha[i]);
         f[i] = fma(step, df[i], f[i]);
+    }
+}
+
+// Anderson acceleration of the chord iteration (depth AA_M).  The chord iteration x <- g(x) is, near the mode, a linear fixed-point
+// iteration whose matrix (Sigma^-1 + W0)^-1 (W0 - W) has a real spectrum of radius rho (0.2 .. 0.8 depending on how stale the
+// coefficients W0 of the factor are); plain iteration gains a factor rho per step, mixing the last AA_M residual differences
+// (a Krylov method on the linearised problem) about rho / (1 + sqrt(1 - rho^2)).  After chord_decide_kernel has taken a plain full
+// step -- alpha = g_a(x_k), f = g_f(x_k), residual r_k = df still in memory -- this kernel
+//   * appends the differences (r_k - r_{k-1}, g_k - g_{k-1}) to the history,
+//   * solves min_gamma | r_k - dR gamma |_2 (normal equations of order <= AA_M, Tikhonov-damped) and
+//   * replaces (alpha, f) by g_k - dG gamma   (f = Sigma alpha is preserved: both are the same combination).
+// The history is dropped when a step was damped / extrapolated / rejected, or when the residual grew.  One CTA, fixed order.
+constexpr int AA_M = 3;
+//   aa: [0] history length, [1] next slot, [2] residual norm (max |df| / max |f|) seen by the previous call
+//   H: [3 * AA_M + 3][N]: dR[AA_M], dGf[AA_M], dGa[AA_M], prev r, prev g_f, prev g_a
+__global__ void __launch_bounds__(1024) chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f,
+                                                              const double* __restrict__ df, int N, const double* __restrict__ state,
+                                                              double* __restrict__ aa, double* __restrict__ H) {
+    __shared__ double red[33];
+    __shared__ double gam[AA_M];
+    __shared__ int nh_s;
+    if (state[4] == 1.0 || state[4] == 3.0) return;                      // converged or rejected for good: nothing to mix
+    double* dR = H;
+    double* dGf = H + (long long)AA_M * N;
+    double* dGa = H + 2LL * AA_M * N;
+    double* pr = H + 3LL * AA_M * N;
+    double* pgf = pr + N;
+    double* pga = pgf + N;
+    const bool plain = state[14] == 1.0;
+    const double rel = state[1];
+    int nh = (int)aa[0], slot = (int)aa[1];
+    const double rel_prev = aa[2];
+    bool have_prev = aa[3] == 1.0;
+    __syncthreads();                                                     // everybody has read the state
+    if (!plain || (have_prev && rel > 1.5 * rel_prev)) {
+        // a damped / extrapolated / rejected step, or a residual that grew: the history no longer describes one linear map
+        if (threadIdx.x == 0) { aa[0] = 0.0; aa[1] = 0.0; aa[2] = rel; aa[3] = 0.0; }
+        if (!plain) return;
+        nh = 0;
+        slot = 0;
+        have_prev = false;
+    }
+    // append the newest differences (needs the previous (r, g)); then remember the current ones
+    if (have_prev) {
+        for (int i = threadIdx.x; i < N; i += 1024) {
+            dR[(long long)slot * N + i] = df[i] - pr[i];
+            dGf[(long long)slot * N + i] = f[i] - pgf[i];
+            dGa[(long long)slot * N + i] = alpha[i] - pga[i];
+        }
+        nh = min(nh + 1, AA_M);
+        slot = (slot + 1) % AA_M;
+    }
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        pr[i] = df[i];
+        pgf[i] = f[i];
+        pga[i] = alpha[i];
+    }
+    __syncthreads();
+    // normal equations A gamma = b, A_ij = <dR_i, dR_j>, b_i = <dR_i, r>
+    double A[AA_M][AA_M], bb[AA_M];
+    for (int i = 0; i < nh; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            double sacc = 0.0;
+            for (int k = threadIdx.x; k < N; k += 1024) sacc = fma(dR[(long long)i * N + k], dR[(long long)j * N + k], sacc);
+            A[i][j] = A[j][i] = block_sum(sacc, red);
+        }
+        double sacc = 0.0;
+        for (int k = threadIdx.x; k < N; k += 1024) sacc = fma(dR[(long long)i * N + k], df[k], sacc);
+        bb[i] = block_sum(sacc, red);
+    }
+    if (threadIdx.x == 0) {
+        double tr = 0.0;
+        for (int i = 0; i < nh; ++i) tr += A[i][i];
+        for (int i = 0; i < nh; ++i) A[i][i] += 1e-10 * tr + 1e-300;     // damping: nearly collinear differences
+        // Gaussian elimination with partial pivoting (order <= 3)
+        int idx[AA_M];
+        for (int i = 0; i < nh; ++i) idx[i] = i;
+        bool ok = true;
+        for (int c = 0; c < nh && ok; ++c) {
+            int p = c;
+            for (int r2 = c + 1; r2 < nh; ++r2) if (fabs(A[r2][c]) > fabs(A[p][c])) p = r2;
+            if (A[p][c] == 0.0) { ok = false; break; }
+            for (int k = 0; k < nh; ++k) { const double t = A[c][k]; A[c][k] = A[p][k]; A[p][k] = t; }
+            { const double t = bb[c]; bb[c] = bb[p]; bb[p] = t; }
+            for (int r2 = c + 1; r2 < nh; ++r2) {
+                const double l = A[r2][c] / A[c][c];
+                for (int k = c; k < nh; ++k) A[r2][k] -= l * A[c][k];
+                bb[r2] -= l * bb[c];
+            }
+        }
+        for (int i = nh - 1; i >= 0 && ok; --i) {
+            double v = bb[i];
+            for (int k = i + 1; k < nh; ++k) v -= A[i][k] * gam[k];
+            gam[i] = v / A[i][i];
+            if (!(fabs(gam[i]) < 1e3)) ok = false;
+        }
+        nh_s = ok ? nh : 0;
+        aa[0] = ok ? nh : 0;
+        aa[1] = ok ? slot : 0;
+        aa[2] = rel;
+        aa[3] = 1.0;                                                      // (prev r, g) are valid from now on
+    }
+    __syncthreads();
+    const int nm = nh_s;
+    if (nm == 0) return;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        double cf = 0.0, ca = 0.0;
+        for (int j = 0; j < nm; ++j) {
+            cf = fma(gam[j], dGf[(long long)j * N + i], cf);
+            ca = fma(gam[j], dGa[(long long)j * N + i], ca);
+        }
+        f[i] -= cf;
+        alpha[i] -= ca;
     }
 }
 
@@ -506,11 +645,13 @@ __global__ void __launch_bounds__(256) newton_rows_kernel(const double* __restri
 struct FitWorkspace {
     double *bvec, *sa, *ap, *t, *Sb, *dalpha, *df, *set_part, *scal, *arrow_tmp, *binv, *state, *hist;
     double *bR, *bT, *bC, *bw;           // bordered warm start: R [BORDER_MAX x M], scratch T [BORDER_MAX x M], C [BORDER_MAX^2], w
+    double *aaH, *aa, *part0;            // Anderson history [(3 AA_M + 3) x N], its state [8], likelihood sums at the current iterate [Q]
     int* info;
     static long long doubles(int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
         return 4 * N + 3 * M + (M + CHOL_NB) + (long long)NSTEP * Q + 32 + 8 + 64 + CHORD_STATE + 2 * CHORD_BATCH_MAX +
-               blockinv_doubles((int)M) + 2LL * BORDER_MAX * (M + 2) + (long long)BORDER_MAX * BORDER_MAX + BORDER_MAX + 8;
+               blockinv_doubles((int)M) + 2LL * BORDER_MAX * (M + 2) + (long long)BORDER_MAX * BORDER_MAX + BORDER_MAX + 8 +
+               (3LL * AA_M + 3) * N + 8 + Q;
     }
     void carve(double* base, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
@@ -534,7 +675,10 @@ struct FitWorkspace {
         bR = p; p += BORDER_MAX * Mp;
         bT = p; p += BORDER_MAX * Mp;
         bC = p; p += (long long)BORDER_MAX * BORDER_MAX;
-        bw = p;
+        bw = p; p += BORDER_MAX;
+        aaH = p; p += (3LL * AA_M + 3) * N;
+        aa = p; p += 8;
+        part0 = p;
     }
 };
 
@@ -703,7 +847,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     // is kept and only the right-hand side is refreshed (chord steps: same fixed point Sigma^-1 f = beta(f), linear
     // convergence at the rate of the relative change of a+; a chord step costs ~1/6 of a factorisation at Qm = 5000, so it
     // is kept as long as it at least halves the step).
-    const double CHORD_REL = getenv("PPBO_CHORD_REL") ? atof(getenv("PPBO_CHORD_REL")) : 0.25;   // env override: diagnostics only
+    double CHORD_REL = getenv("PPBO_CHORD_REL") ? atof(getenv("PPBO_CHORD_REL")) : 0.25;   // env override: diagnostics only
     const bool trace = getenv("PPBO_TRACE") != nullptr;
     bool refactor = true, converged = false;
     // Cold start f = 0: every difference is 0, so a = -Delta phi~(Delta) / (2 m sigma^2) = 0 and the Newton matrix
@@ -716,6 +860,18 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     // tuning: PPBO_CHORD_EXTRAPOLATE=0 switches the Aitken step lengths off (diagnostics)
     const bool chord_extrapolate = !(getenv("PPBO_CHORD_EXTRAPOLATE") && atoi(getenv("PPBO_CHORD_EXTRAPOLATE")) == 0);
     double chord_omega = 1.0, chord_ratio = 0.0, chord_wait = 0.0;
+    // tuning key 13: Anderson acceleration of the chord iteration (1 = on, 2 = on and enter the chord phase after the FIRST Newton
+    // factorisation of a cold fit); PPBO_ANDERSON overrides (diagnostics)
+    int anderson_mode = g_tuning[13] == 0 ? 2 : g_tuning[13] - 1;        // key 13: 0 default (= 2), 1 off, 2 after every factor, 3 = 2
+    if (getenv("PPBO_ANDERSON")) anderson_mode = atoi(getenv("PPBO_ANDERSON"));
+    // mode 2 (default): a fit that starts without a usable factor enters the chord phase after its FIRST factorisation (relative
+    // step <= 0.6 instead of 0.25) and mixes the chord steps there; if three mixed steps do not halve the residual the fit pays for
+    // the second factorisation and continues exactly like the unaccelerated iteration.  Warm (bordered) fits are not mixed: the
+    // border's Newton steps change the map from step to step and the Aitken step lengths do better there (measured).
+    bool aa_failed = false;
+    double rel3_h = INFINITY;
+    auto aa_now = [&]() { return (anderson_mode == 1) || (anderson_mode >= 2 && !warm_factor && n_factor == 1 && !aa_failed); };
+    PPBO_CUDA_CHECK(cudaMemsetAsync(ws.aa, 0, sizeof(double) * 8, st));
     bool factor_current = false;         // Lfac is the factor for the coefficients in ws.sa / ws.ap
     double warm_first_rel = NAN;
     // ---- warm start with the previous iteration's factor (bordered, see border_solve_kernel): chord steps from (f_init, alpha_init)
@@ -781,13 +937,15 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 binv_valid = true;
             }
             double rho = (std::isfinite(prev_rel_h) && last_rel < prev_rel_h) ? last_rel / prev_rel_h : 0.2;
-            rho = std::fmin(std::fmax(rho, 0.02), (warm_factor && n_factor == 0) ? 0.85 : 0.5);
+            const bool anderson = aa_now();
+            rho = std::fmin(std::fmax(rho, 0.02), (anderson || (warm_factor && n_factor == 0)) ? 0.85 : 0.5);
             int kb = !std::isfinite(last_rel) ? 3 : (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
             if (first_chord_batch) kb = std::min(kb, 3);
             kb = std::max(1, std::min(kb, std::min(CHORD_BATCH_MAX, max_iter - it)));
             first_chord_batch = false;
             const double slow = (warm_factor && n_factor == 0) ? 0.85 : 0.5;
-            double state_h[CHORD_STATE] = {T_cur, last_rel, prev_rel_h, last_step, 0.0, 0.0, tol, chord_omega, chord_ratio, chord_wait, slow};
+            double state_h[CHORD_STATE] = {T_cur, last_rel, prev_rel_h, last_step, 0.0, 0.0, tol, chord_omega, chord_ratio, chord_wait, slow,
+                                           rel3_h, 0.0, anderson ? 1.0 : 0.0};
             double hist_h[2 * CHORD_BATCH_MAX];
             PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.state, state_h, sizeof(state_h), cudaMemcpyHostToDevice, st));
             const double* skip = ws.state + 4;               // non-zero once a step of the batch has stopped it
@@ -799,9 +957,10 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 if ((rc = chord_solve(skip))) return rc;
                 PPBO_CL alpha_update_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, ws.sa, ws.t, alpha, Q, m, ws.dalpha, skip);
                 if ((rc = gemv(Sigma, lds, N, N, ws.dalpha, ws.df, st, skip))) return rc;
-                PPBO_CL chord_lik_kernel<<<set_blocks, 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.state, ws.set_part);
+                PPBO_CL chord_lik_kernel<<<set_blocks, 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.state, ws.set_part, anderson ? ws.part0 : nullptr);
                 PPBO_CL chord_decide_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, m, ws.state, ws.hist,
-                                                                  chord_extrapolate ? 1 : 0);
+                                                                  (chord_extrapolate && !anderson) ? 1 : 0, anderson ? ws.part0 : nullptr);
+                if (anderson) PPBO_CL chord_anderson_kernel<<<1, 1024, 0, st>>>(alpha, f_map, ws.df, N, ws.state, ws.aa, ws.aaH);
             }
             PPBO_LAUNCH_CHECK();
             PPBO_CUDA_CHECK(cudaMemcpyAsync(state_h, ws.state, sizeof(state_h), cudaMemcpyDeviceToHost, st));
@@ -823,6 +982,8 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             chord_omega = state_h[7];
             chord_ratio = state_h[8];
             chord_wait = state_h[9];
+            rel3_h = state_h[11];
+            if (anderson && (stop == 2 || stop == 3)) aa_failed = true;      // mixing did not pay: the rest of the fit runs unaccelerated
             if (stop == 1) { converged = true; break; }
             if (stop == 2 || stop == 3) refactor = true;      // contraction too slow / step rejected: pay for a new factor
             continue;
@@ -842,6 +1003,8 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             chord_omega = 1.0;                   // a new factor: new iteration matrix, forget the contraction history
             chord_ratio = 0.0;
             chord_wait = 0.0;
+            PPBO_CUDA_CHECK(cudaMemsetAsync(ws.aa, 0, sizeof(double) * 8, st));
+            rel3_h = INFINITY;
         }
         if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
         PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
@@ -904,7 +1067,8 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         ++it;
         if (step == 1.0 && last_rel <= tol) { converged = true; break; }
         // chord steps once the Newton iteration is in its contraction region and a factor exists to reuse
-        refactor = !(step == 1.0 && last_rel <= CHORD_REL) || identity_factor;
+        const double chord_rel = (anderson_mode >= 2 && !warm_factor && n_factor == 1 && !aa_failed && !getenv("PPBO_CHORD_REL")) ? 0.6 : CHORD_REL;
+        refactor = !(step == 1.0 && last_rel <= chord_rel) || identity_factor;
     }
     // The factor a later warm fit can reuse is the one the last Newton step built (or the warm one it was handed): its
     // coefficients go to sa_fac.  (An identity "factor" -- cold start that converged at once -- is not a factor object.)

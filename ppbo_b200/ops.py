@@ -75,6 +75,15 @@ def kernel_matrix(kernel, X1, X2, lengthscales, sigma_f, out=None):
     return out
 
 
+def sqdist(X1, X2):
+    """squared Euclidean distances between the rows of X1 and X2"""
+    n1, D = X1.shape
+    n2 = X2.shape[0]
+    out = torch.empty((n1, n2), dtype=F64, device=X1.device)
+    check(_lib.load().ppbo_sqdist(_p(X1), n1, _p(X2), n2, D, _p(out), max(n2, 1), _stream()), "ppbo_sqdist")
+    return out
+
+
 def gram_regularized(kernel, X, lengthscales, sigma_f, shrinkage, out=None):
     n, D = X.shape
     out = torch.empty((n, n), dtype=F64, device=X.device) if out is None else out

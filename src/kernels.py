@@ -30,10 +30,10 @@ def _evaluate(name, X1, X2, theta):
 
 
 def dist(X1, X2):
-    """squared Euclidean distances between the rows of X1 and X2 (src/kernels.py:3-11): -2 l^2 log(k_SE / sigma_f^2) is
-    not used -- an RQ kernel with alpha -> the identity is: sqdist = 4 l^2 (k_RQ^-1/2 - 1) at l = sigma_f = 1."""
-    k = _evaluate("RQ_kernel", X1, X2, (0.0, 1.0, 1.0))
-    return np.clip(4.0 * (1.0 / np.sqrt(k) - 1.0), 0.0, np.inf)
+    """squared Euclidean distances between the rows of X1 and X2 (src/kernels.py:3-11), on the GPU (ppbo_sqdist)"""
+    X1 = np.atleast_2d(np.asarray(X1, dtype=np.float64))
+    X2 = np.atleast_2d(np.asarray(X2, dtype=np.float64))
+    return ops.sqdist(ops.to_dev(X1), ops.to_dev(X2)).cpu().numpy()
 
 
 def d(x1, x2):
