@@ -245,10 +245,14 @@ int ppbo_rff_objective(const double* Phi_X, long long ld, int F, int Q, int m, d
 /* omega_MAP (Hsampler.update_omega_MAP, src/random_fourier_sampler.py:124-132, replaces scipy trust-exact): Newton in
  * weight space with the exact clamped Hessian I + Psi' a+ Psi (F x F Cholesky) and backtracking; hess_diag[F] is the
  * reference's diagonal Hessian at the optimum (its Laplace covariance is 1 / -hess_diag, :134-137).
- * stats_h[4]: iterations, last relative step, S(omega_MAP). */
+ * factor_cache (may be NULL; ppbo_rff_factor_cache_doubles(F) doubles): persistent home of the Hessian factor; with
+ * warm_factor = 1 it holds the previous fit's factor and the iteration starts with chord steps from omega0 (a design that grew by
+ * one comparison set changes the F x F Hessian by a rank-m term).
+ * stats_h[4]: iterations, last relative step, S(omega_MAP), factorisations + chord steps / 1000. */
+long long ppbo_rff_factor_cache_doubles(int F);
 int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega0,
-                 int max_iter, double tol, double* omega_map, double* hess_diag, void* workspace,
-                 long long workspace_bytes, double* stats_h, void* stream);
+                 int max_iter, double tol, double* factor_cache, int warm_factor, double* omega_map, double* hess_diag,
+                 void* workspace, long long workspace_bytes, double* stats_h, void* stream);
 /* out[i] = standard normal number (offset + i) of Philox4x32-10 stream `stream_id` under `seed` (Box-Muller on 53-bit uniforms).
  * Counter-based: the value of a given index does not depend on launch shape or on which GPU draws it.  Replaces the host
  * np.random draws of the reference where the caller does not inject its own (oracle: oracle/ppbo_oracle.py philox_normals). */

@@ -739,16 +739,24 @@ extern "C" int ppbo_rff_objective(const double* Phi_X, long long ld, int F, int 
 /* omega_MAP = argmax S(omega) (Hsampler.update_omega_MAP, src/random_fourier_sampler.py:124-132): full Newton in weight
  * space with the exact (clamped) Hessian I + Psi' a+ Psi and a backtracking line search; also returns the DIAGONAL Hessian at the
  * optimum, which is what the reference's Laplace covariance uses (src/random_fourier_sampler.py:118-122,134-137). */
+extern "C" long long ppbo_rff_factor_cache_doubles(int F) { return ppbo_factor_doubles(F) + blockinv_doubles(F); }
+
 extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega0,
-                            int max_iter, double tol, double* omega_map, double* hess_diag, void* workspace,
-                            long long workspace_bytes, double* stats_h, void* stream) {
+                            int max_iter, double tol, double* factor_cache, int warm_factor, double* omega_map, double* hess_diag,
+                            void* workspace, long long workspace_bytes, double* stats_h, void* stream) {
     PPBO_REQUIRE(workspace_bytes >= ppbo_rff_workspace_bytes(F, Q, m), "workspace too small");
+    PPBO_REQUIRE(!warm_factor || (factor_cache != nullptr && omega0 != nullptr), "a warm factor needs the cache and omega0");
     cudaStream_t st = (cudaStream_t)stream;
     const int M = Q * m;
     RffWs ws;
     ws.carve((double*)workspace, F, Q, m);
+    if (factor_cache) {          // the Hessian factor (and its block inverses) live in the caller's persistent buffer
+        ws.H = factor_cache;
+        ws.binv = factor_cache + ppbo_factor_doubles(F);
+    }
     double* Hdinv = ws.H + (long long)F * F;
     int* info_d = reinterpret_cast<int*>(ws.scal + 32);
+    PPBO_CUDA_CHECK(cudaMemsetAsync(info_d, 0, sizeof(int), st));       // (a warm fit may never factorise)
     if (omega0) PPBO_CUDA_CHECK(cudaMemcpyAsync(omega_map, omega0, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
     else PPBO_CUDA_CHECK(cudaMemsetAsync(omega_map, 0, sizeof(double) * F, st));
     int rc, it = 0, info = 0, n_factor = 0, n_chord = 0;
@@ -757,7 +765,9 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
     double* part = ws.setlik + Q;                       // [LS_STEPS][Q]
     const double CHORD_REL = 0.25;
     const bool trace = getenv("PPBO_TRACE") != nullptr;
-    bool refactor = true, binv_valid = false;
+    // warm_factor: the cache holds the factor of the previous fit's Hessian (the design grew by a comparison set, omega0 is the
+    // previous optimum): start with chord steps, factorise only when they are damped or contract too slowly
+    bool refactor = !warm_factor, binv_valid = false;
     constexpr int RFF_BATCH_MAX = 8;
     double* state_d = ws.scal + 40;                     // [8] batch state, [16] history (scal holds 64 doubles)
     double* hist_d = ws.scal + 48;

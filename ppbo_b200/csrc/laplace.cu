@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
 //   * solves min_gamma | r_k - dR gamma |_2 (normal equations of order <= AA_M, Tikhonov-damped) and
 //   * replaces (alpha, f) by g_k - dG gamma   (f = Sigma alpha is preserved: both are the same combination).
 // The history is dropped when a step was damped / extrapolated / rejected, or when the residual grew.  One CTA, fixed order.
-constexpr int AA_M = 3;
+constexpr int AA_M = 5;
 //   aa: [0] history length, [1] next slot, [2] residual norm (max |df| / max |f|) seen by the previous call
 //   H: [3 * AA_M + 3][N]: dR[AA_M], dGf[AA_M], dGa[AA_M], prev r, prev g_f, prev g_a
 __global__ void __launch_bounds__(1024) chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f,

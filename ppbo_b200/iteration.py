@@ -283,14 +283,15 @@ class RFFState:
         self.W, self.b, self.theta, self.m, self.Q, self.Q_cap = W, b, [float(t) for t in theta], m, 0, Q_cap
         self.max_iter, self.tol = max_iter, tol
         self.Phi_cap = torch.empty((W.shape[0], Q_cap * (m + 1)), dtype=F64, device=W.device)
+        self.factor_cache = ops.rff_factor_cache(W.shape[0], W.device)
         self.fit = None
 
-    def _fit(self, Q, omega0):
+    def _fit(self, Q, omega0, warm=False):
         r = RFFFit()
         r.W, r.b, r.sigma_f = self.W, self.b, self.theta[2]
         r.Phi_X = self.Phi_cap[:, :Q * (self.m + 1)]
         r.omega_map, r.hess_diag, r.stats = ops.rff_fit(r.Phi_X, Q, self.m, self.theta[0], omega0=omega0, max_iter=self.max_iter,
-                                                        tol=self.tol)
+                                                        tol=self.tol, factor_cache=self.factor_cache, warm=warm)
         if r.stats["info"] != 0:
             raise PPBOError("RFF fit: weight-space Hessian not positive definite (info=%d)" % r.stats["info"])
         self.Q, self.fit = Q, r
@@ -306,7 +307,10 @@ class RFFState:
             return self.cold(X_block)
         N_old = self.Q * (self.m + 1)
         ops.rff_features(self.W, self.b, X_block, self.theta[2], True, out=self.Phi_cap[:, N_old:N_old + X_block.shape[0]])
-        return self._fit(self.Q + X_block.shape[0] // (self.m + 1), self.fit.omega_map)
+        warm = self.fit.stats.get("factorizations", 0) > 0 or self.fit.stats.get("warm", False)
+        r = self._fit(self.Q + X_block.shape[0] // (self.m + 1), self.fit.omega_map, warm=warm)
+        r.stats["warm"] = True              # the cache holds a factor from now on
+        return r
 
 
 def rff_start_from_gp(Phi_X, f_map, ridge=1e-3):

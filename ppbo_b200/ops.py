@@ -494,15 +494,22 @@ def rff_objective(Phi_X, Q, m, sigma, omega, want_S=True, want_grad=True, want_h
     return (S.value if want_S else None), grad, hd
 
 
-def rff_fit(Phi_X, Q, m, sigma, omega0=None, max_iter=100, tol=1e-10):
+def rff_factor_cache(F, dev):
+    """persistent buffer for the weight-space Hessian factor (rff_fit(..., factor_cache=..., warm=True) reuses it between fits)"""
+    return torch.empty(_lib.load().ppbo_rff_factor_cache_doubles(F) + 2, dtype=F64, device=dev)
+
+
+def rff_fit(Phi_X, Q, m, sigma, omega0=None, max_iter=100, tol=1e-10, factor_cache=None, warm=False):
     F = Phi_X.shape[0]
     ws, wbytes = _rff_ws(F, Q, m, Phi_X.device)
     omega = torch.empty(F, dtype=F64, device=Phi_X.device)
     hd = torch.empty(F, dtype=F64, device=Phi_X.device)
     stats = (ctypes.c_double * 4)()
     rc = check(_lib.load().ppbo_rff_fit(_p(Phi_X), Phi_X.stride(0), F, Q, m, float(sigma), _p(omega0), int(max_iter),
-                                        float(tol), _p(omega), _p(hd), _p(ws), wbytes, stats, _stream()), "ppbo_rff_fit")
-    return omega, hd, dict(iterations=int(stats[0]), last_rel_step=stats[1], S=stats[2], info=rc)
+                                        float(tol), _p(factor_cache), 1 if (warm and factor_cache is not None) else 0, _p(omega), _p(hd),
+                                        _p(ws), wbytes, stats, _stream()), "ppbo_rff_fit")
+    return omega, hd, dict(iterations=int(stats[0]), last_rel_step=stats[1], S=stats[2], info=rc,
+                           factorizations=int(stats[3]), chord_steps=int(round((stats[3] - int(stats[3])) * 1000)))
 
 
 def rff_eval_argmax(Omega, PhiT_grid, want_full=False):
