@@ -247,8 +247,10 @@ int ppbo_rff_objective(const double* Phi_X, long long ld, int F, int Q, int m, d
  * reference's diagonal Hessian at the optimum (its Laplace covariance is 1 / -hess_diag, :134-137).
  * factor_cache (may be NULL; ppbo_rff_factor_cache_doubles(F) doubles): persistent home of the Hessian factor; with
  * warm_factor = 1 it holds the previous fit's factor and the iteration starts with chord steps from omega0 (a design that grew by
- * one comparison set changes the F x F Hessian by a rank-m term).
- * stats_h[4]: iterations, last relative step, S(omega_MAP), factorisations + chord steps / 1000. */
+ * one comparison set changes the F x F Hessian by a rank-m term); warm_factor = 2: its 1024-block inverses are in the cache too.
+ * Chord steps are Anderson-mixed (depth 5).
+ * stats_h[5]: iterations, last relative step, S(omega_MAP), factorisations + chord steps / 1000, 1 if the cache's block inverses are
+ * valid for the cache's factor on return. */
 long long ppbo_rff_factor_cache_doubles(int F);
 int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega0,
                  int max_iter, double tol, double* factor_cache, int warm_factor, double* omega_map, double* hess_diag,

@@ -351,6 +351,36 @@ __global__ void __launch_bounds__(256) rff_grad_hess_kernel(const double* __rest
         if (hdiag) hdiag[f] = -1.0 - h;
     }
 }
+// grad[f] = -omega[f] + sum_rows beta[row] Phi[f][row]: four warps per feature (a quarter of the row each), two features per CTA.
+// One warp per feature (rff_grad_hess_kernel) leaves 125 CTAs of 8 long-running warps for F = 1000: 26-80 us per call in the chord
+// steps of the fit, latency-bound; this shape streams the same 8 F N bytes with 4x the loads in flight.
+__global__ void __launch_bounds__(256) rff_grad_kernel(const double* __restrict__ Phi, long long ld, int F, int N,
+                                                       const double* __restrict__ omega, const double* __restrict__ beta,
+                                                       double* __restrict__ grad, const double* __restrict__ skip) {
+    __shared__ double part[8];
+    if (skip && *skip != 0.0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * 2 + (warp >> 2), qtr = warp & 3;
+    double g0 = 0.0, g1 = 0.0;
+    if (f < F) {
+        const double* ph = Phi + (long long)f * ld;
+        const int per = ((N + 3) / 4 + 31) / 32 * 32, i0 = qtr * per, i1 = min(N, i0 + per);
+        int i = i0 + lane;
+        for (; i + 32 < i1; i += 64) {
+            g0 = fma(beta[i], ph[i], g0);
+            g1 = fma(beta[i + 32], ph[i + 32], g1);
+        }
+        if (i < i1) g0 = fma(beta[i], ph[i], g0);
+    }
+    double g = g0 + g1;
+    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    if (lane == 0) part[warp] = g;
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int ff = blockIdx.x * 2 + threadIdx.x;
+        if (ff < F) grad[ff] = -omega[ff] + ((part[4 * threadIdx.x] + part[4 * threadIdx.x + 1]) + (part[4 * threadIdx.x + 2] + part[4 * threadIdx.x + 3]));
+    }
+}
 // PsiT[f][u] = sa[u] (Phi[f][r(u)] - Phi[f][w(u)])     (F x M, K-contiguous operand of the weight-space Hessian GEMM)
 __global__ void __launch_bounds__(256) rff_psi_kernel(const double* __restrict__ Phi, long long ld, int Q, int m,
                                                       const double* __restrict__ arrow, double* __restrict__ PsiT, long long ldp) {
@@ -442,39 +472,142 @@ __global__ void __launch_bounds__(1024) rff_ls_scalars_kernel(const double* __re
 
 // Device-side acceptance test of one weight-space chord step (same scheme as chord_decide_kernel of laplace.cu): the full step is
 // taken when S does not fall, convergence and contraction are tested here, and the host synchronises once per batch.
-//   state[0] S at the current iterate  state[1] relative size of the last step  state[2] the one before
+//   state[0] S after the last accepted step  state[1] relative size of the last step  state[2] the one before  state[3] the one before that
 //   state[4] 0 = keep going, 1 = converged, 2 = contraction too slow (refactor), 3 = full step rejected (refactor)
-//   state[5] chord steps taken in this batch   state[6] tolerance    hist[2i], hist[2i+1] = (rel, S) of step i
-// scal: output of rff_ls_scalars_kernel for this step.
+//   state[5] chord steps taken in this batch   state[6] tolerance    state[7] 1 = this call took the full step (rff_anderson_kernel)
+//   hist[2i], hist[2i+1] = (rel, S) of step i
+// scal: output of rff_ls_scalars_kernel for this step; scal[24] the likelihood sum at the current iterate (rff_eval), from which S at
+// the current iterate is recomputed every step (the iterate may have been mixed since the last accepted step).
+// anderson: the steps of this batch are mixed (rff_anderson_kernel); mixed steps are not monotone step by step, so the contraction
+// is judged over three steps (a chord step costs ~1/10 of a refactorisation: three steps must gain a factor 5).
 __global__ void __launch_bounds__(256) rff_chord_decide_kernel(double* __restrict__ omega, const double* __restrict__ step, int F,
                                                                const double* __restrict__ scal, int m, double* __restrict__ state,
-                                                               double* __restrict__ hist) {
+                                                               double* __restrict__ hist, int anderson) {
     __shared__ int accept_s;
     if (state[4] != 0.0) return;
     if (threadIdx.x == 0) {
         const double oo = scal[0], od = scal[1], dd = scal[2], max_step = scal[3], max_om = fmax(scal[4], 1e-300);
-        const double S_cur = state[0];
+        const double S_cur = -0.5 * oo - scal[24] / m;
         const double S1 = -0.5 * (oo + 2.0 * od + dd) - scal[8] / m;
         const int accept = S1 >= S_cur - 1e-13 * fabs(S_cur);
         accept_s = accept;
+        state[7] = accept ? 1.0 : 0.0;
         if (!accept) {
             state[4] = 3.0;
         } else {
-            const double rel = max_step / max_om, prev = state[1];
+            const double rel = max_step / max_om, prev = state[1], rel3 = state[3];
             const int n = (int)state[5];
             state[0] = S1;
+            state[3] = state[2];
             state[2] = prev;
             state[1] = rel;
             state[5] = n + 1;
             hist[2 * n] = rel;
             hist[2 * n + 1] = S1;
             if (rel <= state[6]) state[4] = 1.0;
+            else if (anderson) { if (rel3 < 1e300 && !(rel <= 0.2 * rel3)) state[4] = 2.0; }
             else if (!(rel <= 0.5 * prev)) state[4] = 2.0;
         }
     }
     __syncthreads();
     if (!accept_s) return;
     for (int i = threadIdx.x; i < F; i += blockDim.x) omega[i] += step[i];
+}
+
+// Anderson acceleration of the weight-space chord iteration omega <- g(omega) = omega + (-H0)^-1 grad S(omega) (depth RAA_M; same
+// scheme as chord_anderson_kernel of laplace.cu).  With the clamped Hessian the iteration matrix differs from the true Hessian by the
+// negative curvature coefficients, so even a factor built next to the optimum contracts only linearly (0.3 .. 0.45 per step on the
+// bench problem, 0.55 for the factor of the previous PPBO iteration); mixing the last residual differences gains about
+// rho / (1 + sqrt(1 - rho^2)) per step instead.  Called after rff_chord_decide_kernel has taken a full step: omega = g(omega_k),
+// residual r_k = step still in memory.  The history is dropped when a step was rejected or the residual grew.  One CTA, fixed order.
+//   aa: [0] history length, [1] next slot, [2] residual norm seen by the previous call, [3] 1 = (prev r, prev g) valid
+//   Hh: [2 RAA_M + 2][F]: dR[RAA_M], dG[RAA_M], prev r, prev g
+constexpr int RAA_M = 5;
+__global__ void __launch_bounds__(1024) rff_anderson_kernel(double* __restrict__ omega, const double* __restrict__ step, int F,
+                                                            const double* __restrict__ state, double* __restrict__ aa,
+                                                            double* __restrict__ Hh) {
+    __shared__ double red[33];
+    __shared__ double gam[RAA_M];
+    __shared__ int nh_s;
+    if (state[4] != 0.0) return;                                         // converged, rejected or about to refactor: nothing to mix
+    double* dR = Hh;
+    double* dG = Hh + (long long)RAA_M * F;
+    double* pr = Hh + 2LL * RAA_M * F;
+    double* pg = pr + F;
+    const bool plain = state[7] == 1.0;
+    const double rel = state[1];
+    int nh = (int)aa[0], slot = (int)aa[1];
+    const double rel_prev = aa[2];
+    bool have_prev = aa[3] == 1.0;
+    __syncthreads();                                                     // everybody has read the state
+    if (!plain || (have_prev && rel > 1.5 * rel_prev)) {
+        if (threadIdx.x == 0) { aa[0] = 0.0; aa[1] = 0.0; aa[2] = rel; aa[3] = 0.0; }
+        if (!plain) return;
+        nh = 0;
+        slot = 0;
+        have_prev = false;
+    }
+    if (have_prev) {
+        for (int i = threadIdx.x; i < F; i += 1024) {
+            dR[(long long)slot * F + i] = step[i] - pr[i];
+            dG[(long long)slot * F + i] = omega[i] - pg[i];
+        }
+        nh = min(nh + 1, RAA_M);
+        slot = (slot + 1) % RAA_M;
+    }
+    for (int i = threadIdx.x; i < F; i += 1024) {
+        pr[i] = step[i];
+        pg[i] = omega[i];
+    }
+    __syncthreads();
+    double A[RAA_M][RAA_M], bb[RAA_M];
+    for (int i = 0; i < nh; ++i) {
+        for (int j = 0; j <= i; ++j) {
+            double sacc = 0.0;
+            for (int k = threadIdx.x; k < F; k += 1024) sacc = fma(dR[(long long)i * F + k], dR[(long long)j * F + k], sacc);
+            A[i][j] = A[j][i] = block_sum(sacc, red);
+        }
+        double sacc = 0.0;
+        for (int k = threadIdx.x; k < F; k += 1024) sacc = fma(dR[(long long)i * F + k], step[k], sacc);
+        bb[i] = block_sum(sacc, red);
+    }
+    if (threadIdx.x == 0) {
+        double tr = 0.0;
+        for (int i = 0; i < nh; ++i) tr += A[i][i];
+        for (int i = 0; i < nh; ++i) A[i][i] += 1e-10 * tr + 1e-300;     // damping: nearly collinear differences
+        bool ok = true;
+        for (int c = 0; c < nh && ok; ++c) {                             // Gaussian elimination with partial pivoting
+            int pv = c;
+            for (int r2 = c + 1; r2 < nh; ++r2) if (fabs(A[r2][c]) > fabs(A[pv][c])) pv = r2;
+            if (A[pv][c] == 0.0) { ok = false; break; }
+            for (int k = 0; k < nh; ++k) { const double t = A[c][k]; A[c][k] = A[pv][k]; A[pv][k] = t; }
+            { const double t = bb[c]; bb[c] = bb[pv]; bb[pv] = t; }
+            for (int r2 = c + 1; r2 < nh; ++r2) {
+                const double l = A[r2][c] / A[c][c];
+                for (int k = c; k < nh; ++k) A[r2][k] -= l * A[c][k];
+                bb[r2] -= l * bb[c];
+            }
+        }
+        for (int i = nh - 1; i >= 0 && ok; --i) {
+            double v = bb[i];
+            for (int k = i + 1; k < nh; ++k) v -= A[i][k] * gam[k];
+            gam[i] = v / A[i][i];
+            if (!(fabs(gam[i]) < 1e3)) ok = false;
+        }
+        nh_s = ok ? nh : 0;
+        aa[0] = ok ? nh : 0;
+        aa[1] = ok ? slot : 0;
+        aa[2] = rel;
+        aa[3] = 1.0;
+    }
+    __syncthreads();
+    const int nm = nh_s;
+    if (nm == 0) return;
+    for (int i = threadIdx.x; i < F; i += 1024) {
+        double c = 0.0;
+        for (int j = 0; j < nm; ++j) c = fma(gam[j], dG[(long long)j * F + i], c);
+        omega[i] -= c;
+    }
 }
 
 }  // namespace ppbo
@@ -487,8 +620,8 @@ extern "C" long long ppbo_factor_doubles(int n) { return (long long)n * n + potr
 /* number of negative arrow coefficients and their indices (host sync).  idx_h may be NULL. */
 extern "C" int ppbo_neg_count(const double* arrow, int M, int* idx_h, int idx_capacity, void* stream) {
     std::vector<double> a((size_t)M);
-    if (cudaMemcpyAsync(a.data(), arrow, sizeof(double) * M, cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
-        cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    if (readback().add(a.data(), arrow, sizeof(double) * M, (cudaStream_t)stream) != cudaSuccess ||
+        readback().finish((cudaStream_t)stream) != cudaSuccess) {
         set_error("ppbo_neg_count: copy failed");
         return PPBO_ERR_CUDA;
     }
@@ -524,8 +657,8 @@ extern "C" int ppbo_neg_corr_build(const double* G, long long ldg, int M, const 
     if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
     if ((rc = potrf_lower(R, r, r, Rdinv, info_d, st))) return rc;
     int info = 0;
-    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    PPBO_CUDA_CHECK(readback().add(&info, info_d, sizeof(int), st));
+    PPBO_CUDA_CHECK(readback().finish(st));
     if (info) { set_error("posterior precision is not positive definite (negative-coefficient block, pivot %d)", info); return info; }
     return PPBO_OK;
 }
@@ -680,11 +813,11 @@ extern "C" int ppbo_rff_maximize(const double* W, const double* b, int F, int D,
 extern "C" long long ppbo_rff_workspace_bytes(int F, int Q, int m) {
     const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
     return ((3 + FV_SLICES) * N + 2 * M + Q * 9 + 64 + (long long)F * M + ppbo_factor_doubles(F) + 4 * (long long)F + 2 * CHOL_NB +
-            blockinv_doubles(F)) * 8;
+            blockinv_doubles(F) + (2LL * RAA_M + 2) * F + 8) * 8;
 }
 
 struct RffWs {
-    double *fvals, *dfv, *fpart, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp, *binv;
+    double *fvals, *dfv, *fpart, *beta, *arrow, *setlik, *scal, *PsiT, *H, *grad, *step, *trial, *tmp, *binv, *aaH, *aa;
     void carve(double* p, int F, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
         fvals = p; p += N;
@@ -700,6 +833,8 @@ struct RffWs {
         step = p; p += F + CHOL_NB;
         trial = p; p += F;
         tmp = p; p += F;
+        aaH = p; p += (2LL * RAA_M + 2) * F;
+        aa = p; p += 8;
         binv = p;
     }
 };
@@ -710,7 +845,9 @@ static int rff_eval(const double* Phi, long long ld, int F, int Q, int m, double
     launch_rff_fvals(Phi, ld, F, N, omega, ws.fpart, ws.fvals, st, skip);
     launch_lik_terms(ws.fvals, Q, m, sigma, ws.setlik, ws.beta, want_arrow ? ws.arrow : nullptr, nullptr, nullptr, st);
     launch_sum(ws.setlik, Q, lik_sum_dev, st);
-    if (grad || hdiag)
+    if (grad && !hdiag)
+        PPBO_CL rff_grad_kernel<<<ceil_div(F, 2), 256, 0, st>>>(Phi, ld, F, N, omega, ws.beta, grad, skip);
+    else if (grad || hdiag)
         PPBO_CL rff_grad_hess_kernel<<<ceil_div(F, 8), 256, 0, st>>>(Phi, ld, F, Q, m, omega, ws.beta, ws.arrow, grad, hdiag, skip);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
@@ -729,8 +866,8 @@ extern "C" int ppbo_rff_objective(const double* Phi_X, long long ld, int F, int 
     if (S_out) {
         PPBO_CL rff_scalars_kernel<<<1, 1024, 0, st>>>(omega, nullptr, F, ws.scal);
         double h[9];
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(h), cudaMemcpyDeviceToHost, st));
-        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        PPBO_CUDA_CHECK(readback().add(h, ws.scal, sizeof(h), st));
+        PPBO_CUDA_CHECK(readback().finish(st));
         *S_out = h[0] - h[8] / m;
     }
     return PPBO_OK;
@@ -766,15 +903,19 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
     const double CHORD_REL = 0.25;
     const bool trace = getenv("PPBO_TRACE") != nullptr;
     // warm_factor: the cache holds the factor of the previous fit's Hessian (the design grew by a comparison set, omega0 is the
-    // previous optimum): start with chord steps, factorise only when they are damped or contract too slowly
-    bool refactor = !warm_factor, binv_valid = false;
+    // previous optimum): start with chord steps, factorise only when they are rejected or contract too slowly.  warm_factor = 2: the
+    // 1024-block inverses of that factor are in the cache as well.
+    bool refactor = !warm_factor, binv_valid = warm_factor == 2;
     constexpr int RFF_BATCH_MAX = 8;
     double* state_d = ws.scal + 40;                     // [8] batch state, [16] history (scal holds 64 doubles)
     double* hist_d = ws.scal + 48;
-    double prev_rel_h = INFINITY;
+    double prev_rel_h = INFINITY, rel3_h = INFINITY;
     bool first_batch = true;
+    // PPBO_RFF_ANDERSON=0: plain chord steps (diagnostics)
+    const bool anderson = !(getenv("PPBO_RFF_ANDERSON") && atoi(getenv("PPBO_RFF_ANDERSON")) == 0);
+    PPBO_CUDA_CHECK(cudaMemsetAsync(ws.aa, 0, sizeof(double) * 8, st));
     for (it = 0; it < max_iter; ++it) {
-        if (!refactor && !std::isnan(S_cur)) {
+        if (!refactor) {
             // ---- a batch of chord steps with the device-side acceptance test: one host synchronise per batch (a host decision per
             // step cost ~0.29 ms per step for ~0.1 ms of kernels)
             if (!binv_valid) {
@@ -782,12 +923,12 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
                 binv_valid = true;
             }
             double rho = (std::isfinite(prev_rel_h) && last_rel < prev_rel_h) ? last_rel / prev_rel_h : 0.2;
-            rho = std::fmin(std::fmax(rho, 0.02), 0.5);
-            int kb = (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
+            rho = std::fmin(std::fmax(rho, 0.02), anderson ? 0.7 : 0.5);
+            int kb = !std::isfinite(last_rel) ? 3 : (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
             if (first_batch) kb = std::min(kb, 3);
             kb = std::max(1, std::min(kb, std::min(RFF_BATCH_MAX, max_iter - it)));
             first_batch = false;
-            double state_h[8] = {S_cur, last_rel, prev_rel_h, 0.0, 0.0, 0.0, tol, 0.0}, hist_h[2 * RFF_BATCH_MAX];
+            double state_h[8] = {S_cur, last_rel, prev_rel_h, rel3_h, 0.0, 0.0, tol, 0.0}, hist_h[2 * RFF_BATCH_MAX];
             PPBO_CUDA_CHECK(cudaMemcpyAsync(state_d, state_h, sizeof(state_h), cudaMemcpyHostToDevice, st));
             const double* skip = state_d + 4;
             for (int i = 0; i < kb; ++i) {
@@ -797,22 +938,25 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
                 launch_rff_fvals(Phi_X, ld, F, N, ws.step, ws.fpart, ws.dfv, st, skip);
                 if ((rc = launch_linesearch_lik(ws.fvals, ws.dfv, Q, m, sigma, part, st))) return rc;
                 PPBO_CL rff_ls_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, part, Q, ws.scal);
-                PPBO_CL rff_chord_decide_kernel<<<1, 256, 0, st>>>(omega_map, ws.step, F, ws.scal, m, state_d, hist_d);
+                PPBO_CL rff_chord_decide_kernel<<<1, 256, 0, st>>>(omega_map, ws.step, F, ws.scal, m, state_d, hist_d, anderson ? 1 : 0);
+                if (anderson) PPBO_CL rff_anderson_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, state_d, ws.aa, ws.aaH);
             }
             PPBO_LAUNCH_CHECK();
-            PPBO_CUDA_CHECK(cudaMemcpyAsync(state_h, state_d, sizeof(state_h), cudaMemcpyDeviceToHost, st));
-            PPBO_CUDA_CHECK(cudaMemcpyAsync(hist_h, hist_d, sizeof(double) * 2 * kb, cudaMemcpyDeviceToHost, st));
-            PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+            PPBO_CUDA_CHECK(readback().add(state_h, state_d, sizeof(state_h), st));
+            PPBO_CUDA_CHECK(readback().add(hist_h, hist_d, sizeof(double) * 2 * kb, st));
+            PPBO_CUDA_CHECK(readback().finish(st));
             const int taken = (int)state_h[5], stop = (int)state_h[4];
             if (trace)
                 for (int i = 0; i < taken; ++i)
                     fprintf(stderr, "[ppbo_rff_fit] it %d chord  step 1 rel %.3e S %.12g (batch of %d)\n", it + i, hist_h[2 * i], hist_h[2 * i + 1], kb);
             n_chord += taken;
             if (taken > 0) {
-                S_cur = state_h[0];
                 last_rel = state_h[1];
                 prev_rel_h = state_h[2];
+                rel3_h = state_h[3];
             }
+            // S after the last accepted step; stale once that step's result has been mixed (every accepted step but a converging one)
+            S_cur = (stop == 1 || !anderson) ? (taken > 0 ? state_h[0] : S_cur) : NAN;
             it += taken;
             if (stop == 1) break;
             if (stop == 2 || stop == 3) refactor = true;
@@ -830,6 +974,8 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
             if ((rc = potrf_lower(ws.H, F, F, Hdinv, info_d, st))) return rc;
             ++n_factor;
             binv_valid = false;
+            PPBO_CUDA_CHECK(cudaMemsetAsync(ws.aa, 0, sizeof(double) * 8, st));     // new iteration matrix: forget the mixing history
+            rel3_h = INFINITY;
         } else {
             ++n_chord;
             if (!binv_valid) {            // the factor is about to be reused: invert its diagonal blocks once (linalg.cu)
@@ -846,9 +992,9 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
         if ((rc = launch_linesearch_lik(ws.fvals, ws.dfv, Q, m, sigma, part, st))) return rc;
         PPBO_CL rff_ls_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, ws.step, F, part, Q, ws.scal);
         PPBO_LAUNCH_CHECK();
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
-        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        PPBO_CUDA_CHECK(readback().add(h, ws.scal, sizeof(double) * 32, st));
+        PPBO_CUDA_CHECK(readback().add(&info, info_d, sizeof(int), st));
+        PPBO_CUDA_CHECK(readback().finish(st));
         if (info) { set_error("weight-space Hessian not positive definite (pivot %d)", info); return info; }
         const double oo = h[0], od = h[1], dd = h[2], max_step = h[3], max_om = fmax(h[4], 1e-300);
         if (std::isnan(S_cur)) S_cur = -0.5 * oo - h[24] / m;
@@ -879,15 +1025,18 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
     if (std::isnan(S_cur)) {                             // last step left S unevaluated: evaluate at the final point
         if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, nullptr, nullptr, false, ws.scal + 24, st))) return rc;
         PPBO_CL rff_scalars_kernel<<<1, 1024, 0, st>>>(omega_map, nullptr, F, ws.scal);
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
-        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        PPBO_CUDA_CHECK(readback().add(h, ws.scal, sizeof(double) * 32, st));
+        PPBO_CUDA_CHECK(readback().finish(st));
         S_cur = h[0] - h[24] / m;
     }
     if (hess_diag) {
         if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, nullptr, hess_diag, true, ws.scal + 24, st))) return rc;
     }
-    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (stats_h) { stats_h[0] = it; stats_h[1] = last_rel; stats_h[2] = S_cur; stats_h[3] = n_factor + 0.001 * n_chord; }
+    PPBO_CUDA_CHECK(readback().finish(st));
+    if (stats_h) {
+        stats_h[0] = it; stats_h[1] = last_rel; stats_h[2] = S_cur; stats_h[3] = n_factor + 0.001 * n_chord;
+        stats_h[4] = (binv_valid && factor_cache) ? 1.0 : 0.0;      // the cache's block inverses belong to the cache's factor
+    }
     return PPBO_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 
 #define PPBO_MAX_D 64          // max problem dimension carried by value in kernel params
 #define PPBO_SM_COUNT 148      // B200
@@ -35,6 +36,41 @@ extern long long g_launch_count;   // kernels launched by this library (bench.py
             return PPBO_ERR_ARG;                                  \
         }                                                         \
     } while (0)
+
+// Readback of a few scalars through PINNED host memory.  cudaMemcpyAsync into pageable memory (a stack variable) only returns when
+// the stream has reached the copy, and the driver keeps a context lock while it waits: the launches of every other host thread
+// stall for that time.  Two host-driven fits on two threads paid for this with each other's batch lengths (weight-space fit: 6 ms
+// next to the GP fit against 3 ms alone).  With a pinned destination the call returns at once and the wait happens in
+// cudaStreamSynchronize.  One staging buffer per host thread; add() .. add() finish() must not be interleaved with another stream's.
+struct PinnedReadback {
+    static constexpr size_t CAP = 1 << 16;
+    char* buf = nullptr;
+    size_t used = 0;
+    struct Item { void* dst; size_t off, bytes; } items[16];
+    int n = 0;
+    cudaError_t add(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
+        if (!buf && cudaHostAlloc(reinterpret_cast<void**>(&buf), CAP, cudaHostAllocDefault) != cudaSuccess) {
+            buf = nullptr;
+            (void)cudaGetLastError();
+        }
+        const size_t need = (bytes + 15) & ~size_t(15);
+        if (!buf || n == 16 || used + need > CAP) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st);   // pageable fallback
+        const cudaError_t e = cudaMemcpyAsync(buf + used, src_dev, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) {                 // (a failed call leaves nothing behind for the next finish())
+            items[n++] = Item{dst, used, bytes};
+            used += need;
+        }
+        return e;
+    }
+    cudaError_t finish(cudaStream_t st) {
+        const cudaError_t e = cudaStreamSynchronize(st);
+        for (int i = 0; i < n; ++i) memcpy(items[i].dst, buf + items[i].off, items[i].bytes);
+        n = 0;
+        used = 0;
+        return e;
+    }
+};
+PinnedReadback& readback();        // the calling host thread's staging buffer (linalg.cu)
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -756,9 +756,9 @@ extern "C" int ppbo_laplace_refactor(const double* G, long long ldg, int M, cons
     if ((rc = newton_matrix(G, ldg, M, sa_fac, Lfac, cap, st))) return rc;
     if ((rc = potrf_lower(Lfac, cap, M, dinv, info_d, st))) return rc;
     int info = 0;
-    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(readback().add(&info, info_d, sizeof(int), st));
     PPBO_CUDA_CHECK(cudaFreeAsync(info_d, st));
-    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    PPBO_CUDA_CHECK(readback().finish(st));
     if (info) set_error("mode system not positive definite at pivot %d", info);
     return info;
 }
@@ -798,9 +798,9 @@ extern "C" int ppbo_factor_extend(const double* G, long long ldg, int M_old, int
     if ((rc = potrf_lower(Lfac + (long long)b0 * cap + b0, cap, nt, dinv + (long long)(b0 / CHOL_NB) * CHOL_NB * CHOL_NB, info_d, st)))
         return rc;
     int info = 0;
-    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PPBO_CUDA_CHECK(readback().add(&info, info_d, sizeof(int), st));
     PPBO_CUDA_CHECK(cudaFreeAsync(info_d, st));
-    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    PPBO_CUDA_CHECK(readback().finish(st));
     if (info) { info += b0; set_error("extended factor not positive definite at pivot %d", info); }
     return info;
 }
@@ -902,8 +902,8 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         PPBO_CL sum_kernel<<<1, 1024, 0, st>>>(ws.arrow_tmp, Q, ws.scal + 24);
         PPBO_CL dot_kernel<<<1, 1024, 0, st>>>(alpha, f_map, N, ws.scal);
         PPBO_LAUNCH_CHECK();
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(scal_h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
-        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        PPBO_CUDA_CHECK(readback().add(scal_h, ws.scal, sizeof(double) * 32, st));
+        PPBO_CUDA_CHECK(readback().finish(st));
         T_cur = -0.5 * scal_h[0] - scal_h[24] / m;
         last_rel = INFINITY;                 // unknown yet: the first batch (3 steps) measures the contraction
         factor_current = !bordered;          // a bordered factor is not a factor object of the whole system (finalised below)
@@ -963,9 +963,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 if (anderson) PPBO_CL chord_anderson_kernel<<<1, 1024, 0, st>>>(alpha, f_map, ws.df, N, ws.state, ws.aa, ws.aaH);
             }
             PPBO_LAUNCH_CHECK();
-            PPBO_CUDA_CHECK(cudaMemcpyAsync(state_h, ws.state, sizeof(state_h), cudaMemcpyDeviceToHost, st));
-            PPBO_CUDA_CHECK(cudaMemcpyAsync(hist_h, ws.hist, sizeof(double) * 2 * kb, cudaMemcpyDeviceToHost, st));
-            PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+            PPBO_CUDA_CHECK(readback().add(state_h, ws.state, sizeof(state_h), st));
+            PPBO_CUDA_CHECK(readback().add(hist_h, ws.hist, sizeof(double) * 2 * kb, st));
+            PPBO_CUDA_CHECK(readback().finish(st));
             const int taken = (int)state_h[5], stop = (int)state_h[4];
             if (trace)
                 for (int i = 0; i < taken; ++i)
@@ -1027,8 +1027,8 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             PPBO_CUDA_CHECK(cudaMemcpyAsync(alpha, ws.dalpha, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
             PPBO_CUDA_CHECK(cudaMemcpyAsync(f_map, ws.df, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
             alpha_known = true;
-            PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
-            PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+            PPBO_CUDA_CHECK(readback().add(&info, ws.info, sizeof(int), st));
+            PPBO_CUDA_CHECK(readback().finish(st));
             if (info) { set_error("Newton system not positive definite at pivot %d (iteration %d)", info, it); return info; }
             ++it;
             continue;
@@ -1041,9 +1041,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         }
         PPBO_CL newton_scalars_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, ws.scal);
         PPBO_LAUNCH_CHECK();
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(scal_h, ws.scal, sizeof(double) * 32, cudaMemcpyDeviceToHost, st));
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
-        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        PPBO_CUDA_CHECK(readback().add(scal_h, ws.scal, sizeof(double) * 32, st));
+        PPBO_CUDA_CHECK(readback().add(&info, ws.info, sizeof(int), st));
+        PPBO_CUDA_CHECK(readback().finish(st));
         if (info) { set_error("Newton system not positive definite at pivot %d (iteration %d)", info, it); return info; }
         const double af = scal_h[0], adf = scal_h[1], daf = scal_h[2], dadf = scal_h[3];
         if (std::isnan(T_cur)) T_cur = -0.5 * af - scal_h[24] / m;
@@ -1088,8 +1088,8 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         }
         if ((rc = potrf_lower(Lfac + (long long)b0 * ldl + b0, ldl, nt, Mdinv + (long long)(b0 / CHOL_NB) * CHOL_NB * CHOL_NB, ws.info, st)))
             return rc;
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
-        PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+        PPBO_CUDA_CHECK(readback().add(&info, ws.info, sizeof(int), st));
+        PPBO_CUDA_CHECK(readback().finish(st));
         factor_current = info == 0;
         info = 0;
     }
@@ -1117,9 +1117,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         ++n_factor;
         have_factor = true;
         if (sa_fac) PPBO_CUDA_CHECK(cudaMemcpyAsync(sa_fac, ws.sa, sizeof(double) * M, cudaMemcpyDeviceToDevice, st));
-        PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PPBO_CUDA_CHECK(readback().add(&info, ws.info, sizeof(int), st));
     }
-    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    PPBO_CUDA_CHECK(readback().finish(st));
     if (stats_h) {
         stats_h[0] = it;
         stats_h[1] = last_step;

@@ -62,6 +62,11 @@ static bool operands_vec2(const GemmOperands& g) {
            g.strideA2 % 2 == 0 && g.strideB2 % 2 == 0;
 }
 
+PinnedReadback& readback() {
+    static thread_local PinnedReadback r;
+    return r;
+}
+
 static thread_local bool g_launch_pdl = false;      // set by potrf_lower around the launches of its critical path
 
 template <class Cfg>
@@ -1771,9 +1776,9 @@ int lu_logdet(double* A, long long lda, int n, double* ws, double* res_h, cudaSt
     PPBO_LAUNCH_CHECK();
     double h[2];
     int sh[2];
-    PPBO_CUDA_CHECK(cudaMemcpyAsync(h, outd, sizeof(h), cudaMemcpyDeviceToHost, st));
-    PPBO_CUDA_CHECK(cudaMemcpyAsync(sh, stat, sizeof(sh), cudaMemcpyDeviceToHost, st));
-    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    PPBO_CUDA_CHECK(readback().add(h, outd, sizeof(h), st));
+    PPBO_CUDA_CHECK(readback().add(sh, stat, sizeof(sh), st));
+    PPBO_CUDA_CHECK(readback().finish(st));
     res_h[0] = h[0];
     res_h[1] = h[1];
     res_h[2] = (sh[0] % 2 == 0) ? 1.0 : -1.0;
@@ -1844,8 +1849,8 @@ extern "C" int ppbo_potrf_lower(double* A, long long lda, int n, void* workspace
     int rc = potrf_lower(A, lda, n, dinv, info_d, st);
     if (rc) return rc;
     int info = 0;
-    PPBO_CUDA_CHECK(cudaMemcpyAsync(&info, info_d, sizeof(int), cudaMemcpyDeviceToHost, st));
-    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    PPBO_CUDA_CHECK(readback().add(&info, info_d, sizeof(int), st));
+    PPBO_CUDA_CHECK(readback().finish(st));
     if (info_h) *info_h = info;
     return info;
 }

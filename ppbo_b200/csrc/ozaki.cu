@@ -17,11 +17,13 @@
 // replace one FP64 GEMM; the result is a deterministic function of the inputs (no dependence on tile shape, launch shape or
 // rank), which the oracle reproduces bit for bit with integer arithmetic (oracle/ppbo_oracle.py ozaki_*).
 //
-// Kernel structure (one persistent CTA per SM, 192 threads):
+// Kernel structure (one persistent CTA per SM, 320 threads):
 //   warp 0      producer: one cp.async.bulk per operand and k-block (the digit planes are stored in HBM already in the
 //               shared-memory image the tensor core reads, see slice layout below) -> 3-stage mbarrier ring
 //   warp 1      one elected lane issues tcgen05.mma.kind::i8 (M=128, N=BN, K=32): KS accumulators of BN columns in TMEM
-//   warps 2..5  epilogue: tcgen05.ld the KS INT32 accumulators, recombine in INT64 -> FP64, scale, running row max/arg-max
+//   warps 2..9  epilogue: tcgen05.ld the KS INT32 accumulators, recombine in INT64 -> FP64, scale, running row max/arg-max.
+//               Two warps per TMEM lane quarter, each takes one half of the tile's columns: the accumulators are single-buffered
+//               (KS BN = 384 of 512 TMEM columns), so the epilogue is exposed and its length, not its throughput, is what counts
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -41,6 +43,9 @@ constexpr int UMMA_K = 32;                   // K of one tcgen05.mma.kind::i8
 constexpr int LBO = 128;                     // byte distance of K-adjacent 8 x 16 B core matrices
 constexpr int SBO = (KB / 16) * 128;         // byte distance of 8-row groups
 constexpr int MAX_KS = 7;
+constexpr int EPI_WARPS = 8;                 // two per TMEM lane quarter (warp w may only read lanes 32 (w & 3) ..)
+constexpr int THREADS = 64 + 32 * EPI_WARPS; // producer warp + MMA warp + epilogue warps
+constexpr int MERGE_BYTES = 2 * BM * 12;     // (max, arg) of the upper column half, double-buffered over work items
 
 // Slice layout in HBM for an operand of `batch` matrices with rows padded to tiles of TR rows and K padded to KBLK blocks of
 // KB bytes:  plane(b, rt, kb, s) is a contiguous TR x KB byte block at  ((((b NT + rt) KBLK + kb) KS + s) TR KB, stored in the
@@ -319,12 +324,12 @@ struct Cfg {
     static constexpr int A_PLANE = BM * KB, B_PLANE = BN * KB;
     static constexpr int A_STAGE = KS * A_PLANE, B_STAGE = KS * B_PLANE;
     static constexpr int STAGE_BYTES = A_STAGE + B_STAGE;
-    static constexpr int STAGES = (3 * STAGE_BYTES + 256 <= 232448) ? 3 : 2;
+    static constexpr int STAGES = (3 * STAGE_BYTES + 256 + MERGE_BYTES <= 232448) ? 3 : 2;
     static constexpr int A_TMEM_COLS = TS ? KS * (KB / 4) : 0;      // KB bytes per lane and plane, 4 per column
     static constexpr int TMEM_A0 = KS * BN;                         // first column of the A planes
     static constexpr int TMEM_USED = KS * BN + A_TMEM_COLS;
     static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 256;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 256 + MERGE_BYTES;
     static constexpr int G1 = KS < 3 ? KS : 3;               // accumulators recombined into the high INT64 word
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a/b format INT8 = 1 @7/@10, K-major A and B,
     // N >> 3 @17, M >> 4 @24
@@ -405,7 +410,7 @@ __device__ __forceinline__ void epi_columns(const uint32_t (&acc)[KS][NC], const
 }
 
 template <int KS, int BN, bool TS>
-__global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS, 1) ozaki_rowmax_kernel(const Params p) {
     using C = Cfg<KS, BN, TS>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -414,6 +419,8 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
     uint64_t* tfull_bar = bars + 2 * C::STAGES;
     uint64_t* tempty_bar = tfull_bar + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+    double* merge_best = reinterpret_cast<double*>(smem + C::STAGES * C::STAGE_BYTES + 256);       // [2][BM]
+    int* merge_arg = reinterpret_cast<int*>(merge_best + 2 * BM);                                   // [2][BM]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
             mbar_init(empty_bar + s, 1);
         }
         mbar_init(tfull_bar, 1);
-        mbar_init(tempty_bar, 4);
+        mbar_init(tempty_bar, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -532,10 +539,13 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
     } else {
         // ------------------------------------------------------------------------------------- epilogue
         const int q = warp & 3;                                          // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                                // which half of the tile's columns (warps 2..5: 0, 6..9: 1)
+        constexpr int HC = BN / 2;                                       // columns per epilogue warp and tile
+        const int cbase = half * HC;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const double c_hi = ldexp(1.0, -8 * (C::G1 + 1));
-        uint32_t tile = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        uint32_t tile = 0, nitem = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++nitem) {
             int ng, mt, b;
             decode_item(p, item, b, mt, ng);
             const int nt0 = ng * p.ntg, nt1 = min(p.NT, nt0 + p.ntg);
@@ -544,7 +554,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
             double best = -INFINITY;
             int best_arg = 0;
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
-                const double* bs = p.bscale + ((long long)b * p.NT + nt) * BN;
+                const double* bs = p.bscale + ((long long)b * p.NT + nt) * BN + cbase;
                 mbar_wait(tfull_bar, tile & 1, p.err, 4);
                 tc_fence_after();
                 const bool checked = p.full != nullptr || (nt + 1) * BN > p.P;     // partial tile or dense output wanted
@@ -554,25 +564,40 @@ __global__ void __launch_bounds__(192, 1) ozaki_rowmax_kernel(const Params p) {
                 if (!(p.diag & 1)) {
                     uint32_t acc[2][KS][8];
 #pragma unroll
-                    for (int d = 0; d < KS; ++d) tc_ld8(lane_addr + (uint32_t)(d * BN), acc[0][d]);
+                    for (int d = 0; d < KS; ++d) tc_ld8(lane_addr + (uint32_t)(d * BN + cbase), acc[0][d]);
 #pragma unroll
-                    for (int k = 0; k < BN / 8; ++k) {
+                    for (int k = 0; k < HC / 8; ++k) {
                         tc_ld_wait();
-                        if (k + 1 < BN / 8) {
+                        if (k + 1 < HC / 8) {
 #pragma unroll
-                            for (int d = 0; d < KS; ++d) tc_ld8(lane_addr + (uint32_t)(d * BN + (k + 1) * 8), acc[(k + 1) & 1][d]);
+                            for (int d = 0; d < KS; ++d) tc_ld8(lane_addr + (uint32_t)(d * BN + cbase + (k + 1) * 8), acc[(k + 1) & 1][d]);
                         }
-                        if (checked) epi_columns<KS, C::G1, true, 8>(acc[k & 1], bs + k * 8, nt * BN + k * 8, p.P, full_row, as2, best, best_arg);
-                        else epi_columns<KS, C::G1, false, 8>(acc[k & 1], bs + k * 8, nt * BN + k * 8, p.P, nullptr, as2, best, best_arg);
+                        const int col0 = nt * BN + cbase + k * 8;
+                        if (checked) epi_columns<KS, C::G1, true, 8>(acc[k & 1], bs + k * 8, col0, p.P, full_row, as2, best, best_arg);
+                        else epi_columns<KS, C::G1, false, 8>(acc[k & 1], bs + k * 8, col0, p.P, nullptr, as2, best, best_arg);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar);
             }
-            if (row < p.S) {
-                p.fmax[((long long)b * p.NG + ng) * p.S + row] = best * as2;
-                p.arg[((long long)b * p.NG + ng) * p.S + row] = best_arg;
+            // the two column halves of a row meet in shared memory (slot alternates with the work item: the next write to a slot
+            // is two items later, behind the next item's barrier); equal maxima keep the lower column = first arg-max
+            double* mb = merge_best + (nitem & 1) * BM;
+            int* ma = merge_arg + (nitem & 1) * BM;
+            if (half == 1) {
+                mb[q * 32 + lane] = best;
+                ma[q * 32 + lane] = best_arg;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * EPI_WARPS) : "memory");
+            if (half == 0) {
+                const double v1 = mb[q * 32 + lane];
+                const int a1 = ma[q * 32 + lane];
+                if (v1 > best || (v1 == best && a1 < best_arg)) { best = v1; best_arg = a1; }
+                if (row < p.S) {
+                    p.fmax[((long long)b * p.NG + ng) * p.S + row] = best * as2;
+                    p.arg[((long long)b * p.NG + ng) * p.S + row] = best_arg;
+                }
             }
         }
     }
@@ -658,7 +683,14 @@ static int rowmax_launch(const Params& p, cudaStream_t st) {
     PPBO_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int items = p.MT * p.batch * p.NG;
     if (items <= 0) return PPBO_OK;
-    PPBO_CL ozaki_rowmax_kernel<KS, BN, TS><<<min(items, sms), 192, C::SMEM, st>>>(p);
+    // tuning key 14 = R > 0: leave R SMs free (persistent grid of SMs - R CTAs; a CTA fills its SM: 224 KB of shared memory and
+    // 53k registers).  A launch that shares the GPU with the latency-bound GP fit (run_iteration on one GPU: the contraction needs
+    // the weight-space fit only) keeps the tensor pipes of its SMs busy while the fit's kernels find the reserved SMs free at
+    // once.  Measured alternative, one CTA per work item on all SMs (key 14 = -1): the fit's wide bandwidth-bound kernels then
+    // collect their SMs one by one as ~120 us work items end and the GP fit stretches from 10.6 to 15.3 ms.
+    const int reserve = g_tuning[14];
+    const int grid = reserve < 0 ? items : min(items, max(sms - reserve, 1));
+    PPBO_CL ozaki_rowmax_kernel<KS, BN, TS><<<grid, THREADS, C::SMEM, st>>>(p);
     PPBO_LAUNCH_CHECK();
     return PPBO_OK;
 }

@@ -40,6 +40,14 @@ I8_MIN_WORK = 1 << 24     # S * P * F below which the FP64 kernel is used
 # behind the longer.  The RFF fit then starts from omega = 0 (or the caller's omega0) instead of the projection of the GP mode,
 # which costs one extra Newton step (20 against 19 on the Ackley-20D bench problem).
 CONCURRENT_FITS = True
+# One GPU: the sampling contraction needs the weight-space fit only (mu* enters at the reduction), so the background thread goes
+# on from the weight-space fit to the draws and the INT8 contraction on its lowest-priority stream WHILE the GP fit -- a chain of
+# small, latency-bound kernels that leaves most SMs idle -- runs in the foreground.  The contraction's persistent grid then leaves
+# OVERLAP_RESERVED_SMS SMs to the fit (tuning key 14); a contraction CTA fills its SM, so the two never share one.
+# PPBO_OVERLAP_SAMPLING=0 restores the sequential order (diagnostics).
+import os as _os
+OVERLAP_RESERVED_SMS = int(_os.environ.get("PPBO_OVERLAP_RESERVE", "20"))
+OVERLAP_SAMPLING = _os.environ.get("PPBO_OVERLAP_SAMPLING", "1") != "0"
 
 
 def sampling_engine(S, P, Fdim):
@@ -308,6 +316,8 @@ class RFFState:
         N_old = self.Q * (self.m + 1)
         ops.rff_features(self.W, self.b, X_block, self.theta[2], True, out=self.Phi_cap[:, N_old:N_old + X_block.shape[0]])
         warm = self.fit.stats.get("factorizations", 0) > 0 or self.fit.stats.get("warm", False)
+        if warm and self.fit.stats.get("binv_cached", False):
+            warm = 2                            # the cache also holds the block inverses of its factor
         r = self._fit(self.Q + X_block.shape[0] // (self.m + 1), self.fit.omega_map, warm=warm)
         r.stats["warm"] = True              # the cache holds a factor from now on
         return r
@@ -572,9 +582,61 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
     gp = rff = prepared = None
     cand = grids.reshape(B * P, D)
     rff_rank = 1 if (CONCURRENT_FITS and shard.world > 1) else 0      # with more than one GPU the two fits run on two of them
+    if shard.rank == 0 and CONCURRENT_FITS and shard.world == 1 and OVERLAP_SAMPLING and isinstance(PhiT, SlicedGrids):
+        # One GPU, INT8 engine.  Two chains that only share X:
+        #   A  GP fit -> mu*                                   latency-bound, short (8.7 ms cold / 5 ms appended when alone)
+        #   B  weight-space fit -> draws -> contraction        the contraction alone keeps every tensor pipe busy for ~9 ms
+        # B is the longer one and its head (the weight-space fit) is as latency-bound as A, so B runs in the FOREGROUND (this
+        # thread, streams above the default priority) and A on the persistent background thread whose streams all sit at the
+        # lowest priority; the contraction's persistent grid leaves OVERLAP_RESERVED_SMS SMs free, where A finishes while the
+        # tensor pipes of the other SMs are busy.  Only the reduction (3 B sums) needs both chains.
+        bg = _side_stream(dev)
+        bg.wait_stream(main)
+        fg = _side_stream(dev, priority=GP_STREAM_PRIORITY, tag="gp") if GP_STREAM_PRIORITY else main
+        if fg is not main:
+            fg.wait_stream(main)
+
+        def gp_chain():
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(bg):
+                g = fit_gp()
+                return g, mustar_over_candidates(g, cand)
+        fut = _background_worker().submit(gp_chain)
+        lib = ops._lib.load()
+        fmax = None
+        try:
+            with torch.cuda.stream(fg):
+                rff = fit_rff()
+                mark("rff_fit")
+                prepared = rff_prepare_samples(rff, lo, hi, P, seed=seed)
+                fg.wait_stream(grid_stream)
+                for t in (PhiT.PhiT, PhiT.planes, PhiT.scale):
+                    t.record_stream(fg)
+                lib.ppbo_set_tuning(14, OVERLAP_RESERVED_SMS)
+                try:
+                    fmax, _ = rff_sampled_maxima(rff, PhiT, lo, hi, seed=seed, prepared=prepared)
+                finally:
+                    lib.ppbo_set_tuning(14, 0)
+                mark("sampling")
+        finally:
+            gp, mustar = fut.result()          # re-raises on this thread
+        main.wait_stream(bg)
+        for t in (gp.Sigma, gp.lap.G, gp.lap._Lfac, gp.lap.f_map, gp.lap.alpha, gp.lap.arrow, mustar):
+            t.record_stream(main)
+        if fg is not main:
+            main.wait_stream(fg)
+            for t in (rff.omega_map, rff.hess_diag, rff.Phi_X, fmax):
+                t.record_stream(main)
+        mark("gp_tail")                        # what is left of the GP fit + mu* after the contraction has finished
+        sums = rff_reduce(fmax, mustar, B, shard)
+        mark("acquisition")
+        if state is not None:
+            state.Q = Q
+        return sums, gp, rff
     if shard.rank == 0 and CONCURRENT_FITS and shard.world == 1:
-        # GP fit: foreground, on a stream one priority level above the default; weight-space fit: a persistent background host
-        # thread whose streams all sit at the lowest priority, so it only takes the SMs the GP fit leaves idle.
+        # (FP64 engine / PPBO_OVERLAP_SAMPLING=0.)  GP fit: foreground, on a stream one priority level above the default;
+        # weight-space fit: a persistent background host thread whose streams all sit at the lowest priority, so it only takes the
+        # SMs the GP fit leaves idle.
         side = _side_stream(dev)
         side.wait_stream(main)
         gp_stream = _side_stream(dev, priority=GP_STREAM_PRIORITY, tag="gp") if GP_STREAM_PRIORITY else main

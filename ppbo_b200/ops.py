@@ -504,12 +504,14 @@ def rff_fit(Phi_X, Q, m, sigma, omega0=None, max_iter=100, tol=1e-10, factor_cac
     ws, wbytes = _rff_ws(F, Q, m, Phi_X.device)
     omega = torch.empty(F, dtype=F64, device=Phi_X.device)
     hd = torch.empty(F, dtype=F64, device=Phi_X.device)
-    stats = (ctypes.c_double * 4)()
+    stats = (ctypes.c_double * 8)()
+    warm_flag = (int(warm) if warm in (1, 2) else 1) if (warm and factor_cache is not None) else 0      # 2: block inverses cached too
     rc = check(_lib.load().ppbo_rff_fit(_p(Phi_X), Phi_X.stride(0), F, Q, m, float(sigma), _p(omega0), int(max_iter),
-                                        float(tol), _p(factor_cache), 1 if (warm and factor_cache is not None) else 0, _p(omega), _p(hd),
+                                        float(tol), _p(factor_cache), warm_flag, _p(omega), _p(hd),
                                         _p(ws), wbytes, stats, _stream()), "ppbo_rff_fit")
     return omega, hd, dict(iterations=int(stats[0]), last_rel_step=stats[1], S=stats[2], info=rc,
-                           factorizations=int(stats[3]), chord_steps=int(round((stats[3] - int(stats[3])) * 1000)))
+                           factorizations=int(stats[3]), chord_steps=int(round((stats[3] - int(stats[3])) * 1000)),
+                           binv_cached=bool(stats[4]))
 
 
 def rff_eval_argmax(Omega, PhiT_grid, want_full=False):

@@ -106,6 +106,39 @@ def test_rowmax_i8_bit_exact_vs_oracle(ops, slices, S, F, P, B):
 
 
 @pytest.mark.gpu
+def test_rowmax_i8_first_argmax_on_ties_and_launch_shapes(ops):
+    """Equal maxima in the two column halves of a tile (two epilogue warps per row), in different tiles and in different column
+    groups resolve to the LOWEST column, as np.argmax does; other launch shapes (tuning key 14: SMs left free for the overlapped
+    one-GPU pipeline, or one CTA per work item) return the same bits."""
+    from ppbo_b200 import _lib
+    S, F, P, B = 300, 128, 200, 3
+    Omega, _ = _operands(S, F, 8, seed=3)
+    g = _operands(8, F, P, seed=4)[1]
+    grids = np.stack([g, g, g]).copy()
+    big = 3.0 * g[5]
+    grids[0][5] = grids[0][40] = grids[0][70] = big          # half 0 / half 1 of tile 0, half 0 of tile 1   -> 5
+    grids[1][40] = grids[1][70] = big                         # half 1 of tile 0 against half 0 of tile 1      -> 40
+    grids[2][33] = grids[2][199] = big                        # half 1 of tile 0 against tile 3                -> 33
+    lib = _lib.load()
+    outs = []
+    for key, groups in ((0, 0), (-1, 0), (0, 2), (100, 4)):     # key 4: number of column-tile groups (partial maxima merged afterwards)
+        lib.ppbo_set_tuning(14, key)
+        lib.ppbo_set_tuning(4, groups)
+        try:
+            fmax, arg, full = ops.rff_eval_argmax_i8(ops.to_dev(Omega), ops.to_dev(grids), slices=6, want_full=True)
+            torch.cuda.synchronize()
+        finally:
+            lib.ppbo_set_tuning(14, 0)
+            lib.ppbo_set_tuning(4, 0)
+        outs.append((_np(fmax), _np(arg), _np(full)))
+    for b, first in enumerate((5, 40, 33)):
+        mx, am, Fs = O.ozaki_eval_argmax(Omega, grids[b], 6)
+        assert (am == first).sum() > 20                  # the tie really decides the arg-max for many samples
+        for fmax, arg, full in outs:
+            assert np.array_equal(full[b], Fs) and np.array_equal(fmax[b], mx) and np.array_equal(arg[b], am)
+
+
+@pytest.mark.gpu
 def test_rowmax_i8_bench_shape_vs_fp64_oracle(ops):
     """the bench's contraction shape (F = 1000, P = 1024) against the ORACLE's FP64 product (numpy, host): values to the error bound
     of the digit count, arg-max identical wherever the oracle's gap to the runner-up exceeds that bound (tie rule), and the FP64
