@@ -72,6 +72,11 @@ struct PinnedReadback {
 };
 PinnedReadback& readback();        // the calling host thread's staging buffer (linalg.cu)
 
+// Stream-ordered scratch.  The device's default memory pool hands its memory back to the driver at every synchronisation unless a
+// release threshold is set; every scratch request after a sync then pays a real allocation (~0.5 ms).  The first call per device
+// sets the threshold to "keep everything".
+cudaError_t malloc_async(void** p, size_t bytes, cudaStream_t st);
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -309,6 +309,244 @@ __global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_mma_kernel(const 
     }
 }
 
+// ---- streaming version of the tensor-pipe kernel (round 2) ---------------------------------------------------------------------
+// profiles/r01_ncu_gram.txt: the one-tile-per-CTA kernel above executes ~109 instructions per matrix entry, 22 of them FP64: every
+// CTA re-derives its 192 rows of scaled coordinates (integer division per element, constant-bank reads of 1 / l_d), their norms
+// and 64-bit store addresses for 16 entries per thread, at an IPC of 0.5 per scheduler.  Here
+//   * a pre-pass writes every point once in "operand form": per tile of TR points one contiguous block [TR x LDX scaled, shifted
+//     coordinates | TR squared norms | TR weights (alpha, mat-vec mode)], zero-padded to whole tiles;
+//   * a CTA owns one 128-row tile and LOOPS over column tiles g, g + G, g + 2G, ... : the row block arrives once and every column
+//     block as ONE cp.async.bulk (TMA 1-D copy) signalled on an mbarrier, double-buffered, so no thread instruction is spent on
+//     loading, scaling or bounds;
+//   * the epilogue is straight-line (branch-free exp, see exp_nonpos) with row pointers advanced by a constant per tile; tiles
+//     that touch the diagonal or the matrix edge take a guarded path.
+// The per-entry arithmetic (operand roles, DMMA k order, norms) does not depend on the tile or the launch shape, so appended rows
+// (ppbo_gram_append) are bit-identical to a from-scratch build as before.
+// Coefficients live in constant memory and enter the FMAs as constant-bank operands: FP64 literals have no immediate form, and
+// under the 64-register budget of this kernel the compiler otherwise re-materialises every coefficient with two moves per use
+// (253 IMAD.MOV next to 256 DFMA per 16 entries in the first version).  Horner form: one constant per FMA.
+__constant__ double KM_EXP[20] = {
+    1.4426950408889634,          // [0] log2(e)
+    6755399441055744.0,          // [1] 2^52 + 2^51
+    -6.93147180369123816490e-01, // [2] -ln2 (high part)
+    -1.90821492927058770002e-10, // [3] -ln2 (low part)
+    1.0, 1.0, 0.5, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03, 1.3888888888888889e-03,      // [4..] 1/k!
+    1.9841269841269841e-04, 2.4801587301587302e-05, 2.7557319223985893e-06, 2.7557319223985888e-07, 2.5052108385441720e-08,
+    2.0876756987868100e-09, 1.6059043836821613e-10,
+    -708.0, -0.25};
+// SE entry from v = |x|^2 + |y|^2 - 2 x.y (may be slightly negative by cancellation):  sf2' exp(-max(v, 0) / 2), straight-line.
+//   w = v + |v| = 2 max(v, 0) exactly (|.| is an operand modifier), its high word clamped at that of 2832 (exp(-708) = 3e-308: the
+//   result stays a normal number whatever the inputs; one integer min instead of the ~8 instructions of a NaN-aware fmax);
+//   x = -w / 4 = n ln2 + r with |r| <= ln2 / 2 (rint by the 2^52 + 2^51 trick, ln2 in two pieces); exp(r) by its degree-13 Taylor
+//   polynomial in Horner form (truncation 4e-18); 2^n by an integer add to the exponent field.  23 FP64 + 2 integer instructions.
+__device__ __forceinline__ double se_entry(double v, double scale_c) {
+    double w = v + fabs(v);
+    w = __hiloint2double(min(__double2hiint(w), 0x40A62000), __double2loint(w));          // high word of 2832.0
+    const double x = w * KM_EXP[19];
+    const double t = fma(x, KM_EXP[0], KM_EXP[1]);
+    const int n = __double2loint(t);
+    const double nf = t - KM_EXP[1];
+    double r = fma(nf, KM_EXP[2], x);
+    r = fma(nf, KM_EXP[3], r);
+    double pv = KM_EXP[17];
+#pragma unroll
+    for (int k = 16; k >= 4; --k) pv = fma(pv, r, KM_EXP[k]);
+    return scale_c * __hiloint2double(__double2hiint(pv) + (n << 20), __double2loint(pv));
+}
+template <int KIND>
+__device__ __forceinline__ double km_entry(double v, double scale_c, double sf2, double diag_scale) {
+    if (KIND == PPBO_KERNEL_SE) return se_entry(v, scale_c);
+    return diag_scale * kernel_from_sums(KIND, fmax(v, 0.0), sf2);
+}
+
+__host__ __device__ inline long long km_block_doubles(int TR, int LDX) { return (long long)TR * LDX + 2 * TR; }
+
+// operand form of n points (rows of X, row stride D): tile t = rows [t TR, (t+1) TR), zero beyond n
+__global__ void __launch_bounds__(128) km_prepare_kernel(const double* __restrict__ X, int n, int TR, KernelParams p,
+                                                         const double* __restrict__ shift, const double* __restrict__ alpha,
+                                                         double* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int D = p.D, Dp = (D + 3) / 4 * 4, LDX = km_ldx(D);
+    const int tiles = (n + TR - 1) / TR;
+    if (r >= tiles * TR) return;
+    double* blk = out + (long long)(r / TR) * km_block_doubles(TR, LDX);
+    double* row = blk + (long long)(r % TR) * LDX;
+    double s = 0.0;
+    for (int d = 0; d < LDX; ++d) {
+        const double v = (r < n && d < D) ? (X[(long long)r * D + d] - shift[d]) * p.inv_ls[d] : 0.0;
+        row[d] = v;
+        if (d < Dp) s = fma(v, v, s);
+    }
+    blk[(long long)TR * LDX + (r % TR)] = s;
+    blk[(long long)TR * LDX + TR + (r % TR)] = (alpha != nullptr && r < n) ? alpha[r] : 0.0;
+}
+
+__device__ __forceinline__ uint32_t km_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void km_bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(km_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(km_smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(km_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void km_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(km_smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// P1: operand form of X1 in tiles of 128, P2: of X2 in tiles of 64.  grid = (G column groups, row tiles); CTA (g, ti) takes the
+// column tiles tj = g, g + G, ... below nt_of(ti) (all tn tiles, or 2 ti + 2 in symmetric mode: the lower triangle).
+// MATVEC: out[row][g] = sum over the CTA's column tiles of k(x_row, y_j) alpha_j (ld = G).
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_stream_kernel(const double* __restrict__ P1, int n1,
+                                                                          const double* __restrict__ P2, int n2, int D, double sf2,
+                                                                          double diag_scale, double diag_add, double* __restrict__ out,
+                                                                          long long ld, int tn) {
+    extern __shared__ __align__(16) double sm[];
+    const int LDX = km_ldx(D), Dp = (D + 3) / 4 * 4;
+    const long long blk1 = km_block_doubles(KM_B, LDX), blk2 = km_block_doubles(KM_BN, LDX);
+    double* Xs = sm;                                   // [128 x LDX | 128 norms | 128 unused]
+    double* Yb[2] = {sm + blk1, sm + blk1 + blk2};     // [64 x LDX | 64 norms | 64 weights] x 2
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + blk1 + 2 * blk2);      // [0]: row block, [1], [2]: column buffers
+    const int ti = blockIdx.y, g = blockIdx.x, G = gridDim.x;
+    const int nt = (MODE == KM_SYMMETRIC) ? min(tn, 2 * ti + 2) : tn;
+    const int ntiles = (nt > g) ? (nt - g + G - 1) / G : 0;
+    if (ntiles == 0) return;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(km_smem_u32(bars + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        km_bulk_load(Xs, P1 + (long long)ti * blk1, (uint32_t)(blk1 * 8), bars);
+        km_bulk_load(Yb[0], P2 + (long long)g * blk2, (uint32_t)(blk2 * 8), bars + 1);
+    }
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
+    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;       // 4 x 4 warps, 32 x 16 each
+    const int m0 = ti * KM_B;
+    const double scale_c = diag_scale * sf2;
+    const double* nx = Xs + KM_B * LDX;
+    const double* Ap = Xs + (wm0 + gq) * LDX + t4;
+    double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
+    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const bool rows_full = m0 + KM_B <= n1;
+    km_wait(bars, 0);
+    const double* nxp = nx + wm0 + gq;                  // nxp[mi * 8]: squared norm of this thread's row mi
+    for (int it = 0; it < ntiles; ++it) {
+        const int buf = it & 1, tj = g + it * G, c0 = tj * KM_BN;
+        if (tid == 0 && it + 1 < ntiles)               // (buffer buf ^ 1 was last read in iteration it - 1, behind its barrier)
+            km_bulk_load(Yb[buf ^ 1], P2 + (long long)(tj + G) * blk2, (uint32_t)(blk2 * 8), bars + 1 + (buf ^ 1));
+        km_wait(bars + 1 + buf, (uint32_t)((it >> 1) & 1));
+        const double* Ys = Yb[buf];
+        const double* ny = Ys + KM_BN * LDX;
+        const double* al = ny + KM_BN;
+        double acc[4][2][2];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        const double* Bp = Ys + (wn0 + gq) * LDX + t4;
+        for (int k = 0; k < Dp; k += 4) {
+            double a[4], b[2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * LDX + k];
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) b[ni] = Bp[ni * 8 * LDX + k];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+        }
+        const double* nyp = ny + wn0 + 2 * t4;             // nyp[nn * 8 + e], alp likewise (16-byte aligned pairs)
+        const double* alp = al + wn0 + 2 * t4;
+        if (MODE == KM_MATVEC) {
+            // padded columns carry weight 0 and a finite kernel value: no bounds needed
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double r2 = fma(-2.0, acc[mi][nn][e], nxp[mi * 8] + nyp[nn * 8 + e]);      // clamped at 0 inside km_entry
+                        rowsum[mi] = fma(km_entry<KIND>(r2, scale_c, sf2, diag_scale), alp[nn * 8 + e], rowsum[mi]);
+                    }
+        } else {
+            const bool interior = rows_full && c0 + KM_BN <= n2 && vec_ok && !(MODE == KM_SYMMETRIC && c0 + KM_BN > m0);
+            if (interior) {                            // full tile, strictly below the diagonal blocks in symmetric mode
+                double* o = out + (long long)(m0 + wm0 + gq) * ld + c0 + wn0 + 2 * t4;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+                    for (int nn = 0; nn < 2; ++nn) {
+                        double kv[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double r2 = fma(-2.0, acc[mi][nn][e], nxp[mi * 8] + nyp[nn * 8 + e]);      // clamped at 0 inside km_entry
+                            kv[e] = km_entry<KIND>(r2, scale_c, sf2, diag_scale);
+                        }
+                        *reinterpret_cast<double2*>(o + (long long)mi * 8 * ld + nn * 8) = make_double2(kv[0], kv[1]);
+                        if (MODE == KM_SYMMETRIC) {    // mirror (8 consecutive doubles per (t4, e) across gq)
+                            double* om = out + (long long)(c0 + wn0 + nn * 8 + 2 * t4) * ld + m0 + wm0 + mi * 8 + gq;
+                            om[0] = kv[0];
+                            om[ld] = kv[1];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int gr = m0 + wm0 + mi * 8 + gq;
+#pragma unroll
+                    for (int nn = 0; nn < 2; ++nn) {
+                        const int gc = c0 + wn0 + nn * 8 + 2 * t4;
+                        double kv[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double r2 = fma(-2.0, acc[mi][nn][e], nxp[mi * 8] + nyp[nn * 8 + e]);      // clamped at 0 inside km_entry
+                            kv[e] = km_entry<KIND>(r2, scale_c, sf2, diag_scale);
+                            if (MODE == KM_SYMMETRIC && gr == gc + e) kv[e] = fma(diag_scale, sf2, diag_add);  // exact diagonal: ONE rounding,
+                        }                                                                                    // as in gram_mirror_kernel
+                        if (gr < n1) {
+                            double* o = out + (long long)gr * ld + gc;
+                            if (gc + 1 < n2 && vec_ok) *reinterpret_cast<double2*>(o) = make_double2(kv[0], kv[1]);
+                            else {
+                                if (gc < n2) o[0] = kv[0];
+                                if (gc + 1 < n2) o[1] = kv[1];
+                            }
+                            if (MODE == KM_SYMMETRIC && c0 + KM_BN <= m0) {
+                                if (gc < n2) out[(long long)gc * ld + gr] = kv[0];
+                                if (gc + 1 < n2) out[(long long)(gc + 1) * ld + gr] = kv[1];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();                               // everybody is done with Yb[buf] before it is refilled
+    }
+    if (MODE == KM_MATVEC) {
+        double* red = Yb[0];                           // [128][4] cross-warp buffer (all column blocks are consumed)
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            double v = rowsum[mi];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (t4 == 0) red[(wm0 + mi * 8 + gq) * 4 + (warp & 3)] = v;
+        }
+        __syncthreads();
+        if (tid < KM_B && m0 + tid < n1)
+            out[(long long)(m0 + tid) * G + g] = (red[tid * 4] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
+    }
+}
+
 // mu[r] = sum_c partial[r][c] in a fixed order
 __global__ void __launch_bounds__(256) km_rowsum_kernel(const double* __restrict__ partial, int n, int nc, double* __restrict__ mu) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,26 +556,47 @@ __global__ void __launch_bounds__(256) km_rowsum_kernel(const double* __restrict
     mu[r] = s;
 }
 
+// column groups per row tile: ~6 column tiles per CTA (the row block and the per-CTA setup are amortised over them) and enough
+// CTAs for several waves of 2 x 148
+static int km_column_groups(int tm, int tn) {
+    int G = ceil_div(tn, 6);
+    while (G < tn && (long long)G * tm < 4LL * 2 * PPBO_SM_COUNT) ++G;
+    return G < 1 ? 1 : G;
+}
+
 template <int KIND>
 static int launch_kernel_matrix_mma(const KernelParams& p, const double* X1, int n1, const double* X2, int n2, double* out,
-                                    long long ld, int mode, const double* alpha, cudaStream_t st) {
-    const size_t smem = (size_t)((KM_B + KM_BN) * km_ldx(p.D) + KM_B + KM_BN) * sizeof(double);
+                                    long long ld, int mode, const double* alpha, cudaStream_t st, int* groups_out = nullptr) {
+    const int LDX = km_ldx(p.D);
+    const long long blk1 = km_block_doubles(KM_B, LDX), blk2 = km_block_doubles(KM_BN, LDX);
+    const size_t smem = (size_t)(blk1 + 2 * blk2) * sizeof(double) + 32;
     static bool attr_done = false;
     if (!attr_done) {
-        const int max_smem = ((KM_B + KM_BN) * km_ldx(PPBO_MAX_D) + KM_B + KM_BN) * (int)sizeof(double);
-        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_mma_kernel<KIND, KM_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_mma_kernel<KIND, KM_SYMMETRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_mma_kernel<KIND, KM_MATVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        const int LM = km_ldx(PPBO_MAX_D);
+        const int max_smem = (int)((km_block_doubles(KM_B, LM) + 2 * km_block_doubles(KM_BN, LM)) * sizeof(double)) + 32;
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_stream_kernel<KIND, KM_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_stream_kernel<KIND, KM_SYMMETRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        PPBO_CUDA_CHECK(cudaFuncSetAttribute(kernel_matrix_stream_kernel<KIND, KM_MATVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_done = true;
     }
     const int tm = ceil_div(n1, KM_B), tn = ceil_div(n2, KM_BN);
+    // operand form of both point sets (stream-ordered scratch): tiles of 128 rows for X1, of 64 rows for X2
+    double* P1 = nullptr;
+    PPBO_CUDA_CHECK(malloc_async((void**)reinterpret_cast<void**>(&P1), sizeof(double) * (tm * blk1 + tn * blk2), st));
+    double* P2 = P1 + tm * blk1;
+    PPBO_CL km_prepare_kernel<<<ceil_div(tm * KM_B, 128), 128, 0, st>>>(X1, n1, KM_B, p, X2, nullptr, P1);
+    PPBO_CL km_prepare_kernel<<<ceil_div(tn * KM_BN, 128), 128, 0, st>>>(X2, n2, KM_BN, p, X2, alpha, P2);
+    const int G = km_column_groups(tm, tn);
+    if (groups_out) *groups_out = G;
+    const dim3 grid(G, tm);
     if (mode == KM_SYMMETRIC)
-        PPBO_CL kernel_matrix_mma_kernel<KIND, KM_SYMMETRIC><<<(unsigned)((long long)tm * (tm + 1)), KM_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, nullptr, 0);
+        PPBO_CL kernel_matrix_stream_kernel<KIND, KM_SYMMETRIC><<<grid, KM_THREADS, smem, st>>>(P1, n1, P2, n2, p.D, p.sf2, p.diag_scale, p.diag_add, out, ld, tn);
     else if (mode == KM_MATVEC)
-        PPBO_CL kernel_matrix_mma_kernel<KIND, KM_MATVEC><<<dim3(tn, tm), KM_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, alpha, tn);
+        PPBO_CL kernel_matrix_stream_kernel<KIND, KM_MATVEC><<<grid, KM_THREADS, smem, st>>>(P1, n1, P2, n2, p.D, p.sf2, p.diag_scale, p.diag_add, out, G, tn);
     else
-        PPBO_CL kernel_matrix_mma_kernel<KIND, KM_STORE><<<dim3(tn, tm), KM_THREADS, smem, st>>>(X1, n1, X2, n2, p, out, ld, nullptr, 0);
+        PPBO_CL kernel_matrix_stream_kernel<KIND, KM_STORE><<<grid, KM_THREADS, smem, st>>>(P1, n1, P2, n2, p.D, p.sf2, p.diag_scale, p.diag_add, out, ld, tn);
     PPBO_LAUNCH_CHECK();
+    PPBO_CUDA_CHECK(cudaFreeAsync(P1, st));
     return PPBO_OK;
 }
 
@@ -428,10 +687,11 @@ int kernel_matvec(int kind, const double* X1, int n1, const double* X2, int n2, 
     int rc = fill_params(p, kind, D, ls_h, sigma_f);
     if (rc) return rc;
     if (n1 <= 0) return 1;
-    rc = kind == PPBO_KERNEL_SE ? launch_kernel_matrix_mma<PPBO_KERNEL_SE>(p, X1, n1, X2, n2, partial, 0, KM_MATVEC, alpha, st)
-                                : launch_kernel_matrix_mma<PPBO_KERNEL_RQ>(p, X1, n1, X2, n2, partial, 0, KM_MATVEC, alpha, st);
+    int G = 1;
+    rc = kind == PPBO_KERNEL_SE ? launch_kernel_matrix_mma<PPBO_KERNEL_SE>(p, X1, n1, X2, n2, partial, 0, KM_MATVEC, alpha, st, &G)
+                                : launch_kernel_matrix_mma<PPBO_KERNEL_RQ>(p, X1, n1, X2, n2, partial, 0, KM_MATVEC, alpha, st, &G);
     if (rc) return rc;
-    PPBO_CL km_rowsum_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(partial, n1, ceil_div(n2, KM_BN), mu);
+    PPBO_CL km_rowsum_kernel<<<ceil_div(n1, 256), 256, 0, st>>>(partial, n1, G, mu);
     PPBO_LAUNCH_CHECK();
     return 1;
 }
@@ -608,7 +868,7 @@ __global__ void __launch_bounds__(256) gram_mirror_kernel(double* __restrict__ o
                                                           double diag_scale, double sf2, double diag_add) {
     const int i = n_old + blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_new || j > i) return;
-    if (j == i) out[(long long)i * ld + i] = diag_scale * sf2 + diag_add;       // same expression as the from-scratch kernels
+    if (j == i) out[(long long)i * ld + i] = fma(diag_scale, sf2, diag_add);    // same value as the from-scratch kernels (one rounding)
     else out[(long long)j * ld + i] = out[(long long)i * ld + j];
 }
 

@@ -692,7 +692,7 @@ extern "C" int ppbo_lik_terms(const double* f, int Q, int m, double sigma, doubl
     if (Q == 0) return PPBO_OK;
     cudaStream_t st = (cudaStream_t)stream;
     double* part = nullptr;
-    if (lik_sum) PPBO_CUDA_CHECK(cudaMallocAsync(&part, sizeof(double) * Q, st));
+    if (lik_sum) PPBO_CUDA_CHECK(malloc_async((void**)&part, sizeof(double) * Q, st));
     PPBO_CL lik_terms_kernel<<<ceil_div(Q, 8), 256, 0, st>>>(f, Q, m, sigma, part, beta, arrow, nullptr, nullptr);
     PPBO_LAUNCH_CHECK();
     if (lik_sum) {
@@ -750,7 +750,7 @@ extern "C" int ppbo_laplace_refactor(const double* G, long long ldg, int M, cons
     cudaStream_t st = (cudaStream_t)stream;
     double* dinv = Lfac + (long long)cap * cap;
     int* info_d = nullptr;
-    PPBO_CUDA_CHECK(cudaMallocAsync(&info_d, sizeof(int), st));
+    PPBO_CUDA_CHECK(malloc_async((void**)&info_d, sizeof(int), st));
     PPBO_CL sqrt_clamp_kernel<<<ceil_div(M, 256), 256, 0, st>>>(arrow, M, sa_fac);
     int rc;
     if ((rc = newton_matrix(G, ldg, M, sa_fac, Lfac, cap, st))) return rc;
@@ -784,7 +784,7 @@ extern "C" int ppbo_factor_extend(const double* G, long long ldg, int M_old, int
     const int b0 = (M_old / CHOL_NB) * CHOL_NB, nt = M_new - b0;
     int rc;
     int* info_d = nullptr;
-    PPBO_CUDA_CHECK(cudaMallocAsync(&info_d, sizeof(int), st));
+    PPBO_CUDA_CHECK(malloc_async((void**)&info_d, sizeof(int), st));
     PPBO_CL newton_rows_kernel<<<dim3(ceil_div(M_new, 256), nt), 256, 0, st>>>(G, ldg, sa_fac, b0, M_new, M_old, b0, Lfac, cap);
     PPBO_LAUNCH_CHECK();
     if (b0 > 0) {

@@ -67,6 +67,23 @@ PinnedReadback& readback() {
     return r;
 }
 
+cudaError_t malloc_async(void** p, size_t bytes, cudaStream_t st) {
+    static std::once_flag once[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64)
+        std::call_once(once[dev], [dev] {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void)cudaGetLastError();
+        });
+    return cudaMallocAsync(p, bytes, st);
+}
+
 static thread_local bool g_launch_pdl = false;      // set by potrf_lower around the launches of its critical path
 
 template <class Cfg>
