@@ -187,131 +187,21 @@ __global__ void __launch_bounds__(KT_THREADS, 2) kernel_matrix_tiled_kernel(cons
 //   r2 = |x|^2 + |y|^2 - 2 x.y   clipped at 0,
 // with the cross term as a DMMA product (D FMAs per pair instead of the 2 D of the difference form, 0.03 shared-memory loads per
 // FMA).  Both point sets are shifted by the first point of X2 before scaling, which keeps |x|^2 (and with it the cancellation
-// error 2.2e-16 (|x|^2 + |y|^2) of the expansion) at the squared diameter of the data in length-scale units.  What is left per
-// entry is one exp: the kernel is bound by the FP64 exp rate (801 G/s measured) and the store bandwidth.
+// error 2.2e-16 (|x|^2 + |y|^2) of the expansion) at the squared diameter of the data in length-scale units.  Per entry: D FMAs of
+// cross term on DMMA and 24 FP64 instructions of entry function (se_entry) share the FP64 pipe -- at D = 20 that is 1.45 entries
+// per clock and SM (~410 G entries/s), which is what bounds the store and mat-vec modes (profiles/r02_ncu_gram.txt: FP64 41 % +
+// DMMA 38 %); the symmetric mode computes half of the entries and is bound by its 8 N^2 bytes of stores.
 // Modes:  KM_STORE     out[i][j] = k(x_i, y_j)                              (cross-covariances)
 //         KM_SYMMETRIC X1 == X2: lower tiles only, every off-diagonal tile is also written transposed (+ fused shrinkage)
 //         KM_MATVEC    partial[i][tile] = sum_{j in tile} k(x_i, y_j) alpha_j   (posterior mean without materialising the matrix)
-constexpr int KM_B = 128, KM_BN = 64, KM_THREADS = 512;        // 128 x 64 tiles, 16 warps of 32 x 16, two CTAs per SM: the exp
-                                                                  // polynomials of the epilogue are bound by FP64 latency, so the
-                                                                  // kernel wants resident warps (32 per SM) more than big register tiles
+constexpr int KM_B = 128, KM_BN = 64, KM_THREADS = 512;        // 128 x 64 tiles, 16 warps of 32 x 16, two CTAs per SM (32 warps
+                                                                  // hide the 13-deep Horner chains of the entry function)
 enum { KM_STORE = 0, KM_SYMMETRIC = 1, KM_MATVEC = 2 };
 __host__ __device__ inline int km_ldx(int D) { const int Dp = (D + 3) / 4 * 4; return (Dp % 8 == 4) ? Dp : Dp + 4; }
 
-template <int KIND, int MODE>
-__global__ void __launch_bounds__(KM_THREADS, 2) kernel_matrix_mma_kernel(const double* __restrict__ X1, int n1,
-                                                                       const double* __restrict__ X2, int n2, KernelParams p,
-                                                                       double* __restrict__ out, long long ld,
-                                                                       const double* __restrict__ alpha, int ntile_cols) {
-    extern __shared__ __align__(16) double sm[];
-    const int D = p.D, Dp = (D + 3) / 4 * 4, LDX = km_ldx(D);
-    double* Xs = sm;                       // [128][LDX] rows of X1: (x - c) / l, zero-padded dims
-    double* Ys = Xs + KM_B * LDX;          // [64][LDX] rows of X2
-    double* nx = Ys + KM_BN * LDX;         // [128] squared norms
-    double* ny = nx + KM_B;                // [64]
-    int ti, tj;
-    if (MODE == KM_SYMMETRIC) {            // tiles that touch the lower triangle, row-tile major: row tile ti owns column tiles 0 .. 2 ti + 1
-        const long long L = blockIdx.x;
-        ti = (int)((sqrt(1.0 + 4.0 * (double)L) - 1.0) * 0.5);
-        while ((long long)(ti + 1) * (ti + 2) <= L) ++ti;
-        while ((long long)ti * (ti + 1) > L) --ti;
-        tj = (int)(L - (long long)ti * (ti + 1));
-    } else {
-        ti = blockIdx.y;
-        tj = blockIdx.x;
-    }
-    const int m0 = ti * KM_B, c0 = tj * KM_BN;
-    const int tid = threadIdx.x;
-    for (int e = tid; e < KM_B * LDX; e += KM_THREADS) {
-        const int r = e / LDX, d = e % LDX, g1 = m0 + r, g2 = c0 + r;
-        const double c = d < D ? X2[d] : 0.0;                                  // shift: first point of X2
-        Xs[e] = (g1 < n1 && d < D) ? (X1[(long long)g1 * D + d] - c) * p.inv_ls[d] : 0.0;
-        if (r < KM_BN) Ys[e] = (g2 < n2 && d < D) ? (X2[(long long)g2 * D + d] - c) * p.inv_ls[d] : 0.0;
-    }
-    __syncthreads();
-    if (tid < KM_B + KM_BN) {
-        const double* v = tid < KM_B ? Xs + tid * LDX : Ys + (tid - KM_B) * LDX;
-        double s = 0.0;
-        for (int d = 0; d < Dp; ++d) s = fma(v[d], v[d], s);
-        if (tid < KM_B) nx[tid] = s;
-        else ny[tid - KM_B] = s;
-    }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t4 = lane & 3;
-    const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;       // 4 x 4 warps, 32 x 16 each
-    double acc[4][2][2];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    const double* Ap = Xs + (wm0 + gq) * LDX + t4;
-    const double* Bp = Ys + (wn0 + gq) * LDX + t4;
-    for (int k = 0; k < Dp; k += 4) {
-        double a[4], b[2];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * LDX + k];
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni) b[ni] = Bp[ni * 8 * LDX + k];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
-    }
-    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    double rowsum[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-        const int il = wm0 + mi * 8 + gq, gr = m0 + il;
-        const double ni2 = nx[il];
-#pragma unroll
-        for (int nn = 0; nn < 2; ++nn) {
-            const int jl = wn0 + nn * 8 + 2 * t4, gc = c0 + jl;
-            double kv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double r2 = fmax(ni2 + ny[jl + e] - 2.0 * acc[mi][nn][e], 0.0);
-                kv[e] = p.diag_scale * kernel_from_sums(KIND, r2, p.sf2);
-                if (MODE == KM_SYMMETRIC && gr == gc + e) kv[e] = p.diag_scale * p.sf2 + p.diag_add;     // exact diagonal
-            }
-            if (MODE == KM_MATVEC) {
-                if (gc < n2) rowsum[mi] = fma(kv[0], alpha[gc], rowsum[mi]);
-                if (gc + 1 < n2) rowsum[mi] = fma(kv[1], alpha[gc + 1], rowsum[mi]);
-            } else {
-                if (gr < n1) {
-                    double* o = out + (long long)gr * ld + gc;
-                    if (gc + 1 < n2 && vec_ok) *reinterpret_cast<double2*>(o) = make_double2(kv[0], kv[1]);
-                    else {
-                        if (gc < n2) o[0] = kv[0];
-                        if (gc + 1 < n2) o[1] = kv[1];
-                    }
-                }
-                if (MODE == KM_SYMMETRIC && c0 + KM_BN <= m0 && gr < n1) {  // tile strictly below the diagonal block: mirror
-                                                                            // (8 consecutive doubles per (t4, e) across gq)
-                    if (gc < n2) out[(long long)gc * ld + gr] = kv[0];
-                    if (gc + 1 < n2) out[(long long)(gc + 1) * ld + gr] = kv[1];
-                }
-            }
-        }
-    }
-    if (MODE == KM_MATVEC) {
-        __syncthreads();                                   // Xs is dead: reuse it as the [128][4] cross-warp buffer
-        double* red = Xs;
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            double v = rowsum[mi];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (t4 == 0) red[(wm0 + mi * 8 + gq) * 4 + (warp & 3)] = v;
-        }
-        __syncthreads();
-        if (tid < KM_B && m0 + tid < n1)
-            out[(long long)(m0 + tid) * ntile_cols + tj] = (red[tid * 4] + red[tid * 4 + 1]) + (red[tid * 4 + 2] + red[tid * 4 + 3]);
-    }
-}
-
-// ---- streaming version of the tensor-pipe kernel (round 2) ---------------------------------------------------------------------
-// profiles/r01_ncu_gram.txt: the one-tile-per-CTA kernel above executes ~109 instructions per matrix entry, 22 of them FP64: every
-// CTA re-derives its 192 rows of scaled coordinates (integer division per element, constant-bank reads of 1 / l_d), their norms
+// ---- streaming tensor-pipe kernel -------------------------------------------------------------------------------------------
+// profiles/r01_ncu_gram.txt: the one-tile-per-CTA kernel of round 1 executed ~109 instructions per matrix entry, 22 of them FP64:
+// every CTA re-derived its 192 rows of scaled coordinates (integer division per element, constant-bank reads of 1 / l_d), their norms
 // and 64-bit store addresses for 16 entries per thread, at an IPC of 0.5 per scheduler.  Here
 //   * a pre-pass writes every point once in "operand form": per tile of TR points one contiguous block [TR x LDX scaled, shifted
 //     coordinates | TR squared norms | TR weights (alpha, mat-vec mode)], zero-padded to whole tiles;

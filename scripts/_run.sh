@@ -1,5 +1,2 @@
-python scripts/_dbg.py 2>&1 | grep -A1 "levy\|rq3d" | head
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_t8.log 2>&1; tail -3 gpurun_out/pytest_t8.log
-for R in 12 20; do
-PPBO_OVERLAP_RESERVE=$R python bench.py --steps 8 --warmup 3 --no-api-leg --no-cpu-baseline > gpurun_out/bench_t8_R$R.log 2>&1
-done
+ncu --set full --clock-control none --import-source on -k regex:kernel_matrix_stream -c 12 -o gpurun_out/r02_gram python scripts/gram_probe.py > gpurun_out/prof_gram.log 2>&1; tail -3 gpurun_out/prof_gram.log
+ls -la gpurun_out/r02_gram.ncu-rep
