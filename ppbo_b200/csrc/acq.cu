@@ -438,20 +438,25 @@ constexpr int LS_STEPS = 8;      // == NSTEP of laplace.cu: step sizes 1, 1/2, .
 __global__ void __launch_bounds__(1024) rff_ls_scalars_kernel(const double* __restrict__ omega, const double* __restrict__ step,
                                                               int F, const double* __restrict__ part, int Q,
                                                               double* __restrict__ scal) {
-    __shared__ double red[33];
+    __shared__ double red_multi[32 * (3 + LS_STEPS)];
     __shared__ double mx[2][32];
-    double s0 = 0, s1 = 0, s2 = 0, m0 = 0, m1 = 0;
+    double m0 = 0, m1 = 0;
+    double sums[3 + LS_STEPS];
+#pragma unroll
+    for (int c = 0; c < 3 + LS_STEPS; ++c) sums[c] = 0.0;
     for (int i = threadIdx.x; i < F; i += 1024) {
         const double o = omega[i], d = step[i];
-        s0 = fma(o, o, s0);
-        s1 = fma(o, d, s1);
-        s2 = fma(d, d, s2);
+        sums[0] = fma(o, o, sums[0]);
+        sums[1] = fma(o, d, sums[1]);
+        sums[2] = fma(d, d, sums[2]);
         m0 = fmax(m0, fabs(d));
         m1 = fmax(m1, fabs(o));
     }
-    s0 = block_sum(s0, red);
-    s1 = block_sum(s1, red);
-    s2 = block_sum(s2, red);
+    for (int q = threadIdx.x; q < Q; q += 1024) {
+#pragma unroll
+        for (int c = 0; c < LS_STEPS; ++c) sums[3 + c] += part[(long long)c * Q + q];
+    }
+    block_sum_multi<3 + LS_STEPS>(sums, red_multi);          // one pair of barriers for all eleven sums
     for (int o = 16; o > 0; o >>= 1) {
         m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
         m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
@@ -460,13 +465,8 @@ __global__ void __launch_bounds__(1024) rff_ls_scalars_kernel(const double* __re
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 32; ++w) { m0 = fmax(m0, mx[0][w]); m1 = fmax(m1, mx[1][w]); }
-        scal[0] = s0; scal[1] = s1; scal[2] = s2; scal[3] = m0; scal[4] = m1;
-    }
-    for (int c = 0; c < LS_STEPS; ++c) {
-        double s = 0.0;
-        for (int q = threadIdx.x; q < Q; q += 1024) s += part[(long long)c * Q + q];
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) scal[8 + c] = s;
+        scal[0] = sums[0]; scal[1] = sums[1]; scal[2] = sums[2]; scal[3] = m0; scal[4] = m1;
+        for (int c = 0; c < LS_STEPS; ++c) scal[8 + c] = sums[3 + c];
     }
 }
 
@@ -526,7 +526,6 @@ constexpr int RAA_M = 5;
 __global__ void __launch_bounds__(1024) rff_anderson_kernel(double* __restrict__ omega, const double* __restrict__ step, int F,
                                                             const double* __restrict__ state, double* __restrict__ aa,
                                                             double* __restrict__ Hh) {
-    __shared__ double red[33];
     __shared__ double gam[RAA_M];
     __shared__ int nh_s;
     if (state[4] != 0.0) return;                                         // converged, rejected or about to refactor: nothing to mix
@@ -560,16 +559,35 @@ __global__ void __launch_bounds__(1024) rff_anderson_kernel(double* __restrict__
         pg[i] = omega[i];
     }
     __syncthreads();
-    double A[RAA_M][RAA_M], bb[RAA_M];
-    for (int i = 0; i < nh; ++i) {
-        for (int j = 0; j <= i; ++j) {
-            double sacc = 0.0;
-            for (int k = threadIdx.x; k < F; k += 1024) sacc = fma(dR[(long long)i * F + k], dR[(long long)j * F + k], sacc);
-            A[i][j] = A[j][i] = block_sum(sacc, red);
+    // all products of the normal equations in one pass and one multi-value reduction
+    constexpr int NPAIR = RAA_M * (RAA_M + 1) / 2;
+    __shared__ double red_multi[32 * (NPAIR + RAA_M)];
+    double acc[NPAIR + RAA_M];
+#pragma unroll
+    for (int i = 0; i < NPAIR + RAA_M; ++i) acc[i] = 0.0;
+    for (int k = threadIdx.x; k < F; k += 1024) {
+        double dv[RAA_M];
+#pragma unroll
+        for (int i = 0; i < RAA_M; ++i) dv[i] = (i < nh) ? dR[(long long)i * F + k] : 0.0;
+        const double rk = step[k];
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < RAA_M; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) { acc[idx] = fma(dv[i], dv[j], acc[idx]); ++idx; }
+            acc[NPAIR + i] = fma(dv[i], rk, acc[NPAIR + i]);
         }
-        double sacc = 0.0;
-        for (int k = threadIdx.x; k < F; k += 1024) sacc = fma(dR[(long long)i * F + k], step[k], sacc);
-        bb[i] = block_sum(sacc, red);
+    }
+    block_sum_multi<NPAIR + RAA_M>(acc, red_multi);
+    double A[RAA_M][RAA_M], bb[RAA_M];
+    {
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < RAA_M; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) { A[i][j] = A[j][i] = acc[idx]; ++idx; }
+            bb[i] = acc[NPAIR + i];
+        }
     }
     if (threadIdx.x == 0) {
         double tr = 0.0;

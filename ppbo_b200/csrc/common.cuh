@@ -97,4 +97,27 @@ __device__ inline double block_sum(double v, double* smem33) {
     return smem33[32];
 }
 
+// NV block-wide sums at once (fixed order: shuffle tree inside a warp, warps in index order): v[] holds the totals in EVERY thread on
+// return.  smem: 32 * NV doubles.  One pair of barriers instead of two per value (block_sum): the single-CTA decision kernels of the
+// fits spend most of their time in barriers otherwise.
+template <int NV>
+__device__ inline void block_sum_multi(double (&v)[NV], double* smem) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    __syncthreads();
+    if (l == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) smem[w * NV + i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double r = 0.0;
+        for (int k = 0; k < nw; ++k) r += smem[k * NV + i];
+        v[i] = r;
+    }
+}
+
 }  // namespace ppbo

@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "../../include/ppbo_b200.h"
 #include "common.cuh"
 #include "gemm_f64.cuh"
@@ -239,12 +241,12 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
                                                             const double* __restrict__ part, int Q, int m,
                                                             double* __restrict__ state, double* __restrict__ hist, int extrapolate,
                                                             const double* __restrict__ part0) {
-    __shared__ double red[33];
     __shared__ double mx[2][32];
     __shared__ double step_s;
     if (state[4] != 0.0) return;                    // uniform: state[4] is only written after the barriers below
     const double omega = state[7];
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mdf = 0, mf = 0, lik = 0, lik0 = 0;
+#pragma unroll 4
     for (int i = threadIdx.x; i < N; i += 1024) {
         const double a = alpha[i], da = dalpha[i], fi = f[i], dfi = df[i];
         s0 = fma(a, fi, s0);
@@ -258,12 +260,12 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
         lik += part[q];
         if (part0) lik0 += part0[q];
     }
-    s0 = block_sum(s0, red);
-    s1 = block_sum(s1, red);
-    s2 = block_sum(s2, red);
-    s3 = block_sum(s3, red);
-    lik = block_sum(lik, red);
-    if (part0) lik0 = block_sum(lik0, red);
+    {
+        __shared__ double red6[32 * 6];
+        double sums[6] = {s0, s1, s2, s3, lik, lik0};
+        block_sum_multi<6>(sums, red6);               // one pair of barriers for all six sums
+        s0 = sums[0]; s1 = sums[1]; s2 = sums[2]; s3 = sums[3]; lik = sums[4]; lik0 = sums[5];
+    }
     for (int o = 16; o > 0; o >>= 1) {
         mdf = fmax(mdf, __shfl_xor_sync(0xffffffffu, mdf, o));
         mf = fmax(mf, __shfl_xor_sync(0xffffffffu, mf, o));
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
     __syncthreads();
     const double step = step_s;
     if (step == 0.0) return;
+#pragma unroll 4
     for (int i = threadIdx.x; i < N; i += 1024) {
         alpha[i] = fma(step, dalpha[i], alpha[i]);
         f[i] = fma(step, df[i], f[i]);
@@ -338,74 +341,115 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
 //   * appends the differences (r_k - r_{k-1}, g_k - g_{k-1}) to the history,
 //   * solves min_gamma | r_k - dR gamma |_2 (normal equations of order <= AA_M, Tikhonov-damped) and
 //   * replaces (alpha, f) by g_k - dG gamma   (f = Sigma alpha is preserved: both are the same combination).
-// The history is dropped when a step was damped / extrapolated / rejected, or when the residual grew.  One CTA, fixed order.
+// The history is dropped when a step was damped / extrapolated / rejected, or when the residual grew.  Fixed summation order.
 constexpr int AA_M = 5;
+constexpr int AA_CL = 8;       // CTAs of the cluster that shares one call (each takes N / 8 elements)
 //   aa: [0] history length, [1] next slot, [2] residual norm (max |df| / max |f|) seen by the previous call
 //   H: [3 * AA_M + 3][N]: dR[AA_M], dGf[AA_M], dGa[AA_M], prev r, prev g_f, prev g_a
-__global__ void __launch_bounds__(1024) chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f,
-                                                              const double* __restrict__ df, int N, const double* __restrict__ state,
-                                                              double* __restrict__ aa, double* __restrict__ H) {
-    __shared__ double red[33];
+// One call moves ~32 N doubles through dependent global round trips; a single CTA needed 41-58 us for that at N = 5200 (latency of
+// one SM's load path, not arithmetic).  A thread-block cluster of 8 CTAs splits the elements; the partial sums of the normal
+// equations meet through distributed shared memory (fixed order: by cluster rank), every CTA solves the 5 x 5 system redundantly.
+__global__ void __cluster_dims__(AA_CL, 1, 1) __launch_bounds__(1024)
+chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f, const double* __restrict__ df, int N,
+                      const double* __restrict__ state, double* __restrict__ aa, double* __restrict__ H) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned rank = cl.block_rank();
+    constexpr int NPAIR = AA_M * (AA_M + 1) / 2, NV = NPAIR + AA_M;
+    __shared__ double part_s[NV];
+    __shared__ double red_multi[32 * NV];
     __shared__ double gam[AA_M];
     __shared__ int nh_s;
-    if (state[4] == 1.0 || state[4] == 3.0) return;                      // converged or rejected for good: nothing to mix
     double* dR = H;
     double* dGf = H + (long long)AA_M * N;
     double* dGa = H + 2LL * AA_M * N;
     double* pr = H + 3LL * AA_M * N;
     double* pgf = pr + N;
     double* pga = pgf + N;
+    const double stop = state[4];
     const bool plain = state[14] == 1.0;
     const double rel = state[1];
     int nh = (int)aa[0], slot = (int)aa[1];
     const double rel_prev = aa[2];
     bool have_prev = aa[3] == 1.0;
-    __syncthreads();                                                     // everybody has read the state
+    cl.sync();                                                           // every CTA has read the state (rank 0 writes aa below)
+    if (stop == 1.0 || stop == 3.0) return;                              // converged or rejected for good: nothing to mix
     if (!plain || (have_prev && rel > 1.5 * rel_prev)) {
         // a damped / extrapolated / rejected step, or a residual that grew: the history no longer describes one linear map
-        if (threadIdx.x == 0) { aa[0] = 0.0; aa[1] = 0.0; aa[2] = rel; aa[3] = 0.0; }
+        if (rank == 0 && threadIdx.x == 0) { aa[0] = 0.0; aa[1] = 0.0; aa[2] = rel; aa[3] = 0.0; }
         if (!plain) return;
         nh = 0;
         slot = 0;
         have_prev = false;
     }
-    // append the newest differences (needs the previous (r, g)); then remember the current ones
-    if (have_prev) {
-        for (int i = threadIdx.x; i < N; i += 1024) {
-            dR[(long long)slot * N + i] = df[i] - pr[i];
-            dGf[(long long)slot * N + i] = f[i] - pgf[i];
-            dGa[(long long)slot * N + i] = alpha[i] - pga[i];
+    const int per = (N + AA_CL - 1) / AA_CL, lo = (int)rank * per, hi = min(N, lo + per);
+    // append the newest differences (needs the previous (r, g)) and remember the current ones; a thread only ever re-reads
+    // elements it wrote itself, so no barrier is needed between the passes
+    {
+        double* dRs = dR + (long long)slot * N;
+        double* dGfs = dGf + (long long)slot * N;
+        double* dGas = dGa + (long long)slot * N;
+        for (int i = lo + threadIdx.x; i < hi; i += 1024) {
+            const double r = df[i], gf = f[i], ga = alpha[i];
+            if (have_prev) {
+                dRs[i] = r - pr[i];
+                dGfs[i] = gf - pgf[i];
+                dGas[i] = ga - pga[i];
+            }
+            pr[i] = r;
+            pgf[i] = gf;
+            pga[i] = ga;
         }
-        nh = min(nh + 1, AA_M);
-        slot = (slot + 1) % AA_M;
-    }
-    for (int i = threadIdx.x; i < N; i += 1024) {
-        pr[i] = df[i];
-        pgf[i] = f[i];
-        pga[i] = alpha[i];
-    }
-    __syncthreads();
-    // normal equations A gamma = b, A_ij = <dR_i, dR_j>, b_i = <dR_i, r>
-    double A[AA_M][AA_M], bb[AA_M];
-    for (int i = 0; i < nh; ++i) {
-        for (int j = 0; j <= i; ++j) {
-            double sacc = 0.0;
-            for (int k = threadIdx.x; k < N; k += 1024) sacc = fma(dR[(long long)i * N + k], dR[(long long)j * N + k], sacc);
-            A[i][j] = A[j][i] = block_sum(sacc, red);
+        if (have_prev) {
+            nh = min(nh + 1, AA_M);
+            slot = (slot + 1) % AA_M;
         }
-        double sacc = 0.0;
-        for (int k = threadIdx.x; k < N; k += 1024) sacc = fma(dR[(long long)i * N + k], df[k], sacc);
-        bb[i] = block_sum(sacc, red);
     }
+    // normal equations A gamma = b, A_ij = <dR_i, dR_j>, b_i = <dR_i, r>: all products in one pass, one multi-value reduction
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (int k = lo + threadIdx.x; k < hi; k += 1024) {
+        double dv[AA_M];
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i) dv[i] = (i < nh) ? dR[(long long)i * N + k] : 0.0;
+        const double rk = df[k];
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) { acc[idx] = fma(dv[i], dv[j], acc[idx]); ++idx; }
+            acc[NPAIR + i] = fma(dv[i], rk, acc[NPAIR + i]);
+        }
+    }
+    block_sum_multi<NV>(acc, red_multi);
     if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) part_s[i] = acc[i];
+    }
+    cl.sync();                                                           // every CTA's partial sums are in its shared memory
+    if (threadIdx.x == 0) {
+        double tot[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) tot[i] = 0.0;
+        for (unsigned r = 0; r < AA_CL; ++r) {                           // fixed order: identical totals in every CTA
+            const double* rp = cl.map_shared_rank(part_s, r);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) tot[i] += rp[i];
+        }
+        double A[AA_M][AA_M], bb[AA_M];
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) { A[i][j] = A[j][i] = tot[idx]; ++idx; }
+            bb[i] = tot[NPAIR + i];
+        }
         double tr = 0.0;
         for (int i = 0; i < nh; ++i) tr += A[i][i];
         for (int i = 0; i < nh; ++i) A[i][i] += 1e-10 * tr + 1e-300;     // damping: nearly collinear differences
-        // Gaussian elimination with partial pivoting (order <= 3)
-        int idx[AA_M];
-        for (int i = 0; i < nh; ++i) idx[i] = i;
         bool ok = true;
-        for (int c = 0; c < nh && ok; ++c) {
+        for (int c = 0; c < nh && ok; ++c) {                             // Gaussian elimination with partial pivoting
             int p = c;
             for (int r2 = c + 1; r2 < nh; ++r2) if (fabs(A[r2][c]) > fabs(A[p][c])) p = r2;
             if (A[p][c] == 0.0) { ok = false; break; }
@@ -424,15 +468,16 @@ __global__ void __launch_bounds__(1024) chord_anderson_kernel(double* __restrict
             if (!(fabs(gam[i]) < 1e3)) ok = false;
         }
         nh_s = ok ? nh : 0;
-        aa[0] = ok ? nh : 0;
-        aa[1] = ok ? slot : 0;
-        aa[2] = rel;
-        aa[3] = 1.0;                                                      // (prev r, g) are valid from now on
+        if (rank == 0) {
+            aa[0] = ok ? nh : 0;
+            aa[1] = ok ? slot : 0;
+            aa[2] = rel;
+            aa[3] = 1.0;                                                  // (prev r, g) are valid from now on
+        }
     }
     __syncthreads();
     const int nm = nh_s;
-    if (nm == 0) return;
-    for (int i = threadIdx.x; i < N; i += 1024) {
+    for (int i = lo + threadIdx.x; i < hi && nm > 0; i += 1024) {
         double cf = 0.0, ca = 0.0;
         for (int j = 0; j < nm; ++j) {
             cf = fma(gam[j], dGf[(long long)j * N + i], cf);
@@ -441,6 +486,7 @@ __global__ void __launch_bounds__(1024) chord_anderson_kernel(double* __restrict
         f[i] -= cf;
         alpha[i] -= ca;
     }
+    cl.sync();                                  // nobody leaves while another CTA may still read its partial sums
 }
 
 // dense Lambda (public attr GPModel.Lambda_MAP): one thread per row of the output
@@ -960,7 +1006,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 PPBO_CL chord_lik_kernel<<<set_blocks, 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.state, ws.set_part, anderson ? ws.part0 : nullptr);
                 PPBO_CL chord_decide_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, m, ws.state, ws.hist,
                                                                   (chord_extrapolate && !anderson) ? 1 : 0, anderson ? ws.part0 : nullptr);
-                if (anderson) PPBO_CL chord_anderson_kernel<<<1, 1024, 0, st>>>(alpha, f_map, ws.df, N, ws.state, ws.aa, ws.aaH);
+                if (anderson) PPBO_CL chord_anderson_kernel<<<AA_CL, 1024, 0, st>>>(alpha, f_map, ws.df, N, ws.state, ws.aa, ws.aaH);
             }
             PPBO_LAUNCH_CHECK();
             PPBO_CUDA_CHECK(readback().add(state_h, ws.state, sizeof(state_h), st));
@@ -1009,9 +1055,10 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         if ((rc = gemv(Sigma, lds, N, N, ws.bvec, ws.Sb, st))) return rc;
         PPBO_CL diff_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.Sb, ws.sa, Q, m, ws.t);
         if (!identity_factor) {
-            // From the second factorisation on the factor is very likely reused by chord steps, which need the 1024-block
-            // inverses anyway: build them now and let this solve use them too (0.16 ms against 0.48 ms for the chained solve).
-            if (n_factor >= 2 && M >= 2048 && !binv_valid) {
+            // From the second factorisation on -- and for the first one of a cold fit, which enters the Anderson-mixed chord phase
+            // with it -- the factor is very likely reused by chord steps, which need the 1024-block inverses anyway: build them now
+            // and let this solve use them too (0.13 ms against 0.48 ms for the chained solve).
+            if ((n_factor >= 2 || (anderson_mode >= 2 && !warm_factor && !aa_failed)) && M >= 2048 && !binv_valid) {
                 if ((rc = blockinv_build(Lfac, ldl, M, Mdinv, ws.binv, st))) return rc;
                 binv_valid = true;
             }

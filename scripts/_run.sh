@@ -1,2 +1,2 @@
-ncu --set full --clock-control none --import-source on -k regex:kernel_matrix_stream -c 12 -o gpurun_out/r02_gram python scripts/gram_probe.py > gpurun_out/prof_gram.log 2>&1; tail -3 gpurun_out/prof_gram.log
-ls -la gpurun_out/r02_gram.ncu-rep
+python scripts/timeline.py --mode gpfit --dump gpurun_out/seq_gpfit.txt 2>&1 | tail -1
+python -m pytest tests/test_full_size.py tests/test_gpu_ops.py tests/test_incremental.py tests/test_src_full_size.py -m gpu -x -q > gpurun_out/pytest_t10.log 2>&1; tail -3 gpurun_out/pytest_t10.log

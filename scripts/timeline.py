@@ -48,6 +48,23 @@ def main():
         d = {"block": blocks[i], "W": res["W"], "b": res["b"], "grids": res["grids"]}
         return iteration.run_iteration(d, kernel, theta, Q0 + i + 1, m, S, seed=1, state=state)
 
+    if args.mode == "gpfit":            # the cold GP fit alone (one stream of the caller + the library's Cholesky streams)
+        from ppbo_b200 import ops
+        for _ in range(3):
+            g = iteration.gp_fit(res["X"], kernel, theta, Q0, m, tol=1e-8)
+        torch.cuda.synchronize()
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            g = iteration.gp_fit(res["X"], kernel, theta, Q0, m, tol=1e-8)
+            torch.cuda.synchronize()
+        prof.export_chrome_trace("/tmp/ppbo_trace.json")
+        ev = sorted((e for e in json.load(open("/tmp/ppbo_trace.json"))["traceEvents"] if e.get("cat") == "kernel"), key=lambda e: e["ts"])
+        t0 = ev[0]["ts"]
+        with open(args.dump or "gpurun_out/seq_gpfit.txt", "w") as fh:
+            fh.write("# cold GP fit alone: %.2f ms, %d kernels, stats %s\n" % ((max(e["ts"] + e["dur"] for e in ev) - t0) / 1e3, len(ev), g.lap.stats))
+            for e in ev:
+                fh.write("s%-4d %9.1f %8.1f  %s grid=%s\n" % (e["args"]["stream"], e["ts"] - t0, e["dur"], short(e["name"]), e["args"].get("grid", "")))
+        return
     keep = []
     if args.mode == "cold":
         for _ in range(3):
