@@ -261,12 +261,19 @@ def iteration_slices():
     return iteration.SAMPLING_SLICES
 
 
+def iteration_reserved_sms():
+    from ppbo_b200 import iteration
+    return iteration.OVERLAP_RESERVED_SMS if iteration.OVERLAP_SAMPLING else 0
+
+
 def workload_config(prob, n_gpus):
     return {"workload": "%s: D=%d, Q=%d queries x m=%d (N=%d rows, %d pseudo-observations), %s theta=%s, F=%d RFF features, "
                         "%d query directions x P=%d xi-grid points, S=%d samples" % (
                             prob["name"], prob["D"], prob["Q"], prob["m"], prob["N"], prob["Q"] * prob["m"], prob["kernel"],
                             prob["theta"], prob["F"], prob["grids"].shape[0], prob["P"], prob["S"]),
-            "parallelism": ("GP fit + weight-space fit (background thread) + all S samples on one GPU" if n_gpus == 1 else
+            "parallelism": ("one GPU, two concurrent chains: weight-space fit -> draws -> INT8 contraction (foreground streams, persistent "
+                            "grid on all but %d SMs) || GP fit -> mu* (background thread, lowest stream priority, on the SMs left free); "
+                            "only the reduction of 3 x directions sums needs both" % iteration_reserved_sms() if n_gpus == 1 else
                             "GP fit on rank 0, weight-space fit on rank 1, broadcast of (omega_MAP, diag Hessian); S sharded over the "
                             "ranks by measured stage times (rank 0 samples only if its fit ends before the others would); mu* candidates "
                             "sharded from 3 ranks on (all-reduce max); one all-reduce of 3 x directions doubles"),
@@ -766,6 +773,9 @@ def main():
         "clocks": clk,
         "roofline": roof,
         "stages_ms": merge(cold_stages),
+        "stages_note": ("one GPU: rff_fit and sampling time the foreground chain (weight-space fit, then draws + INT8 contraction); the GP "
+                        "fit and mu* run concurrently on the background thread, gp_tail is what is left of them when the contraction "
+                        "has ended" if world == 1 else "rank 0's stages; sampling_other_ranks_mean / rff_fit_rank1 from the other ranks"),
         "steady_state": {"value": ms_steady, "unit": UNIT, "what": "e2e (pinned host buffers in, sums out) per appended query, queries %d..%d "
                          "appended to the fitted %d-query model" % (Q0 + W_steps + 1, Q0 + W_steps + K, Q0),
                          "h2d_bytes_per_step": int(blocks_host[0].numel() * 8 + sum(inputs.host[k].numel() * 8 for k in ("W", "b", "grids"))),

@@ -198,3 +198,33 @@ def test_warm_append_reaches_the_same_mode(case):
     Xp = ops.to_dev(np.concatenate([p["grids"][b][sub] for b in ids]))
     _, Sp = ops.predict(p["kernel"], st.X, p["theta"][1], p["theta"][2], 1e-6, st.lap, Xp, len(sub), len(ids))
     assert np.abs(_np(Sp) - fx["cov_grids"]).max() <= 1e-6 * p["theta"][2] ** 2
+
+
+def test_overlapped_pipeline_equals_sequential(case):
+    """One GPU: run_iteration with the sampling contraction overlapped with the GP fit (two host threads, contraction on a
+    persistent grid that leaves SMs to the fit) returns bit for bit the sums of the sequential order -- cold and after an appended
+    comparison set -- and those sums select the fixture's direction on its 2048-sample slice."""
+    p, fx, it, ops = case.prob, case.fx, case.it, case.ops
+    m, Q, S = p["m"], p["Q"], int(fx["slice_samples"])
+    B, P, D = p["grids"].shape
+    if it.sampling_engine(S, P, p["F"]) != "i8":
+        pytest.skip("contraction below the INT8 threshold: nothing to overlap")
+    n1 = (Q - 1) * (m + 1)
+    d_cold = {"X": case.X[:n1].contiguous(), "W": case.W, "b": case.b, "grids": case.grids}
+    d_warm = {"block": case.X[n1:].contiguous(), "W": case.W, "b": case.b, "grids": case.grids}
+    out = {}
+    saved = it.OVERLAP_SAMPLING
+    try:
+        for mode in (True, False):
+            it.OVERLAP_SAMPLING = mode
+            st = it.IterationState(p["kernel"], p["theta"], D, m, Q, case.X.device, case.W, case.b)
+            s0, _, _ = it.run_iteration(d_cold, p["kernel"], p["theta"], Q - 1, m, S, seed=int(fx["seed"]), state=st)
+            s1, gp, rff = it.run_iteration(d_warm, p["kernel"], p["theta"], Q, m, S, seed=int(fx["seed"]), state=st)
+            torch.cuda.synchronize()
+            out[mode] = (s0.clone(), s1.clone(), gp.f_map.clone(), rff.omega_map.clone())
+    finally:
+        it.OVERLAP_SAMPLING = saved
+    for a, b_ in zip(out[True], out[False]):
+        assert torch.equal(a, b_)
+    ei, _ = it.acquisition_values(_np(out[True][1]), S)
+    assert int(np.argmax(ei)) == int(fx["slice_direction"])
