@@ -255,6 +255,11 @@ long long ppbo_rff_factor_cache_doubles(int F);
 int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega0,
                  int max_iter, double tol, double* factor_cache, int warm_factor, double* omega_map, double* hess_diag,
                  void* workspace, long long workspace_bytes, double* stats_h, void* stream);
+/* Hessian factor (and its block inverses) AT omega into factor_cache, asynchronously and without a host synchronisation: what the
+ * next ppbo_rff_fit(..., warm_factor = 2) of a grown design starts with.  (The reference's trust-exact run rebuilds its Hessian
+ * at every one of its iterations, src/random_fourier_sampler.py:124-132.) */
+int ppbo_rff_refactor(const double* Phi_X, long long ld, int F, int Q, int m, double sigma, const double* omega,
+                      double* factor_cache, void* workspace, long long workspace_bytes, void* stream);
 /* out[i] = standard normal number (offset + i) of Philox4x32-10 stream `stream_id` under `seed` (Box-Muller on 53-bit uniforms).
  * Counter-based: the value of a given index does not depend on launch shape or on which GPU draws it.  Replaces the host
  * np.random draws of the reference where the caller does not inject its own (oracle: oracle/ppbo_oracle.py philox_normals). */

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "ppbo_rff_objective": (_I, [_P, _L, _I, _I, _I, _D, _P, _PD, _P, _P, _P, _L, _P]),
     "ppbo_rff_factor_cache_doubles": (_L, [_I]),
     "ppbo_rff_fit": (_I, [_P, _L, _I, _I, _I, _D, _P, _I, _D, _P, _I, _P, _P, _P, _L, _PD, _P]),
+    "ppbo_rff_refactor": (_I, [_P, _L, _I, _I, _I, _D, _P, _P, _P, _L, _P]),
     "ppbo_normal_fill": (_I, [c_ulonglong, c_uint, _L, _P, _L, _P]),
     "ppbo_rff_sample_omega": (_I, [_P, _P, _P, _L, c_ulonglong, c_uint, _L, _I, _I, _P, _L, _P]),
     "ppbo_rff_eval_argmax": (_I, [_P, _L, _I, _I, _P, _L, _L, _I, _I, _P, _P, _P, _P]),

@@ -343,20 +343,23 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
 //   * replaces (alpha, f) by g_k - dG gamma   (f = Sigma alpha is preserved: both are the same combination).
 // The history is dropped when a step was damped / extrapolated / rejected, or when the residual grew.  Fixed summation order.
 constexpr int AA_M = 5;
-constexpr int AA_CL = 8;       // CTAs of the cluster that shares one call (each takes N / 8 elements)
+constexpr int AA_CL = 8;       // CTAs of the cluster that shares one call (each takes N / 8 elements); 1 on a background thread
 //   aa: [0] history length, [1] next slot, [2] residual norm (max |df| / max |f|) seen by the previous call
 //   H: [3 * AA_M + 3][N]: dR[AA_M], dGf[AA_M], dGa[AA_M], prev r, prev g_f, prev g_a
 // One call moves ~32 N doubles through dependent global round trips; a single CTA needed 41-58 us for that at N = 5200 (latency of
 // one SM's load path, not arithmetic).  A thread-block cluster of 8 CTAs splits the elements; the partial sums of the normal
 // equations meet through distributed shared memory (fixed order: by cluster rank), every CTA solves the 5 x 5 system redundantly.
-__global__ void __cluster_dims__(AA_CL, 1, 1) __launch_bounds__(1024)
+// A fit on a background host thread (the GP chain of the overlapped one-GPU pipeline, which lives on the ~20 SMs the sampling
+// contraction leaves free) launches a cluster of ONE: eight co-scheduled 1024-thread CTAs rarely find room there, and the chain
+// stalled for milliseconds waiting for a slot (measured: +1.8 ms on the cold iteration).
+__global__ void __launch_bounds__(1024)
 chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f, const double* __restrict__ df, int N,
                       const double* __restrict__ state, double* __restrict__ aa, double* __restrict__ H) {
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
-    const unsigned rank = cl.block_rank();
+    const unsigned rank = cl.block_rank(), ncta = cl.num_blocks();       // cluster size chosen at launch (launch_chord_anderson)
     constexpr int NPAIR = AA_M * (AA_M + 1) / 2, NV = NPAIR + AA_M;
-    __shared__ double part_s[NV];
+    __shared__ double part_s[AA_CL * NV];                                // partial sums of this CTA's slices
     __shared__ double red_multi[32 * NV];
     __shared__ double gam[AA_M];
     __shared__ int nh_s;
@@ -382,13 +385,17 @@ chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f, const 
         slot = 0;
         have_prev = false;
     }
-    const int per = (N + AA_CL - 1) / AA_CL, lo = (int)rank * per, hi = min(N, lo + per);
+    // The elements are cut into AA_CL fixed slices; CTA `rank` of a cluster of ncta takes the slices rank, rank + ncta, ...: the
+    // partial sums -- and with them every bit of the result -- do not depend on the cluster size.
+    const int per = (N + AA_CL - 1) / AA_CL;
     // append the newest differences (needs the previous (r, g)) and remember the current ones; a thread only ever re-reads
     // elements it wrote itself, so no barrier is needed between the passes
-    {
-        double* dRs = dR + (long long)slot * N;
-        double* dGfs = dGf + (long long)slot * N;
-        double* dGas = dGa + (long long)slot * N;
+    const int slot_w = slot;
+    for (int v = (int)rank; v < AA_CL; v += (int)ncta) {
+        const int lo = v * per, hi = min(N, lo + per);
+        double* dRs = dR + (long long)slot_w * N;
+        double* dGfs = dGf + (long long)slot_w * N;
+        double* dGas = dGa + (long long)slot_w * N;
         for (int i = lo + threadIdx.x; i < hi; i += 1024) {
             const double r = df[i], gf = f[i], ga = alpha[i];
             if (have_prev) {
@@ -400,40 +407,43 @@ chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f, const 
             pgf[i] = gf;
             pga[i] = ga;
         }
-        if (have_prev) {
-            nh = min(nh + 1, AA_M);
-            slot = (slot + 1) % AA_M;
-        }
     }
-    // normal equations A gamma = b, A_ij = <dR_i, dR_j>, b_i = <dR_i, r>: all products in one pass, one multi-value reduction
-    double acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (int k = lo + threadIdx.x; k < hi; k += 1024) {
-        double dv[AA_M];
-#pragma unroll
-        for (int i = 0; i < AA_M; ++i) dv[i] = (i < nh) ? dR[(long long)i * N + k] : 0.0;
-        const double rk = df[k];
-        int idx = 0;
-#pragma unroll
-        for (int i = 0; i < AA_M; ++i) {
-#pragma unroll
-            for (int j = 0; j <= i; ++j) { acc[idx] = fma(dv[i], dv[j], acc[idx]); ++idx; }
-            acc[NPAIR + i] = fma(dv[i], rk, acc[NPAIR + i]);
-        }
+    if (have_prev) {
+        nh = min(nh + 1, AA_M);
+        slot = (slot + 1) % AA_M;
     }
-    block_sum_multi<NV>(acc, red_multi);
-    if (threadIdx.x == 0) {
+    // normal equations A gamma = b, A_ij = <dR_i, dR_j>, b_i = <dR_i, r>: all products in one pass, one multi-value reduction per slice
+    for (int v = (int)rank, vl = 0; v < AA_CL; v += (int)ncta, ++vl) {
+        const int lo = v * per, hi = min(N, lo + per);
+        double acc[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) part_s[i] = acc[i];
+        for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+        for (int k = lo + threadIdx.x; k < hi; k += 1024) {
+            double dv[AA_M];
+#pragma unroll
+            for (int i = 0; i < AA_M; ++i) dv[i] = (i < nh) ? dR[(long long)i * N + k] : 0.0;
+            const double rk = df[k];
+            int idx = 0;
+#pragma unroll
+            for (int i = 0; i < AA_M; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) { acc[idx] = fma(dv[i], dv[j], acc[idx]); ++idx; }
+                acc[NPAIR + i] = fma(dv[i], rk, acc[NPAIR + i]);
+            }
+        }
+        block_sum_multi<NV>(acc, red_multi);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) part_s[vl * NV + i] = acc[i];
+        }
     }
     cl.sync();                                                           // every CTA's partial sums are in its shared memory
     if (threadIdx.x == 0) {
         double tot[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) tot[i] = 0.0;
-        for (unsigned r = 0; r < AA_CL; ++r) {                           // fixed order: identical totals in every CTA
-            const double* rp = cl.map_shared_rank(part_s, r);
+        for (int v = 0; v < AA_CL; ++v) {                                // fixed order (by slice): identical totals in every CTA
+            const double* rp = cl.map_shared_rank(part_s, (unsigned)v % ncta) + (v / (int)ncta) * NV;
 #pragma unroll
             for (int i = 0; i < NV; ++i) tot[i] += rp[i];
         }
@@ -477,14 +487,17 @@ chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f, const 
     }
     __syncthreads();
     const int nm = nh_s;
-    for (int i = lo + threadIdx.x; i < hi && nm > 0; i += 1024) {
-        double cf = 0.0, ca = 0.0;
-        for (int j = 0; j < nm; ++j) {
-            cf = fma(gam[j], dGf[(long long)j * N + i], cf);
-            ca = fma(gam[j], dGa[(long long)j * N + i], ca);
+    for (int v = (int)rank; v < AA_CL && nm > 0; v += (int)ncta) {
+        const int lo = v * per, hi = min(N, lo + per);
+        for (int i = lo + threadIdx.x; i < hi; i += 1024) {
+            double cf = 0.0, ca = 0.0;
+            for (int j = 0; j < nm; ++j) {
+                cf = fma(gam[j], dGf[(long long)j * N + i], cf);
+                ca = fma(gam[j], dGa[(long long)j * N + i], ca);
+            }
+            f[i] -= cf;
+            alpha[i] -= ca;
         }
-        f[i] -= cf;
-        alpha[i] -= ca;
     }
     cl.sync();                                  // nobody leaves while another CTA may still read its partial sums
 }
@@ -623,6 +636,27 @@ __global__ void __launch_bounds__(256) border_write_rows_kernel(const double* __
                                                                 int M_old, int nb, int b0, double* __restrict__ L, long long ldl) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x, u = blockIdx.y;
     if (v < b0) L[(long long)(M_old + u) * ldl + v] = s_new[u] * R[(long long)u * ldr + v];
+}
+
+bool thread_is_background();        // linalg.cu
+static int launch_chord_anderson(double* alpha, double* f, const double* df, int N, const double* state, double* aa, double* H,
+                                 cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    const unsigned ncta = thread_is_background() ? 1u : (unsigned)AA_CL;
+    cfg.gridDim = dim3(ncta);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ++g_launch_count;
+    PPBO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, chord_anderson_kernel, alpha, f, df, N, state, aa, H));
+    return PPBO_OK;
 }
 
 int launch_lik_terms(const double* f, int Q, int m, double sigma, double* set_lik, double* beta, double* arrow, double* sa,
@@ -939,9 +973,13 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             PPBO_CL border_corner_kernel<<<ceil_div(nb * nb, 256), 256, 0, st>>>(G, ldg, M_old, nb, ws.bC);
             PPBO_LAUNCH_CHECK();
             if ((rc = trsm_right_blockinv(Lfac, ldl, M_old, ws.binv, ws.bT, Mp, ws.bR, Mp, nb, st))) return rc;
-            GemmOperands g{ws.bR, Mp, 0, ws.bR, Mp, 0, nb, nb, M_old};
-            StoreEpilogue ep{ws.bC, nb, 0, -1.0, 1.0, 0, 0, 0};
-            if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;                 // C = G_nn - R R'
+            if (nb <= 32) {                                                     // C = G_nn - R R' (25 x 25 with K = 5000)
+                if ((rc = skinny_nt(ws.bR, Mp, nb, ws.bR, Mp, nb, M_old, -1.0, 1.0, ws.bC, nb, st))) return rc;
+            } else {
+                GemmOperands g{ws.bR, Mp, 0, ws.bR, Mp, 0, nb, nb, M_old};
+                StoreEpilogue ep{ws.bC, nb, 0, -1.0, 1.0, 0, 0, 0};
+                if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
+            }
         }
         // T at the start (the chord acceptance test compares against it): -1/2 alpha.f - lik(f)/m
         PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, nullptr, nullptr, nullptr);
@@ -987,6 +1025,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             rho = std::fmin(std::fmax(rho, 0.02), (anderson || (warm_factor && n_factor == 0)) ? 0.85 : 0.5);
             int kb = !std::isfinite(last_rel) ? 3 : (last_rel > tol) ? (int)std::ceil(std::log(tol / last_rel) / std::log(rho)) : 1;
             if (first_chord_batch) kb = std::min(kb, 3);
+            // warm (bordered) fits converge faster than their contraction predicts once an Aitken step lands; every queued step
+            // behind the converging one still costs ~26 no-op launches (0.15 ms), a batch boundary one synchronise (0.03 ms)
+            if (warm_factor && n_factor == 0) kb = std::min(kb, 4);
             kb = std::max(1, std::min(kb, std::min(CHORD_BATCH_MAX, max_iter - it)));
             first_chord_batch = false;
             const double slow = (warm_factor && n_factor == 0) ? 0.85 : 0.5;
@@ -1006,7 +1047,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 PPBO_CL chord_lik_kernel<<<set_blocks, 256, 0, st>>>(f_map, ws.df, Q, m, sigma, ws.state, ws.set_part, anderson ? ws.part0 : nullptr);
                 PPBO_CL chord_decide_kernel<<<1, 1024, 0, st>>>(alpha, ws.dalpha, f_map, ws.df, N, ws.set_part, Q, m, ws.state, ws.hist,
                                                                   (chord_extrapolate && !anderson) ? 1 : 0, anderson ? ws.part0 : nullptr);
-                if (anderson) PPBO_CL chord_anderson_kernel<<<AA_CL, 1024, 0, st>>>(alpha, f_map, ws.df, N, ws.state, ws.aa, ws.aaH);
+                if (anderson && (rc = launch_chord_anderson(alpha, f_map, ws.df, N, ws.state, ws.aa, ws.aaH, st))) return rc;
             }
             PPBO_LAUNCH_CHECK();
             PPBO_CUDA_CHECK(readback().add(state_h, ws.state, sizeof(state_h), st));

@@ -47,6 +47,12 @@ CONCURRENT_FITS = True
 # PPBO_OVERLAP_SAMPLING=0 restores the sequential order (diagnostics).
 import os as _os
 OVERLAP_RESERVED_SMS = int(_os.environ.get("PPBO_OVERLAP_RESERVE", "20"))
+# Steady state of the overlapped pipeline, opt-in: refresh the weight-space Hessian factor at each new optimum while the contraction
+# runs (RFFState.refresh_factor).  The next fit then needs 10 chord steps and never a mid-fit refactorisation (13 steps and a
+# refactorisation every ~4th iteration with the stale factor), but the refresh (10 GFLOP of Hessian GEMM + a Cholesky) shares
+# the reserved SMs with the GP chain, which then ends AFTER the contraction: 14.05 ms per appended iteration against 13.09 without
+# (measured), so it is off.
+REFRESH_RFF_FACTOR = _os.environ.get("PPBO_RFF_REFRESH", "0") != "0"
 OVERLAP_SAMPLING = _os.environ.get("PPBO_OVERLAP_SAMPLING", "1") != "0"
 
 
@@ -293,6 +299,7 @@ class RFFState:
         self.Phi_cap = torch.empty((W.shape[0], Q_cap * (m + 1)), dtype=F64, device=W.device)
         self.factor_cache = ops.rff_factor_cache(W.shape[0], W.device)
         self.fit = None
+        self.pending = None          # stream of an asynchronous refresh of the factor (refresh_factor): the next fit waits for it
 
     def _fit(self, Q, omega0, warm=False):
         r = RFFFit()
@@ -305,7 +312,23 @@ class RFFState:
         self.Q, self.fit = Q, r
         return r
 
+    def _wait_refresh(self):
+        if self.pending is not None:
+            torch.cuda.current_stream().wait_stream(self.pending)
+            self.pending = None
+
+    def refresh_factor(self):
+        """Rebuild the Hessian factor (and its block inverses) at the optimum just found, asynchronously on the CURRENT stream: the
+        next append then starts its chord steps from a factor built at its own starting point (ppbo_rff_refactor).  The caller
+        runs this off the critical path and leaves the stream in self.pending."""
+        r = self.fit
+        ops.rff_refactor(r.Phi_X, self.Q, self.m, self.theta[0], r.omega_map, self.factor_cache)
+        r.stats["warm"] = True
+        r.stats["binv_cached"] = True
+        self.pending = torch.cuda.current_stream()
+
     def cold(self, X, omega0=None):
+        self._wait_refresh()
         Q = X.shape[0] // (self.m + 1)
         ops.rff_features(self.W, self.b, X, self.theta[2], True, out=self.Phi_cap[:, :X.shape[0]])
         return self._fit(Q, omega0)
@@ -313,6 +336,7 @@ class RFFState:
     def append(self, X_block):
         if self.Q == 0:
             return self.cold(X_block)
+        self._wait_refresh()
         N_old = self.Q * (self.m + 1)
         ops.rff_features(self.W, self.b, X_block, self.theta[2], True, out=self.Phi_cap[:, N_old:N_old + X_block.shape[0]])
         warm = self.fit.stats.get("factorizations", 0) > 0 or self.fit.stats.get("warm", False)
@@ -454,7 +478,7 @@ _SIDE_STREAMS = {}
 # Cholesky bulk (library-internal side stream) sits at the same level, and the background weight-space fit keeps the default
 # (lowest) priority for everything (ppbo_set_thread_background), so it only fills the SMs the GP fit leaves idle.
 # None / 0: stay on the caller's stream.
-GP_STREAM_PRIORITY = -1
+GP_STREAM_PRIORITY = int(_os.environ.get("PPBO_FG_PRIORITY", "-1"))
 _WORKER = None
 
 
@@ -608,6 +632,8 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
             with torch.cuda.stream(fg):
                 rff = fit_rff()
                 mark("rff_fit")
+                fit_done = torch.cuda.Event()
+                fit_done.record(fg)
                 prepared = rff_prepare_samples(rff, lo, hi, P, seed=seed)
                 fg.wait_stream(grid_stream)
                 for t in (PhiT.PhiT, PhiT.planes, PhiT.scale):
@@ -618,6 +644,14 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
                 finally:
                     lib.ppbo_set_tuning(14, 0)
                 mark("sampling")
+            if warm and REFRESH_RFF_FACTOR:
+                # while the contraction runs: the weight-space Hessian factor at the new optimum, for the NEXT iteration's fit
+                # (lowest priority, on the SMs the contraction leaves free; it only waits for this iteration's fit)
+                rf = _side_stream(dev, tag="rff_refresh")
+                rf.wait_event(fit_done)
+                rff.omega_map.record_stream(rf)
+                with torch.cuda.stream(rf):
+                    state.rff.refresh_factor()
         finally:
             gp, mustar = fut.result()          # re-raises on this thread
         main.wait_stream(bg)

@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--out", default=None)
     ap.add_argument("--bucket", type=float, default=0.25)
+    ap.add_argument("--api", action="store_true", help="also record the runtime API calls: the dump then shows how long after its launch call "
+                    "each kernel started (host-side or device-side delay?)")
     ap.add_argument("--dump", default=None, help="file for the full kernel sequence (stream, start us, duration us, name) of the last iteration")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -76,15 +78,18 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
     marks = []
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU] if args.api else [ProfilerActivity.CUDA]) as prof:
         for k in range(args.steps):
             torch.cuda.synchronize()
             keep.append(cold() if args.mode == "cold" else steady(3 + k))
             torch.cuda.synchronize()
     tmp = "/tmp/ppbo_trace.json"
     prof.export_chrome_trace(tmp)
-    ev = [e for e in json.load(open(tmp))["traceEvents"] if e.get("cat") == "kernel"]
+    allev = json.load(open(tmp))["traceEvents"]
+    ev = [e for e in allev if e.get("cat") == "kernel"]
     ev.sort(key=lambda e: e["ts"])
+    launch_ts = {e["args"]["correlation"]: (e["ts"], e.get("tid"), e.get("dur", 0)) for e in allev
+                 if e.get("cat") == "cuda_runtime" and "correlation" in e.get("args", {})}
     out = open(args.out, "w") if args.out else sys.stdout
     # an iteration ends with its acq_reduce_kernel (the reduction of the sampled maxima)
     steps, cur = [], []
@@ -135,12 +140,15 @@ def main():
     if args.out:
         out.close()
     if args.dump:
-        st = steps[-1]
-        t0 = st[0]["ts"]
         with open(args.dump, "w") as fh:
-            for e in st:
-                g = e["args"].get("grid", "")
-                fh.write("s%-4d %9.1f %8.1f  %s grid=%s\n" % (e["args"]["stream"], e["ts"] - t0, e["dur"], short(e["name"]), g))
+            for si, st in enumerate(steps):
+                t0 = st[0]["ts"]
+                fh.write("# iteration %d\n" % si)
+                for e in st:
+                    g = e["args"].get("grid", "")
+                    lt = launch_ts.get(e["args"].get("correlation"))
+                    extra = "  launched %9.1f (+%.1f, call %.1f us) tid %s" % (lt[0] - t0, e["ts"] - lt[0], lt[2], lt[1]) if lt else ""
+                    fh.write("s%-4d %9.1f %8.1f  %s grid=%s%s\n" % (e["args"]["stream"], e["ts"] - t0, e["dur"], short(e["name"]), g, extra))
 
 
 def short(n):
