@@ -566,6 +566,14 @@ __global__ void border_corner_kernel(const double* __restrict__ G, long long ldg
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nb * nb) Cb[e] = G[(long long)(M_old + e / nb) * ldg + M_old + e % nb];
 }
+// Cb[e] -= sum_p part[p][e]  (partial products R R' of the K chunks, fixed order)
+__global__ void border_corner_sum_kernel(const double* __restrict__ part, int nparts, int nb, double* __restrict__ Cb) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nb * nb) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += part[(long long)p * nb * nb + e];
+    Cb[e] -= s;
+}
 // One CTA: r = t_n - s_n (R z);  S = I + s_n C s_n;  y_n = S^-1 r  (Cholesky in shared memory);  t_n <- y_n,  w <- s_n y_n
 __global__ void __launch_bounds__(1024) border_solve_kernel(const double* __restrict__ R, long long ldr, const double* __restrict__ Cb,
                                                             const double* __restrict__ s_new, const double* __restrict__ z, int M_old,
@@ -973,13 +981,24 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             PPBO_CL border_corner_kernel<<<ceil_div(nb * nb, 256), 256, 0, st>>>(G, ldg, M_old, nb, ws.bC);
             PPBO_LAUNCH_CHECK();
             if ((rc = trsm_right_blockinv(Lfac, ldl, M_old, ws.binv, ws.bT, Mp, ws.bR, Mp, nb, st))) return rc;
-            if (nb <= 32) {                                                     // C = G_nn - R R' (25 x 25 with K = 5000)
-                if ((rc = skinny_nt(ws.bR, Mp, nb, ws.bR, Mp, nb, M_old, -1.0, 1.0, ws.bC, nb, st))) return rc;
-            } else {
-                GemmOperands g{ws.bR, Mp, 0, ws.bR, Mp, 0, nb, nb, M_old};
-                StoreEpilogue ep{ws.bC, nb, 0, -1.0, 1.0, 0, 0, 0};
+            // C = G_nn - R R' (25 x 25, K = M_old): as ONE product the tiled GEMM walks all of K on a single CTA (270 us at
+            // K = 5000); cut into 1024-column chunks it is a batched product of the same launch count whose partial results
+            // (in the scratch T, which the solve above has consumed) are added in chunk order by border_corner_sum_kernel.
+            // (One-warp-per-output-column kernels for these 25-row products, with and without a shared-memory stage for R, were
+            // measured and were no faster than the tiled GEMM: 45-110 us / 120-470 us per call against 55-60 us.)
+            const int KC = 1024, nfull = M_old / KC, krem = M_old - nfull * KC, nparts = nfull + (krem > 0 ? 1 : 0);
+            if (nfull > 0) {
+                GemmOperands g{ws.bR, Mp, KC, ws.bR, Mp, KC, nb, nb, KC};
+                StoreEpilogue ep{ws.bT, nb, (long long)nb * nb, 1.0, 0.0, 0, 0, 0};
+                if ((rc = launch_gemm_nt(g, ep, nfull, st))) return rc;
+            }
+            if (krem > 0) {
+                GemmOperands g{ws.bR + (long long)nfull * KC, Mp, 0, ws.bR + (long long)nfull * KC, Mp, 0, nb, nb, krem};
+                StoreEpilogue ep{ws.bT + (long long)nfull * nb * nb, nb, 0, 1.0, 0.0, 0, 0, 0};
                 if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
             }
+            PPBO_CL border_corner_sum_kernel<<<ceil_div(nb * nb, 256), 256, 0, st>>>(ws.bT, nparts, nb, ws.bC);
+            PPBO_LAUNCH_CHECK();
         }
         // T at the start (the chord acceptance test compares against it): -1/2 alpha.f - lik(f)/m
         PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, ws.arrow_tmp, nullptr, nullptr, nullptr, nullptr);

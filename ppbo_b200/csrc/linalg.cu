@@ -1608,74 +1608,12 @@ int potrs_vec_blockinv(const double* L, long long ldl, int n, double* W, double*
 
 // R[nrhs x n] = T . L^-T with the 1024-block inverses (T is destroyed): n / 1024 steps of two GEMMs instead of the n / 128 steps of
 // trsm_right_lower_t -- the few-row triangular solve of the bordered warm start (laplace.cu) is launch-bound, not flop-bound
-// Skinny NT product for a handful of rows (the border of the warm start: nr = m = 25 appended rows against a factor of 5000):
-//   C[r][c] = beta C[r][c] + alpha sum_k A[r][k] B[c][k],   r < nr <= 32, c < nc.
-// The tiled GEMM pads the 25 rows to a 64-row tile and gives every 64 x 64 tile one CTA that walks the whole K range: 16-64 CTAs,
-// 55-60 us per call whatever the size, 280 us for the 25 x 25 Schur complement with K = 5000 on ONE CTA (profiles/
-// r02_timeline_steady.txt) -- 0.9 ms of the appended fit for 0.2 GFLOP.  Here one warp owns an output column: the lanes stride K,
-// keep nr accumulators each and stream B once (8 nc K bytes, the HBM-bound part); A's K-chunk is staged in shared memory per CTA.
-constexpr int SK_NR = 32, SK_WARPS = 8, SK_KC = 128;
-__global__ void __launch_bounds__(SK_WARPS * 32) skinny_nt_kernel(const double* __restrict__ A, long long lda, int nr,
-                                                                  const double* __restrict__ B, long long ldb, int nc, int K,
-                                                                  double alpha, double beta, double* __restrict__ C, long long ldc) {
-    __shared__ double As[SK_NR][SK_KC];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = blockIdx.x * SK_WARPS + warp;
-    const double* Bc = B + (long long)min(c, nc - 1) * ldb;
-    double acc[SK_NR];
-#pragma unroll
-    for (int r = 0; r < SK_NR; ++r) acc[r] = 0.0;
-    for (int k0 = 0; k0 < K; k0 += SK_KC) {
-        const int kc = min(SK_KC, K - k0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < SK_NR * SK_KC; e += SK_WARPS * 32) {
-            const int r = e / SK_KC, k = e % SK_KC;
-            As[r][k] = (r < nr && k < kc) ? A[(long long)r * lda + k0 + k] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < SK_KC / 32; ++j) {
-            const int k = j * 32 + lane;
-            const double b = (k < kc) ? Bc[k0 + k] : 0.0;
-#pragma unroll
-            for (int r = 0; r < SK_NR; ++r) acc[r] = fma(As[r][k], b, acc[r]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < SK_NR; ++r)
-        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-    if (c < nc) {
-        // lane r writes row r (every lane holds all totals after the butterfly)
-#pragma unroll
-        for (int r = 0; r < SK_NR; ++r)
-            if (lane == r && r < nr) {
-                double* dst = C + (long long)r * ldc + c;
-                *dst = (beta == 0.0 ? 0.0 : beta * *dst) + alpha * acc[r];
-            }
-    }
-}
-int skinny_nt(const double* A, long long lda, int nr, const double* B, long long ldb, int nc, int K, double alpha, double beta,
-              double* C, long long ldc, cudaStream_t st) {
-    if (nr <= 0 || nc <= 0) return PPBO_OK;
-    PPBO_REQUIRE(nr <= SK_NR, "skinny_nt: at most 32 rows");
-    PPBO_CL skinny_nt_kernel<<<ceil_div(nc, SK_WARPS), SK_WARPS * 32, 0, st>>>(A, lda, nr, B, ldb, nc, K, alpha, beta, C, ldc);
-    PPBO_LAUNCH_CHECK();
-    return PPBO_OK;
-}
-
 int trsm_right_blockinv(const double* L, long long ldl, int n, const double* W, double* T, long long ldt, double* R, long long ldr,
                         int nrhs, cudaStream_t st) {
     const int nbI = ceil_div(n, BI);
     const long long BB = (long long)BI * BI;
     for (int J = 0; J < nbI; ++J) {
         const int j0 = J * BI, rows = min(BI, n - j0), j1 = j0 + rows;
-        if (nrhs <= SK_NR) {            // a few rows (the border of the warm start): one warp per output column
-            int rc = skinny_nt(T + j0, ldt, nrhs, W + J * BB, BI, rows, rows, 1.0, 0.0, R + j0, ldr, st);
-            if (rc) return rc;
-            if (j1 < n && (rc = skinny_nt(R + j0, ldr, nrhs, L + (long long)j1 * ldl + j0, ldl, n - j1, rows, -1.0, 1.0, T + j1, ldt, st)))
-                return rc;
-            continue;
-        }
         {
             GemmOperands g{T + j0, ldt, 0, W + J * BB, BI, 0, nrhs, rows, rows};
             StoreEpilogue ep{R + j0, ldr, 0, 1.0, 0.0, 0, 0, 0};

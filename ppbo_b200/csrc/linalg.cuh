@@ -24,9 +24,6 @@ int potrs_fwd_blockinv(const double* L, long long ldl, int n, double* W, double*
 int potrs_bwd_blockinv(const double* L, long long ldl, int n, double* W, double* t, cudaStream_t st, const double* skip = nullptr);
 int trsm_right_blockinv(const double* L, long long ldl, int n, const double* W, double* T, long long ldt, double* R, long long ldr,
                         int nrhs, cudaStream_t st);
-// C[nr x nc] = beta C + alpha A[nr x K] B[nc x K]^T for nr <= 32 rows (one warp per output column)
-int skinny_nt(const double* A, long long lda, int nr, const double* B, long long ldb, int nc, int K, double alpha, double beta,
-              double* C, long long ldc, cudaStream_t st);
 int gemv(const double* A, long long lda, int M, int N, const double* x, double* y, cudaStream_t st, const double* skip = nullptr);
 
 }  // namespace ppbo
