@@ -450,7 +450,7 @@ def acquisition_values(sums, S):
     s = np.asarray(sums, dtype=float)
     ei = s[:, 0] / S
     mean = s[:, 1] / S
-    var = s[:, 2] / S - mean * mean
+    var = np.maximum(s[:, 2] / S - mean * mean, 0.0)          # one-pass form: clamp the round-off of the cancellation
     return ei, var
 
 

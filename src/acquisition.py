@@ -101,7 +101,9 @@ def _varmax_values(pairs, GP_model, mc_samples):
     fmax = sampled_max_batch(pairs, GP_model, mc_samples)
     sums = ops.acq_reduce(fmax, 0.0).cpu().numpy()
     mean = sums[:, 1] / mc_samples
-    return sums[:, 2] / mc_samples - mean * mean
+    # (one-pass form E[x^2] - mean^2 from the device sums; the reference's mean((x - mean)^2) is >= 0 by construction, so clamp
+    # the round-off of the cancellation)
+    return np.maximum(sums[:, 2] / mc_samples - mean * mean, 0.0)
 
 
 # ------------------------------------------------------------------------------------------------ reference API
