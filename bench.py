@@ -265,7 +265,7 @@ def iteration_slices():
 
 def iteration_reserved_sms():
     from ppbo_b200 import iteration
-    return iteration.OVERLAP_RESERVED_SMS if iteration.OVERLAP_SAMPLING else 0
+    return "%d (cold) / %d (appended)" % (iteration.OVERLAP_RESERVED_SMS_COLD, iteration.OVERLAP_RESERVED_SMS) if iteration.OVERLAP_SAMPLING else "0"
 
 
 def workload_config(prob, n_gpus):
@@ -274,7 +274,7 @@ def workload_config(prob, n_gpus):
                             prob["name"], prob["D"], prob["Q"], prob["m"], prob["N"], prob["Q"] * prob["m"], prob["kernel"],
                             prob["theta"], prob["F"], prob["grids"].shape[0], prob["P"], prob["S"]),
             "parallelism": ("one GPU, two concurrent chains: weight-space fit -> draws -> INT8 contraction (foreground streams, persistent "
-                            "grid on all but %d SMs) || GP fit -> mu* (background thread, lowest stream priority, on the SMs left free); "
+                            "grid on all but %s SMs) || GP fit -> mu* (background thread, lowest stream priority, on the SMs left free); "
                             "only the reduction of 3 x directions sums needs both" % iteration_reserved_sms() if n_gpus == 1 else
                             "GP fit on rank 0, weight-space fit on rank 1, broadcast of (omega_MAP, diag Hessian); S sharded over the "
                             "ranks by measured stage times (rank 0 samples only if its fit ends before the others would); mu* candidates "

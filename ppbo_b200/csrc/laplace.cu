@@ -646,6 +646,124 @@ __global__ void __launch_bounds__(256) border_write_rows_kernel(const double* __
     if (v < b0) L[(long long)(M_old + u) * ldl + v] = s_new[u] * R[(long long)u * ldr + v];
 }
 
+// ---- chord steps in difference space ------------------------------------------------------------------------------------
+// The likelihood only sees the differences d = B'f (d_qj = f_j - f_winner), and alpha stays in the range of B (alpha = B gamma:
+// beta is, and every step keeps it there), so the iteration can be carried by the M-vectors (gamma, d = G gamma):
+//     c = a0+ d + g(d)            g_qj = -phi~(d_qj / sigma) / (sigma m)      (beta = B g)
+//     (I + s G s) y = s G c       the same factor / border solve as before
+//     gamma_new = c - s y         d_new = G gamma_new = y / s   on every entry with s > 0
+// (from s G s y = s G c - y).  One mat-vec with G (M x M) per step instead of two with Sigma (N x N); the entries whose coefficient
+// is (nearly) zero -- observations above their winner, 130 of 5000 at the mode of the bench problem, and appended rows before
+// their first step -- take their row of G gamma_new directly.  T = -1/2 gamma.d - lik(d)/m, so the acceptance test, the Aitken
+// step lengths and the Anderson mixing (which preserves d = G gamma like it preserved f = Sigma alpha) run on (gamma, d) with
+// the kernels of the alpha-space iteration.  alpha = B gamma and f = Sigma alpha are restored once per batch.
+__global__ void to_diff_kernel(const double* __restrict__ f, const double* __restrict__ alpha, int Q, int m,
+                               double* __restrict__ d, double* __restrict__ gamma) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= Q * m) return;
+    const int q = u / m, j = u % m;
+    const long long w = (long long)q * (m + 1);
+    d[u] = f[w + 1 + j] - f[w];
+    gamma[u] = alpha[w + 1 + j];
+}
+// alpha = B gamma (one warp per set; skip: nothing was changed in this batch is not a case -- always runs)
+__global__ void __launch_bounds__(256) from_diff_kernel(const double* __restrict__ gamma, int Q, int m, double* __restrict__ alpha) {
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const long long base = (long long)q * (m + 1);
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) {
+        const double g = gamma[(long long)q * m + j];
+        s += g;
+        alpha[base + 1 + j] = g;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) alpha[base] = -s;
+}
+// c[u] = ap[u] d[u] + g(d[u])
+__global__ void dchord_rhs_kernel(const double* __restrict__ d, const double* __restrict__ ap, int M, double sigma, int m,
+                                  double* __restrict__ c, const double* __restrict__ skip) {
+    if (skip && *skip != 0.0) return;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= M) return;
+    const double du = d[u];
+    c[u] = fma(ap[u], du, -phi_tilde(du / sigma) / (sigma * m));
+}
+// coefficients of the border rows at the current iterate (their own Newton step inside every chord step)
+__global__ void dborder_coeff_kernel(const double* __restrict__ d, int nb, double sigma, int m, double* __restrict__ sa,
+                                     double* __restrict__ ap, const double* __restrict__ skip) {
+    if (skip && *skip != 0.0) return;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nb) return;
+    const double dl = d[u] / sigma;
+    const double a = -(0.5 / (m * sigma * sigma)) * dl * phi_tilde(dl);
+    const double a_pos = a > 0.0 ? a : 0.0;
+    ap[u] = a_pos;
+    sa[u] = sqrt(a_pos);
+}
+// t[u] *= sa[u]    (t holds G c on entry)
+__global__ void dchord_scale_kernel(double* __restrict__ t, const double* __restrict__ sa, int M, const double* __restrict__ skip) {
+    if (skip && *skip != 0.0) return;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < M) t[u] *= sa[u];
+}
+// dgamma = (c - sa y) - gamma;  dd = y / sa - d where ap >= thr (the other rows: dchord_rows_kernel)
+__global__ void dchord_update_kernel(const double* __restrict__ c, const double* __restrict__ sa, const double* __restrict__ ap,
+                                     const double* __restrict__ y, const double* __restrict__ gamma, const double* __restrict__ d,
+                                     int M, double thr, double* __restrict__ dgamma, double* __restrict__ dd,
+                                     const double* __restrict__ skip) {
+    if (skip && *skip != 0.0) return;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= M) return;
+    const double s = sa[u], yu = y[u];
+    dgamma[u] = fma(-s, yu, c[u]) - gamma[u];
+    if (ap[u] >= thr) dd[u] = yu / s - d[u];
+}
+// rows whose coefficient is below thr: dd[u] = G[u, :] . (gamma + dgamma) - d[u].  One CTA per row, the others leave at once (with
+// one WARP per row the ~150 working warps each stream their 40 KB row alone: 43 us, latency-bound; 256 threads per row: 8 us)
+__global__ void __launch_bounds__(256) dchord_rows_kernel(const double* __restrict__ G, long long ldg, const double* __restrict__ gamma,
+                                                          const double* __restrict__ dgamma, const double* __restrict__ ap,
+                                                          const double* __restrict__ d, int M, double thr, double* __restrict__ dd,
+                                                          const double* __restrict__ skip) {
+    __shared__ double red[33];
+    if (skip && *skip != 0.0) return;
+    const int u = blockIdx.x;
+    if (ap[u] >= thr) return;                              // uniform per CTA
+    const double* g = G + (long long)u * ldg;
+    double s0 = 0.0, s1 = 0.0;
+    int k = threadIdx.x;
+    for (; k + 256 < M; k += 512) {
+        s0 = fma(g[k], gamma[k] + dgamma[k], s0);
+        s1 = fma(g[k + 256], gamma[k + 256] + dgamma[k + 256], s1);
+    }
+    if (k < M) s0 = fma(g[k], gamma[k] + dgamma[k], s0);
+    const double s = block_sum(s0 + s1, red);
+    if (threadIdx.x == 0) dd[u] = s - d[u];
+}
+// likelihood sums of a queued step at its step length omega = state[7] and (part0) at the current iterate, from the differences
+__global__ void __launch_bounds__(256) dchord_lik_kernel(const double* __restrict__ d, const double* __restrict__ dd, int Q, int m,
+                                                         double sigma, const double* __restrict__ state, double* __restrict__ part,
+                                                         double* __restrict__ part0) {
+    if (state[4] != 0.0) return;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= Q) return;
+    const double step = state[7], inv_s = 1.0 / sigma;
+    double s = 0.0, s0 = 0.0;
+    for (int j = lane; j < m; j += 32) {
+        const double du = d[(long long)q * m + j];
+        s += Phi_tilde(fma(step, dd[(long long)q * m + j], du) * inv_s);
+        if (part0) s0 += Phi_tilde(du * inv_s);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    }
+    if (lane == 0) {
+        part[q] = s;
+        if (part0) part0[q] = s0;
+    }
+}
+
 bool thread_is_background();        // linalg.cu
 static int launch_chord_anderson(double* alpha, double* f, const double* df, int N, const double* state, double* aa, double* H,
                                  cudaStream_t st) {
@@ -958,6 +1076,9 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
     // border's Newton steps change the map from step to step and the Aitken step lengths do better there (measured).
     bool aa_failed = false;
     double rel3_h = INFINITY;
+    // PPBO_CHORD_SPACE=alpha: chord steps on (alpha, f) with two Sigma mat-vecs per step (the formulation of the first half of
+    // round 2; diagnostics)
+    const bool diff_space = !(getenv("PPBO_CHORD_SPACE") && getenv("PPBO_CHORD_SPACE")[0] == 'a');
     auto aa_now = [&]() { return (anderson_mode == 1) || (anderson_mode >= 2 && !warm_factor && n_factor == 1 && !aa_failed); };
     PPBO_CUDA_CHECK(cudaMemsetAsync(ws.aa, 0, sizeof(double) * 8, st));
     bool factor_current = false;         // Lfac is the factor for the coefficients in ws.sa / ws.ap
@@ -1055,6 +1176,30 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             double hist_h[2 * CHORD_BATCH_MAX];
             PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.state, state_h, sizeof(state_h), cudaMemcpyHostToDevice, st));
             const double* skip = ws.state + 4;               // non-zero once a step of the batch has stopped it
+            if (diff_space) {
+                // ---- the batch in difference space (see to_diff_kernel): gamma, d, c, dgamma, dd live in the N-vectors of the
+                // alpha-space step, which are idle here
+                double *gam = ws.bvec, *dv = ws.Sb, *cv = ws.dalpha, *dgam = ws.df, *ddv = ws.arrow_tmp;
+                const double thr = 1e-3 * 0.121 / (m * sigma * sigma);       // 1e-3 of the largest possible coefficient
+                PPBO_CL to_diff_kernel<<<ceil_div(M, 256), 256, 0, st>>>(f_map, alpha, Q, m, dv, gam);
+                for (int i = 0; i < kb; ++i) {
+                    if (bordered)
+                        PPBO_CL dborder_coeff_kernel<<<ceil_div(nb, 64), 64, 0, st>>>(dv + M_old, nb, sigma, m, ws.sa + M_old, ws.ap + M_old, skip);
+                    PPBO_CL dchord_rhs_kernel<<<ceil_div(M, 256), 256, 0, st>>>(dv, ws.ap, M, sigma, m, cv, skip);
+                    if ((rc = gemv(G, ldg, M, M, cv, ws.t, st, skip))) return rc;
+                    PPBO_CL dchord_scale_kernel<<<ceil_div(M, 256), 256, 0, st>>>(ws.t, ws.sa, M, skip);
+                    if ((rc = chord_solve(skip))) return rc;
+                    PPBO_CL dchord_update_kernel<<<ceil_div(M, 256), 256, 0, st>>>(cv, ws.sa, ws.ap, ws.t, gam, dv, M, thr, dgam, ddv, skip);
+                    PPBO_CL dchord_rows_kernel<<<M, 256, 0, st>>>(G, ldg, gam, dgam, ws.ap, dv, M, thr, ddv, skip);
+                    PPBO_CL dchord_lik_kernel<<<set_blocks, 256, 0, st>>>(dv, ddv, Q, m, sigma, ws.state, ws.set_part, anderson ? ws.part0 : nullptr);
+                    PPBO_CL chord_decide_kernel<<<1, 1024, 0, st>>>(gam, dgam, dv, ddv, M, ws.set_part, Q, m, ws.state, ws.hist,
+                                                                      (chord_extrapolate && !anderson) ? 1 : 0, anderson ? ws.part0 : nullptr);
+                    if (anderson && (rc = launch_chord_anderson(gam, dv, ddv, M, ws.state, ws.aa, ws.aaH, st))) return rc;
+                }
+                // back to (alpha, f): alpha = B gamma, f = Sigma alpha
+                PPBO_CL from_diff_kernel<<<set_blocks, 256, 0, st>>>(gam, Q, m, alpha);
+                if ((rc = gemv(Sigma, lds, N, N, alpha, f_map, st))) return rc;
+            } else
             for (int i = 0; i < kb; ++i) {
                 if (bordered) refresh_border(skip);
                 PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, nullptr, ws.bvec, ws.ap, nullptr, skip);

@@ -42,11 +42,15 @@ I8_MIN_WORK = 1 << 24     # S * P * F below which the FP64 kernel is used
 CONCURRENT_FITS = True
 # One GPU: the sampling contraction needs the weight-space fit only (mu* enters at the reduction), so the background thread goes
 # on from the weight-space fit to the draws and the INT8 contraction on its lowest-priority stream WHILE the GP fit -- a chain of
-# small, latency-bound kernels that leaves most SMs idle -- runs in the foreground.  The contraction's persistent grid then leaves
-# OVERLAP_RESERVED_SMS SMs to the fit (tuning key 14); a contraction CTA fills its SM, so the two never share one.
+# small, latency-bound kernels that leaves most SMs idle -- runs beside it.  The contraction's persistent grid then leaves
+# OVERLAP_RESERVED_SMS(_COLD) SMs to the fit (tuning key 14); a contraction CTA fills its SM, so the two never share one.
 # PPBO_OVERLAP_SAMPLING=0 restores the sequential order (diagnostics).
 import os as _os
-OVERLAP_RESERVED_SMS = int(_os.environ.get("PPBO_OVERLAP_RESERVE", "20"))
+# Reserved SMs: an appended iteration's GP chain is short (it ends ~2 ms before the contraction on 16 SMs); a cold fit has 13
+# chord steps with two 216 MB mat-vecs each and is the longer chain, so it gets more (sweeps in DESIGN.md 5.1).
+_RESERVE_ENV = _os.environ.get("PPBO_OVERLAP_RESERVE")
+OVERLAP_RESERVED_SMS = int(_RESERVE_ENV) if _RESERVE_ENV else 16            # appended iterations
+OVERLAP_RESERVED_SMS_COLD = int(_RESERVE_ENV) if _RESERVE_ENV else 32       # cold iterations
 # Steady state of the overlapped pipeline, opt-in: refresh the weight-space Hessian factor at each new optimum while the contraction
 # runs (RFFState.refresh_factor).  The next fit then needs 10 chord steps and never a mid-fit refactorisation (13 steps and a
 # refactorisation every ~4th iteration with the stale factor), but the refresh (10 GFLOP of Hessian GEMM + a Cholesky) shares
@@ -638,7 +642,7 @@ def run_iteration(d, kernel, theta, Q, m, S, shard=None, seed=0, fit_iters=100, 
                 fg.wait_stream(grid_stream)
                 for t in (PhiT.PhiT, PhiT.planes, PhiT.scale):
                     t.record_stream(fg)
-                lib.ppbo_set_tuning(14, OVERLAP_RESERVED_SMS)
+                lib.ppbo_set_tuning(14, OVERLAP_RESERVED_SMS if warm else OVERLAP_RESERVED_SMS_COLD)
                 try:
                     fmax, _ = rff_sampled_maxima(rff, PhiT, lo, hi, seed=seed, prepared=prepared)
                 finally:

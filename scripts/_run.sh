@@ -1,3 +1,3 @@
-python -m pytest tests/test_full_size.py tests/test_incremental.py tests/test_gpu_ops.py -m gpu -x -q 2>&1 | tail -2
-python scripts/timeline.py --mode steady --steps 4 --api --out gpurun_out/timeline_steady.txt --dump gpurun_out/seq_steady.txt 2>&1 | tail -1
-python scripts/steady_probe.py 2>&1 | grep "append" | cut -c1-120
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_t18.log 2>&1; tail -2 gpurun_out/pytest_t18.log
+python bench.py --steps 10 --warmup 3 --no-api-leg --no-cpu-baseline > gpurun_out/bench_t18.log 2>&1
+PPBO_CHORD_SPACE=alpha python bench.py --steps 10 --warmup 3 --no-api-leg --no-cpu-baseline > gpurun_out/bench_t18a.log 2>&1
