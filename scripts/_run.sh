@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_t18.log 2>&1; tail -2 gpurun_out/pytest_t18.log
-python bench.py --steps 10 --warmup 3 --no-api-leg --no-cpu-baseline > gpurun_out/bench_t18.log 2>&1
-PPBO_CHORD_SPACE=alpha python bench.py --steps 10 --warmup 3 --no-api-leg --no-cpu-baseline > gpurun_out/bench_t18a.log 2>&1
+for R in 20 26; do
+PPBO_OVERLAP_RESERVE=$R python bench.py --steps 10 --warmup 3 --no-api-leg --no-cpu-baseline > gpurun_out/bench_t19_R$R.log 2>&1
+done
