@@ -98,8 +98,8 @@ __device__ inline double block_sum(double v, double* smem33) {
 }
 
 // NV block-wide sums at once (fixed order: shuffle tree inside a warp, warps in index order): v[] holds the totals in EVERY thread on
-// return.  smem: 32 * NV doubles.  One pair of barriers instead of two per value (block_sum): the single-CTA decision kernels of the
-// fits spend most of their time in barriers otherwise.
+// return.  smem: 32 * NV doubles.  Three barriers instead of two per value (block_sum): the single-CTA decision kernels of the
+// fits spend most of their time in barriers otherwise.  blockDim.x >= NV.
 template <int NV>
 __device__ inline void block_sum_multi(double (&v)[NV], double* smem) {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
@@ -112,12 +112,14 @@ __device__ inline void block_sum_multi(double (&v)[NV], double* smem) {
         for (int i = 0; i < NV; ++i) smem[w * NV + i] = v[i];
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    if (threadIdx.x < NV) {                     // thread i adds the warps' partial sums of value i (in warp order)
         double r = 0.0;
-        for (int k = 0; k < nw; ++k) r += smem[k * NV + i];
-        v[i] = r;
+        for (int k = 0; k < nw; ++k) r += smem[k * NV + threadIdx.x];
+        smem[threadIdx.x] = r;                  // row 0 is warp 0's partials: thread i only reads column i of it, before this write
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = smem[i];
 }
 
 }  // namespace ppbo

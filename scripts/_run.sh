@@ -1,3 +1,2 @@
-for c in 0.25 0.45; do
-PPBO_RFF_CHORD_REL=$c PPBO_TRACE=1 python scripts/steady_probe.py 2>&1 | grep "RFFState.cold\|ppbo_rff_fit\] it" | head -40 | cut -c1-110 > gpurun_out/rffcold_$c.txt
-done
+python -m pytest tests/test_full_size.py tests/test_incremental.py tests/test_gpu_ops.py -m gpu -x -q 2>&1 | tail -2
+python scripts/timeline.py --mode cold --steps 1 --out gpurun_out/timeline_cold.txt --dump gpurun_out/seq_cold.txt 2>&1 | tail -1
