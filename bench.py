@@ -602,11 +602,18 @@ def main():
         # the default partition gives every rank >= 1 an equal share: the whole sample set costs the sum of their sampling stages
         t_sampling_all[0] = float(np.sum([s_.get("sampling", 0.0) for s_ in st_all[1:]]))
         shares[0], smu[0] = plan(st_all)
-    for _ in range(W_steps):
-        held[0] = step(resident)           # (a warm-up that drops its products at once leaves the second timed step to
-    clocks = ClockSampler(local)           # cudaMalloc a second set of 200 MB buffers: +1 ms on one GPU, up to +10 ms on two)
+    # The clock sampler starts BEFORE the warm-up: the start-up of nvidia-smi (NVML initialisation, first query) holds driver locks
+    # for 50-100 ms, and a host-synchronous step that meets it was a 70-110 ms outlier in the timed region (steps 1-4 of the first
+    # timed run, whenever the process came up there).  Its periodic queries keep running through both timed regions.
+    clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        t_wait = time.perf_counter()
+        while not clocks.rows and time.perf_counter() - t_wait < 3.0:      # first sample = start-up is over
+            time.sleep(0.02)
+    for _ in range(W_steps):
+        held[0] = step(resident)           # (a warm-up that drops its products at once leaves the second timed step to
+                                           # cudaMalloc a second set of 200 MB buffers: +1 ms on one GPU, up to +10 ms on two)
     ms_dev, launches, out = timed_run(resident)
     fit_stats = out[1].lap.stats if out[1] is not None else None
     rff_iters = out[2].stats["iterations"] if (out[2] is not None and out[2].stats) else None

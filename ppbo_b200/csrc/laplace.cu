@@ -343,163 +343,249 @@ __global__ void __launch_bounds__(1024) chord_decide_kernel(double* __restrict__
 //   * replaces (alpha, f) by g_k - dG gamma   (f = Sigma alpha is preserved: both are the same combination).
 // The history is dropped when a step was damped / extrapolated / rejected, or when the residual grew.  Fixed summation order.
 constexpr int AA_M = 5;
-constexpr int AA_CL = 8;       // CTAs of the cluster that shares one call (each takes N / 8 elements); 1 on a background thread
-//   aa: [0] history length, [1] next slot, [2] residual norm (max |df| / max |f|) seen by the previous call
+constexpr int AA_CL = 8;       // fixed element slices per call: one per CTA
+constexpr int AA_NPAIR = AA_M * (AA_M + 1) / 2, AA_NV = AA_NPAIR + AA_M;
+constexpr int AA_STATE = 8 + AA_CL * AA_NV + AA_M + 3;      // aa: 8 doubles of state, then scratch of the three-launch variant
+//   aa: [0] history length, [1] next slot, [2] residual norm (max |df| / max |f|) seen by the previous call, [3] 1 = (prev r, g) valid
+//       [8 ..) partial sums [AA_CL][AA_NV], mixing coefficients [AA_M], their count (three-launch variant)
 //   H: [3 * AA_M + 3][N]: dR[AA_M], dGf[AA_M], dGa[AA_M], prev r, prev g_f, prev g_a
-// One call moves ~32 N doubles through dependent global round trips; a single CTA needed 41-58 us for that at N = 5200 (latency of
-// one SM's load path, not arithmetic).  A thread-block cluster of 8 CTAs splits the elements; the partial sums of the normal
-// equations meet through distributed shared memory (fixed order: by cluster rank), every CTA solves the 5 x 5 system redundantly.
-// A fit on a background host thread (the GP chain of the overlapped one-GPU pipeline, which lives on the ~20 SMs the sampling
-// contraction leaves free) launches a cluster of ONE: eight co-scheduled 1024-thread CTAs rarely find room there, and the chain
-// stalled for milliseconds waiting for a slot (measured: +1.8 ms on the cold iteration).
+// One call moves ~32 N doubles through dependent global round trips; a single CTA needs 41-83 us for that at N = 5200 (one SM's
+// load path).  The elements are cut into AA_CL = 8 fixed slices, one per CTA; the partial sums of the normal equations are added
+// in slice order and the 5 x 5 system is solved by the same code wherever it runs, so both variants below return the same bits:
+//   * chord_anderson_kernel: ONE launch of a thread-block cluster of 8 CTAs, partial sums through distributed shared memory, every
+//     CTA solves redundantly (17 us).  Used by fits on a foreground host thread.
+//   * chord_anderson_{sums,solve,apply}_kernel: three ordinary launches (8 CTAs, 1 warp, 8 CTAs; partial sums through global
+//     memory).  Used by fits on a background host thread -- the GP chain of the overlapped one-GPU pipeline, which lives on the
+//     16-32 SMs the sampling contraction leaves free: eight co-scheduled 1024-thread CTAs rarely find room there (the chain stalled
+//     for milliseconds waiting for a slot: +1.8 ms on the cold iteration), and a cluster of one took 46-83 us per call.
+struct AaView {
+    double *dR, *dGf, *dGa, *pr, *pgf, *pga;
+    __device__ AaView(double* H, int N)
+        : dR(H), dGf(H + (long long)AA_M * N), dGa(H + 2LL * AA_M * N), pr(H + 3LL * AA_M * N), pgf(pr + N), pga(pgf + N) {}
+};
+// what every CTA of a call derives from the state: false = leave (nothing to mix); nh / slot / have_prev describe the history the
+// call works with BEFORE its own append
+struct AaPlan { int nh, slot; bool have_prev, reset, run; };
+__device__ __forceinline__ AaPlan aa_plan(const double* __restrict__ state, const double* __restrict__ aa) {
+    AaPlan p;
+    const double stop = state[4];
+    const bool plain = state[14] == 1.0;
+    const double rel = state[1], rel_prev = aa[2];
+    p.nh = (int)aa[0];
+    p.slot = (int)aa[1];
+    p.have_prev = aa[3] == 1.0;
+    p.reset = false;
+    p.run = !(stop == 1.0 || stop == 3.0);            // converged or rejected for good: nothing to mix
+    if (p.run && (!plain || (p.have_prev && rel > 1.5 * rel_prev))) {
+        // a damped / extrapolated / rejected step, or a residual that grew: the history no longer describes one linear map
+        p.reset = true;
+        if (!plain) p.run = false;
+        p.nh = 0;
+        p.slot = 0;
+        p.have_prev = false;
+    }
+    return p;
+}
+// slice v: append the newest differences (needs the previous (r, g)) and remember the current ones
+__device__ __forceinline__ void aa_slice_append(const AaView& h, const double* __restrict__ df, const double* __restrict__ f,
+                                                const double* __restrict__ alpha, int N, int v, int slot, bool have_prev) {
+    const int per = (N + AA_CL - 1) / AA_CL, lo = v * per, hi = min(N, lo + per);
+    double* dRs = h.dR + (long long)slot * N;
+    double* dGfs = h.dGf + (long long)slot * N;
+    double* dGas = h.dGa + (long long)slot * N;
+    for (int i = lo + threadIdx.x; i < hi; i += 1024) {
+        const double r = df[i], gf = f[i], ga = alpha[i];
+        if (have_prev) {
+            dRs[i] = r - h.pr[i];
+            dGfs[i] = gf - h.pgf[i];
+            dGas[i] = ga - h.pga[i];
+        }
+        h.pr[i] = r;
+        h.pgf[i] = gf;
+        h.pga[i] = ga;
+    }
+}
+// slice v: all products of the normal equations A_ij = <dR_i, dR_j>, b_i = <dR_i, r> in one pass + one multi-value block reduction;
+// every thread returns the slice totals in acc.  (A thread only re-reads elements it wrote itself in aa_slice_append.)
+__device__ __forceinline__ void aa_slice_products(const AaView& h, const double* __restrict__ df, int N, int v, int nh,
+                                                  double (&acc)[AA_NV], double* red_multi) {
+    const int per = (N + AA_CL - 1) / AA_CL, lo = v * per, hi = min(N, lo + per);
+#pragma unroll
+    for (int i = 0; i < AA_NV; ++i) acc[i] = 0.0;
+    for (int k = lo + threadIdx.x; k < hi; k += 1024) {
+        double dv[AA_M];
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i) dv[i] = (i < nh) ? h.dR[(long long)i * N + k] : 0.0;
+        const double rk = df[k];
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < AA_M; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) { acc[idx] = fma(dv[i], dv[j], acc[idx]); ++idx; }
+            acc[AA_NPAIR + i] = fma(dv[i], rk, acc[AA_NPAIR + i]);
+        }
+    }
+    block_sum_multi<AA_NV>(acc, red_multi);
+}
+// one thread: min_gamma | r - dR gamma |_2 from the totals (normal equations of order nh, Tikhonov-damped, Gaussian elimination with
+// partial pivoting); returns the number of coefficients to apply (0: none)
+__device__ __forceinline__ int aa_solve(const double (&tot)[AA_NV], int nh, double* gam) {
+    double A[AA_M][AA_M], bb[AA_M];
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < AA_M; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) { A[i][j] = A[j][i] = tot[idx]; ++idx; }
+        bb[i] = tot[AA_NPAIR + i];
+    }
+    double tr = 0.0;
+    for (int i = 0; i < nh; ++i) tr += A[i][i];
+    for (int i = 0; i < nh; ++i) A[i][i] += 1e-10 * tr + 1e-300;     // damping: nearly collinear differences
+    bool ok = true;
+    for (int c = 0; c < nh && ok; ++c) {
+        int p = c;
+        for (int r2 = c + 1; r2 < nh; ++r2) if (fabs(A[r2][c]) > fabs(A[p][c])) p = r2;
+        if (A[p][c] == 0.0) { ok = false; break; }
+        for (int k = 0; k < nh; ++k) { const double t = A[c][k]; A[c][k] = A[p][k]; A[p][k] = t; }
+        { const double t = bb[c]; bb[c] = bb[p]; bb[p] = t; }
+        for (int r2 = c + 1; r2 < nh; ++r2) {
+            const double l = A[r2][c] / A[c][c];
+            for (int k = c; k < nh; ++k) A[r2][k] -= l * A[c][k];
+            bb[r2] -= l * bb[c];
+        }
+    }
+    for (int i = nh - 1; i >= 0 && ok; --i) {
+        double v = bb[i];
+        for (int k = i + 1; k < nh; ++k) v -= A[i][k] * gam[k];
+        gam[i] = v / A[i][i];
+        if (!(fabs(gam[i]) < 1e3)) ok = false;
+    }
+    return ok ? nh : 0;
+}
+// slice v: (alpha, f) <- g_k - dG gamma
+__device__ __forceinline__ void aa_slice_apply(const AaView& h, double* __restrict__ alpha, double* __restrict__ f, int N, int v,
+                                               int nm, const double* gam) {
+    const int per = (N + AA_CL - 1) / AA_CL, lo = v * per, hi = min(N, lo + per);
+    for (int i = lo + threadIdx.x; i < hi; i += 1024) {
+        double cf = 0.0, ca = 0.0;
+        for (int j = 0; j < nm; ++j) {
+            cf = fma(gam[j], h.dGf[(long long)j * N + i], cf);
+            ca = fma(gam[j], h.dGa[(long long)j * N + i], ca);
+        }
+        f[i] -= cf;
+        alpha[i] -= ca;
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 chord_anderson_kernel(double* __restrict__ alpha, double* __restrict__ f, const double* __restrict__ df, int N,
                       const double* __restrict__ state, double* __restrict__ aa, double* __restrict__ H) {
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
-    const unsigned rank = cl.block_rank(), ncta = cl.num_blocks();       // cluster size chosen at launch (launch_chord_anderson)
-    constexpr int NPAIR = AA_M * (AA_M + 1) / 2, NV = NPAIR + AA_M;
-    __shared__ double part_s[AA_CL * NV];                                // partial sums of this CTA's slices
-    __shared__ double red_multi[32 * NV];
+    const int rank = (int)cl.block_rank();                               // cluster of AA_CL CTAs: CTA rank owns slice rank
+    __shared__ double part_s[AA_NV];
+    __shared__ double red_multi[32 * AA_NV];
     __shared__ double gam[AA_M];
-    __shared__ int nh_s;
-    double* dR = H;
-    double* dGf = H + (long long)AA_M * N;
-    double* dGa = H + 2LL * AA_M * N;
-    double* pr = H + 3LL * AA_M * N;
-    double* pgf = pr + N;
-    double* pga = pgf + N;
-    const double stop = state[4];
-    const bool plain = state[14] == 1.0;
+    __shared__ int nm_s;
+    const AaView h(H, N);
+    AaPlan p = aa_plan(state, aa);
     const double rel = state[1];
-    int nh = (int)aa[0], slot = (int)aa[1];
-    const double rel_prev = aa[2];
-    bool have_prev = aa[3] == 1.0;
     cl.sync();                                                           // every CTA has read the state (rank 0 writes aa below)
-    if (stop == 1.0 || stop == 3.0) return;                              // converged or rejected for good: nothing to mix
-    if (!plain || (have_prev && rel > 1.5 * rel_prev)) {
-        // a damped / extrapolated / rejected step, or a residual that grew: the history no longer describes one linear map
-        if (rank == 0 && threadIdx.x == 0) { aa[0] = 0.0; aa[1] = 0.0; aa[2] = rel; aa[3] = 0.0; }
-        if (!plain) return;
-        nh = 0;
-        slot = 0;
-        have_prev = false;
-    }
-    // The elements are cut into AA_CL fixed slices; CTA `rank` of a cluster of ncta takes the slices rank, rank + ncta, ...: the
-    // partial sums -- and with them every bit of the result -- do not depend on the cluster size.
-    const int per = (N + AA_CL - 1) / AA_CL;
-    // append the newest differences (needs the previous (r, g)) and remember the current ones; a thread only ever re-reads
-    // elements it wrote itself, so no barrier is needed between the passes
-    const int slot_w = slot;
-    for (int v = (int)rank; v < AA_CL; v += (int)ncta) {
-        const int lo = v * per, hi = min(N, lo + per);
-        double* dRs = dR + (long long)slot_w * N;
-        double* dGfs = dGf + (long long)slot_w * N;
-        double* dGas = dGa + (long long)slot_w * N;
-        for (int i = lo + threadIdx.x; i < hi; i += 1024) {
-            const double r = df[i], gf = f[i], ga = alpha[i];
-            if (have_prev) {
-                dRs[i] = r - pr[i];
-                dGfs[i] = gf - pgf[i];
-                dGas[i] = ga - pga[i];
-            }
-            pr[i] = r;
-            pgf[i] = gf;
-            pga[i] = ga;
-        }
-    }
-    if (have_prev) {
+    if (p.reset && rank == 0 && threadIdx.x == 0) { aa[0] = 0.0; aa[1] = 0.0; aa[2] = rel; aa[3] = 0.0; }
+    if (!p.run) return;
+    aa_slice_append(h, df, f, alpha, N, rank, p.slot, p.have_prev);
+    int nh = p.nh, slot = p.slot;
+    if (p.have_prev) {
         nh = min(nh + 1, AA_M);
         slot = (slot + 1) % AA_M;
     }
-    // normal equations A gamma = b, A_ij = <dR_i, dR_j>, b_i = <dR_i, r>: all products in one pass, one multi-value reduction per slice
-    for (int v = (int)rank, vl = 0; v < AA_CL; v += (int)ncta, ++vl) {
-        const int lo = v * per, hi = min(N, lo + per);
-        double acc[NV];
+    double acc[AA_NV];
+    aa_slice_products(h, df, N, rank, nh, acc, red_multi);
+    if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-        for (int k = lo + threadIdx.x; k < hi; k += 1024) {
-            double dv[AA_M];
-#pragma unroll
-            for (int i = 0; i < AA_M; ++i) dv[i] = (i < nh) ? dR[(long long)i * N + k] : 0.0;
-            const double rk = df[k];
-            int idx = 0;
-#pragma unroll
-            for (int i = 0; i < AA_M; ++i) {
-#pragma unroll
-                for (int j = 0; j <= i; ++j) { acc[idx] = fma(dv[i], dv[j], acc[idx]); ++idx; }
-                acc[NPAIR + i] = fma(dv[i], rk, acc[NPAIR + i]);
-            }
-        }
-        block_sum_multi<NV>(acc, red_multi);
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) part_s[vl * NV + i] = acc[i];
-        }
+        for (int i = 0; i < AA_NV; ++i) part_s[i] = acc[i];
     }
     cl.sync();                                                           // every CTA's partial sums are in its shared memory
     if (threadIdx.x == 0) {
-        double tot[NV];
+        double tot[AA_NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) tot[i] = 0.0;
+        for (int i = 0; i < AA_NV; ++i) tot[i] = 0.0;
         for (int v = 0; v < AA_CL; ++v) {                                // fixed order (by slice): identical totals in every CTA
-            const double* rp = cl.map_shared_rank(part_s, (unsigned)v % ncta) + (v / (int)ncta) * NV;
+            const double* rp = cl.map_shared_rank(part_s, (unsigned)v);
 #pragma unroll
-            for (int i = 0; i < NV; ++i) tot[i] += rp[i];
+            for (int i = 0; i < AA_NV; ++i) tot[i] += rp[i];
         }
-        double A[AA_M][AA_M], bb[AA_M];
-        int idx = 0;
-#pragma unroll
-        for (int i = 0; i < AA_M; ++i) {
-#pragma unroll
-            for (int j = 0; j <= i; ++j) { A[i][j] = A[j][i] = tot[idx]; ++idx; }
-            bb[i] = tot[NPAIR + i];
-        }
-        double tr = 0.0;
-        for (int i = 0; i < nh; ++i) tr += A[i][i];
-        for (int i = 0; i < nh; ++i) A[i][i] += 1e-10 * tr + 1e-300;     // damping: nearly collinear differences
-        bool ok = true;
-        for (int c = 0; c < nh && ok; ++c) {                             // Gaussian elimination with partial pivoting
-            int p = c;
-            for (int r2 = c + 1; r2 < nh; ++r2) if (fabs(A[r2][c]) > fabs(A[p][c])) p = r2;
-            if (A[p][c] == 0.0) { ok = false; break; }
-            for (int k = 0; k < nh; ++k) { const double t = A[c][k]; A[c][k] = A[p][k]; A[p][k] = t; }
-            { const double t = bb[c]; bb[c] = bb[p]; bb[p] = t; }
-            for (int r2 = c + 1; r2 < nh; ++r2) {
-                const double l = A[r2][c] / A[c][c];
-                for (int k = c; k < nh; ++k) A[r2][k] -= l * A[c][k];
-                bb[r2] -= l * bb[c];
-            }
-        }
-        for (int i = nh - 1; i >= 0 && ok; --i) {
-            double v = bb[i];
-            for (int k = i + 1; k < nh; ++k) v -= A[i][k] * gam[k];
-            gam[i] = v / A[i][i];
-            if (!(fabs(gam[i]) < 1e3)) ok = false;
-        }
-        nh_s = ok ? nh : 0;
+        const int nm = aa_solve(tot, nh, gam);
+        nm_s = nm;
         if (rank == 0) {
-            aa[0] = ok ? nh : 0;
-            aa[1] = ok ? slot : 0;
+            aa[0] = nm;
+            aa[1] = nm ? slot : 0;
             aa[2] = rel;
             aa[3] = 1.0;                                                  // (prev r, g) are valid from now on
         }
     }
     __syncthreads();
-    const int nm = nh_s;
-    for (int v = (int)rank; v < AA_CL && nm > 0; v += (int)ncta) {
-        const int lo = v * per, hi = min(N, lo + per);
-        for (int i = lo + threadIdx.x; i < hi; i += 1024) {
-            double cf = 0.0, ca = 0.0;
-            for (int j = 0; j < nm; ++j) {
-                cf = fma(gam[j], dGf[(long long)j * N + i], cf);
-                ca = fma(gam[j], dGa[(long long)j * N + i], ca);
-            }
-            f[i] -= cf;
-            alpha[i] -= ca;
-        }
-    }
+    aa_slice_apply(h, alpha, f, N, rank, nm_s, gam);
     cl.sync();                                  // nobody leaves while another CTA may still read its partial sums
+}
+
+// ---- the same call as three ordinary launches (see above)
+__global__ void __launch_bounds__(1024)
+chord_anderson_sums_kernel(const double* __restrict__ alpha, const double* __restrict__ f, const double* __restrict__ df, int N,
+                           const double* __restrict__ state, double* __restrict__ aa, double* __restrict__ H) {
+    __shared__ double red_multi[32 * AA_NV];
+    const AaView h(H, N);
+    const AaPlan p = aa_plan(state, aa);                                 // (aa is not written before the solve kernel)
+    if (!p.run) return;
+    aa_slice_append(h, df, f, alpha, N, blockIdx.x, p.slot, p.have_prev);
+    const int nh = p.have_prev ? min(p.nh + 1, AA_M) : p.nh;
+    double acc[AA_NV];
+    aa_slice_products(h, df, N, blockIdx.x, nh, acc, red_multi);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < AA_NV; ++i) aa[8 + blockIdx.x * AA_NV + i] = acc[i];
+    }
+}
+__global__ void chord_anderson_solve_kernel(const double* __restrict__ state, double* __restrict__ aa) {
+    if (threadIdx.x != 0) return;
+    double* gam_g = aa + 8 + AA_CL * AA_NV;
+    const AaPlan p = aa_plan(state, aa);
+    const double rel = state[1];
+    gam_g[AA_M] = 0.0;                                                   // number of coefficients the apply kernel uses
+    if (p.reset) { aa[0] = 0.0; aa[1] = 0.0; aa[2] = rel; aa[3] = 0.0; }
+    if (!p.run) return;
+    int nh = p.nh, slot = p.slot;
+    if (p.have_prev) {
+        nh = min(nh + 1, AA_M);
+        slot = (slot + 1) % AA_M;
+    }
+    double tot[AA_NV];
+#pragma unroll
+    for (int i = 0; i < AA_NV; ++i) tot[i] = 0.0;
+    for (int v = 0; v < AA_CL; ++v) {
+#pragma unroll
+        for (int i = 0; i < AA_NV; ++i) tot[i] += aa[8 + v * AA_NV + i];
+    }
+    double gam[AA_M];
+    const int nm = aa_solve(tot, nh, gam);
+    for (int i = 0; i < AA_M; ++i) gam_g[i] = i < nm ? gam[i] : 0.0;
+    gam_g[AA_M] = nm;
+    aa[0] = nm;
+    aa[1] = nm ? slot : 0;
+    aa[2] = rel;
+    aa[3] = 1.0;
+}
+__global__ void __launch_bounds__(1024)
+chord_anderson_apply_kernel(double* __restrict__ alpha, double* __restrict__ f, int N, const double* __restrict__ aa,
+                            double* __restrict__ H) {
+    __shared__ double gam[AA_M];
+    const double* gam_g = aa + 8 + AA_CL * AA_NV;
+    const int nm = (int)gam_g[AA_M];
+    if (nm == 0) return;
+    if (threadIdx.x < AA_M) gam[threadIdx.x] = gam_g[threadIdx.x];
+    __syncthreads();
+    const AaView h(H, N);
+    aa_slice_apply(h, alpha, f, N, blockIdx.x, nm, gam);
 }
 
 // dense Lambda (public attr GPModel.Lambda_MAP): one thread per row of the output
@@ -767,15 +853,21 @@ __global__ void __launch_bounds__(256) dchord_lik_kernel(const double* __restric
 bool thread_is_background();        // linalg.cu
 static int launch_chord_anderson(double* alpha, double* f, const double* df, int N, const double* state, double* aa, double* H,
                                  cudaStream_t st) {
+    if (thread_is_background()) {               // three ordinary launches (see chord_anderson_kernel)
+        PPBO_CL chord_anderson_sums_kernel<<<AA_CL, 1024, 0, st>>>(alpha, f, df, N, state, aa, H);
+        PPBO_CL chord_anderson_solve_kernel<<<1, 32, 0, st>>>(state, aa);
+        PPBO_CL chord_anderson_apply_kernel<<<AA_CL, 1024, 0, st>>>(alpha, f, N, aa, H);
+        PPBO_LAUNCH_CHECK();
+        return PPBO_OK;
+    }
     cudaLaunchConfig_t cfg = {};
-    const unsigned ncta = thread_is_background() ? 1u : (unsigned)AA_CL;
-    cfg.gridDim = dim3(ncta);
+    cfg.gridDim = dim3(AA_CL);
     cfg.blockDim = dim3(1024);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = ncta;
+    attr[0].val.clusterDim.x = AA_CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -857,7 +949,7 @@ struct FitWorkspace {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
         return 4 * N + 3 * M + (M + CHOL_NB) + (long long)NSTEP * Q + 32 + 8 + 64 + CHORD_STATE + 2 * CHORD_BATCH_MAX +
                blockinv_doubles((int)M) + 2LL * BORDER_MAX * (M + 2) + (long long)BORDER_MAX * BORDER_MAX + BORDER_MAX + 8 +
-               (3LL * AA_M + 3) * N + 8 + Q;
+               (3LL * AA_M + 3) * N + AA_STATE + Q;
     }
     void carve(double* base, int Q, int m) {
         const long long N = (long long)Q * (m + 1), M = (long long)Q * m;
@@ -883,7 +975,7 @@ struct FitWorkspace {
         bC = p; p += (long long)BORDER_MAX * BORDER_MAX;
         bw = p; p += BORDER_MAX;
         aaH = p; p += (3LL * AA_M + 3) * N;
-        aa = p; p += 8;
+        aa = p; p += AA_STATE;
         part0 = p;
     }
 };

@@ -1,2 +1,1 @@
-python -m pytest tests/test_full_size.py tests/test_incremental.py tests/test_gpu_ops.py -m gpu -x -q 2>&1 | tail -2
-python scripts/timeline.py --mode cold --steps 1 --out gpurun_out/timeline_cold.txt --dump gpurun_out/seq_cold.txt 2>&1 | tail -1
+for i in 1 2 3; do python bench.py --steps 10 --warmup 3 --no-api-leg --no-cpu-baseline > gpurun_out/bench_t24_$i.log 2>&1; done
