@@ -981,30 +981,24 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
             --it;                                        // the loop header adds one
             continue;
         }
-        // gradient at omega (always fresh); Hessian factor only on Newton steps, reused on chord steps
-        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, refactor, ws.scal + 24, st))) return rc;
-        if (refactor) {
-            PPBO_CL rff_psi_kernel<<<dim3(ceil_div(M, 256), F), 256, 0, st>>>(Phi_X, ld, Q, m, ws.arrow, ws.PsiT, M);
+        // ---- Newton step: gradient and clamped Hessian at omega, fresh factor (chord steps with a kept factor all go through the
+        // batches above)
+        if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, ws.grad, nullptr, true, ws.scal + 24, st))) return rc;
+        PPBO_CL rff_psi_kernel<<<dim3(ceil_div(M, 256), F), 256, 0, st>>>(Phi_X, ld, Q, m, ws.arrow, ws.PsiT, M);
+        {
             GemmOperands g{ws.PsiT, M, 0, ws.PsiT, M, 0, F, F, M};
             StoreEpilogue ep{ws.H, F, 0, 1.0, 0.0, 0, 0, 0};
             if ((rc = launch_gemm_nt(g, ep, 1, st))) return rc;
-            PPBO_CL add_identity_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.H, F, F);
-            if ((rc = potrf_lower(ws.H, F, F, Hdinv, info_d, st))) return rc;
-            ++n_factor;
-            binv_valid = false;
-            PPBO_CUDA_CHECK(cudaMemsetAsync(ws.aa, 0, sizeof(double) * 8, st));     // new iteration matrix: forget the mixing history
-            rel3_h = INFINITY;
-        } else {
-            ++n_chord;
-            if (!binv_valid) {            // the factor is about to be reused: invert its diagonal blocks once (linalg.cu)
-                if ((rc = blockinv_build(ws.H, F, F, Hdinv, ws.binv, st))) return rc;
-                binv_valid = true;
-            }
         }
+        PPBO_CL add_identity_kernel<<<ceil_div(F, 256), 256, 0, st>>>(ws.H, F, F);
+        if ((rc = potrf_lower(ws.H, F, F, Hdinv, info_d, st))) return rc;
+        ++n_factor;
+        binv_valid = false;
+        PPBO_CUDA_CHECK(cudaMemsetAsync(ws.aa, 0, sizeof(double) * 8, st));     // new iteration matrix: forget the mixing history
+        rel3_h = INFINITY;
         PPBO_CUDA_CHECK(cudaMemcpyAsync(ws.step, ws.grad, sizeof(double) * F, cudaMemcpyDeviceToDevice, st));
         // step = (-Hessian)^-1 grad  (ascent direction)
-        rc = binv_valid ? potrs_vec_blockinv(ws.H, F, F, ws.binv, ws.step, st) : potrs_vec(ws.H, F, F, Hdinv, ws.step, st);
-        if (rc) return rc;
+        if ((rc = potrs_vec(ws.H, F, F, Hdinv, ws.step, st))) return rc;
         // line search, all LS_STEPS step sizes in one pass: f(omega + s step) = f0 + s df, |omega + s step|^2 in closed form
         launch_rff_fvals(Phi_X, ld, F, N, ws.step, ws.fpart, ws.dfv, st);
         if ((rc = launch_linesearch_lik(ws.fvals, ws.dfv, Q, m, sigma, part, st))) return rc;
@@ -1023,22 +1017,15 @@ extern "C" int ppbo_rff_fit(const double* Phi_X, long long ld, int F, int Q, int
             const double S_try = -0.5 * (oo + 2.0 * s * od + s * s * dd) - h[8 + c] / m;
             if (S_try >= S_cur - 1e-13 * fabs(S_cur)) { S_new = S_try; break; }
         }
-        if (!refactor && c > 0) {            // damped chord direction: refactor at this point instead
-            refactor = true;
-            --it;
-            continue;
-        }
         if (c == LS_STEPS) { s = std::ldexp(1.0, -(LS_STEPS - 1)); S_new = NAN; }
         PPBO_CL axpy_kernel<<<ceil_div(F, 256), 256, 0, st>>>(omega_map, ws.step, s, F);
         PPBO_LAUNCH_CHECK();
         S_cur = S_new;
-        const double prev_rel = last_rel;
         prev_rel_h = last_rel;
         last_rel = s * max_step / max_om;
-        if (trace) fprintf(stderr, "[ppbo_rff_fit] it %d %s step %.3g rel %.3e S %.12g\n", it, refactor ? "newton" : "chord ", s, last_rel, S_cur);
+        if (trace) fprintf(stderr, "[ppbo_rff_fit] it %d newton step %.3g rel %.3e S %.12g\n", it, s, last_rel, S_cur);
         if (c == 0 && last_rel <= tol) { ++it; break; }
-        if (refactor) refactor = !(c == 0 && last_rel <= CHORD_REL);
-        else refactor = !(last_rel <= 0.5 * prev_rel);
+        refactor = !(c == 0 && last_rel <= CHORD_REL);       // chord steps once a full Newton step is in the contraction region
     }
     if (std::isnan(S_cur)) {                             // last step left S unevaluated: evaluate at the final point
         if ((rc = rff_eval(Phi_X, ld, F, Q, m, sigma, omega_map, ws, nullptr, nullptr, false, ws.scal + 24, st))) return rc;
