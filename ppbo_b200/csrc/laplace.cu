@@ -1243,6 +1243,14 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         PPBO_CL border_update_kernel<<<ceil_div(M_old, 256), 256, 0, st>>>(ws.bR, Mp, ws.bw, M_old, nb, z, skip);
         return potrs_bwd_blockinv(Lfac, ldl, M_old, ws.binv, ws.t, st, skip);
     };
+    // chord batches in difference space keep (gamma, d) between batches; (alpha, f) are restored when the fit leaves the chord phase
+    bool in_diff = false;
+    auto leave_diff = [&]() -> int {
+        if (!in_diff) return PPBO_OK;
+        in_diff = false;
+        PPBO_CL from_diff_kernel<<<set_blocks, 256, 0, st>>>(ws.bvec, Q, m, alpha);          // alpha = B gamma
+        return gemv(Sigma, lds, N, N, alpha, f_map, st);                                       // f = Sigma alpha
+    };
     while (it < max_iter && !converged) {
         if (!refactor) {
             // ---- a batch of chord steps: the factor is kept, only the right-hand side is refreshed; acceptance, the convergence
@@ -1273,7 +1281,10 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                 // alpha-space step, which are idle here
                 double *gam = ws.bvec, *dv = ws.Sb, *cv = ws.dalpha, *dgam = ws.df, *ddv = ws.arrow_tmp;
                 const double thr = 1e-3 * 0.121 / (m * sigma * sigma);       // 1e-3 of the largest possible coefficient
-                PPBO_CL to_diff_kernel<<<ceil_div(M, 256), 256, 0, st>>>(f_map, alpha, Q, m, dv, gam);
+                if (!in_diff) {              // (consecutive batches stay in difference space: nothing else touches these vectors)
+                    PPBO_CL to_diff_kernel<<<ceil_div(M, 256), 256, 0, st>>>(f_map, alpha, Q, m, dv, gam);
+                    in_diff = true;
+                }
                 for (int i = 0; i < kb; ++i) {
                     if (bordered)
                         PPBO_CL dborder_coeff_kernel<<<ceil_div(nb, 64), 64, 0, st>>>(dv + M_old, nb, sigma, m, ws.sa + M_old, ws.ap + M_old, skip);
@@ -1288,9 +1299,6 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
                                                                       (chord_extrapolate && !anderson) ? 1 : 0, anderson ? ws.part0 : nullptr);
                     if (anderson && (rc = launch_chord_anderson(gam, dv, ddv, M, ws.state, ws.aa, ws.aaH, st))) return rc;
                 }
-                // back to (alpha, f): alpha = B gamma, f = Sigma alpha
-                PPBO_CL from_diff_kernel<<<set_blocks, 256, 0, st>>>(gam, Q, m, alpha);
-                if ((rc = gemv(Sigma, lds, N, N, alpha, f_map, st))) return rc;
             } else
             for (int i = 0; i < kb; ++i) {
                 if (bordered) refresh_border(skip);
@@ -1332,6 +1340,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
             continue;
         }
         // ---- Newton step: refactor I + a+^1/2 G a+^1/2 at the current iterate
+        if ((rc = leave_diff())) return rc;
         PPBO_CL lik_terms_kernel<<<set_blocks, 256, 0, st>>>(f_map, Q, m, sigma, nullptr, nullptr, nullptr, ws.sa, ws.bvec, nullptr, ws.ap);
         identity_factor = (it == 0 && !have_start);
         if (identity_factor) {
@@ -1414,6 +1423,7 @@ extern "C" int ppbo_laplace_fit(const double* Sigma, long long lds, int Q, int m
         const double chord_rel = (anderson_mode >= 2 && !warm_factor && n_factor == 1 && !aa_failed && !getenv("PPBO_CHORD_REL")) ? 0.6 : CHORD_REL;
         refactor = !(step == 1.0 && last_rel <= chord_rel) || identity_factor;
     }
+    if ((rc = leave_diff())) return rc;
     // The factor a later warm fit can reuse is the one the last Newton step built (or the warm one it was handed): its
     // coefficients go to sa_fac.  (An identity "factor" -- cold start that converged at once -- is not a factor object.)
     if (bordered && !factor_at_mode) {
