@@ -202,6 +202,46 @@ def fmap_tight(Sigma, Q, m, sigma, f_start, iters=60, tol=1e-13):
     return f
 
 
+def incidence(Q, m):
+    """B [N x M]: column (q, j) has +1 at pseudo-observation j of set q and -1 at the set's winner, so that W = B diag(a) B^T
+    (create_Lambda above) and B^T f are the differences the likelihood sees."""
+    N, M = Q * (m + 1), Q * m
+    B = np.zeros((N, M))
+    for q in range(Q):
+        for j in range(m):
+            B[q * (m + 1) + 1 + j, q * m + j] = 1.0
+            B[q * (m + 1), q * m + j] = -1.0
+    return B
+
+
+def chord_step_alpha(Sigma, f, a0, Q, m, sigma):
+    """One chord step of the Newton iteration for Sigma^-1 f = beta(f) with FIXED clamped coefficients a0 >= 0 (those of the
+    factor), in the (alpha, f) form of csrc/laplace.cu:  (I + W0 Sigma) alpha_new = W0 f + beta(f),  W0 = B a0 B^T,  solved through
+    the M x M system  alpha_new = b - B s (I + s G s)^-1 s B^T Sigma b  (G = B^T Sigma B, s = sqrt(a0)).  Returns (alpha_new, f_new).
+    Test infrastructure: restates the device iteration; the reference itself uses scipy trust-exact (src/gp_model.py:382-384)."""
+    B = incidence(Q, m)
+    s = np.sqrt(a0)
+    G = B.T @ Sigma @ B
+    b = B @ (a0 * (B.T @ f)) + lik_beta(f, Q, m, sigma)
+    y = np.linalg.solve(np.eye(Q * m) + s[:, None] * G * s[None, :], s * (B.T @ (Sigma @ b)))
+    alpha_new = b - B @ (s * y)
+    return alpha_new, Sigma @ alpha_new
+
+
+def chord_step_diff(G, gamma, d, a0, Q, m, sigma, threshold=0.0):
+    """The same step carried by the M-vectors (gamma, d = G gamma) -- alpha = B gamma, d = B^T f:
+        c = a0 d + g(d),   (I + s G s) y = s G c,   gamma_new = c - s y,   d_new = y / s  where a0 > threshold, else (G gamma_new)
+    (from s G s y = s G c - y).  One product with G instead of two with Sigma.  Returns (gamma_new, d_new)."""
+    s = np.sqrt(a0)
+    g = -var2_normal_pdf(d / sigma) / (sigma * m)                  # beta = B g
+    c = a0 * d + g
+    y = np.linalg.solve(np.eye(Q * m) + s[:, None] * G * s[None, :], s * (G @ c))
+    gamma_new = c - s * y
+    big = a0 > threshold
+    d_new = np.where(big, y / np.where(big, s, 1.0), G @ gamma_new)
+    return gamma_new, d_new
+
+
 def posterior_covariance(Sigma_inv, fMAP, Q, m, sigma):
     """src/gp_model.py:111-117."""
     Lam = create_Lambda(fMAP, Q, m, sigma)
