@@ -667,14 +667,36 @@ __global__ void __launch_bounds__(1024) border_solve_kernel(const double* __rest
                                                             const double* __restrict__ skip) {
     __shared__ double S[BORDER_MAX][BORDER_MAX + 1];
     __shared__ double r[BORDER_MAX];
+    __shared__ double red_multi[32 * 16];
     if (skip && *skip != 0.0) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int u = warp; u < nb; u += 32) {
-        const double* Ru = R + (long long)u * ldr;
-        double a = 0.0;
-        for (int v = lane; v < M_old; v += 32) a = fma(Ru[v], z[v], a);
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) r[u] = t_new[u] - s_new[u] * a;
+    if (nb <= 32) {
+        // R z for all rows in ONE pass: a thread keeps one accumulator per row over its columns (coalesced in v), one multi-value
+        // block reduction follows.  (One warp per row: 157 dependent iterations of a single warp per row, ~25 of the kernel's 35 us.)
+        // (16 rows per pass: 32 accumulators would not fit the 64-register budget of a 1024-thread CTA)
+        for (int u0 = 0; u0 < nb; u0 += 16) {
+            double acc[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc[u] = 0.0;
+            for (int v = tid; v < M_old; v += 1024) {
+                const double zv = z[v];
+#pragma unroll
+                for (int u = 0; u < 16; ++u)
+                    if (u0 + u < nb) acc[u] = fma(R[(long long)(u0 + u) * ldr + v], zv, acc[u]);
+            }
+            block_sum_multi<16>(acc, red_multi);
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (tid == u && u0 + u < nb) r[u0 + u] = t_new[u0 + u] - s_new[u0 + u] * acc[u];
+        }
+    } else {
+        for (int u = warp; u < nb; u += 32) {
+            const double* Ru = R + (long long)u * ldr;
+            double a = 0.0;
+            for (int v = lane; v < M_old; v += 32) a = fma(Ru[v], z[v], a);
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) r[u] = t_new[u] - s_new[u] * a;
+        }
     }
     for (int e = tid; e < nb * nb; e += 1024) {
         const int u = e / nb, v = e % nb;
