@@ -65,6 +65,15 @@ def test_misc_linear_algebra(golden):
         misc.pd_inverse(bad)
     A = np.random.RandomState(0).rand(6, 6) + 3 * np.eye(6)
     assert np.abs(misc.inverse(A) @ A - np.eye(6)).max() < 1e-10
+    # cond 1e6: the normal equations alone lose ten digits (cond^2 eps); the refinement steps return what LAPACK's LU-based
+    # inverse (the reference's scipy.linalg.inv, src/misc.py:91-93) delivers
+    rs = np.random.RandomState(1)
+    U, _ = np.linalg.qr(rs.randn(40, 40))
+    V, _ = np.linalg.qr(rs.randn(40, 40))
+    B = (U * np.logspace(0, -6, 40)) @ V.T
+    Binv = misc.inverse(B)
+    assert relerr(Binv, np.linalg.inv(B)) < 1e-8
+    assert np.abs(B @ Binv - np.eye(40)).max() < 1e-8
 
 
 def test_model_fit_matches_reference(golden):
