@@ -1,9 +1,12 @@
 """Summarise ncu outputs brought back in gpurun_out/ into small text files for profiles/ (run here, no GPU needed).
   python scripts/ncu_summary.py launches gpurun_out/r01_launches.csv            -> per-kernel share table
-  python scripts/ncu_summary.py rep gpurun_out/r01_rowmax.ncu-rep               -> key raw metrics per captured launch"""
+  python scripts/ncu_summary.py rep gpurun_out/r01_rowmax.ncu-rep               -> key raw metrics per captured launch
+  python scripts/ncu_summary.py sass ppbo_b200/libppbo_b200.so                  -> per-kernel registers / spills / shared memory
+                                                                                   and counts of the Blackwell SASS mnemonics"""
 import collections
 import csv
 import io
+import os
 import re
 import subprocess
 import sys
@@ -77,8 +80,55 @@ def traffic(path, key, out_json="profiles/traffic.json", pattern=None):
     print("no matching launch in", path)
 
 
+MNEMONICS = ["UTCIMMA", "UTCCP", "UTCBAR", "LDTM", "UBLKCP", "SYNCS", "DMMA", "LDGSTS", "REDUX", "ATOM", "RED."]
+
+
+def sass(path):
+    """static evidence from the built library (cuobjdump, no GPU): which kernels issue tcgen05 (UTCIMMA / UTCCP / LDTM / UTCBAR),
+    TMA bulk copies (UBLKCP) with mbarrier waits (SYNCS), FP64 tensor-core MMAs (DMMA), cp.async (LDGSTS); registers and spills"""
+    def demangle(names):
+        out = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
+        return dict(zip(names, [re.sub(r"^void ", "", re.sub(r"\(.*", "", d)) for d in out]))
+    res = subprocess.run(["cuobjdump", "--dump-resource-usage", path], capture_output=True, text=True).stdout
+    usage = {m.group(1): m.group(2) for m in re.finditer(r"Function (\S+):\n\s+(REG:.*)", res)}
+    text = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    counts, cur = collections.OrderedDict(), None
+    for line in text.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = counts.setdefault(m.group(1), collections.Counter())
+            continue
+        if cur is None or "/*" not in line:
+            continue
+        cur["_inst"] += 1
+        for k in MNEMONICS:
+            if k in line:
+                cur[k] += 1
+    spills = {}
+    log = os.path.join(os.path.dirname(os.path.abspath(path)), "build", "ptxas.log")     # written by ppbo_b200/build.py (-Xptxas -v)
+    if os.path.exists(log):
+        for m in re.finditer(r"Function properties for (\S+)\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads",
+                             open(log).read()):
+            spills[m.group(1)] = (int(m.group(3)), int(m.group(4)))
+    names = demangle(list(counts))
+    print("# %s: %d kernels, arch sm_100a; columns after smem are SASS instruction counts (static, not executed)" % (path, len(counts)))
+    print("# spill = bytes of spill stores/loads per thread reported by ptxas -v (stack frames without spills are local arrays and the "
+          "slow paths of sin / cos / exp / erfc)")
+    print("%-64s %4s %5s %7s %7s %6s  %s" % ("kernel", "reg", "stack", "spill", "smem", "inst", "mnemonics"))
+    tot = collections.Counter()
+    for k, c in counts.items():
+        u = dict(f.split(":") for f in usage.get(k, "").split() if ":" in f)
+        tot.update(c)
+        marks = " ".join("%s=%d" % (m, c[m]) for m in MNEMONICS if c[m])
+        print("%-64s %4s %5s %7s %7s %6d  %s" % (names[k][:64], u.get("REG", "?"), u.get("STACK", "?"), "%d/%d" % spills.get(k, (0, 0)),
+                                                 u.get("SHARED", "?"), c["_inst"], marks))
+    print("# totals: " + " ".join("%s=%d" % (m, tot[m]) for m in MNEMONICS))
+    print("# kernels with register spills: " + (", ".join("%s (%d/%d B)" % ((names[k][:60],) + spills[k]) for k in counts
+                                                          if sum(spills.get(k, (0, 0)))) or "none"))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "traffic":
         traffic(*sys.argv[2:])
     else:
-        {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2])
+        {"launches": launches, "rep": rep, "sass": sass}[sys.argv[1]](sys.argv[2])
