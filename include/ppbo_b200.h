@@ -201,6 +201,25 @@ int ppbo_predict(int kind, const double* X, int N, int D, const double* lengthsc
  * differential evolution of GPModel.mu_star (src/gp_model.py:415-437: ~10^4 dependent evaluations per model update). */
 int ppbo_mu_pred_point(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f, const double* alpha,
                        const double* x_h, double* mu_h, void* stream);
+/* The sequential differential evolution of GPModel.mu_star (src/gp_model.py:415-437: scipy.optimize.differential_evolution(
+ * mu_pred_neq, bounds, updating='immediate', maxiter=2000)) with the loop on the host in C++ instead of in scipy's Python: strategy
+ * 'best1bin', latin-hypercube start, population popsize x D, dither in [mutation_lo, mutation_hi), stop when
+ * std(energies) <= atol + tol |mean(energies)|.  It replays scipy 1.18 on numpy's legacy global stream draw for draw: mt_key[624] /
+ * mt_pos are the MT19937 state of numpy.random.get_state() on entry and the state to hand to set_state() on return, and the
+ * trial vectors, accepted members, stopping generation and result are bit for bit those of the scipy call on the same objective.
+ * The L-BFGS-B polish scipy runs afterwards is left to the caller.  All pointers are HOST pointers.
+ * x_h[D] / fun_h[1]: best member in problem units and its value; stats_h[4] (may be NULL): generations, evaluations, converged,
+ * population size.  An objective that returns NaN stops the search with an error.
+ *   ppbo_de_minimize : any objective given as a callback (the CPU tests compare it with scipy through this entry)
+ *   ppbo_mu_star_de  : objective -mu(x) = -k(x, X) alpha on the device, one ppbo_mu_pred_point launch per trial (X, alpha: DEVICE) */
+typedef double (*ppbo_objective_fn)(const double* x_h, int D, void* ctx);
+int ppbo_de_minimize(ppbo_objective_fn f, void* ctx, int D, const double* lower_h, const double* upper_h, int popsize, int maxiter,
+                     double tol, double atol, double mutation_lo, double mutation_hi, double recombination, unsigned int* mt_key,
+                     int* mt_pos, double* x_h, double* fun_h, int* stats_h);
+int ppbo_mu_star_de(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f, const double* alpha,
+                    const double* lower_h, const double* upper_h, int popsize, int maxiter, double tol, double atol,
+                    double mutation_lo, double mutation_hi, double recombination, unsigned int* mt_key, int* mt_pos, double* x_h,
+                    double* fun_h, int* stats_h, void* stream);
 /* fmax[b][s] = max_p ( mu[b][p] + sum_k Z[b][s][k] Fac[b][p][k] ), arg[b][s] = first arg-max.
  * Replaces the S calls of np.random.multivariate_normal + np.max in acquisition.EI / varmax
  * (src/acquisition.py:78-80, 175-177); Fac is the (P x P) sampling factor (row p = coefficients of point p). */

@@ -7,9 +7,10 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libppbo_b200.so")
-SOURCES = ["linalg.cu", "gram.cu", "laplace.cu", "acq.cu", "ozaki.cu"]
+SOURCES = ["linalg.cu", "gram.cu", "laplace.cu", "acq.cu", "ozaki.cu", "de.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+         "-Xcompiler", "-ffp-contract=off",        # host arithmetic as written (de.cu replays numpy's operations one by one)
          "-Xptxas", "-v"]
 
 

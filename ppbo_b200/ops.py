@@ -428,6 +428,95 @@ class PointMean:
         return self.out.value
 
 
+# --- GPModel.mu_star's sequential differential evolution with the loop in C++ (csrc/de.cu) -----------------------------------
+_OBJECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_void_p)
+DE_DEFAULTS = dict(popsize=15, maxiter=1000, tol=0.01, atol=0.0, mutation=(0.5, 1.0), recombination=0.7)     # scipy's
+
+
+class DEResult:
+    """x, fun: best member (problem units) and its value at the end of the evolution (before any polish); nit, nfev, converged,
+    population_size as scipy reports them"""
+
+    def __init__(self, x, fun, stats):
+        self.x, self.fun = x, fun
+        self.nit, self.nfev, self.converged, self.population_size = int(stats[0]), int(stats[1]), bool(stats[2]), int(stats[3])
+
+
+def _de_call(entry, head, bounds, tail, popsize, maxiter, tol, atol, mutation, recombination, what):
+    """shared part of the two entries: numpy's global MT19937 state in, the same stream advanced by exactly scipy's draws out"""
+    bounds = np.asarray(bounds, dtype=np.float64)
+    D = bounds.shape[0]
+    lo, hi = _lib.host_doubles(bounds[:, 0]), _lib.host_doubles(bounds[:, 1])
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    if name != "MT19937":
+        raise PPBOError("numpy's global generator is not the legacy MT19937")
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    pos_c = ctypes.c_int(int(pos))
+    x = (ctypes.c_double * D)()
+    fun = ctypes.c_double(0.0)
+    stats = (ctypes.c_int * 4)()
+    mut = sorted(float(v) for v in np.atleast_1d(mutation))
+    if len(mut) != 2:
+        raise PPBOError("mutation must be a (min, max) pair (dither), as in the reference's default call")
+    rc = entry(*head, D, lo, hi, int(popsize), int(maxiter), float(tol), float(atol), mut[0], mut[1], float(recombination),
+               key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.byref(pos_c), x, ctypes.byref(fun), stats, *tail)
+    np.random.set_state((name, key, int(pos_c.value), has_gauss, cached))
+    if rc:
+        raise PPBOError("%s failed (%d): %s" % (what, rc, _lib.last_error()))
+    return DEResult(np.array(x[:], dtype=np.float64), float(fun.value), stats)
+
+
+def de_minimize(func, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0, mutation=(0.5, 1.0), recombination=0.7):
+    """scipy.optimize.differential_evolution(func, bounds, updating='immediate', polish=False) on numpy's GLOBAL legacy stream,
+    replayed draw for draw by ppbo_de_minimize: same result bits, same state of np.random afterwards.  func: x (D,) -> float."""
+    D = len(bounds)
+    failure = []
+
+    def cb(xp, d, _ctx):
+        try:
+            return float(func(np.ctypeslib.as_array(xp, shape=(d,)).copy()))
+        except BaseException as e:                    # an exception must not unwind through the C frames
+            failure.append(e)
+            return float("nan")
+    try:
+        return _de_call(_lib.load().ppbo_de_minimize, (_OBJECTIVE_FN(cb), None), bounds, (), popsize, maxiter, tol, atol, mutation,
+                        recombination, "ppbo_de_minimize")
+    except PPBOError:
+        if failure:
+            raise failure[0]
+        raise
+
+
+def de_polish(func, de, bounds):
+    """the L-BFGS-B polish that ends scipy.optimize.differential_evolution(..., polish=True), made exactly as
+    scipy/optimize/_differentialevolution.py (1.18: solve(), 'if self.polish') makes it: from the best member, inside the bounds,
+    accepted only if it improves.  de: DEResult of the evolution; returns a scipy OptimizeResult (x, fun, nit, nfev, success)."""
+    import scipy.optimize
+    limits = np.array(bounds, dtype=float).T
+    res = scipy.optimize.OptimizeResult(x=de.x, fun=de.fun, nit=de.nit, nfev=de.nfev, success=de.converged)
+    polished = scipy.optimize.minimize(lambda x: func(np.atleast_2d(x)[0]), np.copy(de.x), method='L-BFGS-B',
+                                       bounds=scipy.optimize.Bounds(lb=limits[0], ub=limits[1]), constraints=())
+    res.nfev += polished.get("nfev", 0)
+    if polished.fun < res.fun and polished.success and np.all(polished.x <= limits[1]) and np.all(limits[0] <= polished.x):
+        res.fun, res.x = polished.fun, polished.x
+    return res
+
+
+def mu_star_de(kernel, X, lengthscales, sigma_f, alpha, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0, mutation=(0.5, 1.0),
+               recombination=0.7):
+    """the same search with the objective -mu(x) = -k(x, X) alpha evaluated on the device, one ppbo_mu_pred_point launch per trial
+    (bit-identical to a scipy call over PointMean); returns a DEResult with fun = -mu(x)"""
+    N, D = X.shape
+    head = (_kind(kernel), _p(X), N)
+    # ppbo_mu_star_de(kind, X, N, D, ls, sigma_f, alpha, lower, upper, ...): D and the bounds come from _de_call, so wrap the entry
+    lib = _lib.load()
+    ls = _ls(lengthscales, D)
+
+    def entry(kind, Xp, n, d, lo, hi, *rest):
+        return lib.ppbo_mu_star_de(kind, Xp, n, d, ls, float(sigma_f), _p(alpha), lo, hi, *rest)
+    return _de_call(entry, head, bounds, (_stream(),), popsize, maxiter, tol, atol, mutation, recombination, "ppbo_mu_star_de")
+
+
 def mvn_rowmax(Z, Fac, mu):
     """Z: [B,S,K], Fac: [B,P,K], mu: [B,P] -> fmax [B,S], arg [B,S] (int32)"""
     B, S, K = Z.shape

@@ -430,16 +430,18 @@ class GPModel:
     def mu_star(self, mustar_finding_trials=None):
         if mustar_finding_trials is None:
             mustar_finding_trials = self.mustar_finding_trials
-        batched = self.mustar_method == "batched"
+        method = self.mustar_method
         xstar = xstars_local = None
         best = np.inf
         for i in range(mustar_finding_trials):
-            if batched:
+            if method == "batched":
                 res = scipy.optimize.differential_evolution(self._mu_pred_neq_population, self.bounds, updating='deferred',
                                                             vectorized=True, disp=False, maxiter=2000)
-            else:   # exactly the reference's call: sequential 'immediate' updating on the global RNG
+            elif method == "de-scipy":   # literally the reference's call: sequential 'immediate' updating on the global RNG
                 res = scipy.optimize.differential_evolution(self.mu_pred_neq, self.bounds, updating='immediate', disp=False,
                                                             maxiter=2000)
+            else:                        # 'de': the same search, same draws, same bits, with the loop in C++ (ppbo_mu_star_de)
+                res = self._mu_star_de()
             if i == 0:
                 xstars_local = np.array(res.x, dtype=float).reshape(1, self.D)
             elif all(np.linalg.norm(x - res.x) > 1e-1 for x in xstars_local):
@@ -448,6 +450,17 @@ class GPModel:
                 best, xstar = res.fun, np.array(res.x, dtype=float)
         xstar = xstar.reshape(self.D,)
         return xstar, self.mu_pred(xstar), xstars_local
+
+    def _mu_star_de(self):
+        """scipy.optimize.differential_evolution(self.mu_pred_neq, self.bounds, updating='immediate', maxiter=2000) with the
+        evolution replayed by ppbo_mu_star_de (csrc/de.cu): numpy's global stream is consumed draw for draw as scipy would, every
+        trial is one device evaluation of the posterior mean, and the result equals the scipy call's bit for bit (tests/
+        test_de_replay.py on the CPU, test_src_gpu.py::test_mu_star_native_equals_scipy on the GPU).  The L-BFGS-B polish that
+        ends scipy's call is made by ops.de_polish exactly as scipy makes it."""
+        theta = self.theta
+        de = ops.mu_star_de(self._kernel_name(), self._Xd(), theta[1], theta[2], self._fit.alpha, self.bounds, maxiter=2000)
+        self.mu_pred_calls = getattr(self, "mu_pred_calls", 0) + de.nfev
+        return ops.de_polish(self.mu_pred_neq, de, self.bounds)
 
     # ------------------------------------------------------------------ predictions (src/gp_model.py:441-461)
     def _predict_dev(self, X_pred_dev, P, batch, want_cov=True):

@@ -62,5 +62,7 @@ class PPBO_settings:
         # 'svd-host': numpy's legacy multivariate_normal factor (bit-compatible draws with the reference for the same RNG
         #             stream); 'device': symmetric eigen-factor computed on the GPU (same distribution, own sign convention)
         self.mvn_factor = mvn_factor
-        # 'de': scipy differential evolution exactly as the reference calls it; 'batched': one device evaluation per generation
+        # 'de': the reference's sequential differential evolution, replayed draw for draw with its loop in C++ (same result bits
+        #       as the scipy call, a third of the time); 'de-scipy': the scipy call itself; 'batched': one device evaluation per
+        #       generation (scipy 'deferred' updating: another trajectory)
         self.mustar_method = mustar_method

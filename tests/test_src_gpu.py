@@ -197,6 +197,27 @@ def test_mu_star_replays_reference_search(golden):
     assert abs(gp.mu_pred(xstar) - mustar) == 0
 
 
+def test_mu_star_native_equals_scipy(golden):
+    """the default search ('de': scipy's differential evolution replayed by ppbo_mu_star_de, loop in C++, one device evaluation per
+    trial) against the scipy call itself ('de-scipy') on the same stream: same maximiser, same value, same local maximisers, same
+    number of posterior-mean evaluations, and numpy's global generator left in the same state -- bit for bit"""
+    g = golden
+    st, gp = _model(g)
+    out = {}
+    for method in ("de-scipy", "de"):
+        gp.mustar_method = method
+        gp.mu_pred_calls = 0
+        np.random.seed(int(g["seed_fit"]) + 1)
+        np.random.standard_normal(5)
+        xstar, mustar, local = gp.mu_star(mustar_finding_trials=2)
+        out[method] = (xstar, mustar, local, gp.mu_pred_calls, np.random.get_state())
+    a, b = out["de-scipy"], out["de"]
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+    assert a[2].shape == b[2].shape and np.array_equal(a[2], b[2])
+    assert a[3] == b[3] and a[3] > 0
+    assert a[4][0] == b[4][0] and np.array_equal(a[4][1], b[4][1]) and a[4][2:] == b[4][2:]
+
+
 def test_mu_star_batched(golden):
     """opt-in batched search (one device call per DE generation): no worse than the best of 4096 uniform candidates"""
     g = golden
