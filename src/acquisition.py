@@ -28,20 +28,27 @@ GRID_POINTS = 70          # hard-coded in the reference (src/acquisition.py:73,1
 
 # ------------------------------------------------------------------------------------------------ batched MC engine
 try:
-    from threadpoolctl import threadpool_limits as _blas_limits
+    from threadpoolctl import ThreadpoolController as _ThreadpoolController
 except Exception:        # pragma: no cover
-    _blas_limits = None
+    _ThreadpoolController = None
+_blas_controller = None
 
 
 def _svd_factor(cov):
-    """(P x P) F with F[p][k] = sqrt(s_k) V[k][p]: numpy's legacy multivariate_normal factor, transposed for the GEMM.
-    One BLAS thread: a 70 x 70 SVD on a many-core host otherwise spends its time waking and parking the thread pool."""
-    if _blas_limits is not None:
-        with _blas_limits(limits=1):
+    """cov: (P x P) or a stack (B x P x P) -> F with F[..., p, k] = sqrt(s_k) V[k][p]: numpy's legacy multivariate_normal factor,
+    transposed for the GEMM.  One LAPACK call per matrix (numpy's gufunc loops over the stack in C: the same calls, the same bits
+    as matrix-by-matrix), on ONE BLAS thread: a 70 x 70 SVD on a many-core host otherwise spends its time waking and parking the
+    thread pool.  The thread limit goes through one ThreadpoolController kept for the process (a fresh threadpool_limits context
+    re-scans the loaded libraries, ~0.4 ms per use)."""
+    global _blas_controller
+    if _ThreadpoolController is not None:
+        if _blas_controller is None:
+            _blas_controller = _ThreadpoolController()
+        with _blas_controller.limit(limits=1):
             _, s, v = np.linalg.svd(cov)
     else:
         _, s, v = np.linalg.svd(cov)
-    return np.ascontiguousarray((np.sqrt(s)[:, None] * v).T)
+    return np.ascontiguousarray(np.swapaxes(np.sqrt(s)[..., :, None] * v, -1, -2))
 
 
 def _device_factor(Sp_dev):
@@ -82,7 +89,7 @@ def sampled_max_batch(pairs, GP_model, mc_samples):
     else:
         Sp_h = Sp.cpu().numpy()
         t2 = time.time()
-        Fac = ops.to_dev(np.stack([_svd_factor(Sp_h[b]) for b in range(B)]))
+        Fac = ops.to_dev(_svd_factor(Sp_h))
         t3 = time.time()
     fmax, _arg = ops.mvn_rowmax(ops.to_dev(Z), Fac, mu)
     tm = getattr(GP_model, "timing", None)
