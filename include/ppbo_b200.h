@@ -208,18 +208,31 @@ int ppbo_mu_pred_point(int kind, const double* X, int N, int D, const double* le
  * mt_pos are the MT19937 state of numpy.random.get_state() on entry and the state to hand to set_state() on return, and the
  * trial vectors, accepted members, stopping generation and result are bit for bit those of the scipy call on the same objective.
  * The L-BFGS-B polish scipy runs afterwards is left to the caller.  All pointers are HOST pointers.
- * x_h[D] / fun_h[1]: best member in problem units and its value; stats_h[4] (may be NULL): generations, evaluations, converged,
- * population size.  An objective that returns NaN stops the search with an error.
+ * x_h[D] / fun_h[1]: best member in problem units and its value; stats_h[6] (may be NULL): generations, evaluations (as scipy
+ * counts them), converged, population size, discarded evaluations, calls of f / f_batch.  An objective that returns NaN stops the
+ * search with an error.
+ * window > 1: under 'immediate' updating a trial reads the best member, two sampled members and its own, so the next `window`
+ * trials are built from the population as it is and evaluated in one call (f_batch: B rows of x_h -> f_h[B], return 0; one launch
+ * on the device); the results are walked in order, and the window is cut at the first trial made stale by an earlier acceptance
+ * (a new best member, or a replaced row among its two sampled ones), the stream put back to where it was before that trial was
+ * built.  Same draws, same comparisons, same result bits; about one launch per ten retained evaluations at window 32.
+ * window = 1 (or f_batch NULL): one call of f per trial.
  *   ppbo_de_minimize : any objective given as a callback (the CPU tests compare it with scipy through this entry)
- *   ppbo_mu_star_de  : objective -mu(x) = -k(x, X) alpha on the device, one ppbo_mu_pred_point launch per trial (X, alpha: DEVICE) */
+ *   ppbo_mu_star_de  : objective -mu(x) = -k(x, X) alpha on the device (X, alpha: DEVICE), ppbo_mu_pred_point(s) per trial / window */
 typedef double (*ppbo_objective_fn)(const double* x_h, int D, void* ctx);
-int ppbo_de_minimize(ppbo_objective_fn f, void* ctx, int D, const double* lower_h, const double* upper_h, int popsize, int maxiter,
-                     double tol, double atol, double mutation_lo, double mutation_hi, double recombination, unsigned int* mt_key,
-                     int* mt_pos, double* x_h, double* fun_h, int* stats_h);
+typedef int (*ppbo_objective_batch_fn)(const double* x_h, int B, int D, double* f_h, void* ctx);
+int ppbo_de_minimize(ppbo_objective_fn f, ppbo_objective_batch_fn f_batch, int window, void* ctx, int D, const double* lower_h,
+                     const double* upper_h, int popsize, int maxiter, double tol, double atol, double mutation_lo,
+                     double mutation_hi, double recombination, unsigned int* mt_key, int* mt_pos, double* x_h, double* fun_h,
+                     int* stats_h);
 int ppbo_mu_star_de(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f, const double* alpha,
                     const double* lower_h, const double* upper_h, int popsize, int maxiter, double tol, double atol,
-                    double mutation_lo, double mutation_hi, double recombination, unsigned int* mt_key, int* mt_pos, double* x_h,
-                    double* fun_h, int* stats_h, void* stream);
+                    double mutation_lo, double mutation_hi, double recombination, int window, unsigned int* mt_key, int* mt_pos,
+                    double* x_h, double* fun_h, int* stats_h, void* stream);
+/* B <= 64 points per launch, arguments and results in HOST memory (x_h[B][D], mu_h[B]); point b is evaluated by one CTA with the
+ * arithmetic of ppbo_mu_pred_point (same bits).  GPModel.mu_pred (src/gp_model.py:454-458) for the windows above. */
+int ppbo_mu_pred_points(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f, const double* alpha,
+                        const double* x_h, int B, double* mu_h, void* stream);
 /* fmax[b][s] = max_p ( mu[b][p] + sum_k Z[b][s][k] Fac[b][p][k] ), arg[b][s] = first arg-max.
  * Replaces the S calls of np.random.multivariate_normal + np.max in acquisition.EI / varmax
  * (src/acquisition.py:78-80, 175-177); Fac is the (P x P) sampling factor (row p = coefficients of point p). */

@@ -7,6 +7,7 @@
 
 #define PPBO_MAX_D 64          // max problem dimension carried by value in kernel params
 #define PPBO_SM_COUNT 148      // B200
+#define PPBO_MAX_POINTS 64     // points per ppbo_mu_pred_points launch (speculative window of the differential evolution)
 
 #define PPBO_OK 0
 #define PPBO_ERR_ARG (-1)

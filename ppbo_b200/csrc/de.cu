@@ -8,6 +8,7 @@
 // are consumed in the same order and every floating-point operation is the one numpy performs, so the trial vectors, the accepted
 // members, the stopping generation and the state the stream is left in are bit for bit those of the scipy call
 // (tests/test_de_replay.py compares them on the CPU for arbitrary objectives through a callback; tests/test_src_gpu.py on the GPU).
+// The evaluations can be issued in speculative windows (Solver::generation_windows) without changing any of that.
 //
 // What is restated (scipy/optimize/_differentialevolution.py of scipy 1.18.1, defaults of the reference's call):
 //   strategy 'best1bin', init 'latinhypercube', popsize 15 (population 15 D), mutation (0.5, 1) = dither per generation,
@@ -109,6 +110,7 @@ static double add_reduce(const double* a, long n) { return n == 0 ? 0.0 : a[0] +
 
 struct Solver {
     ppbo_objective_fn f;
+    ppbo_objective_batch_fn fb = nullptr;                  // evaluates B parameter vectors in one call (speculative windows)
     void* ctx;
     int D, n;
     std::vector<double> lo, hi, arg1, arg2, pop, energy, trial, bprime, params, tmp;
@@ -123,6 +125,7 @@ struct Solver {
     double evaluate(const double* t) {                     // _scale_parameters + func
         for (int d = 0; d < D; ++d) params[d] = arg1[d] + (t[d] - 0.5) * arg2[d];
         ++nfev;
+        ++calls;
         const double e = f(params.data(), D, ctx);
         if (e != e && !failed) failed = (int)nfev;         // remember the first NaN (a failed device call reports itself this way)
         return e;
@@ -171,14 +174,17 @@ struct Solver {
         const double sd = std::sqrt(add_reduce(tmp.data(), n) / (double)n);
         return sd <= atol + tol * std::fabs(mean);
     }
-    void generation() {                                    // __next__, updating='immediate'
-        for (int c = 0; c < n; ++c) {
-            // _mutate
+    // trial vector of candidate c from the current population and the next draws of the stream: _mutate + _ensure_constraint
+    int last_r0 = 0, last_r1 = 0;                          // the two sampled members the last make_trial read
+    void make_trial(int c, double* trial) {
+        {
             const int fill_point = (int)rng.interval((uint32_t)(D - 1));          // rng.randint(D)
             rng.shuffle(index.data(), n);                                          // _select_samples(c, 5)
             int r[2], k = 0;
             for (int i = 0; i < 6 && i < n && k < 2; ++i)
                 if (index[i] != c) r[k++] = index[i];
+            last_r0 = r[0];
+            last_r1 = r[1];
             const double *p0 = row(0), *pa = row(r[0]), *pb = row(r[1]), *pc = row(c);
             for (int d = 0; d < D; ++d) {
                 const double diff = pa[d] - pb[d];
@@ -192,20 +198,97 @@ struct Solver {
             // _ensure_constraint
             for (int d = 0; d < D; ++d)
                 if (trial[d] > 1.0 || trial[d] < 0.0) trial[d] = rng.uniform(0.0, 1.0);
-            const double e = evaluate(trial.data());
-            if (e <= energy[c]) {
-                for (int d = 0; d < D; ++d) row(c)[d] = trial[d];
-                energy[c] = e;
-                if (e <= energy[0]) promote_lowest();
+        }
+    }
+    // the compare-and-replace step of __next__: 0 rejected, 1 member c replaced, 2 replaced and the best-member branch taken
+    int accept(int c, const double* t, double e) {
+        if (!(e <= energy[c])) return 0;
+        for (int d = 0; d < D; ++d) row(c)[d] = t[d];
+        energy[c] = e;
+        if (!(e <= energy[0])) return 1;
+        promote_lowest();
+        return 2;
+    }
+    void generation() {                                    // __next__, updating='immediate': one evaluation per call of f
+        for (int c = 0; c < n; ++c) {
+            make_trial(c, trial.data());
+            accept(c, trial.data(), evaluate(trial.data()));
+        }
+    }
+    // The same generation with the evaluations in windows.  A trial reads four members of the population: the best (row 0), two
+    // sampled ones and its own; the draws it consumes do not depend on anything else.  So: build the next W trials from the
+    // population as it is, evaluate them in ONE call and walk the results in order, exactly like the sequential loop.  A rejected
+    // trial changes nothing.  An accepted trial replaces its own member only, unless it is also at least as good as the best: then
+    // row 0 changes and every later trial of the window is stale.  Otherwise a later trial is stale only if one of its two sampled
+    // members is a row replaced earlier in this window.  At the first stale trial the rest of the window is thrown away and the
+    // stream and the shuffled index array are put back to where they were before that trial was built.  Every retained trial, draw
+    // and comparison is the sequential loop's; only evaluations whose results are never looked at are added.
+    std::vector<uint32_t> snap_key;
+    std::vector<int> snap_pos, snap_index, win_r0, win_r1, replaced;
+    std::vector<double> win_trial, win_params, win_energy;
+    long wasted = 0, calls = 0;                            // discarded evaluations; calls of f / fb
+    void generation_windows(int W) {
+        if ((int)snap_pos.size() < W) {
+            snap_key.resize((size_t)W * 624);
+            snap_pos.resize(W);
+            snap_index.resize((size_t)W * n);
+            win_trial.resize((size_t)W * D);
+            win_params.resize((size_t)W * D);
+            win_energy.resize(W);
+            win_r0.resize(W);
+            win_r1.resize(W);
+            replaced.reserve(W);
+        }
+        int c = 0;
+        while (c < n) {
+            const int B = n - c < W ? n - c : W;
+            for (int k = 0; k < B; ++k) {
+                memcpy(&snap_key[(size_t)k * 624], rng.key, sizeof(uint32_t) * 624);      // state BEFORE trial k is built
+                snap_pos[k] = rng.pos;
+                memcpy(&snap_index[(size_t)k * n], index.data(), sizeof(int) * n);
+                double* t = &win_trial[(size_t)k * D];
+                make_trial(c + k, t);
+                win_r0[k] = last_r0;
+                win_r1[k] = last_r1;
+                for (int d = 0; d < D; ++d) win_params[(size_t)k * D + d] = arg1[d] + (t[d] - 0.5) * arg2[d];
             }
+            ++calls;
+            if (fb(win_params.data(), B, D, win_energy.data(), ctx) != 0) {
+                if (!failed) failed = (int)nfev + 1;
+                return;
+            }
+            int k = 0;
+            replaced.clear();
+            while (k < B) {
+                bool stale = false;
+                for (int r : replaced) stale = stale || r == win_r0[k] || r == win_r1[k];
+                if (stale) break;
+                const double e = win_energy[k];
+                ++nfev;
+                if (e != e && !failed) failed = (int)nfev;
+                const int a = accept(c + k, &win_trial[(size_t)k * D], e);
+                if (a == 1) replaced.push_back(c + k);
+                ++k;
+                if (a == 2) break;
+            }
+            if (k < B) {                                   // trials k .. B-1 were built from a population that no longer exists
+                memcpy(rng.key, &snap_key[(size_t)k * 624], sizeof(uint32_t) * 624);
+                rng.pos = snap_pos[k];
+                memcpy(index.data(), &snap_index[(size_t)k * n], sizeof(int) * n);
+                wasted += B - k;
+            }
+            c += k;
+            if (failed) return;
         }
     }
 };
 
-static int run(ppbo_objective_fn f, void* ctx, int D, const double* lower, const double* upper, int popsize, int maxiter, double tol,
-               double atol, double mutation_lo, double mutation_hi, double recombination, unsigned int* mt_key, int* mt_pos, double* x_out,
-               double* fun_out, int* stats, bool own_error_text = true) {
+static int run(ppbo_objective_fn f, ppbo_objective_batch_fn fb, int window, void* ctx, int D, const double* lower, const double* upper,
+               int popsize, int maxiter, double tol, double atol, double mutation_lo, double mutation_hi, double recombination,
+               unsigned int* mt_key, int* mt_pos, double* x_out, double* fun_out, int* stats, bool own_error_text = true) {
     PPBO_REQUIRE(f != nullptr && D >= 1 && D <= PPBO_MAX_D && popsize >= 1 && maxiter >= 0, "problem");
+    PPBO_REQUIRE(window >= 1 && window <= PPBO_MAX_POINTS, "window");
+    if (fb == nullptr) window = 1;
     PPBO_REQUIRE(lower != nullptr && upper != nullptr && mt_key != nullptr && mt_pos != nullptr && x_out != nullptr && fun_out != nullptr,
                  "null pointer");
     PPBO_REQUIRE(*mt_pos >= 0 && *mt_pos <= 624, "position in the MT19937 state");
@@ -213,6 +296,7 @@ static int run(ppbo_objective_fn f, void* ctx, int D, const double* lower, const
     PPBO_REQUIRE(recombination >= 0.0 && recombination <= 1.0, "recombination");
     Solver s;
     s.f = f;
+    s.fb = fb;
     s.ctx = ctx;
     s.D = D;
     int varying = 0;
@@ -245,12 +329,28 @@ static int run(ppbo_objective_fn f, void* ctx, int D, const double* lower, const
     s.own_error_text = own_error_text;
 
     s.init_lhs();
-    for (int i = 0; i < n; ++i) s.energy[i] = s.evaluate(s.row(i));        // solve(): initial energies, in population order
+    if (window > 1) {                                                       // solve(): initial energies, in population order
+        std::vector<double> par((size_t)window * D);
+        for (int i0 = 0; i0 < n && !s.failed; i0 += window) {
+            const int B = n - i0 < window ? n - i0 : window;
+            for (int k = 0; k < B; ++k)
+                for (int d = 0; d < D; ++d) par[(size_t)k * D + d] = s.arg1[d] + (s.row(i0 + k)[d] - 0.5) * s.arg2[d];
+            ++s.calls;
+            if (fb(par.data(), B, D, &s.energy[i0], ctx) != 0) s.failed = (int)s.nfev + 1;
+            for (int k = 0; k < B && !s.failed; ++k) {
+                ++s.nfev;
+                if (s.energy[i0 + k] != s.energy[i0 + k]) s.failed = (int)s.nfev;
+            }
+        }
+    } else {
+        for (int i = 0; i < n; ++i) s.energy[i] = s.evaluate(s.row(i));
+    }
     s.promote_lowest();
     int nit = 0, conv = 0;
     for (nit = 1; nit <= maxiter; ++nit) {
         s.scale = s.rng.uniform(mutation_lo, mutation_hi - mutation_lo);    // dither
-        s.generation();
+        if (window > 1) s.generation_windows(window);
+        else s.generation();
         if (s.failed) break;
         if (s.converged(tol, atol)) {
             conv = 1;
@@ -266,6 +366,8 @@ static int run(ppbo_objective_fn f, void* ctx, int D, const double* lower, const
         stats[1] = (int)s.nfev;
         stats[2] = conv;
         stats[3] = n;
+        stats[4] = (int)s.wasted;
+        stats[5] = (int)s.calls;
     }
     if (s.failed) {
         if (s.own_error_text) set_error("the objective returned NaN at evaluation %d", s.failed);
@@ -292,23 +394,35 @@ static double neg_mu(const double* x, int D, void* p) {
     return -mu;
 }
 
+static int neg_mu_batch(const double* x, int B, int D, double* out, void* p) {
+    MuCtx* c = static_cast<MuCtx*>(p);
+    const int rc = ppbo_mu_pred_points(c->kind, c->X, c->N, D, c->ls, c->sigma_f, c->alpha, x, B, out, c->stream);
+    if (rc) {
+        c->rc = rc;
+        return rc;
+    }
+    for (int k = 0; k < B; ++k) out[k] = -out[k];
+    return 0;
+}
+
 }  // namespace de
 }  // namespace ppbo
 
-extern "C" int ppbo_de_minimize(ppbo_objective_fn f, void* ctx, int D, const double* lower_h, const double* upper_h, int popsize,
-                                int maxiter, double tol, double atol, double mutation_lo, double mutation_hi, double recombination,
-                                unsigned int* mt_key, int* mt_pos, double* x_h, double* fun_h, int* stats_h) {
-    return ppbo::de::run(f, ctx, D, lower_h, upper_h, popsize, maxiter, tol, atol, mutation_lo, mutation_hi, recombination, mt_key,
-                         mt_pos, x_h, fun_h, stats_h);
+extern "C" int ppbo_de_minimize(ppbo_objective_fn f, ppbo_objective_batch_fn f_batch, int window, void* ctx, int D,
+                                const double* lower_h, const double* upper_h, int popsize, int maxiter, double tol, double atol,
+                                double mutation_lo, double mutation_hi, double recombination, unsigned int* mt_key, int* mt_pos,
+                                double* x_h, double* fun_h, int* stats_h) {
+    return ppbo::de::run(f, f_batch, window, ctx, D, lower_h, upper_h, popsize, maxiter, tol, atol, mutation_lo, mutation_hi,
+                         recombination, mt_key, mt_pos, x_h, fun_h, stats_h);
 }
 
 extern "C" int ppbo_mu_star_de(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f,
                                const double* alpha, const double* lower_h, const double* upper_h, int popsize, int maxiter, double tol,
-                               double atol, double mutation_lo, double mutation_hi, double recombination, unsigned int* mt_key,
-                               int* mt_pos, double* x_h, double* fun_h, int* stats_h, void* stream) {
+                               double atol, double mutation_lo, double mutation_hi, double recombination, int window,
+                               unsigned int* mt_key, int* mt_pos, double* x_h, double* fun_h, int* stats_h, void* stream) {
     ppbo::de::MuCtx c{kind, N, D, X, lengthscales_h, alpha, sigma_f, stream, 0};
-    const int rc = ppbo::de::run(ppbo::de::neg_mu, &c, D, lower_h, upper_h, popsize, maxiter, tol, atol, mutation_lo, mutation_hi,
-                                 recombination, mt_key, mt_pos, x_h, fun_h, stats_h, false);
+    const int rc = ppbo::de::run(ppbo::de::neg_mu, ppbo::de::neg_mu_batch, window, &c, D, lower_h, upper_h, popsize, maxiter, tol, atol,
+                                 mutation_lo, mutation_hi, recombination, mt_key, mt_pos, x_h, fun_h, stats_h, false);
     if (rc && !c.rc) ppbo::set_error("the posterior mean is NaN inside the differential evolution");
     return c.rc ? c.rc : rc;            // a failed device call keeps its own status and error text
 }

@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(1024) mu_pred_point_kernel(const double* __res
     __shared__ double xs[PPBO_MAX_D];
     __shared__ double red[33];
     const int D = p.D;
-    for (int d = threadIdx.x; d < D; d += 1024) xs[d] = x_in[d];
+    for (int d = threadIdx.x; d < D; d += 1024) xs[d] = x_in[(long long)blockIdx.x * D + d];     // one point per CTA
     __syncthreads();
     double s = 0.0;
     for (int i = threadIdx.x; i < N; i += 1024) {
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(1024) mu_pred_point_kernel(const double* __res
         s = fma(kernel_from_sums(KIND, a, p.sf2), alpha[i], s);
     }
     s = block_sum(s, red);
-    if (threadIdx.x == 0) out[0] = s;
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
 struct PinnedPoint {
@@ -637,6 +637,18 @@ struct PinnedPoint {
     }
 };
 static thread_local PinnedPoint g_point;
+// B points per launch (ppbo_mu_pred_points: the speculative windows of the differential evolution in de.cu)
+struct PinnedBatch {
+    double* host = nullptr;
+    double* dev = nullptr;
+    int init() {
+        if (host) return PPBO_OK;
+        PPBO_CUDA_CHECK(cudaHostAlloc(&host, sizeof(double) * (PPBO_MAX_D + 1) * PPBO_MAX_POINTS, cudaHostAllocMapped));
+        PPBO_CUDA_CHECK(cudaHostGetDevicePointer(&dev, host, 0));
+        return PPBO_OK;
+    }
+};
+static thread_local PinnedBatch g_batch;
 
 // ---- SE kernel gradients w.r.t. log length-scales and log sigma_f --------------------------------------
 __global__ void __launch_bounds__(256) se_grad_kernel(const double* __restrict__ X1, int n1, const double* __restrict__ X2,
@@ -836,6 +848,29 @@ extern "C" int ppbo_mu_pred_point(int kind, const double* X, int N, int D, const
     PPBO_LAUNCH_CHECK();
     PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
     *mu_h = g_point.host[PPBO_MAX_D];
+    return PPBO_OK;
+}
+
+extern "C" int ppbo_mu_pred_points(int kind, const double* X, int N, int D, const double* lengthscales_h, double sigma_f,
+                                    const double* alpha, const double* x_h, int B, double* mu_h, void* stream) {
+    KernelParams p;
+    int rc = fill_params(p, kind, D, lengthscales_h, sigma_f);
+    if (rc) return rc;
+    PPBO_REQUIRE(N >= 0 && B >= 0 && B <= PPBO_MAX_POINTS && (B == 0 || (x_h != nullptr && mu_h != nullptr)), "arguments");
+    if (B == 0) return PPBO_OK;
+    if ((rc = g_batch.init())) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    memcpy(g_batch.host, x_h, sizeof(double) * (size_t)B * D);
+    double* out_h = g_batch.host + (size_t)PPBO_MAX_D * PPBO_MAX_POINTS;
+    double* out = g_batch.dev + (size_t)PPBO_MAX_D * PPBO_MAX_POINTS;
+    switch (kind) {
+        case PPBO_KERNEL_SE: PPBO_CL mu_pred_point_kernel<PPBO_KERNEL_SE><<<B, 1024, 0, st>>>(X, N, p, alpha, g_batch.dev, out); break;
+        case PPBO_KERNEL_RQ: PPBO_CL mu_pred_point_kernel<PPBO_KERNEL_RQ><<<B, 1024, 0, st>>>(X, N, p, alpha, g_batch.dev, out); break;
+        default: PPBO_CL mu_pred_point_kernel<PPBO_KERNEL_CAMPHOR><<<B, 1024, 0, st>>>(X, N, p, alpha, g_batch.dev, out);
+    }
+    PPBO_LAUNCH_CHECK();
+    PPBO_CUDA_CHECK(cudaStreamSynchronize(st));
+    memcpy(mu_h, out_h, sizeof(double) * (size_t)B);
     return PPBO_OK;
 }
 

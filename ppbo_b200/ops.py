@@ -430,20 +430,25 @@ class PointMean:
 
 # --- GPModel.mu_star's sequential differential evolution with the loop in C++ (csrc/de.cu) -----------------------------------
 _OBJECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_void_p)
-DE_DEFAULTS = dict(popsize=15, maxiter=1000, tol=0.01, atol=0.0, mutation=(0.5, 1.0), recombination=0.7)     # scipy's
+_OBJECTIVE_BATCH_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_double), ctypes.c_void_p)
+DE_MAX_WINDOW = 64                                                                                             # PPBO_MAX_POINTS
 
 
 class DEResult:
     """x, fun: best member (problem units) and its value at the end of the evolution (before any polish); nit, nfev, converged,
-    population_size as scipy reports them"""
+    population_size as scipy reports them; discarded: evaluations of speculative windows whose results were never looked at;
+    calls: calls of the objective (one per window, i.e. launches on the device)"""
 
     def __init__(self, x, fun, stats):
         self.x, self.fun = x, fun
         self.nit, self.nfev, self.converged, self.population_size = int(stats[0]), int(stats[1]), bool(stats[2]), int(stats[3])
+        self.discarded, self.calls = int(stats[4]), int(stats[5])
 
 
-def _de_call(entry, head, bounds, tail, popsize, maxiter, tol, atol, mutation, recombination, what):
-    """shared part of the two entries: numpy's global MT19937 state in, the same stream advanced by exactly scipy's draws out"""
+def _de_call(entry, bounds, popsize, maxiter, tol, atol, mutation, recombination, what):
+    """shared part of the two entries: numpy's global MT19937 state in, the same stream advanced by exactly scipy's draws out.
+    entry(D, lo, hi, popsize, maxiter, tol, atol, mutation_lo, mutation_hi, recombination, key, pos, x, fun, stats) -> status"""
     bounds = np.asarray(bounds, dtype=np.float64)
     D = bounds.shape[0]
     lo, hi = _lib.host_doubles(bounds[:, 0]), _lib.host_doubles(bounds[:, 1])
@@ -454,33 +459,47 @@ def _de_call(entry, head, bounds, tail, popsize, maxiter, tol, atol, mutation, r
     pos_c = ctypes.c_int(int(pos))
     x = (ctypes.c_double * D)()
     fun = ctypes.c_double(0.0)
-    stats = (ctypes.c_int * 4)()
+    stats = (ctypes.c_int * 6)()
     mut = sorted(float(v) for v in np.atleast_1d(mutation))
     if len(mut) != 2:
         raise PPBOError("mutation must be a (min, max) pair (dither), as in the reference's default call")
-    rc = entry(*head, D, lo, hi, int(popsize), int(maxiter), float(tol), float(atol), mut[0], mut[1], float(recombination),
-               key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.byref(pos_c), x, ctypes.byref(fun), stats, *tail)
+    rc = entry(D, lo, hi, int(popsize), int(maxiter), float(tol), float(atol), mut[0], mut[1], float(recombination),
+               key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), ctypes.byref(pos_c), x, ctypes.byref(fun), stats)
     np.random.set_state((name, key, int(pos_c.value), has_gauss, cached))
     if rc:
         raise PPBOError("%s failed (%d): %s" % (what, rc, _lib.last_error()))
     return DEResult(np.array(x[:], dtype=np.float64), float(fun.value), stats)
 
 
-def de_minimize(func, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0, mutation=(0.5, 1.0), recombination=0.7):
+def de_minimize(func, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0, mutation=(0.5, 1.0), recombination=0.7, window=1):
     """scipy.optimize.differential_evolution(func, bounds, updating='immediate', polish=False) on numpy's GLOBAL legacy stream,
-    replayed draw for draw by ppbo_de_minimize: same result bits, same state of np.random afterwards.  func: x (D,) -> float."""
-    D = len(bounds)
+    replayed draw for draw by ppbo_de_minimize: same result bits, same state of np.random afterwards.  func: x (D,) -> float.
+    window > 1: evaluations issued in speculative windows of that many trials (same result; func is called on discarded trials too)."""
     failure = []
 
-    def cb(xp, d, _ctx):
+    def one(xp, d, _ctx):
         try:
             return float(func(np.ctypeslib.as_array(xp, shape=(d,)).copy()))
         except BaseException as e:                    # an exception must not unwind through the C frames
             failure.append(e)
             return float("nan")
+
+    def many(xp, b, d, fp, _ctx):
+        try:
+            X = np.ctypeslib.as_array(xp, shape=(b, d)).copy()
+            for k in range(b):
+                fp[k] = float(func(X[k]))
+            return 0
+        except BaseException as e:
+            failure.append(e)
+            return -1
+    f1, fb = _OBJECTIVE_FN(one), _OBJECTIVE_BATCH_FN(many)
+    lib = _lib.load()
+
+    def entry(D, *rest):
+        return lib.ppbo_de_minimize(f1, fb, int(window), None, D, *rest)
     try:
-        return _de_call(_lib.load().ppbo_de_minimize, (_OBJECTIVE_FN(cb), None), bounds, (), popsize, maxiter, tol, atol, mutation,
-                        recombination, "ppbo_de_minimize")
+        return _de_call(entry, bounds, popsize, maxiter, tol, atol, mutation, recombination, "ppbo_de_minimize")
     except PPBOError:
         if failure:
             raise failure[0]
@@ -503,18 +522,29 @@ def de_polish(func, de, bounds):
 
 
 def mu_star_de(kernel, X, lengthscales, sigma_f, alpha, bounds, popsize=15, maxiter=1000, tol=0.01, atol=0.0, mutation=(0.5, 1.0),
-               recombination=0.7):
-    """the same search with the objective -mu(x) = -k(x, X) alpha evaluated on the device, one ppbo_mu_pred_point launch per trial
-    (bit-identical to a scipy call over PointMean); returns a DEResult with fun = -mu(x)"""
-    N, D = X.shape
-    head = (_kind(kernel), _p(X), N)
-    # ppbo_mu_star_de(kind, X, N, D, ls, sigma_f, alpha, lower, upper, ...): D and the bounds come from _de_call, so wrap the entry
+               recombination=0.7, window=1):
+    """the same search with the objective -mu(x) = -k(x, X) alpha evaluated on the device: one ppbo_mu_pred_point launch per trial
+    (window = 1) or one ppbo_mu_pred_points launch per speculative window; bit-identical to a scipy call over PointMean either
+    way.  Returns a DEResult with fun = -mu(x)."""
+    N, Dx = X.shape
     lib = _lib.load()
-    ls = _ls(lengthscales, D)
+    kind, ls, st = _kind(kernel), _ls(lengthscales, Dx), _stream()
 
-    def entry(kind, Xp, n, d, lo, hi, *rest):
-        return lib.ppbo_mu_star_de(kind, Xp, n, d, ls, float(sigma_f), _p(alpha), lo, hi, *rest)
-    return _de_call(entry, head, bounds, (_stream(),), popsize, maxiter, tol, atol, mutation, recombination, "ppbo_mu_star_de")
+    def entry(D, lo, hi, popsize_, maxiter_, tol_, atol_, m0, m1, rec, key, pos, x, fun, stats):
+        return lib.ppbo_mu_star_de(kind, _p(X), N, D, ls, float(sigma_f), _p(alpha), lo, hi, popsize_, maxiter_, tol_, atol_, m0, m1,
+                                   rec, int(window), key, pos, x, fun, stats, st)
+    return _de_call(entry, bounds, popsize, maxiter, tol, atol, mutation, recombination, "ppbo_mu_star_de")
+
+
+def mu_pred_points(kernel, X, lengthscales, sigma_f, alpha, points):
+    """posterior means of up to 64 host points in one launch, host result (ppbo_mu_pred_points)"""
+    pts = np.ascontiguousarray(np.atleast_2d(np.asarray(points, dtype=np.float64)))
+    B, D = pts.shape
+    out = np.empty(B, dtype=np.float64)
+    check(_lib.load().ppbo_mu_pred_points(_kind(kernel), _p(X), X.shape[0], D, _ls(lengthscales, D), float(sigma_f), _p(alpha),
+                                          pts.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), B,
+                                          out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _stream()), "ppbo_mu_pred_points")
+    return out
 
 
 def mvn_rowmax(Z, Fac, mu):

@@ -1,5 +1,6 @@
 """GPModel.mu_star on the full-size goldens (BASELINE configs 1-3): the scipy call ('de-scipy') against its C++ replay ('de', the
-default): time, evaluations, time per evaluation, and that both return the same bits.  Run on the GPU box:
+default) with one trial per launch and with speculative windows of 32: time, evaluations, time per evaluation, launches, and that all
+return the same bits.  Run on the GPU box:
   python scripts/mustar_probe.py"""
 import os
 import sys
@@ -17,15 +18,17 @@ for name in golden_full_names():
     st, gp = _model(g)
     gp.mu_pred(g["xstar"])                                         # first launch outside the timed region
     res = {}
-    for method in ("de-scipy", "de", "de-scipy", "de"):
-        gp.mustar_method = method
-        gp.mu_pred_calls = 0
+    for tag, method, window in (("scipy", "de-scipy", 1), ("w1", "de", 1), ("w32", "de", 32), ("w32", "de", 32)):
+        gp.mustar_method, gp.mustar_window = method, window
+        gp.mu_pred_calls = gp.mu_star_launches = 0
         np.random.seed(3)
         t0 = time.perf_counter()
         xs, mu, loc = gp.mu_star()
         dt = time.perf_counter() - t0
-        res[method] = (xs, mu, dt, gp.mu_pred_calls)
-    a, b = res["de-scipy"], res["de"]
-    print("%-16s N=%5d D=%2d  scipy %8.1f ms  replay %8.1f ms  (%6d evaluations: %5.1f -> %5.1f us each)  identical: %s" % (
-        name, gp.N, gp.D, 1e3 * a[2], 1e3 * b[2], b[3], 1e6 * a[2] / a[3], 1e6 * b[2] / b[3],
-        bool(np.array_equal(a[0], b[0]) and a[1] == b[1] and a[3] == b[3])))
+        res[tag] = (xs, mu, dt, gp.mu_pred_calls, gp.mu_star_launches)
+    a, b, c = res["scipy"], res["w1"], res["w32"]
+    same = all(bool(np.array_equal(a[0], r[0]) and a[1] == r[1] and a[3] == r[3]) for r in (b, c))
+    print("%-16s N=%5d D=%2d  scipy %7.1f ms | replay, 1 trial per launch %7.1f ms | windows of 32: %6.1f ms, %5d launches  "
+          "(%6d evaluations: %4.1f -> %4.1f -> %4.1f us each)  identical: %s" % (
+              name, gp.N, gp.D, 1e3 * a[2], 1e3 * b[2], 1e3 * c[2], c[4], c[3], 1e6 * a[2] / a[3], 1e6 * b[2] / b[3],
+              1e6 * c[2] / c[3], same), flush=True)

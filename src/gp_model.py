@@ -92,6 +92,7 @@ class GPModel:
         # B200-path knobs (additive, see PPBO_settings)
         self.mvn_factor = getattr(PPBO_settings, "mvn_factor", "svd-host")
         self.mustar_method = getattr(PPBO_settings, "mustar_method", "de")
+        self.mustar_window = getattr(PPBO_settings, "mustar_window", 32)
         self.newton_max_iter, self.newton_tol = 100, 1e-10
         # device state
         self._X_dev = None           # [N x D]
@@ -455,11 +456,14 @@ class GPModel:
         """scipy.optimize.differential_evolution(self.mu_pred_neq, self.bounds, updating='immediate', maxiter=2000) with the
         evolution replayed by ppbo_mu_star_de (csrc/de.cu): numpy's global stream is consumed draw for draw as scipy would, every
         trial is one device evaluation of the posterior mean, and the result equals the scipy call's bit for bit (tests/
-        test_de_replay.py on the CPU, test_src_gpu.py::test_mu_star_native_equals_scipy on the GPU).  The L-BFGS-B polish that
-        ends scipy's call is made by ops.de_polish exactly as scipy makes it."""
+        test_de_replay.py on the CPU, test_src_gpu.py::test_mu_star_native_equals_scipy on the GPU).  The evaluations are
+        issued in speculative windows of `mustar_window` trials, one launch each (1: one launch per trial); the bits do not
+        depend on it.  The L-BFGS-B polish that ends scipy's call is made by ops.de_polish exactly as scipy makes it."""
         theta = self.theta
-        de = ops.mu_star_de(self._kernel_name(), self._Xd(), theta[1], theta[2], self._fit.alpha, self.bounds, maxiter=2000)
+        de = ops.mu_star_de(self._kernel_name(), self._Xd(), theta[1], theta[2], self._fit.alpha, self.bounds, maxiter=2000,
+                            window=self.mustar_window)
         self.mu_pred_calls = getattr(self, "mu_pred_calls", 0) + de.nfev
+        self.mu_star_launches = getattr(self, "mu_star_launches", 0) + de.calls
         return ops.de_polish(self.mu_pred_neq, de, self.bounds)
 
     # ------------------------------------------------------------------ predictions (src/gp_model.py:441-461)

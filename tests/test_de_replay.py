@@ -39,6 +39,27 @@ def _same_state(a, b):
     return a[0] == b[0] and np.array_equal(a[1], b[1]) and a[2:] == b[2:]
 
 
+@pytest.mark.parametrize("window", [2, 16, 32, 64])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_speculative_windows_replay_scipy(case, window):
+    """evaluations issued `window` trials at a time (one device launch per window on the GPU): the retained trials, draws and
+    comparisons are the sequential loop's, so every bit and the generator state still equal scipy's; fewer calls, some discarded"""
+    f, bounds, seed = CASES[case]
+    np.random.seed(seed)
+    np.random.standard_normal(3)
+    ref = scipy.optimize.differential_evolution(f, bounds, updating='immediate', disp=False, maxiter=2000, polish=False)
+    state_ref = np.random.get_state()
+    np.random.seed(seed)
+    np.random.standard_normal(3)
+    got = ops.de_minimize(f, bounds, maxiter=2000, window=window)
+    assert np.array_equal(got.x, ref.x) and got.fun == ref.fun
+    assert (got.nit, got.nfev, got.converged) == (ref.nit, ref.nfev, bool(ref.success))
+    assert _same_state(np.random.get_state(), state_ref)
+    assert got.calls < got.nfev and got.calls * window >= got.nfev + got.discarded - window * (got.nit + 2)
+    if f is not flat and window >= 16:
+        assert got.calls * 3 < got.nfev                    # at least three retained evaluations per call
+
+
 @pytest.mark.parametrize("maxiter", [2000, 3, 0])
 @pytest.mark.parametrize("case", range(len(CASES)))
 def test_evolution_replays_scipy(case, maxiter):
@@ -54,6 +75,7 @@ def test_evolution_replays_scipy(case, maxiter):
     assert (got.nit, got.nfev) == (ref.nit, ref.nfev)
     assert got.converged == bool(ref.success)
     assert got.population_size == len(ref.population)
+    assert got.calls == got.nfev and got.discarded == 0
     assert _same_state(np.random.get_state(), state_ref)
 
 
@@ -101,3 +123,10 @@ def test_objective_failures_surface():
         ops.de_minimize(nan_later, [(0, 1)] * 2, maxiter=50)
     with pytest.raises(PPBOError):
         ops.de_minimize(sphere, [(0, np.inf)], maxiter=5)
+    with pytest.raises(Boom):
+        ops.de_minimize(raises, [(0, 1)] * 2, maxiter=5, window=8)
+    with pytest.raises(PPBOError, match="window"):
+        ops.de_minimize(sphere, [(0, 1)] * 2, maxiter=5, window=65)
+    calls.clear()
+    with pytest.raises(PPBOError, match="NaN"):
+        ops.de_minimize(nan_later, [(0, 1)] * 2, maxiter=50, window=8)

@@ -198,24 +198,35 @@ def test_mu_star_replays_reference_search(golden):
 
 
 def test_mu_star_native_equals_scipy(golden):
-    """the default search ('de': scipy's differential evolution replayed by ppbo_mu_star_de, loop in C++, one device evaluation per
-    trial) against the scipy call itself ('de-scipy') on the same stream: same maximiser, same value, same local maximisers, same
-    number of posterior-mean evaluations, and numpy's global generator left in the same state -- bit for bit"""
+    """the default search ('de': scipy's differential evolution replayed by ppbo_mu_star_de, loop in C++, device evaluations one
+    per launch or in speculative windows of 32) against the scipy call itself ('de-scipy') on the same stream: same maximiser,
+    same value, same local maximisers, same number of posterior-mean evaluations, and numpy's global generator left in the same
+    state -- bit for bit"""
+    from ppbo_b200 import ops
     g = golden
     st, gp = _model(g)
+    assert gp.mustar_method == "de" and gp.mustar_window == 32            # the defaults
     out = {}
-    for method in ("de-scipy", "de"):
-        gp.mustar_method = method
-        gp.mu_pred_calls = 0
+    for tag, method, window in (("scipy", "de-scipy", 1), ("w1", "de", 1), ("w32", "de", 32), ("w5", "de", 5)):
+        gp.mustar_method, gp.mustar_window = method, window
+        gp.mu_pred_calls = gp.mu_star_launches = 0
         np.random.seed(int(g["seed_fit"]) + 1)
         np.random.standard_normal(5)
         xstar, mustar, local = gp.mu_star(mustar_finding_trials=2)
-        out[method] = (xstar, mustar, local, gp.mu_pred_calls, np.random.get_state())
-    a, b = out["de-scipy"], out["de"]
-    assert np.array_equal(a[0], b[0]) and a[1] == b[1]
-    assert a[2].shape == b[2].shape and np.array_equal(a[2], b[2])
-    assert a[3] == b[3] and a[3] > 0
-    assert a[4][0] == b[4][0] and np.array_equal(a[4][1], b[4][1]) and a[4][2:] == b[4][2:]
+        out[tag] = (xstar, mustar, local, gp.mu_pred_calls, np.random.get_state(), gp.mu_star_launches)
+    a = out["scipy"]
+    for tag in ("w1", "w32", "w5"):
+        b = out[tag]
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1], tag
+        assert a[2].shape == b[2].shape and np.array_equal(a[2], b[2]), tag
+        assert a[3] == b[3] and a[3] > 0, tag
+        assert a[4][0] == b[4][0] and np.array_equal(a[4][1], b[4][1]) and a[4][2:] == b[4][2:], tag
+    assert out["w32"][5] * 3 < out["w1"][5]                               # windows: at least three times fewer launches
+    # the batched point evaluation itself: same bits as the one-point launch
+    pts = np.vstack([g["pred_grid"][:7], g["xstar"][None]])
+    theta = gp.theta
+    many = ops.mu_pred_points(gp._kernel_name(), gp._Xd(), theta[1], theta[2], gp._fit.alpha, pts)
+    assert np.array_equal(many, np.array([gp.mu_pred(x) for x in pts]))
 
 
 def test_mu_star_batched(golden):
