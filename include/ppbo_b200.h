@@ -215,7 +215,7 @@ int ppbo_mu_pred_point(int kind, const double* X, int N, int D, const double* le
  * trials are built from the population as it is and evaluated in one call (f_batch: B rows of x_h -> f_h[B], return 0; one launch
  * on the device); the results are walked in order, and the window is cut at the first trial made stale by an earlier acceptance
  * (a new best member, or a replaced row among its two sampled ones), the stream put back to where it was before that trial was
- * built.  Same draws, same comparisons, same result bits; about one launch per ten retained evaluations at window 32.
+ * built.  Same draws, same comparisons, same result bits; about one launch per ten retained evaluations at window 16 .. 32.
  * window = 1 (or f_batch NULL): one call of f per trial.
  *   ppbo_de_minimize : any objective given as a callback (the CPU tests compare it with scipy through this entry)
  *   ppbo_mu_star_de  : objective -mu(x) = -k(x, X) alpha on the device (X, alpha: DEVICE), ppbo_mu_pred_point(s) per trial / window */

@@ -92,7 +92,7 @@ class GPModel:
         # B200-path knobs (additive, see PPBO_settings)
         self.mvn_factor = getattr(PPBO_settings, "mvn_factor", "svd-host")
         self.mustar_method = getattr(PPBO_settings, "mustar_method", "de")
-        self.mustar_window = getattr(PPBO_settings, "mustar_window", 32)
+        self.mustar_window = getattr(PPBO_settings, "mustar_window", 16)
         self.newton_max_iter, self.newton_tol = 100, 1e-10
         # device state
         self._X_dev = None           # [N x D]

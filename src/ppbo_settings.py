@@ -25,7 +25,7 @@ class PPBO_settings:
     def __init__(self, D, bounds, xi_acquisition_function, theta_initial=[1, 0.1, 8], user_feedback_grid_size=100, m=25,
                  verbose=True, EI_EXR_mc_samples=150, EI_EXR_BO_maxiter=20, mustar_finding_trials=3, kernel='SE_kernel',
                  skip_computations_during_initialization=True, skip_xstaroptimization_during_initialization=False,
-                 alpha_grid_distribution='equispaced', *, mvn_factor='svd-host', mustar_method='de', mustar_window=32):
+                 alpha_grid_distribution='equispaced', *, mvn_factor='svd-host', mustar_method='de', mustar_window=16):
         # basic settings (:26-29)
         self.verbose = verbose
         self.user_feedback_grid_size = user_feedback_grid_size
@@ -66,5 +66,6 @@ class PPBO_settings:
         #       as the scipy call, a third of the time); 'de-scipy': the scipy call itself; 'batched': one device evaluation per
         #       generation (scipy 'deferred' updating: another trajectory)
         self.mustar_method = mustar_method
-        # trials evaluated per launch by the 'de' search (speculative windows, csrc/de.cu); the result does not depend on it
+        # trials evaluated per launch by the 'de' search (speculative windows, csrc/de.cu); the result does not depend on it.
+        # 16: least host + launch time per retained evaluation (8-12 of 16 trials are retained; at 32 it is 10-14 of 32)
         self.mustar_window = mustar_window

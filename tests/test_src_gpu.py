@@ -205,7 +205,7 @@ def test_mu_star_native_equals_scipy(golden):
     from ppbo_b200 import ops
     g = golden
     st, gp = _model(g)
-    assert gp.mustar_method == "de" and gp.mustar_window == 32            # the defaults
+    assert gp.mustar_method == "de" and gp.mustar_window == 16            # the defaults
     out = {}
     for tag, method, window in (("scipy", "de-scipy", 1), ("w1", "de", 1), ("w32", "de", 32), ("w5", "de", 5)):
         gp.mustar_method, gp.mustar_window = method, window
