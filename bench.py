@@ -424,7 +424,7 @@ def api_leg(torch):
                 if mode != "append":
                     gp.turn_initialization_off()
                 t1 = time.perf_counter()
-                calls0 = getattr(gp, "mu_pred_calls", 0)
+                calls0, launches0 = getattr(gp, "mu_pred_calls", 0), getattr(gp, "mu_star_launches", 0)
                 gp.update_model()
                 t2 = time.perf_counter()
                 xi, x = acquisition.next_query(st, gp, unscale=True)
@@ -433,7 +433,9 @@ def api_leg(torch):
                     continue
                 res[mode] = {"total_ms": 1e3 * (t3 - t0), "feedback_ms": 1e3 * (t1 - t0), "update_model_ms": 1e3 * (t2 - t1),
                              "fit_ms": 1e3 * gp.timing.get("fit", float("nan")), "mu_star_ms": 1e3 * gp.timing.get("mu_star", float("nan")),
-                             "mu_pred_evaluations": getattr(gp, "mu_pred_calls", 0) - calls0, "next_query_ms": 1e3 * (t3 - t2),
+                             "mu_pred_evaluations": getattr(gp, "mu_pred_calls", 0) - calls0,
+                             "mu_star_search": "%s, windows of %s" % (getattr(gp, "mustar_method", "?"), getattr(gp, "mustar_window", "?")),
+                             "mu_star_launches": getattr(gp, "mu_star_launches", 0) - launches0, "next_query_ms": 1e3 * (t3 - t2),
                              "next_query_parts_ms": {k: round(1e3 * v_, 2) for k, v_ in gp.timing.items() if k.startswith("acq_")},
                              "fit_iterations": gp.fit_stats["iterations"], "selected_direction": int(np.argmax(xi != 0))}
         except Exception as e:       # the leg is a report, never a reason to lose the bench line
