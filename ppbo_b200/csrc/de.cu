@@ -113,7 +113,7 @@ struct Solver {
     ppbo_objective_batch_fn fb = nullptr;                  // evaluates B parameter vectors in one call (speculative windows)
     void* ctx;
     int D, n;
-    std::vector<double> lo, hi, arg1, arg2, pop, energy, trial, bprime, params, tmp;
+    std::vector<double> arg1, arg2, pop, energy, trial, bprime, params, tmp;
     std::vector<int> index;
     MT19937 rng;
     double scale = 0.0, recombination = 0.7;
@@ -176,29 +176,26 @@ struct Solver {
     }
     // trial vector of candidate c from the current population and the next draws of the stream: _mutate + _ensure_constraint
     int last_r0 = 0, last_r1 = 0;                          // the two sampled members the last make_trial read
-    void make_trial(int c, double* trial) {
-        {
-            const int fill_point = (int)rng.interval((uint32_t)(D - 1));          // rng.randint(D)
-            rng.shuffle(index.data(), n);                                          // _select_samples(c, 5)
-            int r[2], k = 0;
-            for (int i = 0; i < 6 && i < n && k < 2; ++i)
-                if (index[i] != c) r[k++] = index[i];
-            last_r0 = r[0];
-            last_r1 = r[1];
-            const double *p0 = row(0), *pa = row(r[0]), *pb = row(r[1]), *pc = row(c);
-            for (int d = 0; d < D; ++d) {
-                const double diff = pa[d] - pb[d];
-                const double sdiff = scale * diff;
-                bprime[d] = p0[d] + sdiff;                                         // _best1
-            }
-            for (int d = 0; d < D; ++d) {
-                const bool cross = rng.uniform(0.0, 1.0) < recombination;
-                trial[d] = (cross || d == fill_point) ? bprime[d] : pc[d];
-            }
-            // _ensure_constraint
-            for (int d = 0; d < D; ++d)
-                if (trial[d] > 1.0 || trial[d] < 0.0) trial[d] = rng.uniform(0.0, 1.0);
+    void make_trial(int c, double* out) {
+        const int fill_point = (int)rng.interval((uint32_t)(D - 1));              // rng.randint(D)
+        rng.shuffle(index.data(), n);                                              // _select_samples(c, 5)
+        int r[2], k = 0;
+        for (int i = 0; i < 6 && i < n && k < 2; ++i)
+            if (index[i] != c) r[k++] = index[i];
+        last_r0 = r[0];
+        last_r1 = r[1];
+        const double *p0 = row(0), *pa = row(r[0]), *pb = row(r[1]), *pc = row(c);
+        for (int d = 0; d < D; ++d) {
+            const double diff = pa[d] - pb[d];
+            const double sdiff = scale * diff;
+            bprime[d] = p0[d] + sdiff;                                             // _best1
         }
+        for (int d = 0; d < D; ++d) {
+            const bool cross = rng.uniform(0.0, 1.0) < recombination;
+            out[d] = (cross || d == fill_point) ? bprime[d] : pc[d];
+        }
+        for (int d = 0; d < D; ++d)                                                // _ensure_constraint
+            if (out[d] > 1.0 || out[d] < 0.0) out[d] = rng.uniform(0.0, 1.0);
     }
     // the compare-and-replace step of __next__: 0 rejected, 1 member c replaced, 2 replaced and the best-member branch taken
     int accept(int c, const double* t, double e) {
@@ -307,8 +304,6 @@ static int run(ppbo_objective_fn f, ppbo_objective_batch_fn fb, int window, void
     s.n = popsize * (varying > 1 ? varying : 1);
     if (s.n < 5) s.n = 5;
     const int n = s.n;
-    s.lo.assign(lower, lower + D);
-    s.hi.assign(upper, upper + D);
     s.arg1.resize(D);
     s.arg2.resize(D);
     for (int d = 0; d < D; ++d) {
