@@ -432,6 +432,8 @@ class GPModel:
         if mustar_finding_trials is None:
             mustar_finding_trials = self.mustar_finding_trials
         method = self.mustar_method
+        if method not in ("de", "de-scipy", "batched"):
+            raise ValueError("mustar_method must be 'de', 'de-scipy' or 'batched', not %r" % (method,))
         xstar = xstars_local = None
         best = np.inf
         for i in range(mustar_finding_trials):
